@@ -1,0 +1,901 @@
+/*
+ * comap_oracle.c -- CPU restatement of CoMap's hot path.  TEST INFRASTRUCTURE ONLY.
+ * See comap_oracle.h for the rules on who may use this file and for pinning status.
+ *
+ * Reference citations are relative to /root/reference (jydu/comap 1.6.0a).  "[Bio++]"
+ * marks arithmetic that lives in the un-vendored bpp-phyl/bpp-core >= 3.0.0 and is
+ * restated from its published algorithm; the CoMap call site is cited instead.
+ *
+ * Single thread, fp64, straight loops (build: gcc -O2 -ffp-contract=off).
+ */
+#include "comap_oracle.h"
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+static char g_err[512] = "";
+const char* orc_last_error(void) { return g_err; }
+#define FAIL(...) do { snprintf(g_err, sizeof g_err, __VA_ARGS__); return -1; } while (0)
+
+/* ------------------------------------------------------------------------------------ */
+/* small dense helpers                                                                   */
+/* ------------------------------------------------------------------------------------ */
+
+static void mat_mul(int n, const double* a, const double* b, double* c) {
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      double s = 0.;
+      for (int k = 0; k < n; k++) s += a[i * n + k] * b[k * n + j];
+      c[i * n + j] = s;
+    }
+}
+
+/* Cyclic Jacobi for a symmetric n*n matrix: a = v diag(w) v^T. */
+static void jacobi_eigh(int n, double* a, double* w, double* v) {
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) v[i * n + j] = (i == j);
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0.;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) off += a[p * n + q] * a[p * n + q];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) {
+        double apq = a[p * n + q];
+        if (fabs(apq) < 1e-300) continue;
+        double theta = (a[q * n + q] - a[p * n + p]) / (2. * apq);
+        double t = (theta >= 0 ? 1. : -1.) / (fabs(theta) + sqrt(theta * theta + 1.));
+        double c = 1. / sqrt(t * t + 1.), s = t * c;
+        for (int k = 0; k < n; k++) {
+          double akp = a[k * n + p], akq = a[k * n + q];
+          a[k * n + p] = c * akp - s * akq;
+          a[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          double apk = a[p * n + k], aqk = a[q * n + k];
+          a[p * n + k] = c * apk - s * aqk;
+          a[q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          double vkp = v[k * n + p], vkq = v[k * n + q];
+          v[k * n + p] = c * vkp - s * vkq;
+          v[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  for (int i = 0; i < n; i++) w[i] = a[i * n + i];
+}
+
+/* Spectral form of a reversible generator: Q = R diag(ev) L with L = R^{-1}.
+ * [Bio++] AbstractReversibleSubstitutionModel::updateMatrices computes the same
+ * right/left eigenvectors with a general eigen-solver; for reversible Q the
+ * symmetrised form sqrt(pi_i) Q_ij / sqrt(pi_j) gives them with an orthogonal basis. */
+typedef struct {
+  int A;
+  double *ev, *R, *L; /* R[x][k], L[k][y] */
+} spectral_t;
+
+static int spectral_init(spectral_t* sp, int A, const double* Q, const double* pi) {
+  sp->A = A;
+  sp->ev = malloc(sizeof(double) * A);
+  sp->R = malloc(sizeof(double) * A * A);
+  sp->L = malloc(sizeof(double) * A * A);
+  double* M = malloc(sizeof(double) * A * A);
+  double* U = malloc(sizeof(double) * A * A);
+  for (int i = 0; i < A; i++) {
+    if (!(pi[i] > 0.)) {
+      free(M); free(U);
+      FAIL("spectral_init: non-positive equilibrium frequency %d", i);
+    }
+  }
+  for (int i = 0; i < A; i++)
+    for (int j = 0; j < A; j++) {
+      double mij = Q[i * A + j] * sqrt(pi[i]) / sqrt(pi[j]);
+      double mji = Q[j * A + i] * sqrt(pi[j]) / sqrt(pi[i]);
+      if (fabs(mij - mji) > 1e-8 * (fabs(mij) + fabs(mji) + 1e-300) + 1e-12) {
+        free(M); free(U);
+        FAIL("spectral_init: generator is not reversible w.r.t. pi (%d,%d)", i, j);
+      }
+      M[i * A + j] = 0.5 * (mij + mji);
+    }
+  jacobi_eigh(A, M, sp->ev, U);
+  for (int x = 0; x < A; x++)
+    for (int k = 0; k < A; k++) {
+      sp->R[x * A + k] = U[x * A + k] / sqrt(pi[x]);
+      sp->L[k * A + x] = U[x * A + k] * sqrt(pi[x]);
+    }
+  free(M); free(U);
+  return 0;
+}
+static void spectral_free(spectral_t* sp) { free(sp->ev); free(sp->R); free(sp->L); }
+
+/* [Bio++] AbstractSubstitutionModel::getPij_t: P = R diag(exp(ev t)) L. */
+static void spectral_pmatrix(const spectral_t* sp, double t, double* P) {
+  int A = sp->A;
+  for (int x = 0; x < A; x++)
+    for (int y = 0; y < A; y++) {
+      double s = 0.;
+      for (int k = 0; k < A; k++) s += sp->R[x * A + k] * exp(sp->ev[k] * t) * sp->L[k * A + y];
+      P[x * A + y] = s;
+    }
+}
+
+int orc_pmatrix(int A, const double* Q, const double* pi, double t, double* P) {
+  spectral_t sp;
+  if (spectral_init(&sp, A, Q, pi)) return -1;
+  spectral_pmatrix(&sp, t, P);
+  spectral_free(&sp);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* substitution counts  (CoMap.cpp:152 selects the method via `nijt=`)                   */
+/* ------------------------------------------------------------------------------------ */
+
+/* [Bio++] UniformizationSubstitutionCount::computeCounts_:
+ *   mu = max_i |Q_ii|, R = I + Q/mu, Bm(j,k) = Q(j,k) w(j,k) for j != k,
+ *   nMax = ceil(4 + 6 sqrt(lam) + lam), lam = mu t,
+ *   s_0 = Bm, s_l = s_{l-1} R + R^l Bm,
+ *   counts = sum_l s_l exp((l+1) ln lam - lam - ln mu - ln (l+1)!),
+ *   counts(j,k) /= P(j,k;t); NaN/Inf -> 0; negatives -> 0 only when unweighted. */
+static void counts_uniformization(const spectral_t* sp, const double* Q, const double* weights,
+                                  double t, double* N) {
+  int A = sp->A, AA = A * A;
+  double mu = 0.;
+  for (int i = 0; i < A; i++)
+    if (fabs(Q[i * A + i]) > mu) mu = fabs(Q[i * A + i]);
+  double lam = mu * t;
+  for (int i = 0; i < AA; i++) N[i] = 0.;
+  if (!(lam > 0.)) return; /* exp(-inf) weights: every term is 0, 0/P -> 0 */
+  double* R = malloc(sizeof(double) * AA);
+  double* Bm = malloc(sizeof(double) * AA);
+  double* Rp = malloc(sizeof(double) * AA);
+  double* s = malloc(sizeof(double) * AA);
+  double* t1 = malloc(sizeof(double) * AA);
+  double* t2 = malloc(sizeof(double) * AA);
+  double* P = malloc(sizeof(double) * AA);
+  for (int i = 0; i < A; i++)
+    for (int j = 0; j < A; j++) {
+      R[i * A + j] = Q[i * A + j] / mu + (i == j ? 1. : 0.);
+      Bm[i * A + j] = (i == j) ? 0. : Q[i * A + j] * (weights ? weights[i * A + j] : 1.);
+      Rp[i * A + j] = (i == j);
+      s[i * A + j] = Bm[i * A + j];
+    }
+  long nmax = (long)ceil(4. + 6. * sqrt(lam) + lam);
+  double loglam = log(lam), logmu = log(mu);
+  for (long l = 0; l <= nmax; l++) {
+    if (l > 0) {
+      mat_mul(A, s, R, t1);   /* s_{l-1} R */
+      mat_mul(A, Rp, R, t2);  /* R^l */
+      memcpy(Rp, t2, sizeof(double) * AA);
+      mat_mul(A, Rp, Bm, t2); /* R^l Bm */
+      for (int i = 0; i < AA; i++) s[i] = t1[i] + t2[i];
+    }
+    double f = exp((double)(l + 1) * loglam - lam - logmu - lgamma((double)(l + 2)));
+    for (int i = 0; i < AA; i++) N[i] += s[i] * f;
+  }
+  spectral_pmatrix(sp, t, P);
+  for (int i = 0; i < AA; i++) {
+    double v = N[i] / P[i];
+    if (isnan(v) || isinf(v) || (!weights && v < 0.)) v = 0.;
+    N[i] = v;
+  }
+  free(R); free(Bm); free(Rp); free(s); free(t1); free(t2); free(P);
+}
+
+/* [Bio++] DecompositionSubstitutionCount::computeCounts_: with Q = R diag(ev) L,
+ *   counts = R [ (L Bm R) o J(t) ] L,  J_ij = t e^{ev_i t} if ev_i == ev_j
+ *   else (e^{ev_i t} - e^{ev_j t}) / (ev_i - ev_j); then the same /P and clean-up. */
+static void counts_decomposition(const spectral_t* sp, const double* Q, const double* weights,
+                                 double t, double* N) {
+  int A = sp->A, AA = A * A;
+  double* Bm = malloc(sizeof(double) * AA);
+  double* t1 = malloc(sizeof(double) * AA);
+  double* t2 = malloc(sizeof(double) * AA);
+  double* P = malloc(sizeof(double) * AA);
+  for (int i = 0; i < A; i++)
+    for (int j = 0; j < A; j++)
+      Bm[i * A + j] = (i == j) ? 0. : Q[i * A + j] * (weights ? weights[i * A + j] : 1.);
+  mat_mul(A, sp->L, Bm, t1);
+  mat_mul(A, t1, sp->R, t2); /* L Bm R */
+  for (int i = 0; i < A; i++)
+    for (int j = 0; j < A; j++) {
+      double dd = sp->ev[i] - sp->ev[j], J;
+      if (dd == 0.) J = t * exp(sp->ev[i] * t);
+      else J = (exp(sp->ev[i] * t) - exp(sp->ev[j] * t)) / dd;
+      t2[i * A + j] *= J;
+    }
+  mat_mul(A, sp->R, t2, t1);
+  mat_mul(A, t1, sp->L, N);
+  spectral_pmatrix(sp, t, P);
+  for (int i = 0; i < AA; i++) {
+    double v = N[i] / P[i];
+    if (isnan(v) || isinf(v) || (!weights && v < 0.)) v = 0.;
+    N[i] = v;
+  }
+  free(Bm); free(t1); free(t2); free(P);
+}
+
+static void counts_any(int method, const spectral_t* sp, const double* Q, const double* weights,
+                       double t, double* N) {
+  if (method == ORC_COUNT_DECOMPOSITION) counts_decomposition(sp, Q, weights, t, N);
+  else counts_uniformization(sp, Q, weights, t, N);
+}
+
+int orc_counts(int method, int A, const double* Q, const double* pi, const double* weights,
+               double t, double* N) {
+  spectral_t sp;
+  if (method != ORC_COUNT_UNIFORMIZATION && method != ORC_COUNT_DECOMPOSITION)
+    FAIL("orc_counts: unknown method %d", method);
+  if (spectral_init(&sp, A, Q, pi)) return -1;
+  counts_any(method, &sp, Q, weights, t, N);
+  spectral_free(&sp);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* tree                                                                                  */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct {
+  int n, root, T;
+  const int32_t* parent;
+  double* len;          /* branch lengths with the [Bio++] 1e-6 lower bound applied */
+  int *nch, *ch_off, *ch; /* children lists in id (= Newick) order */
+  int* leaf_row;        /* node -> alignment row or -1 */
+} tree_t;
+
+static int tree_init(tree_t* t, int n_nodes, const int32_t* parent, const double* brlen) {
+  memset(t, 0, sizeof *t);
+  if (n_nodes < 3) FAIL("tree: need at least 3 nodes");
+  t->n = n_nodes; t->root = n_nodes - 1; t->parent = parent;
+  if (parent[t->root] != -1) FAIL("tree: last node must be the root (parent -1)");
+  t->len = malloc(sizeof(double) * n_nodes);
+  t->nch = calloc(n_nodes, sizeof(int));
+  t->ch_off = malloc(sizeof(int) * (n_nodes + 1));
+  t->ch = malloc(sizeof(int) * n_nodes);
+  t->leaf_row = malloc(sizeof(int) * n_nodes);
+  for (int v = 0; v < n_nodes - 1; v++) {
+    if (parent[v] <= v || parent[v] >= n_nodes) FAIL("tree: ids must be post-order (node %d)", v);
+    t->nch[parent[v]]++;
+    /* [Bio++] branch-length lower bound 1e-6 */
+    t->len[v] = brlen[v] < 1e-6 ? 1e-6 : brlen[v];
+  }
+  t->len[t->root] = 0.;
+  t->ch_off[0] = 0;
+  for (int v = 0; v < n_nodes; v++) t->ch_off[v + 1] = t->ch_off[v] + t->nch[v];
+  int* fill = calloc(n_nodes, sizeof(int));
+  for (int v = 0; v < n_nodes - 1; v++) {
+    int p = parent[v];
+    t->ch[t->ch_off[p] + fill[p]++] = v;
+  }
+  free(fill);
+  t->T = 0;
+  for (int v = 0; v < n_nodes; v++) t->leaf_row[v] = (t->nch[v] == 0) ? t->T++ : -1;
+  if (t->nch[t->root] < 2) FAIL("tree: root must have at least 2 children");
+  return 0;
+}
+static void tree_free(tree_t* t) {
+  free(t->len); free(t->nch); free(t->ch_off); free(t->ch); free(t->leaf_row);
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* likelihood + mapping                                                                  */
+/* ------------------------------------------------------------------------------------ */
+
+typedef struct {
+  int A, C;
+  const double *Q, *pi, *rates, *probs;
+  spectral_t sp;
+  double* P; /* [node][c][x][y]  = exp(Q len rate_c) */
+  double* N; /* [node][c][x][y]  = conditional expected counts */
+} tables_t;
+
+static int tables_init(tables_t* tb, const tree_t* tr, int A, const double* Q, const double* pi,
+                       int C, const double* rates, const double* probs, int method,
+                       const double* weights, int want_counts) {
+  memset(tb, 0, sizeof *tb);
+  tb->A = A; tb->C = C; tb->Q = Q; tb->pi = pi; tb->rates = rates; tb->probs = probs;
+  if (A < 2 || A > 32) FAIL("model: A must be in 2..32");
+  if (C < 1 || C > 32) FAIL("model: C must be in 1..32");
+  if (spectral_init(&tb->sp, A, Q, pi)) return -1;
+  size_t AA = (size_t)A * A;
+  tb->P = malloc(sizeof(double) * tr->n * C * AA);
+  tb->N = want_counts ? malloc(sizeof(double) * tr->n * C * AA) : NULL;
+  for (int v = 0; v < tr->n - 1; v++)
+    for (int c = 0; c < C; c++) {
+      double t = tr->len[v] * rates[c];
+      spectral_pmatrix(&tb->sp, t, tb->P + ((size_t)v * C + c) * AA);
+      if (want_counts) counts_any(method, &tb->sp, Q, weights, t, tb->N + ((size_t)v * C + c) * AA);
+    }
+  return 0;
+}
+static void tables_free(tables_t* tb) { spectral_free(&tb->sp); free(tb->P); free(tb->N); }
+
+/*
+ * Double-recursive likelihood + substitution vectors.
+ *
+ * [Bio++] DRHomogeneousTreeLikelihood::initialize / setData (CoETools.cpp:124,209,358-359;
+ * AnalysisTools.cpp:592-593): for every non-root node v two arrays per (site, class, state)
+ *   down[v] = likelihoods[father][v]  (subtree below v, state at v; tips = 0/1 masks)
+ *   up[v]   = likelihoods[v][father]  (everything else, state at father; root freqs are
+ *             folded in for the root's children and propagate down, prefix recursion)
+ * [Bio++] LegacySubstitutionMappingTools::computeSubstitutionVectors (CoETools.cpp:397,
+ * AnalysisTools.cpp:601, ClusterTools.cpp:227), SURVEY.md s3.3:
+ *   n_v(s) = sum_c p_c sum_x up[v][s][c][x] sum_y P_v,c(x,y) N_v,c(x,y) down[v][s][c][y] / L_s
+ * getLogLikelihoodPerSite / getPosteriorRatePerSite / getRateClassWithMaxPostProbPerSite
+ * (CoETools.cpp:507-510,669-670): logL = ln L_s, PR = sum_c r_c p_c L_sc / L_s,
+ * RC = first argmax_c L_sc (not weighted by p_c).
+ * computeNormForSite (CoMap.cpp:158-163, AnalysisTools.cpp:343-350): sqrt(sum_b n_b^2).
+ */
+static int map_core(const tree_t* tr, const tables_t* tb, int64_t S, const uint8_t* codes,
+                    int n_codes, const uint32_t* code_mask, double* n_out, double* norm,
+                    double* post_rate, int32_t* rate_class, double* loglik) {
+  const int A = tb->A, C = tb->C, n = tr->n, root = tr->root;
+  const size_t CA = (size_t)C * A, AA = (size_t)A * A;
+  const size_t per_node = (size_t)S * CA;
+  double* down = malloc(sizeof(double) * per_node * n);
+  double* up = n_out ? malloc(sizeof(double) * per_node * n) : NULL;
+  double* Lsc = malloc(sizeof(double) * S * C);
+  double* Ls = malloc(sizeof(double) * S);
+  if (!down || (n_out && !up) || !Lsc || !Ls) FAIL("map: out of memory");
+  uint32_t full = (A >= 32) ? 0xffffffffu : ((1u << A) - 1u);
+
+  /* postfix pass */
+  for (int v = 0; v < n; v++) {
+    double* dv = down + per_node * v;
+    if (tr->nch[v] == 0) {
+      const uint8_t* row = codes + (size_t)tr->leaf_row[v] * S;
+      for (int64_t s = 0; s < S; s++) {
+        if (row[s] >= n_codes) FAIL("map: code %d out of range at tip row %d", row[s], tr->leaf_row[v]);
+        uint32_t m = code_mask[row[s]] & full;
+        for (int c = 0; c < C; c++)
+          for (int x = 0; x < A; x++) dv[s * CA + c * A + x] = (m >> x) & 1u ? 1. : 0.;
+      }
+    } else {
+      for (size_t k = 0; k < per_node; k++) dv[k] = 1.;
+      for (int k = 0; k < tr->nch[v]; k++) {
+        int w = tr->ch[tr->ch_off[v] + k];
+        const double* dw = down + per_node * w;
+        for (int64_t s = 0; s < S; s++)
+          for (int c = 0; c < C; c++) {
+            const double* P = tb->P + ((size_t)w * C + c) * AA;
+            const double* dws = dw + s * CA + c * A;
+            for (int x = 0; x < A; x++) {
+              double l = 0.;
+              for (int y = 0; y < A; y++) l += P[x * A + y] * dws[y];
+              dv[s * CA + c * A + x] *= l;
+            }
+          }
+      }
+    }
+  }
+  /* root: product over sons already in down[root]; apply root frequencies */
+  {
+    const double* dr = down + per_node * root;
+    for (int64_t s = 0; s < S; s++) {
+      double L = 0.;
+      for (int c = 0; c < C; c++) {
+        double l = 0.;
+        for (int x = 0; x < A; x++) l += dr[s * CA + c * A + x] * tb->pi[x];
+        Lsc[s * C + c] = l;
+        L += l * tb->probs[c];
+      }
+      Ls[s] = L;
+      if (loglik) loglik[s] = log(L);
+      if (post_rate) {
+        double r = 0.;
+        for (int c = 0; c < C; c++) r += (Lsc[s * C + c] / L) * tb->probs[c] * tb->rates[c];
+        post_rate[s] = r;
+      }
+      if (rate_class) {
+        int best = 0;
+        for (int c = 1; c < C; c++)
+          if (Lsc[s * C + c] > Lsc[s * C + best]) best = c;
+        rate_class[s] = best;
+      }
+    }
+  }
+  if (n_out) {
+    const int B = n - 1;
+    /* prefix pass: parents have larger ids, so walk ids downwards */
+    for (int v = n - 2; v >= 0; v--) {
+      int f = tr->parent[v];
+      double* uv = up + per_node * v;
+      for (size_t k = 0; k < per_node; k++) uv[k] = 1.;
+      for (int k = 0; k < tr->nch[f]; k++) {
+        int w = tr->ch[tr->ch_off[f] + k];
+        if (w == v) continue;
+        const double* dw = down + per_node * w;
+        for (int64_t s = 0; s < S; s++)
+          for (int c = 0; c < C; c++) {
+            const double* P = tb->P + ((size_t)w * C + c) * AA;
+            const double* dws = dw + s * CA + c * A;
+            for (int x = 0; x < A; x++) {
+              double l = 0.;
+              for (int y = 0; y < A; y++) l += P[x * A + y] * dws[y];
+              uv[s * CA + c * A + x] *= l;
+            }
+          }
+      }
+      if (f != root) {
+        const double* uf = up + per_node * f;
+        for (int64_t s = 0; s < S; s++)
+          for (int c = 0; c < C; c++) {
+            const double* P = tb->P + ((size_t)f * C + c) * AA;
+            const double* ufs = uf + s * CA + c * A;
+            for (int x = 0; x < A; x++) {
+              double l = 0.;
+              for (int y = 0; y < A; y++) l += P[y * A + x] * ufs[y]; /* transposed */
+              uv[s * CA + c * A + x] *= l;
+            }
+          }
+      } else {
+        for (int64_t s = 0; s < S; s++)
+          for (int c = 0; c < C; c++)
+            for (int x = 0; x < A; x++) uv[s * CA + c * A + x] *= tb->pi[x];
+      }
+    }
+    /* mapping */
+    for (int v = 0; v < B; v++) {
+      const double* dv = down + per_node * v;
+      const double* uv = up + per_node * v;
+      for (int64_t s = 0; s < S; s++) {
+        double acc = 0.;
+        for (int c = 0; c < C; c++) {
+          const double* P = tb->P + ((size_t)v * C + c) * AA;
+          const double* N = tb->N + ((size_t)v * C + c) * AA;
+          double pc = tb->probs[c];
+          for (int x = 0; x < A; x++) {
+            double fx = pc * uv[s * CA + c * A + x];
+            for (int y = 0; y < A; y++) {
+              double lcxy = fx * P[x * A + y] * dv[s * CA + c * A + y];
+              acc += lcxy * N[x * A + y];
+            }
+          }
+        }
+        n_out[s * B + v] = acc / Ls[s];
+      }
+    }
+    if (norm)
+      for (int64_t s = 0; s < S; s++) {
+        double q = 0.;
+        for (int b = 0; b < B; b++) q += n_out[s * B + b] * n_out[s * B + b];
+        norm[s] = sqrt(q);
+      }
+  }
+  free(down); free(up); free(Lsc); free(Ls);
+  return 0;
+}
+
+int orc_map(int n_nodes, const int32_t* parent, const double* brlen, int A, const double* Q,
+            const double* pi, int C, const double* rates, const double* probs, int method,
+            const double* weights, int64_t S, const uint8_t* codes, int n_codes,
+            const uint32_t* code_mask, double* n_out, double* norm, double* post_rate,
+            int32_t* rate_class, double* loglik) {
+  tree_t tr; tables_t tb;
+  if (norm && !n_out) FAIL("orc_map: norm requires n_out");
+  if (tree_init(&tr, n_nodes, parent, brlen)) { tree_free(&tr); return -1; }
+  if (tables_init(&tb, &tr, A, Q, pi, C, rates, probs, method, weights, n_out != NULL)) {
+    tree_free(&tr); return -1;
+  }
+  int rc = map_core(&tr, &tb, S, codes, n_codes, code_mask, n_out, norm, post_rate, rate_class, loglik);
+  tables_free(&tb); tree_free(&tr);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* statistics  (CoMap/Statistics.h:106-295; VectorTools::cor/cov/cos are [Bio++])        */
+/* ------------------------------------------------------------------------------------ */
+
+/* [Bio++] VectorTools::cov(v1, v2, unbiased=true) = <center(v1), center(v2)>/n * n/(n-1) */
+static double vt_cov(int n, const double* a, const double* b) {
+  double ma = 0., mb = 0.;
+  for (int i = 0; i < n; i++) { ma += a[i]; mb += b[i]; }
+  ma /= (double)n; mb /= (double)n;
+  double s = 0.;
+  for (int i = 0; i < n; i++) s += (a[i] - ma) * (b[i] - mb);
+  double x = s / (double)n;
+  x = x * (double)n / ((double)n - 1.);
+  return x;
+}
+
+double orc_stat(int stat_id, int B, const double* v1, const double* v2) {
+  switch (stat_id) {
+    case ORC_STAT_CORRELATION: /* Statistics.h:164-174 -> cov / (sd * sd) */
+      return vt_cov(B, v1, v2) / (sqrt(vt_cov(B, v1, v1)) * sqrt(vt_cov(B, v2, v2)));
+    case ORC_STAT_COVARIANCE: /* Statistics.h:206-216 */
+      return vt_cov(B, v1, v2);
+    case ORC_STAT_COSINUS: { /* Statistics.h:218-228 -> scalar / (norm * norm) */
+      double s = 0., n1 = 0., n2 = 0.;
+      for (int i = 0; i < B; i++) { s += v1[i] * v2[i]; n1 += v1[i] * v1[i]; n2 += v2[i] * v2[i]; }
+      return s / (sqrt(n1) * sqrt(n2));
+    }
+    case ORC_STAT_COSUBSTITUTION: { /* Statistics.h:230-245 */
+      double c = 0.;
+      for (int i = 0; i < B; i++)
+        if (v1[i] >= 1. && v2[i] >= 1.) c++;
+      return c;
+    }
+    case ORC_STAT_COMPENSATION: { /* Statistics.h:247-265 */
+      double s1 = 0., s2 = 0., s3 = 0.;
+      for (int i = 0; i < B; i++) {
+        s1 += pow(v1[i], 2);
+        s2 += pow(v2[i], 2);
+        s3 += pow(v1[i] + v2[i], 2);
+      }
+      return 1. - sqrt(s3) / (sqrt(s1) + sqrt(s2));
+    }
+  }
+  return NAN;
+}
+
+double orc_stat_group(int stat_id, int B, const double* n, int n_members, const int32_t* members) {
+  if (stat_id == ORC_STAT_COMPENSATION) { /* Statistics.h:267-294 */
+    double* sq = calloc(n_members, sizeof(double));
+    double sumsq2 = 0.;
+    for (int i = 0; i < B; i++) {
+      double s = 0.;
+      for (int j = 0; j < n_members; j++) {
+        double sv = n[(size_t)members[j] * B + i];
+        sq[j] += pow(sv, 2);
+        s += sv;
+      }
+      sumsq2 += pow(s, 2);
+    }
+    double sumnorms = 0.;
+    for (int j = 0; j < n_members; j++) sumnorms += sqrt(sq[j]);
+    free(sq);
+    return 1. - sqrt(sumsq2) / sumnorms;
+  }
+  /* AbstractMinimumStatistic::getValueForGroup, Statistics.h:121-133 */
+  double mini = INFINITY;
+  for (int i = 1; i < n_members; i++)
+    for (int j = 0; j < i; j++) {
+      double val = orc_stat(stat_id, B, n + (size_t)members[i] * B, n + (size_t)members[j] * B);
+      if (val < mini) mini = val;
+    }
+  return mini;
+}
+
+/* Domain(a, b, n) + getIndex, CoMap/Domain.cpp:46-59,113-122 */
+int orc_domain_index(double lo, double hi, int K, double x) {
+  double mini = lo < hi ? lo : hi, maxi = lo < hi ? hi : lo;
+  double w = (maxi - mini) / (double)K;
+  double upper = mini + (double)K * w;
+  if (x < mini || x >= upper) return -1;
+  for (int i = 1; i < K + 1; i++)
+    if (x < mini + (double)i * w) return i - 1;
+  return -1;
+}
+
+/* CoETools::computeIntraStats pair loop, CoETools.cpp:672-724 */
+int orc_pairs(int stat_id, int64_t S, int B, const double* n, const double* norm,
+              const double* post_rate, const int32_t* rate_class, int min_rate_class,
+              double min_rate, int max_rate_class_diff, double max_rate_diff, double min_stat,
+              int K, double nmax, const int64_t* bin_offsets, const double* sorted_null,
+              int64_t capacity, int32_t* out_i, int32_t* out_j, double* out_stat,
+              int32_t* out_rcmin, double* out_prmin, double* out_nmin, double* out_pvalue,
+              int64_t* out_nsim, int64_t* n_rows) {
+  int64_t r = 0;
+  for (int64_t i = 0; i < S; i++) {
+    int iClass = rate_class[i];
+    double iRate = post_rate[i];
+    if (iClass < min_rate_class) continue;
+    if (iRate < min_rate) continue;
+    double iNorm = norm[i];
+    for (int64_t j = i + 1; j < S; j++) {
+      int jClass = rate_class[j];
+      double jRate = post_rate[j];
+      if (jClass < min_rate_class) continue;
+      if (jRate < min_rate) continue;
+      double jNorm = norm[j];
+      if (max_rate_class_diff >= 0 && abs(jClass - iClass) > max_rate_class_diff) continue;
+      if (max_rate_diff >= 0. && fabs(jRate - iRate) > max_rate_diff) continue;
+      double stat = orc_stat(stat_id, B, n + i * B, n + j * B);
+      if (fabs(stat) < min_stat) continue;
+      double minNorm = iNorm < jNorm ? iNorm : jNorm;
+      if (r >= capacity) FAIL("orc_pairs: capacity exceeded");
+      out_i[r] = (int32_t)i; out_j[r] = (int32_t)j; out_stat[r] = stat;
+      out_rcmin[r] = iClass < jClass ? iClass : jClass;
+      out_prmin[r] = iRate < jRate ? iRate : jRate;
+      out_nmin[r] = minNorm;
+      if (K > 0) {
+        int cat = orc_domain_index(0., nmax, K, minNorm);
+        if (cat >= 0) {
+          const double* sim = sorted_null + bin_offsets[cat];
+          int64_t nsim = bin_offsets[cat + 1] - bin_offsets[cat], count;
+          for (count = 0; count < nsim && sim[count] < stat; ++count) {}
+          out_pvalue[r] = (double)(nsim - count + 1) / (double)(nsim + 1);
+          out_nsim[r] = nsim;
+        } else { /* OutOfRangeException -> "NA\t0" */
+          out_pvalue[r] = NAN;
+          out_nsim[r] = 0;
+        }
+      }
+      r++;
+    }
+  }
+  *n_rows = r;
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* simulation                                                                            */
+/* ------------------------------------------------------------------------------------ */
+
+/* Philox4x32-10 (Salmon et al. 2011).  Counter = (site lo, site hi, node, tag),
+ * key = (seed lo, seed hi).  Shared bit-for-bit with comap_b200/csrc (own code there). */
+static void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0];
+    uint64_t p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0;
+    uint32_t n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1;
+    uint32_t n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+static double philox_u01(uint64_t seed, uint64_t site, uint32_t node, uint32_t tag) {
+  uint32_t c[4] = {(uint32_t)site, (uint32_t)(site >> 32), node, tag};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  uint64_t u = (((uint64_t)c[0] << 32) | c[1]) >> 11;
+  return (double)u * (1.0 / 9007199254740992.0);
+}
+
+/* [Bio++] NonHomogeneousSequenceSimulator::simulate(n) in discrete-rate mode
+ * (CoMap.cpp:209-219; AnalysisTools.cpp:591,614; ClusterTools.cpp:224): per site the root
+ * state is drawn from pi (first i with r <= cumulative), the rate class uniformly over
+ * classes (upstream behaviour; weighted_classes=1 draws from probs
+ * instead), each child state by linear inverse-CDF over the cumulative row of P_c(b). */
+int orc_simulate(int n_nodes, const int32_t* parent, const double* brlen, int A, const double* Q,
+                 const double* pi, int C, const double* rates, const double* probs, uint64_t seed,
+                 int64_t first_site, int64_t n, int weighted_classes, uint8_t* states,
+                 int32_t* classes) {
+  tree_t tr; tables_t tb;
+  if (tree_init(&tr, n_nodes, parent, brlen)) { tree_free(&tr); return -1; }
+  if (tables_init(&tb, &tr, A, Q, pi, C, rates, probs, 0, NULL, 0)) { tree_free(&tr); return -1; }
+  size_t AA = (size_t)A * A;
+  double* cum = malloc(sizeof(double) * tr.n * C * AA);
+  for (size_t m = 0; m < (size_t)(tr.n - 1) * C; m++)
+    for (int x = 0; x < A; x++) {
+      double s = 0.;
+      for (int y = 0; y < A; y++) { s += tb.P[m * AA + x * A + y]; cum[m * AA + x * A + y] = s; }
+    }
+  uint8_t* st = malloc(tr.n);
+  for (int64_t j = 0; j < n; j++) {
+    uint64_t site = (uint64_t)(first_site + j);
+    double r = philox_u01(seed, site, (uint32_t)tr.root, 0);
+    int x0 = A - 1;
+    double cp = 0.;
+    for (int i = 0; i < A; i++) { cp += pi[i]; if (r <= cp) { x0 = i; break; } }
+    double rc = philox_u01(seed, site, (uint32_t)tr.root, 1);
+    int c = 0;
+    if (weighted_classes) {
+      double cq = 0.; c = C - 1;
+      for (int i = 0; i < C; i++) { cq += probs[i]; if (rc <= cq) { c = i; break; } }
+    } else {
+      c = (int)(rc * (double)C);
+      if (c >= C) c = C - 1;
+    }
+    if (classes) classes[j] = c;
+    st[tr.root] = (uint8_t)x0;
+    for (int v = tr.n - 2; v >= 0; v--) {
+      int x = st[tr.parent[v]];
+      double u = philox_u01(seed, site, (uint32_t)v, 0);
+      const double* row = cum + ((size_t)v * C + c) * AA + (size_t)x * A;
+      int y = A - 1;
+      for (int k = 0; k < A; k++) if (u < row[k]) { y = k; break; }
+      st[v] = (uint8_t)y;
+      if (tr.leaf_row[v] >= 0) states[(size_t)tr.leaf_row[v] * n + j] = (uint8_t)y;
+    }
+  }
+  free(st); free(cum); tables_free(&tb); tree_free(&tr);
+  return 0;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* null distribution  (AnalysisTools.cpp:564-658 + sort at CoETools.cpp:650-652)         */
+/* ------------------------------------------------------------------------------------ */
+
+static int cmp_double(const void* a, const void* b) {
+  double x = *(const double*)a, y = *(const double*)b;
+  return (x > y) - (x < y);
+}
+
+int orc_null_intra(int n_nodes, const int32_t* parent, const double* brlen, int A, const double* Q,
+                   const double* pi, int C, const double* rates, const double* probs, int method,
+                   const double* weights, int stat_id, int rep_cpu, int rep_ram,
+                   const uint8_t* sim1, const uint8_t* sim2, int K, double nmax, double* raw,
+                   int64_t* bin_offsets, double* sorted) {
+  tree_t tr; tables_t tb;
+  if (tree_init(&tr, n_nodes, parent, brlen)) { tree_free(&tr); return -1; }
+  if (tables_init(&tb, &tr, A, Q, pi, C, rates, probs, method, weights, 1)) { tree_free(&tr); return -1; }
+  const int B = tr.n - 1;
+  uint32_t* mask = malloc(sizeof(uint32_t) * A);
+  for (int x = 0; x < A; x++) mask[x] = 1u << x;
+  size_t total = (size_t)rep_cpu * rep_ram;
+  double* m1 = malloc(sizeof(double) * (size_t)rep_ram * B);
+  double* m2 = malloc(sizeof(double) * (size_t)rep_ram * B);
+  double *n1 = malloc(sizeof(double) * rep_ram), *n2 = malloc(sizeof(double) * rep_ram);
+  double *p1 = malloc(sizeof(double) * rep_ram), *p2 = malloc(sizeof(double) * rep_ram);
+  int32_t *c1 = malloc(sizeof(int32_t) * rep_ram), *c2 = malloc(sizeof(int32_t) * rep_ram);
+  double* st = malloc(sizeof(double) * total);
+  int* cat = malloc(sizeof(int) * total);
+  int rc = 0;
+  for (int i = 0; i < rep_cpu && !rc; i++) {
+    size_t off = (size_t)i * tr.T * rep_ram;
+    rc = map_core(&tr, &tb, rep_ram, sim1 + off, A, mask, m1, n1, p1, c1, NULL);
+    if (!rc) rc = map_core(&tr, &tb, rep_ram, sim2 + off, A, mask, m2, n2, p2, c2, NULL);
+    if (rc) break;
+    for (int j = 0; j < rep_ram; j++) {
+      size_t k = (size_t)i * rep_ram + j;
+      double stat = orc_stat(stat_id, B, m1 + (size_t)j * B, m2 + (size_t)j * B);
+      double nmin = n1[j] < n2[j] ? n1[j] : n2[j];
+      st[k] = stat;
+      cat[k] = K > 0 ? orc_domain_index(0., nmax, K, nmin) : -1;
+      if (raw) {
+        raw[k * 4 + 0] = stat;
+        raw[k * 4 + 1] = (double)(c1[j] < c2[j] ? c1[j] : c2[j]);
+        raw[k * 4 + 2] = p1[j] < p2[j] ? p1[j] : p2[j];
+        raw[k * 4 + 3] = nmin;
+      }
+    }
+  }
+  if (!rc && K > 0 && bin_offsets && sorted) {
+    int64_t* cnt = calloc(K + 1, sizeof(int64_t));
+    for (size_t k = 0; k < total; k++) if (cat[k] >= 0) cnt[cat[k] + 1]++;
+    bin_offsets[0] = 0;
+    for (int b = 0; b < K; b++) bin_offsets[b + 1] = bin_offsets[b] + cnt[b + 1];
+    int64_t* pos = malloc(sizeof(int64_t) * K);
+    for (int b = 0; b < K; b++) pos[b] = bin_offsets[b];
+    for (size_t k = 0; k < total; k++) if (cat[k] >= 0) sorted[pos[cat[k]]++] = st[k];
+    for (int b = 0; b < K; b++)
+      qsort(sorted + bin_offsets[b], bin_offsets[b + 1] - bin_offsets[b], sizeof(double), cmp_double);
+    free(cnt); free(pos);
+  }
+  free(mask); free(m1); free(m2); free(n1); free(n2); free(p1); free(p2); free(c1); free(c2);
+  free(st); free(cat);
+  tables_free(&tb); tree_free(&tr);
+  return rc;
+}
+
+/* ------------------------------------------------------------------------------------ */
+/* clustering                                                                            */
+/* ------------------------------------------------------------------------------------ */
+
+/* CoMap.cpp:401-440; Distance.h:157-171 (Euclidian), :334-337 (comp - stat, comp = 1 for
+ * Correlation, CoMap.cpp:410), :382-385 (1 - Compensation). */
+int orc_distance_matrix(int dist_id, int64_t S, int B, const double* n, double* mat) {
+  for (int64_t i = 0; i < S; i++) {
+    mat[i * S + i] = 0.;
+    for (int64_t j = 0; j < i; j++) {
+      const double *a = n + i * B, *b = n + j * B;
+      double d;
+      if (dist_id == ORC_DIST_EUCLIDIAN) {
+        d = 0.;
+        for (int k = 0; k < B; k++) d += pow(b[k] - a[k], 2);
+        d = sqrt(d);
+      } else if (dist_id == ORC_DIST_CORRELATION) {
+        d = 1. - orc_stat(ORC_STAT_CORRELATION, B, a, b);
+      } else if (dist_id == ORC_DIST_COMPENSATION) {
+        d = 1. - orc_stat(ORC_STAT_COMPENSATION, B, a, b);
+      } else FAIL("orc_distance_matrix: unknown distance %d", dist_id);
+      mat[i * S + j] = mat[j * S + i] = d;
+    }
+  }
+  return 0;
+}
+
+/* [Bio++] HierarchicalClustering(method, matrix, rootTree) + AbstractAgglomerative-
+ * DistanceMethod::computeTree (CoMap.cpp:460-485; ClusterTools.cpp:260-262), SURVEY.md
+ * s8 a14: while more than 2 live clusters: first strict minimum over live pairs (i<j)
+ * in id order; branch lengths d/2 - height(child); parent takes slot i, slot j dies;
+ * Lance-Williams update w1 d1 + w2 d2 + w4 |d1 - d2| with (.5,.5,+.5) complete,
+ * (.5,.5,-.5) single, (n1/(n1+n2), n2/(n1+n2), 0) average; the last two clusters are
+ * joined at d/2. */
+int orc_hclust(int linkage, int64_t S, double* mat, int32_t* left, int32_t* right, double* height) {
+  if (S < 2) FAIL("orc_hclust: need at least 2 sites");
+  int32_t* node = malloc(sizeof(int32_t) * S);  /* dendrogram node held by slot */
+  double* len = calloc(S, sizeof(double));      /* ClusterInfos.length of the slot's node */
+  int64_t* nl = malloc(sizeof(int64_t) * S);    /* numberOfLeaves */
+  char* alive = malloc(S);
+  double* nd = malloc(sizeof(double) * S);
+  for (int64_t i = 0; i < S; i++) { node[i] = (int32_t)i; nl[i] = 1; alive[i] = 1; }
+  int64_t live = S; int32_t next = (int32_t)S;
+  while (live > 2) {
+    double dmin = INFINITY; int64_t bi = -1, bj = -1;
+    for (int64_t i = 0; i < S; i++) {
+      if (!alive[i]) continue;
+      for (int64_t j = i + 1; j < S; j++) {
+        if (!alive[j]) continue;
+        double d = mat[i * S + j];
+        if (d < dmin) { dmin = d; bi = i; bj = j; }
+      }
+    }
+    if (bi < 0) FAIL("orc_hclust: no finite distance left");
+    double half = mat[bi * S + bj] / 2.;
+    double w1, w2, w4;
+    if (linkage == ORC_LINK_SINGLE) { w1 = .5; w2 = .5; w4 = -.5; }
+    else if (linkage == ORC_LINK_COMPLETE) { w1 = .5; w2 = .5; w4 = .5; }
+    else if (linkage == ORC_LINK_AVERAGE) {
+      double a = (double)nl[bi], b = (double)nl[bj];
+      w1 = a / (a + b); w2 = b / (a + b); w4 = 0.;
+    } else FAIL("orc_hclust: unknown linkage %d", linkage);
+    for (int64_t k = 0; k < S; k++) {
+      if (!alive[k]) continue;
+      if (k != bi && k != bj) {
+        double d1 = mat[bi * S + k], d2 = mat[bj * S + k];
+        nd[k] = w1 * d1 + w2 * d2 + 0. * mat[bi * S + bj] + w4 * fabs(d1 - d2);
+      } else nd[k] = 0.;
+    }
+    /* getParentNode: length(parent) = length(son1) + distToFather(son1) = d/2 */
+    left[next - S] = node[bi]; right[next - S] = node[bj];
+    double d0 = half - len[bi];
+    height[next - S] = len[bi] + d0;
+    node[bi] = next; len[bi] = height[next - S]; nl[bi] += nl[bj];
+    alive[bj] = 0; live--; next++;
+    for (int64_t k = 0; k < S; k++)
+      if (alive[k]) mat[bi * S + k] = mat[k * S + bi] = nd[k];
+  }
+  { /* finalStep */
+    int64_t i1 = -1, i2 = -1;
+    for (int64_t i = 0; i < S; i++) if (alive[i]) { if (i1 < 0) i1 = i; else i2 = i; }
+    double d = mat[i1 * S + i2] / 2;
+    left[next - S] = node[i1]; right[next - S] = node[i2];
+    height[next - S] = len[i1] + (d - len[i1]);
+  }
+  free(node); free(len); free(nl); free(alive); free(nd);
+  return 0;
+}
+
+/* ClusterTools::getGroups (ClusterTools.cpp:59-113): one group per inner node, emitted in
+ * post-order, members in DFS leaf order, height = height(last son) + its branch;
+ * computeNormProperties (:296-319): Nmin = min leaf norm; Distance::setStatisticAsProperty
+ * (Distance.h:109-129 Euclidian: 2*height; :346-368 statistic-based: comp - 2*height;
+ * :390-422 compensation: 1 - ||sum v|| / sum ||v||). */
+int orc_groups(int dist_id, int64_t S, int B, const double* n, const double* norm,
+               const int32_t* left, const int32_t* right, const double* height, int max_size,
+               int32_t* members, int64_t* offsets, double* g_height, double* g_stat,
+               double* g_nmin, int64_t* n_groups) {
+  int64_t n_inner = S - 1, ng = 0, fill = 0;
+  int32_t root = (int32_t)(2 * S - 2);
+  /* iterative post-order; each inner node's members = concat(left members, right members) */
+  int32_t* stack = malloc(sizeof(int32_t) * 2 * S);
+  char* state = calloc(2 * S, 1);
+  int64_t* first = malloc(sizeof(int64_t) * 2 * S); /* start of this node's leaves in DFS order */
+  int32_t* dfs = malloc(sizeof(int32_t) * S);
+  int64_t ndfs = 0; int sp = 0;
+  stack[sp++] = root;
+  offsets[0] = 0;
+  while (sp > 0) {
+    int32_t v = stack[sp - 1];
+    if (v < S) { first[v] = ndfs; dfs[ndfs++] = v; sp--; continue; }
+    if (state[v] == 0) { first[v] = ndfs; state[v] = 1; stack[sp++] = left[v - S]; continue; }
+    if (state[v] == 1) { state[v] = 2; stack[sp++] = right[v - S]; continue; }
+    sp--;
+    int64_t cnt = ndfs - first[v];
+    if (cnt > max_size) continue; /* CoMap.cpp:517, ClusterTools.cpp:273 */
+    double nmin = INFINITY;
+    for (int64_t k = 0; k < cnt; k++) {
+      int32_t m = dfs[first[v] + k];
+      members[fill + k] = m;
+      if (norm[m] < nmin) nmin = norm[m];
+    }
+    double h = height[v - S], stat;
+    if (dist_id == ORC_DIST_COMPENSATION) stat = orc_stat_group(ORC_STAT_COMPENSATION, B, n, (int)cnt, members + fill);
+    else if (dist_id == ORC_DIST_CORRELATION) stat = 1. - 2 * h;
+    else stat = 2 * h;
+    fill += cnt;
+    offsets[ng + 1] = fill;
+    g_height[ng] = h; g_stat[ng] = stat; g_nmin[ng] = nmin;
+    ng++;
+    if (ng > n_inner) FAIL("orc_groups: malformed dendrogram");
+  }
+  *n_groups = ng;
+  free(stack); free(state); free(first); free(dfs);
+  return 0;
+}

@@ -1,0 +1,187 @@
+"""ctypes binding of oracle/liboracle.so -- the CPU parity oracle (test infrastructure).
+
+Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline legs may import this.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+
+STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "compensation": 4}
+DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
+LINK = {"complete": 0, "single": 1, "average": 2}
+COUNT = {"uniformization": 0, "decomposition": 1}
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        src = os.path.join(ROOT, "oracle", "comap_oracle.c")
+        if (not os.path.exists(_SO)) or os.path.getmtime(_SO) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle"), "-s"])
+        _lib = C.CDLL(_SO)
+        _lib.orc_last_error.restype = C.c_char_p
+        _lib.orc_stat.restype = C.c_double
+        _lib.orc_stat_group.restype = C.c_double
+    return _lib
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def _d(a):
+    return _p(a, C.c_double)
+
+
+def _chk(rc):
+    if rc != 0:
+        raise RuntimeError("oracle: " + lib().orc_last_error().decode())
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def pmatrix(Q, pi, t):
+    A = len(pi)
+    P = np.empty((A, A))
+    _chk(lib().orc_pmatrix(A, _d(_f64(Q)), _d(_f64(pi)), C.c_double(t), _d(P)))
+    return P
+
+
+def counts(Q, pi, t, method="uniformization", weights=None):
+    A = len(pi)
+    N = np.empty((A, A))
+    w = None if weights is None else _f64(weights)
+    _chk(lib().orc_counts(COUNT[method], A, _d(_f64(Q)), _d(_f64(pi)), _d(w), C.c_double(t), _d(N)))
+    return N
+
+
+def _tree_args(parent, brlen):
+    parent = np.ascontiguousarray(parent, dtype=np.int32)
+    brlen = _f64(brlen)
+    return (len(parent), _p(parent, C.c_int32), _d(brlen)), (parent, brlen)
+
+
+def _model_args(Q, pi, rates, probs):
+    Q, pi, rates, probs = _f64(Q), _f64(pi), _f64(rates), _f64(probs)
+    return (len(pi), _d(Q), _d(pi), len(rates), _d(rates), _d(probs)), (Q, pi, rates, probs)
+
+
+def map_sites(parent, brlen, Q, pi, rates, probs, codes, code_mask, method="uniformization",
+              weights=None, want_vectors=True):
+    ta, keep1 = _tree_args(parent, brlen)
+    ma, keep2 = _model_args(Q, pi, rates, probs)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    T, S = codes.shape
+    code_mask = np.ascontiguousarray(code_mask, dtype=np.uint32)
+    B = len(parent) - 1
+    n = np.empty((S, B)) if want_vectors else None
+    norm = np.empty(S) if want_vectors else None
+    pr = np.empty(S); rc = np.empty(S, dtype=np.int32); ll = np.empty(S)
+    w = None if weights is None else _f64(weights)
+    _chk(lib().orc_map(*ta, *ma, COUNT[method], _d(w), C.c_int64(S), _p(codes, C.c_uint8),
+                       len(code_mask), _p(code_mask, C.c_uint32), _d(n), _d(norm), _d(pr),
+                       _p(rc, C.c_int32), _d(ll)))
+    return dict(n=n, norm=norm, post_rate=pr, rate_class=rc, loglik=ll)
+
+
+def stat(name, v1, v2):
+    v1, v2 = _f64(v1), _f64(v2)
+    return lib().orc_stat(STAT[name], len(v1), _d(v1), _d(v2))
+
+
+def stat_group(name, n, members):
+    n = _f64(n); m = np.ascontiguousarray(members, dtype=np.int32)
+    return lib().orc_stat_group(STAT[name], n.shape[1], _d(n), len(m), _p(m, C.c_int32))
+
+
+def domain_index(lo, hi, K, x):
+    return lib().orc_domain_index(C.c_double(lo), C.c_double(hi), K, C.c_double(x))
+
+
+def pairs(stat_name, n, norm, post_rate, rate_class, min_rate_class=0, min_rate=0.0,
+          max_rate_class_diff=-1, max_rate_diff=-1.0, min_stat=0.0, null=None):
+    """null = (K, nmax, bin_offsets, sorted) or None."""
+    n = _f64(n); S, B = n.shape
+    norm, post_rate = _f64(norm), _f64(post_rate)
+    rate_class = np.ascontiguousarray(rate_class, dtype=np.int32)
+    cap = S * (S - 1) // 2
+    oi = np.empty(cap, np.int32); oj = np.empty(cap, np.int32); st = np.empty(cap)
+    rcm = np.empty(cap, np.int32); prm = np.empty(cap); nm = np.empty(cap)
+    pv = np.full(cap, np.nan); ns = np.zeros(cap, np.int64); nr = C.c_int64(0)
+    if null is None:
+        K, nmax, offs, srt = 0, 0.0, None, None
+    else:
+        K, nmax, offs, srt = null
+        offs = np.ascontiguousarray(offs, dtype=np.int64); srt = _f64(srt)
+    _chk(lib().orc_pairs(STAT[stat_name], C.c_int64(S), B, _d(n), _d(norm), _d(post_rate),
+                         _p(rate_class, C.c_int32), min_rate_class, C.c_double(min_rate),
+                         max_rate_class_diff, C.c_double(max_rate_diff), C.c_double(min_stat),
+                         K, C.c_double(nmax), _p(offs, C.c_int64), _d(srt), C.c_int64(cap),
+                         _p(oi, C.c_int32), _p(oj, C.c_int32), _d(st), _p(rcm, C.c_int32), _d(prm),
+                         _d(nm), _d(pv), _p(ns, C.c_int64), C.byref(nr)))
+    k = nr.value
+    return dict(i=oi[:k], j=oj[:k], stat=st[:k], rcmin=rcm[:k], prmin=prm[:k], nmin=nm[:k],
+                pvalue=pv[:k], nsim=ns[:k])
+
+
+def simulate(parent, brlen, Q, pi, rates, probs, seed, first_site, n, weighted_classes=False):
+    ta, keep1 = _tree_args(parent, brlen)
+    ma, keep2 = _model_args(Q, pi, rates, probs)
+    from comap_b200.synthetic import n_leaves_of
+    T = n_leaves_of(np.asarray(parent))
+    states = np.empty((T, n), dtype=np.uint8); cls = np.empty(n, dtype=np.int32)
+    _chk(lib().orc_simulate(*ta, *ma, C.c_uint64(seed), C.c_int64(first_site), C.c_int64(n),
+                            int(weighted_classes), _p(states, C.c_uint8), _p(cls, C.c_int32)))
+    return states, cls
+
+
+def null_intra(parent, brlen, Q, pi, rates, probs, stat_name, sim1, sim2, K, nmax,
+               method="uniformization", weights=None):
+    ta, keep1 = _tree_args(parent, brlen)
+    ma, keep2 = _model_args(Q, pi, rates, probs)
+    sim1 = np.ascontiguousarray(sim1, dtype=np.uint8); sim2 = np.ascontiguousarray(sim2, dtype=np.uint8)
+    rep_cpu, T, rep_ram = sim1.shape
+    tot = rep_cpu * rep_ram
+    raw = np.empty((tot, 4)); offs = np.zeros(K + 1, dtype=np.int64); srt = np.empty(tot)
+    w = None if weights is None else _f64(weights)
+    _chk(lib().orc_null_intra(*ta, *ma, COUNT[method], _d(w), STAT[stat_name], rep_cpu, rep_ram,
+                              _p(sim1, C.c_uint8), _p(sim2, C.c_uint8), K, C.c_double(nmax),
+                              _d(raw), _p(offs, C.c_int64), _d(srt)))
+    return dict(raw=raw, bin_offsets=offs, sorted=srt[:offs[-1]])
+
+
+def distance_matrix(dist_name, n):
+    n = _f64(n); S, B = n.shape
+    mat = np.empty((S, S))
+    _chk(lib().orc_distance_matrix(DIST[dist_name], C.c_int64(S), B, _d(n), _d(mat)))
+    return mat
+
+
+def hclust(linkage, mat):
+    mat = np.array(mat, dtype=np.float64, order="C"); S = mat.shape[0]
+    left = np.empty(S - 1, np.int32); right = np.empty(S - 1, np.int32); height = np.empty(S - 1)
+    _chk(lib().orc_hclust(LINK[linkage], C.c_int64(S), _d(mat), _p(left, C.c_int32),
+                          _p(right, C.c_int32), _d(height)))
+    return left, right, height
+
+
+def groups(dist_name, n, norm, left, right, height, max_size):
+    n = _f64(n); S, B = n.shape; norm = _f64(norm)
+    left = np.ascontiguousarray(left, np.int32); right = np.ascontiguousarray(right, np.int32)
+    height = _f64(height)
+    members = np.empty(max(1, (S - 1) * max_size), np.int32); offs = np.zeros(S + 1, np.int64)
+    gh = np.empty(S); gs = np.empty(S); gn = np.empty(S); ng = C.c_int64(0)
+    _chk(lib().orc_groups(DIST[dist_name], C.c_int64(S), B, _d(n), _d(norm), _p(left, C.c_int32),
+                          _p(right, C.c_int32), _d(height), max_size, _p(members, C.c_int32),
+                          _p(offs, C.c_int64), _d(gh), _d(gs), _d(gn), C.byref(ng)))
+    k = ng.value
+    return dict(members=[members[offs[g]:offs[g + 1]].copy() for g in range(k)], height=gh[:k],
+                stat=gs[:k], nmin=gn[:k])

@@ -1,0 +1,200 @@
+"""Cross-checks of the C oracle against independent numpy / scipy restatements
+(second opinions for the parts the reference ships no expected outputs for)."""
+import numpy as np
+import pytest
+import helpers as H
+import oracle_binding as O
+from comap_b200 import synthetic as syn
+
+
+@pytest.mark.parametrize("T,S,seed,amb", [(5, 40, 1, 0.0), (12, 64, 2, 0.1), (40, 50, 3, 0.02)])
+def test_map_vs_numpy_dna(T, S, seed, amb):
+    c = H.random_dna_case(T, S, seed, ambiguity=amb)
+    r = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    q = H.map_np(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    assert np.allclose(r["n"], q["n"], rtol=1e-9, atol=1e-14)
+    assert np.allclose(r["norm"], q["norm"], rtol=1e-10)
+    assert np.allclose(r["loglik"], q["loglik"], rtol=1e-11)
+    assert np.allclose(r["post_rate"], q["post_rate"], rtol=1e-10)
+    assert np.array_equal(r["rate_class"], q["rate_class"])
+
+
+def test_map_invariant_class_and_gtr():
+    parent, brlen = syn.random_tree(9, 7, 0.1)
+    Q, pi = syn.gtr(1.6, 0.55, 0.35, 0.30, 0.28, [0.25, 0.2, 0.3, 0.25])
+    rates, probs = syn.invariant(*syn.gamma_rates(0.737, 4), p=0.3666)
+    assert abs((rates * probs).sum() - 1) < 1e-12 and rates[0] == 0
+    rng = np.random.default_rng(5)
+    codes = H.simulate_np(parent, brlen, Q, pi, rates, rng, 80)
+    mask = syn.identity_code_mask(4)
+    r = O.map_sites(parent, brlen, Q, pi, rates, probs, codes, mask)
+    q = H.map_np(parent, brlen, Q, pi, rates, probs, codes, mask)
+    assert np.all(np.isfinite(r["n"]))
+    assert np.allclose(r["n"], q["n"], rtol=1e-9, atol=1e-14)
+    assert np.array_equal(r["rate_class"], q["rate_class"])
+
+
+def test_mapping_total_equals_brute_force_tiny_tree():
+    """3 taxa, 1 class: posterior expected counts by explicit enumeration of ancestral states."""
+    parent = np.array([3, 3, 3, -1], np.int32)
+    brlen = np.array([0.3, 0.1, 0.7, 0.0])
+    Q, pi = syn.hky85(3.0, [0.1, 0.2, 0.3, 0.4])
+    rates, probs = np.array([1.0]), np.array([1.0])
+    codes = np.array([[0, 1, 2], [0, 3, 2], [1, 3, 2]], np.uint8)
+    r = O.map_sites(parent, brlen, Q, pi, rates, probs, codes, syn.identity_code_mask(4))
+    P = [O.pmatrix(Q, pi, t) for t in brlen[:3]]
+    N = [O.counts(Q, pi, t) for t in brlen[:3]]
+    for s in range(3):
+        tip = codes[:, s]
+        w = np.array([pi[x] * P[0][x, tip[0]] * P[1][x, tip[1]] * P[2][x, tip[2]] for x in range(4)])
+        for b in range(3):
+            e = sum(w[x] * N[b][x, tip[b]] for x in range(4)) / w.sum()
+            assert abs(r["n"][s, b] - e) < 1e-13
+        assert abs(r["loglik"][s] - np.log(w.sum())) < 1e-13
+
+
+def test_pmatrix_and_counts_vs_numpy():
+    Q, pi = syn.jtt92()
+    for t in (1e-7, 0.01, 0.5, 3.0):
+        # eigen-based P(t) carries ~1e-16 absolute noise per entry (both sides)
+        assert np.allclose(O.pmatrix(Q, pi, t), H.expm_rev(Q, pi, t), rtol=1e-10, atol=1e-14)
+        Pn = H.expm_rev(Q, pi, t)
+        assert np.allclose(O.counts(Q, pi, t) * O.pmatrix(Q, pi, t), H.unif_counts_np(Q, pi, t) * Pn, rtol=1e-10, atol=1e-15)
+    w = np.abs(np.subtract.outer(np.arange(20.0), np.arange(20.0)))
+    assert np.allclose(O.counts(Q, pi, 0.3, weights=w), H.unif_counts_np(Q, pi, 0.3, w), rtol=1e-10)
+    assert np.all(O.counts(Q, pi, 0.0) == 0)
+
+
+def test_statistics_vs_numpy():
+    rng = np.random.default_rng(0)
+    a, b = rng.gamma(0.3, 1.0, 97), rng.gamma(0.3, 1.0, 97)
+    assert abs(O.stat("correlation", a, b) - np.corrcoef(a, b)[0, 1]) < 1e-13
+    assert abs(O.stat("covariance", a, b) - np.cov(a, b)[0, 1]) < 1e-13
+    assert abs(O.stat("cosinus", a, b) - a @ b / np.linalg.norm(a) / np.linalg.norm(b)) < 1e-13
+    assert O.stat("cosubstitution", a, b) == ((a >= 1) & (b >= 1)).sum()
+    comp = 1 - np.linalg.norm(a + b) / (np.linalg.norm(a) + np.linalg.norm(b))
+    assert abs(O.stat("compensation", a, -b) - (1 - np.linalg.norm(a - b) / (np.linalg.norm(a) + np.linalg.norm(b)))) < 1e-13
+    assert abs(O.stat("compensation", a, b) - comp) < 1e-13
+    assert np.isnan(O.stat("correlation", np.ones(5), a[:5]))
+    n = rng.gamma(0.3, 1.0, (6, 30))
+    g = O.stat_group("correlation", n, [0, 2, 5])
+    assert abs(g - min(np.corrcoef(n[[0, 2, 5]])[np.triu_indices(3, 1)])) < 1e-13
+    gc = O.stat_group("compensation", n, [1, 2, 3, 4])
+    assert abs(gc - (1 - np.linalg.norm(n[1:5].sum(0)) / np.linalg.norm(n[1:5], axis=1).sum())) < 1e-13
+
+
+def test_domain_index_semantics():
+    # Domain.cpp:113-122: [lo, hi) with equal-width bins; upper bound excluded
+    assert O.domain_index(0, 10, 10, 0.0) == 0
+    assert O.domain_index(0, 10, 10, 9.999) == 9
+    assert O.domain_index(0, 10, 10, 10.0) == -1
+    assert O.domain_index(0, 10, 10, -1e-9) == -1
+    assert O.domain_index(0, 1, 4, 0.25) == 1
+
+
+def test_pairs_filters_and_pvalues():
+    rng = np.random.default_rng(3)
+    S, B = 30, 41
+    n = rng.gamma(0.4, 1.0, (S, B)); norm = np.sqrt((n ** 2).sum(1))
+    pr = rng.gamma(2, 0.5, S); rc = rng.integers(0, 4, S).astype(np.int32)
+    K, nmax = 5, norm.max()
+    null_stat = rng.uniform(-1, 1, 4000); null_n = rng.uniform(0, nmax * 1.1, 4000)
+    bins = [np.sort(null_stat[[O.domain_index(0, nmax, K, x) == k for x in null_n]]) for k in range(K)]
+    offs = np.concatenate([[0], np.cumsum([len(b) for b in bins])])
+    r = O.pairs("correlation", n, norm, pr, rc, null=(K, nmax, offs, np.concatenate(bins)))
+    assert len(r["i"]) == S * (S - 1) // 2
+    assert np.all(r["i"][1:] * S + r["j"][1:] > r["i"][:-1] * S + r["j"][:-1])  # reference order
+    cc = np.corrcoef(n)
+    assert np.allclose(r["stat"], cc[r["i"], r["j"]], atol=1e-13)
+    k = 17
+    i, j = r["i"][k], r["j"][k]
+    nm = min(norm[i], norm[j]); cat = O.domain_index(0, nmax, K, nm)
+    cnt = (bins[cat] < r["stat"][k]).sum()
+    assert r["nsim"][k] == len(bins[cat]) and r["pvalue"][k] == (len(bins[cat]) - cnt + 1) / (len(bins[cat]) + 1)
+    # the pair holding the max norm falls out of [0, max) -> NA / 0  (CoETools.cpp:718-720)
+    top = np.argmax(norm)
+    sel = (np.minimum(norm[r["i"]], norm[r["j"]]) == norm[top])
+    assert np.all(np.isnan(r["pvalue"][sel])) and np.all(r["nsim"][sel] == 0)
+    f = O.pairs("correlation", n, norm, pr, rc, min_rate_class=1, min_rate=0.5, max_rate_class_diff=1,
+                max_rate_diff=0.8, min_stat=0.1)
+    ok = (rc[r["i"]] >= 1) & (rc[r["j"]] >= 1) & (pr[r["i"]] >= 0.5) & (pr[r["j"]] >= 0.5) \
+        & (np.abs(rc[r["i"]] - rc[r["j"]]) <= 1) & (np.abs(pr[r["i"]] - pr[r["j"]]) <= 0.8) & (np.abs(r["stat"]) >= 0.1)
+    assert np.array_equal(f["i"], r["i"][ok]) and np.array_equal(f["j"], r["j"][ok])
+
+
+def test_simulate_is_counter_based_and_plausible():
+    parent, brlen = syn.random_tree(8, 11, 0.2)
+    Q, pi = syn.hky85(2.0, [0.4, 0.1, 0.2, 0.3])
+    rates, probs = syn.gamma_rates(0.7, 4)
+    a, ca = O.simulate(parent, brlen, Q, pi, rates, probs, 42, 0, 4000)
+    b, cb = O.simulate(parent, brlen, Q, pi, rates, probs, 42, 1000, 500)
+    assert np.array_equal(a[:, 1000:1500], b) and np.array_equal(ca[1000:1500], cb)
+    c, _ = O.simulate(parent, brlen, Q, pi, rates, probs, 43, 0, 4000)
+    assert not np.array_equal(a, c)
+    freq = np.bincount(a.ravel(), minlength=4) / a.size
+    assert np.allclose(freq, pi, atol=0.03)
+    assert np.allclose(np.bincount(ca, minlength=4) / 4000, 0.25, atol=0.03)
+
+
+def test_null_intra_bins_and_raw():
+    parent, brlen = syn.random_tree(7, 5, 0.15)
+    Q, pi = syn.hky85(2.0, [0.25] * 4)
+    rates, probs = syn.gamma_rates(0.5, 4)
+    rep_cpu, rep_ram = 3, 50
+    T = 7
+    s1 = np.stack([O.simulate(parent, brlen, Q, pi, rates, probs, 9, (2 * i) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    s2 = np.stack([O.simulate(parent, brlen, Q, pi, rates, probs, 9, (2 * i + 1) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    assert s1.shape == (rep_cpu, T, rep_ram)
+    K, nmax = 4, 1.5
+    r = O.null_intra(parent, brlen, Q, pi, rates, probs, "correlation", s1, s2, K, nmax)
+    mask = syn.identity_code_mask(4)
+    m1 = O.map_sites(parent, brlen, Q, pi, rates, probs, s1[1], mask)
+    m2 = O.map_sites(parent, brlen, Q, pi, rates, probs, s2[1], mask)
+    j = 7; k = rep_ram + j
+    st = O.stat("correlation", m1["n"][j], m2["n"][j])
+    assert r["raw"][k, 0] == st or (np.isnan(st) and np.isnan(r["raw"][k, 0]))
+    assert r["raw"][k, 3] == min(m1["norm"][j], m2["norm"][j])
+    assert r["raw"][k, 1] == min(m1["rate_class"][j], m2["rate_class"][j])
+    cat = np.array([O.domain_index(0, nmax, K, x) for x in r["raw"][:, 3]])
+    for b in range(K):
+        seg = r["sorted"][r["bin_offsets"][b]:r["bin_offsets"][b + 1]]
+        assert len(seg) == (cat == b).sum()
+        fin = seg[~np.isnan(seg)]
+        assert np.all(np.diff(fin) >= 0)
+
+
+@pytest.mark.parametrize("linkage,method", [("complete", "complete"), ("single", "single"), ("average", "average")])
+def test_hclust_vs_scipy(linkage, method):
+    from scipy.cluster.hierarchy import linkage as sl
+    from scipy.spatial.distance import squareform
+    rng = np.random.default_rng(1)
+    n = rng.gamma(0.4, 1.0, (25, 60))
+    mat = O.distance_matrix("correlation", n)
+    assert np.allclose(mat, 1 - np.corrcoef(n), atol=1e-13) and np.all(np.diag(mat) == 0)
+    left, right, height = O.hclust(linkage, mat)
+    Z = sl(squareform(mat, checks=False), method=method)
+    assert np.allclose(np.sort(2 * height), np.sort(Z[:, 2]), rtol=1e-12)
+    g = O.groups("correlation", n, np.sqrt((n ** 2).sum(1)), left, right, height, max_size=10)
+    assert all(len(m) <= 10 for m in g["members"])
+    assert np.allclose(g["stat"], 1 - 2 * g["height"])
+    norm = np.sqrt((n ** 2).sum(1))
+    assert np.allclose(g["nmin"], [norm[m].min() for m in g["members"]])
+    if linkage == "complete":
+        # complete linkage: Dmax = max pairwise distance inside the group
+        for m, h in zip(g["members"], g["height"]):
+            assert abs(2 * h - mat[np.ix_(m, m)].max()) < 1e-12
+
+
+def test_groups_compensation_and_euclid():
+    rng = np.random.default_rng(2)
+    n = rng.normal(0, 1, (12, 30)); norm = np.sqrt((n ** 2).sum(1))
+    mat = O.distance_matrix("compensation", n)
+    i, j = 3, 8
+    assert abs(mat[i, j] - np.linalg.norm(n[i] + n[j]) / (norm[i] + norm[j])) < 1e-13
+    left, right, height = O.hclust("complete", mat)
+    g = O.groups("compensation", n, norm, left, right, height, max_size=12)
+    assert len(g["members"]) == 11 and sorted(g["members"][-1]) == list(range(12))
+    for m, s in zip(g["members"], g["stat"]):
+        assert abs(s - (1 - np.linalg.norm(n[m].sum(0)) / norm[m].sum())) < 1e-13
+    me = O.distance_matrix("euclidian", n)
+    assert abs(me[i, j] - np.linalg.norm(n[i] - n[j])) < 1e-13

@@ -1,0 +1,250 @@
+"""ctypes binding of libcomap_b200.so -- the C ABI of include/comap_b200.h.
+
+Thin, explicit and numpy-only; the CUDA library is the product, this file only marshals
+arrays.  Loading fails loudly when the library has not been built (no CPU fallback).
+"""
+import ctypes as C
+import os
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcomap_b200.so")
+
+STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "compensation": 4}
+DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
+LINK = {"complete": 0, "single": 1, "average": 2}
+COUNT = {"uniformization": 0, "decomposition": 1}
+
+# every symbol include/comap_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = [
+    "cmb_last_error", "cmb_version", "cmb_host_alloc", "cmb_host_free", "cmb_ctx_create",
+    "cmb_ctx_destroy", "cmb_sync", "cmb_set_tree", "cmb_set_model", "cmb_set_alignment", "cmb_map",
+    "cmb_simulate", "cmb_null_intra", "cmb_null_intra_from_alignments", "cmb_null_samples_dev",
+    "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_distance_matrix", "cmb_cluster",
+    "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
+    "cmb_launch_count",
+]
+
+
+class Filters(C.Structure):
+    _fields_ = [("min_rate_class", C.c_int32), ("max_rate_class_diff", C.c_int32),
+                ("min_rate", C.c_double), ("max_rate_diff", C.c_double), ("min_stat", C.c_double)]
+
+
+_lib = None
+
+
+def load():
+    """Loads the CUDA library; raises if it is missing (build with python -m comap_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libcomap_b200.so is not built (python -m comap_b200.build); "
+                               "comap_b200 has no CPU fallback")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.cmb_last_error.restype = C.c_char_p
+        _lib.cmb_launch_count.restype = C.c_int64
+    return _lib
+
+
+def _p(a, t):
+    return None if a is None else a.ctypes.data_as(C.POINTER(t))
+
+
+def _d(a):
+    return _p(a, C.c_double)
+
+
+def _i32(a):
+    return _p(a, C.c_int32)
+
+
+def _i64(a):
+    return _p(a, C.c_int64)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class Context:
+    """One GPU, one stream.  Mirrors the reference's flow: set tree / model / alignment, map,
+    null distribution, pairs or clustering (CoMap.cpp:96-737)."""
+
+    def __init__(self, device=-1, stream=None):
+        self.lib = load()
+        h = C.c_void_p()
+        self._chk(self.lib.cmb_ctx_create(int(device), C.c_void_p(stream), C.byref(h)))
+        self.h = h
+        self.S = self.B = self.T = 0
+
+    def _chk(self, rc):
+        if rc != 0:
+            raise RuntimeError("comap_b200: " + self.lib.cmb_last_error().decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.cmb_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        self._chk(self.lib.cmb_sync(self.h))
+
+    # ------------------------------------------------------------------ setup
+    def set_tree(self, parent, brlen):
+        parent = np.ascontiguousarray(parent, dtype=np.int32)
+        brlen = _f64(brlen)
+        self._chk(self.lib.cmb_set_tree(self.h, len(parent), _i32(parent), _d(brlen)))
+        has_child = np.zeros(len(parent), bool)
+        has_child[parent[parent >= 0]] = True
+        self.T = int((~has_child).sum())
+        self.B = len(parent) - 1
+
+    def set_model(self, Q, pi, rates, probs, count_method="uniformization", weights=None):
+        Q, pi, rates, probs = _f64(Q), _f64(pi), _f64(rates), _f64(probs)
+        w = None if weights is None else _f64(weights)
+        self.A, self.C = len(pi), len(rates)
+        self._chk(self.lib.cmb_set_model(self.h, len(pi), _d(Q), _d(pi), len(rates), _d(rates), _d(probs),
+                                         COUNT[count_method], _d(w)))
+
+    def set_alignment(self, codes, code_mask):
+        codes = np.ascontiguousarray(codes, dtype=np.uint8)
+        code_mask = np.ascontiguousarray(code_mask, dtype=np.uint32)
+        T, S = codes.shape
+        if T != self.T:
+            raise ValueError("alignment has %d rows, tree has %d leaves" % (T, self.T))
+        self._chk(self.lib.cmb_set_alignment(self.h, C.c_int64(S), _p(codes, C.c_uint8), len(code_mask),
+                                             _p(code_mask, C.c_uint32)))
+        self.S = S
+
+    # ------------------------------------------------------------------ mapping
+    def map(self, want_vectors=True):
+        S, B = self.S, self.B
+        n = np.empty((S, B)) if want_vectors else None
+        norm = np.empty(S); pr = np.empty(S); rc = np.empty(S, np.int32); ll = np.empty(S)
+        self._chk(self.lib.cmb_map(self.h, _d(n), _d(norm), _d(pr), _i32(rc), _d(ll)))
+        return dict(n=n, norm=norm, post_rate=pr, rate_class=rc, loglik=ll)
+
+    # ------------------------------------------------------------------ simulation / null
+    def simulate(self, seed, first_site, n, weighted_classes=False):
+        states = np.empty((self.T, n), np.uint8); cls = np.empty(n, np.int32)
+        self._chk(self.lib.cmb_simulate(self.h, C.c_uint64(seed), C.c_int64(first_site), C.c_int64(n),
+                                        int(weighted_classes), _p(states, C.c_uint8), _i32(cls)))
+        return states, cls
+
+    def null_intra(self, stat, seed, rep_cpu, rep_ram, K=10, nmax=-1.0, rep_begin=0, rep_end=None,
+                   weighted_classes=False, want_raw=False):
+        rep_end = rep_cpu if rep_end is None else rep_end
+        raw = np.empty(((rep_end - rep_begin) * rep_ram, 4)) if want_raw else None
+        self._chk(self.lib.cmb_null_intra(self.h, STAT[stat], C.c_uint64(seed), rep_cpu, rep_ram, rep_begin,
+                                          rep_end, int(weighted_classes), K, C.c_double(nmax), _d(raw)))
+        return raw
+
+    def null_intra_from_alignments(self, stat, sim1, sim2, K=10, nmax=-1.0, want_raw=True):
+        sim1 = np.ascontiguousarray(sim1, np.uint8); sim2 = np.ascontiguousarray(sim2, np.uint8)
+        rep_cpu, T, rep_ram = sim1.shape
+        raw = np.empty((rep_cpu * rep_ram, 4)) if want_raw else None
+        self._chk(self.lib.cmb_null_intra_from_alignments(self.h, STAT[stat], rep_cpu, rep_ram,
+                                                          _p(sim1, C.c_uint8), _p(sim2, C.c_uint8), K,
+                                                          C.c_double(nmax), _d(raw)))
+        return raw
+
+    def null_samples_dev(self):
+        s = C.c_void_p(); m = C.c_void_p(); n = C.c_int64()
+        self._chk(self.lib.cmb_null_samples_dev(self.h, C.byref(s), C.byref(m), C.byref(n)))
+        return s.value, m.value, n.value
+
+    def null_load_dev(self, stat_ptr, nmin_ptr, n, K, nmax=-1.0):
+        self._chk(self.lib.cmb_null_load_dev(self.h, C.c_void_p(stat_ptr), C.c_void_p(nmin_ptr), C.c_int64(n), K,
+                                             C.c_double(nmax)))
+
+    def null_get(self):
+        K = C.c_int32(); nmax = C.c_double()
+        self._chk(self.lib.cmb_null_get(self.h, C.byref(K), C.byref(nmax), None, None, C.c_int64(0)))
+        offs = np.zeros(K.value + 1, np.int64)
+        self._chk(self.lib.cmb_null_get(self.h, C.byref(K), C.byref(nmax), _i64(offs), None, C.c_int64(0)))
+        srt = np.empty(max(1, offs[-1]))
+        self._chk(self.lib.cmb_null_get(self.h, C.byref(K), C.byref(nmax), _i64(offs), _d(srt), C.c_int64(len(srt))))
+        return dict(K=K.value, nmax=nmax.value, bin_offsets=offs, sorted=srt[:offs[-1]])
+
+    # ------------------------------------------------------------------ pairs
+    def pairs(self, stat, use_null=True, filters=None, shard_index=0, shard_count=1, columns=None, capacity=None):
+        """columns: subset of {'i','j','stat','rcmin','prmin','nmin','pvalue','nsim'} (default: all)."""
+        S = self.S
+        cap = S * (S - 1) // 2 if capacity is None else capacity
+        cols = set(columns) if columns else {"i", "j", "stat", "rcmin", "prmin", "nmin", "pvalue", "nsim"}
+        if not use_null:
+            cols -= {"pvalue", "nsim"}
+        f = Filters(0, -1, 0.0, -1.0, 0.0)
+        if filters:
+            for k, v in filters.items():
+                setattr(f, k, v)
+        mk = lambda name, dt: np.empty(cap, dt) if name in cols else None
+        oi, oj = mk("i", np.int32), mk("j", np.int32)
+        st, rcm, prm, nm = mk("stat", np.float64), mk("rcmin", np.int32), mk("prmin", np.float64), mk("nmin", np.float64)
+        pv, ns = mk("pvalue", np.float64), mk("nsim", np.int64)
+        nr = C.c_int64()
+        self._chk(self.lib.cmb_pairs(self.h, STAT[stat], C.byref(f), int(use_null), shard_index, shard_count,
+                                     C.c_int64(cap), _i32(oi), _i32(oj), _d(st), _i32(rcm), _d(prm), _d(nm), _d(pv),
+                                     _i64(ns), C.byref(nr)))
+        k = nr.value
+        out = dict(i=oi, j=oj, stat=st, rcmin=rcm, prmin=prm, nmin=nm, pvalue=pv, nsim=ns)
+        return {name: (a[:k] if a is not None else None) for name, a in out.items()}, k
+
+    # ------------------------------------------------------------------ clustering
+    def distance_matrix(self, dist, want=True):
+        mat = np.empty((self.S, self.S)) if want else None
+        self._chk(self.lib.cmb_distance_matrix(self.h, DIST[dist], _d(mat)))
+        return mat
+
+    def cluster(self, linkage):
+        S = self.S
+        left = np.empty(S - 1, np.int32); right = np.empty(S - 1, np.int32); height = np.empty(S - 1)
+        self._chk(self.lib.cmb_cluster(self.h, LINK[linkage], _i32(left), _i32(right), _d(height)))
+        return left, right, height
+
+    def groups(self, dist, max_size):
+        S = self.S
+        members = np.empty(max(1, (S - 1) * max_size), np.int32); offs = np.zeros(S + 1, np.int64)
+        gh = np.empty(S); gs = np.empty(S); gn = np.empty(S); ng = C.c_int64()
+        self._chk(self.lib.cmb_groups(self.h, DIST[dist], max_size, _i32(members), _i64(offs), _d(gh), _d(gs),
+                                      _d(gn), C.byref(ng)))
+        k = ng.value
+        return dict(members=[members[offs[g]:offs[g + 1]].copy() for g in range(k)], height=gh[:k], stat=gs[:k],
+                    nmin=gn[:k])
+
+    def cluster_null(self, dist, linkage, seed, rep_begin, rep_end, max_size, weighted_classes=False):
+        S = self.S
+        nrep = rep_end - rep_begin
+        cap_rows = nrep * (S - 1); cap_mem = cap_rows * max_size
+        rep = np.empty(cap_rows, np.int32); size = np.empty(cap_rows, np.int32)
+        dmax = np.empty(cap_rows); st = np.empty(cap_rows); nm = np.empty(cap_rows)
+        members = np.empty(max(1, cap_mem), np.int32); offs = np.zeros(cap_rows + 1, np.int64); nr = C.c_int64()
+        self._chk(self.lib.cmb_cluster_null(self.h, DIST[dist], LINK[linkage], C.c_uint64(seed), rep_begin, rep_end,
+                                            int(weighted_classes), max_size, C.c_int64(cap_rows), C.c_int64(cap_mem),
+                                            _i32(rep), _i32(size), _d(dmax), _d(st), _d(nm), _i32(members), _i64(offs),
+                                            C.byref(nr)))
+        k = nr.value
+        return dict(rep=rep[:k], size=size[:k], dmax=dmax[:k], stat=st[:k], nmin=nm[:k],
+                    members=[members[offs[g]:offs[g + 1]].copy() for g in range(k)])
+
+    # ------------------------------------------------------------------ measurement
+    def profile_enable(self, on=True):
+        self.lib.cmb_profile_enable(self.h, int(on))
+
+    def profile_reset(self):
+        self._chk(self.lib.cmb_profile_reset(self.h))
+
+    def profile_get(self, name):
+        ms = C.c_double(); n = C.c_int64()
+        self._chk(self.lib.cmb_profile_get(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self):
+        return int(self.lib.cmb_launch_count(self.h))

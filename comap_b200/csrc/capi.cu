@@ -1,0 +1,362 @@
+// C ABI of libcomap_b200.so (include/comap_b200.h): context, tree/model/alignment setup,
+// mapping.  The statistics / null / clustering entry points live in capi_stats.cu.
+#include "../../include/comap_b200.h"
+#include "context.h"
+#include <cmath>
+#include <cstring>
+
+namespace cmb {
+
+thread_local std::string g_last_error;
+
+void DevBuf::reserve(size_t bytes) {
+  if (bytes <= cap) return;
+  release();
+  size_t want = (bytes + 255) & ~size_t(255);
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    p = nullptr;
+    fail("cudaMalloc of %zu bytes failed: %s", want, cudaGetErrorString(e));
+  }
+  cap = want;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  cap = 0;
+}
+
+void DevStream::upload(const OpStream& s, cudaStream_t st) {
+  n_chunks = (uint32_t)s.chunk_off.size();
+  cap = (s.chunk_cap + 127) & ~127u;
+  bytes.reserve(s.bytes.size());
+  off.reserve(sizeof(uint32_t) * n_chunks);
+  nbytes.reserve(sizeof(uint32_t) * n_chunks);
+  nrec.reserve(sizeof(uint32_t) * n_chunks);
+  CMB_CUDA(cudaMemcpyAsync(bytes.p, s.bytes.data(), s.bytes.size(), cudaMemcpyHostToDevice, st));
+  CMB_CUDA(cudaMemcpyAsync(off.p, s.chunk_off.data(), sizeof(uint32_t) * n_chunks, cudaMemcpyHostToDevice, st));
+  CMB_CUDA(cudaMemcpyAsync(nbytes.p, s.chunk_bytes.data(), sizeof(uint32_t) * n_chunks, cudaMemcpyHostToDevice, st));
+  CMB_CUDA(cudaMemcpyAsync(nrec.p, s.chunk_nrec.data(), sizeof(uint32_t) * n_chunks, cudaMemcpyHostToDevice, st));
+  CMB_CUDA(cudaStreamSynchronize(st)); // host vectors may go away
+}
+void DevStream::release() {
+  bytes.release(); off.release(); nbytes.release(); nrec.release();
+}
+
+int64_t pad_sites(int64_t n) { return (n + 255) / 256 * 256; }
+
+void Context::require_tree_model() const {
+  if (!have_tree) fail("no tree: call cmb_set_tree first");
+  if (!have_model) fail("no model: call cmb_set_model first");
+}
+
+void Context::ensure_streams() {
+  require_tree_model();
+  if (streams_ready) return;
+  build_model_tables(tables, A, Q.data(), pi.data(), C, rates.data(), probs.data(), count_method,
+                     have_weights ? weights.data() : nullptr, tree.B, tree.brlen.data());
+  int cbmax = map_class_block(A, C);
+  class_blocks.clear();
+  for (int c0 = 0; c0 < C; c0 += cbmax) class_blocks.push_back({c0, std::min(cbmax, C - c0)});
+  for (auto& s : down_streams) s.release();
+  for (auto& s : up_streams) s.release();
+  down_streams.assign(class_blocks.size(), DevStream());
+  up_streams.assign(class_blocks.size(), DevStream());
+  for (size_t i = 0; i < class_blocks.size(); i++) {
+    OpStream os;
+    build_down_stream(os, tree, tables, class_blocks[i].first, class_blocks[i].second);
+    down_streams[i].upload(os, stream);
+    build_up_stream(os, tree, tables, class_blocks[i].first, class_blocks[i].second);
+    up_streams[i].upload(os, stream);
+  }
+  {
+    OpStream os;
+    build_sim_stream(os, tree, tables);
+    sim_stream.upload(os, stream);
+  }
+  d_pi.reserve(sizeof(double) * A);
+  d_rates.reserve(sizeof(double) * C);
+  d_probs.reserve(sizeof(double) * C);
+  CMB_CUDA(cudaMemcpyAsync(d_pi.p, pi.data(), sizeof(double) * A, cudaMemcpyHostToDevice, stream));
+  CMB_CUDA(cudaMemcpyAsync(d_rates.p, rates.data(), sizeof(double) * C, cudaMemcpyHostToDevice, stream));
+  CMB_CUDA(cudaMemcpyAsync(d_probs.p, probs.data(), sizeof(double) * C, cudaMemcpyHostToDevice, stream));
+  std::vector<uint32_t> ident(256, (A >= 32) ? 0xffffffffu : ((1u << A) - 1u));
+  for (int k = 0; k < A; k++) ident[k] = 1u << k;
+  d_identity_mask.reserve(sizeof(uint32_t) * 256);
+  CMB_CUDA(cudaMemcpyAsync(d_identity_mask.p, ident.data(), sizeof(uint32_t) * 256, cudaMemcpyHostToDevice, stream));
+  CMB_CUDA(cudaStreamSynchronize(stream));
+  streams_ready = true;
+}
+
+MapModel Context::map_model() const {
+  MapModel m;
+  m.A = A; m.C = C; m.B = tree.B; m.n_slots = tree.n_slots;
+  m.code_mask = d_code_mask.as<uint32_t>();
+  m.pi = d_pi.as<double>();
+  m.rates = d_rates.as<double>();
+  m.probs = d_probs.as<double>();
+  return m;
+}
+
+void Context::prof_begin(const char* name) {
+  if (!prof.enabled) return;
+  cudaEvent_t a, b;
+  CMB_CUDA(cudaEventCreate(&a));
+  CMB_CUDA(cudaEventCreate(&b));
+  CMB_CUDA(cudaEventRecord(a, stream));
+  prof.pending.emplace_back(name, a, b, 0);
+}
+void Context::prof_end(int launches) {
+  prof.total_launches += launches;
+  if (!prof.enabled) return;
+  auto& t = prof.pending.back();
+  std::get<3>(t) = launches;
+  CMB_CUDA(cudaEventRecord(std::get<2>(t), stream));
+}
+void Context::prof_collect() {
+  if (prof.pending.empty()) return;
+  CMB_CUDA(cudaStreamSynchronize(stream));
+  for (auto& t : prof.pending) {
+    float ms = 0.f;
+    CMB_CUDA(cudaEventElapsedTime(&ms, std::get<1>(t), std::get<2>(t)));
+    auto& e = prof.entries[std::get<0>(t)];
+    e.ms += ms;
+    e.launches += std::get<3>(t);
+    cudaEventDestroy(std::get<1>(t));
+    cudaEventDestroy(std::get<2>(t));
+  }
+  prof.pending.clear();
+}
+
+// Down pass for every class block, site likelihoods, then up pass + contraction.
+void Context::run_map(const MapBuffers& b, bool simulated) {
+  MapModel m = map_model();
+  if (simulated) m.code_mask = d_identity_mask.as<uint32_t>();
+  prof_begin("map_down");
+  for (size_t i = 0; i < class_blocks.size(); i++)
+    launch_map_down(m, b, down_streams[i], class_blocks[i].first, class_blocks[i].second, stream);
+  launch_map_finish(m, b, stream);
+  prof_end((int)class_blocks.size() + 1);
+  prof_begin("map_up");
+  bool single = class_blocks.size() == 1;
+  for (size_t i = 0; i < class_blocks.size(); i++)
+    launch_map_up(m, b, up_streams[i], class_blocks[i].first, class_blocks[i].second, i > 0, single, stream);
+  if (!single) launch_map_norms(m, b, stream);
+  prof_end((int)class_blocks.size() + (single ? 0 : 1));
+}
+
+} // namespace cmb
+
+using namespace cmb;
+
+#define CMB_TRY try {
+#define CMB_CATCH                                   \
+  }                                                 \
+  catch (const std::exception& e) {                 \
+    g_last_error = e.what();                        \
+    return 1;                                       \
+  }                                                 \
+  catch (...) {                                     \
+    g_last_error = "unknown error";                 \
+    return 1;                                       \
+  }                                                 \
+  return 0;
+
+struct cmb_ctx { Context c; };
+
+extern "C" {
+
+const char* cmb_last_error(void) { return g_last_error.c_str(); }
+int cmb_version(void) { return 100; }
+
+int cmb_host_alloc(uint64_t bytes, void** out) {
+  CMB_TRY
+  CMB_CUDA(cudaMallocHost(out, bytes));
+  CMB_CATCH
+}
+int cmb_host_free(void* p) {
+  CMB_TRY
+  CMB_CUDA(cudaFreeHost(p));
+  CMB_CATCH
+}
+
+int cmb_ctx_create(int device, void* stream, cmb_ctx** out) {
+  CMB_TRY
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0)
+    fail("no CUDA device available (%s); comap_b200 has no CPU fallback", cudaGetErrorString(e));
+  if (device < 0) CMB_CUDA(cudaGetDevice(&device));
+  if (device >= n) fail("device %d out of range (%d devices)", device, n);
+  CMB_CUDA(cudaSetDevice(device));
+  cmb_ctx* ctx = new cmb_ctx();
+  ctx->c.device = device;
+  if (stream) ctx->c.stream = (cudaStream_t)stream;
+  else {
+    CMB_CUDA(cudaStreamCreateWithFlags(&ctx->c.stream, cudaStreamNonBlocking));
+    ctx->c.own_stream = true;
+  }
+  *out = ctx;
+  CMB_CATCH
+}
+
+int cmb_ctx_destroy(cmb_ctx* ctx) {
+  CMB_TRY
+  if (!ctx) return 0;
+  Context& c = ctx->c;
+  cudaSetDevice(c.device);
+  cudaStreamSynchronize(c.stream);
+  for (auto& t : c.prof.pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
+  DevBuf* bufs[] = {&c.d_code_mask, &c.d_pi, &c.d_rates, &c.d_probs, &c.d_tips, &c.d_D, &c.d_Lc, &c.d_invL,
+                    &c.d_loglik, &c.d_pr, &c.d_rc, &c.d_out, &c.d_sum, &c.d_sumsq, &c.s_tips[0], &c.s_tips[1],
+                    &c.s_D, &c.s_Lc, &c.s_invL, &c.s_loglik, &c.s_pr[0], &c.s_pr[1], &c.s_rc[0], &c.s_rc[1],
+                    &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
+                    &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
+                    &c.d_dist, &c.scratch, &c.scratch2, &c.staging};
+  for (DevBuf* b : bufs) b->release();
+  for (auto& s : c.down_streams) s.release();
+  for (auto& s : c.up_streams) s.release();
+  c.sim_stream.release();
+  if (c.own_stream) cudaStreamDestroy(c.stream);
+  delete ctx;
+  CMB_CATCH
+}
+
+int cmb_sync(cmb_ctx* ctx) {
+  CMB_TRY
+  CMB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  CMB_CATCH
+}
+
+int cmb_set_tree(cmb_ctx* ctx, int32_t n_nodes, const int32_t* parent, const double* brlen) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  build_tree(c.tree, n_nodes, parent, brlen);
+  c.have_tree = true;
+  c.streams_ready = false;
+  c.mapped = false;
+  c.have_alignment = false;
+  c.null.ready = false;
+  CMB_CATCH
+}
+
+int cmb_set_model(cmb_ctx* ctx, int32_t A, const double* Q, const double* pi, int32_t C, const double* rates,
+                  const double* probs, int32_t count_method, const double* weight_xy) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (A < 2 || A > 32) fail("cmb_set_model: A must be in 2..32 (got %d)", A);
+  if (C < 1 || C > 32) fail("cmb_set_model: C must be in 1..32 (got %d)", C);
+  map_class_block(A, C); // validates that kernels exist for this alphabet size
+  c.A = A; c.C = C; c.count_method = count_method;
+  c.Q.assign(Q, Q + (size_t)A * A);
+  c.pi.assign(pi, pi + A);
+  c.rates.assign(rates, rates + C);
+  c.probs.assign(probs, probs + C);
+  c.have_weights = weight_xy != nullptr;
+  if (weight_xy) c.weights.assign(weight_xy, weight_xy + (size_t)A * A);
+  c.have_model = true;
+  c.streams_ready = false;
+  c.mapped = false;
+  c.null.ready = false;
+  if (c.have_tree) c.ensure_streams(); // validates reversibility etc. now
+  CMB_CATCH
+}
+
+int cmb_set_alignment(cmb_ctx* ctx, int64_t S, const uint8_t* codes, int32_t n_codes, const uint32_t* code_mask) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (!c.have_tree) fail("cmb_set_alignment: call cmb_set_tree first");
+  if (S < 1) fail("cmb_set_alignment: empty alignment");
+  if (n_codes < 1 || n_codes > 256) fail("cmb_set_alignment: n_codes must be in 1..256");
+  const int T = c.tree.n_leaves;
+  for (int64_t i = 0; i < (int64_t)T * S; i++)
+    if (codes[i] >= n_codes) fail("cmb_set_alignment: code %d out of range at row %lld", codes[i], (long long)(i / S));
+  c.S = S;
+  c.S_pad = pad_sites(S);
+  c.code_mask.assign(256, 0);
+  for (int k = 0; k < n_codes; k++) c.code_mask[k] = code_mask[k];
+  for (int k = n_codes; k < 256; k++) c.code_mask[k] = code_mask[0];
+  c.d_code_mask.reserve(sizeof(uint32_t) * 256);
+  CMB_CUDA(cudaMemcpyAsync(c.d_code_mask.p, c.code_mask.data(), sizeof(uint32_t) * 256, cudaMemcpyHostToDevice, c.stream));
+  c.d_tips.reserve((size_t)T * c.S_pad);
+  CMB_CUDA(cudaMemsetAsync(c.d_tips.p, 0, (size_t)T * c.S_pad, c.stream));
+  CMB_CUDA(cudaMemcpy2DAsync(c.d_tips.p, c.S_pad, codes, S, S, T, cudaMemcpyHostToDevice, c.stream));
+  CMB_CUDA(cudaStreamSynchronize(c.stream));
+  c.have_alignment = true;
+  c.mapped = false;
+  CMB_CATCH
+}
+
+int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_t* rate_class, double* loglik) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (!c.have_alignment) fail("cmb_map: call cmb_set_alignment first");
+  c.ensure_streams();
+  const int64_t S = c.S, Sp = c.S_pad;
+  const int A = c.A, C = c.C, B = c.tree.B;
+  c.d_D.reserve(sizeof(double) * (size_t)c.tree.n_slots * C * A * Sp);
+  c.d_Lc.reserve(sizeof(double) * (size_t)C * Sp);
+  c.d_invL.reserve(sizeof(double) * Sp);
+  c.d_loglik.reserve(sizeof(double) * Sp);
+  c.d_pr.reserve(sizeof(double) * Sp);
+  c.d_rc.reserve(sizeof(int32_t) * Sp);
+  c.d_out.reserve(sizeof(double) * (size_t)B * Sp);
+  c.d_sum.reserve(sizeof(double) * Sp);
+  c.d_sumsq.reserve(sizeof(double) * Sp);
+  MapBuffers b;
+  b.n = S; b.n_pad = Sp;
+  b.tips = c.d_tips.as<uint8_t>();
+  b.D = c.d_D.as<double>(); b.Lc = c.d_Lc.as<double>(); b.invL = c.d_invL.as<double>();
+  b.loglik = c.d_loglik.as<double>(); b.post_rate = c.d_pr.as<double>(); b.rate_class = c.d_rc.as<int32_t>();
+  b.out = c.d_out.as<double>(); b.sum = c.d_sum.as<double>(); b.sumsq = c.d_sumsq.as<double>();
+  c.run_map(b, false);
+  // norms are needed on the host by the null (Domain upper bound) and for the caller
+  c.h_norm.resize(S);
+  CMB_CUDA(cudaMemcpyAsync(c.h_norm.data(), c.d_sumsq.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+  if (n_out) {
+    c.scratch.reserve(sizeof(double) * (size_t)S * B);
+    launch_transpose_out(b.out, B, S, Sp, c.scratch.as<double>(), c.stream);
+    c.prof.total_launches += 1;
+    CMB_CUDA(cudaMemcpyAsync(n_out, c.scratch.p, sizeof(double) * (size_t)S * B, cudaMemcpyDeviceToHost, c.stream));
+  }
+  if (post_rate) CMB_CUDA(cudaMemcpyAsync(post_rate, c.d_pr.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+  if (rate_class) CMB_CUDA(cudaMemcpyAsync(rate_class, c.d_rc.p, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, c.stream));
+  if (loglik) CMB_CUDA(cudaMemcpyAsync(loglik, c.d_loglik.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaStreamSynchronize(c.stream));
+  c.max_norm = 0.;
+  for (int64_t i = 0; i < S; i++) {
+    c.h_norm[i] = std::sqrt(c.h_norm[i]);
+    if (c.h_norm[i] > c.max_norm) c.max_norm = c.h_norm[i];
+  }
+  if (norm) std::memcpy(norm, c.h_norm.data(), sizeof(double) * S);
+  c.mapped = true;
+  c.have_dist = false;
+  CMB_CATCH
+}
+
+int cmb_profile_enable(cmb_ctx* ctx, int32_t on) {
+  ctx->c.prof.enabled = on != 0;
+  return 0;
+}
+int cmb_profile_reset(cmb_ctx* ctx) {
+  CMB_TRY
+  ctx->c.prof_collect();
+  ctx->c.prof.entries.clear();
+  ctx->c.prof.total_launches = 0;
+  CMB_CATCH
+}
+int cmb_profile_get(cmb_ctx* ctx, const char* name, double* ms, int64_t* launches) {
+  CMB_TRY
+  ctx->c.prof_collect();
+  auto it = ctx->c.prof.entries.find(name);
+  if (ms) *ms = it == ctx->c.prof.entries.end() ? 0. : it->second.ms;
+  if (launches) *launches = it == ctx->c.prof.entries.end() ? 0 : it->second.launches;
+  CMB_CATCH
+}
+int64_t cmb_launch_count(cmb_ctx* ctx) { return ctx->c.prof.total_launches; }
+
+} // extern "C"

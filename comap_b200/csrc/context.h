@@ -1,0 +1,85 @@
+// The context object behind cmb_ctx: one GPU, one stream, device arenas.
+#pragma once
+#include "kernels.h"
+#include <memory>
+
+namespace cmb {
+
+struct Profile {
+  struct Entry { double ms = 0.; int64_t launches = 0; };
+  std::map<std::string, Entry> entries;
+  std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t, int>> pending;
+  bool enabled = false;
+  int64_t total_launches = 0;
+};
+
+struct NullState {            // binned, sorted null distribution (device + host mirror)
+  int K = 0;
+  double nmax = 0.;
+  int64_t n_samples = 0;      // unbinned samples held in stat/nmin
+  DevBuf stat, nmin;          // [n_samples] raw samples of this shard
+  DevBuf sorted;              // [bin_off[K]] ascending within each bin
+  DevBuf bin_off_dev;         // int64 [K+1]
+  std::vector<int64_t> bin_off;
+  bool ready = false;
+};
+
+struct Context {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+
+  Tree tree;
+  bool have_tree = false;
+  ModelTables tables;
+  bool have_model = false;
+  // model inputs kept to rebuild tables when the tree changes
+  std::vector<double> Q, pi, rates, probs, weights;
+  int A = 0, C = 0, count_method = 0;
+  bool have_weights = false;
+
+  // device-resident model + op streams
+  DevBuf d_code_mask, d_pi, d_rates, d_probs;
+  std::vector<DevStream> down_streams, up_streams; // one per class block
+  std::vector<std::pair<int, int>> class_blocks;   // (c0, cb)
+  DevStream sim_stream;
+  bool streams_ready = false;
+
+  // observed alignment + its mapping
+  int64_t S = 0, S_pad = 0;
+  DevBuf d_tips;                 // [T][S_pad]
+  std::vector<uint32_t> code_mask;
+  bool have_alignment = false, mapped = false;
+  DevBuf d_D, d_Lc, d_invL, d_loglik, d_pr, d_rc, d_out, d_sum, d_sumsq;
+  std::vector<double> h_norm;    // host copies used by null / pairs
+  double max_norm = 0.;
+
+  // scratch for simulated batches
+  DevBuf s_tips[2], s_D, s_Lc, s_invL, s_loglik, s_pr[2], s_rc[2], s_out[2], s_sum[2], s_sumsq[2], s_cls;
+  DevBuf d_identity_mask;
+
+  NullState null;
+
+  // clustering
+  DevBuf d_dist;                 // [S][S]
+  bool have_dist = false;
+  std::vector<int32_t> h_left, h_right;
+  std::vector<double> h_height;
+  bool have_dendro = false;
+
+  DevBuf scratch, scratch2, staging;
+  Profile prof;
+
+  void require_tree_model() const;
+  void ensure_streams();
+  MapModel map_model() const;
+  // maps n sites whose tips are at `tips` ([T][n_pad]); buffers given explicitly
+  void run_map(const MapBuffers& b, bool simulated);
+  void prof_begin(const char* name);
+  void prof_end(int launches);
+  void prof_collect();
+};
+
+int64_t pad_sites(int64_t n);
+
+} // namespace cmb

@@ -1,0 +1,123 @@
+// K3: on-device sequence simulation for the parametric-bootstrap null.
+//
+// Replaces NonHomogeneousSequenceSimulator::simulate(n) in discrete-rate mode (call sites
+// CoMap.cpp:209-219, AnalysisTools.cpp:591,614, ClusterTools.cpp:224):
+// root state ~ pi (first i with r <= cumulative pi), rate class uniform over classes
+// (upstream behaviour) or ~ probs, child state by linear inverse-CDF over the cumulative
+// row of P_c(b).  Randomness is counter based -- Philox4x32-10 keyed (seed; site, node,
+// tag) -- so a site's column does not depend on batching, GPU count or launch geometry.
+// One thread per site walks the precompiled pre-order stream (schedule.cpp); tips are
+// written [row][site] (site contiguous) in the layout K1 reads.
+#include "device_utils.cuh"
+#include "kernels.h"
+
+namespace cmb {
+namespace {
+
+constexpr int NT = 256;
+
+struct SimParams {
+  const unsigned char* src;
+  const uint32_t *off, *bytes, *nrec;
+  uint32_t n_chunks, cap;
+  int A, C, root_node, weighted;
+  uint64_t seed;
+  int64_t base, group, stride; // site id = base + (idx / group) * stride + idx % group
+  int64_t n, n_pad;
+  const double *pi, *probs;
+  uint8_t* tips;
+  int32_t* classes;
+};
+
+__device__ __forceinline__ int draw_state(const double* __restrict__ row, int A, double u) {
+  int y = A - 1;
+  for (int k = A - 1; k >= 0; k--)
+    if (u < row[k]) y = k;
+  return y;
+}
+
+__global__ void __launch_bounds__(NT) k3_simulate(SimParams p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x;
+  const bool live = idx < p.n;
+  const int64_t ii = live ? idx : p.n - 1;
+  const uint64_t site = (uint64_t)(p.base + (ii / p.group) * p.stride + ii % p.group);
+  ChunkStream cs{p.src, p.off, p.bytes, p.n_chunks, p.cap, nullptr, nullptr};
+  cs.start(smem + 128, reinterpret_cast<uint64_t*>(smem));
+  const int A = p.A, C = p.C, AA = A * A;
+
+  int st;
+  {
+    double r = philox_u01(p.seed, site, (uint32_t)p.root_node, 0);
+    st = A - 1;
+    double cp = 0.;
+    bool done = false;
+    for (int i = 0; i < A; i++) {
+      cp += __ldg(p.pi + i);
+      if (!done && r <= cp) { st = i; done = true; }
+    }
+  }
+  int c;
+  {
+    double r = philox_u01(p.seed, site, (uint32_t)p.root_node, 1);
+    if (p.weighted) {
+      c = C - 1;
+      double cq = 0.;
+      bool done = false;
+      for (int i = 0; i < C; i++) {
+        cq += __ldg(p.probs + i);
+        if (!done && r <= cq) { c = i; done = true; }
+      }
+    } else {
+      c = (int)(r * (double)C);
+      if (c >= C) c = C - 1;
+    }
+  }
+  if (live && p.classes) p.classes[idx] = c;
+
+  uint8_t stk[kMaxStack];
+  int sp = 0;
+  const size_t tab = (size_t)C * AA;
+  for (uint32_t k = 0; k < p.n_chunks; k++) {
+    const unsigned char* rp = cs.wait(k);
+    const uint32_t nrec = __ldg(p.nrec + k);
+    for (uint32_t r = 0; r < nrec; r++) {
+      const int4 h0 = *reinterpret_cast<const int4*>(rp);
+      const int4 h1 = *reinterpret_cast<const int4*>(rp + 16);
+      const uint32_t flags = (uint32_t)h0.x;
+      const double* cumA = reinterpret_cast<const double*>(rp + 32);
+      const double* cumB = cumA + tab;
+      rp += (32 + 2 * tab * sizeof(double) + 15) & ~size_t(15);
+      int sa = st, sb = st;
+      if (h0.w >= 0) sa = draw_state(cumA + ((size_t)c * A + st) * A, A, philox_u01(p.seed, site, (uint32_t)h0.w, 0));
+      if (h1.x >= 0) sb = draw_state(cumB + ((size_t)c * A + st) * A, A, philox_u01(p.seed, site, (uint32_t)h1.x, 0));
+      if ((flags & kUpTipA) && live) p.tips[(size_t)h0.y * p.n_pad + idx] = (uint8_t)sa;
+      if ((flags & kUpTipB) && live) p.tips[(size_t)h0.z * p.n_pad + idx] = (uint8_t)sb;
+      if (flags & kUpTakeA) {
+        if (flags & kUpPush) stk[sp++] = (uint8_t)sb;
+        st = sa;
+      } else if (flags & kUpTakeB) st = sb;
+      else if (flags & kUpPop) st = stk[--sp];
+    }
+    cs.release(k);
+  }
+}
+
+} // namespace
+
+void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,
+                     int64_t stride, int64_t n, int64_t n_pad, int weighted, int root_node, uint8_t* tips,
+                     int32_t* classes, cudaStream_t st) {
+  SimParams p;
+  p.src = s.bytes.as<unsigned char>(); p.off = s.off.as<uint32_t>(); p.bytes = s.nbytes.as<uint32_t>();
+  p.nrec = s.nrec.as<uint32_t>(); p.n_chunks = s.n_chunks; p.cap = s.cap;
+  p.A = m.A; p.C = m.C; p.root_node = root_node; p.weighted = weighted; p.seed = seed;
+  p.base = base; p.group = group; p.stride = stride; p.n = n; p.n_pad = n_pad;
+  p.pi = m.pi; p.probs = m.probs; p.tips = tips; p.classes = classes;
+  size_t smem = 128 + 2 * (size_t)s.cap;
+  CMB_CUDA(cudaFuncSetAttribute(k3_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k3_simulate<<<(unsigned)((n + NT - 1) / NT), NT, smem, st>>>(p);
+  CMB_CUDA(cudaGetLastError());
+}
+
+} // namespace cmb

@@ -1,0 +1,287 @@
+// Tree handling and packed op streams for the mapping / simulation kernels.
+//
+// The reference walks TreeTemplate<Node> recursively per call (Bio++
+// DRHomogeneousTreeLikelihood::computeSubtreeLikelihoodPostfix/Prefix,
+// NonHomogeneousSequenceSimulator::evolveInternal; call sites CoETools.cpp:209,
+// AnalysisTools.cpp:591-593).  Here the walk is compiled once per tree into flat, chunked
+// op streams that each CTA streams through shared memory with TMA bulk copies; every
+// record carries the transition / count tables it needs, in the order it needs them.
+#include "common.h"
+#include <algorithm>
+#include <cstring>
+
+namespace cmb {
+
+void build_tree(Tree& t, int n_nodes, const int32_t* parent, const double* brlen) {
+  if (n_nodes < 3) fail("cmb_set_tree: need at least 3 nodes");
+  if (parent[n_nodes - 1] != -1) fail("cmb_set_tree: the last node must be the root (parent -1)");
+  t = Tree();
+  t.n_nodes = n_nodes;
+  t.B = n_nodes - 1;
+  t.parent.assign(parent, parent + n_nodes);
+  t.brlen.assign(n_nodes, 0.);
+  std::vector<std::vector<int>> kids(n_nodes);
+  for (int v = 0; v < n_nodes - 1; v++) {
+    if (parent[v] <= v || parent[v] >= n_nodes)
+      fail("cmb_set_tree: ids must be in post-order (node %d has parent %d)", v, parent[v]);
+    if (!(brlen[v] >= 0.) || !(brlen[v] <= 10000.)) fail("cmb_set_tree: bad branch length at node %d", v);
+    kids[parent[v]].push_back(v);
+    t.brlen[v] = brlen[v] < 1e-6 ? 1e-6 : brlen[v]; // Bio++ lower bound
+  }
+  t.leaf_row.assign(n_nodes, -1);
+  for (int v = 0; v < n_nodes; v++) {
+    if (kids[v].empty()) t.leaf_row[v] = t.n_leaves++;
+    else if (kids[v].size() == 1) fail("cmb_set_tree: node %d has a single child", v);
+  }
+  if (kids[n_nodes - 1].empty()) fail("cmb_set_tree: root is a leaf");
+
+  // binarise: a k-ary node becomes a chain of binary nodes joined by virtual zero-length
+  // edges (P = I, no output row); products are taken in the same child order.
+  t.bin.resize(n_nodes);
+  for (int v = 0; v < n_nodes; v++) {
+    t.bin[v].orig = v;
+    t.bin[v].branch = (v == n_nodes - 1) ? -1 : v;
+    t.bin[v].tip_row = t.leaf_row[v];
+  }
+  for (int v = 0; v < n_nodes; v++) {
+    const auto& k = kids[v];
+    if (k.empty()) continue;
+    int cur = v;
+    for (size_t i = 0; i + 2 < k.size(); i++) {
+      BinNode u;
+      int uid = (int)t.bin.size();
+      t.bin.push_back(u);
+      t.bin[cur].left = k[i];
+      t.bin[cur].right = uid;
+      t.bin[k[i]].parent = cur;
+      t.bin[uid].parent = cur;
+      cur = uid;
+    }
+    t.bin[cur].left = k[k.size() - 2];
+    t.bin[cur].right = k[k.size() - 1];
+    t.bin[k[k.size() - 2]].parent = cur;
+    t.bin[k[k.size() - 1]].parent = cur;
+  }
+  t.bin_root = n_nodes - 1;
+  // leaves below (iterative post-order)
+  {
+    std::vector<std::pair<int, int>> st{{t.bin_root, 0}};
+    while (!st.empty()) {
+      auto [v, phase] = st.back();
+      st.pop_back();
+      BinNode& n = t.bin[v];
+      if (n.left < 0) { n.leaves = 1; continue; }
+      if (phase == 0) {
+        st.push_back({v, 1});
+        st.push_back({n.left, 0});
+        st.push_back({n.right, 0});
+      } else n.leaves = t.bin[n.left].leaves + t.bin[n.right].leaves;
+    }
+  }
+  // down order: post-order, larger child first (its message waits on the stack while the
+  // smaller subtree is processed -> stack depth <= log2(#leaves))
+  {
+    int depth = 0;
+    std::vector<std::pair<int, int>> st{{t.bin_root, 0}};
+    while (!st.empty()) {
+      auto [v, phase] = st.back();
+      st.pop_back();
+      const BinNode& n = t.bin[v];
+      if (n.left < 0) continue;
+      if (phase == 0) {
+        int a = n.left, b = n.right;
+        if (t.bin[b].leaves > t.bin[a].leaves) std::swap(a, b);
+        st.push_back({v, 1});
+        st.push_back({b, 0});
+        st.push_back({a, 0});
+      } else t.down_order.push_back(v);
+    }
+    // slots + depth
+    int sp = 0;
+    for (int v : t.down_order) {
+      BinNode& n = t.bin[v];
+      int a = n.left, b = n.right;
+      if (t.bin[b].leaves > t.bin[a].leaves) std::swap(a, b);
+      if (t.bin[a].left >= 0) sp--; // pop a's message
+      if (v != t.bin_root) {
+        n.slot = t.n_slots++;
+        const BinNode& p = t.bin[n.parent];
+        int pa = p.left, pb = p.right;
+        if (t.bin[pb].leaves > t.bin[pa].leaves) std::swap(pa, pb);
+        if (pa == v) { sp++; depth = std::max(depth, sp); }
+      }
+    }
+    t.down_depth = depth;
+  }
+  // up order: pre-order, smaller child first (the larger one's message waits)
+  {
+    int depth = 0;
+    std::vector<int> st;
+    int v = t.bin_root;
+    while (v >= 0) {
+      t.up_order.push_back(v);
+      const BinNode& n = t.bin[v];
+      int a = n.left, b = n.right;
+      if (t.bin[a].leaves > t.bin[b].leaves) std::swap(a, b);
+      bool ia = t.bin[a].left >= 0, ib = t.bin[b].left >= 0;
+      if (ia) {
+        if (ib) { st.push_back(b); depth = std::max(depth, (int)st.size()); }
+        v = a;
+      } else if (ib) v = b;
+      else if (!st.empty()) { v = st.back(); st.pop_back(); }
+      else v = -1;
+    }
+    t.up_depth = depth;
+  }
+  if (t.down_depth > kMaxStack || t.up_depth > kMaxStack)
+    fail("cmb_set_tree: traversal stack depth %d exceeds %d", std::max(t.down_depth, t.up_depth), kMaxStack);
+}
+
+namespace {
+
+struct Packer {
+  OpStream& s;
+  uint32_t cap;
+  std::vector<unsigned char> cur;
+  uint32_t nrec = 0;
+  Packer(OpStream& s_, uint32_t cap_) : s(s_), cap(cap_) {}
+  void flush() {
+    if (cur.empty()) return;
+    s.chunk_off.push_back((uint32_t)s.bytes.size());
+    s.chunk_bytes.push_back((uint32_t)cur.size());
+    s.chunk_nrec.push_back(nrec);
+    s.chunk_cap = std::max<uint32_t>(s.chunk_cap, (uint32_t)cur.size());
+    s.bytes.insert(s.bytes.end(), cur.begin(), cur.end());
+    cur.clear();
+    nrec = 0;
+  }
+  void add(const std::vector<unsigned char>& rec) {
+    if (!cur.empty() && cur.size() + rec.size() > cap) flush();
+    cur.insert(cur.end(), rec.begin(), rec.end());
+    nrec++;
+  }
+};
+
+void append(std::vector<unsigned char>& rec, const void* p, size_t n) {
+  const unsigned char* b = static_cast<const unsigned char*>(p);
+  rec.insert(rec.end(), b, b + n);
+}
+void pad16(std::vector<unsigned char>& rec) { rec.resize((rec.size() + 15) & ~size_t(15), 0); }
+
+// table of `what` (0 = P, 1 = W, 2 = cumP) for bin node v's edge, classes [c0, c0+cb)
+void append_table(std::vector<unsigned char>& rec, const Tree& t, const ModelTables& mt, int v,
+                  int what, int c0, int cb) {
+  const int A = mt.A;
+  const size_t AA = (size_t)A * A;
+  int br = t.bin[v].branch;
+  if (br >= 0) {
+    const std::vector<double>& src = what == 0 ? mt.P : what == 1 ? mt.W : mt.cumP;
+    append(rec, &src[((size_t)br * mt.C + c0) * AA], sizeof(double) * AA * cb);
+  } else { // virtual edge: P = I, W = 0, cumP = step
+    std::vector<double> tab(AA * cb, 0.);
+    for (int c = 0; c < cb; c++)
+      for (int x = 0; x < A; x++)
+        for (int y = 0; y < A; y++)
+          tab[c * AA + x * A + y] = what == 0 ? (x == y) : what == 1 ? 0. : (y >= x ? 1. : 0.);
+    append(rec, tab.data(), sizeof(double) * tab.size());
+  }
+}
+
+uint32_t chunk_capacity(size_t max_rec) { return (uint32_t)std::max<size_t>(16384, max_rec); }
+
+} // namespace
+
+void build_down_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb) {
+  s = OpStream();
+  std::vector<std::vector<unsigned char>> recs;
+  size_t max_rec = 0;
+  for (int v : t.down_order) {
+    const BinNode& n = t.bin[v];
+    int a = n.left, b = n.right;
+    if (t.bin[b].leaves > t.bin[a].leaves) std::swap(a, b);
+    DownHdr h{};
+    bool ta = t.bin[a].left < 0, tb = t.bin[b].left < 0;
+    h.flags = (ta ? kDownTipA : 0) | (tb ? kDownTipB : 0);
+    h.row_a = ta ? t.bin[a].tip_row : -1;
+    h.row_b = tb ? t.bin[b].tip_row : -1;
+    h.slot = n.slot;
+    bool push = false;
+    if (v == t.bin_root) h.flags |= kDownRoot;
+    else {
+      const BinNode& p = t.bin[n.parent];
+      int pa = p.left, pb = p.right;
+      if (t.bin[pb].leaves > t.bin[pa].leaves) std::swap(pa, pb);
+      push = (pa == v);
+    }
+    if (push) h.flags |= kDownPush;
+    std::vector<unsigned char> rec;
+    append(rec, &h, sizeof h);
+    append_table(rec, t, mt, b, 0, c0, cb);
+    if (ta) append_table(rec, t, mt, a, 0, c0, cb);
+    if (push) append_table(rec, t, mt, v, 0, c0, cb);
+    pad16(rec);
+    max_rec = std::max(max_rec, rec.size());
+    recs.push_back(std::move(rec));
+  }
+  Packer pk(s, chunk_capacity(max_rec));
+  for (auto& r : recs) pk.add(r);
+  pk.flush();
+}
+
+static void up_like_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb, bool sim) {
+  s = OpStream();
+  std::vector<std::vector<unsigned char>> recs;
+  size_t max_rec = 0;
+  std::vector<int> st;
+  for (size_t i = 0; i < t.up_order.size(); i++) {
+    int v = t.up_order[i];
+    const BinNode& n = t.bin[v];
+    int a = n.left, b = n.right;
+    if (t.bin[a].leaves > t.bin[b].leaves) std::swap(a, b);
+    bool ta = t.bin[a].left < 0, tb = t.bin[b].left < 0;
+    UpHdr h{};
+    h.flags = (ta ? kUpTipA : 0) | (tb ? kUpTipB : 0);
+    if (!ta) {
+      h.flags |= kUpTakeA;
+      if (!tb) { h.flags |= kUpPush; st.push_back(b); }
+    } else if (!tb) h.flags |= kUpTakeB;
+    else if (!st.empty()) { h.flags |= kUpPop; st.pop_back(); }
+    if (sim) {
+      h.ref_a = ta ? t.bin[a].tip_row : -1;
+      h.ref_b = tb ? t.bin[b].tip_row : -1;
+      h.out_a = t.bin[a].orig;
+      h.out_b = t.bin[b].orig;
+    } else {
+      h.ref_a = ta ? t.bin[a].tip_row : t.bin[a].slot;
+      h.ref_b = tb ? t.bin[b].tip_row : t.bin[b].slot;
+      h.out_a = t.bin[a].branch;
+      h.out_b = t.bin[b].branch;
+    }
+    std::vector<unsigned char> rec;
+    append(rec, &h, sizeof h);
+    if (sim) {
+      append_table(rec, t, mt, a, 2, 0, mt.C);
+      append_table(rec, t, mt, b, 2, 0, mt.C);
+    } else {
+      append_table(rec, t, mt, a, 0, c0, cb);
+      append_table(rec, t, mt, a, 1, c0, cb);
+      append_table(rec, t, mt, b, 0, c0, cb);
+      append_table(rec, t, mt, b, 1, c0, cb);
+    }
+    pad16(rec);
+    max_rec = std::max(max_rec, rec.size());
+    recs.push_back(std::move(rec));
+  }
+  Packer pk(s, chunk_capacity(max_rec));
+  for (auto& r : recs) pk.add(r);
+  pk.flush();
+}
+
+void build_up_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb) {
+  up_like_stream(s, t, mt, c0, cb, false);
+}
+void build_sim_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
+  up_like_stream(s, t, mt, 0, mt.C, true);
+}
+
+} // namespace cmb

@@ -1,0 +1,203 @@
+// K0: per (branch, class) transition and count tables, host fp64.
+//
+// Replaces what Bio++ evaluates inside DRHomogeneousTreeLikelihood (pxy_) and
+// SubstitutionCount::getAllNumbersOfSubstitutions(d*r_c, 1) for every mapping call
+// (call sites CoETools.cpp:124,397; CoMap.cpp:152).  The tables
+// depend only on tree + model, so they are built once per analysis and reused by every
+// null replicate.  Compile with -ffp-contract=off: eigen-based P(t) carries ~1e-16
+// absolute noise per entry, which is 1e-7 relative on the tiny off-diagonals of 1e-6
+// branches; keeping the arithmetic order fixed keeps that noise reproducible.
+#include "common.h"
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+
+namespace cmb {
+
+void fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  throw Error(buf);
+}
+
+namespace {
+
+using Mat = std::vector<double>;
+
+void matmul(int n, const Mat& a, const Mat& b, Mat& c) {
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) {
+      double s = 0.;
+      for (int k = 0; k < n; k++) s += a[i * n + k] * b[k * n + j];
+      c[i * n + j] = s;
+    }
+}
+
+// Cyclic Jacobi sweeps on a symmetric matrix.
+void jacobi(int n, Mat& a, std::vector<double>& w, Mat& v) {
+  v.assign((size_t)n * n, 0.);
+  for (int i = 0; i < n; i++) v[i * n + i] = 1.;
+  for (int sweep = 0; sweep < 100; sweep++) {
+    double off = 0.;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) off += a[p * n + q] * a[p * n + q];
+    if (off < 1e-300) break;
+    for (int p = 0; p < n; p++)
+      for (int q = p + 1; q < n; q++) {
+        double apq = a[p * n + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        double theta = (a[q * n + q] - a[p * n + p]) / (2. * apq);
+        double t = (theta >= 0 ? 1. : -1.) / (std::fabs(theta) + std::sqrt(theta * theta + 1.));
+        double c = 1. / std::sqrt(t * t + 1.), s = t * c;
+        for (int k = 0; k < n; k++) {
+          double akp = a[k * n + p], akq = a[k * n + q];
+          a[k * n + p] = c * akp - s * akq;
+          a[k * n + q] = s * akp + c * akq;
+        }
+        for (int k = 0; k < n; k++) {
+          double apk = a[p * n + k], aqk = a[q * n + k];
+          a[p * n + k] = c * apk - s * aqk;
+          a[q * n + k] = s * apk + c * aqk;
+        }
+        for (int k = 0; k < n; k++) {
+          double vkp = v[k * n + p], vkq = v[k * n + q];
+          v[k * n + p] = c * vkp - s * vkq;
+          v[k * n + q] = s * vkp + c * vkq;
+        }
+      }
+  }
+  w.resize(n);
+  for (int i = 0; i < n; i++) w[i] = a[i * n + i];
+}
+
+struct Spectrum {
+  int A;
+  std::vector<double> ev;
+  Mat R, L; // Q = R diag(ev) L
+  Spectrum(int A_, const double* Q, const double* pi) : A(A_), R((size_t)A_ * A_), L((size_t)A_ * A_) {
+    Mat M((size_t)A * A), U;
+    for (int i = 0; i < A; i++)
+      if (!(pi[i] > 0.)) fail("cmb_set_model: equilibrium frequency %d is not positive", i);
+    for (int i = 0; i < A; i++)
+      for (int j = 0; j < A; j++) {
+        double mij = Q[i * A + j] * std::sqrt(pi[i]) / std::sqrt(pi[j]);
+        double mji = Q[j * A + i] * std::sqrt(pi[j]) / std::sqrt(pi[i]);
+        if (std::fabs(mij - mji) > 1e-8 * (std::fabs(mij) + std::fabs(mji) + 1e-300) + 1e-12)
+          fail("cmb_set_model: generator is not reversible with respect to pi (entry %d,%d)", i, j);
+        M[i * A + j] = 0.5 * (mij + mji);
+      }
+    jacobi(A, M, ev, U);
+    for (int x = 0; x < A; x++)
+      for (int k = 0; k < A; k++) {
+        R[x * A + k] = U[x * A + k] / std::sqrt(pi[x]);
+        L[k * A + x] = U[x * A + k] * std::sqrt(pi[x]);
+      }
+  }
+  void pmatrix(double t, double* P) const {
+    for (int x = 0; x < A; x++)
+      for (int y = 0; y < A; y++) {
+        double s = 0.;
+        for (int k = 0; k < A; k++) s += R[x * A + k] * std::exp(ev[k] * t) * L[k * A + y];
+        P[x * A + y] = s;
+      }
+  }
+};
+
+// Uniformization series (Bio++ UniformizationSubstitutionCount): returns
+// the NUMERATOR sum_l s_l w_l(t), i.e. P o n before the division by P.
+void uniformization_numerator(int A, const double* Q, const double* weights, double t, Mat& num) {
+  const int AA = A * A;
+  num.assign(AA, 0.);
+  double mu = 0.;
+  for (int i = 0; i < A; i++) mu = std::fabs(Q[i * A + i]) > mu ? std::fabs(Q[i * A + i]) : mu;
+  double lam = mu * t;
+  if (!(lam > 0.)) return;
+  Mat R(AA), Bm(AA), Rp(AA), s(AA), t1(AA), t2(AA);
+  for (int i = 0; i < A; i++)
+    for (int j = 0; j < A; j++) {
+      R[i * A + j] = Q[i * A + j] / mu + (i == j ? 1. : 0.);
+      Bm[i * A + j] = (i == j) ? 0. : Q[i * A + j] * (weights ? weights[i * A + j] : 1.);
+      Rp[i * A + j] = (i == j);
+      s[i * A + j] = Bm[i * A + j];
+    }
+  long nmax = (long)std::ceil(4. + 6. * std::sqrt(lam) + lam);
+  double loglam = std::log(lam), logmu = std::log(mu);
+  for (long l = 0; l <= nmax; l++) {
+    if (l > 0) {
+      matmul(A, s, R, t1);
+      matmul(A, Rp, R, t2);
+      Rp = t2;
+      matmul(A, Rp, Bm, t2);
+      for (int i = 0; i < AA; i++) s[i] = t1[i] + t2[i];
+    }
+    double f = std::exp((double)(l + 1) * loglam - lam - logmu - std::lgamma((double)(l + 2)));
+    for (int i = 0; i < AA; i++) num[i] += s[i] * f;
+  }
+}
+
+// Eigen closed form (Bio++ DecompositionSubstitutionCount): R [ (L Bm R) o J(t) ] L.
+void decomposition_numerator(const Spectrum& sp, const double* Q, const double* weights, double t, Mat& num) {
+  const int A = sp.A, AA = A * A;
+  Mat Bm(AA), t1(AA), t2(AA);
+  for (int i = 0; i < A; i++)
+    for (int j = 0; j < A; j++)
+      Bm[i * A + j] = (i == j) ? 0. : Q[i * A + j] * (weights ? weights[i * A + j] : 1.);
+  matmul(A, sp.L, Bm, t1);
+  matmul(A, t1, sp.R, t2);
+  for (int i = 0; i < A; i++)
+    for (int j = 0; j < A; j++) {
+      double dd = sp.ev[i] - sp.ev[j];
+      double J = dd == 0. ? t * std::exp(sp.ev[i] * t)
+                          : (std::exp(sp.ev[i] * t) - std::exp(sp.ev[j] * t)) / dd;
+      t2[i * A + j] *= J;
+    }
+  matmul(A, sp.R, t2, t1);
+  num.resize(AA);
+  matmul(A, t1, sp.L, num);
+}
+
+} // namespace
+
+void build_model_tables(ModelTables& mt, int A, const double* Q, const double* pi, int C,
+                        const double* rates, const double* probs, int count_method,
+                        const double* weights, int B, const double* brlen) {
+  if (A < 2 || A > 32) fail("cmb_set_model: A must be in 2..32 (got %d)", A);
+  if (C < 1 || C > 32) fail("cmb_set_model: C must be in 1..32 (got %d)", C);
+  if (count_method != 0 && count_method != 1) fail("cmb_set_model: unknown count method %d", count_method);
+  Spectrum sp(A, Q, pi);
+  const size_t AA = (size_t)A * A;
+  mt.A = A; mt.C = C; mt.B = B;
+  mt.pi.assign(pi, pi + A);
+  mt.rates.assign(rates, rates + C);
+  mt.probs.assign(probs, probs + C);
+  mt.P.assign((size_t)B * C * AA, 0.);
+  mt.W.assign((size_t)B * C * AA, 0.);
+  mt.cumP.assign((size_t)B * C * AA, 0.);
+  Mat num;
+  for (int b = 0; b < B; b++)
+    for (int c = 0; c < C; c++) {
+      double t = brlen[b] * rates[c];
+      double* P = &mt.P[((size_t)b * C + c) * AA];
+      double* W = &mt.W[((size_t)b * C + c) * AA];
+      double* cum = &mt.cumP[((size_t)b * C + c) * AA];
+      sp.pmatrix(t, P);
+      if (count_method == 0) uniformization_numerator(A, Q, weights, t, num);
+      else decomposition_numerator(sp, Q, weights, t, num);
+      for (size_t i = 0; i < AA; i++) {
+        // reference: n = num / P with NaN/Inf -> 0 and (unweighted) negatives -> 0, then
+        // the mapping multiplies by P again; W = P * n folds both.
+        double n = num[i] / P[i];
+        if (std::isnan(n) || std::isinf(n) || (!weights && n < 0.)) n = 0.;
+        W[i] = probs[c] * (P[i] * n);
+      }
+      for (int x = 0; x < A; x++) {
+        double s = 0.;
+        for (int y = 0; y < A; y++) { s += P[x * A + y]; cum[x * A + y] = s; }
+      }
+    }
+}
+
+} // namespace cmb

@@ -1,0 +1,189 @@
+/*
+ * comap_b200.h -- C ABI of libcomap_b200.so: CoMap's data-parallel hot path on B200.
+ *
+ * The reference (jydu/comap 1.6.0a) has no plugin / FFI interface: its hot path is four
+ * C++ call sites into Bio++ objects.  Each entry point below replaces one
+ * of those call sites; the citation names the reference file:line (relative to
+ * /root/reference) whose semantics it keeps.  A C++ front-end that mirrors CoMap.cpp's
+ * flow on top of this ABI is comap_b200/host/ (binary `comap_b200`); INTEGRATION.md shows
+ * the stub a CoMap maintainer would add to call it from CoETools.cpp.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, non-zero on error; cmb_last_error() gives the
+ *     message (maps onto the reference's bpp::Exception -> message -> exit(-1),
+ *     CoMap.cpp:730-734).  There is NO CPU fallback: without a CUDA device
+ *     cmb_ctx_create fails.
+ *   - All pointers are caller-allocated HOST buffers (pinned memory makes copies faster;
+ *     cmb_host_alloc provides it) unless the name ends in _dev.  Any output pointer
+ *     documented "nullable" may be NULL.
+ *   - A cmb_ctx is bound to one GPU and one CUDA stream; it is not thread-safe.  One
+ *     process per GPU; multi-GPU runs shard work with the shard_* arguments and exchange
+ *     null samples through the *_dev entry points (NCCL is the caller's plumbing).
+ *   - tree  : n_nodes nodes, ids in Newick post-order (children before parent), root =
+ *             n_nodes-1 with parent -1.  Branch b = edge above node b, B = n_nodes-1.
+ *             Leaf k (k-th childless node in id order) is row k of every alignment.
+ *             Lengths below 1e-6 are raised to 1e-6 as Bio++ does.
+ *   - model : A states (2..32), generator Q row-major A*A, reversible w.r.t. pi and
+ *             normalised by the caller; C rate classes (1..32).
+ *   - sites : uint8 codes, tip-major [T][S]; code_mask[code] = bitmask of compatible
+ *             states, so ambiguity codes are multi-state tips, not gaps.
+ *   - Substitution register: Total (one type), optionally weighted (weight_xy).
+ */
+#ifndef COMAP_B200_H
+#define COMAP_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct cmb_ctx cmb_ctx;
+
+/* nijt= : PhylogeneticsApplicationTools::getSubstitutionCount, CoMap.cpp:152 */
+enum { CMB_COUNT_UNIFORMIZATION = 0, CMB_COUNT_DECOMPOSITION = 1 };
+/* statistic= : CoETools::getStatistic, CoETools.cpp:535-600; Statistics.h:164-295 */
+enum {
+  CMB_STAT_CORRELATION = 0,
+  CMB_STAT_COVARIANCE = 1,
+  CMB_STAT_COSINUS = 2,
+  CMB_STAT_COSUBSTITUTION = 3,
+  CMB_STAT_COMPENSATION = 4
+};
+/* clustering.distance= : CoMap.cpp:401-427; Distance.h:150-173,316-424 */
+enum { CMB_DIST_CORRELATION = 0, CMB_DIST_COMPENSATION = 1, CMB_DIST_EUCLIDIAN = 2 };
+/* clustering.method= : CoMap.cpp:460-481 */
+enum { CMB_LINK_COMPLETE = 0, CMB_LINK_SINGLE = 1, CMB_LINK_AVERAGE = 2 };
+
+/* statistic.min_rate_class / .min_rate / .max_rate_class_diff / .max_rate_diff / .min,
+ * CoETools.cpp:420-481; defaults 0, 0, -1, -1, 0 disable every filter. */
+typedef struct cmb_filters {
+  int32_t min_rate_class;
+  int32_t max_rate_class_diff;
+  double min_rate;
+  double max_rate_diff;
+  double min_stat;
+} cmb_filters;
+
+const char* cmb_last_error(void);
+int cmb_version(void);
+
+/* Pinned host memory for fast host<->device copies (optional convenience). */
+int cmb_host_alloc(uint64_t bytes, void** out);
+int cmb_host_free(void* p);
+
+/* device < 0 uses the current device.  stream == NULL creates a private stream;
+ * otherwise the given cudaStream_t (e.g. torch's current stream) is used. */
+int cmb_ctx_create(int device, void* stream, cmb_ctx** out);
+int cmb_ctx_destroy(cmb_ctx* ctx);
+int cmb_sync(cmb_ctx* ctx);
+
+/* Replaces the TreeTemplate<Node> handed to DRHomogeneousTreeLikelihood,
+ * CoMap.cpp:125-126, CoETools.cpp:124. */
+int cmb_set_tree(cmb_ctx* ctx, int32_t n_nodes, const int32_t* parent, const double* brlen);
+
+/* Replaces model / rDist / substitutionCount (CoMap.cpp:136-152; CoETools.cpp:113,122).
+ * Builds P_c(b) = exp(Q d_b r_c) and the count tables n_c(b) for every branch x class.
+ * weight_xy: nullable A*A weights (AlphabetIndex2) of the weighted Total register. */
+int cmb_set_model(cmb_ctx* ctx, int32_t A, const double* Q, const double* pi, int32_t C,
+                  const double* rates, const double* probs, int32_t count_method,
+                  const double* weight_xy);
+
+/* Replaces tl->setData(*sites); tl->initialize() (CoETools.cpp:358-359). */
+int cmb_set_alignment(cmb_ctx* ctx, int64_t S, const uint8_t* codes, int32_t n_codes,
+                      const uint32_t* code_mask);
+
+/* Replaces CoETools::getVectors -> LegacySubstitutionMappingTools::computeSubstitutionVectors
+ * (CoETools.cpp:395-397), the norms loop (CoMap.cpp:158-163) and the per-site columns of
+ * writeInfos (CoETools.cpp:507-510).  n_out is site-major [S][B] (mapping[i] is site i's
+ * branch vector, Statistics.h:154-160); all outputs nullable.  The vectors stay resident
+ * on the device for cmb_pairs / cmb_distance_matrix. */
+int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_t* rate_class,
+            double* loglik);
+
+/* Replaces seqSim.simulate(n) (AnalysisTools.cpp:591,614; ClusterTools.cpp:224) in
+ * discrete-rate mode with a counter-based Philox4x32-10 stream keyed
+ * (seed, global site index, node).  weighted_classes = 0 draws the rate class uniformly
+ * (upstream behaviour), 1 draws it from probs.  states is [T][n]; classes nullable. */
+int cmb_simulate(cmb_ctx* ctx, uint64_t seed, int64_t first_site, int64_t n,
+                 int32_t weighted_classes, uint8_t* states, int32_t* classes);
+
+/* Replaces AnalysisTools::getNullDistributionIntraDR (AnalysisTools.cpp:564-658) + the
+ * per-bin sort (CoETools.cpp:650-652): rep_cpu x { simulate 2 x rep_ram sites, map both,
+ * paired statistic j<->j, bin by Nmin in Domain(0, nmax, K) }.  Outer replicates
+ * [rep_begin, rep_end) are computed (shard of a multi-GPU run; pass 0, rep_cpu for all);
+ * site indices are global so results do not depend on the sharding.  raw (nullable) is
+ * [(rep_end-rep_begin)*rep_ram][4] = Stat, RCmin, PRmin, Nmin
+ * (statistic.null.output.file, AnalysisTools.cpp:642).  The binned, sorted null stays in
+ * the context for cmb_pairs.  nmax < 0 uses max(norm) of the mapped alignment
+ * (CoETools.cpp:640). */
+int cmb_null_intra(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t rep_cpu, int32_t rep_ram,
+                   int32_t rep_begin, int32_t rep_end, int32_t weighted_classes, int32_t K,
+                   double nmax, double* raw);
+
+/* Parity hook: same as cmb_null_intra with the RNG bypassed.  sim1/sim2 are
+ * [rep_cpu][T][rep_ram] state codes under the identity code table. */
+int cmb_null_intra_from_alignments(cmb_ctx* ctx, int32_t stat_id, int32_t rep_cpu, int32_t rep_ram,
+                                   const uint8_t* sim1, const uint8_t* sim2, int32_t K,
+                                   double nmax, double* raw);
+
+/* Multi-GPU exchange step: the unbinned null samples of this context's shard live in
+ * device memory; export them, all-gather with NCCL, then load the union into every rank. */
+int cmb_null_samples_dev(cmb_ctx* ctx, const double** stat_dev, const double** nmin_dev,
+                         int64_t* n);
+int cmb_null_load_dev(cmb_ctx* ctx, const double* stat_dev, const double* nmin_dev, int64_t n,
+                      int32_t K, double nmax);
+/* Sorted per-bin null: bin_offsets [K+1], sorted [bin_offsets[K]] (both nullable). */
+int cmb_null_get(cmb_ctx* ctx, int32_t* K, double* nmax, int64_t* bin_offsets, double* sorted,
+                 int64_t capacity);
+
+/* Replaces the pair loop of CoETools::computeIntraStats (CoETools.cpp:672-724): all pairs
+ * i<j of the mapped alignment, filters, p = (nsim - #{sim < stat} + 1)/(nsim + 1) in the
+ * Nmin bin, NaN / 0 when Nmin is outside [0, nmax) (the "NA\t0" rows).  Rows come out in
+ * the reference's order (i ascending, then j).  Only rows i with
+ * i % (2*shard_count) in {shard_index, 2*shard_count-1-shard_index} are produced
+ * (shard_count = 1: all rows).  use_null = 0 skips the p-value columns.  Every output
+ * column is nullable; capacity is in rows. */
+int cmb_pairs(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* filters, int32_t use_null,
+              int32_t shard_index, int32_t shard_count, int64_t capacity, int32_t* out_i,
+              int32_t* out_j, double* out_stat, int32_t* out_rcmin, double* out_prmin,
+              double* out_nmin, double* out_pvalue, int64_t* out_nsim, int64_t* n_rows);
+
+/* Replaces the distance-matrix loop (CoMap.cpp:432-440; ClusterTools.cpp:242-251).
+ * mat (nullable) receives the full symmetric S*S matrix; it also stays on the device. */
+int cmb_distance_matrix(cmb_ctx* ctx, int32_t dist_id, double* mat);
+
+/* Replaces HierarchicalClustering(method, mat, false) + computeTree (CoMap.cpp:460-485;
+ * ClusterTools.cpp:260-262) on the resident distance matrix (consumed).  Dendrogram:
+ * leaves 0..S-1, inner nodes S..2S-2 in creation order; left/right/height [S-1],
+ * height = merge distance / 2. */
+int cmb_cluster(cmb_ctx* ctx, int32_t linkage, int32_t* left, int32_t* right, double* height);
+
+/* Replaces ClusterTools::getGroups + computeNormProperties + Distance::setStatisticAsProperty
+ * and the size filter (CoMap.cpp:488-545; ClusterTools.cpp:59-113,296-319;
+ * Distance.h:109-129,346-368,390-422) on the last dendrogram.  members: flat, capacity
+ * (S-1)*max_size; offsets [S]; g_* [S-1]. */
+int cmb_groups(cmb_ctx* ctx, int32_t dist_id, int32_t max_size, int32_t* members, int64_t* offsets,
+               double* g_height, double* g_stat, double* g_nmin, int64_t* n_groups);
+
+/* Replaces ClusterTools::computeGlobalDistanceDistribution (ClusterTools.cpp:200-294):
+ * replicates [rep_begin, rep_end) of { simulate S sites, map, distance matrix, cluster,
+ * groups <= max_size }.  Rows: rep, size, Dmax = 2*height, Stat, Nmin, and the member
+ * matrix indices (flat + offsets).  capacity_rows / capacity_members bound the outputs. */
+int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t seed,
+                     int32_t rep_begin, int32_t rep_end, int32_t weighted_classes, int32_t max_size,
+                     int64_t capacity_rows, int64_t capacity_members, int32_t* row_rep,
+                     int32_t* row_size, double* row_dmax, double* row_stat, double* row_nmin,
+                     int32_t* members, int64_t* offsets, int64_t* n_rows);
+
+/* Measurement: device time (CUDA events on the context's stream) and launch counts per
+ * kernel family since the last reset.  name in {"map_down","map_up","simulate","pairs",
+ * "null_pairs","sort","distance","cluster","other"}. */
+int cmb_profile_enable(cmb_ctx* ctx, int32_t on);
+int cmb_profile_reset(cmb_ctx* ctx);
+int cmb_profile_get(cmb_ctx* ctx, const char* name, double* ms, int64_t* launches);
+int64_t cmb_launch_count(cmb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,94 @@
+"""GPU parity of K1 (likelihood + substitution mapping) against the CPU oracle, through
+the C ABI.  Tolerance: 1e-9 relative on mapping vectors (north_star), fp64."""
+import numpy as np
+import pytest
+import helpers as H
+import oracle_binding as O
+from comap_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from comap_b200 import api
+    c = api.Context()
+    yield c
+    c.close()
+
+
+def _setup(ctx, c):
+    ctx.set_tree(c["parent"], c["brlen"])
+    ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(c["codes"], c["code_mask"])
+
+
+def _check(r, q, atol=1e-14):
+    assert np.allclose(r["n"], q["n"], rtol=RTOL, atol=atol)
+    assert np.allclose(r["norm"], q["norm"], rtol=RTOL)
+    assert np.allclose(r["loglik"], q["loglik"], rtol=1e-12)
+    assert np.allclose(r["post_rate"], q["post_rate"], rtol=RTOL)
+    assert np.array_equal(r["rate_class"], q["rate_class"])
+
+
+@pytest.mark.parametrize("T,S,seed,amb", [(3, 1, 1, 0.0), (5, 40, 1, 0.0), (12, 300, 2, 0.1), (40, 777, 3, 0.02),
+                                          (200, 513, 4, 0.0)])
+def test_map_dna_vs_oracle(ctx, T, S, seed, amb):
+    c = H.random_dna_case(T, S, seed, ambiguity=amb)
+    _setup(ctx, c)
+    r = ctx.map()
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    _check(r, q)
+
+
+def test_map_invariant_five_classes(ctx):
+    """GTR + Invariant(Gamma4): C = 5 with a rate-0 class -> two class blocks (4 + 1)."""
+    parent, brlen = syn.random_tree(30, 7, 0.1)
+    Q, pi = syn.gtr(1.6, 0.55, 0.35, 0.30, 0.28, [0.25, 0.2, 0.3, 0.25])
+    rates, probs = syn.invariant(*syn.gamma_rates(0.737, 4), p=0.3666)
+    codes = H.simulate_np(parent, brlen, Q, pi, rates, np.random.default_rng(5), 400)
+    mask = syn.identity_code_mask(4)
+    ctx.set_tree(parent, brlen); ctx.set_model(Q, pi, rates, probs); ctx.set_alignment(codes, mask)
+    r = ctx.map()
+    q = O.map_sites(parent, brlen, Q, pi, rates, probs, codes, mask)
+    _check(r, q)
+
+
+def test_map_multifurcations(ctx):
+    """Polytomies are binarised internally with virtual zero-length edges."""
+    parent = np.array([6, 6, 6, 6, 7, 7, 9, 9, 9, -1], np.int32)  # leaf 8 attaches to the root too
+    brlen = np.array([0.1, 0.2, 0.05, 0.3, 0.15, 0.02, 0.2, 0.1, 0.4, 0.0])
+    Q, pi = syn.hky85(2.0, [0.3, 0.2, 0.2, 0.3])
+    rates, probs = syn.gamma_rates(0.6, 4)
+    rng = np.random.default_rng(0)
+    codes = rng.integers(0, 4, (7, 100)).astype(np.uint8)
+    mask = syn.identity_code_mask(4)
+    ctx.set_tree(parent, brlen); ctx.set_model(Q, pi, rates, probs); ctx.set_alignment(codes, mask)
+    r = ctx.map()
+    q = O.map_sites(parent, brlen, Q, pi, rates, probs, codes, mask)
+    _check(r, q)
+
+
+def test_map_myoglobin_golden(ctx):
+    """Protein path (A = 20) against the oracle AND the reference's golden vectors."""
+    m = H.myoglobin_inputs()
+    _setup(ctx, m)
+    r = ctx.map()
+    q = O.map_sites(m["parent"], m["brlen"], m["Q"], m["pi"], m["rates"], m["probs"], m["codes"], m["code_mask"])
+    _check(r, q, atol=1e-16)
+    gold = m["golden"]["vec_unif"].T
+    rel = np.abs(r["n"] - gold) / np.abs(gold)
+    assert np.median(rel) < 5e-6 and rel.max() < 1e-4
+    assert np.all(np.abs(r["loglik"] - m["golden"]["infos_logl"]) <= 6e-6 * np.abs(m["golden"]["infos_logl"]))
+
+
+def test_errors_are_reported(ctx):
+    from comap_b200 import api
+    c2 = api.Context()
+    with pytest.raises(RuntimeError, match="cmb_set_alignment"):
+        c2.lib.cmb_map  # symbol exists
+        c2._chk(c2.lib.cmb_map(c2.h, None, None, None, None, None))
+    with pytest.raises(RuntimeError, match="post-order"):
+        c2.set_tree(np.array([1, 0, -1], np.int32), np.array([0.1, 0.1, 0.0]))
+    c2.close()

@@ -20,7 +20,7 @@ SYMBOLS = [
     "cmb_last_error", "cmb_version", "cmb_host_alloc", "cmb_host_free", "cmb_ctx_create",
     "cmb_ctx_destroy", "cmb_sync", "cmb_set_tree", "cmb_set_model", "cmb_set_alignment", "cmb_map",
     "cmb_simulate", "cmb_null_intra", "cmb_null_intra_from_alignments", "cmb_null_samples_dev",
-    "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_distance_matrix", "cmb_cluster",
+    "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
     "cmb_launch_count",
 ]
@@ -196,6 +196,24 @@ class Context:
         k = nr.value
         out = dict(i=oi, j=oj, stat=st, rcmin=rcm, prmin=prm, nmin=nm, pvalue=pv, nsim=ns)
         return {name: (a[:k] if a is not None else None) for name, a in out.items()}, k
+
+    COLS = ("i", "j", "stat", "rcmin", "prmin", "nmin", "pvalue", "nsim")
+    COL_DTYPE = (np.int32, np.int32, np.float64, np.int32, np.float64, np.float64, np.float64, np.int64)
+
+    def pairs_resident(self, stat, use_null=True, filters=None, shard_index=0, shard_count=1, columns=0xFF):
+        f = Filters(0, -1, 0.0, -1.0, 0.0)
+        if filters:
+            for k, v in filters.items():
+                setattr(f, k, v)
+        nr = C.c_int64()
+        self._chk(self.lib.cmb_pairs_resident(self.h, STAT[stat], C.byref(f), int(use_null), shard_index,
+                                              shard_count, C.c_uint32(columns), C.byref(nr)))
+        return nr.value
+
+    def pairs_fetch(self, column, host_array):
+        """Asynchronous copy of one resident column into host_array (pinned for speed); sync() after."""
+        self._chk(self.lib.cmb_pairs_fetch(self.h, column, C.c_void_p(host_array.ctypes.data),
+                                           C.c_int64(host_array.size)))
 
     # ------------------------------------------------------------------ clustering
     def distance_matrix(self, dist, want=True):

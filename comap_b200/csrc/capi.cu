@@ -138,11 +138,9 @@ void Context::run_map(const MapBuffers& b, bool simulated) {
   launch_map_finish(m, b, stream);
   prof_end((int)class_blocks.size() + 1);
   prof_begin("map_up");
-  bool single = class_blocks.size() == 1;
   for (size_t i = 0; i < class_blocks.size(); i++)
-    launch_map_up(m, b, up_streams[i], class_blocks[i].first, class_blocks[i].second, i > 0, single, stream);
-  if (!single) launch_map_norms(m, b, stream);
-  prof_end((int)class_blocks.size() + (single ? 0 : 1));
+    launch_map_up(m, b, up_streams[i], class_blocks[i].first, class_blocks[i].second, i > 0, false, stream);
+  prof_end((int)class_blocks.size());
 }
 
 } // namespace cmb
@@ -212,7 +210,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_D, &c.s_Lc, &c.s_invL, &c.s_loglik, &c.s_pr[0], &c.s_pr[1], &c.s_rc[0], &c.s_rc[1],
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
-                    &c.d_dist, &c.scratch, &c.scratch2, &c.staging};
+                    &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm};
   for (DevBuf* b : bufs) b->release();
   for (auto& s : c.down_streams) s.release();
   for (auto& s : c.up_streams) s.release();
@@ -314,9 +312,15 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   b.loglik = c.d_loglik.as<double>(); b.post_rate = c.d_pr.as<double>(); b.rate_class = c.d_rc.as<int32_t>();
   b.out = c.d_out.as<double>(); b.sum = c.d_sum.as<double>(); b.sumsq = c.d_sumsq.as<double>();
   c.run_map(b, false);
-  // norms are needed on the host by the null (Domain upper bound) and for the caller
+  // per-site mean / sd / norm in the reference's summation order (k2_prep); norms are needed
+  // on the host by the null (Domain upper bound) and for the caller
+  c.pairs_mean.reserve(sizeof(double) * Sp);
+  c.pairs_sd.reserve(sizeof(double) * Sp);
+  c.pairs_norm.reserve(sizeof(double) * Sp);
+  launch_prep(B, S, Sp, b.out, c.pairs_mean.as<double>(), c.pairs_sd.as<double>(), c.pairs_norm.as<double>(), c.stream);
+  c.prof.total_launches += 1;
   c.h_norm.resize(S);
-  CMB_CUDA(cudaMemcpyAsync(c.h_norm.data(), c.d_sumsq.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaMemcpyAsync(c.h_norm.data(), c.pairs_norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
   if (n_out) {
     c.scratch.reserve(sizeof(double) * (size_t)S * B);
     launch_transpose_out(b.out, B, S, Sp, c.scratch.as<double>(), c.stream);
@@ -328,10 +332,8 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   if (loglik) CMB_CUDA(cudaMemcpyAsync(loglik, c.d_loglik.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
   CMB_CUDA(cudaStreamSynchronize(c.stream));
   c.max_norm = 0.;
-  for (int64_t i = 0; i < S; i++) {
-    c.h_norm[i] = std::sqrt(c.h_norm[i]);
+  for (int64_t i = 0; i < S; i++)
     if (c.h_norm[i] > c.max_norm) c.max_norm = c.h_norm[i];
-  }
   if (norm) std::memcpy(norm, c.h_norm.data(), sizeof(double) * S);
   c.mapped = true;
   c.have_dist = false;

@@ -68,6 +68,9 @@ struct Context {
   bool have_dendro = false;
 
   DevBuf scratch, scratch2, staging;
+  int64_t pairs_col_off[8] = {-1, -1, -1, -1, -1, -1, -1, -1}; // resident pair columns in `staging`
+  int64_t pairs_rows = -1;
+  DevBuf pairs_mean, pairs_sd, pairs_norm; // per-site mean / sd / norm for the tile kernels
   Profile prof;
 
   void require_tree_model() const;

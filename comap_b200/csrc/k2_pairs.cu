@@ -1,0 +1,416 @@
+// K2: site-pair statistics on the device.
+//
+//  * k2_paired   -- null distribution: statistic of site j of batch 1 with site j of batch 2
+//                   (AnalysisTools.cpp:637-640), one thread per pair, coalesced over sites.
+//  * k2_tiles    -- all pairs i<j of the mapped alignment (CoETools.cpp:672-724) or the full
+//                   distance matrix (CoMap.cpp:432-440): 64x64 register-tiled fp64 Gram
+//                   tiles over the [branch][site] matrix; centring / indicator transforms
+//                   are fused into the tile load, the statistic, the filters and the
+//                   p-value lookup (binary search in the sorted per-bin null) into the
+//                   epilogue.  Statistics formulas: Statistics.h:164-265; VectorTools::cor
+//                   = cov/(sd sd) with the unbiased factors kept as the reference has them.
+//  * null binning + per-bin sort (Domain.cpp:113-122, CoETools.cpp:650-652) with CUB radix
+//    sorts (library code, not a hot step: 1e6 keys).
+#include "kernels.h"
+#include <cub/cub.cuh>
+
+namespace cmb {
+namespace {
+
+// Domain(0, nmax, K).getIndex, CoMap/Domain.cpp:46-59,113-122 (bounds_[i] = mini + i*w)
+__device__ __forceinline__ int domain_index(double nmax, int K, double x) {
+  double w = nmax / (double)K;
+  double upper = 0. + (double)K * w;
+  if (x < 0. || x >= upper || !(x == x)) return -1;
+  for (int i = 1; i < K + 1; i++)
+    if (x < 0. + (double)i * w) return i - 1;
+  return -1;
+}
+
+// ---------------------------------------------------------------------------- paired
+// Exactness: p-values count null values strictly below an observed statistic
+// (CoETools.cpp:715), and low-rate sites produce massive ties (e.g. r = 1 between two
+// constant sites), so a 1-ulp change of a statistic moves counts by dozens.  All pair
+// statistics therefore replicate the reference's operation order (VectorTools::mean ->
+// center -> scalar, sums over branches in id order) with explicitly unfused multiplies
+// and adds: given identical mapping vectors they are bit-identical to the CPU restatement.
+__device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
+
+__global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* __restrict__ o1,
+                          const double* __restrict__ o2, double* __restrict__ stat, double* __restrict__ nmin) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const double nb = (double)B;
+  double sx = 0., sy = 0., qx = 0., qy = 0., sxy = 0., s3 = 0., cnt = 0.;
+  for (int b = 0; b < B; b++) {
+    const double x = o1[(size_t)b * n_pad + j], y = o2[(size_t)b * n_pad + j];
+    sx = add_(sx, x);
+    sy = add_(sy, y);
+    qx = add_(qx, mul_(x, x));
+    qy = add_(qy, mul_(y, y));
+    if (stat_id == 2) sxy = add_(sxy, mul_(x, y));
+    if (stat_id == 3 && x >= 1. && y >= 1.) cnt += 1.;
+    if (stat_id == 4) { double t = add_(x, y); s3 = add_(s3, mul_(t, t)); }
+  }
+  double r;
+  if (stat_id == 0 || stat_id == 1) {
+    const double mx = sx / nb, my = sy / nb;
+    double cxy = 0., cxx = 0., cyy = 0.;
+    for (int b = 0; b < B; b++) {
+      const double x = add_(o1[(size_t)b * n_pad + j], -mx), y = add_(o2[(size_t)b * n_pad + j], -my);
+      cxy = add_(cxy, mul_(x, y));
+      cxx = add_(cxx, mul_(x, x));
+      cyy = add_(cyy, mul_(y, y));
+    }
+    cxy = cxy / nb * nb / (nb - 1.);
+    cxx = cxx / nb * nb / (nb - 1.);
+    cyy = cyy / nb * nb / (nb - 1.);
+    r = stat_id == 0 ? cxy / mul_(sqrt(cxx), sqrt(cyy)) : cxy;
+  } else if (stat_id == 2) r = sxy / mul_(sqrt(qx), sqrt(qy));
+  else if (stat_id == 3) r = cnt;
+  else r = add_(1., -(sqrt(s3) / add_(sqrt(qx), sqrt(qy))));
+  stat[j] = r;
+  const double a = sqrt(qx), c = sqrt(qy);
+  nmin[j] = a < c ? a : c;
+}
+
+__global__ void k2_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1,
+                            const int32_t* rc2, const double* pr1, const double* pr2, double* raw) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  raw[j * 4 + 0] = stat[j];
+  raw[j * 4 + 1] = (double)(rc1[j] < rc2[j] ? rc1[j] : rc2[j]);
+  raw[j * 4 + 2] = pr1[j] < pr2[j] ? pr1[j] : pr2[j];
+  raw[j * 4 + 3] = nmin[j];
+}
+
+// ---------------------------------------------------------------------------- binning
+__global__ void k2_bin_keys(int64_t n, const double* nmin, double nmax, int K, uint32_t* cat) {
+  const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  int c = domain_index(nmax, K, nmin[j]);
+  cat[j] = c < 0 ? (uint32_t)K : (uint32_t)c;
+}
+__global__ void k2_bin_offsets(int64_t n, const uint32_t* cat_sorted, int K, int64_t* off) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > K) return;
+  int64_t lo = 0, hi = n; // first index with cat >= k
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (cat_sorted[mid] < (uint32_t)k) lo = mid + 1; else hi = mid;
+  }
+  off[k] = lo;
+}
+
+// ---------------------------------------------------------------------------- per-site prep
+// mean, sd (unbiased, as VectorTools::sd) and norm per site from the [B][n_pad] matrix,
+// summed over branches in id order without fused operations (see k2_paired)
+__global__ void k2_prep(int B, int64_t n, int64_t n_pad, const double* __restrict__ out, double* mean,
+                        double* sd, double* norm) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const double nb = (double)B;
+  double sx = 0., qx = 0.;
+  for (int b = 0; b < B; b++) {
+    const double x = out[(size_t)b * n_pad + s];
+    sx = add_(sx, x);
+    qx = add_(qx, mul_(x, x));
+  }
+  const double m = sx / nb;
+  double css = 0.;
+  for (int b = 0; b < B; b++) {
+    const double x = add_(out[(size_t)b * n_pad + s], -m);
+    css = add_(css, mul_(x, x));
+  }
+  mean[s] = m;
+  sd[s] = sqrt(css / nb * nb / (nb - 1.));
+  norm[s] = sqrt(qx);
+}
+
+// ---------------------------------------------------------------------------- tiles
+constexpr int TS = 64;  // tile edge (sites)
+constexpr int BK = 16;  // branches per smem stage
+enum { MODE_PAIRS = 0, MODE_DIST = 1 };
+
+struct TileParams {
+  int stat_id, mode, B;
+  int64_t S, S_pad;
+  const double* out;          // [B][S_pad]
+  const double *mean, *sd, *norm, *post_rate;
+  const int32_t* rate_class;
+  const int2* tiles;          // (ti, tj) with tj >= ti
+  const int32_t* rows;        // owned row list (gathered i-dimension) or nullptr = identity
+  int64_t n_rows;             // number of owned rows
+  const int64_t* row_off;     // [n_rows] start of each owned row in the dense output
+  // filters (CoETools.cpp:420-481)
+  int min_rate_class, max_rate_class_diff;
+  double min_rate, max_rate_diff, min_stat;
+  int any_filter;
+  // null
+  int K;
+  double nmax;
+  const int64_t* bin_off;
+  const double* sorted;
+  // outputs (dense upper triangle of the owned rows), all nullable
+  int32_t *o_i, *o_j, *o_rcmin;
+  double *o_stat, *o_prmin, *o_nmin, *o_pvalue;
+  int64_t* o_nsim;
+  uint8_t* o_keep;
+  double* mat;                // MODE_DIST: [S][S]
+  double dist_comp;           // distance = comp - stat (Distance.h:334-337), or stat itself
+  int dist_is_stat;
+};
+
+template <int STAT>
+__device__ __forceinline__ double tile_load(double x, double mean) {
+  if (STAT == 0 || STAT == 1) return add_(x, -mean);
+  if (STAT == 3) return x >= 1. ? 1. : 0.;
+  return x;
+}
+
+template <int STAT>
+__global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
+  __shared__ __align__(16) double As[BK][TS];
+  __shared__ __align__(16) double Bs[BK][TS];
+  const int2 t = p.tiles[blockIdx.x];
+  const int64_t i0 = (int64_t)t.x * TS, j0 = (int64_t)t.y * TS;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4; // thread tile: rows ty*4.., cols tx*4..
+  // loader mapping: 4 elements per thread per operand: k = tid / 16, cols (tid % 16) * 4 ..
+  const int lk = tid >> 4, lc = (tid & 15) * 4;
+  int64_t ai[4], bj[4];
+  double am[4], bm[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    int64_t ri = i0 + lc + u;
+    ai[u] = ri < p.n_rows ? (p.rows ? p.rows[ri] : ri) : -1;
+    int64_t cj = j0 + lc + u;
+    bj[u] = cj < p.S ? cj : -1;
+    am[u] = ai[u] >= 0 ? p.mean[ai[u]] : 0.;
+    bm[u] = bj[u] >= 0 ? p.mean[bj[u]] : 0.;
+  }
+  double acc[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+#pragma unroll
+    for (int v = 0; v < 4; v++) acc[u][v] = 0.;
+
+  for (int k0 = 0; k0 < p.B; k0 += BK) {
+    const int k = k0 + lk;
+    const double* rowp = p.out + (size_t)k * p.S_pad;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      double a = 0., b = 0.;
+      if (k < p.B) {
+        if (ai[u] >= 0) a = tile_load<STAT>(rowp[ai[u]], am[u]);
+        if (bj[u] >= 0) b = tile_load<STAT>(rowp[bj[u]], bm[u]);
+      }
+      As[lk][lc + u] = a;
+      Bs[lk][lc + u] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; kk++) {
+      double a[4], b[4];
+      const double2* ap = reinterpret_cast<const double2*>(&As[kk][ty * 4]);
+      const double2* bp = reinterpret_cast<const double2*>(&Bs[kk][tx * 4]);
+      double2 a0 = ap[0], a1 = ap[1], b0 = bp[0], b1 = bp[1];
+      a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+          if (STAT == 4) { double s = add_(a[u], b[v]); acc[u][v] = add_(acc[u][v], mul_(s, s)); }
+          else if (STAT == 5) { double s = add_(b[v], -a[u]); acc[u][v] = add_(acc[u][v], mul_(s, s)); }
+          else acc[u][v] = add_(acc[u][v], mul_(a[u], b[v]));
+        }
+    }
+    __syncthreads();
+  }
+
+  const double nb = (double)p.B;
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const int64_t ri = i0 + ty * 4 + u;
+    if (ri >= p.n_rows) continue;
+    const int64_t i = p.rows ? p.rows[ri] : ri;
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+      const int64_t j = j0 + tx * 4 + v;
+      if (j >= p.S || j <= i) continue;
+      double stat;
+      if (STAT == 0) stat = (acc[u][v] / nb * nb / (nb - 1.)) / mul_(p.sd[i], p.sd[j]);
+      else if (STAT == 1) stat = acc[u][v] / nb * nb / (nb - 1.);
+      else if (STAT == 2) stat = acc[u][v] / mul_(p.norm[i], p.norm[j]);
+      else if (STAT == 3) stat = acc[u][v];
+      else if (STAT == 4) stat = add_(1., -(sqrt(acc[u][v]) / add_(p.norm[i], p.norm[j])));
+      else stat = sqrt(acc[u][v]);
+      if (p.mode == MODE_DIST) {
+        double d = p.dist_is_stat ? stat : p.dist_comp - stat;
+        p.mat[(size_t)i * p.S + j] = d;
+        p.mat[(size_t)j * p.S + i] = d;
+        continue;
+      }
+      const int64_t idx = p.row_off[ri] + (j - i - 1);
+      const int ci = p.rate_class[i], cj = p.rate_class[j];
+      const double pi_ = p.post_rate[i], pj = p.post_rate[j];
+      const double ni = p.norm[i], nj = p.norm[j];
+      if (p.any_filter) {
+        bool keep = ci >= p.min_rate_class && cj >= p.min_rate_class && !(pi_ < p.min_rate) && !(pj < p.min_rate);
+        if (p.max_rate_class_diff >= 0 && abs(cj - ci) > p.max_rate_class_diff) keep = false;
+        if (p.max_rate_diff >= 0. && fabs(pj - pi_) > p.max_rate_diff) keep = false;
+        if (fabs(stat) < p.min_stat) keep = false;
+        p.o_keep[idx] = keep ? 1 : 0;
+      }
+      const double nm = ni < nj ? ni : nj;
+      if (p.o_i) p.o_i[idx] = (int32_t)i;
+      if (p.o_j) p.o_j[idx] = (int32_t)j;
+      if (p.o_stat) p.o_stat[idx] = stat;
+      if (p.o_rcmin) p.o_rcmin[idx] = ci < cj ? ci : cj;
+      if (p.o_prmin) p.o_prmin[idx] = pi_ < pj ? pi_ : pj;
+      if (p.o_nmin) p.o_nmin[idx] = nm;
+      if (p.K > 0 && (p.o_pvalue || p.o_nsim)) {
+        int cat = domain_index(p.nmax, p.K, nm);
+        double pv = nan("");
+        int64_t nsim = 0;
+        if (cat >= 0) {
+          const double* sim = p.sorted + p.bin_off[cat];
+          nsim = p.bin_off[cat + 1] - p.bin_off[cat];
+          int64_t lo = 0, hi = nsim; // count = #{sim < stat} on the ascending bin
+          while (lo < hi) {
+            int64_t mid = (lo + hi) >> 1;
+            if (sim[mid] < stat) lo = mid + 1; else hi = mid;
+          }
+          pv = (double)(nsim - lo + 1) / (double)(nsim + 1);
+        }
+        if (p.o_pvalue) p.o_pvalue[idx] = pv;
+        if (p.o_nsim) p.o_nsim[idx] = nsim;
+      }
+    }
+  }
+  if (p.mode == MODE_DIST && t.x == t.y) { // zero diagonal
+    for (int d = tid; d < TS; d += blockDim.x) {
+      int64_t i = i0 + d;
+      if (i < p.S) p.mat[(size_t)i * p.S + i] = 0.;
+    }
+  }
+}
+
+template <class T>
+__global__ void k2_compact(int64_t n, const uint8_t* keep, const int64_t* pos, const T* src, T* dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && keep[i]) dst[pos[i]] = src[i];
+}
+__global__ void k2_keep_to_i64(int64_t n, const uint8_t* keep, int64_t* out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = keep[i];
+}
+
+} // namespace
+
+void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* o1, const double* o2, double* stat,
+                   double* nmin, cudaStream_t st) {
+  k2_paired<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stat_id, B, n, n_pad, o1, o2, stat, nmin);
+  CMB_CUDA(cudaGetLastError());
+}
+void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
+                     const double* pr1, const double* pr2, double* raw, cudaStream_t st) {
+  k2_raw_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, stat, nmin, rc1, rc2, pr1, pr2, raw);
+  CMB_CUDA(cudaGetLastError());
+}
+void launch_prep(int B, int64_t n, int64_t n_pad, const double* out, double* mean, double* sd, double* norm,
+                 cudaStream_t st) {
+  k2_prep<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, n, n_pad, out, mean, sd, norm);
+  CMB_CUDA(cudaGetLastError());
+}
+
+// Bins the n samples by Nmin and sorts each bin ascending.  sorted gets the retained
+// samples grouped by bin; off (K+1 int64, device) the bin boundaries.  Returns launches.
+int bin_and_sort(int64_t n, const double* stat, const double* nmin, int K, double nmax, DevBuf& tmp,
+                 double* sorted, int64_t* off_dev, cudaStream_t st) {
+  if (n == 0) {
+    CMB_CUDA(cudaMemsetAsync(off_dev, 0, sizeof(int64_t) * (K + 1), st));
+    return 0;
+  }
+  // layout of tmp: cat[n] u32 | cat2[n] u32 | stat1[n] f64 | cub temp
+  size_t need1 = 0, need2 = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, need1, (const double*)nullptr, (double*)nullptr, (const uint32_t*)nullptr,
+                                  (uint32_t*)nullptr, (int)n, 0, 64, st);
+  cub::DeviceRadixSort::SortPairs(nullptr, need2, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const double*)nullptr,
+                                  (double*)nullptr, (int)n, 0, 32, st);
+  size_t need = need1 > need2 ? need1 : need2;
+  size_t a = ((size_t)n * 4 + 255) & ~size_t(255), d = ((size_t)n * 8 + 255) & ~size_t(255);
+  tmp.reserve(2 * a + d + need + 256);
+  unsigned char* base = tmp.as<unsigned char>();
+  uint32_t* cat = (uint32_t*)base;
+  uint32_t* cat2 = (uint32_t*)(base + a);
+  double* stat1 = (double*)(base + 2 * a);
+  void* ctemp = base + 2 * a + d;
+  k2_bin_keys<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, nmin, nmax, K, cat);
+  CMB_CUDA(cudaGetLastError());
+  // sort by statistic, then stable sort by bin
+  CMB_CUDA(cub::DeviceRadixSort::SortPairs(ctemp, need, stat, stat1, cat, cat2, (int)n, 0, 64, st));
+  int bits = 1;
+  while ((1 << bits) <= K) bits++;
+  CMB_CUDA(cub::DeviceRadixSort::SortPairs(ctemp, need, cat2, cat, stat1, sorted, (int)n, 0, bits, st));
+  k2_bin_offsets<<<1, 64, 0, st>>>(n, cat, K, off_dev);
+  CMB_CUDA(cudaGetLastError());
+  return 6;
+}
+
+int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
+  TileParams p{};
+  p.stat_id = L.stat_id; p.mode = L.dist_mode ? MODE_DIST : MODE_PAIRS; p.B = L.B; p.S = L.S; p.S_pad = L.S_pad;
+  p.out = L.out; p.mean = L.mean; p.sd = L.sd; p.norm = L.norm; p.post_rate = L.post_rate; p.rate_class = L.rate_class;
+  p.tiles = L.tiles; p.rows = L.rows; p.n_rows = L.n_rows; p.row_off = L.row_off;
+  p.min_rate_class = L.min_rate_class; p.max_rate_class_diff = L.max_rate_class_diff; p.min_rate = L.min_rate;
+  p.max_rate_diff = L.max_rate_diff; p.min_stat = L.min_stat; p.any_filter = L.any_filter;
+  p.K = L.K; p.nmax = L.nmax; p.bin_off = L.bin_off; p.sorted = L.sorted;
+  p.o_i = L.o_i; p.o_j = L.o_j; p.o_rcmin = L.o_rcmin; p.o_stat = L.o_stat; p.o_prmin = L.o_prmin; p.o_nmin = L.o_nmin;
+  p.o_pvalue = L.o_pvalue; p.o_nsim = L.o_nsim; p.o_keep = L.o_keep; p.mat = L.mat; p.dist_comp = L.dist_comp;
+  p.dist_is_stat = L.dist_is_stat;
+  if (L.n_tiles == 0) return 0;
+  unsigned g = (unsigned)L.n_tiles;
+  switch (L.stat_id) {
+    case 0: k2_tiles<0><<<g, 256, 0, st>>>(p); break;
+    case 1: k2_tiles<1><<<g, 256, 0, st>>>(p); break;
+    case 2: k2_tiles<2><<<g, 256, 0, st>>>(p); break;
+    case 3: k2_tiles<3><<<g, 256, 0, st>>>(p); break;
+    case 4: k2_tiles<4><<<g, 256, 0, st>>>(p); break;
+    case 5: k2_tiles<5><<<g, 256, 0, st>>>(p); break;
+    default: fail("unknown statistic id %d", L.stat_id);
+  }
+  CMB_CUDA(cudaGetLastError());
+  return 1;
+}
+
+// exclusive scan of the keep flags -> positions; returns number kept (synchronises)
+int64_t compact_positions(int64_t n, const uint8_t* keep, DevBuf& tmp, int64_t** pos_out, cudaStream_t st) {
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, (const int64_t*)nullptr, (int64_t*)nullptr, (int)n, st);
+  size_t a = ((size_t)n * 8 + 255) & ~size_t(255);
+  tmp.reserve(2 * a + need + 256);
+  int64_t* flags = tmp.as<int64_t>();
+  int64_t* pos = (int64_t*)(tmp.as<unsigned char>() + a);
+  void* ctemp = tmp.as<unsigned char>() + 2 * a;
+  k2_keep_to_i64<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, keep, flags);
+  CMB_CUDA(cub::DeviceScan::ExclusiveSum(ctemp, need, flags, pos, (int)n, st));
+  int64_t last_pos = 0, last_flag = 0;
+  CMB_CUDA(cudaMemcpyAsync(&last_pos, pos + n - 1, 8, cudaMemcpyDeviceToHost, st));
+  CMB_CUDA(cudaMemcpyAsync(&last_flag, flags + n - 1, 8, cudaMemcpyDeviceToHost, st));
+  CMB_CUDA(cudaStreamSynchronize(st));
+  *pos_out = pos;
+  return last_pos + last_flag;
+}
+template <class T>
+void compact_column(int64_t n, const uint8_t* keep, const int64_t* pos, const T* src, T* dst, cudaStream_t st) {
+  k2_compact<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, keep, pos, src, dst);
+  CMB_CUDA(cudaGetLastError());
+}
+template void compact_column<int32_t>(int64_t, const uint8_t*, const int64_t*, const int32_t*, int32_t*, cudaStream_t);
+template void compact_column<int64_t>(int64_t, const uint8_t*, const int64_t*, const int64_t*, int64_t*, cudaStream_t);
+template void compact_column<double>(int64_t, const uint8_t*, const int64_t*, const double*, double*, cudaStream_t);
+
+} // namespace cmb

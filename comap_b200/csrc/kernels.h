@@ -44,9 +44,52 @@ void launch_map_up(const MapModel& m, const MapBuffers& b, const DevStream& s, i
 void launch_map_norms(const MapModel& m, const MapBuffers& b, cudaStream_t st);
 int map_class_block(int A, int C); // classes per pass for this (A, C)
 
-void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t first_site, int64_t n,
-                     int64_t n_pad, int weighted, int root_node, uint8_t* tips, int32_t* classes,
-                     cudaStream_t st);
+// site id of thread idx = base + (idx / group) * stride + idx % group
+void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,
+                     int64_t stride, int64_t n, int64_t n_pad, int weighted, int root_node, uint8_t* tips,
+                     int32_t* classes, cudaStream_t st);
+
+// ---- K2
+void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* o1, const double* o2, double* stat,
+                   double* nmin, cudaStream_t st);
+void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
+                     const double* pr1, const double* pr2, double* raw, cudaStream_t st);
+void launch_prep(int B, int64_t n, int64_t n_pad, const double* out, double* mean, double* sd, double* norm,
+                 cudaStream_t st);
+int bin_and_sort(int64_t n, const double* stat, const double* nmin, int K, double nmax, DevBuf& tmp,
+                 double* sorted, int64_t* off_dev, cudaStream_t st);
+
+struct TilesLaunch {
+  int stat_id = 0, B = 0;       // stat ids 0..4 as in the C ABI, 5 = euclidian distance
+  bool dist_mode = false;
+  int64_t S = 0, S_pad = 0;
+  const double* out = nullptr;
+  const double *mean = nullptr, *sd = nullptr, *norm = nullptr, *post_rate = nullptr;
+  const int32_t* rate_class = nullptr;
+  const int2* tiles = nullptr;
+  int64_t n_tiles = 0;
+  const int32_t* rows = nullptr;
+  int64_t n_rows = 0;
+  const int64_t* row_off = nullptr;
+  int min_rate_class = 0, max_rate_class_diff = -1;
+  double min_rate = 0., max_rate_diff = -1., min_stat = 0.;
+  int any_filter = 0;
+  int K = 0;
+  double nmax = 0.;
+  const int64_t* bin_off = nullptr;
+  const double* sorted = nullptr;
+  int32_t *o_i = nullptr, *o_j = nullptr, *o_rcmin = nullptr;
+  double *o_stat = nullptr, *o_prmin = nullptr, *o_nmin = nullptr, *o_pvalue = nullptr;
+  int64_t* o_nsim = nullptr;
+  uint8_t* o_keep = nullptr;
+  double* mat = nullptr;
+  double dist_comp = 1.;
+  int dist_is_stat = 0;
+};
+int launch_tiles(const TilesLaunch& L, cudaStream_t st);
+int64_t compact_positions(int64_t n, const uint8_t* keep, DevBuf& tmp, int64_t** pos_out, cudaStream_t st);
+template <class T>
+void compact_column(int64_t n, const uint8_t* keep, const int64_t* pos, const T* src, T* dst, cudaStream_t st);
 
 // [B][n_pad] -> [n][B] for the host-facing site-major output
 void launch_transpose_out(const double* out, int B, int64_t n, int64_t n_pad, double* dst, cudaStream_t st);

@@ -1,0 +1,188 @@
+"""GPU parity of K2 (pair statistics, p-values), K3 (simulation) and the null pipeline
+against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+import helpers as H
+import oracle_binding as O
+from comap_b200 import synthetic as syn
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9  # north_star tolerance for pair statistics (fp64)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from comap_b200 import api
+    c = api.Context()
+    yield c
+    c.close()
+
+
+def _case(T=24, S=150, seed=11, C=4):
+    c = H.random_dna_case(T, S, seed, mean_brlen=0.08, C=C)
+    return c
+
+
+def _setup(ctx, c):
+    ctx.set_tree(c["parent"], c["brlen"])
+    ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(c["codes"], c["code_mask"])
+    return ctx.map()
+
+
+def _close(a, b, rtol=RTOL, atol=1e-12):
+    a, b = np.asarray(a), np.asarray(b)
+    nan = np.isnan(a)
+    return np.array_equal(nan, np.isnan(b)) and np.allclose(a[~nan], b[~nan], rtol=rtol, atol=atol)
+
+
+def test_simulate_bit_exact_vs_oracle(ctx):
+    c = _case(T=40, S=10)
+    _setup(ctx, c)
+    for weighted in (False, True):
+        a, ca = ctx.simulate(1234, 0, 3000, weighted_classes=weighted)
+        b, cb = O.simulate(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], 1234, 0, 3000, weighted)
+        assert np.array_equal(ca, cb)
+        assert np.array_equal(a, b)
+    # counter based: a window of the stream equals the same sites simulated alone
+    w, _ = ctx.simulate(1234, 1000, 257, weighted_classes=True)
+    assert np.array_equal(w, a[:, 1000:1257])
+
+
+def test_simulate_protein_bit_exact(ctx):
+    m = H.myoglobin_inputs()
+    ctx.set_tree(m["parent"], m["brlen"]); ctx.set_model(m["Q"], m["pi"], m["rates"], m["probs"])
+    a, ca = ctx.simulate(7, 5, 300)
+    b, cb = O.simulate(m["parent"], m["brlen"], m["Q"], m["pi"], m["rates"], m["probs"], 7, 5, 300)
+    assert np.array_equal(a, b) and np.array_equal(ca, cb)
+
+
+@pytest.mark.parametrize("stat", ["correlation", "covariance", "cosinus", "cosubstitution", "compensation"])
+def test_pairs_all_statistics_vs_oracle(ctx, stat):
+    c = _case()
+    r = _setup(ctx, c)
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    g, k = ctx.pairs(stat, use_null=False)
+    o = O.pairs(stat, q["n"], q["norm"], q["post_rate"], q["rate_class"])
+    assert k == len(o["i"]) == 150 * 149 // 2
+    assert np.array_equal(g["i"], o["i"]) and np.array_equal(g["j"], o["j"])  # reference row order
+    assert _close(g["stat"], o["stat"])
+    assert np.array_equal(g["rcmin"], o["rcmin"])
+    assert np.allclose(g["prmin"], o["prmin"], rtol=RTOL) and np.allclose(g["nmin"], o["nmin"], rtol=RTOL)
+    if stat == "cosubstitution":
+        assert np.array_equal(g["stat"], o["stat"])  # integer valued: exact
+
+
+def test_pairs_filters_and_shards(ctx):
+    c = _case(S=203)
+    _setup(ctx, c)
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    f = dict(min_rate_class=1, min_rate=0.3, max_rate_class_diff=1, max_rate_diff=1.0, min_stat=0.05)
+    g, k = ctx.pairs("correlation", use_null=False, filters=f)
+    o = O.pairs("correlation", q["n"], q["norm"], q["post_rate"], q["rate_class"], **f)
+    assert k == len(o["i"]) and 0 < k < 203 * 202 // 2
+    assert np.array_equal(g["i"], o["i"]) and np.array_equal(g["j"], o["j"])
+    assert _close(g["stat"], o["stat"])
+    # row shards partition the full result
+    full, _ = ctx.pairs("correlation", use_null=False)
+    parts = [ctx.pairs("correlation", use_null=False, shard_index=s, shard_count=3)[0] for s in range(3)]
+    key = np.concatenate([p["i"].astype(np.int64) * 203 + p["j"] for p in parts])
+    order = np.argsort(key, kind="stable")
+    assert np.array_equal(key[order], full["i"].astype(np.int64) * 203 + full["j"])
+    assert np.array_equal(np.concatenate([p["stat"] for p in parts])[order], full["stat"])
+    sizes = [len(p["i"]) for p in parts]
+    assert max(sizes) - min(sizes) < 203 * 4  # balanced
+
+
+def _eq(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    return np.array_equal(np.isnan(a), np.isnan(b)) and np.array_equal(a[~np.isnan(a)], b[~np.isnan(b)])
+
+
+def test_null_from_alignments_vs_oracle(ctx):
+    """Same simulated alignments in -> same null distribution out (1e-9 on the statistics,
+    identical bin occupancy)."""
+    c = _case(T=16, S=120, seed=5)
+    r = _setup(ctx, c)
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    rep_cpu, rep_ram, K = 4, 300, 6
+    s1 = np.stack([ctx.simulate(99, (2 * i) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    s2 = np.stack([ctx.simulate(99, (2 * i + 1) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    nmax = float(q["norm"].max())
+    assert abs(nmax - r["norm"].max()) <= 1e-12 * nmax
+    raw = ctx.null_intra_from_alignments("correlation", s1, s2, K=K, nmax=nmax)
+    o = O.null_intra(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], "correlation", s1, s2, K, nmax)
+    assert _close(raw[:, 0], o["raw"][:, 0])
+    assert np.array_equal(raw[:, 1], o["raw"][:, 1])
+    assert np.allclose(raw[:, 2:], o["raw"][:, 2:], rtol=RTOL)
+    g = ctx.null_get()
+    assert g["K"] == K and np.array_equal(g["bin_offsets"], o["bin_offsets"])
+    fin = ~np.isnan(o["sorted"])
+    assert _close(g["sorted"][fin], o["sorted"][fin])
+
+
+@pytest.mark.parametrize("stat", ["correlation", "covariance", "cosinus", "cosubstitution", "compensation"])
+def test_statistics_and_pvalues_bit_exact_given_vectors(ctx, stat):
+    """north_star: null counts and p-values bit-exact.  p = (nsim - #{sim < stat} + 1)/(nsim + 1)
+    with massive ties among low-rate sites (r = 1 between constant sites), so one ulp moves
+    counts by dozens.  The pair kernels therefore replicate the reference's operation order
+    without fused multiply-adds: fed the SAME mapping vectors, statistics, bin occupancy,
+    counts and p-values equal the CPU restatement bit for bit."""
+    c = _case(T=16, S=120, seed=5)
+    r = _setup(ctx, c)
+    rep_cpu, rep_ram, K = 3, 200, 6
+    s1 = np.stack([ctx.simulate(99, (2 * i) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    s2 = np.stack([ctx.simulate(99, (2 * i + 1) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    nmax = 0.6 * float(r["norm"].max())  # some pairs fall outside [0, nmax) -> "NA\t0" rows
+    raw = ctx.null_intra_from_alignments(stat, s1, s2, K=K, nmax=nmax)
+    g = ctx.null_get()
+    gp, k = ctx.pairs(stat, use_null=True)
+    # device mapping vectors of the simulated batches, then the CPU restatement on them
+    mask = syn.identity_code_mask(4)
+    exp_stat, exp_nmin = [], []
+    for i in range(rep_cpu):
+        ctx.set_alignment(s1[i], mask); m1 = ctx.map()
+        ctx.set_alignment(s2[i], mask); m2 = ctx.map()
+        for j in range(rep_ram):
+            exp_stat.append(O.stat(stat, m1["n"][j], m2["n"][j]))
+            exp_nmin.append(min(np.sqrt((m1["n"][j] ** 2).sum()), np.sqrt((m2["n"][j] ** 2).sum())))
+    assert _eq(raw[:, 0], exp_stat)
+    cat = np.array([O.domain_index(0, nmax, K, x) for x in raw[:, 3]])
+    assert np.array_equal(np.diff(g["bin_offsets"]), np.bincount(cat[cat >= 0], minlength=K))
+    op = O.pairs(stat, r["n"], r["norm"], r["post_rate"], r["rate_class"], null=(K, nmax, g["bin_offsets"], g["sorted"]))
+    assert k == len(op["i"])
+    assert _eq(gp["stat"], op["stat"])
+    assert np.array_equal(gp["nsim"], op["nsim"])
+    assert _eq(gp["pvalue"], op["pvalue"])
+    assert np.array_equal(gp["nmin"], op["nmin"]) and np.array_equal(gp["prmin"], op["prmin"])
+    assert (gp["nsim"] == 0).any() and np.all(np.isnan(gp["pvalue"][gp["nsim"] == 0]))  # "NA\t0" rows
+
+
+def test_null_intra_device_rng_equals_exported_alignments(ctx):
+    """cmb_null_intra (device RNG) == cmb_null_intra_from_alignments on the alignments that
+    cmb_simulate exports for the same global site indices; shards concatenate."""
+    c = _case(T=16, S=60, seed=8)
+    _setup(ctx, c)
+    rep_cpu, rep_ram, K = 5, 128, 4
+    raw = ctx.null_intra("correlation", 4242, rep_cpu, rep_ram, K=K, nmax=2.0, want_raw=True)
+    s1 = np.stack([ctx.simulate(4242, (2 * i) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    s2 = np.stack([ctx.simulate(4242, (2 * i + 1) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    raw2 = ctx.null_intra_from_alignments("correlation", s1, s2, K=K, nmax=2.0)
+    assert np.array_equal(np.isnan(raw), np.isnan(raw2))
+    assert np.array_equal(np.nan_to_num(raw), np.nan_to_num(raw2))
+    a = ctx.null_intra("correlation", 4242, rep_cpu, rep_ram, K=0, rep_begin=0, rep_end=2, want_raw=True)
+    b = ctx.null_intra("correlation", 4242, rep_cpu, rep_ram, K=0, rep_begin=2, rep_end=5, want_raw=True)
+    assert np.array_equal(np.nan_to_num(np.concatenate([a, b])), np.nan_to_num(raw))
+
+
+def test_null_other_statistics(ctx):
+    c = _case(T=12, S=40, seed=9)
+    _setup(ctx, c)
+    rep_cpu, rep_ram = 2, 200
+    s1 = np.stack([ctx.simulate(1, (2 * i) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    s2 = np.stack([ctx.simulate(1, (2 * i + 1) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+    for stat in ("cosubstitution", "compensation", "cosinus", "covariance"):
+        raw = ctx.null_intra_from_alignments(stat, s1, s2, K=3, nmax=3.0)
+        o = O.null_intra(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], stat, s1, s2, 3, 3.0)
+        assert _close(raw[:, 0], o["raw"][:, 0]), stat
+        assert np.array_equal(ctx.null_get()["bin_offsets"], o["bin_offsets"])

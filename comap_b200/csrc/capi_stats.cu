@@ -141,6 +141,107 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
   else CMB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+
+struct GroupTable {
+  std::vector<int32_t> members;
+  std::vector<int64_t> offsets{0};
+  std::vector<double> height, stat, nmin;
+};
+
+// distance matrix of the [B][n_pad] vectors into c.d_dist (CoMap.cpp:432-440)
+void distance_on_device(Context& c, int dist_id, const double* out, int64_t S, int64_t S_pad, const double* mean,
+                        const double* sd, const double* norm) {
+  if (dist_id < 0 || dist_id > 2) fail("unknown distance id %d", dist_id);
+  constexpr int TS = 64;
+  std::vector<int2> tiles;
+  const int64_t nt = (S + TS - 1) / TS;
+  for (int64_t ti = 0; ti < nt; ti++)
+    for (int64_t tj = ti; tj < nt; tj++) tiles.push_back(make_int2((int)ti, (int)tj));
+  c.scratch.reserve(tiles.size() * 8 + 256);
+  CMB_CUDA(cudaMemcpyAsync(c.scratch.p, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice, c.stream));
+  c.d_dist.reserve(sizeof(double) * (size_t)S * S);
+  TilesLaunch L;
+  L.dist_mode = true;
+  L.stat_id = dist_id == 0 ? 0 : dist_id == 1 ? 4 : 5;
+  L.dist_is_stat = dist_id == 2;
+  L.dist_comp = 1.; // StatisticBasedDistance(cor, 1.) (CoMap.cpp:410); CompensationDistance = 1 - stat
+  L.B = c.tree.B; L.S = S; L.S_pad = S_pad; L.out = out; L.mean = mean; L.sd = sd; L.norm = norm;
+  L.tiles = c.scratch.as<int2>(); L.n_tiles = (int64_t)tiles.size(); L.n_rows = S; L.mat = c.d_dist.as<double>();
+  c.prof_begin("distance");
+  int nl = launch_tiles(L, c.stream);
+  c.prof_end(nl);
+  CMB_CUDA(cudaStreamSynchronize(c.stream)); // tiles vector goes out of scope
+}
+
+void cluster_on_device(Context& c, int linkage, int64_t S) {
+  if (linkage < 0 || linkage > 2) fail("unknown clustering method %d", linkage);
+  if (S < 2) fail("clustering needs at least 2 sites");
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  size_t o_l = 0, o_r = al(4 * S), o_h = al(o_r + 4 * S);
+  c.staging.reserve(al(o_h + 8 * S));
+  unsigned char* sb = c.staging.as<unsigned char>();
+  c.prof_begin("cluster");
+  int nl = launch_cluster(S, linkage, c.d_dist.as<double>(), c.scratch2, (int32_t*)(sb + o_l), (int32_t*)(sb + o_r),
+                          (double*)(sb + o_h), c.stream);
+  c.prof_end(nl);
+  c.h_left.resize(S - 1); c.h_right.resize(S - 1); c.h_height.resize(S - 1);
+  CMB_CUDA(cudaMemcpyAsync(c.h_left.data(), sb + o_l, 4 * (S - 1), cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaMemcpyAsync(c.h_right.data(), sb + o_r, 4 * (S - 1), cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaMemcpyAsync(c.h_height.data(), sb + o_h, 8 * (S - 1), cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaStreamSynchronize(c.stream));
+  for (int64_t k = 0; k + 1 < S; k++)
+    if (c.h_left[k] < 0) fail("clustering stopped early: the distance matrix holds NaN");
+}
+
+// One group per inner node of the dendrogram, emitted in post-order with members in DFS
+// leaf order (ClusterTools::getGroups, ClusterTools.cpp:59-113), Nmin = min leaf norm
+// (:296-319), Stat per Distance::setStatisticAsProperty (Distance.h:109-129,346-368,
+// 390-422), size filter of CoMap.cpp:517.
+void groups_of_dendrogram(Context& c, int dist_id, int max_size, int64_t S, int64_t S_pad, const double* out_dev,
+                          const double* h_norm, GroupTable& g) {
+  if (max_size < 1) fail("clustering.maximum_group_size must be positive");
+  const std::vector<int32_t>&left = c.h_left, &right = c.h_right;
+  const int32_t root = (int32_t)(2 * S - 2);
+  std::vector<int32_t> stack{root}, dfs;
+  std::vector<char> state(2 * S, 0);
+  std::vector<int64_t> first(2 * S, 0);
+  dfs.reserve(S);
+  while (!stack.empty()) {
+    int32_t v = stack.back();
+    if (v < S) { first[v] = (int64_t)dfs.size(); dfs.push_back(v); stack.pop_back(); continue; }
+    if (state[v] == 0) { first[v] = (int64_t)dfs.size(); state[v] = 1; stack.push_back(left[v - S]); continue; }
+    if (state[v] == 1) { state[v] = 2; stack.push_back(right[v - S]); continue; }
+    stack.pop_back();
+    const int64_t cnt = (int64_t)dfs.size() - first[v];
+    if (cnt > max_size) continue;
+    double nmin = INFINITY;
+    for (int64_t k = 0; k < cnt; k++) {
+      int32_t mmb = dfs[first[v] + k];
+      g.members.push_back(mmb);
+      if (h_norm[mmb] < nmin) nmin = h_norm[mmb];
+    }
+    g.offsets.push_back((int64_t)g.members.size());
+    const double h = c.h_height[v - S];
+    g.height.push_back(h);
+    g.nmin.push_back(nmin);
+    g.stat.push_back(dist_id == 0 ? 1. - 2 * h : 2 * h); // compensation filled below
+  }
+  if (dist_id == 1 && !g.height.empty()) {
+    const size_t ng = g.height.size();
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t o_m = 0, o_o = al(4 * g.members.size()), o_s = al(o_o + 8 * (ng + 1));
+    c.scratch.reserve(al(o_s + 8 * ng));
+    unsigned char* sb = c.scratch.as<unsigned char>();
+    CMB_CUDA(cudaMemcpyAsync(sb + o_m, g.members.data(), 4 * g.members.size(), cudaMemcpyHostToDevice, c.stream));
+    CMB_CUDA(cudaMemcpyAsync(sb + o_o, g.offsets.data(), 8 * (ng + 1), cudaMemcpyHostToDevice, c.stream));
+    launch_group_compensation((int64_t)ng, (const int32_t*)(sb + o_m), (const int64_t*)(sb + o_o), c.tree.B, S_pad,
+                              out_dev, (double*)(sb + o_s), c.stream);
+    c.prof.total_launches += 1;
+    CMB_CUDA(cudaMemcpyAsync(g.stat.data(), sb + o_s, 8 * ng, cudaMemcpyDeviceToHost, c.stream));
+    CMB_CUDA(cudaStreamSynchronize(c.stream));
+  }
+}
+
 } // namespace
 
 extern "C" {
@@ -350,10 +451,107 @@ int cmb_pairs(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int32_t use_n
   CMB_CATCH
 }
 
-#define CMB_TODO(name) CMB_TRY fail(name ": not implemented yet"); CMB_CATCH
-int cmb_distance_matrix(cmb_ctx*, int32_t, double*) { CMB_TODO("cmb_distance_matrix") }
-int cmb_cluster(cmb_ctx*, int32_t, int32_t*, int32_t*, double*) { CMB_TODO("cmb_cluster") }
-int cmb_groups(cmb_ctx*, int32_t, int32_t, int32_t*, int64_t*, double*, double*, double*, int64_t*) { CMB_TODO("cmb_groups") }
-int cmb_cluster_null(cmb_ctx*, int32_t, int32_t, uint64_t, int32_t, int32_t, int32_t, int32_t, int64_t, int64_t, int32_t*, int32_t*, double*, double*, double*, int32_t*, int64_t*, int64_t*) { CMB_TODO("cmb_cluster_null") }
+int cmb_distance_matrix(cmb_ctx* ctx, int32_t dist_id, double* mat) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (!c.mapped) fail("cmb_distance_matrix: call cmb_map first");
+  distance_on_device(c, dist_id, c.d_out.as<double>(), c.S, c.S_pad, c.pairs_mean.as<double>(),
+                     c.pairs_sd.as<double>(), c.pairs_norm.as<double>());
+  c.have_dist = true;
+  c.dist_id = dist_id;
+  if (mat) {
+    CMB_CUDA(cudaMemcpyAsync(mat, c.d_dist.p, sizeof(double) * (size_t)c.S * c.S, cudaMemcpyDeviceToHost, c.stream));
+    CMB_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  CMB_CATCH
+}
+
+int cmb_cluster(cmb_ctx* ctx, int32_t linkage, int32_t* left, int32_t* right, double* height) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (!c.have_dist) fail("cmb_cluster: call cmb_distance_matrix first");
+  cluster_on_device(c, linkage, c.S);
+  c.have_dist = false; // the matrix is consumed
+  c.have_dendro = true;
+  const int64_t n = c.S - 1;
+  if (left) std::memcpy(left, c.h_left.data(), sizeof(int32_t) * n);
+  if (right) std::memcpy(right, c.h_right.data(), sizeof(int32_t) * n);
+  if (height) std::memcpy(height, c.h_height.data(), sizeof(double) * n);
+  CMB_CATCH
+}
+
+int cmb_groups(cmb_ctx* ctx, int32_t dist_id, int32_t max_size, int32_t* members, int64_t* offsets, double* g_height,
+               double* g_stat, double* g_nmin, int64_t* n_groups) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (!c.have_dendro) fail("cmb_groups: call cmb_cluster first");
+  GroupTable g;
+  groups_of_dendrogram(c, dist_id, max_size, c.S, c.S_pad, c.d_out.as<double>(), c.h_norm.data(), g);
+  const int64_t ng = (int64_t)g.height.size();
+  if (members && !g.members.empty()) std::memcpy(members, g.members.data(), sizeof(int32_t) * g.members.size());
+  if (offsets) std::memcpy(offsets, g.offsets.data(), sizeof(int64_t) * (ng + 1));
+  if (g_height && ng) std::memcpy(g_height, g.height.data(), sizeof(double) * ng);
+  if (g_stat && ng) std::memcpy(g_stat, g.stat.data(), sizeof(double) * ng);
+  if (g_nmin && ng) std::memcpy(g_nmin, g.nmin.data(), sizeof(double) * ng);
+  if (n_groups) *n_groups = ng;
+  CMB_CATCH
+}
+
+int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t seed, int32_t rep_begin, int32_t rep_end,
+                     int32_t weighted_classes, int32_t max_size, int64_t capacity_rows, int64_t capacity_members,
+                     int32_t* row_rep, int32_t* row_size, double* row_dmax, double* row_stat, double* row_nmin,
+                     int32_t* members, int64_t* offsets, int64_t* n_rows) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (!c.have_alignment) fail("cmb_cluster_null: the data set size comes from the alignment (cmb_set_alignment)");
+  if (rep_begin < 0 || rep_end < rep_begin) fail("cmb_cluster_null: bad replicate range");
+  c.ensure_streams();
+  const int64_t S = c.S, S_pad = c.S_pad;
+  const int B = c.tree.B;
+  MapModel m = c.map_model();
+  int64_t rows = 0, mem = 0;
+  if (offsets) offsets[0] = 0;
+  DevBuf mean, sd, norm;
+  std::vector<double> h_norm(S);
+  for (int rep = rep_begin; rep < rep_end; rep++) {
+    // ClusterTools.cpp:224-227: simulate sizeOfDataSet sites, re-initialise, map
+    MapBuffers b = sim_buffers(c, 0, S, S_pad);
+    c.prof_begin("simulate");
+    launch_simulate(m, c.sim_stream, seed, (int64_t)rep * S, S, 0, S, S_pad, weighted_classes, c.tree.n_nodes - 1,
+                    c.s_tips[0].as<uint8_t>(), nullptr, c.stream);
+    c.prof_end(1);
+    c.run_map(b, true);
+    mean.reserve(sizeof(double) * S_pad); sd.reserve(sizeof(double) * S_pad); norm.reserve(sizeof(double) * S_pad);
+    launch_prep(B, S, S_pad, b.out, mean.as<double>(), sd.as<double>(), norm.as<double>(), c.stream);
+    c.prof.total_launches += 1;
+    CMB_CUDA(cudaMemcpyAsync(h_norm.data(), norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+    distance_on_device(c, dist_id, b.out, S, S_pad, mean.as<double>(), sd.as<double>(), norm.as<double>());
+    cluster_on_device(c, linkage, S);
+    GroupTable g;
+    groups_of_dendrogram(c, dist_id, max_size, S, S_pad, b.out, h_norm.data(), g);
+    const int64_t ng = (int64_t)g.height.size();
+    if (rows + ng > capacity_rows || mem + (int64_t)g.members.size() > capacity_members)
+      fail("cmb_cluster_null: output capacity exceeded");
+    for (int64_t k = 0; k < ng; k++) {
+      if (row_rep) row_rep[rows + k] = rep;
+      if (row_size) row_size[rows + k] = (int32_t)(g.offsets[k + 1] - g.offsets[k]);
+      if (row_dmax) row_dmax[rows + k] = g.height[k] * 2.; // ClusterTools.cpp:286
+      if (row_stat) row_stat[rows + k] = g.stat[k];
+      if (row_nmin) row_nmin[rows + k] = g.nmin[k];
+      if (offsets) offsets[rows + k + 1] = mem + g.offsets[k + 1];
+    }
+    if (members && !g.members.empty()) std::memcpy(members + mem, g.members.data(), sizeof(int32_t) * g.members.size());
+    rows += ng;
+    mem += (int64_t)g.members.size();
+  }
+  mean.release(); sd.release(); norm.release();
+  c.have_dendro = false;
+  if (n_rows) *n_rows = rows;
+  CMB_CATCH
+}
 
 } // extern "C"

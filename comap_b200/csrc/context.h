@@ -63,6 +63,7 @@ struct Context {
   // clustering
   DevBuf d_dist;                 // [S][S]
   bool have_dist = false;
+  int dist_id = 0;
   std::vector<int32_t> h_left, h_right;
   std::vector<double> h_height;
   bool have_dendro = false;

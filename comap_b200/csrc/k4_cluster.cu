@@ -1,0 +1,252 @@
+// K4: agglomerative clustering of sites on the device.
+//
+// Replaces Bio++ HierarchicalClustering(method, matrix, rootTree = false) + computeTree()
+// (call sites CoMap.cpp:460-485, ClusterTools.cpp:260-262):
+//   repeat while more than two clusters live: take the FIRST strictly smallest entry over
+//   live pairs i<j in id order; the parent takes slot i, slot j dies; distances to every
+//   other live k become w1 d(i,k) + w2 d(j,k) + w4 |d(i,k) - d(j,k)| with
+//   (.5,.5,+.5) complete, (.5,.5,-.5) single, (n_i/(n_i+n_j), n_j/(n_i+n_j), 0) average;
+//   height(parent) = d(i,j)/2; the last two clusters are joined at d/2.
+// The reference rescans the whole matrix per merge (O(S^3)); here one persistent
+// cooperative kernel keeps, per live row, the first minimum over live columns j>i
+// (value + column), so a merge costs an argmin over S cached row minima, one row/column
+// update and a rescan of the few rows whose cached minimum was invalidated -- O(S^2)
+// in the common case -- with the reference's tie-breaking preserved exactly.
+#include "kernels.h"
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace cmb {
+namespace {
+
+constexpr int CT = 512;
+
+struct ClusterParams {
+  int64_t S;
+  int linkage;
+  double* mat;          // [S][S] symmetric, consumed
+  double* rmin_val;     // [S] first minimum over live j>i
+  int32_t* rmin_idx;    // [S] its column, -1 if none
+  uint8_t* alive;       // [S]
+  double* len;          // [S] height of the cluster in the slot
+  int32_t* nleaves;     // [S]
+  int32_t* node;        // [S] dendrogram node in the slot
+  int32_t* wl;          // [2][S] worklist: row | (full ? 1<<31 : 0)
+  int32_t* wl_count;    // [2]
+  int32_t *left, *right; // [S-1]
+  double* height;       // [S-1]
+};
+
+struct Best { double v; int i; };
+__device__ __forceinline__ bool better(double v, int i, const Best& b) {
+  return b.i < 0 || v < b.v || (v == b.v && i < b.i);
+}
+__device__ __forceinline__ Best warp_best(Best b) {
+  for (int o = 16; o > 0; o >>= 1) {
+    double v = __shfl_down_sync(0xffffffffu, b.v, o);
+    int i = __shfl_down_sync(0xffffffffu, b.i, o);
+    if (i >= 0 && better(v, i, b)) { b.v = v; b.i = i; }
+  }
+  return b;
+}
+// block-wide argmin with smallest-index tie-break; result valid in every thread
+__device__ Best block_best(Best b, Best* sh) {
+  b = warp_best(b);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = b;
+  __syncthreads();
+  if (w == 0) {
+    Best t = l < (int)(blockDim.x >> 5) ? sh[l] : Best{0., -1};
+    t = warp_best(t);
+    if (l == 0) sh[0] = t;
+  }
+  __syncthreads();
+  return sh[0];
+}
+
+// first minimum of row r over live columns j>r (skipping `skip`)
+__device__ void rescan_row(const ClusterParams& p, int r, int skip, Best* sh) {
+  Best b{0., -1};
+  const double* row = p.mat + (size_t)r * p.S;
+  for (int64_t j = r + 1 + threadIdx.x; j < p.S; j += blockDim.x)
+    if (p.alive[j] && j != skip) {
+      double v = row[j];
+      if (better(v, (int)j, b) && !(v != v)) { b.v = v; b.i = (int)j; }
+    }
+  b = block_best(b, sh);
+  if (threadIdx.x == 0) { p.rmin_val[r] = b.v; p.rmin_idx[r] = b.i; }
+}
+
+__global__ void __launch_bounds__(CT) k4_init_rows(ClusterParams p) {
+  __shared__ Best sh[32];
+  for (int r = blockIdx.x; r < p.S; r += gridDim.x) {
+    rescan_row(p, r, -1, sh);
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
+  cg::grid_group grid = cg::this_grid();
+  __shared__ Best sh[32];
+  const int64_t S = p.S;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t step = 0; step + 2 < S; step++) {
+    // (1) first global minimum from the cached row minima (every CTA computes it)
+    Best b{0., -1};
+    for (int64_t i = threadIdx.x; i < S; i += blockDim.x)
+      if (p.alive[i] && p.rmin_idx[i] >= 0) {
+        double v = p.rmin_val[i];
+        if (better(v, (int)i, b)) { b.v = v; b.i = (int)i; }
+      }
+    b = block_best(b, sh);
+    const int a = b.i;
+    if (a < 0) return; // nothing mergeable (NaN distances): host reports the error
+    const int bb = p.rmin_idx[a];
+    const double dab = b.v;
+    double w1, w2, w4;
+    if (p.linkage == 1) { w1 = .5; w2 = .5; w4 = -.5; }
+    else if (p.linkage == 0) { w1 = .5; w2 = .5; w4 = .5; }
+    else {
+      double na = (double)p.nleaves[a], nb = (double)p.nleaves[bb];
+      w1 = na / (na + nb); w2 = nb / (na + nb); w4 = 0.;
+    }
+    // (A) new distances to the merged cluster (slot a); queue the rows whose cached
+    //     minimum has to be revisited
+    int32_t* wl = p.wl + (step & 1) * S;
+    int32_t* wlc = p.wl_count + (step & 1);
+    for (int64_t k = gtid; k < S; k += gsz) {
+      if (k == a || k == bb || !p.alive[k]) continue;
+      const double d1 = p.mat[(size_t)a * S + k], d2 = p.mat[(size_t)bb * S + k];
+      // left-to-right, unfused, as the reference's C++ expression evaluates
+      const double nd = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w1, d1), __dmul_rn(w2, d2)), __dmul_rn(0., dab)),
+                                  __dmul_rn(w4, fabs(__dadd_rn(d1, -d2))));
+      p.mat[(size_t)a * S + k] = nd;
+      p.mat[(size_t)k * S + a] = nd;
+      if (k < a) {
+        const int idx = p.rmin_idx[k];
+        const bool full = idx == a || idx == bb;
+        wl[atomicAdd(wlc, 1)] = (int32_t)k | (full ? (int32_t)0x80000000 : 0);
+      } else if (k < bb && p.rmin_idx[k] == bb) {
+        wl[atomicAdd(wlc, 1)] = (int32_t)k | (int32_t)0x80000000;
+      }
+    }
+    if (gtid == 0) wl[atomicAdd(wlc, 1)] = (int32_t)a | (int32_t)0x80000000;
+    grid.sync();
+    // (B) bookkeeping + cached minima
+    if (gtid == 0) {
+      const int32_t parent = (int32_t)(S + step);
+      const double half = dab / 2.;
+      const double d0 = half - p.len[a];
+      p.left[step] = p.node[a];
+      p.right[step] = p.node[bb];
+      p.height[step] = p.len[a] + d0;
+      p.node[a] = parent;
+      p.len[a] = p.len[a] + d0;
+      p.nleaves[a] += p.nleaves[bb];
+      p.alive[bb] = 0;
+      p.wl_count[(step + 1) & 1] = 0;
+    }
+    const int n_wl = *wlc;
+    for (int w = blockIdx.x; w < n_wl; w += gridDim.x) {
+      const int32_t e = wl[w];
+      const int r = e & 0x7fffffff;
+      if (e < 0) rescan_row(p, r, bb, sh);
+      else if (threadIdx.x == 0) {
+        const double nd = p.mat[(size_t)r * S + a];
+        const double cv = p.rmin_val[r];
+        const int ci = p.rmin_idx[r];
+        if (!(nd != nd) && (ci < 0 || nd < cv || (nd == cv && a < ci))) { p.rmin_val[r] = nd; p.rmin_idx[r] = a; }
+      }
+      __syncthreads();
+    }
+    grid.sync();
+  }
+  // finalStep: join the last two clusters at d/2
+  if (gtid == 0) {
+    int i1 = -1, i2 = -1;
+    for (int64_t i = 0; i < S; i++)
+      if (p.alive[i]) { if (i1 < 0) i1 = (int)i; else i2 = (int)i; }
+    const double d = p.mat[(size_t)i1 * S + i2] / 2;
+    p.left[S - 2] = p.node[i1];
+    p.right[S - 2] = p.node[i2];
+    p.height[S - 2] = p.len[i1] + (d - p.len[i1]);
+  }
+}
+
+__global__ void k4_init_state(ClusterParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.S) return;
+  p.alive[i] = 1;
+  p.len[i] = 0.;
+  p.nleaves[i] = 1;
+  p.node[i] = (int32_t)i;
+  if (i < 2) p.wl_count[i] = 0;
+  if (i < p.S - 1) { p.left[i] = -1; p.right[i] = -1; p.height[i] = 0.; }
+}
+
+// Compensation group statistic (Statistics.h:267-294): 1 - ||sum_j v_j|| / sum_j ||v_j||,
+// one thread per group, branches in id order, unfused arithmetic.
+__global__ void k4_group_compensation(int64_t n_groups, const int32_t* __restrict__ members,
+                                      const int64_t* __restrict__ offsets, int B, int64_t S_pad,
+                                      const double* __restrict__ out, double* __restrict__ stat) {
+  const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= n_groups) return;
+  const int64_t m0 = offsets[g], m1 = offsets[g + 1];
+  double sumsq2 = 0., sumnorms = 0.;
+  for (int b = 0; b < B; b++) {
+    double s = 0.;
+    for (int64_t m = m0; m < m1; m++) s = __dadd_rn(s, out[(size_t)b * S_pad + members[m]]);
+    sumsq2 = __dadd_rn(sumsq2, __dmul_rn(s, s));
+  }
+  for (int64_t m = m0; m < m1; m++) {
+    double q = 0.;
+    for (int b = 0; b < B; b++) {
+      double v = out[(size_t)b * S_pad + members[m]];
+      q = __dadd_rn(q, __dmul_rn(v, v));
+    }
+    sumnorms = __dadd_rn(sumnorms, sqrt(q));
+  }
+  stat[g] = __dadd_rn(1., -(sqrt(sumsq2) / sumnorms));
+}
+
+} // namespace
+
+int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* left_dev, int32_t* right_dev,
+                   double* height_dev, cudaStream_t st) {
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  size_t o_val = 0, o_idx = al(o_val + 8 * S), o_alive = al(o_idx + 4 * S), o_len = al(o_alive + S),
+         o_nl = al(o_len + 8 * S), o_node = al(o_nl + 4 * S), o_wl = al(o_node + 4 * S), o_wlc = al(o_wl + 8 * S),
+         o_end = al(o_wlc + 64);
+  work.reserve(o_end);
+  unsigned char* w = work.as<unsigned char>();
+  ClusterParams p;
+  p.S = S; p.linkage = linkage; p.mat = mat;
+  p.rmin_val = (double*)(w + o_val); p.rmin_idx = (int32_t*)(w + o_idx); p.alive = w + o_alive;
+  p.len = (double*)(w + o_len); p.nleaves = (int32_t*)(w + o_nl); p.node = (int32_t*)(w + o_node);
+  p.wl = (int32_t*)(w + o_wl); p.wl_count = (int32_t*)(w + o_wlc);
+  p.left = left_dev; p.right = right_dev; p.height = height_dev;
+  k4_init_state<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(p);
+  CMB_CUDA(cudaGetLastError());
+  int dev = 0, sms = 0, per_sm = 0;
+  CMB_CUDA(cudaGetDevice(&dev));
+  CMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_cluster, CT, 0));
+  if (per_sm < 1) fail("k4_cluster cannot be made resident");
+  int grid = sms; // one CTA per SM: enough threads for S up to ~75k columns per pass
+  k4_init_rows<<<grid, CT, 0, st>>>(p);
+  CMB_CUDA(cudaGetLastError());
+  void* args[] = {&p};
+  CMB_CUDA(cudaLaunchCooperativeKernel((void*)k4_cluster, dim3(grid), dim3(CT), args, 0, st));
+  return 3;
+}
+
+void launch_group_compensation(int64_t n_groups, const int32_t* members, const int64_t* offsets, int B,
+                               int64_t S_pad, const double* out, double* stat, cudaStream_t st) {
+  if (n_groups == 0) return;
+  k4_group_compensation<<<(unsigned)((n_groups + 127) / 128), 128, 0, st>>>(n_groups, members, offsets, B, S_pad, out, stat);
+  CMB_CUDA(cudaGetLastError());
+}
+
+} // namespace cmb

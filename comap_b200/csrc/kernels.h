@@ -94,4 +94,11 @@ void compact_column(int64_t n, const uint8_t* keep, const int64_t* pos, const T*
 // [B][n_pad] -> [n][B] for the host-facing site-major output
 void launch_transpose_out(const double* out, int B, int64_t n, int64_t n_pad, double* dst, cudaStream_t st);
 
+
+// ---- K4
+int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* left_dev, int32_t* right_dev,
+                   double* height_dev, cudaStream_t st);
+void launch_group_compensation(int64_t n_groups, const int32_t* members, const int64_t* offsets, int B,
+                               int64_t S_pad, const double* out, double* stat, cudaStream_t st);
+
 } // namespace cmb

@@ -55,19 +55,13 @@ void Context::ensure_streams() {
   if (streams_ready) return;
   build_model_tables(tables, A, Q.data(), pi.data(), C, rates.data(), probs.data(), count_method,
                      have_weights ? weights.data() : nullptr, tree.B, tree.brlen.data());
-  int cbmax = map_class_block(A, C);
-  class_blocks.clear();
-  for (int c0 = 0; c0 < C; c0 += cbmax) class_blocks.push_back({c0, std::min(cbmax, C - c0)});
-  for (auto& s : down_streams) s.release();
-  for (auto& s : up_streams) s.release();
-  down_streams.assign(class_blocks.size(), DevStream());
-  up_streams.assign(class_blocks.size(), DevStream());
-  for (size_t i = 0; i < class_blocks.size(); i++) {
+  check_map_support(A, C);
+  {
     OpStream os;
-    build_down_stream(os, tree, tables, class_blocks[i].first, class_blocks[i].second);
-    down_streams[i].upload(os, stream);
-    build_up_stream(os, tree, tables, class_blocks[i].first, class_blocks[i].second);
-    up_streams[i].upload(os, stream);
+    build_down_stream(os, tree, tables, 0, C);
+    down_stream.upload(os, stream);
+    build_up_stream(os, tree, tables, 0, C);
+    up_stream.upload(os, stream);
   }
   {
     OpStream os;
@@ -133,14 +127,12 @@ void Context::run_map(const MapBuffers& b, bool simulated) {
   MapModel m = map_model();
   if (simulated) m.code_mask = d_identity_mask.as<uint32_t>();
   prof_begin("map_down");
-  for (size_t i = 0; i < class_blocks.size(); i++)
-    launch_map_down(m, b, down_streams[i], class_blocks[i].first, class_blocks[i].second, stream);
+  launch_map_down(m, b, down_stream, stream);
   launch_map_finish(m, b, stream);
-  prof_end((int)class_blocks.size() + 1);
+  prof_end(2);
   prof_begin("map_up");
-  for (size_t i = 0; i < class_blocks.size(); i++)
-    launch_map_up(m, b, up_streams[i], class_blocks[i].first, class_blocks[i].second, i > 0, false, stream);
-  prof_end((int)class_blocks.size());
+  launch_map_up(m, b, up_stream, stream);
+  prof_end(1);
 }
 
 } // namespace cmb
@@ -212,8 +204,8 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
                     &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm};
   for (DevBuf* b : bufs) b->release();
-  for (auto& s : c.down_streams) s.release();
-  for (auto& s : c.up_streams) s.release();
+  c.down_stream.release();
+  c.up_stream.release();
   c.sim_stream.release();
   if (c.own_stream) cudaStreamDestroy(c.stream);
   delete ctx;
@@ -246,7 +238,7 @@ int cmb_set_model(cmb_ctx* ctx, int32_t A, const double* Q, const double* pi, in
   CMB_CUDA(cudaSetDevice(c.device));
   if (A < 2 || A > 32) fail("cmb_set_model: A must be in 2..32 (got %d)", A);
   if (C < 1 || C > 32) fail("cmb_set_model: C must be in 1..32 (got %d)", C);
-  map_class_block(A, C); // validates that kernels exist for this alphabet size
+  check_map_support(A, C);
   c.A = A; c.C = C; c.count_method = count_method;
   c.Q.assign(Q, Q + (size_t)A * A);
   c.pi.assign(pi, pi + A);
@@ -303,14 +295,12 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   c.d_pr.reserve(sizeof(double) * Sp);
   c.d_rc.reserve(sizeof(int32_t) * Sp);
   c.d_out.reserve(sizeof(double) * (size_t)B * Sp);
-  c.d_sum.reserve(sizeof(double) * Sp);
-  c.d_sumsq.reserve(sizeof(double) * Sp);
   MapBuffers b;
   b.n = S; b.n_pad = Sp;
   b.tips = c.d_tips.as<uint8_t>();
   b.D = c.d_D.as<double>(); b.Lc = c.d_Lc.as<double>(); b.invL = c.d_invL.as<double>();
   b.loglik = c.d_loglik.as<double>(); b.post_rate = c.d_pr.as<double>(); b.rate_class = c.d_rc.as<int32_t>();
-  b.out = c.d_out.as<double>(); b.sum = c.d_sum.as<double>(); b.sumsq = c.d_sumsq.as<double>();
+  b.out = c.d_out.as<double>();
   c.run_map(b, false);
   // per-site mean / sd / norm in the reference's summation order (k2_prep); norms are needed
   // on the host by the null (Domain upper bound) and for the caller

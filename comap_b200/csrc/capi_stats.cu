@@ -46,14 +46,12 @@ MapBuffers sim_buffers(Context& c, int k, int64_t n, int64_t n_pad) {
   c.s_pr[k].reserve(sizeof(double) * n_pad);
   c.s_rc[k].reserve(sizeof(int32_t) * n_pad);
   c.s_out[k].reserve(sizeof(double) * (size_t)B * n_pad);
-  c.s_sum[k].reserve(sizeof(double) * n_pad);
-  c.s_sumsq[k].reserve(sizeof(double) * n_pad);
   MapBuffers b;
   b.n = n; b.n_pad = n_pad;
   b.tips = c.s_tips[k].as<uint8_t>();
   b.D = c.s_D.as<double>(); b.Lc = c.s_Lc.as<double>(); b.invL = c.s_invL.as<double>();
   b.loglik = c.s_loglik.as<double>(); b.post_rate = c.s_pr[k].as<double>(); b.rate_class = c.s_rc[k].as<int32_t>();
-  b.out = c.s_out[k].as<double>(); b.sum = c.s_sum[k].as<double>(); b.sumsq = c.s_sumsq[k].as<double>();
+  b.out = c.s_out[k].as<double>();
   return b;
 }
 

@@ -40,9 +40,7 @@ struct Context {
 
   // device-resident model + op streams
   DevBuf d_code_mask, d_pi, d_rates, d_probs;
-  std::vector<DevStream> down_streams, up_streams; // one per class block
-  std::vector<std::pair<int, int>> class_blocks;   // (c0, cb)
-  DevStream sim_stream;
+  DevStream down_stream, up_stream, sim_stream;
   bool streams_ready = false;
 
   // observed alignment + its mapping

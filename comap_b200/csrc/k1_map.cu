@@ -6,7 +6,10 @@
 // AnalysisTools.cpp:592-611.
 //
 // Design (DESIGN.md "K1"):
-//   * one thread per site, a block of CB rate classes in registers; 256 sites per CTA;
+//   * one warp per (32-site group, rate class): lane = site, so every table read is a
+//     warp-uniform 128-bit shared load and every partial access is a coalesced 256-byte
+//     row; the C class-warps of a site group sit in the same CTA and combine their
+//     class terms through shared memory in a fixed order (deterministic, no atomics);
 //   * the tree walk is a precompiled op stream (schedule.cpp) whose records carry the
 //     branch transition matrices P_c(b) and reward matrices W_c(b) = p_c P o n; the CTA
 //     streams it through shared memory with double-buffered TMA bulk copies, so table
@@ -24,8 +27,6 @@
 namespace cmb {
 
 namespace {
-
-constexpr int NT = 256;
 
 struct ChunkMeta {
   const unsigned char* src;
@@ -114,81 +115,117 @@ __device__ __forceinline__ TipInfo read_tip(const uint8_t* __restrict__ tips, co
   return t;
 }
 
+__device__ __forceinline__ TipInfo tip_from_code(const uint32_t* __restrict__ code_mask, uint32_t code) {
+  TipInfo t;
+  t.mask = __ldg(code_mask + code);
+  bool single = t.mask != 0 && (t.mask & (t.mask - 1)) == 0;
+  t.state = __ffs(t.mask) - 1;
+  t.fast = __all_sync(0xffffffffu, single);
+  return t;
+}
+
 // ------------------------------------------------------------------------------ down
-template <int A, int CB>
-__global__ void __launch_bounds__(NT) k1_down(MapModel m, MapBuffers b, ChunkMeta cm, int c0) {
+struct WarpMap {
+  int c;        // rate class of this warp
+  int g;        // site group inside the CTA
+  int64_t site; // site of this lane
+};
+__device__ __forceinline__ WarpMap warp_map(int C, int groups) {
+  const int w = threadIdx.x >> 5;
+  WarpMap m;
+  m.c = w % C;
+  m.g = w / C;
+  m.site = ((int64_t)blockIdx.x * groups + m.g) * 32 + (threadIdx.x & 31);
+  return m;
+}
+
+template <int A>
+__global__ void __launch_bounds__(256) k1_down(MapModel m, MapBuffers b, ChunkMeta cm, int groups) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int N = CB * A * A;
-  const int64_t site = (int64_t)blockIdx.x * NT + threadIdx.x;
-  const int64_t n_pad = b.n_pad;
+  constexpr int AA = A * A;
+  const WarpMap wm = warp_map(m.C, groups);
+  const int64_t site = wm.site, n_pad = b.n_pad;
+  const int N = m.C * AA; // doubles per table (all classes)
   ChunkStream cs{cm.src, cm.off, cm.bytes, cm.n_chunks, cm.cap, nullptr, nullptr};
   cs.start(smem + 128, reinterpret_cast<uint64_t*>(smem));
 
-  double cur[CB * A];
-  double stk[kMaxStack][CB * A];
+  double cur[A];
+  double stk[kMaxStack][A];
   int sp = 0;
 #pragma unroll
-  for (int i = 0; i < CB * A; i++) cur[i] = 0.;
+  for (int i = 0; i < A; i++) cur[i] = 0.;
 
+  // software pipeline: the tip codes of the next record are loaded while this one computes
+  auto fetch_tips = [&](const unsigned char* rec, uint32_t& ca, uint32_t& cb) {
+    const int4 h = *reinterpret_cast<const int4*>(rec);
+    ca = ((uint32_t)h.x & kDownTipA) ? b.tips[(size_t)h.y * n_pad + site] : 0u;
+    cb = ((uint32_t)h.x & kDownTipB) ? b.tips[(size_t)h.z * n_pad + site] : 0u;
+  };
+  uint32_t code_a = 0, code_b = 0;
+  const unsigned char* rp = cs.wait(0);
+  fetch_tips(rp, code_a, code_b);
   for (uint32_t k = 0; k < cm.n_chunks; k++) {
-    const unsigned char* rp = cs.wait(k);
     const uint32_t nrec = __ldg(cm.nrec + k);
+    const unsigned char* next_chunk = nullptr;
     for (uint32_t r = 0; r < nrec; r++) {
       const int4 h = *reinterpret_cast<const int4*>(rp);
       const uint32_t flags = (uint32_t)h.x;
-      const double* tp = reinterpret_cast<const double*>(rp + 16);
-      double prod[CB * A];
+      const int ntab = 1 + ((flags & kDownTipA) ? 1 : 0) + ((flags & kDownPush) ? 1 : 0);
+      const unsigned char* rp_next = rp + ((16 + (size_t)ntab * N * sizeof(double) + 15) & ~size_t(15));
+      if (r + 1 == nrec) rp_next = next_chunk = (k + 1 < cm.n_chunks) ? cs.wait(k + 1) : nullptr;
+      uint32_t nca = 0, ncb = 0;
+      if (rp_next) fetch_tips(rp_next, nca, ncb);
+      const double* tp = reinterpret_cast<const double*>(rp + 16) + wm.c * AA;
+      double prod[A];
       if (flags & kDownTipB) {
-        TipInfo t = read_tip(b.tips, m.code_mask, h.z, n_pad, site);
-        if (t.fast) tip_column<A, CB>(tp, t.state, prod);
+        TipInfo t = tip_from_code(m.code_mask, code_b);
+        if (t.fast) tip_column<A, 1>(tp, t.state, prod);
         else {
-          double d[CB * A];
-          tip_dense<A, CB>(t.mask, d);
-          matvec<A, CB>(tp, d, prod);
+          double d[A];
+          tip_dense<A, 1>(t.mask, d);
+          matvec<A, 1>(tp, d, prod);
         }
-      } else matvec<A, CB>(tp, cur, prod);
+      } else matvec<A, 1>(tp, cur, prod);
       tp += N;
       if (flags & kDownTipA) {
-        double ma[CB * A];
-        TipInfo t = read_tip(b.tips, m.code_mask, h.y, n_pad, site);
-        if (t.fast) tip_column<A, CB>(tp, t.state, ma);
+        double ma[A];
+        TipInfo t = tip_from_code(m.code_mask, code_a);
+        if (t.fast) tip_column<A, 1>(tp, t.state, ma);
         else {
-          double d[CB * A];
-          tip_dense<A, CB>(t.mask, d);
-          matvec<A, CB>(tp, d, ma);
+          double d[A];
+          tip_dense<A, 1>(t.mask, d);
+          matvec<A, 1>(tp, d, ma);
         }
         tp += N;
 #pragma unroll
-        for (int i = 0; i < CB * A; i++) prod[i] *= ma[i];
+        for (int i = 0; i < A; i++) prod[i] *= ma[i];
       } else {
         --sp;
 #pragma unroll
-        for (int i = 0; i < CB * A; i++) prod[i] *= stk[sp][i];
+        for (int i = 0; i < A; i++) prod[i] *= stk[sp][i];
       }
 #pragma unroll
-      for (int i = 0; i < CB * A; i++) cur[i] = prod[i];
+      for (int i = 0; i < A; i++) cur[i] = prod[i];
       if (h.w >= 0) {
-        double* d = b.D + ((size_t)h.w * (m.C * A) + (size_t)c0 * A) * n_pad + site;
+        double* d = b.D + ((size_t)h.w * (m.C * A) + (size_t)wm.c * A) * n_pad + site;
 #pragma unroll
-        for (int i = 0; i < CB * A; i++) d[(size_t)i * n_pad] = cur[i];
+        for (int i = 0; i < A; i++) d[(size_t)i * n_pad] = cur[i];
       }
       if (flags & kDownPush) {
-        matvec<A, CB>(tp, cur, stk[sp]);
+        matvec<A, 1>(tp, cur, stk[sp]);
         ++sp;
-        tp += N;
       }
-      rp += (reinterpret_cast<const unsigned char*>(tp) - rp + 15) & ~size_t(15);
+      rp = rp_next;
+      code_a = nca;
+      code_b = ncb;
     }
     cs.release(k);
   }
-  // root: class likelihoods L_c = sum_x pi_x root[c][x]
+  // root: class likelihood L_c = sum_x pi_x root[c][x]
+  double l = 0.;
 #pragma unroll
-  for (int c = 0; c < CB; c++) {
-    double l = 0.;
-#pragma unroll
-    for (int x = 0; x < A; x++) l = fma(cur[c * A + x], __ldg(m.pi + x), l);
-    b.Lc[(size_t)(c0 + c) * n_pad + site] = l;
-  }
+  for (int x = 0; x < A; x++) l = fma(cur[x], __ldg(m.pi + x), l);
+  b.Lc[(size_t)wm.c * n_pad + site] = l;
 }
 
 // ---------------------------------------------------------------------------- finish
@@ -214,143 +251,155 @@ __global__ void k1_finish(MapModel m, MapBuffers b) {
 }
 
 // -------------------------------------------------------------------------------- up
-template <int A, int CB>
-__global__ void __launch_bounds__(NT) k1_up(MapModel m, MapBuffers b, ChunkMeta cm, int c0, int accumulate,
-                                            int with_norms) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int N = CB * A * A;
-  const int64_t site = (int64_t)blockIdx.x * NT + threadIdx.x;
-  const int64_t n_pad = b.n_pad;
-  ChunkStream cs{cm.src, cm.off, cm.bytes, cm.n_chunks, cm.cap, nullptr, nullptr};
-  cs.start(smem + 128, reinterpret_cast<uint64_t*>(smem));
+__device__ __forceinline__ void group_barrier(int g, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
+}
 
-  double G[CB * A];
-  double stk[kMaxStack][CB * A];
+template <int A>
+__global__ void __launch_bounds__(256) k1_up(MapModel m, MapBuffers b, ChunkMeta cm, int groups) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int AA = A * A;
+  const int C = m.C;
+  const WarpMap wm = warp_map(C, groups);
+  const int lane = threadIdx.x & 31;
+  const int64_t site = wm.site, n_pad = b.n_pad;
+  const int N = C * AA;
+  // smem: [0,128) mbarriers | red[2][groups][C][2][32] doubles | chunk buffers
+  double* red = reinterpret_cast<double*>(smem + 128);
+  const size_t red_bytes = ((size_t)2 * groups * C * 2 * 32 * sizeof(double) + 127) & ~size_t(127);
+  ChunkStream cs{cm.src, cm.off, cm.bytes, cm.n_chunks, cm.cap, nullptr, nullptr};
+  cs.start(smem + 128 + red_bytes, reinterpret_cast<uint64_t*>(smem));
+
+  double G[A];
+  double stk[kMaxStack][A];
   int sp = 0;
 #pragma unroll
-  for (int c = 0; c < CB; c++)
-#pragma unroll
-    for (int x = 0; x < A; x++) G[c * A + x] = __ldg(m.pi + x);
+  for (int x = 0; x < A; x++) G[x] = __ldg(m.pi + x);
   const double invL = b.invL[site];
-  double s1 = 0., s2 = 0.;
+  uint32_t node = 0;
+
+  // software pipeline: the partials (or tip codes) of the next record are in flight while
+  // this record computes
+  const size_t rec_bytes = 32 + (size_t)4 * N * sizeof(double);
+  auto fetch = [&](const unsigned char* rec, double (&da)[A], double (&db)[A], uint32_t& ca, uint32_t& cb) {
+    const int4 h0 = *reinterpret_cast<const int4*>(rec);
+    if ((uint32_t)h0.x & kUpTipA) ca = b.tips[(size_t)h0.y * n_pad + site];
+    else {
+      const double* d = b.D + ((size_t)h0.y * (C * A) + (size_t)wm.c * A) * n_pad + site;
+#pragma unroll
+      for (int i = 0; i < A; i++) da[i] = d[(size_t)i * n_pad];
+    }
+    if ((uint32_t)h0.x & kUpTipB) cb = b.tips[(size_t)h0.z * n_pad + site];
+    else {
+      const double* d = b.D + ((size_t)h0.z * (C * A) + (size_t)wm.c * A) * n_pad + site;
+#pragma unroll
+      for (int i = 0; i < A; i++) db[i] = d[(size_t)i * n_pad];
+    }
+  };
+  double Da[A], Db[A];
+  uint32_t code_a = 0, code_b = 0;
+  const unsigned char* rp = cs.wait(0);
+  fetch(rp, Da, Db, code_a, code_b);
 
   for (uint32_t k = 0; k < cm.n_chunks; k++) {
-    const unsigned char* rp = cs.wait(k);
     const uint32_t nrec = __ldg(cm.nrec + k);
-    for (uint32_t r = 0; r < nrec; r++) {
+    for (uint32_t r = 0; r < nrec; r++, node++) {
       const int4 h0 = *reinterpret_cast<const int4*>(rp);
       const int4 h1 = *reinterpret_cast<const int4*>(rp + 16);
       const uint32_t flags = (uint32_t)h0.x;
-      const int ref_a = h0.y, ref_b = h0.z, out_a = h0.w, out_b = h1.x;
-      const double* Pa = reinterpret_cast<const double*>(rp + 32);
+      const int out_a = h0.w, out_b = h1.x;
+      const double* Pa = reinterpret_cast<const double*>(rp + 32) + wm.c * AA;
       const double* Wa = Pa + N;
       const double* Pb = Wa + N;
       const double* Wb = Pb + N;
-      rp += 32 + (size_t)4 * N * sizeof(double);
+      const unsigned char* rp_next = rp + rec_bytes;
+      if (r + 1 == nrec) rp_next = (k + 1 < cm.n_chunks) ? cs.wait(k + 1) : nullptr;
+      double nDa[A], nDb[A];
+      uint32_t nca = 0, ncb = 0;
+      if (rp_next) fetch(rp_next, nDa, nDb, nca, ncb);
 
-      double Da[CB * A], Db[CB * A], Ma[CB * A], Mb[CB * A];
+      double Ma[A], Mb[A];
       TipInfo ta{0, 0, false}, tb{0, 0, false};
       const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB;
-      // issue all global loads of this node first
-      if (tipa) ta = read_tip(b.tips, m.code_mask, ref_a, n_pad, site);
-      else {
-        const double* d = b.D + ((size_t)ref_a * (m.C * A) + (size_t)c0 * A) * n_pad + site;
-#pragma unroll
-        for (int i = 0; i < CB * A; i++) Da[i] = d[(size_t)i * n_pad];
-      }
-      if (tipb) tb = read_tip(b.tips, m.code_mask, ref_b, n_pad, site);
-      else {
-        const double* d = b.D + ((size_t)ref_b * (m.C * A) + (size_t)c0 * A) * n_pad + site;
-#pragma unroll
-        for (int i = 0; i < CB * A; i++) Db[i] = d[(size_t)i * n_pad];
-      }
-      if (tipa && !ta.fast) tip_dense<A, CB>(ta.mask, Da);
-      if (tipb && !tb.fast) tip_dense<A, CB>(tb.mask, Db);
+      if (tipa) ta = tip_from_code(m.code_mask, code_a);
+      if (tipb) tb = tip_from_code(m.code_mask, code_b);
+      if (tipa && !ta.fast) tip_dense<A, 1>(ta.mask, Da);
+      if (tipb && !tb.fast) tip_dense<A, 1>(tb.mask, Db);
       const bool fasta = tipa && ta.fast, fastb = tipb && tb.fast;
-      if (fasta) tip_column<A, CB>(Pa, ta.state, Ma); else matvec<A, CB>(Pa, Da, Ma);
-      if (fastb) tip_column<A, CB>(Pb, tb.state, Mb); else matvec<A, CB>(Pb, Db, Mb);
-      // Ua = G o Mb (stored in Mb), Ub = G o Ma (stored in Ma)
+      if (fasta) tip_column<A, 1>(Pa, ta.state, Ma); else matvec<A, 1>(Pa, Da, Ma);
+      if (fastb) tip_column<A, 1>(Pb, tb.state, Mb); else matvec<A, 1>(Pb, Db, Mb);
 #pragma unroll
-      for (int i = 0; i < CB * A; i++) {
+      for (int i = 0; i < A; i++) {
         double g = G[i];
         double ua = g * Mb[i], ub = g * Ma[i];
         Mb[i] = ua;
         Ma[i] = ub;
       }
-      double (&Ua)[CB * A] = Mb;
-      double (&Ub)[CB * A] = Ma;
-      // contraction with the reward tables
+      double (&Ua)[A] = Mb;
+      double (&Ub)[A] = Ma;
+      // class term of the contraction with the reward tables (W includes p_c)
+      double acc_a = 0., acc_b = 0.;
       if (out_a >= 0) {
-        double acc = 0.;
         if (fasta) {
 #pragma unroll
-          for (int i = 0; i < CB * A; i++) acc = fma(Ua[i], Wa[i * A + ta.state], acc);
+          for (int i = 0; i < A; i++) acc_a = fma(Ua[i], Wa[i * A + ta.state], acc_a);
         } else {
-          double wd[CB * A];
-          matvec<A, CB>(Wa, Da, wd);
+          double wd[A];
+          matvec<A, 1>(Wa, Da, wd);
 #pragma unroll
-          for (int i = 0; i < CB * A; i++) acc = fma(Ua[i], wd[i], acc);
+          for (int i = 0; i < A; i++) acc_a = fma(Ua[i], wd[i], acc_a);
         }
-        double* o = b.out + (size_t)out_a * n_pad + site;
-        double val = acc * invL;
-        if (accumulate) val += *o;
-        *o = val;
-        s1 += val;
-        s2 = fma(val, val, s2);
       }
       if (out_b >= 0) {
-        double acc = 0.;
         if (fastb) {
 #pragma unroll
-          for (int i = 0; i < CB * A; i++) acc = fma(Ub[i], Wb[i * A + tb.state], acc);
+          for (int i = 0; i < A; i++) acc_b = fma(Ub[i], Wb[i * A + tb.state], acc_b);
         } else {
-          double wd[CB * A];
-          matvec<A, CB>(Wb, Db, wd);
+          double wd[A];
+          matvec<A, 1>(Wb, Db, wd);
 #pragma unroll
-          for (int i = 0; i < CB * A; i++) acc = fma(Ub[i], wd[i], acc);
+          for (int i = 0; i < A; i++) acc_b = fma(Ub[i], wd[i], acc_b);
         }
-        double* o = b.out + (size_t)out_b * n_pad + site;
-        double val = acc * invL;
-        if (accumulate) val += *o;
-        *o = val;
-        s1 += val;
-        s2 = fma(val, val, s2);
+      }
+      // combine the C class terms of this site group in class order; warp 0 of the group
+      // finishes branch a, warp 1 (if any) branch b
+      double* rb = red + ((size_t)((node & 1) * groups + wm.g) * C) * 64;
+      rb[(size_t)wm.c * 64 + lane] = acc_a;
+      rb[(size_t)wm.c * 64 + 32 + lane] = acc_b;
+      group_barrier(wm.g, 32 * C);
+      const int wb = C > 1 ? 1 : 0;
+      if (wm.c == 0 && out_a >= 0) {
+        double t = 0.;
+        for (int c = 0; c < C; c++) t += rb[(size_t)c * 64 + lane];
+        b.out[(size_t)out_a * n_pad + site] = t * invL;
+      }
+      if (wm.c == wb && out_b >= 0) {
+        double t = 0.;
+        for (int c = 0; c < C; c++) t += rb[(size_t)c * 64 + 32 + lane];
+        b.out[(size_t)out_b * n_pad + site] = t * invL;
       }
       // messages for the children that are expanded later
       if (flags & kUpTakeA) {
         if (flags & kUpPush) {
-          matvec_t<A, CB>(Pb, Ub, stk[sp]);
+          matvec_t<A, 1>(Pb, Ub, stk[sp]);
           ++sp;
         }
-        matvec_t<A, CB>(Pa, Ua, G);
+        matvec_t<A, 1>(Pa, Ua, G);
       } else if (flags & kUpTakeB) {
-        matvec_t<A, CB>(Pb, Ub, G);
+        matvec_t<A, 1>(Pb, Ub, G);
       } else if (flags & kUpPop) {
         --sp;
 #pragma unroll
-        for (int i = 0; i < CB * A; i++) G[i] = stk[sp][i];
+        for (int i = 0; i < A; i++) G[i] = stk[sp][i];
       }
+      rp = rp_next;
+      code_a = nca;
+      code_b = ncb;
+#pragma unroll
+      for (int i = 0; i < A; i++) { Da[i] = nDa[i]; Db[i] = nDb[i]; }
     }
     cs.release(k);
   }
-  if (with_norms) {
-    b.sum[site] = s1;
-    b.sumsq[site] = s2;
-  }
-}
-
-// sum_b n_b and sum_b n_b^2 per site from the finished vectors (multi-block case)
-__global__ void k1_norms(MapModel m, MapBuffers b) {
-  const int64_t site = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (site >= b.n_pad) return;
-  double s1 = 0., s2 = 0.;
-  for (int br = 0; br < m.B; br++) {
-    double v = b.out[(size_t)br * b.n_pad + site];
-    s1 += v;
-    s2 = fma(v, v, s2);
-  }
-  b.sum[site] = s1;
-  b.sumsq[site] = s2;
 }
 
 __global__ void k_transpose_out(const double* __restrict__ out, int B, int64_t n, int64_t n_pad,
@@ -376,55 +425,47 @@ ChunkMeta meta_of(const DevStream& s) {
                    s.nrec.as<uint32_t>(), s.n_chunks, s.cap};
 }
 
-template <int A, int CB>
-void run_down(const MapModel& m, const MapBuffers& b, const DevStream& s, int c0, cudaStream_t st) {
+int groups_per_cta(int C) { return C >= 8 ? 1 : 8 / C; }
+
+template <int A>
+void run_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  const int groups = groups_per_cta(m.C);
   size_t smem = 128 + 2 * (size_t)s.cap;
-  CMB_CUDA(cudaFuncSetAttribute(k1_down<A, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k1_down<A, CB><<<(unsigned)(b.n_pad / NT), NT, smem, st>>>(m, b, meta_of(s), c0);
+  CMB_CUDA(cudaFuncSetAttribute(k1_down<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1_down<A><<<(unsigned)(b.n_pad / (32 * groups)), 32 * groups * m.C, smem, st>>>(m, b, meta_of(s), groups);
   CMB_CUDA(cudaGetLastError());
 }
-template <int A, int CB>
-void run_up(const MapModel& m, const MapBuffers& b, const DevStream& s, int c0, bool acc, bool norms,
-            cudaStream_t st) {
-  size_t smem = 128 + 2 * (size_t)s.cap;
-  CMB_CUDA(cudaFuncSetAttribute(k1_up<A, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k1_up<A, CB><<<(unsigned)(b.n_pad / NT), NT, smem, st>>>(m, b, meta_of(s), c0, acc ? 1 : 0, norms ? 1 : 0);
+template <int A>
+void run_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  const int groups = groups_per_cta(m.C);
+  size_t red = ((size_t)2 * groups * m.C * 2 * 32 * sizeof(double) + 127) & ~size_t(127);
+  size_t smem = 128 + red + 2 * (size_t)s.cap;
+  CMB_CUDA(cudaFuncSetAttribute(k1_up<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1_up<A><<<(unsigned)(b.n_pad / (32 * groups)), 32 * groups * m.C, smem, st>>>(m, b, meta_of(s), groups);
   CMB_CUDA(cudaGetLastError());
 }
 
 } // namespace
 
-int map_class_block(int A, int C) {
-  if (A == 4) return C < 4 ? C : 4;
-  if (A == 20) return 1;
-  fail("mapping kernels are built for A = 4 (nucleotides) and A = 20 (proteins); got A = %d", A);
+void check_map_support(int A, int C) {
+  if (A != 4 && A != 20)
+    fail("mapping kernels are built for A = 4 (nucleotides) and A = 20 (proteins); got A = %d", A);
+  if (C < 1 || C > 8) fail("mapping kernels support 1..8 rate classes; got C = %d", C);
 }
 
-#define CMB_DISPATCH(FN, ...)                                                     \
-  do {                                                                            \
-    if (m.A == 4 && cb == 4) FN<4, 4>(__VA_ARGS__);                               \
-    else if (m.A == 4 && cb == 3) FN<4, 3>(__VA_ARGS__);                          \
-    else if (m.A == 4 && cb == 2) FN<4, 2>(__VA_ARGS__);                          \
-    else if (m.A == 4 && cb == 1) FN<4, 1>(__VA_ARGS__);                          \
-    else if (m.A == 20 && cb == 1) FN<20, 1>(__VA_ARGS__);                        \
-    else fail("no mapping kernel for A = %d, class block %d", m.A, cb);           \
-  } while (0)
-
-void launch_map_down(const MapModel& m, const MapBuffers& b, const DevStream& s, int c0, int cb,
-                     cudaStream_t st) {
-  if (b.n_pad % NT) fail("internal: n_pad must be a multiple of %d", NT);
-  CMB_DISPATCH(run_down, m, b, s, c0, st);
+void launch_map_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  if (b.n_pad % 256) fail("internal: n_pad must be a multiple of 256");
+  if (m.A == 4) run_down<4>(m, b, s, st);
+  else if (m.A == 20) run_down<20>(m, b, s, st);
+  else fail("no mapping kernel for A = %d", m.A);
 }
-void launch_map_up(const MapModel& m, const MapBuffers& b, const DevStream& s, int c0, int cb,
-                   bool accumulate, bool with_norms, cudaStream_t st) {
-  CMB_DISPATCH(run_up, m, b, s, c0, accumulate, with_norms, st);
+void launch_map_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  if (m.A == 4) run_up<4>(m, b, s, st);
+  else if (m.A == 20) run_up<20>(m, b, s, st);
+  else fail("no mapping kernel for A = %d", m.A);
 }
 void launch_map_finish(const MapModel& m, const MapBuffers& b, cudaStream_t st) {
   k1_finish<<<(unsigned)((b.n_pad + 255) / 256), 256, 0, st>>>(m, b);
-  CMB_CUDA(cudaGetLastError());
-}
-void launch_map_norms(const MapModel& m, const MapBuffers& b, cudaStream_t st) {
-  k1_norms<<<(unsigned)((b.n_pad + 255) / 256), 256, 0, st>>>(m, b);
   CMB_CUDA(cudaGetLastError());
 }
 void launch_transpose_out(const double* out, int B, int64_t n, int64_t n_pad, double* dst, cudaStream_t st) {

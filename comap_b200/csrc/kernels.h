@@ -21,8 +21,6 @@ struct MapBuffers {          // per-batch device arrays, n_pad sites (multiple o
   double* post_rate = nullptr;     // [n_pad]
   int32_t* rate_class = nullptr;   // [n_pad]
   double* out = nullptr;           // [B][n_pad]
-  double* sum = nullptr;           // [n_pad]  sum_b n_b
-  double* sumsq = nullptr;         // [n_pad]  sum_b n_b^2
 };
 
 struct MapModel {            // device-resident model constants
@@ -33,16 +31,10 @@ struct MapModel {            // device-resident model constants
   const double* probs = nullptr;       // [C]
 };
 
-// class block [c0, c0+cb) of the down (post-order) pass
-void launch_map_down(const MapModel& m, const MapBuffers& b, const DevStream& s, int c0, int cb,
-                     cudaStream_t st);
+void check_map_support(int A, int C); // throws when no kernel is built for (A, C)
+void launch_map_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
 void launch_map_finish(const MapModel& m, const MapBuffers& b, cudaStream_t st);
-// up (pre-order) pass + contraction; accumulate: add to out instead of overwrite;
-// with_norms: also write sum / sumsq (only valid when one block covers all classes)
-void launch_map_up(const MapModel& m, const MapBuffers& b, const DevStream& s, int c0, int cb,
-                   bool accumulate, bool with_norms, cudaStream_t st);
-void launch_map_norms(const MapModel& m, const MapBuffers& b, cudaStream_t st);
-int map_class_block(int A, int C); // classes per pass for this (A, C)
+void launch_map_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
 
 // site id of thread idx = base + (idx / group) * stride + idx % group
 void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,

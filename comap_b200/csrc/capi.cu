@@ -37,10 +37,15 @@ void DevStream::upload(const OpStream& s, cudaStream_t st) {
   CMB_CUDA(cudaMemcpyAsync(off.p, s.chunk_off.data(), sizeof(uint32_t) * n_chunks, cudaMemcpyHostToDevice, st));
   CMB_CUDA(cudaMemcpyAsync(nbytes.p, s.chunk_bytes.data(), sizeof(uint32_t) * n_chunks, cudaMemcpyHostToDevice, st));
   CMB_CUDA(cudaMemcpyAsync(nrec.p, s.chunk_nrec.data(), sizeof(uint32_t) * n_chunks, cudaMemcpyHostToDevice, st));
+  n_records = s.n_records;
+  if (!s.aux.empty()) {
+    aux.reserve(sizeof(int32_t) * s.aux.size());
+    CMB_CUDA(cudaMemcpyAsync(aux.p, s.aux.data(), sizeof(int32_t) * s.aux.size(), cudaMemcpyHostToDevice, st));
+  }
   CMB_CUDA(cudaStreamSynchronize(st)); // host vectors may go away
 }
 void DevStream::release() {
-  bytes.release(); off.release(); nbytes.release(); nrec.release();
+  bytes.release(); off.release(); nbytes.release(); nrec.release(); aux.release();
 }
 
 int64_t pad_sites(int64_t n) { return (n + 255) / 256 * 256; }

@@ -77,6 +77,8 @@ void build_tree(Tree& t, int n_nodes, const int32_t* parent, const double* brlen
 struct OpStream {
   std::vector<unsigned char> bytes;
   std::vector<uint32_t> chunk_off, chunk_bytes, chunk_nrec;
+  std::vector<int32_t> aux;   // 4 ints per record: flags, ref_a, ref_b, 0 (producer-side view)
+  uint32_t n_records = 0;
   uint32_t chunk_cap = 0; // largest chunk in bytes
 };
 constexpr uint32_t kDownTipA = 1, kDownTipB = 2, kDownPush = 4, kDownRoot = 8;

@@ -5,8 +5,8 @@
 namespace cmb {
 
 struct DevStream {           // an OpStream uploaded to the device
-  DevBuf bytes, off, nbytes, nrec;
-  uint32_t n_chunks = 0, cap = 0;
+  DevBuf bytes, off, nbytes, nrec, aux;
+  uint32_t n_chunks = 0, cap = 0, n_records = 0;
   void upload(const OpStream& s, cudaStream_t st);
   void release();
 };

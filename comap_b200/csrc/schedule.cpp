@@ -187,7 +187,7 @@ void append_table(std::vector<unsigned char>& rec, const Tree& t, const ModelTab
   }
 }
 
-uint32_t chunk_capacity(size_t max_rec) { return (uint32_t)std::max<size_t>(16384, max_rec); }
+uint32_t chunk_capacity(size_t max_rec) { return (uint32_t)std::max<size_t>(8192, max_rec); }
 
 } // namespace
 
@@ -257,6 +257,8 @@ static void up_like_stream(OpStream& s, const Tree& t, const ModelTables& mt, in
       h.out_a = t.bin[a].branch;
       h.out_b = t.bin[b].branch;
     }
+    s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.ref_a); s.aux.push_back(h.ref_b); s.aux.push_back(0);
+    s.n_records++;
     std::vector<unsigned char> rec;
     append(rec, &h, sizeof h);
     if (sim) {

@@ -61,6 +61,9 @@ void Context::ensure_streams() {
   build_model_tables(tables, A, Q.data(), pi.data(), C, rates.data(), probs.data(), count_method,
                      have_weights ? weights.data() : nullptr, tree.B, tree.brlen.data());
   check_map_support(A, C);
+  // cherries are recomputed instead of stored when their two extra tables per record are
+  // small (nucleotides); for A = 20 the records would outgrow the shared-memory budget
+  assign_slots(tree, A <= 4);
   {
     OpStream os;
     build_down_stream(os, tree, tables, 0, C);

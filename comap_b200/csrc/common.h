@@ -56,6 +56,7 @@ struct BinNode {
   int tip_row = -1;  // alignment row for leaves
   int slot = -1;     // storage slot of the down partial (inner, non-root)
   int leaves = 0;    // leaves below
+  bool cherry = false; // inner non-root node whose two children are leaves: no slot
   int orig = -1;     // original node id (-1 for virtual nodes)
 };
 
@@ -72,19 +73,21 @@ struct Tree {
   int down_depth = 0, up_depth = 0;
 };
 void build_tree(Tree& t, int n_nodes, const int32_t* parent, const double* brlen);
+void assign_slots(Tree& t, bool skip_cherries);
 
 // Packed op stream for one class block [c0, c0+cb).
 struct OpStream {
   std::vector<unsigned char> bytes;
   std::vector<uint32_t> chunk_off, chunk_bytes, chunk_nrec;
-  std::vector<int32_t> aux;   // 4 ints per record: flags, ref_a, ref_b, 0 (producer-side view)
+  std::vector<int32_t> aux;   // 8 ints per record: flags, ref_a, ref_b, 0, ref_a2, ref_b2, 0, 0 (producer-side view)
   uint32_t n_records = 0;
   uint32_t chunk_cap = 0; // largest chunk in bytes
 };
 constexpr uint32_t kDownTipA = 1, kDownTipB = 2, kDownPush = 4, kDownRoot = 8;
-constexpr uint32_t kUpTipA = 1, kUpTipB = 2, kUpPop = 4, kUpPush = 8, kUpTakeA = 16, kUpTakeB = 32;
+constexpr uint32_t kUpTipA = 1, kUpTipB = 2, kUpPop = 4, kUpPush = 8, kUpTakeA = 16, kUpTakeB = 32,
+                   kUpCherryA = 64, kUpCherryB = 128;
 struct DownHdr { uint32_t flags; int32_t row_a, row_b, slot; };
-struct UpHdr { uint32_t flags; int32_t ref_a, ref_b, out_a, out_b, pad0, pad1, pad2; };
+struct UpHdr { uint32_t flags; int32_t ref_a, ref_b, out_a, out_b, ref_a2, ref_b2, pad2; };
 void build_down_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb);
 void build_up_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb);
 // Simulation walk: per inner bin node (pre-order, smaller first), cumulative tables of

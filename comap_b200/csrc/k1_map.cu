@@ -23,12 +23,23 @@
 //   * nothing is accumulated with atomics: results are deterministic.
 #include <algorithm>
 #include <cstdlib>
+#include <vector>
+#include <cstdio>
 #include "device_utils.cuh"
 #include "kernels.h"
 
 namespace cmb {
 
 namespace {
+
+// Down partials live in HBM block-major: [site block of 256][slot][c*A+x][256 sites].  A CTA
+// of the up pass then walks one contiguous region (n_slots * C*A * 2 KB) instead of touching
+// a different 2 MB page for every row of every node -- with the flat [slot][row][n_pad]
+// layout the ring traffic alone ran at 2.2 TB/s (TLB / DRAM-page misses).
+constexpr int kDSites = 256;
+__host__ __device__ __forceinline__ size_t d_block(int64_t site_block, int slot, int n_slots, int rows) {
+  return ((size_t)site_block * n_slots + slot) * ((size_t)rows * kDSites);
+}
 
 struct ChunkMeta {
   const unsigned char* src;
@@ -107,16 +118,6 @@ struct TipInfo {
   int state;
   bool fast; // warp-uniform: every lane's tip is a single resolved state
 };
-__device__ __forceinline__ TipInfo read_tip(const uint8_t* __restrict__ tips, const uint32_t* __restrict__ code_mask,
-                                            int row, int64_t n_pad, int64_t site) {
-  TipInfo t;
-  t.mask = __ldg(code_mask + tips[(size_t)row * n_pad + site]);
-  bool single = t.mask != 0 && (t.mask & (t.mask - 1)) == 0;
-  t.state = __ffs(t.mask) - 1;
-  t.fast = __all_sync(0xffffffffu, single);
-  return t;
-}
-
 __device__ __forceinline__ TipInfo tip_from_code(const uint32_t* __restrict__ code_mask, uint32_t code) {
   TipInfo t;
   t.mask = __ldg(code_mask + code);
@@ -209,9 +210,9 @@ __global__ void __launch_bounds__(256) k1_down(MapModel m, MapBuffers b, ChunkMe
 #pragma unroll
       for (int i = 0; i < A; i++) cur[i] = prod[i];
       if (h.w >= 0) {
-        double* d = b.D + ((size_t)h.w * (m.C * A) + (size_t)wm.c * A) * n_pad + site;
+        double* d = b.D + d_block(site >> 8, h.w, m.n_slots, m.C * A) + (size_t)(wm.c * A) * kDSites + (site & (kDSites - 1));
 #pragma unroll
-        for (int i = 0; i < A; i++) d[(size_t)i * n_pad] = cur[i];
+        for (int i = 0; i < A; i++) d[i * kDSites] = cur[i];
       }
       if (flags & kDownPush) {
         matvec<A, 1>(tp, cur, stk[sp]);
@@ -253,62 +254,132 @@ __global__ void k1_finish(MapModel m, MapBuffers b) {
 }
 
 // -------------------------------------------------------------------------------- up
+// named barrier of site group g (immediate ids, so the kernel reserves 1 + 4 hardware
+// barriers instead of all 16 and two CTAs fit on an SM)
 __device__ __forceinline__ void group_barrier(int g, int nthreads) {
-  asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "r"(nthreads) : "memory");
+  switch (g) {
+    case 0: asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); break;
+    case 1: asm volatile("bar.sync 2, %0;" ::"r"(nthreads) : "memory"); break;
+    case 2: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
+    default: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
+  }
 }
-
-// Up pass with a producer/consumer pipeline: two producer warps stream (i) the table
-// chunks and (ii) the children's partials / tip codes of upcoming nodes into shared-memory
-// rings with cp.async.bulk (TMA bulk copies, mbarrier full/empty pairs); G*C consumer
-// warps never touch global memory on the read side, so the whole HBM latency is covered
-// by the ring depth instead of by occupancy.
-struct UpParams {
-  ChunkMeta cm;
-  const int4* refs;     // per node: flags, ref_a, ref_b, 0 (same values as the record header)
-  uint32_t n_nodes;
-  int groups, n_stages;
-  uint32_t stage_bytes; // bytes of one ring stage
-};
-
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-template <int A>
-__global__ void __launch_bounds__(320) k1_up(MapModel m, MapBuffers b, UpParams up) {
+// Up pass + contraction.  Shape of one CTA:
+//   * G*C consumer warps: warp = (site group g, rate class c); every lane owns NS sites
+//     (g*32*NS + k*32 + lane, k < NS); NS > 1 reuses each warp-uniform table row read from
+//     shared memory for NS sites (the table reads, not the fp64 pipe, load the SM most:
+//     ncu r1b, one site per lane: shared-memory wavefronts 58 % of peak, fp64 pipe 22 %);
+//   * producer warp 1 streams the table chunks (double buffered);
+//   * producer warp 2 streams, node by node, everything a node needs -- tip rows and the
+//     stored partials of its inner children -- into one stage of a ring with cp.async.bulk;
+//     one mbarrier full/empty pair per stage, producers back off with nanosleep.
+// Consumers never read partials from global memory, so HBM latency is covered by the ring
+// depth rather than by occupancy.  Cherry children (both grandchildren are tips) are not
+// stored by the down pass: their partial is recomputed here from two tip codes.
+// What bounds it (profiles/r1c, r1e): not HBM (ring traffic alone runs at 2.5 TB/s with the
+// math switched off) but per-warp latency -- shared-memory and fixed-latency dependencies
+// with 4 warps per SM sub-partition at 96 registers; see DESIGN.md "K1 up: what was tried".
+struct UpParams {
+  ChunkMeta cm;
+  const int4* refs;     // per node 2 x int4: (flags, ref_a, ref_b, 0), (ref_a2, ref_b2, 0, 0)
+  uint32_t n_nodes;
+  int groups;           // G
+  int n_blocks, n_tips; // stage ring depth (n_tips unused)
+  uint32_t block_bytes; // C*A*SG*8
+};
+constexpr int kMaxBlocks = 8; // stage ring depth
+
+template <int A, int NS>
+__device__ __forceinline__ void matvec_n(const double* __restrict__ T, const double (&v)[NS][A], double (&o)[NS][A]) {
+#pragma unroll
+  for (int x = 0; x < A; x++) {
+    double row[A];
+    load_row<A>(T + x * A, row);
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      double s = row[0] * v[k][0];
+#pragma unroll
+      for (int y = 1; y < A; y++) s = fma(row[y], v[k][y], s);
+      o[k][x] = s;
+    }
+  }
+}
+template <int A, int NS>
+__device__ __forceinline__ void matvec_t_n(const double* __restrict__ T, const double (&v)[NS][A], double (&o)[NS][A]) {
+#pragma unroll
+  for (int y = 0; y < A; y++) {
+    double row[A];
+    load_row<A>(T + y * A, row);
+#pragma unroll
+    for (int k = 0; k < NS; k++)
+#pragma unroll
+      for (int x = 0; x < A; x++) o[k][x] = (y == 0) ? row[x] * v[k][0] : fma(row[x], v[k][y], o[k][x]);
+  }
+}
+// acc[k] = sum_x u[k][x] * (W d[k])[x]
+template <int A, int NS>
+__device__ __forceinline__ void contract_n(const double* __restrict__ W, const double (&u)[NS][A],
+                                           const double (&d)[NS][A], double (&acc)[NS]) {
+#pragma unroll
+  for (int k = 0; k < NS; k++) acc[k] = 0.;
+#pragma unroll
+  for (int x = 0; x < A; x++) {
+    double row[A];
+    load_row<A>(W + x * A, row);
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      double s = row[0] * d[k][0];
+#pragma unroll
+      for (int y = 1; y < A; y++) s = fma(row[y], d[k][y], s);
+      acc[k] = fma(u[k][x], s, acc[k]);
+    }
+  }
+}
+
+template <int A, int NS, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k1_up(MapModel m, MapBuffers b, UpParams up) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int AA = A * A;
-  const int C = m.C, groups = up.groups, NS = up.n_stages;
-  const int n_cons_warps = groups * C;
+  constexpr int SW = 32 * NS;                     // sites per consumer warp
+  const int C = m.C, G = up.groups, NSTG = up.n_blocks; // ring of per-node stages
+  const int W = G * C;                            // consumer warps
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_pad = b.n_pad;
-  const int SG = 32 * groups;                    // sites per CTA
+  const int SG = SW * G;                          // sites per CTA
   const int64_t site0 = (int64_t)blockIdx.x * SG;
   const int N = C * AA;
-  // smem: barriers | red | table chunk buffers | partial ring
+  // smem: barriers (512 B) | red | table chunk buffers | tip ring | block ring
   uint64_t* tab_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* tab_empty = tab_full + 2;
-  uint64_t* d_full = tab_empty + 2;
-  uint64_t* d_empty = d_full + 8;
-  double* red = reinterpret_cast<double*>(smem + 256);
-  const size_t red_bytes = ((size_t)2 * groups * C * 2 * 32 * sizeof(double) + 127) & ~size_t(127);
-  unsigned char* tab_buf = smem + 256 + red_bytes;
-  unsigned char* ring = tab_buf + 2 * (size_t)up.cm.cap;
-  const uint32_t child_bytes = (uint32_t)(C * A) * SG * sizeof(double);
-  const uint32_t tip_off = 2 * child_bytes; // two tip rows of SG bytes after the partials
+  uint64_t* stg_full = tab_empty + 2;
+  uint64_t* stg_empty = stg_full + kMaxBlocks;
+  double* red = reinterpret_cast<double*>(smem + 512);
+  const size_t red_bytes = (size_t)2 * W * 2 * SW * sizeof(double);
+  unsigned char* tab_buf = smem + 512 + red_bytes;
+  // stage = 4 tip rows (a, b, a2, b2) | partial block of child a | partial block of child b
+  unsigned char* stg_ring = tab_buf + 2 * (size_t)up.cm.cap;
+  const uint32_t tip_slot = 4u * (uint32_t)SG;
+  const uint32_t stage_bytes = tip_slot + 2u * up.block_bytes;
 
+  // code -> state mask table in shared memory: the lookup sits on every node's critical path
+  __shared__ uint32_t cmask[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) cmask[i] = __ldg(m.code_mask + i);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; i++) { mbar_init(&tab_full[i], 1); mbar_init(&tab_empty[i], n_cons_warps); }
-    for (int i = 0; i < NS; i++) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], n_cons_warps); }
+    for (int i = 0; i < 2; i++) { mbar_init(&tab_full[i], 1); mbar_init(&tab_empty[i], W); }
+    for (int i = 0; i < NSTG; i++) { mbar_init(&stg_full[i], 1); mbar_init(&stg_empty[i], W); }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp == n_cons_warps) {
+  if (warp == W) {
     // ---- producer 1: table chunks
     if (lane == 0) {
       for (uint32_t k = 0; k < up.cm.n_chunks; k++) {
-        if (k >= 2) mbar_wait(&tab_empty[k & 1], ((k >> 1) - 1) & 1);
+        if (k >= 2) mbar_wait_sleep(&tab_empty[k & 1], ((k >> 1) - 1) & 1, 200);
         const uint32_t nb = __ldg(up.cm.bytes + k);
         mbar_expect_tx(&tab_full[k & 1], nb);
         tma_bulk_g2s(tab_buf + (size_t)(k & 1) * up.cm.cap, up.cm.src + __ldg(up.cm.off + k), nb, &tab_full[k & 1]);
@@ -316,338 +387,292 @@ __global__ void __launch_bounds__(320) k1_up(MapModel m, MapBuffers b, UpParams 
     }
     return;
   }
-  if (warp == n_cons_warps + 1) {
-    // ---- producer 2: partials and tip codes of node n into stage n % NS
+  if (warp == W + 1) {
+    // ---- producer 2: everything node n needs (tip rows, partial blocks of its inner
+    //      children) into stage n % NSTG, one mbarrier phase per node
     const int rows = C * A;
-    int4 h_next = __ldg(up.refs);
+    const uint32_t row_bytes = (uint32_t)SG * 8u;
+    uint32_t s = 0, ph = 1;
+    bool first = true;
+    int4 r0 = __ldg(up.refs), r1 = __ldg(up.refs + 1);
     for (uint32_t n = 0; n < up.n_nodes; n++) {
-      const int s = n % NS;
-      const int4 h = h_next;
-      if (n + 1 < up.n_nodes) h_next = __ldg(up.refs + n + 1);
-      if (n >= (uint32_t)NS) mbar_wait(&d_empty[s], ((n / NS) - 1) & 1);
-      const uint32_t flags = (uint32_t)h.x;
-      unsigned char* st = ring + (size_t)s * up.stage_bytes;
-      const uint32_t bytes = ((flags & kUpTipA) ? (uint32_t)SG : child_bytes) + ((flags & kUpTipB) ? (uint32_t)SG : child_bytes);
-      if (lane == 0) mbar_expect_tx(&d_full[s], bytes);
+      const int4 h0 = r0, h1 = r1;
+      if (n + 1 < up.n_nodes) { r0 = __ldg(up.refs + 2 * (n + 1)); r1 = __ldg(up.refs + 2 * (n + 1) + 1); }
+      const uint32_t flags = (uint32_t)h0.x;
+      const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB, cha = flags & kUpCherryA, chb = flags & kUpCherryB;
+      const bool ina = !(tipa || cha), inb = !(tipb || chb);
+      if (!first) mbar_wait_sleep(&stg_empty[s], ph, 100);
+      unsigned char* st = stg_ring + (size_t)s * stage_bytes;
+      if (lane == 0) {
+        const uint32_t nrows = (tipa || cha) + (tipb || chb) + cha + chb;
+        mbar_expect_tx(&stg_full[s], nrows * (uint32_t)SG + ((uint32_t)ina + (uint32_t)inb) * up.block_bytes);
+        if (tipa || cha) tma_bulk_g2s(st, b.tips + (size_t)h0.y * n_pad + site0, SG, &stg_full[s]);
+        if (tipb || chb) tma_bulk_g2s(st + SG, b.tips + (size_t)h0.z * n_pad + site0, SG, &stg_full[s]);
+        if (cha) tma_bulk_g2s(st + 2 * SG, b.tips + (size_t)h1.x * n_pad + site0, SG, &stg_full[s]);
+        if (chb) tma_bulk_g2s(st + 3 * SG, b.tips + (size_t)h1.y * n_pad + site0, SG, &stg_full[s]);
+      }
       __syncwarp();
-      if (flags & kUpTipA) {
-        if (lane == 0) tma_bulk_g2s(st + tip_off, b.tips + (size_t)h.y * n_pad + site0, SG, &d_full[s]);
-      } else {
-        const double* src = b.D + ((size_t)h.y * rows) * n_pad + site0;
+      if (ina) {
+        const double* src = b.D + d_block(site0 >> 8, h0.y, m.n_slots, rows) + (site0 & (kDSites - 1));
         for (int r = lane; r < rows; r += 32)
-          tma_bulk_g2s(st + (size_t)r * SG * 8, src + (size_t)r * n_pad, SG * 8, &d_full[s]);
+          tma_bulk_g2s(st + tip_slot + (size_t)r * row_bytes, src + (size_t)r * kDSites, row_bytes, &stg_full[s]);
       }
-      if (flags & kUpTipB) {
-        if (lane == 0) tma_bulk_g2s(st + tip_off + SG, b.tips + (size_t)h.z * n_pad + site0, SG, &d_full[s]);
-      } else {
-        const double* src = b.D + ((size_t)h.z * rows) * n_pad + site0;
+      if (inb) {
+        const double* src = b.D + d_block(site0 >> 8, h0.z, m.n_slots, rows) + (site0 & (kDSites - 1));
         for (int r = lane; r < rows; r += 32)
-          tma_bulk_g2s(st + child_bytes + (size_t)r * SG * 8, src + (size_t)r * n_pad, SG * 8, &d_full[s]);
+          tma_bulk_g2s(st + tip_slot + up.block_bytes + (size_t)r * row_bytes, src + (size_t)r * kDSites, row_bytes, &stg_full[s]);
       }
+      if (++s == (uint32_t)NSTG) { s = 0; ph ^= 1; first = false; }
     }
     return;
   }
 
-  // ---- consumers: warp = (site group g, class c), lane = site
+  // ---- consumers
   const int c = warp % C, g = warp / C;
-  const int64_t site = site0 + g * 32 + lane;
-  double G[A];
-  double stk[kMaxStack][A];
+  const int lsite = g * SW + lane;               // + k*32: site inside the CTA
+  double Gm[NS][A];
+  double stk[kMaxStack][NS][A];
   int sp = 0;
+  double invL[NS];
 #pragma unroll
-  for (int x = 0; x < A; x++) G[x] = __ldg(m.pi + x);
-  const double invL = b.invL[site];
-  uint32_t node = 0;
-  const size_t rec_bytes = 32 + (size_t)4 * N * sizeof(double);
+  for (int k = 0; k < NS; k++) {
+    invL[k] = b.invL[site0 + lsite + k * 32];
+#pragma unroll
+    for (int x = 0; x < A; x++) Gm[k][x] = __ldg(m.pi + x);
+  }
+  uint32_t node = 0, cs = 0, cph = 0; // stage slot and parity to wait for
+  uint32_t my_items = 0; // (branch a|b, k) outputs this warp finishes: item it -> class it % C
+  for (int it = 0; it < 2 * NS; it++)
+    if (it % C == c) my_items |= 1u << it;
 
-  for (uint32_t k = 0; k < up.cm.n_chunks; k++) {
-    mbar_wait(&tab_full[k & 1], (k >> 1) & 1);
-    const unsigned char* rp = tab_buf + (size_t)(k & 1) * up.cm.cap;
-    const uint32_t nrec = __ldg(up.cm.nrec + k);
-    for (uint32_t r = 0; r < nrec; r++, node++, rp += rec_bytes) {
+  for (uint32_t kc = 0; kc < up.cm.n_chunks; kc++) {
+    mbar_wait(&tab_full[kc & 1], (kc >> 1) & 1);
+    const unsigned char* rp = tab_buf + (size_t)(kc & 1) * up.cm.cap;
+    const uint32_t nrec = __ldg(up.cm.nrec + kc);
+    for (uint32_t r = 0; r < nrec; r++, node++) {
       const int4 h0 = *reinterpret_cast<const int4*>(rp);
       const int4 h1 = *reinterpret_cast<const int4*>(rp + 16);
       const uint32_t flags = (uint32_t)h0.x;
       const int out_a = h0.w, out_b = h1.x;
+      const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB, cha = flags & kUpCherryA, chb = flags & kUpCherryB;
       const double* Pa = reinterpret_cast<const double*>(rp + 32) + c * AA;
       const double* Wa = Pa + N;
       const double* Pb = Wa + N;
       const double* Wb = Pb + N;
+      const double* Px = Wb + N; // cherry tables follow
+      rp += 32 + (size_t)(4 + (cha ? 2 : 0) + (chb ? 2 : 0)) * N * sizeof(double);
 
-      // children data from the ring
-      const int s = node % NS;
-      mbar_wait(&d_full[s], (node / NS) & 1);
-      const unsigned char* st = ring + (size_t)s * up.stage_bytes;
-      double Da[A], Db[A], Ma[A], Mb[A];
-      TipInfo ta{0, 0, false}, tb{0, 0, false};
-      const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB;
-      uint32_t code_a = 0, code_b = 0;
-      if (tipa) code_a = st[tip_off + g * 32 + lane];
-      else {
-        const double* d = reinterpret_cast<const double*>(st) + (size_t)(c * A) * SG + g * 32 + lane;
+      double Da[NS][A], Db[NS][A];
+      int sa[NS], sb[NS];
+      bool fasta = false, fastb = false;
+      // ---- tip codes / cherry partials
+      {
+        mbar_wait(&stg_full[cs], cph);
+        const unsigned char* ts = stg_ring + (size_t)cs * stage_bytes + lsite;
+        if (tipa) {
+          uint32_t mk[NS];
+          bool single = true;
 #pragma unroll
-        for (int i = 0; i < A; i++) Da[i] = d[(size_t)i * SG];
-      }
-      if (tipb) code_b = st[tip_off + SG + g * 32 + lane];
-      else {
-        const double* d = reinterpret_cast<const double*>(st + child_bytes) + (size_t)(c * A) * SG + g * 32 + lane;
+          for (int k = 0; k < NS; k++) {
+            mk[k] = cmask[ts[k * 32]];
+            single = single && mk[k] != 0 && (mk[k] & (mk[k] - 1)) == 0;
+            sa[k] = __ffs(mk[k]) - 1;
+          }
+          fasta = __all_sync(0xffffffffu, single);
+          if (!fasta) {
 #pragma unroll
-        for (int i = 0; i < A; i++) Db[i] = d[(size_t)i * SG];
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&d_empty[s]); // stage is in registers now
-      if (tipa) ta = tip_from_code(m.code_mask, code_a);
-      if (tipb) tb = tip_from_code(m.code_mask, code_b);
-      if (tipa && !ta.fast) tip_dense<A, 1>(ta.mask, Da);
-      if (tipb && !tb.fast) tip_dense<A, 1>(tb.mask, Db);
-      const bool fasta = tipa && ta.fast, fastb = tipb && tb.fast;
-      if (fasta) tip_column<A, 1>(Pa, ta.state, Ma); else matvec<A, 1>(Pa, Da, Ma);
-      if (fastb) tip_column<A, 1>(Pb, tb.state, Mb); else matvec<A, 1>(Pb, Db, Mb);
+            for (int k = 0; k < NS; k++)
 #pragma unroll
-      for (int i = 0; i < A; i++) {
-        double gg = G[i];
-        double ua = gg * Mb[i], ub = gg * Ma[i];
-        Mb[i] = ua;
-        Ma[i] = ub;
+              for (int y = 0; y < A; y++) Da[k][y] = (mk[k] >> y) & 1u ? 1. : 0.;
+          }
+        } else if (cha) {
+          uint32_t m1[NS], m2[NS];
+          bool single = true;
+#pragma unroll
+          for (int k = 0; k < NS; k++) {
+            m1[k] = cmask[ts[k * 32]];
+            m2[k] = cmask[ts[2 * SG + k * 32]];
+            single = single && m1[k] != 0 && (m1[k] & (m1[k] - 1)) == 0 && m2[k] != 0 && (m2[k] & (m2[k] - 1)) == 0;
+          }
+          const double* P1 = Px;
+          const double* P2 = Px + N;
+          if (__all_sync(0xffffffffu, single)) {
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+              const int s1 = __ffs(m1[k]) - 1, s2 = __ffs(m2[k]) - 1;
+#pragma unroll
+              for (int x = 0; x < A; x++) Da[k][x] = P1[x * A + s1] * P2[x * A + s2];
+            }
+          } else {
+            double d1[NS][A], d2[NS][A], t1[NS][A];
+#pragma unroll
+            for (int k = 0; k < NS; k++)
+#pragma unroll
+              for (int y = 0; y < A; y++) { d1[k][y] = (m1[k] >> y) & 1u ? 1. : 0.; d2[k][y] = (m2[k] >> y) & 1u ? 1. : 0.; }
+            matvec_n<A, NS>(P1, d1, t1);
+            matvec_n<A, NS>(P2, d2, Da);
+#pragma unroll
+            for (int k = 0; k < NS; k++)
+#pragma unroll
+              for (int x = 0; x < A; x++) Da[k][x] *= t1[k][x];
+          }
+        }
+        if (tipb) {
+          uint32_t mk[NS];
+          bool single = true;
+#pragma unroll
+          for (int k = 0; k < NS; k++) {
+            mk[k] = cmask[ts[SG + k * 32]];
+            single = single && mk[k] != 0 && (mk[k] & (mk[k] - 1)) == 0;
+            sb[k] = __ffs(mk[k]) - 1;
+          }
+          fastb = __all_sync(0xffffffffu, single);
+          if (!fastb) {
+#pragma unroll
+            for (int k = 0; k < NS; k++)
+#pragma unroll
+              for (int y = 0; y < A; y++) Db[k][y] = (mk[k] >> y) & 1u ? 1. : 0.;
+          }
+        } else if (chb) {
+          uint32_t m1[NS], m2[NS];
+          bool single = true;
+#pragma unroll
+          for (int k = 0; k < NS; k++) {
+            m1[k] = cmask[ts[SG + k * 32]];
+            m2[k] = cmask[ts[3 * SG + k * 32]];
+            single = single && m1[k] != 0 && (m1[k] & (m1[k] - 1)) == 0 && m2[k] != 0 && (m2[k] & (m2[k] - 1)) == 0;
+          }
+          const double* P1 = Px + (cha ? 2 * N : 0);
+          const double* P2 = P1 + N;
+          if (__all_sync(0xffffffffu, single)) {
+#pragma unroll
+            for (int k = 0; k < NS; k++) {
+              const int s1 = __ffs(m1[k]) - 1, s2 = __ffs(m2[k]) - 1;
+#pragma unroll
+              for (int x = 0; x < A; x++) Db[k][x] = P1[x * A + s1] * P2[x * A + s2];
+            }
+          } else {
+            double d1[NS][A], d2[NS][A], t1[NS][A];
+#pragma unroll
+            for (int k = 0; k < NS; k++)
+#pragma unroll
+              for (int y = 0; y < A; y++) { d1[k][y] = (m1[k] >> y) & 1u ? 1. : 0.; d2[k][y] = (m2[k] >> y) & 1u ? 1. : 0.; }
+            matvec_n<A, NS>(P1, d1, t1);
+            matvec_n<A, NS>(P2, d2, Db);
+#pragma unroll
+            for (int k = 0; k < NS; k++)
+#pragma unroll
+              for (int x = 0; x < A; x++) Db[k][x] *= t1[k][x];
+          }
+        }
       }
-      double (&Ua)[A] = Mb;
-      double (&Ub)[A] = Ma;
-      // class term of the contraction with the reward tables (W includes p_c)
-      double acc_a = 0., acc_b = 0.;
+      // ---- stored partials of inner children, in ring order (a, then b)
+      {
+        const double* d = reinterpret_cast<const double*>(stg_ring + (size_t)cs * stage_bytes + tip_slot) + (size_t)(c * A) * SG + lsite;
+        if (!(tipa || cha)) {
+#pragma unroll
+          for (int k = 0; k < NS; k++)
+#pragma unroll
+            for (int i = 0; i < A; i++) Da[k][i] = d[(size_t)i * SG + k * 32];
+        }
+        d += up.block_bytes / 8;
+        if (!(tipb || chb)) {
+#pragma unroll
+          for (int k = 0; k < NS; k++)
+#pragma unroll
+            for (int i = 0; i < A; i++) Db[k][i] = d[(size_t)i * SG + k * 32];
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&stg_empty[cs]); // the stage is in registers now
+        if (++cs == (uint32_t)NSTG) { cs = 0; cph ^= 1; }
+      }
+
+      // ---- Ua = G o (Pb Db), branch a's class term, Ub = G o (Pa Da), branch b's class term
+      double Ua[NS][A], Ub[NS][A], acc_a[NS], acc_b[NS];
+      if (fastb) {
+#pragma unroll
+        for (int k = 0; k < NS; k++)
+#pragma unroll
+          for (int x = 0; x < A; x++) Ua[k][x] = Pb[x * A + sb[k]];
+      } else matvec_n<A, NS>(Pb, Db, Ua);
+#pragma unroll
+      for (int k = 0; k < NS; k++)
+#pragma unroll
+        for (int x = 0; x < A; x++) Ua[k][x] = Gm[k][x] * Ua[k][x];
       if (out_a >= 0) {
         if (fasta) {
 #pragma unroll
-          for (int i = 0; i < A; i++) acc_a = fma(Ua[i], Wa[i * A + ta.state], acc_a);
-        } else {
-          double wd[A];
-          matvec<A, 1>(Wa, Da, wd);
+          for (int k = 0; k < NS; k++) {
+            double t = 0.;
 #pragma unroll
-          for (int i = 0; i < A; i++) acc_a = fma(Ua[i], wd[i], acc_a);
-        }
+            for (int x = 0; x < A; x++) t = fma(Ua[k][x], Wa[x * A + sa[k]], t);
+            acc_a[k] = t;
+          }
+        } else contract_n<A, NS>(Wa, Ua, Da, acc_a);
       }
+      if (fasta) {
+#pragma unroll
+        for (int k = 0; k < NS; k++)
+#pragma unroll
+          for (int x = 0; x < A; x++) Ub[k][x] = Pa[x * A + sa[k]];
+      } else matvec_n<A, NS>(Pa, Da, Ub);
+#pragma unroll
+      for (int k = 0; k < NS; k++)
+#pragma unroll
+        for (int x = 0; x < A; x++) Ub[k][x] = Gm[k][x] * Ub[k][x];
       if (out_b >= 0) {
         if (fastb) {
 #pragma unroll
-          for (int i = 0; i < A; i++) acc_b = fma(Ub[i], Wb[i * A + tb.state], acc_b);
-        } else {
-          double wd[A];
-          matvec<A, 1>(Wb, Db, wd);
+          for (int k = 0; k < NS; k++) {
+            double t = 0.;
 #pragma unroll
-          for (int i = 0; i < A; i++) acc_b = fma(Ub[i], wd[i], acc_b);
+            for (int x = 0; x < A; x++) t = fma(Ub[k][x], Wb[x * A + sb[k]], t);
+            acc_b[k] = t;
+          }
+        } else contract_n<A, NS>(Wb, Ub, Db, acc_b);
+      }
+      // ---- sum the C class terms of each site in class order; the 2*NS (branch, k) items
+      //      of a site group are dealt round-robin to its C warps
+      {
+        double* rb = red + (size_t)(node & 1) * ((size_t)W * 2 * SW);
+        double* mine = rb + (size_t)((g * C + c) * 2) * SW + lane;
+#pragma unroll
+        for (int k = 0; k < NS; k++) {
+          if (out_a >= 0) mine[k * 32] = acc_a[k];
+          if (out_b >= 0) mine[SW + k * 32] = acc_b[k];
+        }
+        group_barrier(g, 32 * C);
+#pragma unroll
+        for (int it = 0; it < 2 * NS; it++) {
+          if (!(my_items >> it & 1u)) continue;
+          const int ab = it / NS, k = it % NS;
+          const int ob = ab ? out_b : out_a;
+          if (ob < 0) continue;
+          const double* src = rb + (size_t)(g * C * 2 + ab) * SW + k * 32 + lane;
+          double t = 0.;
+          for (int cc = 0; cc < C; cc++) t += src[(size_t)cc * 2 * SW];
+          b.out[(size_t)ob * n_pad + site0 + lsite + k * 32] = t * invL[k];
         }
       }
-      // combine the C class terms of this site group in class order; warp 0 of the group
-      // finishes branch a, warp 1 (if any) branch b
-      double* rb = red + ((size_t)((node & 1) * groups + g) * C) * 64;
-      rb[(size_t)c * 64 + lane] = acc_a;
-      rb[(size_t)c * 64 + 32 + lane] = acc_b;
-      group_barrier(g, 32 * C);
-      const int wb = C > 1 ? 1 : 0;
-      if (c == 0 && out_a >= 0) {
-        double t = 0.;
-        for (int cc = 0; cc < C; cc++) t += rb[(size_t)cc * 64 + lane];
-        b.out[(size_t)out_a * n_pad + site] = t * invL;
-      }
-      if (c == wb && out_b >= 0) {
-        double t = 0.;
-        for (int cc = 0; cc < C; cc++) t += rb[(size_t)cc * 64 + 32 + lane];
-        b.out[(size_t)out_b * n_pad + site] = t * invL;
-      }
-      // messages for the children that are expanded later
+      // ---- messages for the children that are expanded later
       if (flags & kUpTakeA) {
         if (flags & kUpPush) {
-          matvec_t<A, 1>(Pb, Ub, stk[sp]);
+          matvec_t_n<A, NS>(Pb, Ub, stk[sp]);
           ++sp;
         }
-        matvec_t<A, 1>(Pa, Ua, G);
+        matvec_t_n<A, NS>(Pa, Ua, Gm);
       } else if (flags & kUpTakeB) {
-        matvec_t<A, 1>(Pb, Ub, G);
+        matvec_t_n<A, NS>(Pb, Ub, Gm);
       } else if (flags & kUpPop) {
         --sp;
 #pragma unroll
-        for (int i = 0; i < A; i++) G[i] = stk[sp][i];
+        for (int k = 0; k < NS; k++)
+#pragma unroll
+          for (int i = 0; i < A; i++) Gm[k][i] = stk[sp][k][i];
       }
     }
     __syncwarp();
-    if (lane == 0) mbar_arrive(&tab_empty[k & 1]);
-  }
-}
-
-// Up pass, nucleotide fast path: one thread per site with all CB = C rate classes in
-// registers (no cross-warp class reduction, ~2.5x fewer instructions per site than the
-// warp-per-class kernel), fed by the same producer warps / shared-memory rings.
-template <int A, int CB>
-__global__ void __launch_bounds__(320, 1) k1_up_site(MapModel m, MapBuffers b, UpParams up) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int N = CB * A * A;
-  constexpr int SG = 256;      // sites per CTA = consumer threads
-  constexpr int ROWS = CB * A;
-  const int NS = up.n_stages;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_pad = b.n_pad;
-  const int64_t site0 = (int64_t)blockIdx.x * SG;
-  uint64_t* tab_full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* tab_empty = tab_full + 2;
-  uint64_t* d_full = tab_empty + 2;
-  uint64_t* d_empty = d_full + 8;
-  unsigned char* tab_buf = smem + 256;
-  unsigned char* ring = tab_buf + 2 * (size_t)up.cm.cap;
-  constexpr uint32_t child_bytes = (uint32_t)ROWS * SG * sizeof(double);
-  constexpr uint32_t tip_off = 2 * child_bytes;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; i++) { mbar_init(&tab_full[i], 1); mbar_init(&tab_empty[i], 8); }
-    for (int i = 0; i < NS; i++) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 8); }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  if (warp == 8) { // producer 1: table chunks
-    if (lane == 0) {
-      for (uint32_t k = 0; k < up.cm.n_chunks; k++) {
-        if (k >= 2) mbar_wait(&tab_empty[k & 1], ((k >> 1) - 1) & 1);
-        const uint32_t nb = __ldg(up.cm.bytes + k);
-        mbar_expect_tx(&tab_full[k & 1], nb);
-        tma_bulk_g2s(tab_buf + (size_t)(k & 1) * up.cm.cap, up.cm.src + __ldg(up.cm.off + k), nb, &tab_full[k & 1]);
-      }
-    }
-    return;
-  }
-  if (warp == 9) { // producer 2: children partials / tip codes of node n into stage n % NS
-    int4 h_next = __ldg(up.refs);
-    for (uint32_t n = 0; n < up.n_nodes; n++) {
-      const int s = n % NS;
-      const int4 h = h_next;
-      if (n + 1 < up.n_nodes) h_next = __ldg(up.refs + n + 1);
-      if (n >= (uint32_t)NS) mbar_wait(&d_empty[s], ((n / NS) - 1) & 1);
-      const uint32_t flags = (uint32_t)h.x;
-      unsigned char* st = ring + (size_t)s * up.stage_bytes;
-      const uint32_t bytes = ((flags & kUpTipA) ? (uint32_t)SG : child_bytes) + ((flags & kUpTipB) ? (uint32_t)SG : child_bytes);
-      if (lane == 0) mbar_expect_tx(&d_full[s], bytes);
-      __syncwarp();
-      if (flags & kUpTipA) {
-        if (lane == 0) tma_bulk_g2s(st + tip_off, b.tips + (size_t)h.y * n_pad + site0, SG, &d_full[s]);
-      } else if (lane < ROWS) {
-        const double* src = b.D + ((size_t)h.y * ROWS + lane) * n_pad + site0;
-        tma_bulk_g2s(st + (size_t)lane * SG * 8, src, SG * 8, &d_full[s]);
-      }
-      if (flags & kUpTipB) {
-        if (lane == 0) tma_bulk_g2s(st + tip_off + SG, b.tips + (size_t)h.z * n_pad + site0, SG, &d_full[s]);
-      } else if (lane < ROWS) {
-        const double* src = b.D + ((size_t)h.z * ROWS + lane) * n_pad + site0;
-        tma_bulk_g2s(st + child_bytes + (size_t)lane * SG * 8, src, SG * 8, &d_full[s]);
-      }
-    }
-    return;
-  }
-
-  // ---- consumers: thread = site, all classes in registers
-  const int t = threadIdx.x;
-  const int64_t site = site0 + t;
-  double G[CB * A];
-  double stk[kMaxStack][CB * A];
-  int sp = 0;
-#pragma unroll
-  for (int c = 0; c < CB; c++)
-#pragma unroll
-    for (int x = 0; x < A; x++) G[c * A + x] = __ldg(m.pi + x);
-  const double invL = b.invL[site];
-  uint32_t node = 0;
-  constexpr size_t rec_bytes = 32 + (size_t)4 * N * sizeof(double);
-
-  for (uint32_t k = 0; k < up.cm.n_chunks; k++) {
-    mbar_wait(&tab_full[k & 1], (k >> 1) & 1);
-    const unsigned char* rp = tab_buf + (size_t)(k & 1) * up.cm.cap;
-    const uint32_t nrec = __ldg(up.cm.nrec + k);
-    for (uint32_t r = 0; r < nrec; r++, node++, rp += rec_bytes) {
-      const int4 h0 = *reinterpret_cast<const int4*>(rp);
-      const int4 h1 = *reinterpret_cast<const int4*>(rp + 16);
-      const uint32_t flags = (uint32_t)h0.x;
-      const int out_a = h0.w, out_b = h1.x;
-      const double* Pa = reinterpret_cast<const double*>(rp + 32);
-      const double* Wa = Pa + N;
-      const double* Pb = Wa + N;
-      const double* Wb = Pb + N;
-
-      const int s = node % NS;
-      mbar_wait(&d_full[s], (node / NS) & 1);
-      const unsigned char* st = ring + (size_t)s * up.stage_bytes;
-      double Da[CB * A], Db[CB * A], Ma[CB * A], Mb[CB * A];
-      TipInfo ta{0, 0, false}, tb{0, 0, false};
-      const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB;
-      uint32_t code_a = 0, code_b = 0;
-      if (tipa) code_a = st[tip_off + t];
-      else {
-        const double* d = reinterpret_cast<const double*>(st) + t;
-#pragma unroll
-        for (int i = 0; i < CB * A; i++) Da[i] = d[(size_t)i * SG];
-      }
-      if (tipb) code_b = st[tip_off + SG + t];
-      else {
-        const double* d = reinterpret_cast<const double*>(st + child_bytes) + t;
-#pragma unroll
-        for (int i = 0; i < CB * A; i++) Db[i] = d[(size_t)i * SG];
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&d_empty[s]);
-      if (tipa) ta = tip_from_code(m.code_mask, code_a);
-      if (tipb) tb = tip_from_code(m.code_mask, code_b);
-      if (tipa && !ta.fast) tip_dense<A, CB>(ta.mask, Da);
-      if (tipb && !tb.fast) tip_dense<A, CB>(tb.mask, Db);
-      const bool fasta = tipa && ta.fast, fastb = tipb && tb.fast;
-      if (fasta) tip_column<A, CB>(Pa, ta.state, Ma); else matvec<A, CB>(Pa, Da, Ma);
-      if (fastb) tip_column<A, CB>(Pb, tb.state, Mb); else matvec<A, CB>(Pb, Db, Mb);
-#pragma unroll
-      for (int i = 0; i < CB * A; i++) {
-        double gg = G[i];
-        double ua = gg * Mb[i], ub = gg * Ma[i];
-        Mb[i] = ua;
-        Ma[i] = ub;
-      }
-      double (&Ua)[CB * A] = Mb;
-      double (&Ub)[CB * A] = Ma;
-      if (out_a >= 0) {
-        double acc = 0.;
-        if (fasta) {
-#pragma unroll
-          for (int i = 0; i < CB * A; i++) acc = fma(Ua[i], Wa[i * A + ta.state], acc);
-        } else {
-          double wd[CB * A];
-          matvec<A, CB>(Wa, Da, wd);
-#pragma unroll
-          for (int i = 0; i < CB * A; i++) acc = fma(Ua[i], wd[i], acc);
-        }
-        b.out[(size_t)out_a * n_pad + site] = acc * invL;
-      }
-      if (out_b >= 0) {
-        double acc = 0.;
-        if (fastb) {
-#pragma unroll
-          for (int i = 0; i < CB * A; i++) acc = fma(Ub[i], Wb[i * A + tb.state], acc);
-        } else {
-          double wd[CB * A];
-          matvec<A, CB>(Wb, Db, wd);
-#pragma unroll
-          for (int i = 0; i < CB * A; i++) acc = fma(Ub[i], wd[i], acc);
-        }
-        b.out[(size_t)out_b * n_pad + site] = acc * invL;
-      }
-      if (flags & kUpTakeA) {
-        if (flags & kUpPush) {
-          matvec_t<A, CB>(Pb, Ub, stk[sp]);
-          ++sp;
-        }
-        matvec_t<A, CB>(Pa, Ua, G);
-      } else if (flags & kUpTakeB) {
-        matvec_t<A, CB>(Pb, Ub, G);
-      } else if (flags & kUpPop) {
-        --sp;
-#pragma unroll
-        for (int i = 0; i < CB * A; i++) G[i] = stk[sp][i];
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&tab_empty[k & 1]);
+    if (lane == 0) mbar_arrive(&tab_empty[kc & 1]);
   }
 }
 
@@ -684,70 +709,75 @@ void run_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaSt
   k1_down<A><<<(unsigned)(b.n_pad / (32 * groups)), 32 * groups * m.C, smem, st>>>(m, b, meta_of(s), groups);
   CMB_CUDA(cudaGetLastError());
 }
-template <int A, int CB>
-bool run_up_site(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+// Launch shape of the up pass: NS sites per lane, G site groups per CTA (G*C consumer warps
+// + 2 producer warps), ring depths from the shared-memory budget.
+struct UpShape { int groups, n_blocks, n_tips; size_t smem; uint32_t block_bytes; };
+template <int A, int NS>
+bool up_shape(int C, uint32_t cap, int max_smem, int max_warps, UpShape& sh) {
+  // at most 4 site groups (named barriers 1..4); fewer when the warp budget or shared
+  // memory (two stages at least) does not allow more
+  for (int G = 4; G >= 1; G /= 2) {
+    if (G * NS > 8 || G * C > max_warps) continue;
+    const int SG = 32 * NS * G, W = G * C;
+    const size_t red = (size_t)2 * W * 2 * 32 * NS * sizeof(double);
+    const size_t block = (size_t)C * A * SG * 8;
+    const size_t stage = 4 * (size_t)SG + 2 * block;
+    const size_t fixed = 512 + red + 2 * (size_t)cap;
+    if ((size_t)max_smem < fixed + 2 * stage) continue;
+    sh.groups = G;
+    sh.n_tips = 0;
+    sh.n_blocks = (int)std::min<size_t>(kMaxBlocks, ((size_t)max_smem - fixed) / stage);
+    sh.block_bytes = (uint32_t)block;
+    sh.smem = fixed + (size_t)sh.n_blocks * stage;
+    return true;
+  }
+  return false;
+}
+
+template <int A, int NS, int MAXT, int MINB>
+bool try_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   int dev = 0, max_smem = 0;
   CMB_CUDA(cudaGetDevice(&dev));
   CMB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  UpShape sh;
+  max_smem = max_smem / MINB - 1024; // the system reserves 1 KB of shared memory per CTA
+  if (!up_shape<A, NS>(m.C, s.cap, max_smem, MAXT / 32 - 2, sh)) return false;
+  const int SG = 32 * NS * sh.groups;
+  if (b.n_pad % SG) return false;
   UpParams up;
   up.cm = meta_of(s);
   up.refs = s.aux.as<int4>();
   up.n_nodes = s.n_records;
-  up.groups = 8;
-  const size_t stage = ((size_t)2 * CB * A * 256 * 8 + 2 * 256 + 127) & ~size_t(127);
-  const size_t fixed = 256 + 2 * (size_t)s.cap;
-  if ((size_t)max_smem < fixed + 2 * stage) return false;
-  const int ns = (int)std::min<size_t>(8, ((size_t)max_smem - fixed) / stage);
-  up.n_stages = ns;
-  up.stage_bytes = (uint32_t)stage;
-  const size_t smem = fixed + (size_t)ns * stage;
-  CMB_CUDA(cudaFuncSetAttribute(k1_up_site<A, CB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k1_up_site<A, CB><<<(unsigned)(b.n_pad / 256), 320, smem, st>>>(m, b, up);
+  up.groups = sh.groups;
+  up.n_blocks = sh.n_blocks;
+  up.n_tips = sh.n_tips;
+  up.block_bytes = sh.block_bytes;
+  CMB_CUDA(cudaFuncSetAttribute(k1_up<A, NS, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+  k1_up<A, NS, MAXT, MINB><<<(unsigned)(b.n_pad / SG), 32 * (sh.groups * m.C + 2), sh.smem, st>>>(m, b, up);
   CMB_CUDA(cudaGetLastError());
   return true;
 }
 
 template <int A>
 void run_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
-  static const bool site_kernel = getenv("CMB_UP_SITE_KERNEL") != nullptr; // experiment switch
-  if constexpr (A == 4) if (site_kernel) { // thread-per-site variant: all classes in one thread
-    bool done = false;
-    if (m.C == 4) done = run_up_site<4, 4>(m, b, s, st);
-    else if (m.C == 3) done = run_up_site<4, 3>(m, b, s, st);
-    else if (m.C == 2) done = run_up_site<4, 2>(m, b, s, st);
-    else if (m.C == 1) done = run_up_site<4, 1>(m, b, s, st);
-    if (done) return;
+  // Shapes measured on B200 at config 4 (517 k sites per step, ms per step for the up pass):
+  //   1 site/lane, 2 CTAs/SM (16 consumer warps, 96 regs)   18.3   <- default
+  //   2 sites/lane, 1 CTA/SM (8 consumer warps, 168 regs)    20.7
+  //   1 site/lane, 3 CTAs/SM (24 consumer warps, 64 regs)    27.5
+  //   2 sites/lane, 2 CTAs/SM (96 regs, spills)              28.9
+  //   4 sites/lane, 1 CTA/SM (168 regs, spills)              50.4
+  // Registers are per SM sub-partition (16 K each): 10 warps -> 3 on one -> <= 168 per thread,
+  // two CTAs of 10 warps -> 5 on one -> <= 96.
+  static const int shape = getenv("CMB_UP_SHAPE") ? atoi(getenv("CMB_UP_SHAPE")) : 0; // experiment switch
+  bool done = false;
+  if constexpr (A == 4) {
+    if (shape == 2) done = try_up<4, 2, 320, 1>(m, b, s, st);
+    if (!done) done = try_up<4, 1, 320, 2>(m, b, s, st);
+    if (!done) done = try_up<4, 1, 320, 1>(m, b, s, st);
+  } else {
+    done = try_up<A, 1, 320, 1>(m, b, s, st);
   }
-  // site groups per CTA and ring depth from the shared-memory budget
-  int dev = 0, max_smem = 0;
-  CMB_CUDA(cudaGetDevice(&dev));
-  CMB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  int groups = groups_per_cta(m.C);
-  UpParams up;
-  up.cm = meta_of(s);
-  up.refs = s.aux.as<int4>();
-  up.n_nodes = s.n_records;
-  size_t smem = 0;
-  int ns = 0;
-  for (;; groups = groups > 1 ? groups / 2 : 1) {
-    const size_t red = ((size_t)2 * groups * m.C * 2 * 32 * sizeof(double) + 127) & ~size_t(127);
-    const size_t stage = ((size_t)2 * m.C * A * 32 * groups * 8 + 2 * 32 * groups + 127) & ~size_t(127);
-    const size_t fixed = 256 + red + 2 * (size_t)s.cap;
-    // aim at two resident CTAs per SM when the tables are small, else one
-    const size_t budget = fixed + 4 * stage <= (size_t)max_smem / 2 - 1024 ? (size_t)max_smem / 2 - 1024 : (size_t)max_smem;
-    ns = (int)std::min<size_t>(8, budget > fixed ? (budget - fixed) / stage : 0);
-    if (ns >= 2 || groups == 1) {
-      up.stage_bytes = (uint32_t)stage;
-      smem = fixed + (size_t)ns * stage;
-      break;
-    }
-  }
-  if (ns < 2) fail("mapping up pass: shared memory too small for A = %d, C = %d", A, m.C);
-  up.groups = groups;
-  up.n_stages = ns;
-  CMB_CUDA(cudaFuncSetAttribute(k1_up<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k1_up<A><<<(unsigned)(b.n_pad / (32 * groups)), 32 * (groups * m.C + 2), smem, st>>>(m, b, up);
-  CMB_CUDA(cudaGetLastError());
+  if (!done) fail("mapping up pass: no launch shape fits shared memory for A = %d, C = %d", A, m.C);
 }
 
 } // namespace

@@ -14,7 +14,7 @@ struct DevStream {           // an OpStream uploaded to the device
 struct MapBuffers {          // per-batch device arrays, n_pad sites (multiple of 256)
   int64_t n = 0, n_pad = 0;
   const uint8_t* tips = nullptr;   // [T][n_pad]
-  double* D = nullptr;             // [n_slots][C*A][n_pad]
+  double* D = nullptr;             // [n_pad/256][n_slots][C*A][256] (block-major, k1_map.cu d_block)
   double* Lc = nullptr;            // [C][n_pad]
   double* invL = nullptr;          // [n_pad]
   double* loglik = nullptr;        // [n_pad]

@@ -96,7 +96,7 @@ void build_tree(Tree& t, int n_nodes, const int32_t* parent, const double* brlen
         st.push_back({a, 0});
       } else t.down_order.push_back(v);
     }
-    // slots + depth
+    // depth of the message stack
     int sp = 0;
     for (int v : t.down_order) {
       BinNode& n = t.bin[v];
@@ -104,7 +104,6 @@ void build_tree(Tree& t, int n_nodes, const int32_t* parent, const double* brlen
       if (t.bin[b].leaves > t.bin[a].leaves) std::swap(a, b);
       if (t.bin[a].left >= 0) sp--; // pop a's message
       if (v != t.bin_root) {
-        n.slot = t.n_slots++;
         const BinNode& p = t.bin[n.parent];
         int pa = p.left, pb = p.right;
         if (t.bin[pb].leaves > t.bin[pa].leaves) std::swap(pa, pb);
@@ -135,6 +134,23 @@ void build_tree(Tree& t, int n_nodes, const int32_t* parent, const double* brlen
   }
   if (t.down_depth > kMaxStack || t.up_depth > kMaxStack)
     fail("cmb_set_tree: traversal stack depth %d exceeds %d", std::max(t.down_depth, t.up_depth), kMaxStack);
+  assign_slots(t, false);
+}
+
+// Storage slots of the down partials.  With skip_cherries, a cherry (inner non-root node
+// whose two children are leaves) gets none: the up pass recomputes its partial from the
+// two tip rows, so it never travels through HBM (about a third of the inner nodes of a
+// random tree).
+void assign_slots(Tree& t, bool skip_cherries) {
+  t.n_slots = 0;
+  for (int v : t.down_order) {
+    BinNode& n = t.bin[v];
+    n.slot = -1;
+    n.cherry = false;
+    if (v == t.bin_root) continue;
+    n.cherry = skip_cherries && t.bin[n.left].left < 0 && t.bin[n.right].left < 0;
+    if (!n.cherry) n.slot = t.n_slots++;
+  }
 }
 
 namespace {
@@ -246,18 +262,24 @@ static void up_like_stream(OpStream& s, const Tree& t, const ModelTables& mt, in
       if (!tb) { h.flags |= kUpPush; st.push_back(b); }
     } else if (!tb) h.flags |= kUpTakeB;
     else if (!st.empty()) { h.flags |= kUpPop; st.pop_back(); }
+    const bool ca = !sim && t.bin[a].cherry, cb_ = !sim && t.bin[b].cherry;
     if (sim) {
       h.ref_a = ta ? t.bin[a].tip_row : -1;
       h.ref_b = tb ? t.bin[b].tip_row : -1;
       h.out_a = t.bin[a].orig;
       h.out_b = t.bin[b].orig;
     } else {
-      h.ref_a = ta ? t.bin[a].tip_row : t.bin[a].slot;
-      h.ref_b = tb ? t.bin[b].tip_row : t.bin[b].slot;
+      h.ref_a = ta ? t.bin[a].tip_row : ca ? t.bin[t.bin[a].left].tip_row : t.bin[a].slot;
+      h.ref_b = tb ? t.bin[b].tip_row : cb_ ? t.bin[t.bin[b].left].tip_row : t.bin[b].slot;
+      h.ref_a2 = ca ? t.bin[t.bin[a].right].tip_row : -1;
+      h.ref_b2 = cb_ ? t.bin[t.bin[b].right].tip_row : -1;
+      if (ca) h.flags |= kUpCherryA;
+      if (cb_) h.flags |= kUpCherryB;
       h.out_a = t.bin[a].branch;
       h.out_b = t.bin[b].branch;
     }
     s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.ref_a); s.aux.push_back(h.ref_b); s.aux.push_back(0);
+    s.aux.push_back(h.ref_a2); s.aux.push_back(h.ref_b2); s.aux.push_back(0); s.aux.push_back(0);
     s.n_records++;
     std::vector<unsigned char> rec;
     append(rec, &h, sizeof h);
@@ -269,6 +291,8 @@ static void up_like_stream(OpStream& s, const Tree& t, const ModelTables& mt, in
       append_table(rec, t, mt, a, 1, c0, cb);
       append_table(rec, t, mt, b, 0, c0, cb);
       append_table(rec, t, mt, b, 1, c0, cb);
+      if (ca) { append_table(rec, t, mt, t.bin[a].left, 0, c0, cb); append_table(rec, t, mt, t.bin[a].right, 0, c0, cb); }
+      if (cb_) { append_table(rec, t, mt, t.bin[b].left, 0, c0, cb); append_table(rec, t, mt, t.bin[b].right, 0, c0, cb); }
     }
     pad16(rec);
     max_rec = std::max(max_rec, rec.size());

@@ -53,5 +53,22 @@ def build(force=False, verbose=False):
     return OUT
 
 
+HOST_SRC = ["main.cpp", "options.cpp", "seq.cpp", "tree.cpp", "models.cpp"]
+HOST_BIN = os.path.join(HERE, "bin", "comap_b200")
+
+
+def build_host(force=False):
+    """Builds the C++ front-end (CoMap's command line over the C ABI) with g++."""
+    hdir = os.path.join(HERE, "host")
+    srcs = [os.path.join(hdir, f) for f in HOST_SRC]
+    deps = srcs + [os.path.join(hdir, "bpp.h"), os.path.join(os.path.dirname(HERE), "include", "comap_b200.h"), OUT]
+    os.makedirs(os.path.dirname(HOST_BIN), exist_ok=True)
+    if force or _stale(HOST_BIN, deps):
+        cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread", "-o", HOST_BIN] + srcs + \
+              ["-L" + HERE, "-lcomap_b200", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath-link," + "/usr/local/cuda/lib64"]
+        subprocess.check_call(cmd)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build_host(force="--force" in sys.argv) if "--host" in sys.argv else build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,503 @@
+// comap_b200 -- CoMap's command line on top of libcomap_b200.so.
+//
+//   comap_b200 param=options.bpp key=value ... [--seed=N] [--dry-run]
+//
+// Mirrors the flow of CoMap.cpp:96-737 for the homogeneous, single data set case: same
+// option keys, same messages where cheap, same output tables.  Everything
+// numerical goes through the C ABI (include/comap_b200.h); there is no CPU fallback.
+// --dry-run stops after the inputs are prepared and prints what would be handed to the
+// device (used by the CPU tests).
+#include "bpp.h"
+#include "../../include/comap_b200.h"
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <random>
+#include <sstream>
+#include <thread>
+
+using namespace host;
+
+namespace {
+
+void display_result(const std::string& what, const std::string& value) {
+  std::string w = what;
+  while (w.size() < 39) w += '.';
+  std::cout << w << ": " << value << std::endl;
+}
+template <class T> void display_result(const std::string& what, const T& v) {
+  std::ostringstream ss;
+  ss << v;
+  display_result(what, ss.str());
+}
+void display_message(const std::string& m) { std::cout << m << std::endl; }
+
+void chk(int rc) {
+  if (rc) throw Error(std::string("comap_b200: ") + cmb_last_error());
+}
+
+// operator<<(double) at default precision == "%g" with 6 significant digits
+inline int fmt_g(char* p, double v) { return snprintf(p, 32, "%g", v); }
+
+// Formats rows [r0, r1) with `row(r, buf)` on all host cores and writes them in order:
+// 12.5 M "%g" rows are the reference's dominant wall-time term.
+template <class F> void write_rows_parallel(std::ostream& out, int64_t n, size_t max_row_bytes, F row) {
+  const int nt = (int)std::max(1u, std::min(std::thread::hardware_concurrency(), 32u));
+  const int64_t chunk = 1 << 16;
+  for (int64_t base = 0; base < n; base += chunk * nt) {
+    std::vector<std::string> bufs(nt);
+    std::vector<std::thread> th;
+    for (int t = 0; t < nt; t++) {
+      const int64_t a = base + (int64_t)t * chunk, b = std::min(n, a + chunk);
+      if (a >= b) break;
+      th.emplace_back([&, t, a, b]() {
+        std::string& s = bufs[t];
+        s.resize((size_t)(b - a) * max_row_bytes);
+        char* p = &s[0];
+        for (int64_t r = a; r < b; r++) p += row(r, p);
+        s.resize((size_t)(p - &s[0]));
+      });
+    }
+    for (auto& x : th) x.join();
+    for (auto& s : bufs) out.write(s.data(), (std::streamsize)s.size());
+  }
+}
+
+struct Inputs {
+  Application app;
+  Tree tree;
+  Alphabet alpha;
+  Alignment aln;
+  std::vector<int> cols;      // kept columns (0-based)
+  std::vector<int> all_cols;  // before input.remove_const
+  Model model;
+  RateDist rdist;
+  std::vector<uint8_t> codes; // [T][S], rows in leaf order
+  std::vector<uint32_t> code_mask;
+  int count_method = CMB_COUNT_UNIFORMIZATION;
+};
+
+std::string data_dir_of(const char* argv0) {
+  if (const char* e = getenv("COMAP_B200_DATA")) return e;
+  std::string p = argv0;
+  size_t k = p.find_last_of('/');
+  std::string dir = k == std::string::npos ? "." : p.substr(0, k);
+  return dir + "/../data";
+}
+
+void prepare(Inputs& in, const char* argv0) {
+  const Params& P = in.app.params;
+  display_message("\n\n-*- Retrieve data and model -*-\n");
+  // tree (PhylogeneticsApplicationTools::getTree, CoMap.cpp:125-129)
+  std::string tree_path = get_path(P, "input.tree.file", "none");
+  if (tree_path == "none") throw Error("input.tree.file is not set");
+  std::string tfmt = get_string(P, "input.tree.format", "Newick");
+  if (lower(parse_procedure(tfmt).name) != "newick") throw Error("input.tree.format '" + tfmt + "' is not supported (Newick)");
+  display_result("Input tree file ", tree_path);
+  in.tree = parse_newick(read_file(tree_path));
+  display_result("Number of leaves", in.tree.leaves.size());
+  display_result("Number of sons at root", in.tree.n_root_children);
+  if (in.tree.was_unrooted) display_message("WARNING!!! Tree has been unrooted.");
+  // data (CoETools::readData, CoETools.cpp:78-124)
+  in.alpha = make_alphabet(get_string(P, "alphabet", "DNA"));
+  display_result("Alphabet type ", in.alpha.name);
+  std::string seq_path = get_path(P, "input.sequence.file", "none");
+  if (seq_path == "none") throw Error("input.sequence.file is not set");
+  std::string sfmt = get_string(P, "input.sequence.format", "Fasta");
+  in.aln = read_alignment(seq_path, sfmt);
+  display_result("Sequence file ", seq_path);
+  in.cols = select_sites(in.aln, in.alpha, P, sfmt, &in.all_cols);
+  if (get_string(P, "nonhomogeneous", "no") != "no")
+    throw Error("nonhomogeneous models are outside the B200 hot path (SURVEY.md s2.1); use nonhomogeneous=no");
+  in.model = make_model(get_string(P, "model", "JC69"), in.alpha, data_dir_of(argv0));
+  display_result("Substitution model", in.model.name);
+  in.rdist = make_rate_distribution(get_string(P, "rate_distribution", "Constant()"));
+  display_result("Rate distribution", in.rdist.name);
+  display_result("Number of classes", in.rdist.rates.size());
+  std::string opt = get_string(P, "optimization", "None");
+  if (lower(parse_procedure(opt).name) != "none" && !opt.empty())
+    display_message("WARNING!!! optimization=" + opt + " is outside the B200 hot path: parameters are used as given.");
+  // nijt (PhylogeneticsApplicationTools::getSubstitutionCount, CoMap.cpp:152)
+  std::string nijt = get_string(P, "nijt", "Uniformization");
+  if (nijt.empty()) nijt = "Uniformization";
+  Procedure nj = parse_procedure(nijt);
+  if (nj.name == "Uniformization") in.count_method = CMB_COUNT_UNIFORMIZATION;
+  else if (nj.name == "Decomposition") in.count_method = CMB_COUNT_DECOMPOSITION;
+  else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition)");
+  std::string w = get_string(nj.args, "weight", "None");
+  if (w != "None" && w != "none")
+    throw Error("weighted substitution counts (weight=" + w + ") need Bio++'s AAIndex tables, which are not bundled");
+  if (!get_bool(P, "nijt.average", true) || !get_bool(P, "nijt.joint", true))
+    throw Error("nijt.average=no / nijt.joint=no (benchmark-only variants) are not available in this build");
+  display_result("Substitution count", nj.name);
+  // leaf rows: sequence of every leaf, in leaf id order
+  std::map<std::string, int> row;
+  for (size_t i = 0; i < in.aln.names.size(); i++) row[in.aln.names[i]] = (int)i;
+  const size_t T = in.tree.leaves.size(), S = in.cols.size();
+  if (S == 0) throw Error("no site left to analyse after filtering");
+  std::map<char, int> code_of;
+  in.code_mask.clear();
+  for (size_t k = 0; k < in.alpha.states.size(); k++) in.code_mask.push_back(1u << k);
+  in.codes.assign(T * S, 0);
+  for (size_t k = 0; k < T; k++) {
+    const std::string& nm = in.tree.name[in.tree.leaves[k]];
+    auto it = row.find(nm);
+    if (it == row.end()) throw Error("leaf '" + nm + "' of the tree has no sequence in the alignment");
+    const std::string& s = in.aln.seqs[it->second];
+    for (size_t j = 0; j < S; j++) {
+      char c = s[in.cols[j]];
+      uint32_t m = in.alpha.mask_of(c);
+      int code;
+      if (m && !(m & (m - 1)) && c != '-') code = __builtin_ctz(m);
+      else {
+        auto f = code_of.find((char)toupper((unsigned char)c));
+        if (f == code_of.end()) {
+          if (in.code_mask.size() >= 256) throw Error("too many distinct ambiguity characters");
+          code = (int)in.code_mask.size();
+          code_of[(char)toupper((unsigned char)c)] = code;
+          in.code_mask.push_back(m);
+        } else code = f->second;
+      }
+      in.codes[k * S + j] = (uint8_t)code;
+    }
+  }
+  display_result("Number of sites in file", in.aln.length());
+  display_result("Number of sites to analyse", S);
+}
+
+void dry_run_dump(const Inputs& in) {
+  std::cout.precision(17);
+  std::cout << "DRYRUN n_nodes " << in.tree.parent.size() << "\n";
+  std::cout << "DRYRUN parent";
+  for (int p : in.tree.parent) std::cout << ' ' << p;
+  std::cout << "\nDRYRUN brlen";
+  for (double b : in.tree.brlen) std::cout << ' ' << b;
+  std::cout << "\nDRYRUN leaves";
+  for (int l : in.tree.leaves) std::cout << ' ' << in.tree.name[l];
+  std::cout << "\nDRYRUN A " << in.model.A << "\nDRYRUN Q";
+  for (double q : in.model.Q) std::cout << ' ' << q;
+  std::cout << "\nDRYRUN pi";
+  for (double q : in.model.pi) std::cout << ' ' << q;
+  std::cout << "\nDRYRUN rates";
+  for (double q : in.rdist.rates) std::cout << ' ' << q;
+  std::cout << "\nDRYRUN probs";
+  for (double q : in.rdist.probs) std::cout << ' ' << q;
+  std::cout << "\nDRYRUN coords";
+  for (int c : in.cols) std::cout << ' ' << c + 1;
+  std::cout << "\nDRYRUN code_mask";
+  for (uint32_t m : in.code_mask) std::cout << ' ' << m;
+  std::cout << "\nDRYRUN codes";
+  for (uint8_t c : in.codes) std::cout << ' ' << (int)c;
+  std::cout << "\nDRYRUN count_method " << in.count_method << std::endl;
+}
+
+int stat_id_of(const Params& P) {
+  Procedure st = parse_procedure(get_string(P, "statistic", "Correlation"));
+  if (st.name == "Cosinus") return CMB_STAT_COSINUS;
+  if (st.name == "Correlation") return CMB_STAT_CORRELATION;
+  if (st.name == "Covariance") return CMB_STAT_COVARIANCE;
+  if (st.name == "Cosubstitution") return CMB_STAT_COSUBSTITUTION;
+  if (st.name == "Compensation")
+    throw Error("Compensation distance must be used with a mapping procedure allowing weights, e.g. "
+                "'nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))'.");
+  if (st.name == "CorrectedCorrelation" || st.name == "MI")
+    throw Error("statistic=" + st.name + " is not available in this build (SURVEY.md s8f)");
+  throw Error("Unknown statistic used: " + get_string(P, "statistic", ""));
+}
+
+std::string group_string(const int32_t* m, int64_t n, const std::vector<int>* coords) {
+  std::string s = "[";
+  for (int64_t i = 0; i < n; i++) {
+    if (i) s += ';';
+    s += std::to_string(coords ? (*coords)[m[i]] + 1 : m[i]);
+  }
+  return s + "]";
+}
+
+// Newick of the clustering dendrogram with leaf names translated to coordinates
+// (ClusterTools::translate + Newick::writeTree, CoMap.cpp:553-561)
+std::string dendrogram_newick(const std::vector<int32_t>& left, const std::vector<int32_t>& right,
+                              const std::vector<double>& height, int64_t S, const std::vector<int>& cols) {
+  std::vector<std::string> txt(2 * S - 1);
+  auto h = [&](int v) { return v < S ? 0. : height[v - S]; };
+  for (int64_t v = 0; v < S; v++) txt[v] = std::to_string(cols[v] + 1);
+  for (int64_t k = 0; k + 1 < S; k++) {
+    int l = left[k], r = right[k];
+    std::ostringstream ss;
+    ss << "(" << txt[l] << ":" << (height[k] - h(l)) << "," << txt[r] << ":" << (height[k] - h(r)) << ")";
+    txt[S + k] = ss.str();
+    txt[l].clear();
+    txt[r].clear();
+  }
+  return txt[2 * S - 2] + ";";
+}
+
+} // namespace
+
+int main(int argc, char** argv) {
+  std::cout << "\n\n***********************************************************\n"
+            << "* This is comap_b200: CoMap's hot path on NVIDIA B200      *\n"
+            << "*     Coevolution Detection Using Substitution Mapping    *\n"
+            << "***********************************************************\n"
+            << std::endl;
+  if (argc == 1) {
+    std::cout << "comap_b200 param=option_file [key=value ...] [--seed=N] [--dry-run]\n"
+              << "Option keys are CoMap's (see the CoMap manual / SURVEY.md s5.1)." << std::endl;
+    return 0;
+  }
+  try {
+    auto t_start = std::chrono::steady_clock::now();
+    Inputs in;
+    in.app = parse_command_line(argc, argv);
+    bool dry = false;
+    for (int i = 1; i < argc; i++) dry |= std::string(argv[i]) == "--dry-run";
+    const Params& P = in.app.params;
+    prepare(in, argv[0]);
+    if (dry) {
+      dry_run_dump(in);
+      return 0;
+    }
+    const int64_t S = (int64_t)in.cols.size();
+    const int T = (int)in.tree.leaves.size();
+    const int B = (int)in.tree.parent.size() - 1;
+    uint64_t seed = in.app.seed;
+    if (!in.app.seed_given) seed = ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}();
+
+    cmb_ctx* ctx = nullptr;
+    chk(cmb_ctx_create(-1, nullptr, &ctx));
+    chk(cmb_set_tree(ctx, (int32_t)in.tree.parent.size(), in.tree.parent.data(), in.tree.brlen.data()));
+    chk(cmb_set_model(ctx, in.model.A, in.model.Q.data(), in.model.pi.data(), (int32_t)in.rdist.rates.size(),
+                      in.rdist.rates.data(), in.rdist.probs.data(), in.count_method, nullptr));
+    chk(cmb_set_alignment(ctx, S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
+    (void)T;
+    const bool weighted_classes = get_bool(P, "simulations.weighted_classes", false);
+    display_result("Rate distribution for simulations", get_bool(P, "simulations.continuous", false) ? "continuous" : "discrete");
+    if (get_bool(P, "simulations.continuous", false))
+      throw Error("simulations.continuous=yes is not available in this build (discrete rate classes only)");
+
+    display_message("\n\n-*- Get substitution vectors -*-\n");
+    if (get_path(P, "input.vectors.file", "none") != "none")
+      throw Error("input.vectors.file (restart from a mapping file) is not available in this build");
+    std::string vec_path = get_path(P, "output.vectors.file", "none");
+    display_result("Output mapping to file", vec_path);
+    std::vector<double> n_out, norm(S), pr(S), ll(S);
+    std::vector<int32_t> rc(S);
+    if (vec_path != "none") n_out.resize((size_t)S * B);
+    chk(cmb_map(ctx, n_out.empty() ? nullptr : n_out.data(), norm.data(), pr.data(), rc.data(), ll.data()));
+    if (vec_path != "none") {
+      // LegacySubstitutionMappingTools::writeToStream (CoETools.cpp:408-412)
+      std::ofstream out(vec_path);
+      out << "Branches\tMean";
+      for (int c : in.cols) out << "\tSite" << c + 1;
+      out << "\n";
+      for (int b = 0; b < B; b++) {
+        out << b << "\t" << in.tree.brlen[b];
+        for (int64_t s = 0; s < S; s++) out << "\t" << n_out[(size_t)s * B + b];
+        out << "\n";
+      }
+    }
+    // CoETools::writeInfos (CoETools.cpp:496-531)
+    std::string infos = get_path(P, "output.infos", "none");
+    if (infos != "none") {
+      display_result("Alignment information logfile", infos);
+      std::ofstream out(infos);
+      out << "Group\tIsComplete\tIsConstant\tRC\tPR\tN\tlogLn" << std::endl;
+      for (int64_t i = 0; i < S; i++)
+        out << "[" << in.cols[i] + 1 << "]\t" << (site_is_complete(in.aln, in.alpha, in.cols[i]) ? 1 : 0) << "\t"
+            << (site_is_constant(in.aln, in.alpha, in.cols[i]) ? 1 : 0) << "\t" << rc[i] << "\t" << pr[i] << "\t"
+            << norm[i] << "\t" << ll[i] << std::endl;
+    }
+    std::string analysis = get_string(P, "analysis", "pairwise");
+    display_result("Analysis type", analysis);
+    if (get_string(P, "asr.method", "none") != "none")
+      throw Error("asr.method (side output, not used by the analysis) is not available in this build");
+
+    if (analysis == "none") {
+      // mapping only
+    } else if (analysis == "pairwise") {
+      const int stat_id = stat_id_of(P);
+      const bool null = get_bool(P, "statistic.null", true);
+      if (get_path(P, "input.sequence.file2", "none") != "none")
+        throw Error("the two-data-set (inter-gene) analysis is not available in this build (SURVEY.md s8f)");
+      display_message("\n\n-*- Perform pairwise analysis -*-\n");
+      std::string stat_path = get_path(P, "statistic.output.file", "statistics.txt");
+      if (stat_path == "none") stat_path = "statistics.txt";
+      cmb_filters f;
+      f.min_rate_class = (int32_t)get_int(P, "statistic.min_rate_class", 0);
+      f.min_rate = get_double(P, "statistic.min_rate", 0.);
+      f.max_rate_class_diff = (int32_t)get_int(P, "statistic.max_rate_class_diff", -1);
+      f.max_rate_diff = get_double(P, "statistic.max_rate_diff", -1.);
+      f.min_stat = get_double(P, "statistic.min", 0.);
+      if (null) {
+        // CoETools.cpp:638-652, 836-872
+        const int K = (int)get_int(P, "statistic.null.nb_rate_classes", 10);
+        display_result("Number of sub-distributions", K);
+        const int rep_cpu = (int)get_int(P, "statistic.null.nb_rep_CPU", 100);
+        const int rep_ram = (int)get_int(P, "statistic.null.nb_rep_RAM", 1000);
+        std::string null_path = get_path(P, "statistic.null.output.file", "none");
+        if (null_path != "none") display_result("Write simulation results to", null_path);
+        display_result("Nb of simulations to perform", (long)rep_cpu * rep_ram);
+        if (!get_bool(P, "statistic.null.compute_pvalue", true) && null_path == "none")
+          display_message("WARNING!!! statistic.null.compute_pvalue=no without an output file: nothing to do.");
+        std::vector<double> raw;
+        if (null_path != "none") raw.resize((size_t)rep_cpu * rep_ram * 4);
+        chk(cmb_null_intra(ctx, stat_id, seed, rep_cpu, rep_ram, 0, rep_cpu, weighted_classes ? 1 : 0, K, -1.,
+                           raw.empty() ? nullptr : raw.data()));
+        if (null_path != "none") {
+          std::ofstream out(null_path);
+          out << "Stat\tRCmin\tPRmin\tNmin\n"; // AnalysisTools.cpp:580,642
+          write_rows_parallel(out, (int64_t)rep_cpu * rep_ram, 80, [&](int64_t r, char* p) {
+            char* q = p;
+            q += fmt_g(q, raw[r * 4]); *q++ = '\t';
+            q += snprintf(q, 16, "%d", (int)raw[r * 4 + 1]); *q++ = '\t';
+            q += fmt_g(q, raw[r * 4 + 2]); *q++ = '\t';
+            q += fmt_g(q, raw[r * 4 + 3]); *q++ = '\n';
+            return (int)(q - p);
+          });
+        }
+      }
+      const bool pvalues = null && get_bool(P, "statistic.null.compute_pvalue", true);
+      display_message("\n\n-*- Compute statistics -*- \n");
+      display_message(std::to_string(S) + " sites => " + std::to_string(S * (S + 1) / 2) + " pairs to compute!");
+      const int64_t cap = S * (S - 1) / 2;
+      std::vector<int32_t> I(cap), J(cap), RC(cap);
+      std::vector<double> ST(cap), PR(cap), NM(cap), PV(pvalues ? cap : 0);
+      std::vector<int64_t> NS(pvalues ? cap : 0);
+      int64_t rows = 0;
+      chk(cmb_pairs(ctx, stat_id, &f, pvalues ? 1 : 0, 0, 1, cap, I.data(), J.data(), ST.data(), RC.data(), PR.data(),
+                    NM.data(), pvalues ? PV.data() : nullptr, pvalues ? NS.data() : nullptr, &rows));
+      std::ofstream out(stat_path);
+      out << "Group\tStat\tRCmin\tPRmin\tNmin";
+      if (null) out << "\tPValue\tNsim";
+      out << "\n";
+      write_rows_parallel(out, rows, 160, [&](int64_t r, char* p) {
+        char* q = p;
+        q += snprintf(q, 40, "[%d;%d]\t", in.cols[I[r]] + 1, in.cols[J[r]] + 1);
+        q += fmt_g(q, ST[r]); *q++ = '\t';
+        q += snprintf(q, 16, "%d", RC[r]); *q++ = '\t';
+        q += fmt_g(q, PR[r]); *q++ = '\t';
+        q += fmt_g(q, NM[r]);
+        if (null) {
+          if (pvalues && !std::isnan(PV[r])) {
+            *q++ = '\t';
+            q += fmt_g(q, PV[r]);
+            q += snprintf(q, 24, "\t%lld", (long long)NS[r]);
+          } else q += snprintf(q, 8, "\tNA\t0");
+        }
+        *q++ = '\n';
+        return (int)(q - p);
+      });
+      display_result("Wrote statistics to", stat_path);
+      display_result("Number of pairs written", rows);
+    } else if (analysis == "clustering") {
+      display_message("\n\n-*- Perform clustering analysis -*-\n");
+      std::string method = get_string(P, "clustering.method", "complete");
+      if (method != "none") {
+        std::string dm = get_string(P, "clustering.distance", "cor");
+        int dist_id;
+        if (dm == "Euclidian" || dm == "euclidian") dist_id = CMB_DIST_EUCLIDIAN;
+        else if (dm == "Correlation" || dm == "cor") dist_id = CMB_DIST_CORRELATION;
+        else if (dm == "Compensation" || dm == "comp")
+          throw Error("Compensation distance must be used with a mapping procedure allowing weights, e.g. "
+                      "'nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))'.");
+        else throw Error("Unknown distance method.");
+        display_result("Distance to use", dm);
+        int link;
+        if (method == "complete") link = CMB_LINK_COMPLETE;
+        else if (method == "single") link = CMB_LINK_SINGLE;
+        else if (method == "average") link = CMB_LINK_AVERAGE;
+        else throw Error("Unknown clustering method.");
+        std::string mat_path = get_path(P, "clustering.output.matrix.file", "none");
+        std::vector<double> mat;
+        if (mat_path != "none") mat.resize((size_t)S * S);
+        chk(cmb_distance_matrix(ctx, dist_id, mat.empty() ? nullptr : mat.data()));
+        if (mat_path != "none") {
+          // PhylipDistanceMatrixFormat(extended = true): count, then "name  d d d ..."
+          std::ofstream out(mat_path);
+          out << "   " << S << "\n";
+          for (int64_t i = 0; i < S; i++) {
+            out << in.cols[i] + 1 << " ";
+            for (int64_t j = 0; j < S; j++) out << " " << mat[(size_t)i * S + j];
+            out << "\n";
+          }
+          display_result("Wrote matrix to file", mat_path);
+        }
+        display_result("Clustering method", method);
+        std::vector<int32_t> left(S - 1), right(S - 1);
+        std::vector<double> height(S - 1);
+        chk(cmb_cluster(ctx, link, left.data(), right.data(), height.data()));
+        const int max_size = (int)get_int(P, "clustering.maximum_group_size", 10);
+        std::vector<int32_t> members((size_t)std::max<int64_t>(1, (S - 1) * max_size));
+        std::vector<int64_t> offs(S + 1);
+        std::vector<double> gh(S), gs(S), gn(S);
+        int64_t ng = 0;
+        chk(cmb_groups(ctx, dist_id, max_size, members.data(), offs.data(), gh.data(), gs.data(), gn.data(), &ng));
+        std::string groups_path = get_path(P, "clustering.output.groups.file", "groups_output_stats.txt");
+        if (groups_path == "none") groups_path = "groups_output_stats.txt";
+        display_result("Site clusters output file", groups_path);
+        {
+          std::ofstream out(groups_path);
+          out << "Group\tSize\tIsConstant\tDmax\tStat\tNmin\n"; // CoMap.cpp:494-550
+          for (int64_t g = 0; g < ng; g++) {
+            const int64_t n = offs[g + 1] - offs[g];
+            bool cst = false;
+            for (int64_t k = 0; k < n && !cst; k++) cst = site_is_constant(in.aln, in.alpha, in.cols[members[offs[g] + k]]);
+            out << group_string(&members[offs[g]], n, &in.cols) << "\t" << n << "\t" << (cst ? "yes" : "no") << "\t"
+                << gh[g] * 2. << "\t" << gs[g] << "\t" << gn[g] << "\n";
+          }
+        }
+        std::string tree_path = get_path(P, "clustering.output.tree.file", "none");
+        if (tree_path != "none") {
+          std::ofstream out(tree_path);
+          out << dendrogram_newick(left, right, height, S, in.cols) << std::endl;
+          display_result("Wrote tree to file", tree_path);
+        }
+        display_message("\n\n-*- Compute null distribution of clusters -*-\n");
+        display_result("Maximum group size to test", max_size);
+        if (get_bool(P, "clustering.null", false)) {
+          std::string sim_path = get_path(P, "clustering.null.output.file", "groups_output_null.txt");
+          const int nrep = (int)get_int(P, "clustering.null.number", 1);
+          display_result("Number of simulations", nrep);
+          display_result("Simulations output file", sim_path);
+          std::ofstream out;
+          if (sim_path != "none") {
+            out.open(sim_path);
+            out << "Rep\tGroup\tSize\tDmax\tStat\tNmin\n"; // ClusterTools.cpp:219
+          }
+          // replicates in batches so the host buffers stay small
+          const int batch = std::max(1, (int)std::min<int64_t>(nrep, (int64_t)(1 << 22) / std::max<int64_t>(1, S)));
+          for (int r0 = 0; r0 < nrep; r0 += batch) {
+            const int r1 = std::min(nrep, r0 + batch);
+            const int64_t cap_rows = (int64_t)(r1 - r0) * (S - 1), cap_mem = cap_rows * max_size;
+            std::vector<int32_t> rep(cap_rows), size(cap_rows), mem((size_t)std::max<int64_t>(1, cap_mem));
+            std::vector<double> dmax(cap_rows), st(cap_rows), nm(cap_rows);
+            std::vector<int64_t> off(cap_rows + 1);
+            int64_t nr = 0;
+            chk(cmb_cluster_null(ctx, dist_id, link, seed, r0, r1, weighted_classes ? 1 : 0, max_size, cap_rows, cap_mem,
+                                 rep.data(), size.data(), dmax.data(), st.data(), nm.data(), mem.data(), off.data(), &nr));
+            if (out.is_open())
+              for (int64_t k = 0; k < nr; k++) // Group holds matrix indices here (ClusterTools.cpp:284)
+                out << rep[k] << "\t" << group_string(&mem[off[k]], off[k + 1] - off[k], nullptr) << "\t" << size[k]
+                    << "\t" << dmax[k] << "\t" << st[k] << "\t" << nm[k] << "\n";
+          }
+        }
+      }
+    } else if (analysis == "candidates") {
+      throw Error("analysis=candidates (sequential accept/reject sampler) is outside the B200 hot path (SURVEY.md s2.1)");
+    } else throw Error("Unknown analysis type: " + analysis);
+
+    chk(cmb_ctx_destroy(ctx));
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+    std::cout << "Total execution time: " << secs << "s" << std::endl;
+    std::cout << "Bye bye ;-)" << std::endl;
+    return 0;
+  } catch (const std::exception& e) {
+    // CoMap.cpp:730-734: message, exit(-1)
+    std::cout << std::endl << e.what() << std::endl;
+    return 255;
+  }
+}

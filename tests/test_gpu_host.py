@@ -1,0 +1,154 @@
+"""End-to-end through the C++ front-end (`comap_b200 param=...`): the reference's option
+file for the Myoglobin example, output tables compared with the reference's own golden
+files (mapping, infos) and with the same analysis driven through the C ABI from Python."""
+import os
+import subprocess
+import numpy as np
+import pytest
+import helpers as H
+import oracle_binding as O
+from test_host import BIN, write_fixture, dry_run, decode
+
+pytestmark = pytest.mark.gpu
+
+
+def run(cwd, *args):
+    p = subprocess.run([BIN] + list(args), cwd=cwd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+def table(path):
+    rows = [ln.rstrip("\n").split("\t") for ln in open(path)]
+    return rows[0], rows[1:]
+
+
+def g(v):
+    return "%g" % v
+
+
+@pytest.fixture(scope="module")
+def myo(tmp_path_factory):
+    from comap_b200 import build as b
+    b.build_host()
+    tmp = str(tmp_path_factory.mktemp("myo"))
+    golden = write_fixture(tmp, "myoglobin")
+    return tmp, golden
+
+
+def host_inputs(tmp):
+    """Exactly the arrays the binary hands to the library (17-digit dump): parameters computed
+    by the C++ host (own incomplete gamma, own normalisation) differ from numpy/scipy in the last
+    bits, which is enough to break ties differently in clustering."""
+    p, out = dry_run(BIN, tmp, *COMMON[:-1])
+    assert p.returncode == 0
+    d = decode(out)
+    d["parent"] = d["parent"].astype(np.int32)
+    return d
+
+
+COMMON = ["param=comap.bpp", "input.sequence.file=Myoglobin.aln.sel.mase", "input.tree.file=Myo.dnd",
+          "nijt=Uniformization", "--seed=11"]
+
+
+def test_mapping_only_matches_reference_golden_files(myo):
+    tmp, golden = myo
+    run(tmp, *COMMON, "analysis=none", "output.vectors.file=Myo.vec", "output.infos=Myo.infos")
+    hdr, rows = table(os.path.join(tmp, "Myo.vec"))
+    assert hdr[:2] == ["Branches", "Mean"] and hdr[2:] == ["Site%d" % c for c in golden["vec_coords"]]
+    vec = np.array([[float(x) for x in r[2:]] for r in rows])
+    assert vec.shape == (197, 129) and [int(r[0]) for r in rows] == list(range(197))
+    assert np.allclose([float(r[1]) for r in rows], golden["vec_brlen"], rtol=1e-5)
+    # both files hold 6 significant digits; same bar as tests/test_oracle_golden.py (the golden was
+    # produced in 2012 by an older Bio++), widened by one printed ulp
+    rel = np.abs(vec - golden["vec_unif"]) / np.abs(golden["vec_unif"])
+    assert np.median(rel) < 1e-5 and rel.max() < 1.2e-4 and (rel > 2e-5).mean() < 0.1
+    hdr, rows = table(os.path.join(tmp, "Myo.infos"))
+    assert hdr == ["Group", "IsComplete", "IsConstant", "RC", "PR", "N", "logLn"]   # CoETools.cpp:515
+    assert [r[0] for r in rows] == ["[%d]" % c for c in golden["infos_coord"]]
+    assert [int(r[1]) for r in rows] == golden["infos_complete"].tolist()
+    assert [int(r[2]) for r in rows] == golden["infos_const"].tolist()
+    assert [int(r[3]) for r in rows] == golden["infos_rc"].tolist()
+    assert np.allclose([float(r[4]) for r in rows], golden["infos_pr"], rtol=2e-5)
+    assert np.allclose([float(r[6]) for r in rows], golden["infos_logl"], rtol=2e-5)
+
+
+def test_pairwise_table_equals_c_abi_run(myo):
+    from comap_b200 import api
+    tmp, _ = myo
+    run(tmp, *COMMON, "analysis=pairwise", "statistic=Correlation", "statistic.output.file=stats.txt",
+        "statistic.null.nb_rep_CPU=3", "statistic.null.nb_rep_RAM=200", "statistic.null.nb_rate_classes=4",
+        "statistic.null.output.file=null.txt")
+    c = host_inputs(tmp)
+    ctx = api.Context(device=0)
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(c["codes"], c["code_mask"])
+    m = ctx.map()
+    raw = ctx.null_intra("correlation", 11, 3, 200, K=4, want_raw=True)
+    p, k = ctx.pairs("correlation", use_null=True)
+    hdr, rows = table(os.path.join(tmp, "stats.txt"))
+    assert hdr == ["Group", "Stat", "RCmin", "PRmin", "Nmin", "PValue", "Nsim"]      # CoETools.cpp:662-665
+    assert len(rows) == k == 129 * 128 // 2
+    co = c["coords"]
+    for r in (0, 1, 127, 128, 5000, k - 1):
+        want = ["[%d;%d]" % (co[p["i"][r]], co[p["j"][r]]), g(p["stat"][r]), str(p["rcmin"][r]), g(p["prmin"][r]),
+                g(p["nmin"][r])] + (["NA", "0"] if np.isnan(p["pvalue"][r]) else [g(p["pvalue"][r]), str(p["nsim"][r])])
+        assert rows[r] == want
+    assert [x[5] for x in rows] == ["NA" if np.isnan(v) else g(v) for v in p["pvalue"]]
+    assert [x[1] for x in rows] == [g(v) for v in p["stat"]]
+    # statistics against the oracle on the oracle's own mapping (6 printed digits)
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    op = O.pairs("correlation", q["n"], q["norm"], q["post_rate"], q["rate_class"])
+    assert np.allclose([float(x[1]) for x in rows], op["stat"], rtol=2e-5, atol=2e-6)
+    hdr, nrows = table(os.path.join(tmp, "null.txt"))
+    assert hdr == ["Stat", "RCmin", "PRmin", "Nmin"] and len(nrows) == 600            # AnalysisTools.cpp:580,642
+    assert [x[0] for x in nrows] == [g(v) for v in raw[:, 0]] and [x[3] for x in nrows] == [g(v) for v in raw[:, 3]]
+    ctx.close()
+
+
+def test_clustering_tables_equal_c_abi_run(myo):
+    from comap_b200 import api
+    tmp, _ = myo
+    run(tmp, *COMMON, "analysis=clustering", "clustering.distance=cor", "clustering.method=complete",
+        "clustering.output.groups.file=groups.txt", "clustering.output.matrix.file=mat.phy",
+        "clustering.output.tree.file=clust.dnd", "clustering.null=yes", "clustering.null.number=2",
+        "clustering.null.output.file=groups_null.txt", "clustering.maximum_group_size=6")
+    c = host_inputs(tmp)
+    ctx = api.Context(device=0)
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(c["codes"], c["code_mask"])
+    ctx.map()
+    mat = ctx.distance_matrix("correlation")
+    ctx.cluster("complete")
+    grp = ctx.groups("correlation", 6)
+    hdr, rows = table(os.path.join(tmp, "groups.txt"))
+    assert hdr == ["Group", "Size", "IsConstant", "Dmax", "Stat", "Nmin"]              # CoMap.cpp:494-550
+    assert len(rows) == len(grp["members"])
+    co = c["coords"]
+    for r, mem in zip(rows, grp["members"]):
+        assert r[0] == "[" + ";".join(str(co[x]) for x in mem) + "]" and int(r[1]) == len(mem) and r[2] == "no"
+    assert [r[3] for r in rows] == [g(2 * h) for h in grp["height"]]
+    assert [r[4] for r in rows] == [g(v) for v in grp["stat"]] and [r[5] for r in rows] == [g(v) for v in grp["nmin"]]
+    lines = open(os.path.join(tmp, "mat.phy")).read().split("\n")
+    assert int(lines[0]) == 129
+    first = lines[1].split()
+    assert first[0] == str(co[0]) and [float(x) for x in first[1:]] == [float(g(v)) for v in mat[0]]
+    nul = ctx.cluster_null("correlation", "complete", 11, 0, 2, 6)
+    hdr, rows = table(os.path.join(tmp, "groups_null.txt"))
+    assert hdr == ["Rep", "Group", "Size", "Dmax", "Stat", "Nmin"]                     # ClusterTools.cpp:219
+    assert [int(r[0]) for r in rows] == nul["rep"].tolist()
+    assert [r[1] for r in rows] == ["[" + ";".join(str(x) for x in mem) + "]" for mem in nul["members"]]
+    assert [r[3] for r in rows] == [g(v) for v in nul["dmax"]] and [r[4] for r in rows] == [g(v) for v in nul["stat"]]
+    tree = open(os.path.join(tmp, "clust.dnd")).read().strip()
+    assert tree.endswith(";") and tree.count("(") == 128 and tree.count(",") == 128
+    parent, brlen, leaf_names = H.parse_newick(tree)
+    assert sorted(int(x) for x in leaf_names) == sorted(co.tolist())
+    ctx.close()
+
+
+def test_error_exit_code_and_message(myo):
+    tmp, _ = myo
+    p = subprocess.run([BIN] + COMMON + ["analysis=pairwise", "statistic=Compensation"], cwd=tmp, capture_output=True, text=True)
+    assert p.returncode == 255 and "Compensation distance must be used with a mapping procedure" in p.stdout
+    p = subprocess.run([BIN] + COMMON + ["analysis=bogus"], cwd=tmp, capture_output=True, text=True)
+    assert p.returncode == 255 and "Unknown analysis type" in p.stdout

@@ -201,7 +201,7 @@ class _DevArr:
 def run_ours(args, cfg):
     import torch
     import torch.distributed as dist
-    from comap_b200 import api
+    from comap_b200 import api, parallel as par
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -217,9 +217,9 @@ def run_ours(args, cfg):
     B = 2 * T - 3
     stat = cfg["statistic"]
     # shard of the null replicates / pair rows owned by this rank
-    bounds = np.linspace(0, RC, world + 1).astype(int)
-    r0, r1 = int(bounds[rank]), int(bounds[rank + 1])
-    max_reps = int(np.max(np.diff(bounds)))
+    bounds = par.replicate_bounds(RC, world)
+    r0, r1 = bounds[rank]
+    max_reps = max(e - b for b, e in bounds)
 
     with torch.cuda.stream(stream):
         ctx = api.Context(device=local, stream=stream.cuda_stream)
@@ -229,11 +229,9 @@ def run_ours(args, cfg):
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
         codes_pin = pin((T, S), torch.uint8); codes_pin[:] = codes
         ctx.set_alignment(codes_pin, w["code_mask"])
-        n_own = sum(S - 1 - i for i in range(S) if world == 1 or i % (2 * world) in (rank, 2 * world - 1 - rank))
+        n_own = par.owned_pairs(S, rank, world)
         cols_pin = [pin((max(1, n_own),), {np.int32: torch.int32, np.float64: torch.float64, np.int64: torch.int64}[dt])
                     for dt in api.Context.COL_DTYPE]
-        gather_buf = torch.empty((2, world, max_reps * R), dtype=torch.float64, device="cuda") if world > 1 else None
-        send_buf = torch.full((2, max_reps * R), float("nan"), dtype=torch.float64, device="cuda") if world > 1 else None
 
         def null_and_pairs():
             if world == 1:
@@ -241,12 +239,10 @@ def run_ours(args, cfg):
             else:
                 ctx.null_intra(stat, cfg["null_seed"], RC, R, K=0, rep_begin=r0, rep_end=r1)
                 sp, mp, n = ctx.null_samples_dev()
-                send_buf[0, :n].copy_(torch.as_tensor(_DevArr(sp, n), device="cuda"))
-                send_buf[1, :n].copy_(torch.as_tensor(_DevArr(mp, n), device="cuda"))
-                dist.all_gather_into_tensor(gather_buf[0].view(-1), send_buf[0])
-                dist.all_gather_into_tensor(gather_buf[1].view(-1), send_buf[1])
+                st_all, nm_all = par.all_gather_null(torch.as_tensor(_DevArr(sp, max(n, 1)), device="cuda"),
+                                                     torch.as_tensor(_DevArr(mp, max(n, 1)), device="cuda"), n, max_reps * R)
                 stream.synchronize()
-                ctx.null_load_dev(gather_buf[0].data_ptr(), gather_buf[1].data_ptr(), world * max_reps * R, K, -1.0)
+                ctx.null_load_dev(st_all.data_ptr(), nm_all.data_ptr(), st_all.numel(), K, -1.0)
             return ctx.pairs_resident(stat, use_null=True, shard_index=rank, shard_count=world)
 
         def step_resident():

@@ -233,7 +233,7 @@ def run_ours(args, cfg):
         cols_pin = [pin((max(1, n_own),), {np.int32: torch.int32, np.float64: torch.float64, np.int64: torch.int64}[dt])
                     for dt in api.Context.COL_DTYPE]
 
-        def null_and_pairs():
+        def null_dist():
             if world == 1:
                 ctx.null_intra(stat, cfg["null_seed"], RC, R, K=K, nmax=-1.0)
             else:
@@ -243,17 +243,23 @@ def run_ours(args, cfg):
                                                      torch.as_tensor(_DevArr(mp, max(n, 1)), device="cuda"), n, max_reps * R)
                 stream.synchronize()
                 ctx.null_load_dev(st_all.data_ptr(), nm_all.data_ptr(), st_all.numel(), K, -1.0)
-            return ctx.pairs_resident(stat, use_null=True, shard_index=rank, shard_count=world)
 
         def step_resident():
             ctx.map(want_vectors=False)
-            return null_and_pairs()
+            null_dist()
+            return ctx.pairs_resident(stat, use_null=True, shard_index=rank, shard_count=world)
 
         def step_e2e():
+            # the six null-independent columns are scored first and copied out while the null
+            # distribution is simulated; PValue / Nsim follow once the null exists
             ctx.set_alignment(codes_pin, w["code_mask"])
             ctx.map(want_vectors=False)
-            n = null_and_pairs()
-            for k in range(8):
+            ctx.pairs_resident(stat, use_null=False, shard_index=rank, shard_count=world, columns=0x3F)
+            for k in range(6):
+                ctx.pairs_fetch(k, cols_pin[k])
+            null_dist()
+            n = ctx.pairs_resident(stat, use_null=True, shard_index=rank, shard_count=world, columns=0xC0)
+            for k in (6, 7):
                 ctx.pairs_fetch(k, cols_pin[k])
             ctx.sync()
             return n

@@ -204,13 +204,15 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
   Context& c = ctx->c;
   cudaSetDevice(c.device);
   cudaStreamSynchronize(c.stream);
+  if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); }
+  if (c.copy_event) cudaEventDestroy(c.copy_event);
   for (auto& t : c.prof.pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
   DevBuf* bufs[] = {&c.d_code_mask, &c.d_pi, &c.d_rates, &c.d_probs, &c.d_tips, &c.d_D, &c.d_Lc, &c.d_invL,
                     &c.d_loglik, &c.d_pr, &c.d_rc, &c.d_out, &c.d_sum, &c.d_sumsq, &c.s_tips[0], &c.s_tips[1],
                     &c.s_D, &c.s_Lc, &c.s_invL, &c.s_loglik, &c.s_pr[0], &c.s_pr[1], &c.s_rc[0], &c.s_rc[1],
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
-                    &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm};
+                    &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm};
   for (DevBuf* b : bufs) b->release();
   c.down_stream.release();
   c.up_stream.release();
@@ -223,6 +225,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
 int cmb_sync(cmb_ctx* ctx) {
   CMB_TRY
   CMB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  if (ctx->c.copy_stream) CMB_CUDA(cudaStreamSynchronize(ctx->c.copy_stream));
   CMB_CATCH
 }
 
@@ -335,6 +338,8 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   if (norm) std::memcpy(norm, c.h_norm.data(), sizeof(double) * S);
   c.mapped = true;
   c.have_dist = false;
+  c.pairs_rows = -1; // resident pair columns belong to the previous mapping
+  for (auto& o : c.pairs_col_off) o = -1;
   CMB_CATCH
 }
 

@@ -364,17 +364,19 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
   }
   if (!tiles.empty())
     CMB_CUDA(cudaMemcpyAsync(mb + o_tiles, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice, c.stream));
-  // dense columns and, when filtering, compacted copies
+  // dense columns and, when filtering, compacted copies.  The layout is the same for every
+  // column mask, so columns can be produced by separate calls (the null-independent ones
+  // first, PValue / Nsim once the null exists) while earlier ones are still being copied out.
   size_t off[8] = {0}, off2[8] = {0}, cur = 0;
-  for (int k = 0; k < 8; k++)
-    if (columns >> k & 1) {
-      off[k] = cur; cur = al(cur + kColElt[k] * nT);
-      if (any_filter) { off2[k] = cur; cur = al(cur + kColElt[k] * nT); }
-    }
+  for (int k = 0; k < 8; k++) {
+    off[k] = cur; cur = al(cur + kColElt[k] * nT);
+    if (any_filter) { off2[k] = cur; cur = al(cur + kColElt[k] * nT); }
+  }
   size_t o_keep = cur;
   cur = al(cur + nT);
-  c.staging.reserve(cur + 256);
-  unsigned char* sb = c.staging.as<unsigned char>();
+  if (c.copy_stream && cur + 256 > c.pair_table.cap) CMB_CUDA(cudaStreamSynchronize(c.copy_stream)); // growing frees the old table
+  c.pair_table.reserve(cur + 256);
+  unsigned char* sb = c.pair_table.as<unsigned char>();
 
   TilesLaunch L;
   L.stat_id = stat_id; L.B = c.tree.B; L.S = S; L.S_pad = c.S_pad; L.out = c.d_out.as<double>();
@@ -412,7 +414,10 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
       c.prof.total_launches += 1;
     }
   }
-  for (int k = 0; k < 8; k++) c.pairs_col_off[k] = (columns >> k & 1) ? (int64_t)off[k] : -1;
+  if (any_filter || c.pairs_rows != kept) // filtered tables are only valid as one consistent call
+    for (auto& o : c.pairs_col_off) o = -1;
+  for (int k = 0; k < 8; k++)
+    if (columns >> k & 1) c.pairs_col_off[k] = (int64_t)off[k];
   c.pairs_rows = kept;
   if (n_rows) *n_rows = kept;
   CMB_CATCH
@@ -424,9 +429,18 @@ int cmb_pairs_fetch(cmb_ctx* ctx, int32_t column, void* host, int64_t capacity) 
   if (column < 0 || column > 7) fail("cmb_pairs_fetch: bad column %d", column);
   if (c.pairs_rows < 0 || c.pairs_col_off[column] < 0) fail("cmb_pairs_fetch: column %d is not resident", column);
   if (capacity < c.pairs_rows) fail("cmb_pairs_fetch: capacity %lld < %lld rows", (long long)capacity, (long long)c.pairs_rows);
-  if (c.pairs_rows > 0)
-    CMB_CUDA(cudaMemcpyAsync(host, c.staging.as<unsigned char>() + c.pairs_col_off[column],
-                             kColElt[column] * (size_t)c.pairs_rows, cudaMemcpyDeviceToHost, c.stream));
+  if (c.pairs_rows > 0) {
+    // copies run on their own stream behind an event, so kernels enqueued later on the
+    // compute stream (the null distribution) overlap the transfer
+    if (!c.copy_stream) {
+      CMB_CUDA(cudaStreamCreateWithFlags(&c.copy_stream, cudaStreamNonBlocking));
+      CMB_CUDA(cudaEventCreateWithFlags(&c.copy_event, cudaEventDisableTiming));
+    }
+    CMB_CUDA(cudaEventRecord(c.copy_event, c.stream));
+    CMB_CUDA(cudaStreamWaitEvent(c.copy_stream, c.copy_event, 0));
+    CMB_CUDA(cudaMemcpyAsync(host, c.pair_table.as<unsigned char>() + c.pairs_col_off[column],
+                             kColElt[column] * (size_t)c.pairs_rows, cudaMemcpyDeviceToHost, c.copy_stream));
+  }
   CMB_CATCH
 }
 
@@ -445,6 +459,7 @@ int cmb_pairs(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int32_t use_n
   for (int k = 0; k < 8; k++)
     if (columns >> k & 1) { if (cmb_pairs_fetch(ctx, k, host[k], capacity)) return 1; }
   CMB_CUDA(cudaStreamSynchronize(ctx->c.stream));
+  if (ctx->c.copy_stream) CMB_CUDA(cudaStreamSynchronize(ctx->c.copy_stream));
   if (n_rows) *n_rows = kept;
   CMB_CATCH
 }

@@ -67,7 +67,10 @@ struct Context {
   bool have_dendro = false;
 
   DevBuf scratch, scratch2, staging;
-  int64_t pairs_col_off[8] = {-1, -1, -1, -1, -1, -1, -1, -1}; // resident pair columns in `staging`
+  DevBuf pair_table;            // resident pair columns (fixed layout, see cmb_pairs_resident)
+  cudaStream_t copy_stream = nullptr; // D2H of pair columns overlaps later kernels
+  cudaEvent_t copy_event = nullptr;
+  int64_t pairs_col_off[8] = {-1, -1, -1, -1, -1, -1, -1, -1}; // resident pair columns in `pair_table`
   int64_t pairs_rows = -1;
   DevBuf pairs_mean, pairs_sd, pairs_norm; // per-site mean / sd / norm for the tile kernels
   Profile prof;

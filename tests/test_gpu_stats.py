@@ -186,3 +186,27 @@ def test_null_other_statistics(ctx):
         o = O.null_intra(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], stat, s1, s2, 3, 3.0)
         assert _close(raw[:, 0], o["raw"][:, 0]), stat
         assert np.array_equal(ctx.null_get()["bin_offsets"], o["bin_offsets"])
+
+
+def test_pair_columns_in_two_calls_overlapping_the_null(ctx):
+    """Null-independent columns scored and fetched first, PValue / Nsim after the null: same
+    table as one call (the end-to-end flow of bench.py)."""
+    c = _case(S=177)
+    _setup(ctx, c)
+    n0 = ctx.pairs_resident("correlation", use_null=False, columns=0x3F)
+    bufs = [np.empty(n0, dt) for dt in ctx.COL_DTYPE]
+    for k in range(6):
+        ctx.pairs_fetch(k, bufs[k])
+    ctx.null_intra("correlation", 5, 3, 160, K=5)
+    n1 = ctx.pairs_resident("correlation", use_null=True, columns=0xC0)
+    for k in (6, 7):
+        ctx.pairs_fetch(k, bufs[k])
+    ctx.sync()
+    ref, k = ctx.pairs("correlation", use_null=True)
+    assert n0 == n1 == k == 177 * 176 // 2
+    for name, b in zip(ctx.COLS, bufs):
+        assert _eq(b, ref[name]), name
+    with pytest.raises(RuntimeError):          # a column that was never produced cannot be fetched
+        ctx.map()
+        ctx.pairs_resident("correlation", use_null=False, columns=0x04)
+        ctx.pairs_fetch(0, bufs[0])

@@ -340,12 +340,14 @@ __device__ __forceinline__ void contract_n(const double* __restrict__ W, const d
   }
 }
 
-template <int A, int NS, int MAXT, int MINB>
+template <int A, int NS, int MAXT, int MINB, int CT, int GT>
 __global__ void __launch_bounds__(MAXT, MINB) k1_up(MapModel m, MapBuffers b, UpParams up) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int AA = A * A;
   constexpr int SW = 32 * NS;                     // sites per consumer warp
-  const int C = m.C, G = up.groups, NSTG = up.n_blocks; // ring of per-node stages
+  // CT / GT > 0 fix the class count and the site groups at compile time (every stride becomes
+  // an immediate); 0 = read them from the launch parameters
+  const int C = CT > 0 ? CT : m.C, G = GT > 0 ? GT : up.groups, NSTG = up.n_blocks; // ring of per-node stages
   const int W = G * C;                            // consumer warps
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_pad = b.n_pad;
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_up(MapModel m, MapBuffers b, Up
     // ---- producer 1: table chunks
     if (lane == 0) {
       for (uint32_t k = 0; k < up.cm.n_chunks; k++) {
-        if (k >= 2) mbar_wait_sleep(&tab_empty[k & 1], ((k >> 1) - 1) & 1, 200);
+        if (k >= 2) mbar_wait_sleep(&tab_empty[k & 1], ((k >> 1) - 1) & 1, 500);
         const uint32_t nb = __ldg(up.cm.bytes + k);
         mbar_expect_tx(&tab_full[k & 1], nb);
         tma_bulk_g2s(tab_buf + (size_t)(k & 1) * up.cm.cap, up.cm.src + __ldg(up.cm.off + k), nb, &tab_full[k & 1]);
@@ -401,7 +403,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_up(MapModel m, MapBuffers b, Up
       const uint32_t flags = (uint32_t)h0.x;
       const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB, cha = flags & kUpCherryA, chb = flags & kUpCherryB;
       const bool ina = !(tipa || cha), inb = !(tipb || chb);
-      if (!first) mbar_wait_sleep(&stg_empty[s], ph, 100);
+      if (!first) mbar_wait_sleep(&stg_empty[s], ph, 200);
       unsigned char* st = stg_ring + (size_t)s * stage_bytes;
       if (lane == 0) {
         const uint32_t nrows = (tipa || cha) + (tipb || chb) + cha + chb;
@@ -734,14 +736,16 @@ bool up_shape(int C, uint32_t cap, int max_smem, int max_warps, UpShape& sh) {
   return false;
 }
 
-template <int A, int NS, int MAXT, int MINB>
+template <int A, int NS, int MAXT, int MINB, int CT = 0, int GT = 0>
 bool try_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   int dev = 0, max_smem = 0;
   CMB_CUDA(cudaGetDevice(&dev));
   CMB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   UpShape sh;
   max_smem = max_smem / MINB - 1024; // the system reserves 1 KB of shared memory per CTA
+  if (CT > 0 && m.C != CT) return false;
   if (!up_shape<A, NS>(m.C, s.cap, max_smem, MAXT / 32 - 2, sh)) return false;
+  if (GT > 0 && sh.groups != GT) return false;
   const int SG = 32 * NS * sh.groups;
   if (b.n_pad % SG) return false;
   UpParams up;
@@ -752,8 +756,8 @@ bool try_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStre
   up.n_blocks = sh.n_blocks;
   up.n_tips = sh.n_tips;
   up.block_bytes = sh.block_bytes;
-  CMB_CUDA(cudaFuncSetAttribute(k1_up<A, NS, MAXT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
-  k1_up<A, NS, MAXT, MINB><<<(unsigned)(b.n_pad / SG), 32 * (sh.groups * m.C + 2), sh.smem, st>>>(m, b, up);
+  CMB_CUDA(cudaFuncSetAttribute(k1_up<A, NS, MAXT, MINB, CT, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh.smem));
+  k1_up<A, NS, MAXT, MINB, CT, GT><<<(unsigned)(b.n_pad / SG), 32 * (sh.groups * m.C + 2), sh.smem, st>>>(m, b, up);
   CMB_CUDA(cudaGetLastError());
   return true;
 }
@@ -772,6 +776,10 @@ void run_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStre
   bool done = false;
   if constexpr (A == 4) {
     if (shape == 2) done = try_up<4, 2, 320, 1>(m, b, s, st);
+    if (shape == 22) done = try_up<4, 2, 320, 2, 4, 2>(m, b, s, st);
+    if (shape == 12) done = try_up<4, 2, 320, 1, 4, 2>(m, b, s, st);
+    if (!done && shape != 1) done = try_up<4, 1, 320, 2, 4, 2>(m, b, s, st); // Gamma(4): strides as immediates
+    if (!done && shape != 1) done = try_up<4, 1, 320, 2, 5, 1>(m, b, s, st); // Invariant + Gamma(4)
     if (!done) done = try_up<4, 1, 320, 2>(m, b, s, st);
     if (!done) done = try_up<4, 1, 320, 1>(m, b, s, st);
   } else {

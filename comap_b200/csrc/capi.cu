@@ -92,7 +92,7 @@ void Context::ensure_streams() {
 
 MapModel Context::map_model() const {
   MapModel m;
-  m.A = A; m.C = C; m.B = tree.B; m.n_slots = tree.n_slots;
+  m.A = A; m.C = C; m.B = tree.B; m.n_slots = tree.n_slots; m.T = tree.n_leaves;
   m.code_mask = d_code_mask.as<uint32_t>();
   m.pi = d_pi.as<double>();
   m.rates = d_rates.as<double>();

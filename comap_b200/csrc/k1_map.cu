@@ -127,108 +127,226 @@ __device__ __forceinline__ TipInfo tip_from_code(const uint32_t* __restrict__ co
   return t;
 }
 
-// ------------------------------------------------------------------------------ down
-struct WarpMap {
-  int c;        // rate class of this warp
-  int g;        // site group inside the CTA
-  int64_t site; // site of this lane
-};
-__device__ __forceinline__ WarpMap warp_map(int C, int groups) {
-  const int w = threadIdx.x >> 5;
-  WarpMap m;
-  m.c = w % C;
-  m.g = w / C;
-  m.site = ((int64_t)blockIdx.x * groups + m.g) * 32 + (threadIdx.x & 31);
-  return m;
+template <int A, int NS>
+__device__ __forceinline__ void matvec_n(const double* __restrict__ T, const double (&v)[NS][A], double (&o)[NS][A]) {
+#pragma unroll
+  for (int x = 0; x < A; x++) {
+    double row[A];
+    load_row<A>(T + x * A, row);
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      double s = row[0] * v[k][0];
+#pragma unroll
+      for (int y = 1; y < A; y++) s = fma(row[y], v[k][y], s);
+      o[k][x] = s;
+    }
+  }
+}
+template <int A, int NS>
+__device__ __forceinline__ void matvec_t_n(const double* __restrict__ T, const double (&v)[NS][A], double (&o)[NS][A]) {
+#pragma unroll
+  for (int y = 0; y < A; y++) {
+    double row[A];
+    load_row<A>(T + y * A, row);
+#pragma unroll
+    for (int k = 0; k < NS; k++)
+#pragma unroll
+      for (int x = 0; x < A; x++) o[k][x] = (y == 0) ? row[x] * v[k][0] : fma(row[x], v[k][y], o[k][x]);
+  }
+}
+// acc[k] = sum_x u[k][x] * (W d[k])[x]
+template <int A, int NS>
+__device__ __forceinline__ void contract_n(const double* __restrict__ W, const double (&u)[NS][A],
+                                           const double (&d)[NS][A], double (&acc)[NS]) {
+#pragma unroll
+  for (int k = 0; k < NS; k++) acc[k] = 0.;
+#pragma unroll
+  for (int x = 0; x < A; x++) {
+    double row[A];
+    load_row<A>(W + x * A, row);
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      double s = row[0] * d[k][0];
+#pragma unroll
+      for (int y = 1; y < A; y++) s = fma(row[y], d[k][y], s);
+      acc[k] = fma(u[k][x], s, acc[k]);
+    }
+  }
 }
 
-template <int A>
-__global__ void __launch_bounds__(256) k1_down(MapModel m, MapBuffers b, ChunkMeta cm, int groups) {
+// ------------------------------------------------------------------------------ down
+// One warp per (site group, rate class); a lane owns NS sites (k*32 + lane), so every table
+// row read from shared memory serves NS sites.  ncu r1f (NS = 1): the LSU / L1 path is the
+// busiest unit of this kernel (l1tex 85 %: broadcast table reads, the per-thread message
+// stack in local memory, the partial stores), DRAM 44 %.
+template <int A, int NS, int CT>
+__global__ void __launch_bounds__(256) k1_down(MapModel m, MapBuffers b, ChunkMeta cm, int groups, int tips_in_smem) {
   extern __shared__ __align__(128) unsigned char smem[];
+  __shared__ uint32_t cmask[256];
   constexpr int AA = A * A;
-  const WarpMap wm = warp_map(m.C, groups);
-  const int64_t site = wm.site, n_pad = b.n_pad;
-  const int N = m.C * AA; // doubles per table (all classes)
+  const int C = CT > 0 ? CT : m.C;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = warp % C, g = warp / C;
+  const int64_t n_pad = b.n_pad;
+  const int64_t site = ((int64_t)blockIdx.x * groups + g) * (32 * NS) + lane; // + k*32
+  const int N = C * AA; // doubles per table (all classes)
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) cmask[i] = __ldg(m.code_mask + i);
+  // The tip codes of this CTA's sites, all T rows, are staged in shared memory up front
+  // (T x 64..128 bytes): fetching them node by node from HBM, one node ahead, made every node
+  // cost one DRAM round trip (1.3 us per node per CTA regardless of the work per node).
+  const int SGT = 32 * NS * groups;              // sites per CTA
+  unsigned char* tipbuf = smem + 128 + 2 * (size_t)cm.cap;
+  if (tips_in_smem) {
+    const int64_t cta0 = (int64_t)blockIdx.x * SGT;
+    const int per_row = SGT / 16;                // 16-byte pieces per row
+    for (int i = threadIdx.x; i < m.T * per_row; i += blockDim.x) {
+      const int row = i / per_row, piece = i % per_row;
+      *reinterpret_cast<int4*>(tipbuf + (size_t)row * SGT + piece * 16) =
+          *reinterpret_cast<const int4*>(b.tips + (size_t)row * n_pad + cta0 + piece * 16);
+    }
+  }
+  const int lsite = g * (32 * NS) + lane;        // site inside the CTA (+ k*32)
   ChunkStream cs{cm.src, cm.off, cm.bytes, cm.n_chunks, cm.cap, nullptr, nullptr};
-  cs.start(smem + 128, reinterpret_cast<uint64_t*>(smem));
+  cs.start(smem + 128, reinterpret_cast<uint64_t*>(smem)); // __syncthreads inside: cmask / tipbuf are visible
 
-  double cur[A];
-  double stk[kMaxStack][A];
-  int sp = 0;
+  double cur[NS][A];
+  // message stack: the two youngest entries live in registers (t1 on top of t0), older ones
+  // in local memory.  On a random 500-leaf tree 327 pushes cause 31 local spills instead of
+  // 327 -- the write-through local stores were 44 % of this kernel's L1 -> L2 write traffic.
+  double stk[kMaxStack][NS][A], t0[NS][A], t1[NS][A];
+  int sp = 0, nc = 0;
 #pragma unroll
-  for (int i = 0; i < A; i++) cur[i] = 0.;
+  for (int k = 0; k < NS; k++)
+#pragma unroll
+    for (int i = 0; i < A; i++) cur[k][i] = 0.;
 
   // software pipeline: the tip codes of the next record are loaded while this one computes
-  auto fetch_tips = [&](const unsigned char* rec, uint32_t& ca, uint32_t& cb) {
+  auto fetch_tips = [&](const unsigned char* rec, uint32_t (&ca)[NS], uint32_t (&cb)[NS]) {
     const int4 h = *reinterpret_cast<const int4*>(rec);
-    ca = ((uint32_t)h.x & kDownTipA) ? b.tips[(size_t)h.y * n_pad + site] : 0u;
-    cb = ((uint32_t)h.x & kDownTipB) ? b.tips[(size_t)h.z * n_pad + site] : 0u;
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      if (tips_in_smem) {
+        ca[k] = ((uint32_t)h.x & kDownTipA) ? tipbuf[(size_t)h.y * SGT + lsite + k * 32] : 0u;
+        cb[k] = ((uint32_t)h.x & kDownTipB) ? tipbuf[(size_t)h.z * SGT + lsite + k * 32] : 0u;
+      } else {
+        ca[k] = ((uint32_t)h.x & kDownTipA) ? b.tips[(size_t)h.y * n_pad + site + k * 32] : 0u;
+        cb[k] = ((uint32_t)h.x & kDownTipB) ? b.tips[(size_t)h.z * n_pad + site + k * 32] : 0u;
+      }
+    }
   };
-  uint32_t code_a = 0, code_b = 0;
+  // message of a tip through its edge: column pick when every lane holds a resolved state
+  auto tip_message = [&](const double* tp, const uint32_t (&code)[NS], double (&out)[NS][A]) {
+    uint32_t mk[NS];
+    bool single = true;
+#pragma unroll
+    for (int k = 0; k < NS; k++) {
+      mk[k] = cmask[code[k]];
+      single = single && mk[k] != 0 && (mk[k] & (mk[k] - 1)) == 0;
+    }
+    if (__all_sync(0xffffffffu, single)) {
+#pragma unroll
+      for (int k = 0; k < NS; k++) {
+        const int st = __ffs(mk[k]) - 1;
+#pragma unroll
+        for (int x = 0; x < A; x++) out[k][x] = tp[x * A + st];
+      }
+    } else {
+      double d[NS][A];
+#pragma unroll
+      for (int k = 0; k < NS; k++)
+#pragma unroll
+        for (int y = 0; y < A; y++) d[k][y] = (mk[k] >> y) & 1u ? 1. : 0.;
+      matvec_n<A, NS>(tp, d, out);
+    }
+  };
+  uint32_t code_a[NS], code_b[NS];
   const unsigned char* rp = cs.wait(0);
   fetch_tips(rp, code_a, code_b);
-  for (uint32_t k = 0; k < cm.n_chunks; k++) {
-    const uint32_t nrec = __ldg(cm.nrec + k);
-    const unsigned char* next_chunk = nullptr;
+  for (uint32_t kc = 0; kc < cm.n_chunks; kc++) {
+    const uint32_t nrec = __ldg(cm.nrec + kc);
     for (uint32_t r = 0; r < nrec; r++) {
       const int4 h = *reinterpret_cast<const int4*>(rp);
       const uint32_t flags = (uint32_t)h.x;
       const int ntab = 1 + ((flags & kDownTipA) ? 1 : 0) + ((flags & kDownPush) ? 1 : 0);
       const unsigned char* rp_next = rp + ((16 + (size_t)ntab * N * sizeof(double) + 15) & ~size_t(15));
-      if (r + 1 == nrec) rp_next = next_chunk = (k + 1 < cm.n_chunks) ? cs.wait(k + 1) : nullptr;
-      uint32_t nca = 0, ncb = 0;
+      if (r + 1 == nrec) rp_next = (kc + 1 < cm.n_chunks) ? cs.wait(kc + 1) : nullptr;
+      uint32_t nca[NS], ncb[NS];
+#pragma unroll
+      for (int k = 0; k < NS; k++) nca[k] = ncb[k] = 0;
       if (rp_next) fetch_tips(rp_next, nca, ncb);
-      const double* tp = reinterpret_cast<const double*>(rp + 16) + wm.c * AA;
-      double prod[A];
-      if (flags & kDownTipB) {
-        TipInfo t = tip_from_code(m.code_mask, code_b);
-        if (t.fast) tip_column<A, 1>(tp, t.state, prod);
-        else {
-          double d[A];
-          tip_dense<A, 1>(t.mask, d);
-          matvec<A, 1>(tp, d, prod);
-        }
-      } else matvec<A, 1>(tp, cur, prod);
+      const double* tp = reinterpret_cast<const double*>(rp + 16) + c * AA;
+      double prod[NS][A];
+      if (flags & kDownTipB) tip_message(tp, code_b, prod);
+      else matvec_n<A, NS>(tp, cur, prod);
       tp += N;
       if (flags & kDownTipA) {
-        double ma[A];
-        TipInfo t = tip_from_code(m.code_mask, code_a);
-        if (t.fast) tip_column<A, 1>(tp, t.state, ma);
-        else {
-          double d[A];
-          tip_dense<A, 1>(t.mask, d);
-          matvec<A, 1>(tp, d, ma);
-        }
+        double ma[NS][A];
+        tip_message(tp, code_a, ma);
         tp += N;
 #pragma unroll
-        for (int i = 0; i < A; i++) prod[i] *= ma[i];
+        for (int k = 0; k < NS; k++)
+#pragma unroll
+          for (int i = 0; i < A; i++) prod[k][i] *= ma[k][i];
+      } else if (nc == 2) {
+        nc = 1;
+#pragma unroll
+        for (int k = 0; k < NS; k++)
+#pragma unroll
+          for (int i = 0; i < A; i++) prod[k][i] *= t1[k][i];
+      } else if (nc == 1) {
+        nc = 0;
+#pragma unroll
+        for (int k = 0; k < NS; k++)
+#pragma unroll
+          for (int i = 0; i < A; i++) prod[k][i] *= t0[k][i];
       } else {
         --sp;
 #pragma unroll
-        for (int i = 0; i < A; i++) prod[i] *= stk[sp][i];
+        for (int k = 0; k < NS; k++)
+#pragma unroll
+          for (int i = 0; i < A; i++) prod[k][i] *= stk[sp][k][i];
       }
 #pragma unroll
-      for (int i = 0; i < A; i++) cur[i] = prod[i];
-      if (h.w >= 0) {
-        double* d = b.D + d_block(site >> 8, h.w, m.n_slots, m.C * A) + (size_t)(wm.c * A) * kDSites + (site & (kDSites - 1));
+      for (int k = 0; k < NS; k++)
 #pragma unroll
-        for (int i = 0; i < A; i++) d[i * kDSites] = cur[i];
+        for (int i = 0; i < A; i++) cur[k][i] = prod[k][i];
+      if (h.w >= 0) {
+        double* d = b.D + d_block(site >> 8, h.w, m.n_slots, C * A) + (size_t)(c * A) * kDSites + (site & (kDSites - 1));
+#pragma unroll
+        for (int k = 0; k < NS; k++)
+#pragma unroll
+          for (int i = 0; i < A; i++) d[i * kDSites + k * 32] = cur[k][i];
       }
       if (flags & kDownPush) {
-        matvec<A, 1>(tp, cur, stk[sp]);
-        ++sp;
+        if (nc == 2) { // spill the oldest cached entry
+#pragma unroll
+          for (int k = 0; k < NS; k++)
+#pragma unroll
+            for (int i = 0; i < A; i++) { stk[sp][k][i] = t0[k][i]; t0[k][i] = t1[k][i]; }
+          ++sp;
+          matvec_n<A, NS>(tp, cur, t1);
+        } else if (nc == 1) {
+          matvec_n<A, NS>(tp, cur, t1);
+          nc = 2;
+        } else {
+          matvec_n<A, NS>(tp, cur, t0);
+          nc = 1;
+        }
       }
       rp = rp_next;
-      code_a = nca;
-      code_b = ncb;
+#pragma unroll
+      for (int k = 0; k < NS; k++) { code_a[k] = nca[k]; code_b[k] = ncb[k]; }
     }
-    cs.release(k);
+    cs.release(kc);
   }
   // root: class likelihood L_c = sum_x pi_x root[c][x]
-  double l = 0.;
 #pragma unroll
-  for (int x = 0; x < A; x++) l = fma(cur[x], __ldg(m.pi + x), l);
-  b.Lc[(size_t)wm.c * n_pad + site] = l;
+  for (int k = 0; k < NS; k++) {
+    double l = 0.;
+#pragma unroll
+    for (int x = 0; x < A; x++) l = fma(cur[k][x], __ldg(m.pi + x), l);
+    b.Lc[(size_t)c * n_pad + site + k * 32] = l;
+  }
 }
 
 // ---------------------------------------------------------------------------- finish
@@ -292,53 +410,6 @@ struct UpParams {
   uint32_t block_bytes; // C*A*SG*8
 };
 constexpr int kMaxBlocks = 8; // stage ring depth
-
-template <int A, int NS>
-__device__ __forceinline__ void matvec_n(const double* __restrict__ T, const double (&v)[NS][A], double (&o)[NS][A]) {
-#pragma unroll
-  for (int x = 0; x < A; x++) {
-    double row[A];
-    load_row<A>(T + x * A, row);
-#pragma unroll
-    for (int k = 0; k < NS; k++) {
-      double s = row[0] * v[k][0];
-#pragma unroll
-      for (int y = 1; y < A; y++) s = fma(row[y], v[k][y], s);
-      o[k][x] = s;
-    }
-  }
-}
-template <int A, int NS>
-__device__ __forceinline__ void matvec_t_n(const double* __restrict__ T, const double (&v)[NS][A], double (&o)[NS][A]) {
-#pragma unroll
-  for (int y = 0; y < A; y++) {
-    double row[A];
-    load_row<A>(T + y * A, row);
-#pragma unroll
-    for (int k = 0; k < NS; k++)
-#pragma unroll
-      for (int x = 0; x < A; x++) o[k][x] = (y == 0) ? row[x] * v[k][0] : fma(row[x], v[k][y], o[k][x]);
-  }
-}
-// acc[k] = sum_x u[k][x] * (W d[k])[x]
-template <int A, int NS>
-__device__ __forceinline__ void contract_n(const double* __restrict__ W, const double (&u)[NS][A],
-                                           const double (&d)[NS][A], double (&acc)[NS]) {
-#pragma unroll
-  for (int k = 0; k < NS; k++) acc[k] = 0.;
-#pragma unroll
-  for (int x = 0; x < A; x++) {
-    double row[A];
-    load_row<A>(W + x * A, row);
-#pragma unroll
-    for (int k = 0; k < NS; k++) {
-      double s = row[0] * d[k][0];
-#pragma unroll
-      for (int y = 1; y < A; y++) s = fma(row[y], d[k][y], s);
-      acc[k] = fma(u[k][x], s, acc[k]);
-    }
-  }
-}
 
 template <int A, int NS, int MAXT, int MINB, int CT, int GT>
 __global__ void __launch_bounds__(MAXT, MINB) k1_up(MapModel m, MapBuffers b, UpParams up) {
@@ -703,16 +774,32 @@ ChunkMeta meta_of(const DevStream& s) {
 
 int groups_per_cta(int C) { return C >= 8 ? 1 : 8 / C; }
 
-template <int A>
-void run_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
-  const int groups = groups_per_cta(m.C);
+template <int A, int NS, int CT>
+void launch_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  int groups = groups_per_cta(m.C);
+  while (groups > 1 && 32 * NS * groups > kDSites) groups /= 2;
   size_t smem = 128 + 2 * (size_t)s.cap;
-  CMB_CUDA(cudaFuncSetAttribute(k1_down<A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k1_down<A><<<(unsigned)(b.n_pad / (32 * groups)), 32 * groups * m.C, smem, st>>>(m, b, meta_of(s), groups);
+  const size_t tip_bytes = (size_t)m.T * 32 * NS * groups;
+  const int tips_in_smem = tip_bytes <= 64 * 1024 && !getenv("CMB_DOWN_GLOBAL_TIPS");
+  if (tips_in_smem) smem += tip_bytes;
+  CMB_CUDA(cudaFuncSetAttribute(k1_down<A, NS, CT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1_down<A, NS, CT><<<(unsigned)(b.n_pad / (32 * NS * groups)), 32 * groups * m.C, smem, st>>>(m, b, meta_of(s), groups,
+                                                                                               tips_in_smem);
   CMB_CUDA(cudaGetLastError());
 }
-// Launch shape of the up pass: NS sites per lane, G site groups per CTA (G*C consumer warps
-// + 2 producer warps), ring depths from the shared-memory budget.
+template <int A>
+void run_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  static const int shape = getenv("CMB_DOWN_SHAPE") ? atoi(getenv("CMB_DOWN_SHAPE")) : 0; // experiment switch
+  if constexpr (A == 4) {
+    if (shape == 1) return launch_down<4, 1, 0>(m, b, s, st);
+    if (shape == 4) return m.C == 4 ? launch_down<4, 4, 4>(m, b, s, st) : launch_down<4, 1, 0>(m, b, s, st);
+    if (m.C == 4) return launch_down<4, 2, 4>(m, b, s, st);
+    if (m.C == 5) return launch_down<4, 2, 5>(m, b, s, st);
+    return launch_down<4, 2, 0>(m, b, s, st);
+  } else {
+    return launch_down<A, 1, 0>(m, b, s, st);
+  }
+}
 struct UpShape { int groups, n_blocks, n_tips; size_t smem; uint32_t block_bytes; };
 template <int A, int NS>
 bool up_shape(int C, uint32_t cap, int max_smem, int max_warps, UpShape& sh) {

@@ -72,6 +72,22 @@ __global__ void k_ldg(const unsigned char* src, size_t per_cta, double* sink) {
   if (s == 12345.678) sink[blockIdx.x] = s;
 }
 
+// write-only streams: each CTA writes its own region; piece = contiguous bytes per row, rows `stride` apart
+__global__ void k_write(unsigned char* dst, size_t per_cta, int piece, int stride) {
+  double2* base = (double2*)(dst + (size_t)blockIdx.x * per_cta);
+  const size_t n = per_cta / 16;
+  if (piece == 0) {
+    for (size_t i = threadIdx.x; i < n; i += blockDim.x) base[i] = make_double2(1.0, 2.0);
+  } else {
+    // rows of `piece` bytes at `stride`: thread t writes 8 B of row r (like the down pass: 32 lanes x 8 B x groups)
+    const int per_row = piece / 8;
+    double* b8 = (double*)base;
+    const size_t rows = per_cta / stride;
+    for (size_t r = threadIdx.x / per_row; r < rows; r += blockDim.x / per_row)
+      b8[r * (stride / 8) + threadIdx.x % per_row] = 1.0;
+  }
+}
+
 int main(int argc, char** argv) {
   const size_t total = (size_t)8 << 30;
   unsigned char* d; double* sink;
@@ -79,6 +95,30 @@ int main(int argc, char** argv) {
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
   auto report = [&](const char* name, float ms) { printf("%-60s %8.3f ms  %8.1f GB/s\n", name, ms, total / ms / 1e6); fflush(stdout); };
   char name[256];
+  for (int mode = 0; mode < 4; mode++) {
+    const int grid = 148 * 16;
+    const size_t per_cta = total / grid / 65536 * 65536;
+    int piece = mode == 0 ? 0 : mode == 1 ? 2048 : mode == 2 ? 512 : 256, stride = 2048;
+    k_write<<<grid, 256>>>(d, per_cta, piece, stride);
+    cudaEventRecord(e0);
+    k_write<<<grid, 256>>>(d, per_cta, piece, stride);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    double bytes = piece == 0 ? (double)per_cta * grid : (double)(per_cta / stride) * piece * grid;
+    printf("write-only piece=%d stride=%d: %8.3f ms %8.1f GB/s\n", piece, stride, ms, bytes / ms / 1e6);
+  }
+  {
+    cudaEventRecord(e0);
+    cudaMemsetAsync(d, 0, total);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("cudaMemset: %8.3f ms %8.1f GB/s\n", ms, total / ms / 1e6);
+    cudaEventRecord(e0);
+    cudaMemcpyAsync(d, d + total / 2, total / 2, cudaMemcpyDeviceToDevice);
+    cudaEventRecord(e1); cudaEventSynchronize(e1);
+    cudaEventElapsedTime(&ms, e0, e1);
+    printf("cudaMemcpy D2D (read+write bytes): %8.3f ms %8.1f GB/s\n", ms, total / ms / 1e6);
+  }
   for (int ctas_per_sm : {1, 2, 4}) {
     const int grid = 148 * ctas_per_sm * 8; // 8 waves
     const size_t per_cta = total / grid / 65536 * 65536;

@@ -68,7 +68,8 @@ void Context::ensure_streams() {
     OpStream os;
     build_down_stream(os, tree, tables, 0, C);
     down_stream.upload(os, stream);
-    build_up_stream(os, tree, tables, 0, C);
+    if (A == 4) build_up_mma_stream(os, tree, tables); // tensor-core up pass (k1_mma.cu)
+    else build_up_stream(os, tree, tables, 0, C);
     up_stream.upload(os, stream);
   }
   {

@@ -90,6 +90,8 @@ struct DownHdr { uint32_t flags; int32_t row_a, row_b, slot; };
 struct UpHdr { uint32_t flags; int32_t ref_a, ref_b, out_a, out_b, ref_a2, ref_b2, pad2; };
 void build_down_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb);
 void build_up_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb);
+// Same walk with the tables packed as DMMA m8n8k4 B-operand fragments (A = 4, all classes).
+void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt);
 // Simulation walk: per inner bin node (pre-order, smaller first), cumulative tables of
 // all classes.  Same header as UpHdr with ref = tip row / unused, out = original node id.
 void build_sim_stream(OpStream& s, const Tree& t, const ModelTables& mt);

@@ -41,12 +41,6 @@ __host__ __device__ __forceinline__ size_t d_block(int64_t site_block, int slot,
   return ((size_t)site_block * n_slots + slot) * ((size_t)rows * kDSites);
 }
 
-struct ChunkMeta {
-  const unsigned char* src;
-  const uint32_t *off, *bytes, *nrec;
-  uint32_t n_chunks, cap;
-};
-
 template <int A>
 __device__ __forceinline__ void load_row(const double* __restrict__ row, double (&r)[A]) {
   if constexpr (A % 2 == 0) {
@@ -311,11 +305,21 @@ __global__ void __launch_bounds__(256) k1_down(MapModel m, MapBuffers b, ChunkMe
 #pragma unroll
         for (int i = 0; i < A; i++) cur[k][i] = prod[k][i];
       if (h.w >= 0) {
-        double* d = b.D + d_block(site >> 8, h.w, m.n_slots, C * A) + (size_t)(c * A) * kDSites + (site & (kDSites - 1));
+        if constexpr (A == 4) { // [chunk][slot][class][site][state]: the layout k1_mma.cu's DMMA operands read
+          double* d = b.D + d_chunk(site / kChunkSites, h.w, m.n_slots, C) +
+                      ((size_t)c * kChunkSites + (site % kChunkSites)) * 4;
 #pragma unroll
-        for (int k = 0; k < NS; k++)
+          for (int k = 0; k < NS; k++) {
+            *reinterpret_cast<double2*>(d + k * 128) = make_double2(cur[k][0], cur[k][1]);
+            *reinterpret_cast<double2*>(d + k * 128 + 2) = make_double2(cur[k][2], cur[k][3]);
+          }
+        } else {
+          double* d = b.D + d_block(site >> 8, h.w, m.n_slots, C * A) + (size_t)(c * A) * kDSites + (site & (kDSites - 1));
 #pragma unroll
-          for (int i = 0; i < A; i++) d[i * kDSites + k * 32] = cur[k][i];
+          for (int k = 0; k < NS; k++)
+#pragma unroll
+            for (int i = 0; i < A; i++) d[i * kDSites + k * 32] = cur[k][i];
+        }
       }
       if (flags & kDownPush) {
         if (nc == 2) { // spill the oldest cached entry
@@ -381,9 +385,6 @@ __device__ __forceinline__ void group_barrier(int g, int nthreads) {
     case 2: asm volatile("bar.sync 3, %0;" ::"r"(nthreads) : "memory"); break;
     default: asm volatile("bar.sync 4, %0;" ::"r"(nthreads) : "memory"); break;
   }
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
 // Up pass + contraction.  Shape of one CTA:
@@ -767,11 +768,6 @@ __global__ void k_transpose_out(const double* __restrict__ out, int B, int64_t n
   }
 }
 
-ChunkMeta meta_of(const DevStream& s) {
-  return ChunkMeta{s.bytes.as<unsigned char>(), s.off.as<uint32_t>(), s.nbytes.as<uint32_t>(),
-                   s.nrec.as<uint32_t>(), s.n_chunks, s.cap};
-}
-
 int groups_per_cta(int C) { return C >= 8 ? 1 : 8 / C; }
 
 template <int A, int NS, int CT>
@@ -859,16 +855,10 @@ void run_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStre
   //   4 sites/lane, 1 CTA/SM (168 regs, spills)              50.4
   // Registers are per SM sub-partition (16 K each): 10 warps -> 3 on one -> <= 168 per thread,
   // two CTAs of 10 warps -> 5 on one -> <= 96.
-  static const int shape = getenv("CMB_UP_SHAPE") ? atoi(getenv("CMB_UP_SHAPE")) : 0; // experiment switch
   bool done = false;
   if constexpr (A == 4) {
-    if (shape == 2) done = try_up<4, 2, 320, 1>(m, b, s, st);
-    if (shape == 22) done = try_up<4, 2, 320, 2, 4, 2>(m, b, s, st);
-    if (shape == 12) done = try_up<4, 2, 320, 1, 4, 2>(m, b, s, st);
-    if (!done && shape != 1) done = try_up<4, 1, 320, 2, 4, 2>(m, b, s, st); // Gamma(4): strides as immediates
-    if (!done && shape != 1) done = try_up<4, 1, 320, 2, 5, 1>(m, b, s, st); // Invariant + Gamma(4)
-    if (!done) done = try_up<4, 1, 320, 2>(m, b, s, st);
-    if (!done) done = try_up<4, 1, 320, 1>(m, b, s, st);
+    launch_map_up_mma(m, b, s, st);
+    return;
   } else {
     done = try_up<A, 1, 320, 1>(m, b, s, st);
   }

@@ -1,0 +1,405 @@
+// K1 up pass + contraction for nucleotides (A = 4) on the FP64 tensor cores (DMMA m8n8k4).
+//
+// Same contract as k1_up in k1_map.cu (Bio++ computeSubtreeLikelihoodPrefix +
+// LegacySubstitutionMappingTools::computeSubstitutionVectors; reference call sites
+// CoETools.cpp:395-397, AnalysisTools.cpp:597-611), different
+// machine mapping.  The thread-per-site kernel was bound by shared-memory bandwidth: every
+// lane re-reads every 4x4 table as warp-uniform broadcast loads (ncu r1f: LSU 66 %, FP64
+// pipe 21 %).  Here a warp owns 8*NG sites and ALL rate classes; lane = (site s = lane / 4,
+// state q = lane % 4) holds ONE double per 4-vector, and every 4x4 matrix-vector product of
+// 8 sites is one DMMA.8x8x4 whose B operand (the table) is one double per lane:
+//   MMA1/2  D_child (8 sites x 4) x [P | W]      -> lane (s, q): S[q] = (P D)[q], T[q] = (W D)[q]
+//   U_a = G o S_b, U_b = G o S_a;   n_a += U_a . T_a  (per lane product, summed over classes
+//   in registers, then over q with two shuffle stages per node)
+//   MMA3/4  U (8 sites x 4) x P^T                -> lane (s, q): message to an inner child
+// B fragments come precomputed in the op stream (schedule.cpp build_up_mma_stream), so a
+// table costs 256 B of shared-memory reads per warp instead of 32 broadcast rows.  Tips need
+// no special case: their partial is the 0/1 state mask.  DMMA.8x8x4 runs at the FP64 pipe's
+// full rate (tools/dmmabench: 37 TFLOP/s, 4 cycles per SM), so the kernel trades an issue /
+// LSU bound for the FP64 pipe bound: ~3 DMMA per (node, class, 8 sites).
+//
+// Partials: [128-site chunk][slot][class][site][state] -- a lane reads its double at
+// consecutive addresses (256 B per DMMA A operand) and one TMA bulk copy moves a child's
+// whole chunk (C * 4 KB) into the stage ring.
+#include <algorithm>
+#include <cstdlib>
+#include <type_traits>
+#include "device_utils.cuh"
+#include "kernels.h"
+
+namespace cmb {
+
+namespace {
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%4,%5};"
+               : "=d"(d0), "=d"(d1)
+               : "d"(a), "d"(b), "d"(0.), "d"(0.));
+}
+
+struct UpMmaParams {
+  const unsigned char* stream;                   // records, one per node
+  const uint32_t *rec_off, *rec_bytes;
+  const int4* refs;     // per node 2 x int4: (flags, ref_a, ref_b, 0), (ref_a2, ref_b2, 0, 0)
+  uint32_t n_nodes, rec_cap;
+  int n_stages;         // ring depth
+};
+constexpr int kMaxStages = 8;
+constexpr int kSG = kChunkSites; // sites per CTA
+
+// what a child is, warp-uniform
+enum : int { kInner = 0, kTip = 1, kCherry = 2 };
+
+struct NodePtrs {       // record and stage pointers of one node, lane offsets NOT applied
+  const double *F1a, *F1b, *F3a, *F3b, *Pxa, *Pxb; // tables (shared memory)
+  const double *blk_a, *blk_b;                     // partial chunks of inner children
+};
+
+// One node, every leaf state below it resolved (no ambiguity codes in this warp's sites):
+// straight-line code over the classes so the C x NG independent DMMA chains interleave.
+//   inner child : D from the stage, (S, T) = DMMA(D, [P | W])
+//   tip child   : S = P[q][state], T = W[q][state]   (column picks from the same fragment)
+//   cherry child: D = P1[q][s1] * P2[q][s2], then as inner
+template <int NG, int C, int KA, int KB>
+__device__ __forceinline__ void node_fast(const NodePtrs& p, int lane, const int (&sa)[NG], const int (&sa2)[NG],
+                                          const int (&sb)[NG], const int (&sb2)[NG], double (&G)[C][NG],
+                                          double (*push)[NG], const double (*pop)[NG], double (&acc_a)[NG],
+                                          double (&acc_b)[NG]) {
+  const int q = lane & 3;
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    double Sa[NG], Ta[NG], Sb[NG], Tb[NG];
+    auto child = [&](auto kind, const double* F1, const double* blk, const double* Px, const int (&s1)[NG],
+                     const int (&s2)[NG], double (&S)[NG], double (&T)[NG]) {
+      constexpr int K = decltype(kind)::value;
+      if constexpr (K == kTip) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+          S[g] = F1[c * 32 + 8 * q + s1[g]];
+          T[g] = F1[c * 32 + 8 * q + 4 + s1[g]];
+        }
+      } else {
+        double D[NG];
+        if constexpr (K == kInner) {
+#pragma unroll
+          for (int g = 0; g < NG; g++) D[g] = blk[(size_t)c * (kSG * 4) + g * 32 + lane];
+        } else {
+#pragma unroll
+          for (int g = 0; g < NG; g++) D[g] = Px[c * 16 + q * 4 + s1[g]] * Px[(C + c) * 16 + q * 4 + s2[g]];
+        }
+        const double f = F1[c * 32 + lane];
+#pragma unroll
+        for (int g = 0; g < NG; g++) dmma(S[g], T[g], D[g], f);
+      }
+    };
+    child(std::integral_constant<int, KA>(), p.F1a, p.blk_a, p.Pxa, sa, sa2, Sa, Ta);
+    child(std::integral_constant<int, KB>(), p.F1b, p.blk_b, p.Pxb, sb, sb2, Sb, Tb);
+    double Ua[NG], Ub[NG];
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      Ua[g] = G[c][g] * Sb[g];
+      Ub[g] = G[c][g] * Sa[g];
+      acc_a[g] = c == 0 ? Ua[g] * Ta[g] : fma(Ua[g], Ta[g], acc_a[g]);
+      acc_b[g] = c == 0 ? Ub[g] * Tb[g] : fma(Ub[g], Tb[g], acc_b[g]);
+    }
+    double unused;
+    if constexpr (KA != kTip) {
+      if constexpr (KB != kTip) { // both expanded later: b's message waits on the stack
+        const double f3 = p.F3b[c * 32 + lane];
+#pragma unroll
+        for (int g = 0; g < NG; g++) dmma(push[c][g], unused, Ub[g], f3);
+      }
+      const double f3 = p.F3a[c * 32 + lane];
+#pragma unroll
+      for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ua[g], f3);
+    } else if constexpr (KB != kTip) {
+      const double f3 = p.F3b[c * 32 + lane];
+#pragma unroll
+      for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ub[g], f3);
+    } else if (pop) {
+#pragma unroll
+      for (int g = 0; g < NG; g++) G[c][g] = pop[c][g];
+    }
+  }
+}
+
+// Same node with ambiguity codes somewhere in the warp's sites (gaps, N, ...): a tip's partial
+// is its 0/1 state mask and goes through the DMMA like an inner child's.
+template <int NG, int C>
+__device__ __forceinline__ void node_masks(const NodePtrs& p, int lane, int kind_a, int kind_b, const uint32_t (&ma)[NG],
+                                        const uint32_t (&ma2)[NG], const uint32_t (&mb)[NG], const uint32_t (&mb2)[NG],
+                                        double (&G)[C][NG], double (*push)[NG], const double (*pop)[NG],
+                                        double (&acc_a)[NG], double (&acc_b)[NG]) {
+  const int q = lane & 3;
+#pragma unroll
+  for (int c = 0; c < C; c++) {
+    double Da[NG], Db[NG];
+    auto child = [&](int kind, const double* blk, const uint32_t (&m1)[NG], const uint32_t (&m2)[NG], const double* Px,
+                     double (&D)[NG]) {
+      if (kind == kInner) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) D[g] = blk[(size_t)c * (kSG * 4) + g * 32 + lane];
+      } else if (kind == kTip) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) D[g] = (m1[g] >> q) & 1u ? 1. : 0.;
+      } else {
+        const double* P1 = Px + c * 16 + q * 4;  // row q of the first leaf's table
+        const double* P2 = P1 + C * 16;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+          double u = 0., v = 0.;
+#pragma unroll
+          for (int y = 0; y < 4; y++) {
+            u += (m1[g] >> y) & 1u ? P1[y] : 0.;
+            v += (m2[g] >> y) & 1u ? P2[y] : 0.;
+          }
+          D[g] = u * v;
+        }
+      }
+    };
+    child(kind_a, p.blk_a, ma, ma2, p.Pxa, Da);
+    child(kind_b, p.blk_b, mb, mb2, p.Pxb, Db);
+    const double fa = p.F1a[c * 32 + lane], fb = p.F1b[c * 32 + lane];
+    double Sa[NG], Ta[NG], Sb[NG], Tb[NG], Ua[NG], Ub[NG];
+#pragma unroll
+    for (int g = 0; g < NG; g++) dmma(Sa[g], Ta[g], Da[g], fa);
+#pragma unroll
+    for (int g = 0; g < NG; g++) dmma(Sb[g], Tb[g], Db[g], fb);
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      Ua[g] = G[c][g] * Sb[g];
+      Ub[g] = G[c][g] * Sa[g];
+      acc_a[g] = c == 0 ? Ua[g] * Ta[g] : fma(Ua[g], Ta[g], acc_a[g]);
+      acc_b[g] = c == 0 ? Ub[g] * Tb[g] : fma(Ub[g], Tb[g], acc_b[g]);
+    }
+    double unused;
+    if (kind_a != kTip) {
+      if (kind_b != kTip) {
+        const double f3 = p.F3b[c * 32 + lane];
+#pragma unroll
+        for (int g = 0; g < NG; g++) dmma(push[c][g], unused, Ub[g], f3);
+      }
+      const double f3 = p.F3a[c * 32 + lane];
+#pragma unroll
+      for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ua[g], f3);
+    } else if (kind_b != kTip) {
+      const double f3 = p.F3b[c * 32 + lane];
+#pragma unroll
+      for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ub[g], f3);
+    } else if (pop) {
+#pragma unroll
+      for (int g = 0; g < NG; g++) G[c][g] = pop[c][g];
+    }
+  }
+}
+
+template <int NG, int C, int MINB>
+__global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(MapModel m, MapBuffers b, UpMmaParams up) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int W = kSG / (8 * NG);                // consumer warps
+  constexpr uint32_t kBlock = C * kSG * 32;        // bytes of one child's partial chunk
+  constexpr uint32_t kTipSlot = 4 * kSG;           // four tip rows (a, b, a2, b2)
+  const uint32_t stage_bytes = up.rec_cap + kTipSlot + 2 * kBlock; // record | tip rows | chunk a | chunk b
+  const int NSTG = up.n_stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_pad = b.n_pad;
+  const int64_t site0 = (int64_t)blockIdx.x * kSG;
+  uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* stg_empty = stg_full + kMaxStages;
+  unsigned char* stg_ring = smem + 128;
+
+  __shared__ uint32_t cmask[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) cmask[i] = __ldg(m.code_mask + i);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTG; i++) { mbar_init(&stg_full[i], 1); mbar_init(&stg_empty[i], W); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == W) {
+    // ---- producer: node n's record, tip rows and the partial chunks of its inner children go
+    //      to stage n % NSTG; one mbarrier full / empty pair per stage.  The 32 lanes fetch the
+    //      descriptors of 32 nodes at a time; lane 0 issues the copies.
+    uint32_t s = 0, ph = 1;
+    bool first = true;
+    const int64_t chunk = site0 / kChunkSites;
+    for (uint32_t n0 = 0; n0 < up.n_nodes; n0 += 32) {
+      const uint32_t mine = min(n0 + lane, up.n_nodes - 1);
+      const int4 r0 = __ldg(up.refs + 2 * mine), r1 = __ldg(up.refs + 2 * mine + 1);
+      const uint32_t off = __ldg(up.rec_off + mine), nb = __ldg(up.rec_bytes + mine);
+      const uint32_t cnt = min(32u, up.n_nodes - n0);
+      for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t flags = (uint32_t)__shfl_sync(0xffffffffu, r0.x, j);
+        const int ref_a = __shfl_sync(0xffffffffu, r0.y, j), ref_b = __shfl_sync(0xffffffffu, r0.z, j);
+        const int ref_a2 = __shfl_sync(0xffffffffu, r1.x, j), ref_b2 = __shfl_sync(0xffffffffu, r1.y, j);
+        const uint32_t roff = __shfl_sync(0xffffffffu, off, j), rnb = __shfl_sync(0xffffffffu, nb, j);
+        if (!first) mbar_wait_sleep(&stg_empty[s], ph, 200);
+        if (lane == 0) {
+          const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB, cha = flags & kUpCherryA, chb = flags & kUpCherryB;
+          const bool ina = !(tipa || cha), inb = !(tipb || chb);
+          unsigned char* st = stg_ring + (size_t)s * stage_bytes;
+          unsigned char* tp = st + up.rec_cap;
+          const uint32_t nrows = (tipa || cha) + (tipb || chb) + cha + chb;
+          mbar_expect_tx(&stg_full[s], rnb + nrows * (uint32_t)kSG + ((uint32_t)ina + (uint32_t)inb) * kBlock);
+          tma_bulk_g2s(st, up.stream + roff, rnb, &stg_full[s]);
+          if (tipa || cha) tma_bulk_g2s(tp, b.tips + (size_t)ref_a * n_pad + site0, kSG, &stg_full[s]);
+          if (tipb || chb) tma_bulk_g2s(tp + kSG, b.tips + (size_t)ref_b * n_pad + site0, kSG, &stg_full[s]);
+          if (cha) tma_bulk_g2s(tp + 2 * kSG, b.tips + (size_t)ref_a2 * n_pad + site0, kSG, &stg_full[s]);
+          if (chb) tma_bulk_g2s(tp + 3 * kSG, b.tips + (size_t)ref_b2 * n_pad + site0, kSG, &stg_full[s]);
+          if (ina) tma_bulk_g2s(tp + kTipSlot, b.D + d_chunk(chunk, ref_a, m.n_slots, C), kBlock, &stg_full[s]);
+          if (inb) tma_bulk_g2s(tp + kTipSlot + kBlock, b.D + d_chunk(chunk, ref_b, m.n_slots, C), kBlock, &stg_full[s]);
+        }
+        __syncwarp();
+        if (++s == (uint32_t)NSTG) { s = 0; ph ^= 1; first = false; }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int q = lane & 3, s8 = lane >> 2;
+  const int wsite = warp * (8 * NG);             // first site of this warp inside the CTA
+  double G[C][NG];
+  double stk[kMaxStack][C][NG];
+  int sp = 0;
+  {
+    const double piq = __ldg(m.pi + q);
+#pragma unroll
+    for (int c = 0; c < C; c++)
+#pragma unroll
+      for (int g = 0; g < NG; g++) G[c][g] = piq;
+  }
+  // after the quad reduction lane q owns the items (branch = q >> 1, groups j * 2 + (q & 1))
+  constexpr int NJ = NG / 2;
+  double invL[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; j++) invL[j] = b.invL[site0 + wsite + 8 * (2 * j + (q & 1)) + s8];
+
+  uint32_t cs = 0, cph = 0;
+  for (uint32_t node = 0; node < up.n_nodes; node++) {
+    mbar_wait(&stg_full[cs], cph);
+    const unsigned char* stage = stg_ring + (size_t)cs * stage_bytes;
+    const int4 h0 = *reinterpret_cast<const int4*>(stage);
+    const int4 h1 = *reinterpret_cast<const int4*>(stage + 16);
+    const uint32_t flags = (uint32_t)h0.x;
+    const int out_a = h0.w, out_b = h1.x;
+    const int kind_a = (flags & kUpTipA) ? kTip : (flags & kUpCherryA) ? kCherry : kInner;
+    const int kind_b = (flags & kUpTipB) ? kTip : (flags & kUpCherryB) ? kCherry : kInner;
+    NodePtrs p;
+    p.F1a = reinterpret_cast<const double*>(stage + 32);
+    p.F1b = p.F1a + C * 32;
+    p.F3a = p.F1b + C * 32;
+    p.F3b = p.F3a + (kind_a != kTip ? C * 32 : 0);
+    p.Pxa = p.F3b + (kind_b != kTip ? C * 32 : 0); // raw leaf tables of cherry a: P1[C], P2[C]
+    p.Pxb = p.Pxa + (kind_a == kCherry ? 2 * C * 16 : 0);
+    const unsigned char* ts = stage + up.rec_cap + wsite + s8; // tip code of (row, group g): ts[row * kSG + 8 g]
+    p.blk_a = reinterpret_cast<const double*>(stage + up.rec_cap + kTipSlot) + (size_t)wsite * 4;
+    p.blk_b = p.blk_a + kBlock / 8;
+
+    // ---- tips and cherries: state masks of this lane's NG sites
+    uint32_t ma[NG], ma2[NG], mb[NG], mb2[NG];
+    bool single = true;
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      ma[g] = kind_a != kInner ? cmask[ts[8 * g]] : 1u;
+      ma2[g] = kind_a == kCherry ? cmask[ts[2 * kSG + 8 * g]] : 1u;
+      mb[g] = kind_b != kInner ? cmask[ts[kSG + 8 * g]] : 1u;
+      mb2[g] = kind_b == kCherry ? cmask[ts[3 * kSG + 8 * g]] : 1u;
+      single = single && __popc(ma[g]) == 1 && __popc(ma2[g]) == 1 && __popc(mb[g]) == 1 && __popc(mb2[g]) == 1;
+    }
+    const bool fast = __all_sync(0xffffffffu, single);
+
+    double acc_a[NG], acc_b[NG];
+    double (*push)[NG] = stk[sp];
+    const double (*pop)[NG] = (flags & kUpPop) ? stk[sp > 0 ? sp - 1 : 0] : nullptr;
+    if (fast) {
+      int sa[NG], sa2[NG], sb[NG], sb2[NG];
+#pragma unroll
+      for (int g = 0; g < NG; g++) {
+        sa[g] = __ffs(ma[g]) - 1; sa2[g] = __ffs(ma2[g]) - 1;
+        sb[g] = __ffs(mb[g]) - 1; sb2[g] = __ffs(mb2[g]) - 1;
+      }
+      switch (kind_a * 3 + kind_b) {
+#define CMB_NODE(KA, KB) \
+  case KA * 3 + KB: node_fast<NG, C, KA, KB>(p, lane, sa, sa2, sb, sb2, G, push, pop, acc_a, acc_b); break;
+        CMB_NODE(kInner, kInner) CMB_NODE(kInner, kTip) CMB_NODE(kInner, kCherry)
+        CMB_NODE(kTip, kInner) CMB_NODE(kTip, kTip) CMB_NODE(kTip, kCherry)
+        CMB_NODE(kCherry, kInner) CMB_NODE(kCherry, kTip) CMB_NODE(kCherry, kCherry)
+#undef CMB_NODE
+      }
+    } else {
+      node_masks<NG, C>(p, lane, kind_a, kind_b, ma, ma2, mb, mb2, G, push, pop, acc_a, acc_b);
+    }
+    if (flags & kUpPush) ++sp;
+    else if (flags & kUpPop) --sp;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&stg_empty[cs]);   // the stage has been read
+    if (++cs == (uint32_t)NSTG) { cs = 0; cph ^= 1; }
+
+    // ---- sum over the four state lanes of a site: 2 NG values per lane -> NG / 2 complete
+    //      sums per lane (transposing reduction, 3 NG / 2 shuffles instead of 4 NG)
+    double v[NG];
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      const double send = (q & 2) ? acc_a[g] : acc_b[g];
+      const double keep = (q & 2) ? acc_b[g] : acc_a[g];
+      v[g] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    const int ob = (q & 2) ? out_b : out_a;
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const double send = (q & 1) ? v[2 * j] : v[2 * j + 1];
+      const double keep = (q & 1) ? v[2 * j + 1] : v[2 * j];
+      const double t = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      if (ob >= 0) b.out[(size_t)ob * n_pad + site0 + wsite + 8 * (2 * j + (q & 1)) + s8] = t * invL[j];
+    }
+  }
+}
+
+template <int NG, int C, int MINB>
+bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  if (m.C != C) return false;
+  int dev = 0, max_smem = 0;
+  CMB_CUDA(cudaGetDevice(&dev));
+  CMB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  max_smem = max_smem / MINB - 1024 - 1024;      // 1 KB system reserve per CTA, 1 KB static (cmask)
+  const size_t stage = (size_t)s.cap + 4 * (size_t)kSG + 2 * (size_t)C * kSG * 32;
+  const size_t fixed = 128;
+  if ((size_t)max_smem < fixed + 2 * stage) return false;
+  static const int stage_cap = getenv("CMB_UP_STAGES") ? atoi(getenv("CMB_UP_STAGES")) : kMaxStages;
+  UpMmaParams up;
+  up.stream = s.bytes.as<unsigned char>();
+  up.rec_off = s.off.as<uint32_t>();
+  up.rec_bytes = s.nbytes.as<uint32_t>();
+  up.refs = s.aux.as<int4>();
+  up.n_nodes = s.n_records;
+  up.rec_cap = s.cap;
+  up.n_stages = (int)std::min<size_t>(std::min(kMaxStages, stage_cap), ((size_t)max_smem - fixed) / stage);
+  const size_t smem = fixed + (size_t)up.n_stages * stage;
+  constexpr int threads = 32 * (kSG / (8 * NG) + 1);
+  CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1_up_mma<NG, C, MINB><<<(unsigned)(b.n_pad / kSG), threads, smem, st>>>(m, b, up);
+  CMB_CUDA(cudaGetLastError());
+  return true;
+}
+
+template <int C>
+bool up_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  static const int shape = getenv("CMB_UP_SHAPE") ? atoi(getenv("CMB_UP_SHAPE")) : 0; // experiment switch
+  if (m.C != C) return false;
+  if (shape == 41) return try_up_mma<4, C, 1>(m, b, s, st);
+  if (shape == 42) return try_up_mma<4, C, 2>(m, b, s, st);
+  if (shape == 21) return try_up_mma<2, C, 1>(m, b, s, st);
+  return try_up_mma<2, C, 2>(m, b, s, st) || try_up_mma<2, C, 1>(m, b, s, st);
+}
+
+} // namespace
+
+void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  if (m.A != 4) fail("internal: the tensor-core up pass is built for A = 4");
+  if (b.n_pad % kSG) fail("internal: n_pad must be a multiple of %d", kSG);
+  const bool done = up_mma_for<4>(m, b, s, st) || up_mma_for<5>(m, b, s, st);
+  if (!done) fail("mapping up pass: no launch shape fits shared memory for A = 4, C = %d", m.C);
+}
+
+} // namespace cmb

@@ -11,10 +11,21 @@ struct DevStream {           // an OpStream uploaded to the device
   void release();
 };
 
+struct ChunkMeta {           // kernel-side view of a DevStream
+  const unsigned char* src;
+  const uint32_t *off, *bytes, *nrec;
+  uint32_t n_chunks, cap;
+};
+inline ChunkMeta meta_of(const DevStream& s) {
+  return ChunkMeta{s.bytes.as<unsigned char>(), s.off.as<uint32_t>(), s.nbytes.as<uint32_t>(),
+                   s.nrec.as<uint32_t>(), s.n_chunks, s.cap};
+}
+
 struct MapBuffers {          // per-batch device arrays, n_pad sites (multiple of 256)
   int64_t n = 0, n_pad = 0;
   const uint8_t* tips = nullptr;   // [T][n_pad]
-  double* D = nullptr;             // [n_pad/256][n_slots][C*A][256] (block-major, k1_map.cu d_block)
+  double* D = nullptr;             // A = 20: [n_pad/256][n_slots][C*A][256] (k1_map.cu d_block);
+                                   // A = 4:  [n_pad/128][n_slots][C][128][4] (k1_mma.cu d_chunk)
   double* Lc = nullptr;            // [C][n_pad]
   double* invL = nullptr;          // [n_pad]
   double* loglik = nullptr;        // [n_pad]
@@ -35,6 +46,13 @@ void check_map_support(int A, int C); // throws when no kernel is built for (A, 
 void launch_map_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
 void launch_map_finish(const MapModel& m, const MapBuffers& b, cudaStream_t st);
 void launch_map_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
+// A = 4: tensor-core up pass (k1_mma.cu); the stream is build_up_mma_stream's
+void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
+// A = 4 partial layout: 128-site chunks, [chunk][slot][class][site][state]
+constexpr int kChunkSites = 128;
+__host__ __device__ inline size_t d_chunk(int64_t chunk, int slot, int n_slots, int C) {
+  return ((size_t)chunk * n_slots + slot) * ((size_t)C * kChunkSites * 4);
+}
 
 // site id of thread idx = base + (idx / group) * stride + idx % group
 void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,

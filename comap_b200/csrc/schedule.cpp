@@ -303,6 +303,93 @@ static void up_like_stream(OpStream& s, const Tree& t, const ModelTables& mt, in
   pk.flush();
 }
 
+// ---- tensor-core (DMMA m8n8k4) flavour of the up stream, A = 4 (k1_mma.cu)
+// One chunk per node (chunk_off / chunk_bytes = the record's offset and size; the producer
+// warp copies record n into ring stage n).  A record = UpHdr | F1a[C] | F1b[C] | F3a[C] (child
+// a inner) | F3b[C] (child b inner) | raw P of a's two leaves [C] each (a cherry) | same for
+// b.  F* are 32-double B-operand fragments, one double per lane (lane = 4 n + k holds B[k][n]):
+//   F1: B[y][2x] = P[x][y], B[y][2x+1] = W[x][y]  -> lane (site s, q) gets (P D)[q], (W D)[q]
+//   F3: B[x][2y] = P[x][y], B[x][2y+1] = 0        -> lane (site s, q) gets (P^T U)[q]
+// (so P[x][y] is also F1[8 x + y] and W[x][y] is F1[8 x + 4 + y]: the column picks of tips).
+static void table_of(const Tree& t, const ModelTables& mt, int v, int what, int c, double (&tab)[16]) {
+  const int br = t.bin[v].branch;
+  for (int x = 0; x < 4; x++)
+    for (int y = 0; y < 4; y++) {
+      if (br >= 0) tab[x * 4 + y] = (what == 0 ? mt.P : mt.W)[(((size_t)br * mt.C + c) * 4 + x) * 4 + y];
+      else tab[x * 4 + y] = what == 0 ? (x == y ? 1. : 0.) : 0.; // virtual edge: P = I, W = 0
+    }
+}
+void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
+  if (mt.A != 4) fail("internal: the tensor-core up stream is built for A = 4");
+  s = OpStream();
+  const int C = mt.C;
+  std::vector<std::vector<unsigned char>> recs;
+  size_t max_rec = 0;
+  std::vector<int> st;
+  for (size_t i = 0; i < t.up_order.size(); i++) {
+    const int v = t.up_order[i];
+    const BinNode& n = t.bin[v];
+    int a = n.left, b = n.right;
+    if (t.bin[a].leaves > t.bin[b].leaves) std::swap(a, b);
+    const bool ta = t.bin[a].left < 0, tb = t.bin[b].left < 0;
+    const bool ca = t.bin[a].cherry, cb = t.bin[b].cherry;
+    UpHdr h{};
+    h.flags = (ta ? kUpTipA : 0) | (tb ? kUpTipB : 0) | (ca ? kUpCherryA : 0) | (cb ? kUpCherryB : 0);
+    if (!ta) {
+      h.flags |= kUpTakeA;
+      if (!tb) { h.flags |= kUpPush; st.push_back(b); }
+    } else if (!tb) h.flags |= kUpTakeB;
+    else if (!st.empty()) { h.flags |= kUpPop; st.pop_back(); }
+    h.ref_a = ta ? t.bin[a].tip_row : ca ? t.bin[t.bin[a].left].tip_row : t.bin[a].slot;
+    h.ref_b = tb ? t.bin[b].tip_row : cb ? t.bin[t.bin[b].left].tip_row : t.bin[b].slot;
+    h.ref_a2 = ca ? t.bin[t.bin[a].right].tip_row : -1;
+    h.ref_b2 = cb ? t.bin[t.bin[b].right].tip_row : -1;
+    h.out_a = t.bin[a].branch;
+    h.out_b = t.bin[b].branch;
+    s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.ref_a); s.aux.push_back(h.ref_b); s.aux.push_back(0);
+    s.aux.push_back(h.ref_a2); s.aux.push_back(h.ref_b2); s.aux.push_back(0); s.aux.push_back(0);
+    s.n_records++;
+    std::vector<unsigned char> rec;
+    append(rec, &h, sizeof h);
+    double P[16], W[16], frag[32];
+    for (int e = 0; e < 2; e++) // F1a, F1b
+      for (int c = 0; c < C; c++) {
+        table_of(t, mt, e ? b : a, 0, c, P);
+        table_of(t, mt, e ? b : a, 1, c, W);
+        for (int l = 0; l < 32; l++) {
+          const int k = l & 3, nn = l >> 2;
+          frag[l] = (nn & 1) ? W[(nn >> 1) * 4 + k] : P[(nn >> 1) * 4 + k];
+        }
+        append(rec, frag, sizeof frag);
+      }
+    for (int e = 0; e < 2; e++) { // F3a, F3b for inner children
+      if (e ? tb : ta) continue;
+      for (int c = 0; c < C; c++) {
+        table_of(t, mt, e ? b : a, 0, c, P);
+        for (int l = 0; l < 32; l++) {
+          const int k = l & 3, nn = l >> 2;
+          frag[l] = (nn & 1) ? 0. : P[k * 4 + (nn >> 1)];
+        }
+        append(rec, frag, sizeof frag);
+      }
+    }
+    for (int e = 0; e < 2; e++) { // raw leaf tables of cherries
+      if (!(e ? cb : ca)) continue;
+      const BinNode& ch = t.bin[e ? b : a];
+      for (int leaf : {ch.left, ch.right})
+        for (int c = 0; c < C; c++) {
+          table_of(t, mt, leaf, 0, c, P);
+          append(rec, P, sizeof P);
+        }
+    }
+    pad16(rec);
+    max_rec = std::max(max_rec, rec.size());
+    recs.push_back(std::move(rec));
+  }
+  Packer pk(s, (uint32_t)max_rec);
+  for (auto& r : recs) { pk.add(r); pk.flush(); }
+}
+
 void build_up_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb) {
   up_like_stream(s, t, mt, c0, cb, false);
 }

@@ -132,9 +132,10 @@ void Context::prof_collect() {
 }
 
 // Down pass for every class block, site likelihoods, then up pass + contraction.
-void Context::run_map(const MapBuffers& b, bool simulated) {
+void Context::run_map(const MapBuffers& b, bool simulated, bool states_only) {
   MapModel m = map_model();
   if (simulated) m.code_mask = d_identity_mask.as<uint32_t>();
+  m.states_only = simulated && states_only;
   prof_begin("map_down");
   launch_map_down(m, b, down_stream, stream);
   launch_map_finish(m, b, stream);

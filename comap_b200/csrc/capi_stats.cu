@@ -118,7 +118,7 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
                         c.s_tips[k].as<uint8_t>(), nullptr, c.stream);
         c.prof_end(1);
       }
-      c.run_map(b[k], true);
+      c.run_map(b[k], true, sim1 == nullptr);
     }
     c.prof_begin("null_pairs");
     launch_paired(stat_id, B, n, n_pad, b[0].out, b[1].out, ns.stat.as<double>() + off, ns.nmin.as<double>() + off,

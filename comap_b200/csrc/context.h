@@ -79,7 +79,8 @@ struct Context {
   void ensure_streams();
   MapModel map_model() const;
   // maps n sites whose tips are at `tips` ([T][n_pad]); buffers given explicitly
-  void run_map(const MapBuffers& b, bool simulated);
+  // simulated: codes are state indices (identity mask); states_only: ... and known to be < A
+  void run_map(const MapBuffers& b, bool simulated, bool states_only = false);
   void prof_begin(const char* name);
   void prof_end(int launches);
   void prof_collect();

@@ -51,14 +51,14 @@ constexpr int kSG = kChunkSites; // sites per CTA
 enum : int { kInner = 0, kTip = 1, kCherry = 2 };
 
 struct NodePtrs {       // record and stage pointers of one node, lane offsets NOT applied
-  const double *F1a, *F1b, *F3a, *F3b, *Pxa, *Pxb; // tables (shared memory)
+  const double *F1a, *F1b, *F3a, *F3b, *Pxa, *Pxb, *Rta, *Rtb; // tables (shared memory)
   const double *blk_a, *blk_b;                     // partial chunks of inner children
 };
 
 // One node, every leaf state below it resolved (no ambiguity codes in this warp's sites):
 // straight-line code over the classes so the C x NG independent DMMA chains interleave.
 //   inner child : D from the stage, (S, T) = DMMA(D, [P | W])
-//   tip child   : S = P[q][state], T = W[q][state]   (column picks from the same fragment)
+//   tip child   : S = P[q][state], T = W[q][state]   (column picks from the raw tables)
 //   cherry child: D = P1[q][s1] * P2[q][s2], then as inner
 template <int NG, int C, int KA, int KB>
 __device__ __forceinline__ void node_fast(const NodePtrs& p, int lane, const int (&sa)[NG], const int (&sa2)[NG],
@@ -69,14 +69,14 @@ __device__ __forceinline__ void node_fast(const NodePtrs& p, int lane, const int
 #pragma unroll
   for (int c = 0; c < C; c++) {
     double Sa[NG], Ta[NG], Sb[NG], Tb[NG];
-    auto child = [&](auto kind, const double* F1, const double* blk, const double* Px, const int (&s1)[NG],
-                     const int (&s2)[NG], double (&S)[NG], double (&T)[NG]) {
+    auto child = [&](auto kind, const double* F1, const double* blk, const double* Px, const double* Rt,
+                     const int (&s1)[NG], const int (&s2)[NG], double (&S)[NG], double (&T)[NG]) {
       constexpr int K = decltype(kind)::value;
       if constexpr (K == kTip) {
 #pragma unroll
         for (int g = 0; g < NG; g++) {
-          S[g] = F1[c * 32 + 8 * q + s1[g]];
-          T[g] = F1[c * 32 + 8 * q + 4 + s1[g]];
+          S[g] = Rt[c * 16 + q * 4 + s1[g]];
+          T[g] = Rt[(C + c) * 16 + q * 4 + s1[g]];
         }
       } else {
         double D[NG];
@@ -92,8 +92,8 @@ __device__ __forceinline__ void node_fast(const NodePtrs& p, int lane, const int
         for (int g = 0; g < NG; g++) dmma(S[g], T[g], D[g], f);
       }
     };
-    child(std::integral_constant<int, KA>(), p.F1a, p.blk_a, p.Pxa, sa, sa2, Sa, Ta);
-    child(std::integral_constant<int, KB>(), p.F1b, p.blk_b, p.Pxb, sb, sb2, Sb, Tb);
+    child(std::integral_constant<int, KA>(), p.F1a, p.blk_a, p.Pxa, p.Rta, sa, sa2, Sa, Ta);
+    child(std::integral_constant<int, KB>(), p.F1b, p.blk_b, p.Pxb, p.Rtb, sb, sb2, Sb, Tb);
     double Ua[NG], Ub[NG];
 #pragma unroll
     for (int g = 0; g < NG; g++) {
@@ -292,33 +292,42 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
     p.F3b = p.F3a + (kind_a != kTip ? C * 32 : 0);
     p.Pxa = p.F3b + (kind_b != kTip ? C * 32 : 0); // raw leaf tables of cherry a: P1[C], P2[C]
     p.Pxb = p.Pxa + (kind_a == kCherry ? 2 * C * 16 : 0);
+    p.Rta = p.Pxb + (kind_b == kCherry ? 2 * C * 16 : 0); // raw P[C], W[C] of tip a
+    p.Rtb = p.Rta + (kind_a == kTip ? 2 * C * 16 : 0);
     const unsigned char* ts = stage + up.rec_cap + wsite + s8; // tip code of (row, group g): ts[row * kSG + 8 g]
     p.blk_a = reinterpret_cast<const double*>(stage + up.rec_cap + kTipSlot) + (size_t)wsite * 4;
     p.blk_b = p.blk_a + kBlock / 8;
 
-    // ---- tips and cherries: state masks of this lane's NG sites
-    uint32_t ma[NG], ma2[NG], mb[NG], mb2[NG];
-    bool single = true;
-#pragma unroll
-    for (int g = 0; g < NG; g++) {
-      ma[g] = kind_a != kInner ? cmask[ts[8 * g]] : 1u;
-      ma2[g] = kind_a == kCherry ? cmask[ts[2 * kSG + 8 * g]] : 1u;
-      mb[g] = kind_b != kInner ? cmask[ts[kSG + 8 * g]] : 1u;
-      mb2[g] = kind_b == kCherry ? cmask[ts[3 * kSG + 8 * g]] : 1u;
-      single = single && __popc(ma[g]) == 1 && __popc(ma2[g]) == 1 && __popc(mb[g]) == 1 && __popc(mb2[g]) == 1;
-    }
-    const bool fast = __all_sync(0xffffffffu, single);
-
+    // ---- tips and cherries: states (or state masks) of this lane's NG sites
     double acc_a[NG], acc_b[NG];
     double (*push)[NG] = stk[sp];
     const double (*pop)[NG] = (flags & kUpPop) ? stk[sp > 0 ? sp - 1 : 0] : nullptr;
-    if (fast) {
-      int sa[NG], sa2[NG], sb[NG], sb2[NG];
+    int sa[NG], sa2[NG], sb[NG], sb2[NG];
+    uint32_t ma[NG], ma2[NG], mb[NG], mb2[NG];
+    bool fast = true;
+    if (m.states_only) { // device-simulated alignment: the codes are the states
 #pragma unroll
       for (int g = 0; g < NG; g++) {
+        sa[g] = kind_a != kInner ? ts[8 * g] : 0;
+        sa2[g] = kind_a == kCherry ? ts[2 * kSG + 8 * g] : 0;
+        sb[g] = kind_b != kInner ? ts[kSG + 8 * g] : 0;
+        sb2[g] = kind_b == kCherry ? ts[3 * kSG + 8 * g] : 0;
+      }
+    } else {
+      bool single = true;
+#pragma unroll
+      for (int g = 0; g < NG; g++) {
+        ma[g] = kind_a != kInner ? cmask[ts[8 * g]] : 1u;
+        ma2[g] = kind_a == kCherry ? cmask[ts[2 * kSG + 8 * g]] : 1u;
+        mb[g] = kind_b != kInner ? cmask[ts[kSG + 8 * g]] : 1u;
+        mb2[g] = kind_b == kCherry ? cmask[ts[3 * kSG + 8 * g]] : 1u;
+        single = single && __popc(ma[g]) == 1 && __popc(ma2[g]) == 1 && __popc(mb[g]) == 1 && __popc(mb2[g]) == 1;
         sa[g] = __ffs(ma[g]) - 1; sa2[g] = __ffs(ma2[g]) - 1;
         sb[g] = __ffs(mb[g]) - 1; sb2[g] = __ffs(mb2[g]) - 1;
       }
+      fast = __all_sync(0xffffffffu, single);
+    }
+    if (fast) {
       switch (kind_a * 3 + kind_b) {
 #define CMB_NODE(KA, KB) \
   case KA * 3 + KB: node_fast<NG, C, KA, KB>(p, lane, sa, sa2, sb, sb2, G, push, pop, acc_a, acc_b); break;
@@ -385,11 +394,14 @@ bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
 
 template <int C>
 bool up_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
-  static const int shape = getenv("CMB_UP_SHAPE") ? atoi(getenv("CMB_UP_SHAPE")) : 0; // experiment switch
   if (m.C != C) return false;
-  if (shape == 41) return try_up_mma<4, C, 1>(m, b, s, st);
-  if (shape == 42) return try_up_mma<4, C, 2>(m, b, s, st);
-  if (shape == 21) return try_up_mma<2, C, 1>(m, b, s, st);
+  // B200, config 4 (517 k sites): 2 groups/warp x 2 CTAs/SM (16 consumer warps) 10.8 ms;
+  // 4 groups/warp x 2 CTAs/SM (8 warps, 168 regs) 11.2 ms; 2 groups/warp x 1 CTA/SM 12.7 ms
+  if constexpr (C == 4) {
+    static const int shape = getenv("CMB_UP_SHAPE") ? atoi(getenv("CMB_UP_SHAPE")) : 0; // experiment switch
+    if (shape == 42) return try_up_mma<4, C, 2>(m, b, s, st);
+    if (shape == 21) return try_up_mma<2, C, 1>(m, b, s, st);
+  }
   return try_up_mma<2, C, 2>(m, b, s, st) || try_up_mma<2, C, 1>(m, b, s, st);
 }
 
@@ -398,7 +410,9 @@ bool up_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
 void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.A != 4) fail("internal: the tensor-core up pass is built for A = 4");
   if (b.n_pad % kSG) fail("internal: n_pad must be a multiple of %d", kSG);
-  const bool done = up_mma_for<4>(m, b, s, st) || up_mma_for<5>(m, b, s, st);
+  const bool done = up_mma_for<1>(m, b, s, st) || up_mma_for<2>(m, b, s, st) || up_mma_for<3>(m, b, s, st) ||
+                    up_mma_for<4>(m, b, s, st) || up_mma_for<5>(m, b, s, st) || up_mma_for<6>(m, b, s, st) ||
+                    up_mma_for<7>(m, b, s, st) || up_mma_for<8>(m, b, s, st);
   if (!done) fail("mapping up pass: no launch shape fits shared memory for A = 4, C = %d", m.C);
 }
 

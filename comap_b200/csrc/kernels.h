@@ -37,6 +37,7 @@ struct MapBuffers {          // per-batch device arrays, n_pad sites (multiple o
 struct MapModel {            // device-resident model constants
   int A = 0, C = 0, B = 0, n_slots = 0, T = 0; // T = leaves (rows of the alignment)
   const uint32_t* code_mask = nullptr; // [256]
+  int states_only = 0;                 // tips hold resolved state indices 0..A-1 (device simulator output)
   const double* pi = nullptr;          // [A]
   const double* rates = nullptr;       // [C]
   const double* probs = nullptr;       // [C]

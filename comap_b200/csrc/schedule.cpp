@@ -310,7 +310,7 @@ static void up_like_stream(OpStream& s, const Tree& t, const ModelTables& mt, in
 // b.  F* are 32-double B-operand fragments, one double per lane (lane = 4 n + k holds B[k][n]):
 //   F1: B[y][2x] = P[x][y], B[y][2x+1] = W[x][y]  -> lane (site s, q) gets (P D)[q], (W D)[q]
 //   F3: B[x][2y] = P[x][y], B[x][2y+1] = 0        -> lane (site s, q) gets (P^T U)[q]
-// (so P[x][y] is also F1[8 x + y] and W[x][y] is F1[8 x + 4 + y]: the column picks of tips).
+// The raw 4x4 tables are 128 B = one word per bank pair: any column pick is conflict-free.
 static void table_of(const Tree& t, const ModelTables& mt, int v, int what, int c, double (&tab)[16]) {
   const int br = t.bin[v].branch;
   for (int x = 0; x < 4; x++)
@@ -379,6 +379,14 @@ void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
       for (int leaf : {ch.left, ch.right})
         for (int c = 0; c < C; c++) {
           table_of(t, mt, leaf, 0, c, P);
+          append(rec, P, sizeof P);
+        }
+    }
+    for (int e = 0; e < 2; e++) { // raw P and W of tip children: conflict-free column picks
+      if (!(e ? tb : ta)) continue;
+      for (int what = 0; what < 2; what++)
+        for (int c = 0; c < C; c++) {
+          table_of(t, mt, e ? b : a, what, c, P);
           append(rec, P, sizeof P);
         }
     }

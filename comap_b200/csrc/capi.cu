@@ -38,6 +38,7 @@ void DevStream::upload(const OpStream& s, cudaStream_t st) {
   CMB_CUDA(cudaMemcpyAsync(nbytes.p, s.chunk_bytes.data(), sizeof(uint32_t) * n_chunks, cudaMemcpyHostToDevice, st));
   CMB_CUDA(cudaMemcpyAsync(nrec.p, s.chunk_nrec.data(), sizeof(uint32_t) * n_chunks, cudaMemcpyHostToDevice, st));
   n_records = s.n_records;
+  stack_depth = s.stack_depth;
   if (!s.aux.empty()) {
     aux.reserve(sizeof(int32_t) * s.aux.size());
     CMB_CUDA(cudaMemcpyAsync(aux.p, s.aux.data(), sizeof(int32_t) * s.aux.size(), cudaMemcpyHostToDevice, st));
@@ -66,7 +67,8 @@ void Context::ensure_streams() {
   assign_slots(tree, A <= 4);
   {
     OpStream os;
-    build_down_stream(os, tree, tables, 0, C);
+    if (A == 4) build_down_mma_stream(os, tree, tables); // tensor-core passes (k1_mma.cu)
+    else build_down_stream(os, tree, tables, 0, C);
     down_stream.upload(os, stream);
     if (A == 4) build_up_mma_stream(os, tree, tables); // tensor-core up pass (k1_mma.cu)
     else build_up_stream(os, tree, tables, 0, C);

@@ -82,6 +82,7 @@ struct OpStream {
   std::vector<int32_t> aux;   // 8 ints per record: flags, ref_a, ref_b, 0, ref_a2, ref_b2, 0, 0 (producer-side view)
   uint32_t n_records = 0;
   uint32_t chunk_cap = 0; // largest chunk in bytes
+  int stack_depth = 0;    // message stack depth the walk needs (tensor-core down stream)
 };
 constexpr uint32_t kDownTipA = 1, kDownTipB = 2, kDownPush = 4, kDownRoot = 8;
 constexpr uint32_t kUpTipA = 1, kUpTipB = 2, kUpPop = 4, kUpPush = 8, kUpTakeA = 16, kUpTakeB = 32,
@@ -92,6 +93,7 @@ void build_down_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0
 void build_up_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb);
 // Same walk with the tables packed as DMMA m8n8k4 B-operand fragments (A = 4, all classes).
 void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt);
+void build_down_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt);
 // Simulation walk: per inner bin node (pre-order, smaller first), cumulative tables of
 // all classes.  Same header as UpHdr with ref = tip row / unused, out = original node id.
 void build_sim_stream(OpStream& s, const Tree& t, const ModelTables& mt);

@@ -107,20 +107,6 @@ __device__ __forceinline__ void tip_dense(uint32_t mask, double (&d)[CB * A]) {
     for (int y = 0; y < A; y++) d[c * A + y] = (mask >> y) & 1u ? 1. : 0.;
 }
 
-struct TipInfo {
-  uint32_t mask;
-  int state;
-  bool fast; // warp-uniform: every lane's tip is a single resolved state
-};
-__device__ __forceinline__ TipInfo tip_from_code(const uint32_t* __restrict__ code_mask, uint32_t code) {
-  TipInfo t;
-  t.mask = __ldg(code_mask + code);
-  bool single = t.mask != 0 && (t.mask & (t.mask - 1)) == 0;
-  t.state = __ffs(t.mask) - 1;
-  t.fast = __all_sync(0xffffffffu, single);
-  return t;
-}
-
 template <int A, int NS>
 __device__ __forceinline__ void matvec_n(const double* __restrict__ T, const double (&v)[NS][A], double (&o)[NS][A]) {
 #pragma unroll
@@ -785,16 +771,9 @@ void launch_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cud
 }
 template <int A>
 void run_down(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
-  static const int shape = getenv("CMB_DOWN_SHAPE") ? atoi(getenv("CMB_DOWN_SHAPE")) : 0; // experiment switch
-  if constexpr (A == 4) {
-    if (shape == 1) return launch_down<4, 1, 0>(m, b, s, st);
-    if (shape == 4) return m.C == 4 ? launch_down<4, 4, 4>(m, b, s, st) : launch_down<4, 1, 0>(m, b, s, st);
-    if (m.C == 4) return launch_down<4, 2, 4>(m, b, s, st);
-    if (m.C == 5) return launch_down<4, 2, 5>(m, b, s, st);
-    return launch_down<4, 2, 0>(m, b, s, st);
-  } else {
-    return launch_down<A, 1, 0>(m, b, s, st);
-  }
+  // nucleotides run on the tensor-core kernels (k1_mma.cu); their stream is build_down_mma_stream's
+  if constexpr (A == 4) return launch_map_down_mma(m, b, s, st);
+  else return launch_down<A, 1, 0>(m, b, s, st);
 }
 struct UpShape { int groups, n_blocks, n_tips; size_t smem; uint32_t block_bytes; };
 template <int A, int NS>
@@ -847,22 +826,9 @@ bool try_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStre
 
 template <int A>
 void run_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
-  // Shapes measured on B200 at config 4 (517 k sites per step, ms per step for the up pass):
-  //   1 site/lane, 2 CTAs/SM (16 consumer warps, 96 regs)   18.3   <- default
-  //   2 sites/lane, 1 CTA/SM (8 consumer warps, 168 regs)    20.7
-  //   1 site/lane, 3 CTAs/SM (24 consumer warps, 64 regs)    27.5
-  //   2 sites/lane, 2 CTAs/SM (96 regs, spills)              28.9
-  //   4 sites/lane, 1 CTA/SM (168 regs, spills)              50.4
-  // Registers are per SM sub-partition (16 K each): 10 warps -> 3 on one -> <= 168 per thread,
-  // two CTAs of 10 warps -> 5 on one -> <= 96.
-  bool done = false;
-  if constexpr (A == 4) {
-    launch_map_up_mma(m, b, s, st);
-    return;
-  } else {
-    done = try_up<A, 1, 320, 1>(m, b, s, st);
-  }
-  if (!done) fail("mapping up pass: no launch shape fits shared memory for A = %d, C = %d", A, m.C);
+  if constexpr (A == 4) return launch_map_up_mma(m, b, s, st);
+  else if (!try_up<A, 1, 320, 1>(m, b, s, st))
+    fail("mapping up pass: no launch shape fits shared memory for A = %d, C = %d", A, m.C);
 }
 
 } // namespace

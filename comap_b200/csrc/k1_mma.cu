@@ -405,6 +405,258 @@ bool up_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   return try_up_mma<2, C, 2>(m, b, s, st) || try_up_mma<2, C, 1>(m, b, s, st);
 }
 
+// ------------------------------------------------------------------------------ down
+// Felsenstein post-order pass in the same lane mapping (lane = (site, state), warp = 8 NG
+// sites x all classes).  A child's message through its edge, P D, is one DMMA per 8 sites
+// (the second half of the B operand is unused) or, for a resolved tip, a column pick; the
+// message of a larger sibling waits in a SHARED-MEMORY stack (depth <= log2 T, known from the
+// schedule) instead of per-thread local memory; every stored partial leaves as one 256-byte
+// row per (class, 8 sites).  The only global reads are the op stream and the tip rows, both
+// through the producer warp's TMA ring.
+struct DownMmaParams {
+  const unsigned char* stream;
+  const uint32_t *rec_off, *rec_bytes;
+  const int4* refs;     // per node (flags, row_a, row_b, 0)
+  uint32_t n_nodes, rec_cap;
+  int n_stages, smem_levels;
+};
+constexpr int kDownStages = 8;
+
+template <int NG, int C, int MINB>
+__global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_down_mma(MapModel m, MapBuffers b, DownMmaParams dp) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int W = kSG / (8 * NG);
+  constexpr uint32_t kEntry = C * kSG * 32;        // one stack level of the CTA
+  const uint32_t stage_bytes = dp.rec_cap + 2 * kSG;
+  const int NSTG = dp.n_stages;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_pad = b.n_pad;
+  const int64_t site0 = (int64_t)blockIdx.x * kSG;
+  uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* stg_empty = stg_full + kDownStages;
+  unsigned char* stg_ring = smem + 128;
+  double* stack = reinterpret_cast<double*>(stg_ring + (size_t)NSTG * stage_bytes);
+
+  __shared__ uint32_t cmask[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) cmask[i] = __ldg(m.code_mask + i);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTG; i++) { mbar_init(&stg_full[i], 1); mbar_init(&stg_empty[i], W); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp == W) {
+    // ---- producer: record + the tip rows of node n into stage n % NSTG
+    uint32_t s = 0, ph = 1;
+    bool first = true;
+    for (uint32_t n0 = 0; n0 < dp.n_nodes; n0 += 32) {
+      const uint32_t mine = min(n0 + lane, dp.n_nodes - 1);
+      const int4 r0 = __ldg(dp.refs + mine);
+      const uint32_t off = __ldg(dp.rec_off + mine), nb = __ldg(dp.rec_bytes + mine);
+      const uint32_t cnt = min(32u, dp.n_nodes - n0);
+      for (uint32_t j = 0; j < cnt; j++) {
+        const uint32_t flags = (uint32_t)__shfl_sync(0xffffffffu, r0.x, j);
+        const int row_a = __shfl_sync(0xffffffffu, r0.y, j), row_b = __shfl_sync(0xffffffffu, r0.z, j);
+        const uint32_t roff = __shfl_sync(0xffffffffu, off, j), rnb = __shfl_sync(0xffffffffu, nb, j);
+        if (!first) mbar_wait_sleep(&stg_empty[s], ph, 200);
+        if (lane == 0) {
+          const bool tipa = flags & kDownTipA, tipb = flags & kDownTipB;
+          unsigned char* st = stg_ring + (size_t)s * stage_bytes;
+          mbar_expect_tx(&stg_full[s], rnb + ((uint32_t)tipa + (uint32_t)tipb) * (uint32_t)kSG);
+          tma_bulk_g2s(st, dp.stream + roff, rnb, &stg_full[s]);
+          if (tipa) tma_bulk_g2s(st + dp.rec_cap, b.tips + (size_t)row_a * n_pad + site0, kSG, &stg_full[s]);
+          if (tipb) tma_bulk_g2s(st + dp.rec_cap + kSG, b.tips + (size_t)row_b * n_pad + site0, kSG, &stg_full[s]);
+        }
+        __syncwarp();
+        if (++s == (uint32_t)NSTG) { s = 0; ph ^= 1; first = false; }
+      }
+    }
+    return;
+  }
+
+  // ---- consumers
+  const int q = lane & 3, s8 = lane >> 2;
+  const int wsite = warp * (8 * NG);
+  double cur[C][NG];
+  double stk_l[kMaxStack][C][NG];                  // levels beyond the shared-memory stack
+  int sp = 0;
+#pragma unroll
+  for (int c = 0; c < C; c++)
+#pragma unroll
+    for (int g = 0; g < NG; g++) cur[c][g] = 0.;
+  double* my_stack = stack + (size_t)wsite * 4 + lane; // + level * kEntry / 8 + c * kSG * 4 + g * 32
+  double* my_D = b.D + d_chunk(site0 / kChunkSites, 0, m.n_slots, C) + (size_t)wsite * 4 + lane;
+  const size_t slot_stride = (size_t)C * kChunkSites * 4;
+
+  uint32_t cs = 0, cph = 0;
+  for (uint32_t node = 0; node < dp.n_nodes; node++) {
+    mbar_wait(&stg_full[cs], cph);
+    const unsigned char* stage = stg_ring + (size_t)cs * stage_bytes;
+    const int4 h = *reinterpret_cast<const int4*>(stage);
+    const uint32_t flags = (uint32_t)h.x;
+    const bool tipa = flags & kDownTipA, tipb = flags & kDownTipB;
+    const double* F = reinterpret_cast<const double*>(stage + 16);              // fragment of the running child
+    const double* Ra = F + (tipa ? 0 : C * 32);                                  // raw P of tip a
+    const double* Rb = Ra + (tipa ? C * 16 : 0);                                 // raw P of tip b
+    const double* Fv = Rb + (tipb ? C * 16 : 0);                                 // fragment of v's own edge (push)
+    const unsigned char* ts = stage + dp.rec_cap + wsite + s8;
+
+    // message of a tip through its edge: lane q's component, all classes
+    auto tip_message = [&](const unsigned char* codes, const double* R, double (&M)[C][NG]) {
+      bool fast = true;
+      uint32_t mk[NG];
+      if (m.states_only) {
+#pragma unroll
+        for (int g = 0; g < NG; g++) mk[g] = codes[8 * g];
+      } else {
+        bool single = true;
+#pragma unroll
+        for (int g = 0; g < NG; g++) {
+          mk[g] = cmask[codes[8 * g]];
+          single = single && __popc(mk[g]) == 1;
+        }
+        fast = __all_sync(0xffffffffu, single);
+        if (fast) {
+#pragma unroll
+          for (int g = 0; g < NG; g++) mk[g] = __ffs(mk[g]) - 1;
+        }
+      }
+      if (fast) {
+#pragma unroll
+        for (int c = 0; c < C; c++)
+#pragma unroll
+          for (int g = 0; g < NG; g++) M[c][g] = R[c * 16 + q * 4 + mk[g]];
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; c++)
+#pragma unroll
+          for (int g = 0; g < NG; g++) {
+            double t = 0.;
+#pragma unroll
+            for (int y = 0; y < 4; y++) t += (mk[g] >> y) & 1u ? R[c * 16 + q * 4 + y] : 0.;
+            M[c][g] = t;
+          }
+      }
+    };
+    auto edge_message = [&](const double* Fr, double (&M)[C][NG]) { // M = P cur, one DMMA per (class, 8 sites)
+      double unused;
+#pragma unroll
+      for (int c = 0; c < C; c++) {
+        const double f = Fr[c * 32 + lane];
+#pragma unroll
+        for (int g = 0; g < NG; g++) dmma(M[c][g], unused, cur[c][g], f);
+      }
+    };
+
+    double Ma[C][NG], Mb[C][NG];
+    if (tipa) {                       // cherry
+      tip_message(ts, Ra, Ma);
+      tip_message(ts + kSG, Rb, Mb);
+    } else if (tipb) {                // a's partial is the running one
+      edge_message(F, Ma);
+      tip_message(ts + kSG, Rb, Mb);
+    } else {                          // a's message waits on the stack, b's partial is the running one
+      edge_message(F, Mb);
+      --sp;
+      if (sp < dp.smem_levels) {
+        const double* e = my_stack + (size_t)sp * (kEntry / 8);
+#pragma unroll
+        for (int c = 0; c < C; c++)
+#pragma unroll
+          for (int g = 0; g < NG; g++) Ma[c][g] = e[c * (kSG * 4) + g * 32];
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; c++)
+#pragma unroll
+          for (int g = 0; g < NG; g++) Ma[c][g] = stk_l[sp - dp.smem_levels][c][g];
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++)
+#pragma unroll
+      for (int g = 0; g < NG; g++) cur[c][g] = Ma[c][g] * Mb[c][g];
+    if (h.w >= 0) {
+      double* d = my_D + (size_t)h.w * slot_stride;
+#pragma unroll
+      for (int c = 0; c < C; c++)
+#pragma unroll
+        for (int g = 0; g < NG; g++) d[c * (kChunkSites * 4) + g * 32] = cur[c][g];
+    }
+    if (flags & kDownPush) {
+      double M[C][NG];
+      edge_message(Fv, M);
+      if (sp < dp.smem_levels) {
+        double* e = my_stack + (size_t)sp * (kEntry / 8);
+#pragma unroll
+        for (int c = 0; c < C; c++)
+#pragma unroll
+          for (int g = 0; g < NG; g++) e[c * (kSG * 4) + g * 32] = M[c][g];
+      } else {
+#pragma unroll
+        for (int c = 0; c < C; c++)
+#pragma unroll
+          for (int g = 0; g < NG; g++) stk_l[sp - dp.smem_levels][c][g] = M[c][g];
+      }
+      ++sp;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&stg_empty[cs]);
+    if (++cs == (uint32_t)NSTG) { cs = 0; cph ^= 1; }
+  }
+  // ---- root: class likelihood L_c = sum_x pi_x root[c][x]
+  const double piq = __ldg(m.pi + q);
+#pragma unroll
+  for (int c = 0; c < C; c++)
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      double v = cur[c][g] * piq;
+      v += __shfl_xor_sync(0xffffffffu, v, 1);
+      v += __shfl_xor_sync(0xffffffffu, v, 2);
+      if (q == 0) b.Lc[(size_t)c * n_pad + site0 + wsite + 8 * g + s8] = v;
+    }
+}
+
+template <int NG, int C, int MINB>
+bool try_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  if (m.C != C) return false;
+  int dev = 0, max_smem = 0;
+  CMB_CUDA(cudaGetDevice(&dev));
+  CMB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+  max_smem = max_smem / MINB - 1024 - 1024;      // 1 KB system reserve per CTA, 1 KB static (cmask)
+  const size_t stage = (size_t)s.cap + 2 * (size_t)kSG, entry = (size_t)C * kSG * 32;
+  DownMmaParams dp;
+  dp.stream = s.bytes.as<unsigned char>();
+  dp.rec_off = s.off.as<uint32_t>();
+  dp.rec_bytes = s.nbytes.as<uint32_t>();
+  dp.refs = s.aux.as<int4>();
+  dp.n_nodes = s.n_records;
+  dp.rec_cap = s.cap;
+  dp.n_stages = kDownStages;
+  while (dp.n_stages > 2 && 128 + dp.n_stages * stage + entry > (size_t)max_smem) dp.n_stages /= 2;
+  if (128 + dp.n_stages * stage > (size_t)max_smem) return false;
+  // as many stack levels in shared memory as fit; deeper ones (rare) spill to local memory
+  dp.smem_levels = (int)std::min<size_t>((size_t)s.stack_depth, ((size_t)max_smem - 128 - dp.n_stages * stage) / entry);
+  if (MINB > 1 && dp.smem_levels < s.stack_depth) return false; // prefer one CTA per SM with the whole stack
+  const size_t smem = 128 + dp.n_stages * stage + (size_t)dp.smem_levels * entry;
+  constexpr int threads = 32 * (kSG / (8 * NG) + 1);
+  CMB_CUDA(cudaFuncSetAttribute(k1_down_mma<NG, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1_down_mma<NG, C, MINB><<<(unsigned)(b.n_pad / kSG), threads, smem, st>>>(m, b, dp);
+  CMB_CUDA(cudaGetLastError());
+  return true;
+}
+
+template <int C>
+bool down_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  if (m.C != C) return false;
+  if constexpr (C == 4) {
+    static const int shape = getenv("CMB_DOWN_SHAPE") ? atoi(getenv("CMB_DOWN_SHAPE")) : 0; // experiment switch
+    if (shape == 21) return try_down_mma<2, C, 1>(m, b, s, st);
+    if (shape == 11) return try_down_mma<1, C, 1>(m, b, s, st);
+    if (shape == 12) return try_down_mma<1, C, 2>(m, b, s, st);
+  }
+  return try_down_mma<2, C, 2>(m, b, s, st) || try_down_mma<2, C, 1>(m, b, s, st);
+}
+
 } // namespace
 
 void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
@@ -416,4 +668,15 @@ void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& 
   if (!done) fail("mapping up pass: no launch shape fits shared memory for A = 4, C = %d", m.C);
 }
 
+} // namespace cmb
+
+namespace cmb {
+void launch_map_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
+  if (m.A != 4) fail("internal: the tensor-core down pass is built for A = 4");
+  if (b.n_pad % kSG) fail("internal: n_pad must be a multiple of %d", kSG);
+  const bool done = down_mma_for<1>(m, b, s, st) || down_mma_for<2>(m, b, s, st) || down_mma_for<3>(m, b, s, st) ||
+                    down_mma_for<4>(m, b, s, st) || down_mma_for<5>(m, b, s, st) || down_mma_for<6>(m, b, s, st) ||
+                    down_mma_for<7>(m, b, s, st) || down_mma_for<8>(m, b, s, st);
+  if (!done) fail("mapping down pass: no launch shape fits shared memory for A = 4, C = %d", m.C);
+}
 } // namespace cmb

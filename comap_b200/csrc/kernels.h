@@ -7,6 +7,7 @@ namespace cmb {
 struct DevStream {           // an OpStream uploaded to the device
   DevBuf bytes, off, nbytes, nrec, aux;
   uint32_t n_chunks = 0, cap = 0, n_records = 0;
+  int stack_depth = 0;
   void upload(const OpStream& s, cudaStream_t st);
   void release();
 };
@@ -49,6 +50,7 @@ void launch_map_finish(const MapModel& m, const MapBuffers& b, cudaStream_t st);
 void launch_map_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
 // A = 4: tensor-core up pass (k1_mma.cu); the stream is build_up_mma_stream's
 void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
+void launch_map_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
 // A = 4 partial layout: 128-site chunks, [chunk][slot][class][site][state]
 constexpr int kChunkSites = 128;
 __host__ __device__ inline size_t d_chunk(int64_t chunk, int slot, int n_slots, int C) {

@@ -398,6 +398,78 @@ void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
   for (auto& r : recs) { pk.add(r); pk.flush(); }
 }
 
+// Down stream for the tensor-core kernels (A = 4), one chunk per node, post-order with the
+// larger child (a) first.  Where the operands of node v come from:
+//   a tip, b tip    : two column picks                          (raw P_a[C], P_b[C])
+//   a inner, b tip  : a's partial is the running one -> DMMA    (F_a[C], raw P_b[C])
+//   a inner, b inner: a's message waits on the stack, b's partial is the running one (F_b[C])
+// kDownPush: v is the larger child of a node whose other child is inner too, so v's message
+// P_v D_v goes to the stack (F_v[C] follows).  F: B[y][2x] = P[x][y], B[y][2x+1] = 0.
+void build_down_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
+  if (mt.A != 4) fail("internal: the tensor-core down stream is built for A = 4");
+  s = OpStream();
+  const int C = mt.C;
+  std::vector<std::vector<unsigned char>> recs;
+  size_t max_rec = 0;
+  auto larger_first = [&](int v, int& a, int& b) {
+    a = t.bin[v].left; b = t.bin[v].right;
+    if (t.bin[b].leaves > t.bin[a].leaves) std::swap(a, b);
+  };
+  int depth = 0, sp = 0;
+  for (int v : t.down_order) {
+    const BinNode& n = t.bin[v];
+    int a, b;
+    larger_first(v, a, b);
+    const bool ta = t.bin[a].left < 0, tb = t.bin[b].left < 0;
+    if (ta && !tb) fail("internal: down order must expand the larger child first");
+    DownHdr h{};
+    h.flags = (ta ? kDownTipA : 0) | (tb ? kDownTipB : 0);
+    h.row_a = ta ? t.bin[a].tip_row : -1;
+    h.row_b = tb ? t.bin[b].tip_row : -1;
+    h.slot = n.slot;
+    if (!ta && !tb) sp--; // pops a's message
+    bool push = false;
+    if (v == t.bin_root) h.flags |= kDownRoot;
+    else {
+      int pa, pb;
+      larger_first(n.parent, pa, pb);
+      push = pa == v && t.bin[pb].left >= 0;
+    }
+    if (push) { h.flags |= kDownPush; depth = std::max(depth, ++sp); }
+    s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.row_a); s.aux.push_back(h.row_b); s.aux.push_back(0);
+    s.n_records++;
+    std::vector<unsigned char> rec;
+    append(rec, &h, sizeof h);
+    double P[16], frag[32];
+    auto add_frag = [&](int node) {
+      for (int c = 0; c < C; c++) {
+        table_of(t, mt, node, 0, c, P);
+        for (int l = 0; l < 32; l++) {
+          const int k = l & 3, nn = l >> 2;
+          frag[l] = (nn & 1) ? 0. : P[(nn >> 1) * 4 + k];
+        }
+        append(rec, frag, sizeof frag);
+      }
+    };
+    auto add_raw = [&](int node) {
+      for (int c = 0; c < C; c++) {
+        table_of(t, mt, node, 0, c, P);
+        append(rec, P, sizeof P);
+      }
+    };
+    if (!ta) add_frag(tb ? a : b);
+    if (ta) add_raw(a);
+    if (tb) add_raw(b);
+    if (push) add_frag(v);
+    pad16(rec);
+    max_rec = std::max(max_rec, rec.size());
+    recs.push_back(std::move(rec));
+  }
+  s.stack_depth = depth;
+  Packer pk(s, (uint32_t)max_rec);
+  for (auto& r : recs) { pk.add(r); pk.flush(); }
+}
+
 void build_up_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb) {
   up_like_stream(s, t, mt, c0, cb, false);
 }

@@ -42,6 +42,25 @@ def test_map_dna_vs_oracle(ctx, T, S, seed, amb):
     _check(r, q)
 
 
+@pytest.mark.parametrize("C", [1, 2, 3, 6, 8])
+def test_map_dna_class_counts(ctx, C):
+    """Every rate-class count the tensor-core kernels are instantiated for (1..8), with gaps."""
+    c = H.random_dna_case(17, 260, 10 + C, C=C, ambiguity=0.05)
+    _setup(ctx, c)
+    r = ctx.map()
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    _check(r, q)
+
+
+def test_map_dna_deep_tree(ctx):
+    """500 taxa (the bench tree shape): message stack several levels deep, cherries, long walks."""
+    c = H.random_dna_case(500, 300, 20251018, mean_brlen=0.02)
+    _setup(ctx, c)
+    r = ctx.map()
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    _check(r, q)
+
+
 def test_map_invariant_five_classes(ctx):
     """GTR + Invariant(Gamma4): C = 5 with a rate-0 class -> two class blocks (4 + 1)."""
     parent, brlen = syn.random_tree(30, 7, 0.1)

@@ -10,7 +10,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcomap_b200.so")
 
-STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "compensation": 4}
+STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "compensation": 4,
+        "corrected_correlation": 5}
 DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
 LINK = {"complete": 0, "single": 1, "average": 2}
 COUNT = {"uniformization": 0, "decomposition": 1}

@@ -103,6 +103,23 @@ MapModel Context::map_model() const {
   return m;
 }
 
+const double* Context::mean_vector() {
+  if (!mapped) fail("the corrected correlation needs a mapped alignment (cmb_map) for its mean vector");
+  if (!have_meanvec) {
+    const int B = tree.B;
+    d_meanvec.reserve(sizeof(double) * B);
+    corr_mean.reserve(sizeof(double) * S_pad);
+    corr_sd.reserve(sizeof(double) * S_pad);
+    scratch2.reserve(sizeof(double) * S_pad);
+    launch_mean_vector(B, S, S_pad, d_out.as<double>(), d_meanvec.as<double>(), stream);
+    launch_prep(B, S, S_pad, d_out.as<double>(), d_meanvec.as<double>(), corr_mean.as<double>(), corr_sd.as<double>(),
+                scratch2.as<double>(), stream);
+    prof.total_launches += 2;
+    have_meanvec = true;
+  }
+  return d_meanvec.as<double>();
+}
+
 void Context::prof_begin(const char* name) {
   if (!prof.enabled) return;
   cudaEvent_t a, b;
@@ -216,7 +233,8 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_D, &c.s_Lc, &c.s_invL, &c.s_loglik, &c.s_pr[0], &c.s_pr[1], &c.s_rc[0], &c.s_rc[1],
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
-                    &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm};
+                    &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm,
+                    &c.d_meanvec, &c.corr_mean, &c.corr_sd};
   for (DevBuf* b : bufs) b->release();
   c.down_stream.release();
   c.up_stream.release();
@@ -322,7 +340,8 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   c.pairs_mean.reserve(sizeof(double) * Sp);
   c.pairs_sd.reserve(sizeof(double) * Sp);
   c.pairs_norm.reserve(sizeof(double) * Sp);
-  launch_prep(B, S, Sp, b.out, c.pairs_mean.as<double>(), c.pairs_sd.as<double>(), c.pairs_norm.as<double>(), c.stream);
+  launch_prep(B, S, Sp, b.out, nullptr, c.pairs_mean.as<double>(), c.pairs_sd.as<double>(), c.pairs_norm.as<double>(), c.stream);
+  c.have_meanvec = false;
   c.prof.total_launches += 1;
   c.h_norm.resize(S);
   CMB_CUDA(cudaMemcpyAsync(c.h_norm.data(), c.pairs_norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));

@@ -25,7 +25,7 @@ struct cmb_ctx { Context c; };
 namespace {
 
 void check_stat(int stat_id) {
-  if (stat_id < 0 || stat_id > 4) fail("unknown statistic id %d", stat_id);
+  if (stat_id < 0 || stat_id > CMB_STAT_CORRECTED_CORRELATION) fail("unknown statistic id %d", stat_id);
 }
 
 // Bytes of device memory one simulated site needs through simulate -> map x2 -> paired.
@@ -101,6 +101,10 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
   max_sites = std::min<int64_t>(max_sites, (int64_t)1 << 20);
   int64_t rpb = std::max<int64_t>(1, max_sites / R);
   MapModel m = c.map_model();
+  // the corrected correlation scores simulated pairs with the OBSERVED alignment's mean vector
+  // (one statistic object serves both loops upstream, CoMap.cpp:350-359)
+  const bool corrected = stat_id == CMB_STAT_CORRECTED_CORRELATION;
+  const double* mv = corrected ? c.mean_vector() : nullptr;
   int64_t off = 0;
   for (int64_t r0 = rep_begin; r0 < rep_end; r0 += rpb) {
     const int64_t nb = std::min<int64_t>(rpb, rep_end - r0), n = nb * R, n_pad = pad_sites(n);
@@ -121,7 +125,7 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
       c.run_map(b[k], true, sim1 == nullptr);
     }
     c.prof_begin("null_pairs");
-    launch_paired(stat_id, B, n, n_pad, b[0].out, b[1].out, ns.stat.as<double>() + off, ns.nmin.as<double>() + off,
+    launch_paired(corrected ? 0 : stat_id, B, n, n_pad, b[0].out, b[1].out, mv, ns.stat.as<double>() + off, ns.nmin.as<double>() + off,
                   c.stream);
     c.prof_end(1);
     if (raw) {
@@ -381,6 +385,11 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
   TilesLaunch L;
   L.stat_id = stat_id; L.B = c.tree.B; L.S = S; L.S_pad = c.S_pad; L.out = c.d_out.as<double>();
   L.mean = c.pairs_mean.as<double>(); L.sd = c.pairs_sd.as<double>(); L.norm = c.pairs_norm.as<double>();
+  if (stat_id == CMB_STAT_CORRECTED_CORRELATION) { // correlation of the mean-vector-corrected rows
+    L.mv = c.mean_vector();
+    L.stat_id = CMB_STAT_CORRELATION;
+    L.mean = c.corr_mean.as<double>(); L.sd = c.corr_sd.as<double>();
+  }
   L.post_rate = c.d_pr.as<double>(); L.rate_class = c.d_rc.as<int32_t>();
   L.tiles = (const int2*)(mb + o_tiles); L.n_tiles = (int64_t)tiles.size();
   L.rows = shard_count == 1 ? nullptr : (const int32_t*)(mb + o_rows);
@@ -539,7 +548,7 @@ int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t se
     c.prof_end(1);
     c.run_map(b, true);
     mean.reserve(sizeof(double) * S_pad); sd.reserve(sizeof(double) * S_pad); norm.reserve(sizeof(double) * S_pad);
-    launch_prep(B, S, S_pad, b.out, mean.as<double>(), sd.as<double>(), norm.as<double>(), c.stream);
+    launch_prep(B, S, S_pad, b.out, nullptr, mean.as<double>(), sd.as<double>(), norm.as<double>(), c.stream);
     c.prof.total_launches += 1;
     CMB_CUDA(cudaMemcpyAsync(h_norm.data(), norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
     distance_on_device(c, dist_id, b.out, S, S_pad, mean.as<double>(), sd.as<double>(), norm.as<double>());

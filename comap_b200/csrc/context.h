@@ -73,6 +73,11 @@ struct Context {
   int64_t pairs_col_off[8] = {-1, -1, -1, -1, -1, -1, -1, -1}; // resident pair columns in `pair_table`
   int64_t pairs_rows = -1;
   DevBuf pairs_mean, pairs_sd, pairs_norm; // per-site mean / sd / norm for the tile kernels
+  // corrected correlation (Statistics.h:176-205): mean vector of the mapped alignment and the
+  // per-site mean / sd of the corrected vectors; built on first use after cmb_map
+  DevBuf d_meanvec, corr_mean, corr_sd;
+  bool have_meanvec = false;
+  const double* mean_vector();  // device pointer [B]; computes it (and corr_mean / corr_sd) when stale
   Profile prof;
 
   void require_tree_model() const;

@@ -120,4 +120,14 @@ __host__ __device__ __forceinline__ double philox_u01(uint64_t seed, uint64_t si
   return (double)u * (1.0 / 9007199254740992.0);
 }
 
+// Two uniforms from one Philox block: (c0, c1) and (c2, c3).  The simulator draws the states of
+// the (2 k)-th and (2 k + 1)-th child of a node from ONE block keyed by the parent.
+__host__ __device__ __forceinline__ void philox_u01x2(uint64_t seed, uint64_t site, uint32_t node, uint32_t tag,
+                                                      double& u0, double& u1) {
+  uint32_t c[4] = {(uint32_t)site, (uint32_t)(site >> 32), node, tag};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  u0 = (double)((((uint64_t)c[0] << 32) | c[1]) >> 11) * (1.0 / 9007199254740992.0);
+  u1 = (double)((((uint64_t)c[2] << 32) | c[3]) >> 11) * (1.0 / 9007199254740992.0);
+}
+
 } // namespace cmb

@@ -37,16 +37,24 @@ __device__ __forceinline__ int domain_index(double nmax, int K, double x) {
 __device__ __forceinline__ double mul_(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a, b); }
 
+// mv (nullable): the observed alignment's mean vector, subtracted from both sites before a
+// correlation (CorrectedCorrelationStatistic, Statistics.h:176-205); the norms stay raw.
 __global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* __restrict__ o1,
-                          const double* __restrict__ o2, double* __restrict__ stat, double* __restrict__ nmin) {
+                          const double* __restrict__ o2, const double* __restrict__ mv, double* __restrict__ stat,
+                          double* __restrict__ nmin) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const double nb = (double)B;
   double sx = 0., sy = 0., qx = 0., qy = 0., sxy = 0., s3 = 0., cnt = 0.;
   for (int b = 0; b < B; b++) {
     const double x = o1[(size_t)b * n_pad + j], y = o2[(size_t)b * n_pad + j];
-    sx = add_(sx, x);
-    sy = add_(sy, y);
+    if (mv) {
+      sx = add_(sx, add_(x, -mv[b]));
+      sy = add_(sy, add_(y, -mv[b]));
+    } else {
+      sx = add_(sx, x);
+      sy = add_(sy, y);
+    }
     qx = add_(qx, mul_(x, x));
     qy = add_(qy, mul_(y, y));
     if (stat_id == 2) sxy = add_(sxy, mul_(x, y));
@@ -58,7 +66,10 @@ __global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, const do
     const double mx = sx / nb, my = sy / nb;
     double cxy = 0., cxx = 0., cyy = 0.;
     for (int b = 0; b < B; b++) {
-      const double x = add_(o1[(size_t)b * n_pad + j], -mx), y = add_(o2[(size_t)b * n_pad + j], -my);
+      double x = o1[(size_t)b * n_pad + j], y = o2[(size_t)b * n_pad + j];
+      if (mv) { x = add_(x, -mv[b]); y = add_(y, -mv[b]); }
+      x = add_(x, -mx);
+      y = add_(y, -my);
       cxy = add_(cxy, mul_(x, y));
       cxx = add_(cxx, mul_(x, x));
       cyy = add_(cyy, mul_(y, y));
@@ -106,26 +117,38 @@ __global__ void k2_bin_offsets(int64_t n, const uint32_t* cat_sorted, int K, int
 // ---------------------------------------------------------------------------- per-site prep
 // mean, sd (unbiased, as VectorTools::sd) and norm per site from the [B][n_pad] matrix,
 // summed over branches in id order without fused operations (see k2_paired)
-__global__ void k2_prep(int B, int64_t n, int64_t n_pad, const double* __restrict__ out, double* mean,
-                        double* sd, double* norm) {
+__global__ void k2_prep(int B, int64_t n, int64_t n_pad, const double* __restrict__ out,
+                        const double* __restrict__ mv, double* mean, double* sd, double* norm) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n) return;
   const double nb = (double)B;
   double sx = 0., qx = 0.;
   for (int b = 0; b < B; b++) {
     const double x = out[(size_t)b * n_pad + s];
-    sx = add_(sx, x);
+    sx = add_(sx, mv ? add_(x, -mv[b]) : x);
     qx = add_(qx, mul_(x, x));
   }
   const double m = sx / nb;
   double css = 0.;
   for (int b = 0; b < B; b++) {
-    const double x = add_(out[(size_t)b * n_pad + s], -m);
+    double x = out[(size_t)b * n_pad + s];
+    if (mv) x = add_(x, -mv[b]);
+    x = add_(x, -m);
     css = add_(css, mul_(x, x));
   }
   mean[s] = m;
   sd[s] = sqrt(css / nb * nb / (nb - 1.));
   norm[s] = sqrt(qx);
+}
+
+// mean vector of the mapped alignment: mv[b] = (sum over sites, in site order, of n_b(site)) / S
+// (CoMap.cpp:350-359), one thread per branch
+__global__ void k2_mean_vector(int B, int64_t S, int64_t n_pad, const double* __restrict__ out, double* mv) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  double t = 0.;
+  for (int64_t s = 0; s < S; s++) t = add_(t, out[(size_t)b * n_pad + s]);
+  mv[b] = t / (double)S;
 }
 
 // ---------------------------------------------------------------------------- tiles
@@ -138,6 +161,7 @@ struct TileParams {
   int64_t S, S_pad;
   const double* out;          // [B][S_pad]
   const double *mean, *sd, *norm, *post_rate;
+  const double* mv;           // mean vector subtracted before centring (corrected correlation) or nullptr
   const int32_t* rate_class;
   const int2* tiles;          // (ti, tj) with tj >= ti
   const int32_t* rows;        // owned row list (gathered i-dimension) or nullptr = identity
@@ -199,12 +223,18 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
   for (int k0 = 0; k0 < p.B; k0 += BK) {
     const int k = k0 + lk;
     const double* rowp = p.out + (size_t)k * p.S_pad;
+    const double mvk = (STAT == 0 && p.mv && k < p.B) ? p.mv[k] : 0.;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       double a = 0., b = 0.;
       if (k < p.B) {
-        if (ai[u] >= 0) a = tile_load<STAT>(rowp[ai[u]], am[u]);
-        if (bj[u] >= 0) b = tile_load<STAT>(rowp[bj[u]], bm[u]);
+        if (STAT == 0 && p.mv) {
+          if (ai[u] >= 0) a = tile_load<STAT>(add_(rowp[ai[u]], -mvk), am[u]);
+          if (bj[u] >= 0) b = tile_load<STAT>(add_(rowp[bj[u]], -mvk), bm[u]);
+        } else {
+          if (ai[u] >= 0) a = tile_load<STAT>(rowp[ai[u]], am[u]);
+          if (bj[u] >= 0) b = tile_load<STAT>(rowp[bj[u]], bm[u]);
+        }
       }
       As[lk][lc + u] = a;
       Bs[lk][lc + u] = b;
@@ -310,9 +340,9 @@ __global__ void k2_keep_to_i64(int64_t n, const uint8_t* keep, int64_t* out) {
 
 } // namespace
 
-void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* o1, const double* o2, double* stat,
-                   double* nmin, cudaStream_t st) {
-  k2_paired<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stat_id, B, n, n_pad, o1, o2, stat, nmin);
+void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* o1, const double* o2, const double* mv,
+                   double* stat, double* nmin, cudaStream_t st) {
+  k2_paired<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stat_id, B, n, n_pad, o1, o2, mv, stat, nmin);
   CMB_CUDA(cudaGetLastError());
 }
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
@@ -320,9 +350,13 @@ void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const in
   k2_raw_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, stat, nmin, rc1, rc2, pr1, pr2, raw);
   CMB_CUDA(cudaGetLastError());
 }
-void launch_prep(int B, int64_t n, int64_t n_pad, const double* out, double* mean, double* sd, double* norm,
-                 cudaStream_t st) {
-  k2_prep<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, n, n_pad, out, mean, sd, norm);
+void launch_prep(int B, int64_t n, int64_t n_pad, const double* out, const double* mv, double* mean, double* sd,
+                 double* norm, cudaStream_t st) {
+  k2_prep<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, n, n_pad, out, mv, mean, sd, norm);
+  CMB_CUDA(cudaGetLastError());
+}
+void launch_mean_vector(int B, int64_t S, int64_t n_pad, const double* out, double* mv, cudaStream_t st) {
+  k2_mean_vector<<<(unsigned)((B + 127) / 128), 128, 0, st>>>(B, S, n_pad, out, mv);
   CMB_CUDA(cudaGetLastError());
 }
 
@@ -364,6 +398,7 @@ int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
   TileParams p{};
   p.stat_id = L.stat_id; p.mode = L.dist_mode ? MODE_DIST : MODE_PAIRS; p.B = L.B; p.S = L.S; p.S_pad = L.S_pad;
   p.out = L.out; p.mean = L.mean; p.sd = L.sd; p.norm = L.norm; p.post_rate = L.post_rate; p.rate_class = L.rate_class;
+  p.mv = L.mv;
   p.tiles = L.tiles; p.rows = L.rows; p.n_rows = L.n_rows; p.row_off = L.row_off;
   p.min_rate_class = L.min_rate_class; p.max_rate_class_diff = L.max_rate_class_diff; p.min_rate = L.min_rate;
   p.max_rate_diff = L.max_rate_diff; p.min_stat = L.min_stat; p.any_filter = L.any_filter;

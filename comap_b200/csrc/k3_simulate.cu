@@ -6,6 +6,9 @@
 // (upstream behaviour) or ~ probs, child state by linear inverse-CDF over the cumulative
 // row of P_c(b).  Randomness is counter based -- Philox4x32-10 keyed (seed; site, node,
 // tag) -- so a site's column does not depend on batching, GPU count or launch geometry.
+// The k-th child of node p (children in id order) uses half k % 2 of the block keyed
+// (p, tag 2 + k / 2): one Philox block serves both children of a binary node (the RNG was
+// 3/4 of this kernel's instructions with one block per child).
 // One thread per site walks the precompiled pre-order stream (schedule.cpp); tips are
 // written [row][site] (site contiguous) in the layout K1 reads.
 #include "device_utils.cuh"
@@ -30,6 +33,10 @@ struct SimParams {
 };
 
 __device__ __forceinline__ int draw_state(const double* __restrict__ row, int A, double u) {
+  if (A == 4) { // nucleotides: the cumulative row is two 128-bit shared loads
+    const double2 lo = *reinterpret_cast<const double2*>(row), hi = *reinterpret_cast<const double2*>(row + 2);
+    return u < lo.x ? 0 : u < lo.y ? 1 : u < hi.x ? 2 : 3;
+  }
   int y = A - 1;
   for (int k = A - 1; k >= 0; k--)
     if (u < row[k]) y = k;
@@ -89,8 +96,17 @@ __global__ void __launch_bounds__(NT) k3_simulate(SimParams p) {
       const double* cumB = cumA + tab;
       rp += (32 + 2 * tab * sizeof(double) + 15) & ~size_t(15);
       int sa = st, sb = st;
-      if (h0.w >= 0) sa = draw_state(cumA + ((size_t)c * A + st) * A, A, philox_u01(p.seed, site, (uint32_t)h0.w, 0));
-      if (h1.x >= 0) sb = draw_state(cumB + ((size_t)c * A + st) * A, A, philox_u01(p.seed, site, (uint32_t)h1.x, 0));
+      // h1.y / h1.z = (block index << 1 | half) of child a / b among the children of node h1.w
+      double u0 = 0., u1 = 0.;
+      if (h0.w >= 0) {
+        philox_u01x2(p.seed, site, (uint32_t)h1.w, 2u + ((uint32_t)h1.y >> 1), u0, u1);
+        sa = draw_state(cumA + ((size_t)c * A + st) * A, A, (h1.y & 1) ? u1 : u0);
+      }
+      if (h1.x >= 0) {
+        if (h0.w < 0 || (h1.y >> 1) != (h1.z >> 1))
+          philox_u01x2(p.seed, site, (uint32_t)h1.w, 2u + ((uint32_t)h1.z >> 1), u0, u1);
+        sb = draw_state(cumB + ((size_t)c * A + st) * A, A, (h1.z & 1) ? u1 : u0);
+      }
       if ((flags & kUpTipA) && live) p.tips[(size_t)h0.y * p.n_pad + idx] = (uint8_t)sa;
       if ((flags & kUpTipB) && live) p.tips[(size_t)h0.z * p.n_pad + idx] = (uint8_t)sb;
       if (flags & kUpTakeA) {

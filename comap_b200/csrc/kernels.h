@@ -63,12 +63,14 @@ void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64
                      int32_t* classes, cudaStream_t st);
 
 // ---- K2
-void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* o1, const double* o2, double* stat,
-                   double* nmin, cudaStream_t st);
+// mv: mean vector subtracted before a correlation (corrected correlation) or nullptr
+void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* o1, const double* o2, const double* mv,
+                   double* stat, double* nmin, cudaStream_t st);
+void launch_mean_vector(int B, int64_t S, int64_t n_pad, const double* out, double* mv, cudaStream_t st);
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
                      const double* pr1, const double* pr2, double* raw, cudaStream_t st);
-void launch_prep(int B, int64_t n, int64_t n_pad, const double* out, double* mean, double* sd, double* norm,
-                 cudaStream_t st);
+void launch_prep(int B, int64_t n, int64_t n_pad, const double* out, const double* mv, double* mean, double* sd,
+                 double* norm, cudaStream_t st);
 int bin_and_sort(int64_t n, const double* stat, const double* nmin, int K, double nmax, DevBuf& tmp,
                  double* sorted, int64_t* off_dev, cudaStream_t st);
 
@@ -78,6 +80,7 @@ struct TilesLaunch {
   int64_t S = 0, S_pad = 0;
   const double* out = nullptr;
   const double *mean = nullptr, *sd = nullptr, *norm = nullptr, *post_rate = nullptr;
+  const double* mv = nullptr;   // mean vector (corrected correlation)
   const int32_t* rate_class = nullptr;
   const int2* tiles = nullptr;
   int64_t n_tiles = 0;

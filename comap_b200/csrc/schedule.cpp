@@ -268,6 +268,18 @@ static void up_like_stream(OpStream& s, const Tree& t, const ModelTables& mt, in
       h.ref_b = tb ? t.bin[b].tip_row : -1;
       h.out_a = t.bin[a].orig;
       h.out_b = t.bin[b].orig;
+      // RNG key: the original parent and the child's rank among its children (id order)
+      auto rank_of = [&](int child) {
+        if (t.bin[child].orig < 0) return 0;
+        const int par = t.parent[t.bin[child].orig];
+        int k = 0;
+        for (int u = 0; u < t.bin[child].orig; u++) k += t.parent[u] == par;
+        return k;
+      };
+      const int real = t.bin[a].orig >= 0 ? t.bin[a].orig : t.bin[b].orig;
+      h.ref_a2 = rank_of(a);
+      h.ref_b2 = rank_of(b);
+      h.pad2 = real >= 0 ? t.parent[real] : -1;
     } else {
       h.ref_a = ta ? t.bin[a].tip_row : ca ? t.bin[t.bin[a].left].tip_row : t.bin[a].slot;
       h.ref_b = tb ? t.bin[b].tip_row : cb_ ? t.bin[t.bin[b].left].tip_row : t.bin[b].slot;

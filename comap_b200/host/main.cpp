@@ -204,8 +204,9 @@ int stat_id_of(const Params& P) {
   if (st.name == "Compensation")
     throw Error("Compensation distance must be used with a mapping procedure allowing weights, e.g. "
                 "'nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))'.");
-  if (st.name == "CorrectedCorrelation" || st.name == "MI")
-    throw Error("statistic=" + st.name + " is not available in this build (SURVEY.md s8f)");
+  if (st.name == "CorrectedCorrelation") return CMB_STAT_CORRECTED_CORRELATION; // mean vector: CoMap.cpp:350-359
+  if (st.name == "MI")
+    throw Error("statistic=MI (with nijt=Label) is not available in this build (SURVEY.md s8f)");
   throw Error("Unknown statistic used: " + get_string(P, "statistic", ""));
 }
 

@@ -47,7 +47,8 @@ enum {
   CMB_STAT_COVARIANCE = 1,
   CMB_STAT_COSINUS = 2,
   CMB_STAT_COSUBSTITUTION = 3,
-  CMB_STAT_COMPENSATION = 4
+  CMB_STAT_COMPENSATION = 4,
+  CMB_STAT_CORRECTED_CORRELATION = 5 /* Statistics.h:176-205; mean vector as CoMap.cpp:350-359 */
 };
 /* clustering.distance= : CoMap.cpp:401-427; Distance.h:150-173,316-424 */
 enum { CMB_DIST_CORRELATION = 0, CMB_DIST_COMPENSATION = 1, CMB_DIST_EUCLIDIAN = 2 };

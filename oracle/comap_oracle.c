@@ -501,8 +501,33 @@ static double vt_cov(int n, const double* a, const double* b) {
   return x;
 }
 
+static double* g_mean_vector = NULL;
+static int g_mean_vector_len = 0;
+void orc_set_mean_vector(int B, const double* mv) {
+  free(g_mean_vector);
+  g_mean_vector = malloc(sizeof(double) * (size_t)B);
+  memcpy(g_mean_vector, mv, sizeof(double) * (size_t)B);
+  g_mean_vector_len = B;
+}
+/* CoMap.cpp:350-359 */
+void orc_mean_vector(int64_t S, int B, const double* n, double* mv) {
+  for (int b = 0; b < B; b++) mv[b] = 0.;
+  for (int64_t i = 0; i < S; i++)
+    for (int b = 0; b < B; b++) mv[b] += n[i * B + b];
+  for (int b = 0; b < B; b++) mv[b] /= (double)S;
+}
+
 double orc_stat(int stat_id, int B, const double* v1, const double* v2) {
   switch (stat_id) {
+    case ORC_STAT_CORRECTED_CORRELATION: { /* Statistics.h:188-194: cor(v1 - mean vector, v2 - mean vector) */
+      if (g_mean_vector_len != B) return NAN;
+      double* a = malloc(sizeof(double) * (size_t)B * 2);
+      double* b = a + B;
+      for (int i = 0; i < B; i++) { a[i] = v1[i] - g_mean_vector[i]; b[i] = v2[i] - g_mean_vector[i]; }
+      double r = vt_cov(B, a, b) / (sqrt(vt_cov(B, a, a)) * sqrt(vt_cov(B, b, b)));
+      free(a);
+      return r;
+    }
     case ORC_STAT_CORRELATION: /* Statistics.h:164-174 -> cov / (sd * sd) */
       return vt_cov(B, v1, v2) / (sqrt(vt_cov(B, v1, v1)) * sqrt(vt_cov(B, v2, v2)));
     case ORC_STAT_COVARIANCE: /* Statistics.h:206-216 */
@@ -646,6 +671,14 @@ static double philox_u01(uint64_t seed, uint64_t site, uint32_t node, uint32_t t
   return (double)u * (1.0 / 9007199254740992.0);
 }
 
+/* two uniforms from one block: (c0, c1) and (c2, c3) */
+static void philox_u01x2(uint64_t seed, uint64_t site, uint32_t node, uint32_t tag, double* u0, double* u1) {
+  uint32_t c[4] = {(uint32_t)site, (uint32_t)(site >> 32), node, tag};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  *u0 = (double)((((uint64_t)c[0] << 32) | c[1]) >> 11) * (1.0 / 9007199254740992.0);
+  *u1 = (double)((((uint64_t)c[2] << 32) | c[3]) >> 11) * (1.0 / 9007199254740992.0);
+}
+
 /* [Bio++] NonHomogeneousSequenceSimulator::simulate(n) in discrete-rate mode
  * (CoMap.cpp:209-219; AnalysisTools.cpp:591,614; ClusterTools.cpp:224): per site the root
  * state is drawn from pi (first i with r <= cumulative), the rate class uniformly over
@@ -666,6 +699,14 @@ int orc_simulate(int n_nodes, const int32_t* parent, const double* brlen, int A,
       for (int y = 0; y < A; y++) { s += tb.P[m * AA + x * A + y]; cum[m * AA + x * A + y] = s; }
     }
   uint8_t* st = malloc(tr.n);
+  /* RNG key of node v: its parent and its rank k among the parent's children (id order); the
+   * state is drawn with half k % 2 of the Philox block (parent, tag 2 + k / 2) */
+  int* rank = calloc(tr.n, sizeof(int));
+  {
+    int* seen = calloc(tr.n, sizeof(int));
+    for (int v = 0; v < tr.n - 1; v++) rank[v] = seen[tr.parent[v]]++;
+    free(seen);
+  }
   for (int64_t j = 0; j < n; j++) {
     uint64_t site = (uint64_t)(first_site + j);
     double r = philox_u01(seed, site, (uint32_t)tr.root, 0);
@@ -685,7 +726,9 @@ int orc_simulate(int n_nodes, const int32_t* parent, const double* brlen, int A,
     st[tr.root] = (uint8_t)x0;
     for (int v = tr.n - 2; v >= 0; v--) {
       int x = st[tr.parent[v]];
-      double u = philox_u01(seed, site, (uint32_t)v, 0);
+      double u0, u1;
+      philox_u01x2(seed, site, (uint32_t)tr.parent[v], 2u + ((uint32_t)rank[v] >> 1), &u0, &u1);
+      double u = (rank[v] & 1) ? u1 : u0;
       const double* row = cum + ((size_t)v * C + c) * AA + (size_t)x * A;
       int y = A - 1;
       for (int k = 0; k < A; k++) if (u < row[k]) { y = k; break; }
@@ -693,7 +736,7 @@ int orc_simulate(int n_nodes, const int32_t* parent, const double* brlen, int A,
       if (tr.leaf_row[v] >= 0) states[(size_t)tr.leaf_row[v] * n + j] = (uint8_t)y;
     }
   }
-  free(st); free(cum); tables_free(&tb); tree_free(&tr);
+  free(rank); free(st); free(cum); tables_free(&tb); tree_free(&tr);
   return 0;
 }
 

@@ -42,7 +42,8 @@ enum {
   ORC_STAT_COVARIANCE = 1,
   ORC_STAT_COSINUS = 2,
   ORC_STAT_COSUBSTITUTION = 3,
-  ORC_STAT_COMPENSATION = 4
+  ORC_STAT_COMPENSATION = 4,
+  ORC_STAT_CORRECTED_CORRELATION = 5 /* needs orc_set_mean_vector */
 };
 enum { ORC_DIST_CORRELATION = 0, ORC_DIST_COMPENSATION = 1, ORC_DIST_EUCLIDIAN = 2 };
 enum { ORC_LINK_COMPLETE = 0, ORC_LINK_SINGLE = 1, ORC_LINK_AVERAGE = 2 };
@@ -67,6 +68,11 @@ int orc_map(int n_nodes, const int32_t* parent, const double* brlen,
 
 /* One pair statistic on two branch vectors of length B. */
 double orc_stat(int stat_id, int B, const double* v1, const double* v2);
+/* CorrectedCorrelationStatistic (Statistics.h:176-205): the mean vector the statistic subtracts from
+ * both sites, and how CoMap builds it from the mapping (CoMap.cpp:350-359: running sum over
+ * sites in site order, divided by the number of sites). */
+void orc_set_mean_vector(int B, const double* mv);
+void orc_mean_vector(int64_t S, int B, const double* n, double* mv);
 /* Group statistic (min over pairs; closed form for Compensation). idx = site rows. */
 double orc_stat_group(int stat_id, int B, const double* n /* [S][B] */, int n_members,
                       const int32_t* members);

@@ -10,7 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(ROOT, "oracle", "liboracle.so")
 
-STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "compensation": 4}
+STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "compensation": 4,
+        "corrected_correlation": 5}
 DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
 LINK = {"complete": 0, "single": 1, "average": 2}
 COUNT = {"uniformization": 0, "decomposition": 1}
@@ -90,6 +91,16 @@ def map_sites(parent, brlen, Q, pi, rates, probs, codes, code_mask, method="unif
                        len(code_mask), _p(code_mask, C.c_uint32), _d(n), _d(norm), _d(pr),
                        _p(rc, C.c_int32), _d(ll)))
     return dict(n=n, norm=norm, post_rate=pr, rate_class=rc, loglik=ll)
+
+
+def mean_vector(n):
+    """Mean vector of a mapping as CoMap builds it (CoMap.cpp:350-359); also installs it for the
+    corrected correlation."""
+    n = _f64(n); S, B = n.shape
+    mv = np.empty(B)
+    lib().orc_mean_vector(C.c_int64(S), B, _d(n), _d(mv))
+    lib().orc_set_mean_vector(B, _d(mv))
+    return mv
 
 
 def stat(name, v1, v2):

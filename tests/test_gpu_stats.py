@@ -57,11 +57,15 @@ def test_simulate_protein_bit_exact(ctx):
     assert np.array_equal(a, b) and np.array_equal(ca, cb)
 
 
-@pytest.mark.parametrize("stat", ["correlation", "covariance", "cosinus", "cosubstitution", "compensation"])
+ALL_STATS = ["correlation", "covariance", "cosinus", "cosubstitution", "compensation", "corrected_correlation"]
+
+
+@pytest.mark.parametrize("stat", ALL_STATS)
 def test_pairs_all_statistics_vs_oracle(ctx, stat):
     c = _case()
     r = _setup(ctx, c)
     q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    O.mean_vector(q["n"])  # the corrected correlation's mean vector (CoMap.cpp:350-359)
     g, k = ctx.pairs(stat, use_null=False)
     o = O.pairs(stat, q["n"], q["norm"], q["post_rate"], q["rate_class"])
     assert k == len(o["i"]) == 150 * 149 // 2
@@ -121,7 +125,7 @@ def test_null_from_alignments_vs_oracle(ctx):
     assert _close(g["sorted"][fin], o["sorted"][fin])
 
 
-@pytest.mark.parametrize("stat", ["correlation", "covariance", "cosinus", "cosubstitution", "compensation"])
+@pytest.mark.parametrize("stat", ALL_STATS)
 def test_statistics_and_pvalues_bit_exact_given_vectors(ctx, stat):
     """north_star: null counts and p-values bit-exact.  p = (nsim - #{sim < stat} + 1)/(nsim + 1)
     with massive ties among low-rate sites (r = 1 between constant sites), so one ulp moves
@@ -134,6 +138,7 @@ def test_statistics_and_pvalues_bit_exact_given_vectors(ctx, stat):
     s1 = np.stack([ctx.simulate(99, (2 * i) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
     s2 = np.stack([ctx.simulate(99, (2 * i + 1) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
     nmax = 0.6 * float(r["norm"].max())  # some pairs fall outside [0, nmax) -> "NA\t0" rows
+    O.mean_vector(r["n"])  # observed mean vector, used for observed AND simulated pairs
     raw = ctx.null_intra_from_alignments(stat, s1, s2, K=K, nmax=nmax)
     g = ctx.null_get()
     gp, k = ctx.pairs(stat, use_null=True)

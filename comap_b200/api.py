@@ -23,7 +23,7 @@ SYMBOLS = [
     "cmb_simulate", "cmb_null_intra", "cmb_null_intra_from_alignments", "cmb_null_samples_dev",
     "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
-    "cmb_launch_count",
+    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter",
 ]
 
 
@@ -197,6 +197,33 @@ class Context:
         k = nr.value
         out = dict(i=oi, j=oj, stat=st, rcmin=rcm, prmin=prm, nmin=nm, pvalue=pv, nsim=ns)
         return {name: (a[:k] if a is not None else None) for name, a in out.items()}, k
+
+    # ------------------------------------------------------------------ two data sets
+    def pairs_inter(self, other, stat, filters=None, min_rate_class2=0, min_rate2=0.0, independent=False,
+                    nmin_by_row=True):
+        """Statistic of every site of this data set with every site of `other` (CoETools.cpp:732-840);
+        independent: site i with site i only.  nmin_by_row reproduces upstream's Nmin (norms2[i])."""
+        cap = self.S if independent else self.S * other.S
+        f = Filters(0, -1, 0.0, -1.0, 0.0)
+        if filters:
+            for k, v in filters.items():
+                setattr(f, k, v)
+        oi, oj = np.empty(cap, np.int32), np.empty(cap, np.int32)
+        st, rcm, prm, nm = np.empty(cap), np.empty(cap, np.int32), np.empty(cap), np.empty(cap)
+        nr = C.c_int64()
+        self._chk(self.lib.cmb_pairs_inter(self.h, other.h, STAT[stat], C.byref(f), int(min_rate_class2),
+                                           C.c_double(min_rate2), int(independent), int(nmin_by_row), C.c_int64(cap),
+                                           _i32(oi), _i32(oj), _d(st), _i32(rcm), _d(prm), _d(nm), C.byref(nr)))
+        k = nr.value
+        return dict(i=oi[:k], j=oj[:k], stat=st[:k], rcmin=rcm[:k], prmin=prm[:k], nmin=nm[:k]), k
+
+    def null_inter(self, other, stat, seed, rep_cpu, rep_ram, weighted_classes=False):
+        """rep_cpu x rep_ram paired null statistics of the two data sets' simulators
+        (AnalysisTools.cpp:662-735); rows Stat, RCmin, PRmin, Nmin."""
+        raw = np.empty((rep_cpu * rep_ram, 4))
+        self._chk(self.lib.cmb_null_inter(self.h, other.h, STAT[stat], C.c_uint64(seed), rep_cpu, rep_ram,
+                                          int(weighted_classes), _d(raw)))
+        return raw
 
     COLS = ("i", "j", "stat", "rcmin", "prmin", "nmin", "pvalue", "nsim")
     COL_DTYPE = (np.int32, np.int32, np.float64, np.int32, np.float64, np.float64, np.float64, np.int64)

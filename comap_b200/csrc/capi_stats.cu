@@ -125,7 +125,7 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
       c.run_map(b[k], true, sim1 == nullptr);
     }
     c.prof_begin("null_pairs");
-    launch_paired(corrected ? 0 : stat_id, B, n, n_pad, b[0].out, b[1].out, mv, ns.stat.as<double>() + off, ns.nmin.as<double>() + off,
+    launch_paired(corrected ? 0 : stat_id, B, n, n_pad, n_pad, b[0].out, b[1].out, mv, mv, ns.stat.as<double>() + off, ns.nmin.as<double>() + off,
                   c.stream);
     c.prof_end(1);
     if (raw) {

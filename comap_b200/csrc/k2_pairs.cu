@@ -39,18 +39,18 @@ __device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a,
 
 // mv (nullable): the observed alignment's mean vector, subtracted from both sites before a
 // correlation (CorrectedCorrelationStatistic, Statistics.h:176-205); the norms stay raw.
-__global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* __restrict__ o1,
-                          const double* __restrict__ o2, const double* __restrict__ mv, double* __restrict__ stat,
-                          double* __restrict__ nmin) {
+__global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* __restrict__ o1,
+                          const double* __restrict__ o2, const double* __restrict__ mv, const double* __restrict__ mv2,
+                          double* __restrict__ stat, double* __restrict__ nmin) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
   const double nb = (double)B;
   double sx = 0., sy = 0., qx = 0., qy = 0., sxy = 0., s3 = 0., cnt = 0.;
   for (int b = 0; b < B; b++) {
-    const double x = o1[(size_t)b * n_pad + j], y = o2[(size_t)b * n_pad + j];
+    const double x = o1[(size_t)b * n_pad + j], y = o2[(size_t)b * n_pad2 + j];
     if (mv) {
       sx = add_(sx, add_(x, -mv[b]));
-      sy = add_(sy, add_(y, -mv[b]));
+      sy = add_(sy, add_(y, -mv2[b]));
     } else {
       sx = add_(sx, x);
       sy = add_(sy, y);
@@ -66,8 +66,8 @@ __global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, const do
     const double mx = sx / nb, my = sy / nb;
     double cxy = 0., cxx = 0., cyy = 0.;
     for (int b = 0; b < B; b++) {
-      double x = o1[(size_t)b * n_pad + j], y = o2[(size_t)b * n_pad + j];
-      if (mv) { x = add_(x, -mv[b]); y = add_(y, -mv[b]); }
+      double x = o1[(size_t)b * n_pad + j], y = o2[(size_t)b * n_pad2 + j];
+      if (mv) { x = add_(x, -mv[b]); y = add_(y, -mv2[b]); }
       x = add_(x, -mx);
       y = add_(y, -my);
       cxy = add_(cxy, mul_(x, y));
@@ -154,7 +154,7 @@ __global__ void k2_mean_vector(int B, int64_t S, int64_t n_pad, const double* __
 // ---------------------------------------------------------------------------- tiles
 constexpr int TS = 64;  // tile edge (sites)
 constexpr int BK = 16;  // branches per smem stage
-enum { MODE_PAIRS = 0, MODE_DIST = 1 };
+enum { MODE_PAIRS = 0, MODE_DIST = 1, MODE_RECT = 2 };
 
 struct TileParams {
   int stat_id, mode, B;
@@ -163,6 +163,14 @@ struct TileParams {
   const double *mean, *sd, *norm, *post_rate;
   const double* mv;           // mean vector subtracted before centring (corrected correlation) or nullptr
   const int32_t* rate_class;
+  // MODE_RECT (two data sets, CoETools.cpp:732-840): the column operand, its per-site arrays
+  // and the second data set's own rate filters; in the other modes these alias the first
+  int64_t S2, S2_pad;
+  const double *out2, *mean2, *sd2, *norm2, *post_rate2, *mv2;
+  const int32_t* rate_class2;
+  int min_rate_class2;
+  double min_rate2;
+  int nmin_by_row;            // upstream quirk: min(Nmin) pairs norms1[i] with norms2[i] (CoETools.cpp:803)
   const int2* tiles;          // (ti, tj) with tj >= ti
   const int32_t* rows;        // owned row list (gathered i-dimension) or nullptr = identity
   int64_t n_rows;             // number of owned rows
@@ -210,9 +218,9 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
     int64_t ri = i0 + lc + u;
     ai[u] = ri < p.n_rows ? (p.rows ? p.rows[ri] : ri) : -1;
     int64_t cj = j0 + lc + u;
-    bj[u] = cj < p.S ? cj : -1;
+    bj[u] = cj < p.S2 ? cj : -1;
     am[u] = ai[u] >= 0 ? p.mean[ai[u]] : 0.;
-    bm[u] = bj[u] >= 0 ? p.mean[bj[u]] : 0.;
+    bm[u] = bj[u] >= 0 ? p.mean2[bj[u]] : 0.;
   }
   double acc[4][4];
 #pragma unroll
@@ -223,17 +231,19 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
   for (int k0 = 0; k0 < p.B; k0 += BK) {
     const int k = k0 + lk;
     const double* rowp = p.out + (size_t)k * p.S_pad;
+    const double* colp = p.out2 + (size_t)k * p.S2_pad;
     const double mvk = (STAT == 0 && p.mv && k < p.B) ? p.mv[k] : 0.;
+    const double mvk2 = (STAT == 0 && p.mv && k < p.B) ? p.mv2[k] : 0.;
 #pragma unroll
     for (int u = 0; u < 4; u++) {
       double a = 0., b = 0.;
       if (k < p.B) {
         if (STAT == 0 && p.mv) {
           if (ai[u] >= 0) a = tile_load<STAT>(add_(rowp[ai[u]], -mvk), am[u]);
-          if (bj[u] >= 0) b = tile_load<STAT>(add_(rowp[bj[u]], -mvk), bm[u]);
+          if (bj[u] >= 0) b = tile_load<STAT>(add_(colp[bj[u]], -mvk2), bm[u]);
         } else {
           if (ai[u] >= 0) a = tile_load<STAT>(rowp[ai[u]], am[u]);
-          if (bj[u] >= 0) b = tile_load<STAT>(rowp[bj[u]], bm[u]);
+          if (bj[u] >= 0) b = tile_load<STAT>(colp[bj[u]], bm[u]);
         }
       }
       As[lk][lc + u] = a;
@@ -269,13 +279,13 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
 #pragma unroll
     for (int v = 0; v < 4; v++) {
       const int64_t j = j0 + tx * 4 + v;
-      if (j >= p.S || j <= i) continue;
+      if (j >= p.S2 || (p.mode != MODE_RECT && j <= i)) continue;
       double stat;
-      if (STAT == 0) stat = (acc[u][v] / nb * nb / (nb - 1.)) / mul_(p.sd[i], p.sd[j]);
+      if (STAT == 0) stat = (acc[u][v] / nb * nb / (nb - 1.)) / mul_(p.sd[i], p.sd2[j]);
       else if (STAT == 1) stat = acc[u][v] / nb * nb / (nb - 1.);
-      else if (STAT == 2) stat = acc[u][v] / mul_(p.norm[i], p.norm[j]);
+      else if (STAT == 2) stat = acc[u][v] / mul_(p.norm[i], p.norm2[j]);
       else if (STAT == 3) stat = acc[u][v];
-      else if (STAT == 4) stat = add_(1., -(sqrt(acc[u][v]) / add_(p.norm[i], p.norm[j])));
+      else if (STAT == 4) stat = add_(1., -(sqrt(acc[u][v]) / add_(p.norm[i], p.norm2[j])));
       else stat = sqrt(acc[u][v]);
       if (p.mode == MODE_DIST) {
         double d = p.dist_is_stat ? stat : p.dist_comp - stat;
@@ -283,12 +293,12 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
         p.mat[(size_t)j * p.S + i] = d;
         continue;
       }
-      const int64_t idx = p.row_off[ri] + (j - i - 1);
-      const int ci = p.rate_class[i], cj = p.rate_class[j];
-      const double pi_ = p.post_rate[i], pj = p.post_rate[j];
-      const double ni = p.norm[i], nj = p.norm[j];
+      const int64_t idx = p.mode == MODE_RECT ? i * p.S2 + j : p.row_off[ri] + (j - i - 1);
+      const int ci = p.rate_class[i], cj = p.rate_class2[j];
+      const double pi_ = p.post_rate[i], pj = p.post_rate2[j];
+      const double ni = p.norm[i], nj = p.norm2[p.nmin_by_row && i < p.S2 ? i : j];
       if (p.any_filter) {
-        bool keep = ci >= p.min_rate_class && cj >= p.min_rate_class && !(pi_ < p.min_rate) && !(pj < p.min_rate);
+        bool keep = ci >= p.min_rate_class && cj >= p.min_rate_class2 && !(pi_ < p.min_rate) && !(pj < p.min_rate2);
         if (p.max_rate_class_diff >= 0 && abs(cj - ci) > p.max_rate_class_diff) keep = false;
         if (p.max_rate_diff >= 0. && fabs(pj - pi_) > p.max_rate_diff) keep = false;
         if (fabs(stat) < p.min_stat) keep = false;
@@ -328,6 +338,27 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
   }
 }
 
+// independant comparisons (CoETools.cpp:795-796): row i pairs site i of data set 1 with site i of
+// data set 2; statistic and Nmin come from k2_paired, this fills the other columns and the filters
+__global__ void k2_diag_rows(TileParams p) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.S) return;
+  const int ci = p.rate_class[i], cj = p.rate_class2[i];
+  const double pi_ = p.post_rate[i], pj = p.post_rate2[i];
+  const double stat = p.o_stat[i];
+  if (p.any_filter) {
+    bool keep = ci >= p.min_rate_class && cj >= p.min_rate_class2 && !(pi_ < p.min_rate) && !(pj < p.min_rate2);
+    if (p.max_rate_class_diff >= 0 && abs(cj - ci) > p.max_rate_class_diff) keep = false;
+    if (p.max_rate_diff >= 0. && fabs(pj - pi_) > p.max_rate_diff) keep = false;
+    if (fabs(stat) < p.min_stat) keep = false;
+    p.o_keep[i] = keep ? 1 : 0;
+  }
+  p.o_i[i] = (int32_t)i;
+  p.o_j[i] = (int32_t)i;
+  p.o_rcmin[i] = ci < cj ? ci : cj;
+  p.o_prmin[i] = pi_ < pj ? pi_ : pj;
+}
+
 template <class T>
 __global__ void k2_compact(int64_t n, const uint8_t* keep, const int64_t* pos, const T* src, T* dst) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -340,9 +371,9 @@ __global__ void k2_keep_to_i64(int64_t n, const uint8_t* keep, int64_t* out) {
 
 } // namespace
 
-void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* o1, const double* o2, const double* mv,
-                   double* stat, double* nmin, cudaStream_t st) {
-  k2_paired<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stat_id, B, n, n_pad, o1, o2, mv, stat, nmin);
+void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
+                   const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st) {
+  k2_paired<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stat_id, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin);
   CMB_CUDA(cudaGetLastError());
 }
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
@@ -399,6 +430,14 @@ int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
   p.stat_id = L.stat_id; p.mode = L.dist_mode ? MODE_DIST : MODE_PAIRS; p.B = L.B; p.S = L.S; p.S_pad = L.S_pad;
   p.out = L.out; p.mean = L.mean; p.sd = L.sd; p.norm = L.norm; p.post_rate = L.post_rate; p.rate_class = L.rate_class;
   p.mv = L.mv;
+  const bool rect = L.out2 != nullptr;
+  if (rect) p.mode = MODE_RECT;
+  p.S2 = rect ? L.S2 : L.S; p.S2_pad = rect ? L.S2_pad : L.S_pad; p.out2 = rect ? L.out2 : L.out;
+  p.mean2 = rect ? L.mean2 : L.mean; p.sd2 = rect ? L.sd2 : L.sd; p.norm2 = rect ? L.norm2 : L.norm;
+  p.post_rate2 = rect ? L.post_rate2 : L.post_rate; p.rate_class2 = rect ? L.rate_class2 : L.rate_class;
+  p.mv2 = rect ? L.mv2 : L.mv;
+  p.min_rate_class2 = rect ? L.min_rate_class2 : L.min_rate_class; p.min_rate2 = rect ? L.min_rate2 : L.min_rate;
+  p.nmin_by_row = rect ? L.nmin_by_row : 0;
   p.tiles = L.tiles; p.rows = L.rows; p.n_rows = L.n_rows; p.row_off = L.row_off;
   p.min_rate_class = L.min_rate_class; p.max_rate_class_diff = L.max_rate_class_diff; p.min_rate = L.min_rate;
   p.max_rate_diff = L.max_rate_diff; p.min_stat = L.min_stat; p.any_filter = L.any_filter;
@@ -419,6 +458,22 @@ int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
   }
   CMB_CUDA(cudaGetLastError());
   return 1;
+}
+
+int launch_inter_diagonal(const TilesLaunch& L, cudaStream_t st) {
+  if (!L.out2 || L.S != L.S2) fail("internal: diagonal comparison needs two data sets of the same length");
+  if (L.S == 0) return 0;
+  TileParams p{};
+  p.S = L.S; p.rate_class = L.rate_class; p.rate_class2 = L.rate_class2; p.post_rate = L.post_rate; p.post_rate2 = L.post_rate2;
+  p.min_rate_class = L.min_rate_class; p.min_rate_class2 = L.min_rate_class2; p.min_rate = L.min_rate; p.min_rate2 = L.min_rate2;
+  p.max_rate_class_diff = L.max_rate_class_diff; p.max_rate_diff = L.max_rate_diff; p.min_stat = L.min_stat;
+  p.any_filter = L.any_filter;
+  p.o_i = L.o_i; p.o_j = L.o_j; p.o_stat = L.o_stat; p.o_rcmin = L.o_rcmin; p.o_prmin = L.o_prmin; p.o_keep = L.o_keep;
+  k2_paired<<<(unsigned)((L.S + 127) / 128), 128, 0, st>>>(L.stat_id, L.B, L.S, L.S_pad, L.S2_pad, L.out, L.out2, L.mv, L.mv2,
+                                                        L.o_stat, L.o_nmin);
+  k2_diag_rows<<<(unsigned)((L.S + 127) / 128), 128, 0, st>>>(p);
+  CMB_CUDA(cudaGetLastError());
+  return 2;
 }
 
 // exclusive scan of the keep flags -> positions; returns number kept (synchronises)

@@ -64,8 +64,8 @@ void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64
 
 // ---- K2
 // mv: mean vector subtracted before a correlation (corrected correlation) or nullptr
-void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, const double* o1, const double* o2, const double* mv,
-                   double* stat, double* nmin, cudaStream_t st);
+void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
+                   const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st);
 void launch_mean_vector(int B, int64_t S, int64_t n_pad, const double* out, double* mv, cudaStream_t st);
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
                      const double* pr1, const double* pr2, double* raw, cudaStream_t st);
@@ -81,6 +81,12 @@ struct TilesLaunch {
   const double* out = nullptr;
   const double *mean = nullptr, *sd = nullptr, *norm = nullptr, *post_rate = nullptr;
   const double* mv = nullptr;   // mean vector (corrected correlation)
+  // two data sets (rectangle S x S2): column operand and its per-site arrays; nullptr = one data set
+  const double *out2 = nullptr, *mean2 = nullptr, *sd2 = nullptr, *norm2 = nullptr, *post_rate2 = nullptr, *mv2 = nullptr;
+  const int32_t* rate_class2 = nullptr;
+  int64_t S2 = 0, S2_pad = 0;
+  int min_rate_class2 = 0, nmin_by_row = 0;
+  double min_rate2 = 0.;
   const int32_t* rate_class = nullptr;
   const int2* tiles = nullptr;
   int64_t n_tiles = 0;
@@ -103,6 +109,7 @@ struct TilesLaunch {
   int dist_is_stat = 0;
 };
 int launch_tiles(const TilesLaunch& L, cudaStream_t st);
+int launch_inter_diagonal(const TilesLaunch& L, cudaStream_t st); // site i of data set 1 with site i of data set 2
 int64_t compact_positions(int64_t n, const uint8_t* keep, DevBuf& tmp, int64_t** pos_out, cudaStream_t st);
 template <class T>
 void compact_column(int64_t n, const uint8_t* keep, const int64_t* pos, const T* src, T* dst, cudaStream_t st);

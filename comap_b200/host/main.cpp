@@ -89,16 +89,42 @@ std::string data_dir_of(const char* argv0) {
   return dir + "/../data";
 }
 
-void prepare(Inputs& in, const char* argv0) {
-  const Params& P = in.app.params;
-  display_message("\n\n-*- Retrieve data and model -*-\n");
-  // tree (PhylogeneticsApplicationTools::getTree, CoMap.cpp:125-129)
+// Params of the second data set: the keys CoMap reads with the suffix "2" (suffix optional --
+// CoETools::readData, CoETools.cpp:91-93; getVectors :374,390; writeInfos :503; the rate
+// thresholds :422,435) take the value of KEY2 when it is set.  model / rate_distribution / nijt
+// are read without suffix upstream, so both data sets share them.
+Params second_data_set_params(const Params& P) {
+  Params Q = P;
+  for (const auto& kv : P) {
+    const std::string& k = kv.first;
+    if (k.size() < 2 || k.back() != '2') continue;
+    const std::string base = k.substr(0, k.size() - 1);
+    if (base == "alphabet" || base.rfind("input.sequence.", 0) == 0 || base.rfind("input.tree.", 0) == 0 ||
+        base == "output.vectors.file" || base == "input.vectors.file" || base == "output.infos" ||
+        base == "statistic.min_rate_class" || base == "statistic.min_rate")
+      Q[base] = kv.second;
+  }
+  if (P.find("input.tree.file2") == P.end()) Q["input.tree.file"] = "none";            // -> copy of tree 1
+  for (const char* k : {"output.vectors.file", "input.vectors.file", "output.infos"})  // never shared
+    if (P.find(std::string(k) + "2") == P.end()) Q[k] = "none";
+  return Q;
+}
+
+void prepare(Inputs& in, const char* argv0, const Params* override_params = nullptr, const Tree* first_tree = nullptr) {
+  const Params& P = override_params ? *override_params : in.app.params;
+  display_message(first_tree ? "\nLoading second dataset...\n" : "\n\n-*- Retrieve data and model -*-\n");
+  // tree (PhylogeneticsApplicationTools::getTree, CoMap.cpp:125-129; second data set: CoMap.cpp:238-252)
   std::string tree_path = get_path(P, "input.tree.file", "none");
-  if (tree_path == "none") throw Error("input.tree.file is not set");
-  std::string tfmt = get_string(P, "input.tree.format", "Newick");
-  if (lower(parse_procedure(tfmt).name) != "newick") throw Error("input.tree.format '" + tfmt + "' is not supported (Newick)");
-  display_result("Input tree file ", tree_path);
-  in.tree = parse_newick(read_file(tree_path));
+  if (tree_path == "none" && first_tree) in.tree = *first_tree; // "Copy tree."
+  else {
+    if (tree_path == "none") throw Error("input.tree.file is not set");
+    std::string tfmt = get_string(P, "input.tree.format", "Newick");
+    if (lower(parse_procedure(tfmt).name) != "newick") throw Error("input.tree.format '" + tfmt + "' is not supported (Newick)");
+    display_result("Input tree file ", tree_path);
+    in.tree = parse_newick(read_file(tree_path));
+    if (first_tree && in.tree.parent != first_tree->parent)
+      throw Error("The second tree must have the same topology as the first tree.");
+  }
   display_result("Number of leaves", in.tree.leaves.size());
   display_result("Number of sons at root", in.tree.n_root_children);
   if (in.tree.was_unrooted) display_message("WARNING!!! Tree has been unrooted.");
@@ -237,6 +263,56 @@ std::string dendrogram_newick(const std::vector<int32_t>& left, const std::vecto
   return txt[2 * S - 2] + ";";
 }
 
+struct Mapped {           // a data set on the device and its per-site results
+  cmb_ctx* ctx = nullptr;
+  std::vector<double> norm, pr, ll;
+  std::vector<int32_t> rc;
+};
+
+// cmb_set_* + CoETools::getVectors (CoETools.cpp:364-413) + norms (CoMap.cpp:158-163) + writeInfos
+// (CoETools.cpp:496-531) for one data set; P holds that data set's view of the options
+Mapped map_data_set(const Inputs& in, const Params& P, const std::string& suffix) {
+  Mapped m;
+  const int64_t S = (int64_t)in.cols.size();
+  const int B = (int)in.tree.parent.size() - 1;
+  chk(cmb_ctx_create(-1, nullptr, &m.ctx));
+  chk(cmb_set_tree(m.ctx, (int32_t)in.tree.parent.size(), in.tree.parent.data(), in.tree.brlen.data()));
+  chk(cmb_set_model(m.ctx, in.model.A, in.model.Q.data(), in.model.pi.data(), (int32_t)in.rdist.rates.size(),
+                    in.rdist.rates.data(), in.rdist.probs.data(), in.count_method, nullptr));
+  chk(cmb_set_alignment(m.ctx, S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
+  if (get_path(P, "input.vectors.file", "none") != "none")
+    throw Error("input.vectors.file (restart from a mapping file) is not available in this build");
+  std::string vec_path = get_path(P, "output.vectors.file", "none");
+  display_result("Output mapping to file" + suffix, vec_path);
+  std::vector<double> n_out;
+  m.norm.resize(S); m.pr.resize(S); m.ll.resize(S); m.rc.resize(S);
+  if (vec_path != "none") n_out.resize((size_t)S * B);
+  chk(cmb_map(m.ctx, n_out.empty() ? nullptr : n_out.data(), m.norm.data(), m.pr.data(), m.rc.data(), m.ll.data()));
+  if (vec_path != "none") {
+    // LegacySubstitutionMappingTools::writeToStream (CoETools.cpp:408-412)
+    std::ofstream out(vec_path);
+    out << "Branches\tMean";
+    for (int c : in.cols) out << "\tSite" << c + 1;
+    out << "\n";
+    for (int b = 0; b < B; b++) {
+      out << b << "\t" << in.tree.brlen[b];
+      for (int64_t s = 0; s < S; s++) out << "\t" << n_out[(size_t)s * B + b];
+      out << "\n";
+    }
+  }
+  std::string infos = get_path(P, "output.infos", "none");
+  if (infos != "none") {
+    display_result("Alignment information logfile", infos);
+    std::ofstream out(infos);
+    out << "Group\tIsComplete\tIsConstant\tRC\tPR\tN\tlogLn" << std::endl;
+    for (int64_t i = 0; i < S; i++)
+      out << "[" << in.cols[i] + 1 << "]\t" << (site_is_complete(in.aln, in.alpha, in.cols[i]) ? 1 : 0) << "\t"
+          << (site_is_constant(in.aln, in.alpha, in.cols[i]) ? 1 : 0) << "\t" << m.rc[i] << "\t" << m.pr[i] << "\t"
+          << m.norm[i] << "\t" << m.ll[i] << std::endl;
+  }
+  return m;
+}
+
 } // namespace
 
 int main(int argc, char** argv) {
@@ -268,50 +344,16 @@ int main(int argc, char** argv) {
     uint64_t seed = in.app.seed;
     if (!in.app.seed_given) seed = ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}();
 
-    cmb_ctx* ctx = nullptr;
-    chk(cmb_ctx_create(-1, nullptr, &ctx));
-    chk(cmb_set_tree(ctx, (int32_t)in.tree.parent.size(), in.tree.parent.data(), in.tree.brlen.data()));
-    chk(cmb_set_model(ctx, in.model.A, in.model.Q.data(), in.model.pi.data(), (int32_t)in.rdist.rates.size(),
-                      in.rdist.rates.data(), in.rdist.probs.data(), in.count_method, nullptr));
-    chk(cmb_set_alignment(ctx, S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
     (void)T;
+    (void)B;
     const bool weighted_classes = get_bool(P, "simulations.weighted_classes", false);
     display_result("Rate distribution for simulations", get_bool(P, "simulations.continuous", false) ? "continuous" : "discrete");
     if (get_bool(P, "simulations.continuous", false))
       throw Error("simulations.continuous=yes is not available in this build (discrete rate classes only)");
 
     display_message("\n\n-*- Get substitution vectors -*-\n");
-    if (get_path(P, "input.vectors.file", "none") != "none")
-      throw Error("input.vectors.file (restart from a mapping file) is not available in this build");
-    std::string vec_path = get_path(P, "output.vectors.file", "none");
-    display_result("Output mapping to file", vec_path);
-    std::vector<double> n_out, norm(S), pr(S), ll(S);
-    std::vector<int32_t> rc(S);
-    if (vec_path != "none") n_out.resize((size_t)S * B);
-    chk(cmb_map(ctx, n_out.empty() ? nullptr : n_out.data(), norm.data(), pr.data(), rc.data(), ll.data()));
-    if (vec_path != "none") {
-      // LegacySubstitutionMappingTools::writeToStream (CoETools.cpp:408-412)
-      std::ofstream out(vec_path);
-      out << "Branches\tMean";
-      for (int c : in.cols) out << "\tSite" << c + 1;
-      out << "\n";
-      for (int b = 0; b < B; b++) {
-        out << b << "\t" << in.tree.brlen[b];
-        for (int64_t s = 0; s < S; s++) out << "\t" << n_out[(size_t)s * B + b];
-        out << "\n";
-      }
-    }
-    // CoETools::writeInfos (CoETools.cpp:496-531)
-    std::string infos = get_path(P, "output.infos", "none");
-    if (infos != "none") {
-      display_result("Alignment information logfile", infos);
-      std::ofstream out(infos);
-      out << "Group\tIsComplete\tIsConstant\tRC\tPR\tN\tlogLn" << std::endl;
-      for (int64_t i = 0; i < S; i++)
-        out << "[" << in.cols[i] + 1 << "]\t" << (site_is_complete(in.aln, in.alpha, in.cols[i]) ? 1 : 0) << "\t"
-            << (site_is_constant(in.aln, in.alpha, in.cols[i]) ? 1 : 0) << "\t" << rc[i] << "\t" << pr[i] << "\t"
-            << norm[i] << "\t" << ll[i] << std::endl;
-    }
+    Mapped m1 = map_data_set(in, P, "");
+    cmb_ctx* ctx = m1.ctx;
     std::string analysis = get_string(P, "analysis", "pairwise");
     display_result("Analysis type", analysis);
     if (get_string(P, "asr.method", "none") != "none")
@@ -322,8 +364,82 @@ int main(int argc, char** argv) {
     } else if (analysis == "pairwise") {
       const int stat_id = stat_id_of(P);
       const bool null = get_bool(P, "statistic.null", true);
-      if (get_path(P, "input.sequence.file2", "none") != "none")
-        throw Error("the two-data-set (inter-gene) analysis is not available in this build (SURVEY.md s8f)");
+      if (get_path(P, "input.sequence.file2", "none") != "none") {
+        // ---- two data sets (CoMap.cpp:236-347): data set 2 on the same topology, rectangle of
+        //      statistics, null distribution of the two simulators
+        const Params P2 = second_data_set_params(P);
+        Inputs in2;
+        in2.app = in.app;
+        prepare(in2, argv[0], &P2, &in.tree);
+        display_message("\n... and get its substitution vectors.\n");
+        Mapped m2 = map_data_set(in2, P2, "2");
+        const int64_t S2 = (int64_t)in2.cols.size();
+        display_message("\n\n-*- Compute statistics -*-\n");
+        display_message("Compares data set 1 with data set 2.");
+        const bool indep = get_bool(P, "independant_comparisons", false);
+        cmb_filters f;
+        f.min_rate_class = (int32_t)get_int(P, "statistic.min_rate_class", 0);
+        f.min_rate = get_double(P, "statistic.min_rate", 0.);
+        f.max_rate_class_diff = (int32_t)get_int(P, "statistic.max_rate_class_diff", -1);
+        f.max_rate_diff = get_double(P, "statistic.max_rate_diff", -1.);
+        f.min_stat = get_double(P, "statistic.min", 0.);
+        const int32_t min_rc2 = (int32_t)get_int(P2, "statistic.min_rate_class", 0);
+        const double min_r2 = get_double(P2, "statistic.min_rate", 0.);
+        std::string stat_path = get_path(P, "statistic.output.file", "statistics.txt");
+        if (stat_path == "none") stat_path = "statistics.txt";
+        display_message(std::to_string(S) + " sites * " + std::to_string(S2) + " = " +
+                        std::to_string(indep ? S : S * S2) + " pairs to compute!");
+        const int64_t cap = indep ? S : S * S2;
+        std::vector<int32_t> I(cap), J(cap), RC(cap);
+        std::vector<double> ST(cap), PR(cap), NM(cap);
+        int64_t rows = 0;
+        // nmin_by_row = 1: upstream pairs norms1[i] with norms2[i] (CoETools.cpp:803); comap_b200.nmin_by_site=yes fixes it
+        chk(cmb_pairs_inter(m1.ctx, m2.ctx, stat_id, &f, min_rc2, min_r2, indep ? 1 : 0,
+                            get_bool(P, "comap_b200.nmin_by_site", false) ? 0 : 1, cap, I.data(), J.data(), ST.data(),
+                            RC.data(), PR.data(), NM.data(), &rows));
+        {
+          std::ofstream out(stat_path);
+          out << "Group\tStat\tRCmin\tPRmin\tNmin\n";
+          write_rows_parallel(out, rows, 160, [&](int64_t r, char* p) {
+            char* q = p;
+            q += snprintf(q, 40, "[%d;%d]\t", in.cols[I[r]] + 1, in2.cols[J[r]] + 1);
+            q += fmt_g(q, ST[r]); *q++ = '\t';
+            q += snprintf(q, 16, "%d", RC[r]); *q++ = '\t';
+            q += fmt_g(q, PR[r]); *q++ = '\t';
+            q += fmt_g(q, NM[r]); *q++ = '\n';
+            return (int)(q - p);
+          });
+        }
+        display_result("Wrote statistics to", stat_path);
+        display_result("Number of pairs written", rows);
+        if (null) {
+          // CoETools::computeInterNullDistribution (CoETools.cpp:874-897): defaults 10 x 1000
+          std::string null_path = get_path(P, "statistic.null.output.file", "statistics.null.txt");
+          if (null_path == "none") null_path = "statistics.null.txt";
+          const int rep_cpu = (int)get_int(P, "statistic.null.nb_rep_CPU", 10);
+          const int rep_ram = (int)get_int(P, "statistic.null.nb_rep_RAM", 1000);
+          display_message("Compute statistic under null hypothesis...");
+          std::vector<double> raw((size_t)rep_cpu * rep_ram * 4);
+          chk(cmb_null_inter(m1.ctx, m2.ctx, stat_id, seed, rep_cpu, rep_ram, weighted_classes ? 1 : 0, raw.data()));
+          std::ofstream out(null_path);
+          out << "Stat\tRCmin\tPRmin\tNmin\n";
+          write_rows_parallel(out, (int64_t)rep_cpu * rep_ram, 80, [&](int64_t r, char* p) {
+            char* q = p;
+            q += fmt_g(q, raw[r * 4]); *q++ = '\t';
+            q += snprintf(q, 16, "%d", (int)raw[r * 4 + 1]); *q++ = '\t';
+            q += fmt_g(q, raw[r * 4 + 2]); *q++ = '\t';
+            q += fmt_g(q, raw[r * 4 + 3]); *q++ = '\n';
+            return (int)(q - p);
+          });
+          display_result("Wrote null distribution to", null_path);
+        }
+        chk(cmb_ctx_destroy(m2.ctx));
+        chk(cmb_ctx_destroy(ctx));
+        double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
+        std::cout << "Total execution time: " << secs << "s" << std::endl;
+        std::cout << "Bye bye ;-)" << std::endl;
+        return 0;
+      }
       display_message("\n\n-*- Perform pairwise analysis -*-\n");
       std::string stat_path = get_path(P, "statistic.output.file", "statistics.txt");
       if (stat_path == "none") stat_path = "statistics.txt";

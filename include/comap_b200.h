@@ -157,6 +157,27 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* filters
                        int32_t shard_index, int32_t shard_count, uint32_t columns, int64_t* n_rows);
 int cmb_pairs_fetch(cmb_ctx* ctx, int32_t column, void* host, int64_t capacity);
 
+/* Two data sets on the same tree topology ("inter-gene" analysis), one context each.
+ * Replaces CoETools::computeInterStats (CoETools.cpp:732-840): the statistic of every site i of
+ * data set 1 with every site j of data set 2 -- or of site i with site i when `independent`
+ * (independant_comparisons, CoETools.cpp:744-749,795-796) -- in the reference's row order (i, then
+ * j).  `filters` holds data set 1's rate thresholds and the shared ones; min_rate_class2 /
+ * min_rate2 are statistic.min_rate_class2 / .min_rate2 (CoETools.cpp:757-761).  nmin_by_row = 1
+ * reproduces upstream's Nmin = min(norms1[i], norms2[i]) (CoETools.cpp:803), 0 pairs norms2[j].
+ * No p-values upstream for this analysis.  Every output column is nullable. */
+int cmb_pairs_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, const cmb_filters* filters,
+                    int32_t min_rate_class2, double min_rate2, int32_t independent, int32_t nmin_by_row,
+                    int64_t capacity, int32_t* out_i, int32_t* out_j, double* out_stat, int32_t* out_rcmin,
+                    double* out_prmin, double* out_nmin, int64_t* n_rows);
+
+/* Replaces AnalysisTools::getNullDistributionInterDR (AnalysisTools.cpp:662-735;
+ * CoETools.cpp:878-897): rep_cpu x { simulate rep_ram sites under each data set's own tree /
+ * model / rate distribution, map both, paired statistic j<->j }.  raw is
+ * [rep_cpu*rep_ram][4] = Stat, RCmin, PRmin, Nmin (statistic.null.output.file).  Data set 2
+ * draws from the stream keyed seed ^ 0x9E3779B97F4A7C15 at the same site indices. */
+int cmb_null_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, uint64_t seed, int32_t rep_cpu,
+                   int32_t rep_ram, int32_t weighted_classes, double* raw);
+
 /* Replaces the distance-matrix loop (CoMap.cpp:432-440; ClusterTools.cpp:242-251).
  * mat (nullable) receives the full symmetric S*S matrix; it also stays on the device. */
 int cmb_distance_matrix(cmb_ctx* ctx, int32_t dist_id, double* mat);

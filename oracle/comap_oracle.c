@@ -501,14 +501,16 @@ static double vt_cov(int n, const double* a, const double* b) {
   return x;
 }
 
-static double* g_mean_vector = NULL;
+static double* g_mean_vector = NULL;  /* [2][B]: mean vector of the first / second site's data set */
 static int g_mean_vector_len = 0;
-void orc_set_mean_vector(int B, const double* mv) {
+void orc_set_mean_vectors(int B, const double* mv1, const double* mv2) { /* setMeanVectors, Statistics.h:200-203 */
   free(g_mean_vector);
-  g_mean_vector = malloc(sizeof(double) * (size_t)B);
-  memcpy(g_mean_vector, mv, sizeof(double) * (size_t)B);
+  g_mean_vector = malloc(sizeof(double) * (size_t)B * 2);
+  memcpy(g_mean_vector, mv1, sizeof(double) * (size_t)B);
+  memcpy(g_mean_vector + B, mv2, sizeof(double) * (size_t)B);
   g_mean_vector_len = B;
 }
+void orc_set_mean_vector(int B, const double* mv) { orc_set_mean_vectors(B, mv, mv); }
 /* CoMap.cpp:350-359 */
 void orc_mean_vector(int64_t S, int B, const double* n, double* mv) {
   for (int b = 0; b < B; b++) mv[b] = 0.;
@@ -523,7 +525,7 @@ double orc_stat(int stat_id, int B, const double* v1, const double* v2) {
       if (g_mean_vector_len != B) return NAN;
       double* a = malloc(sizeof(double) * (size_t)B * 2);
       double* b = a + B;
-      for (int i = 0; i < B; i++) { a[i] = v1[i] - g_mean_vector[i]; b[i] = v2[i] - g_mean_vector[i]; }
+      for (int i = 0; i < B; i++) { a[i] = v1[i] - g_mean_vector[i]; b[i] = v2[i] - g_mean_vector[B + i]; }
       double r = vt_cov(B, a, b) / (sqrt(vt_cov(B, a, a)) * sqrt(vt_cov(B, b, b)));
       free(a);
       return r;
@@ -555,6 +557,8 @@ double orc_stat(int stat_id, int B, const double* v1, const double* v2) {
   }
   return NAN;
 }
+
+double orc_stat2(int stat_id, int B, const double* v1, const double* v2) { return orc_stat(stat_id, B, v1, v2); }
 
 double orc_stat_group(int stat_id, int B, const double* n, int n_members, const int32_t* members) {
   if (stat_id == ORC_STAT_COMPENSATION) { /* Statistics.h:267-294 */
@@ -639,6 +643,46 @@ int orc_pairs(int stat_id, int64_t S, int B, const double* n, const double* norm
           out_nsim[r] = 0;
         }
       }
+      r++;
+    }
+  }
+  *n_rows = r;
+  return 0;
+}
+
+/* CoETools::computeInterStats (CoETools.cpp:732-840): data set 1 x data set 2 (or i <-> i when
+ * independent); the statistic's mean vectors, if any, are the caller's business.  nmin_by_row
+ * keeps upstream's jNorm = norms2[i] (CoETools.cpp:803). */
+int orc_pairs_inter(int stat_id, int64_t S1, int64_t S2, int B, const double* n1, const double* n2,
+                    const double* norm1, const double* norm2, const double* pr1, const double* pr2,
+                    const int32_t* rc1, const int32_t* rc2, int min_rate_class1, int min_rate_class2,
+                    double min_rate1, double min_rate2, int max_rate_class_diff, double max_rate_diff,
+                    double min_stat, int independent, int nmin_by_row, int64_t capacity, int32_t* out_i,
+                    int32_t* out_j, double* out_stat, int32_t* out_rcmin, double* out_prmin,
+                    double* out_nmin, int64_t* n_rows) {
+  int64_t r = 0;
+  for (int64_t i = 0; i < S1; i++) {
+    int iClass = rc1[i];
+    double iRate = pr1[i];
+    if (iClass < min_rate_class1) continue;
+    if (iRate < min_rate1) continue;
+    double iNorm = norm1[i];
+    int64_t begin = independent ? i : 0, end = independent ? i + 1 : S2;
+    for (int64_t j = begin; j < end; j++) {
+      int jClass = rc2[j];
+      double jRate = pr2[j];
+      if (jClass < min_rate_class2) continue;
+      if (jRate < min_rate2) continue;
+      double jNorm = norm2[(nmin_by_row && i < S2) ? i : j];
+      if (max_rate_class_diff >= 0 && abs(jClass - iClass) > max_rate_class_diff) continue;
+      if (max_rate_diff >= 0. && fabs(jRate - iRate) > max_rate_diff) continue;
+      double stat = orc_stat2(stat_id, B, n1 + i * B, n2 + j * B);
+      if (fabs(stat) < min_stat) continue;
+      if (r >= capacity) FAIL("orc_pairs_inter: capacity exceeded");
+      out_i[r] = (int32_t)i; out_j[r] = (int32_t)j; out_stat[r] = stat;
+      out_rcmin[r] = iClass < jClass ? iClass : jClass;
+      out_prmin[r] = iRate < jRate ? iRate : jRate;
+      out_nmin[r] = iNorm < jNorm ? iNorm : jNorm;
       r++;
     }
   }

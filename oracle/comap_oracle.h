@@ -72,6 +72,16 @@ double orc_stat(int stat_id, int B, const double* v1, const double* v2);
  * both sites, and how CoMap builds it from the mapping (CoMap.cpp:350-359: running sum over
  * sites in site order, divided by the number of sites). */
 void orc_set_mean_vector(int B, const double* mv);
+void orc_set_mean_vectors(int B, const double* mv1, const double* mv2);
+double orc_stat2(int stat_id, int B, const double* v1, const double* v2);
+/* CoETools::computeInterStats, CoETools.cpp:732-840 */
+int orc_pairs_inter(int stat_id, int64_t S1, int64_t S2, int B, const double* n1, const double* n2,
+                    const double* norm1, const double* norm2, const double* pr1, const double* pr2,
+                    const int32_t* rc1, const int32_t* rc2, int min_rate_class1, int min_rate_class2,
+                    double min_rate1, double min_rate2, int max_rate_class_diff, double max_rate_diff,
+                    double min_stat, int independent, int nmin_by_row, int64_t capacity, int32_t* out_i,
+                    int32_t* out_j, double* out_stat, int32_t* out_rcmin, double* out_prmin,
+                    double* out_nmin, int64_t* n_rows);
 void orc_mean_vector(int64_t S, int B, const double* n, double* mv);
 /* Group statistic (min over pairs; closed form for Compensation). idx = site rows. */
 double orc_stat_group(int stat_id, int B, const double* n /* [S][B] */, int n_members,

@@ -103,6 +103,34 @@ def mean_vector(n):
     return mv
 
 
+def mean_vectors(n1, n2):
+    """Installs the two data sets' mean vectors (setMeanVectors, CoMap.cpp:295-309)."""
+    mv2 = mean_vector(n2).copy()
+    mv1 = mean_vector(n1).copy()
+    lib().orc_set_mean_vectors(len(mv1), _d(mv1), _d(mv2))
+    return mv1, mv2
+
+
+def pairs_inter(stat_name, m1, m2, min_rate_class1=0, min_rate_class2=0, min_rate1=0.0, min_rate2=0.0,
+                max_rate_class_diff=-1, max_rate_diff=-1.0, min_stat=0.0, independent=False, nmin_by_row=True):
+    """m1, m2: dicts with n, norm, post_rate, rate_class of the two data sets."""
+    n1, n2 = _f64(m1["n"]), _f64(m2["n"])
+    S1, B = n1.shape; S2 = n2.shape[0]
+    cap = S1 * S2
+    oi = np.empty(cap, np.int32); oj = np.empty(cap, np.int32); st = np.empty(cap)
+    rcm = np.empty(cap, np.int32); prm = np.empty(cap); nm = np.empty(cap); nr = C.c_int64(0)
+    rc1 = np.ascontiguousarray(m1["rate_class"], dtype=np.int32); rc2 = np.ascontiguousarray(m2["rate_class"], dtype=np.int32)
+    _chk(lib().orc_pairs_inter(STAT[stat_name], C.c_int64(S1), C.c_int64(S2), B, _d(n1), _d(n2), _d(_f64(m1["norm"])),
+                               _d(_f64(m2["norm"])), _d(_f64(m1["post_rate"])), _d(_f64(m2["post_rate"])),
+                               _p(rc1, C.c_int32), _p(rc2, C.c_int32), min_rate_class1, min_rate_class2,
+                               C.c_double(min_rate1), C.c_double(min_rate2), max_rate_class_diff,
+                               C.c_double(max_rate_diff), C.c_double(min_stat), int(independent), int(nmin_by_row),
+                               C.c_int64(cap), _p(oi, C.c_int32), _p(oj, C.c_int32), _d(st), _p(rcm, C.c_int32),
+                               _d(prm), _d(nm), C.byref(nr)))
+    k = nr.value
+    return dict(i=oi[:k], j=oj[:k], stat=st[:k], rcmin=rcm[:k], prmin=prm[:k], nmin=nm[:k])
+
+
 def stat(name, v1, v2):
     v1, v2 = _f64(v1), _f64(v2)
     return lib().orc_stat(STAT[name], len(v1), _d(v1), _d(v2))

@@ -146,6 +146,35 @@ def test_clustering_tables_equal_c_abi_run(myo):
     ctx.close()
 
 
+def test_two_data_sets_table_equals_c_abi_run(myo):
+    """input.sequence.file2 -> inter-gene flow (CoMap.cpp:236-347): rectangle of statistics without
+    p-values, per-data-set rate thresholds (KEY2), null rows of the two simulators."""
+    from comap_b200 import api
+    tmp, _ = myo
+    run(tmp, *COMMON, "analysis=pairwise", "statistic=Correlation", "input.sequence.file2=Myoglobin.aln.sel.mase",
+        "statistic.output.file=inter.txt", "statistic.min_rate_class2=2", "statistic.min=0.2", "output.infos2=infos2.txt",
+        "statistic.null.nb_rep_CPU=2", "statistic.null.nb_rep_RAM=150", "statistic.null.output.file=inter_null.txt")
+    c = host_inputs(tmp)
+    a, b = api.Context(device=0), api.Context(device=0)
+    for ctx in (a, b):
+        ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+        ctx.set_alignment(c["codes"], c["code_mask"]); ctx.map()
+    p, k = a.pairs_inter(b, "correlation", filters=dict(min_stat=0.2), min_rate_class2=2)
+    hdr, rows = table(os.path.join(tmp, "inter.txt"))
+    assert hdr == ["Group", "Stat", "RCmin", "PRmin", "Nmin"]                           # CoETools.cpp:779
+    assert 0 < len(rows) == k < 129 * 129
+    co = c["coords"]
+    assert [x[0] for x in rows] == ["[%d;%d]" % (co[i], co[j]) for i, j in zip(p["i"], p["j"])]
+    assert [x[1] for x in rows] == [g(v) for v in p["stat"]] and [x[4] for x in rows] == [g(v) for v in p["nmin"]]
+    raw = a.null_inter(b, "correlation", 11, 2, 150)
+    hdr, nrows = table(os.path.join(tmp, "inter_null.txt"))
+    assert hdr == ["Stat", "RCmin", "PRmin", "Nmin"] and len(nrows) == 300
+    assert [x[0] for x in nrows] == [g(v) for v in raw[:, 0]]
+    hdr, irows = table(os.path.join(tmp, "infos2.txt"))
+    assert hdr[0] == "Group" and len(irows) == 129
+    a.close(); b.close()
+
+
 def test_error_exit_code_and_message(myo):
     tmp, _ = myo
     p = subprocess.run([BIN] + COMMON + ["analysis=pairwise", "statistic=Compensation"], cwd=tmp, capture_output=True, text=True)

@@ -23,7 +23,7 @@ SYMBOLS = [
     "cmb_simulate", "cmb_null_intra", "cmb_null_intra_from_alignments", "cmb_null_samples_dev",
     "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
-    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter",
+    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors",
 ]
 
 
@@ -197,6 +197,15 @@ class Context:
         k = nr.value
         out = dict(i=oi, j=oj, stat=st, rcmin=rcm, prmin=prm, nmin=nm, pvalue=pv, nsim=ns)
         return {name: (a[:k] if a is not None else None) for name, a in out.items()}, k
+
+    def load_vectors(self, n):
+        """Replaces the mapping of the mapped alignment with vectors read from a file
+        (input.vectors.file, CoETools.cpp:374-385); returns their norms."""
+        n = _f64(n)
+        assert n.shape == (self.S, self.B)
+        norm = np.empty(self.S)
+        self._chk(self.lib.cmb_load_vectors(self.h, _d(n), _d(norm)))
+        return norm
 
     # ------------------------------------------------------------------ two data sets
     def pairs_inter(self, other, stat, filters=None, min_rate_class2=0, min_rate2=0.0, independent=False,

@@ -366,6 +366,36 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   CMB_CATCH
 }
 
+int cmb_load_vectors(cmb_ctx* ctx, const double* n_in, double* norm) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (!c.mapped) fail("cmb_load_vectors: call cmb_map first (site likelihoods and rates come from the alignment)");
+  if (!n_in) fail("cmb_load_vectors: no vectors given");
+  const int64_t S = c.S, Sp = c.S_pad;
+  const int B = c.tree.B;
+  c.scratch.reserve(sizeof(double) * (size_t)S * B);
+  CMB_CUDA(cudaMemcpyAsync(c.scratch.p, n_in, sizeof(double) * (size_t)S * B, cudaMemcpyHostToDevice, c.stream));
+  // [S][B] -> [B][S_pad]: the transpose kernel with the two dimensions swapped
+  CMB_CUDA(cudaMemsetAsync(c.d_out.p, 0, sizeof(double) * (size_t)B * Sp, c.stream));
+  launch_transpose_out(c.scratch.as<double>(), (int)S, B, B, c.d_out.as<double>(), c.stream, Sp);
+  launch_prep(B, S, Sp, c.d_out.as<double>(), nullptr, c.pairs_mean.as<double>(), c.pairs_sd.as<double>(),
+              c.pairs_norm.as<double>(), c.stream);
+  c.prof.total_launches += 2;
+  c.have_meanvec = false;
+  CMB_CUDA(cudaMemcpyAsync(c.h_norm.data(), c.pairs_norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaStreamSynchronize(c.stream));
+  c.max_norm = 0.;
+  for (int64_t i = 0; i < S; i++)
+    if (c.h_norm[i] > c.max_norm) c.max_norm = c.h_norm[i];
+  if (norm) std::memcpy(norm, c.h_norm.data(), sizeof(double) * S);
+  c.have_dist = false;
+  c.null.ready = false;
+  c.pairs_rows = -1;
+  for (auto& o : c.pairs_col_off) o = -1;
+  CMB_CATCH
+}
+
 int cmb_profile_enable(cmb_ctx* ctx, int32_t on) {
   ctx->c.prof.enabled = on != 0;
   return 0;

@@ -737,7 +737,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k1_up(MapModel m, MapBuffers b, Up
 }
 
 __global__ void k_transpose_out(const double* __restrict__ out, int B, int64_t n, int64_t n_pad,
-                                double* __restrict__ dst) {
+                                double* __restrict__ dst, int64_t dst_stride) {
   __shared__ double tile[32][33];
   int64_t s0 = (int64_t)blockIdx.x * 32;
   int b0 = blockIdx.y * 32;
@@ -750,7 +750,7 @@ __global__ void k_transpose_out(const double* __restrict__ out, int B, int64_t n
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     int64_t s = s0 + i;
     int br = b0 + threadIdx.x;
-    if (s < n && br < B) dst[(size_t)s * B + br] = tile[threadIdx.x][i];
+    if (s < n && br < B) dst[(size_t)s * dst_stride + br] = tile[threadIdx.x][i];
   }
 }
 
@@ -854,9 +854,10 @@ void launch_map_finish(const MapModel& m, const MapBuffers& b, cudaStream_t st) 
   k1_finish<<<(unsigned)((b.n_pad + 255) / 256), 256, 0, st>>>(m, b);
   CMB_CUDA(cudaGetLastError());
 }
-void launch_transpose_out(const double* out, int B, int64_t n, int64_t n_pad, double* dst, cudaStream_t st) {
+void launch_transpose_out(const double* out, int B, int64_t n, int64_t n_pad, double* dst, cudaStream_t st,
+                          int64_t dst_stride) {
   dim3 grid((unsigned)((n + 31) / 32), (unsigned)((B + 31) / 32)), block(32, 8);
-  k_transpose_out<<<grid, block, 0, st>>>(out, B, n, n_pad, dst);
+  k_transpose_out<<<grid, block, 0, st>>>(out, B, n, n_pad, dst, dst_stride > 0 ? dst_stride : B);
   CMB_CUDA(cudaGetLastError());
 }
 

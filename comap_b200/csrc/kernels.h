@@ -115,7 +115,10 @@ template <class T>
 void compact_column(int64_t n, const uint8_t* keep, const int64_t* pos, const T* src, T* dst, cudaStream_t st);
 
 // [B][n_pad] -> [n][B] for the host-facing site-major output
-void launch_transpose_out(const double* out, int B, int64_t n, int64_t n_pad, double* dst, cudaStream_t st);
+// (dst_stride: row stride of dst, default B; the same kernel loads a site-major matrix into the
+// [B][n_pad] layout by swapping the roles of the two dimensions)
+void launch_transpose_out(const double* out, int B, int64_t n, int64_t n_pad, double* dst, cudaStream_t st,
+                          int64_t dst_stride = 0);
 
 
 // ---- K4

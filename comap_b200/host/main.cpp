@@ -280,14 +280,42 @@ Mapped map_data_set(const Inputs& in, const Params& P, const std::string& suffix
   chk(cmb_set_model(m.ctx, in.model.A, in.model.Q.data(), in.model.pi.data(), (int32_t)in.rdist.rates.size(),
                     in.rdist.rates.data(), in.rdist.probs.data(), in.count_method, nullptr));
   chk(cmb_set_alignment(m.ctx, S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
-  if (get_path(P, "input.vectors.file", "none") != "none")
-    throw Error("input.vectors.file (restart from a mapping file) is not available in this build");
+  const std::string in_vec = get_path(P, "input.vectors.file", "none");
   std::string vec_path = get_path(P, "output.vectors.file", "none");
-  display_result("Output mapping to file" + suffix, vec_path);
+  if (in_vec != "none") vec_path = "none"; // CoETools.cpp:374-390: vectors are read OR computed (+ written)
+  else display_result("Output mapping to file" + suffix, vec_path);
   std::vector<double> n_out;
   m.norm.resize(S); m.pr.resize(S); m.ll.resize(S); m.rc.resize(S);
   if (vec_path != "none") n_out.resize((size_t)S * B);
   chk(cmb_map(m.ctx, n_out.empty() ? nullptr : n_out.data(), m.norm.data(), m.pr.data(), m.rc.data(), m.ll.data()));
+  if (in_vec != "none") {
+    // restart from a mapping file (LegacySubstitutionMappingTools::readFromStream, CoETools.cpp:376-384):
+    // header "Branches\tMean\tSite<coord>...", one row per branch: id, length, the branch's entry per site
+    display_result("Substitution mapping in file" + suffix, in_vec);
+    std::ifstream vf(in_vec);
+    if (!vf) throw Error("input.vectors.file: cannot open '" + in_vec + "'");
+    std::string line;
+    std::getline(vf, line);
+    std::istringstream hs(line);
+    std::string tok;
+    int64_t n_cols = 0;
+    while (std::getline(hs, tok, '\t')) n_cols++;
+    if (n_cols != S + 2)
+      throw Error("input.vectors.file: " + std::to_string(n_cols - 2) + " sites in the mapping file, " + std::to_string(S) +
+                  " sites to analyse");
+    std::vector<double> n_in((size_t)S * B);
+    for (int b = 0; b < B; b++) {
+      if (!std::getline(vf, line)) throw Error("input.vectors.file: " + std::to_string(b) + " branches in the file, tree has " + std::to_string(B));
+      std::istringstream ls(line);
+      std::getline(ls, tok, '\t'); // branch id
+      std::getline(ls, tok, '\t'); // branch length
+      for (int64_t s2 = 0; s2 < S; s2++) {
+        if (!std::getline(ls, tok, '\t')) throw Error("input.vectors.file: short row for branch " + std::to_string(b));
+        n_in[(size_t)s2 * B + b] = std::stod(tok);
+      }
+    }
+    chk(cmb_load_vectors(m.ctx, n_in.data(), m.norm.data()));
+  }
   if (vec_path != "none") {
     // LegacySubstitutionMappingTools::writeToStream (CoETools.cpp:408-412)
     std::ofstream out(vec_path);

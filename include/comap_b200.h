@@ -101,6 +101,12 @@ int cmb_set_alignment(cmb_ctx* ctx, int64_t S, const uint8_t* codes, int32_t n_c
 int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_t* rate_class,
             double* loglik);
 
+/* Restart path, input.vectors.file (CoETools.cpp:374-385): replaces the mapping computed by
+ * cmb_map with vectors read from a file (site-major [S][B], as LegacySubstitutionMappingTools::
+ * readFromStream yields them); site likelihoods, rates and rate classes stay those of the
+ * alignment, as upstream.  norm (nullable) receives the norms of the loaded vectors. */
+int cmb_load_vectors(cmb_ctx* ctx, const double* n_in, double* norm);
+
 /* Replaces seqSim.simulate(n) (AnalysisTools.cpp:591,614; ClusterTools.cpp:224) in
  * discrete-rate mode with a counter-based Philox4x32-10 stream keyed
  * (seed, global site index, node).  weighted_classes = 0 draws the rate class uniformly

@@ -146,6 +146,27 @@ def test_clustering_tables_equal_c_abi_run(myo):
     ctx.close()
 
 
+def test_restart_from_the_reference_mapping_file(myo):
+    """input.vectors.file (CoETools.cpp:374-385): the pairwise analysis restarted from the
+    REFERENCE's own golden mapping file equals the statistics of those vectors."""
+    tmp, golden = myo
+    with open(os.path.join(tmp, "golden.vec"), "w") as f:
+        f.write("Branches\tMean" + "".join("\tSite%d" % c for c in golden["vec_coords"]) + "\n")
+        for b in range(197):
+            f.write("%d\t%g" % (b, golden["vec_brlen"][b]) + "".join("\t%.6g" % v for v in golden["vec_unif"][b]) + "\n")
+    run(tmp, *COMMON, "analysis=pairwise", "statistic=Correlation", "input.vectors.file=golden.vec",
+        "statistic.null=no", "statistic.output.file=restart.txt", "output.infos=restart.infos")
+    hdr, rows = table(os.path.join(tmp, "restart.txt"))
+    assert hdr == ["Group", "Stat", "RCmin", "PRmin", "Nmin"] and len(rows) == 129 * 128 // 2
+    vec = np.array([[float("%.6g" % v) for v in row] for row in golden["vec_unif"]]).T   # [site][branch]
+    for r in (0, 1, 500, 8000, len(rows) - 1):
+        i, j = [list(golden["vec_coords"]).index(int(x)) for x in rows[r][0].strip("[]").split(";")]
+        assert rows[r][1] == g(O.stat("correlation", vec[i], vec[j]))
+        assert rows[r][4] == g(min(np.sqrt((vec[i] ** 2).sum()), np.sqrt((vec[j] ** 2).sum())))
+    hdr, irows = table(os.path.join(tmp, "restart.infos"))                                 # N column = loaded norms
+    assert np.allclose([float(r[5]) for r in irows], np.sqrt((vec ** 2).sum(axis=1)), rtol=2e-5)
+
+
 def test_two_data_sets_table_equals_c_abi_run(myo):
     """input.sequence.file2 -> inter-gene flow (CoMap.cpp:236-347): rectangle of statistics without
     p-values, per-data-set rate thresholds (KEY2), null rows of the two simulators."""

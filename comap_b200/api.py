@@ -23,7 +23,7 @@ SYMBOLS = [
     "cmb_simulate", "cmb_null_intra", "cmb_null_intra_from_alignments", "cmb_null_samples_dev",
     "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
-    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors",
+    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates",
 ]
 
 
@@ -206,6 +206,27 @@ class Context:
         norm = np.empty(self.S)
         self._chk(self.lib.cmb_load_vectors(self.h, _d(n), _d(norm)))
         return norm
+
+    # ------------------------------------------------------------------ candidate groups
+    def candidates(self, stat, groups, omega=0.25, min_sim=1000, max_trials=10, rep_ram=1000, seed=0,
+                   weighted_classes=False, analysable=None):
+        """groups: list of lists of site indices (of the mapped alignment).  Returns the observed
+        group statistics, p-values (n1+1)/(n2+1), n1, n2 and the number of simulated sites
+        (CoMap.cpp:592-711; CoETools.cpp:901-1087)."""
+        off = np.zeros(len(groups) + 1, np.int64)
+        off[1:] = np.cumsum([len(g) for g in groups])
+        sites = np.ascontiguousarray(np.concatenate([np.asarray(g, np.int32) for g in groups]) if len(groups) else
+                                     np.zeros(0, np.int32), dtype=np.int32)
+        an = None if analysable is None else np.ascontiguousarray(analysable, dtype=np.uint8)
+        G = len(groups)
+        st, pv = np.empty(G), np.empty(G)
+        n1, n2 = np.empty(G, np.int64), np.empty(G, np.int64)
+        ns = C.c_int64()
+        self._chk(self.lib.cmb_candidates(self.h, STAT[stat], G, _i64(off), _i32(sites), _p(an, C.c_uint8),
+                                          C.c_double(omega), C.c_int64(min_sim), int(max_trials), int(rep_ram),
+                                          C.c_uint64(seed), int(weighted_classes), _d(st), _d(pv), _i64(n1), _i64(n2),
+                                          C.byref(ns)))
+        return dict(stat=st, pvalue=pv, n1=n1, n2=n2, n_simulated=ns.value)
 
     # ------------------------------------------------------------------ two data sets
     def pairs_inter(self, other, stat, filters=None, min_rate_class2=0, min_rate2=0.0, independent=False,

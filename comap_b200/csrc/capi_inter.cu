@@ -238,3 +238,219 @@ int cmb_null_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, uint64_t seed,
 }
 
 } // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Candidate groups: CoMap.cpp:592-711, CandidateGroupSet (CoETools.h:139-300,
+// CoETools.cpp:901-1038), computePValuesForCandidateGroups (CoETools.cpp:1042-1087).
+// The sampler is the reference's sequential state machine, driven by the NORMS of the simulated
+// sites; simulate / map / every statistic run on the device (K3, K1, k2_pair_list or the
+// compensation group kernel).  Like upstream, simulated sites a group has not completed when a
+// batch ends are dropped (CoETools.cpp:990-991).
+namespace {
+
+struct CandidateSet {
+  int n_groups = 0;
+  const int64_t* off = nullptr;      // [n_groups + 1] into sites
+  const int32_t* sites = nullptr;    // site indices of the mapped alignment
+  std::vector<char> analysable;
+  std::vector<double> lo, hi;        // norm range per candidate site (flat, as `sites`)
+  std::vector<int64_t> n1, n2;
+  int64_t min_sim = 0;
+  int64_t n_completed = 0, n_analysable = 0, n_trials = 0;
+  int64_t group_pos = 0, site_pos = 0;
+  std::vector<std::vector<int64_t>> pending; // per candidate site (flat): simulated columns waiting, FIFO
+  std::vector<size_t> pending_head;
+  int64_t size_of(int64_t g) const { return off[g + 1] - off[g]; }
+
+  // CandidateGroupSet::nextCandidateSite, CoETools.cpp:901-933
+  void next_site() {
+    if (n2[group_pos] < min_sim) {
+      site_pos++;
+      if (site_pos >= size_of(group_pos)) {
+        group_pos++;
+        if (group_pos >= n_groups) group_pos = 0;
+        site_pos = 0;
+      }
+    }
+    const int64_t start = group_pos;
+    if (n2[group_pos] >= min_sim || !analysable[group_pos]) {
+      while (n2[group_pos] >= min_sim || !analysable[group_pos]) {
+        group_pos++;
+        if (group_pos >= n_groups) group_pos = 0;
+        if (group_pos == start) fail("DEBUG: something wrong happened, this message should never appear!");
+      }
+      site_pos = 0;
+    }
+  }
+};
+
+struct GroupJob { int64_t group; std::vector<int64_t> cols; };
+
+// group statistics on the device: min over the pairs (i > j) of the pair statistic, or the
+// compensation group formula (Statistics.h:118-131, 267-295); `cols` index columns of `out`
+void group_stats(Context& c, int stat_id, const double* out, int64_t n_pad, const double* mv,
+                 const std::vector<GroupJob>& jobs, std::vector<double>& result) {
+  result.assign(jobs.size(), 0.);
+  if (jobs.empty()) return;
+  const int B = c.tree.B;
+  if (stat_id == CMB_STAT_COMPENSATION) {
+    std::vector<int32_t> members;
+    std::vector<int64_t> offsets{0};
+    for (const auto& j : jobs) {
+      for (int64_t col : j.cols) members.push_back((int32_t)col);
+      offsets.push_back((int64_t)members.size());
+    }
+    auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+    const size_t o_off = al(members.size() * 4), o_stat = al(o_off + offsets.size() * 8);
+    c.scratch2.reserve(o_stat + jobs.size() * 8 + 256);
+    unsigned char* sb = c.scratch2.as<unsigned char>();
+    CMB_CUDA(cudaMemcpyAsync(sb, members.data(), members.size() * 4, cudaMemcpyHostToDevice, c.stream));
+    CMB_CUDA(cudaMemcpyAsync(sb + o_off, offsets.data(), offsets.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    launch_group_compensation((int64_t)jobs.size(), (const int32_t*)sb, (const int64_t*)(sb + o_off), B, n_pad, out,
+                              (double*)(sb + o_stat), c.stream);
+    c.prof.total_launches += 1;
+    CMB_CUDA(cudaMemcpyAsync(result.data(), sb + o_stat, jobs.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+    CMB_CUDA(cudaStreamSynchronize(c.stream));
+    return;
+  }
+  std::vector<int2> pairs;
+  for (const auto& j : jobs)
+    for (size_t a = 1; a < j.cols.size(); a++)
+      for (size_t b = 0; b < a; b++) pairs.push_back(make_int2((int)j.cols[a], (int)j.cols[b])); // getValueForPair(v[i], v[j])
+  std::vector<double> vals(pairs.size());
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t o_stat = al(pairs.size() * sizeof(int2));
+  c.scratch2.reserve(o_stat + pairs.size() * 8 + 256);
+  unsigned char* sb = c.scratch2.as<unsigned char>();
+  if (!pairs.empty()) {
+    CMB_CUDA(cudaMemcpyAsync(sb, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
+    const bool corrected = stat_id == CMB_STAT_CORRECTED_CORRELATION;
+    launch_pair_list(corrected ? 0 : stat_id, B, n_pad, out, corrected ? mv : nullptr, (const int2*)sb, (int64_t)pairs.size(),
+                     (double*)(sb + o_stat), c.stream);
+    c.prof.total_launches += 1;
+    CMB_CUDA(cudaMemcpyAsync(vals.data(), sb + o_stat, pairs.size() * 8, cudaMemcpyDeviceToHost, c.stream));
+    CMB_CUDA(cudaStreamSynchronize(c.stream));
+  }
+  size_t k = 0;
+  for (size_t g = 0; g < jobs.size(); g++) {
+    double mini = INFINITY; // -log(0)
+    const size_t n = jobs[g].cols.size();
+    for (size_t a = 1; a < n; a++)
+      for (size_t b = 0; b < a; b++) {
+        const double val = vals[k++];
+        if (val < mini) mini = val;
+      }
+    result[g] = mini;
+  }
+}
+
+} // namespace
+
+extern "C" int cmb_candidates(cmb_ctx* ctx, int32_t stat_id, int32_t n_groups, const int64_t* group_off,
+                              const int32_t* group_sites, const uint8_t* analysable, double omega, int64_t min_sim,
+                              int32_t max_trials, int32_t rep_ram, uint64_t seed, int32_t weighted_classes,
+                              double* out_stat, double* out_pvalue, int64_t* out_n1, int64_t* out_n2, int64_t* n_simulated) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (stat_id < 0 || stat_id > CMB_STAT_CORRECTED_CORRELATION) fail("unknown statistic id %d", stat_id);
+  if (!c.mapped) fail("cmb_candidates: call cmb_map first");
+  if (n_groups < 1) fail("ERROR!!! No group can be tested!"); // CoMap.cpp:679-680
+  if (rep_ram < 1 || min_sim < 1) fail("cmb_candidates: bad simulation counts");
+  c.ensure_streams();
+  const double* mv = stat_id == CMB_STAT_CORRECTED_CORRELATION ? c.mean_vector() : nullptr;
+  CandidateSet cs;
+  cs.n_groups = n_groups; cs.off = group_off; cs.sites = group_sites; cs.min_sim = min_sim;
+  cs.analysable.assign(n_groups, 1);
+  cs.n1.assign(n_groups, 0); cs.n2.assign(n_groups, 0);
+  const int64_t n_sites = group_off[n_groups];
+  cs.lo.resize(n_sites); cs.hi.resize(n_sites);
+  cs.pending.assign(n_sites, {}); cs.pending_head.assign(n_sites, 0);
+  std::vector<GroupJob> obs;
+  for (int g = 0; g < n_groups; g++) {
+    cs.analysable[g] = analysable ? (analysable[g] != 0) : 1;
+    if (!cs.analysable[g]) continue;
+    cs.n_analysable++;
+    if (cs.size_of(g) < 2) fail("Error, group %d has %lld sites.", g, (long long)cs.size_of(g)); // CoMap.cpp:645-648
+    GroupJob j; j.group = g;
+    for (int64_t k = group_off[g]; k < group_off[g + 1]; k++) {
+      const int32_t s = group_sites[k];
+      if (s < 0 || s >= c.S) fail("cmb_candidates: site index %d out of range", s);
+      j.cols.push_back(s);
+      cs.lo[k] = c.h_norm[s] - omega; // CandidateGroup::computeNormRanges, CoETools.h:118-128
+      cs.hi[k] = c.h_norm[s] + omega;
+    }
+    obs.push_back(std::move(j));
+  }
+  if (cs.n_analysable == 0) fail("ERROR!!! No group can be tested!");
+  std::vector<double> observed(n_groups, NAN), tmp;
+  group_stats(c, stat_id, c.d_out.as<double>(), c.S_pad, mv, obs, tmp);
+  for (size_t k = 0; k < obs.size(); k++) observed[obs[k].group] = tmp[k];
+
+  MapModel m = c.map_model();
+  const int64_t R = rep_ram, n_pad = pad_sites(R);
+  std::vector<double> norms(R);
+  int64_t batch = 0;
+  bool test = true;
+  while (test) { // CoETools::computePValuesForCandidateGroups, CoETools.cpp:1053-1086
+    MapBuffers b = sim_buffers0(c, R, n_pad);
+    c.prof_begin("simulate");
+    launch_simulate(m, c.sim_stream, seed, batch * R, R, R, R, n_pad, weighted_classes, c.tree.n_nodes - 1,
+                    c.s_tips[0].as<uint8_t>(), nullptr, c.stream);
+    c.prof_end(1);
+    c.run_map(b, true, true);
+    c.scratch.reserve(sizeof(double) * 3 * (size_t)n_pad);
+    double* dmean = c.scratch.as<double>();
+    launch_prep(c.tree.B, R, n_pad, b.out, nullptr, dmean, dmean + n_pad, dmean + 2 * n_pad, c.stream);
+    c.prof.total_launches += 1;
+    CMB_CUDA(cudaMemcpyAsync(norms.data(), dmean + 2 * n_pad, sizeof(double) * R, cudaMemcpyDeviceToHost, c.stream));
+    CMB_CUDA(cudaStreamSynchronize(c.stream));
+    batch++;
+    // ---- CandidateGroupSet::analyseSimulations, CoETools.cpp:948-995
+    std::vector<GroupJob> jobs;
+    bool test_free = true;
+    for (int64_t i = 0; test && i < R; i++) {
+      bool first = true, test_norm = false;
+      int64_t start_g = 0, start_s = 0;
+      while (test && !test_norm) {
+        cs.next_site();
+        if (first) { start_g = cs.group_pos; start_s = cs.site_pos; first = false; }
+        else if (cs.group_pos == start_g && cs.site_pos == start_s) break; // looped over the whole set: drop this site
+        const int64_t k = group_off[cs.group_pos] + cs.site_pos;
+        test_norm = norms[i] >= cs.lo[k] && norms[i] <= cs.hi[k];
+        if (test_norm) {
+          // addSimulatedSite, CoETools.cpp:999-1038
+          const int64_t g = cs.group_pos;
+          cs.pending[k].push_back(i);
+          bool complete = true;
+          for (int64_t q = group_off[g]; complete && q < group_off[g + 1]; q++)
+            if (cs.pending_head[q] >= cs.pending[q].size()) complete = false;
+          if (complete) {
+            GroupJob j; j.group = g;
+            for (int64_t q = group_off[g]; q < group_off[g + 1]; q++) j.cols.push_back(cs.pending[q][cs.pending_head[q]++]);
+            jobs.push_back(std::move(j));
+            cs.n2[g]++;
+            if (cs.n2[g] == min_sim) cs.n_completed++;
+            test_free = false;
+          }
+          if (cs.n_completed == cs.n_analysable) test = false;
+        }
+      }
+    }
+    if (test_free) cs.n_trials++;
+    for (auto& p : cs.pending) p.clear(); // resetSimulations: unfinished groups lose their sites
+    std::fill(cs.pending_head.begin(), cs.pending_head.end(), 0);
+    group_stats(c, stat_id, b.out, n_pad, mv, jobs, tmp);
+    for (size_t k = 0; k < jobs.size(); k++)
+      if (tmp[k] >= observed[jobs[k].group]) cs.n1[jobs[k].group]++;
+    test = test && cs.n_trials < max_trials;
+  }
+  for (int g = 0; g < n_groups; g++) {
+    if (out_stat) out_stat[g] = observed[g];
+    if (out_pvalue) out_pvalue[g] = cs.analysable[g] ? ((double)cs.n1[g] + 1.) / ((double)cs.n2[g] + 1.) : NAN;
+    if (out_n1) out_n1[g] = cs.n1[g];
+    if (out_n2) out_n2[g] = cs.n2[g];
+  }
+  if (n_simulated) *n_simulated = batch * R;
+  CMB_CATCH
+}

@@ -86,6 +86,54 @@ __global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t 
   nmin[j] = a < c ? a : c;
 }
 
+// statistic of listed column pairs (a, b) of ONE mapping matrix: the group statistics of the
+// candidates analysis (AbstractMinimumStatistic::getValueForGroup, Statistics.h:118-131).  Same
+// operation order as k2_paired; one thread per pair.
+__global__ void k2_pair_list(int stat_id, int B, int64_t n_pad, const double* __restrict__ o, const double* __restrict__ mv,
+                             const int2* __restrict__ pairs, int64_t n_pairs, double* __restrict__ stat) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= n_pairs) return;
+  const int64_t ja = pairs[t].x, jb = pairs[t].y;
+  const double nb = (double)B;
+  double sx = 0., sy = 0., qx = 0., qy = 0., sxy = 0., s3 = 0., cnt = 0.;
+  for (int b = 0; b < B; b++) {
+    const double x = o[(size_t)b * n_pad + ja], y = o[(size_t)b * n_pad + jb];
+    if (mv) {
+      sx = add_(sx, add_(x, -mv[b]));
+      sy = add_(sy, add_(y, -mv[b]));
+    } else {
+      sx = add_(sx, x);
+      sy = add_(sy, y);
+    }
+    qx = add_(qx, mul_(x, x));
+    qy = add_(qy, mul_(y, y));
+    if (stat_id == 2) sxy = add_(sxy, mul_(x, y));
+    if (stat_id == 3 && x >= 1. && y >= 1.) cnt += 1.;
+    if (stat_id == 4) { double u = add_(x, y); s3 = add_(s3, mul_(u, u)); }
+  }
+  double r;
+  if (stat_id == 0 || stat_id == 1) {
+    const double mx = sx / nb, my = sy / nb;
+    double cxy = 0., cxx = 0., cyy = 0.;
+    for (int b = 0; b < B; b++) {
+      double x = o[(size_t)b * n_pad + ja], y = o[(size_t)b * n_pad + jb];
+      if (mv) { x = add_(x, -mv[b]); y = add_(y, -mv[b]); }
+      x = add_(x, -mx);
+      y = add_(y, -my);
+      cxy = add_(cxy, mul_(x, y));
+      cxx = add_(cxx, mul_(x, x));
+      cyy = add_(cyy, mul_(y, y));
+    }
+    cxy = cxy / nb * nb / (nb - 1.);
+    cxx = cxx / nb * nb / (nb - 1.);
+    cyy = cyy / nb * nb / (nb - 1.);
+    r = stat_id == 0 ? cxy / mul_(sqrt(cxx), sqrt(cyy)) : cxy;
+  } else if (stat_id == 2) r = sxy / mul_(sqrt(qx), sqrt(qy));
+  else if (stat_id == 3) r = cnt;
+  else r = add_(1., -(sqrt(s3) / add_(sqrt(qx), sqrt(qy))));
+  stat[t] = r;
+}
+
 __global__ void k2_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1,
                             const int32_t* rc2, const double* pr1, const double* pr2, double* raw) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -374,6 +422,12 @@ __global__ void k2_keep_to_i64(int64_t n, const uint8_t* keep, int64_t* out) {
 void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
                    const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st) {
   k2_paired<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stat_id, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin);
+  CMB_CUDA(cudaGetLastError());
+}
+void launch_pair_list(int stat_id, int B, int64_t n_pad, const double* out, const double* mv, const int2* pairs,
+                      int64_t n_pairs, double* stat, cudaStream_t st) {
+  if (n_pairs == 0) return;
+  k2_pair_list<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(stat_id, B, n_pad, out, mv, pairs, n_pairs, stat);
   CMB_CUDA(cudaGetLastError());
 }
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,

@@ -66,6 +66,9 @@ void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64
 // mv: mean vector subtracted before a correlation (corrected correlation) or nullptr
 void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
                    const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st);
+// statistic of listed column pairs of one [B][n_pad] matrix (candidate-group statistics)
+void launch_pair_list(int stat_id, int B, int64_t n_pad, const double* out, const double* mv, const int2* pairs,
+                      int64_t n_pairs, double* stat, cudaStream_t st);
 void launch_mean_vector(int B, int64_t S, int64_t n_pad, const double* out, double* mv, cudaStream_t st);
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
                      const double* pr1, const double* pr2, double* raw, cudaStream_t st);

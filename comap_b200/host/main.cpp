@@ -632,7 +632,113 @@ int main(int argc, char** argv) {
         }
       }
     } else if (analysis == "candidates") {
-      throw Error("analysis=candidates (sequential accept/reject sampler) is outside the B200 hot path (SURVEY.md s2.1)");
+      // ---- candidate groups (CoMap.cpp:592-711)
+      const int stat_id = stat_id_of(P);
+      std::string groups_path = get_path(P, "candidates.input.file", "none");
+      if (groups_path != "none") {
+        display_result("Candidate groups are in file", groups_path);
+        const int64_t min_sim = get_int(P, "candidates.null.min", 1000);
+        display_result("Minimum number of simulations", min_sim);
+        display_result("Verbose level", get_int(P, "candidates.null.verbose", 1));
+        std::map<int, int> pos_index; // coordinate -> site index
+        for (size_t i = 0; i < in.cols.size(); i++) pos_index[in.cols[i] + 1] = (int)i;
+        // DataTable::read(file, sep, header = true)
+        std::string sep = get_string(P, "candidates.input.column_sep", "\t");
+        if (sep == "\\t" || sep == "tab") sep = "\t";
+        std::ifstream gf(groups_path);
+        if (!gf) throw Error("candidates.input.file: cannot open '" + groups_path + "'");
+        auto split = [&](const std::string& line) {
+          std::vector<std::string> out;
+          size_t a = 0;
+          for (;;) {
+            size_t b = line.find(sep, a);
+            out.push_back(line.substr(a, b == std::string::npos ? std::string::npos : b - a));
+            if (b == std::string::npos) break;
+            a = b + sep.size();
+          }
+          return out;
+        };
+        std::string line;
+        std::getline(gf, line);
+        if (!line.empty() && line.back() == '\r') line.pop_back();
+        std::vector<std::string> header = split(line);
+        std::vector<std::vector<std::string>> table;
+        while (std::getline(gf, line)) {
+          if (!line.empty() && line.back() == '\r') line.pop_back();
+          if (line.empty()) continue;
+          table.push_back(split(line));
+          if (table.back().size() != header.size())
+            throw Error("candidates.input.file: row " + std::to_string(table.size()) + " has " +
+                        std::to_string(table.back().size()) + " columns, header has " + std::to_string(header.size()));
+        }
+        const std::string col_name = get_string(P, "candidates.input.column_name", "Group");
+        const auto hc = std::find(header.begin(), header.end(), col_name);
+        if (hc == header.end()) throw Error("candidates.input.file: no column '" + col_name + "'");
+        const size_t gc = (size_t)(hc - header.begin());
+        double omega = get_double(P, "candidates.omega", 0.25);
+        display_result("Norm interval", omega);
+        if (omega < 0) {
+          display_message("WARNING!!! Norm range parameter 'omega' must be positive... |omega| was used instead.");
+          omega = -omega;
+        }
+        // groups: digits and ; , only (CoMap.cpp:632-664)
+        std::vector<int64_t> off{0};
+        std::vector<int32_t> gsites;
+        std::vector<uint8_t> analysable;
+        for (size_t i = 0; i < table.size(); i++) {
+          std::string clean;
+          for (char ch : table[i][gc])
+            if (std::strchr("0123456789;,", ch)) clean += ch;
+          std::vector<int> positions;
+          std::string tok;
+          for (char ch : clean + ";") {
+            if (ch == ';' || ch == ',') {
+              if (!tok.empty()) positions.push_back(std::stoi(tok));
+              tok.clear();
+            } else tok += ch;
+          }
+          if (positions.size() <= 1)
+            throw Error("Error, group " + std::to_string(i) + " has " + std::to_string(positions.size()) + "sites.");
+          bool ok = true;
+          for (int pos : positions) {
+            auto it = pos_index.find(pos);
+            if (it == pos_index.end()) {
+              ok = false;
+              display_message("WARNING!!! Position " + std::to_string(pos) + " is not included in the selected sites. The group "
+                              "will be ignored (line " + std::to_string(i + 1) + " in input file).");
+              break;
+            }
+            gsites.push_back(it->second);
+          }
+          off.push_back((int64_t)gsites.size());
+          analysable.push_back(ok ? 1 : 0);
+        }
+        display_result("Number of groups to test", table.size());
+        if (table.empty()) throw Error("ERROR!!! No group can be tested!");
+        const int max_trials = (int)get_int(P, "candidates.nb_max_trials", 10);
+        const int rep_ram = (int)get_int(P, "candidates.null.nb_rep_RAM", 1000);
+        std::vector<double> gstat(table.size()), gp(table.size());
+        int64_t n_sim = 0;
+        chk(cmb_candidates(ctx, stat_id, (int32_t)table.size(), off.data(), gsites.data(), analysable.data(), omega, min_sim,
+                           max_trials, rep_ram, seed, weighted_classes ? 1 : 0, gstat.data(), gp.data(), nullptr, nullptr,
+                           &n_sim));
+        display_result("Number of sites simulated", n_sim);
+        // table + Stat + p-value (TextTools::toString(x, 6)), DataTable::write
+        std::string out_path = get_path(P, "candidates.output.file", "none");
+        if (out_path == "none") throw Error("candidates.output.file is not set");
+        std::string osep = get_string(P, "candidates.output.column_sep", sep);
+        if (osep == "\\t" || osep == "tab") osep = "\t";
+        std::ofstream out(out_path);
+        for (size_t k = 0; k < header.size(); k++) out << header[k] << osep;
+        out << "Stat" << osep << "p-value\n";
+        char buf[64];
+        for (size_t i = 0; i < table.size(); i++) {
+          for (const auto& cell : table[i]) out << cell << osep;
+          if (analysable[i]) { fmt_g(buf, gstat[i]); out << buf << osep; fmt_g(buf, gp[i]); out << buf << "\n"; }
+          else out << "NA" << osep << "NA\n";
+        }
+        display_result("Wrote results in file", out_path);
+      }
     } else throw Error("Unknown analysis type: " + analysis);
 
     chk(cmb_ctx_destroy(ctx));

@@ -184,6 +184,21 @@ int cmb_pairs_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, const cmb_fil
 int cmb_null_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, uint64_t seed, int32_t rep_cpu,
                    int32_t rep_ram, int32_t weighted_classes, double* raw);
 
+/* Candidate groups (analysis=candidates): replaces CandidateGroup::computeStatisticValue /
+ * computeNormRanges (CoMap.cpp:663-667; CoETools.h:106-128) and
+ * CoETools::computePValuesForCandidateGroups + CandidateGroupSet::analyseSimulations
+ * (CoETools.cpp:901-1087).  Group g = sites group_sites[group_off[g] .. group_off[g+1]) of the
+ * mapped alignment; analysable (nullable) marks groups to test.  Batches of rep_ram sites are
+ * simulated and mapped until every analysable group has min_sim simulated groups (sites dealt to
+ * candidate sites whose norm lies within +-omega, upstream's iteration order) or max_trials
+ * batches completed no group.  out_stat: observed group statistic (minimum over pairs, or the
+ * compensation group formula); out_pvalue = (n1 + 1) / (n2 + 1); all outputs nullable. */
+int cmb_candidates(cmb_ctx* ctx, int32_t stat_id, int32_t n_groups, const int64_t* group_off,
+                   const int32_t* group_sites, const uint8_t* analysable, double omega, int64_t min_sim,
+                   int32_t max_trials, int32_t rep_ram, uint64_t seed, int32_t weighted_classes,
+                   double* out_stat, double* out_pvalue, int64_t* out_n1, int64_t* out_n2,
+                   int64_t* n_simulated);
+
 /* Replaces the distance-matrix loop (CoMap.cpp:432-440; ClusterTools.cpp:242-251).
  * mat (nullable) receives the full symmetric S*S matrix; it also stays on the device. */
 int cmb_distance_matrix(cmb_ctx* ctx, int32_t dist_id, double* mat);

@@ -224,3 +224,81 @@ def groups(dist_name, n, norm, left, right, height, max_size):
     k = ng.value
     return dict(members=[members[offs[g]:offs[g + 1]].copy() for g in range(k)], height=gh[:k],
                 stat=gs[:k], nmin=gn[:k])
+
+
+def group_stat_min(name, vectors):
+    """AbstractMinimumStatistic::getValueForGroup (Statistics.h:118-131): minimum over i > j of
+    getValueForPair(v[i], v[j]); NaN never replaces the running minimum."""
+    mini = np.inf
+    for i in range(1, len(vectors)):
+        for j in range(i):
+            val = stat(name, vectors[i], vectors[j])
+            if val < mini:
+                mini = val
+    return mini
+
+
+def candidates_reference(stat_name, n_obs, norm_obs, groups, omega, min_sim, max_trials, batches, analysable=None):
+    """Pure-Python restatement (small cases only) of CandidateGroupSet (CoETools.h:139-300,
+    CoETools.cpp:901-1038) + computePValuesForCandidateGroups (CoETools.cpp:1042-1087).
+    `batches` yields (vectors [R][B], norms [R]) of successive simulated batches."""
+    G = len(groups)
+    an = [True] * G if analysable is None else [bool(x) for x in analysable]
+    gstat = (lambda vs: stat_group(stat_name, np.stack(vs), np.arange(len(vs)))) if stat_name == "compensation" else \
+            (lambda vs: group_stat_min(stat_name, vs))
+    observed = [gstat([n_obs[s] for s in g]) if an[k] else np.nan for k, g in enumerate(groups)]
+    lo = [[norm_obs[s] - omega for s in g] for g in groups]
+    hi = [[norm_obs[s] + omega for s in g] for g in groups]
+    n1 = [0] * G; n2 = [0] * G
+    st = dict(g=0, s=0, completed=0, trials=0)
+    n_an = sum(an)
+
+    def next_site():
+        if n2[st["g"]] < min_sim:
+            st["s"] += 1
+            if st["s"] >= len(groups[st["g"]]):
+                st["g"] = (st["g"] + 1) % G
+                st["s"] = 0
+        start = st["g"]
+        if n2[st["g"]] >= min_sim or not an[st["g"]]:
+            while n2[st["g"]] >= min_sim or not an[st["g"]]:
+                st["g"] = (st["g"] + 1) % G
+                assert st["g"] != start
+            st["s"] = 0
+
+    test, n_sim = True, 0
+    for vec, norms in batches:
+        if not test:
+            break
+        n_sim += len(norms)
+        pending = [[[] for _ in g] for g in groups]
+        test_free = True
+        i = 0
+        while test and i < len(norms):
+            first, test_norm = True, False
+            while test and not test_norm:
+                next_site()
+                if first:
+                    start, first = (st["g"], st["s"]), False
+                elif (st["g"], st["s"]) == start:
+                    break
+                g, s = st["g"], st["s"]
+                test_norm = lo[g][s] <= norms[i] <= hi[g][s]
+                if test_norm:
+                    pending[g][s].append(vec[i])
+                    if all(len(q) > 0 for q in pending[g]):
+                        vs = [q.pop(0) for q in pending[g]]
+                        n2[g] += 1
+                        if gstat(vs) >= observed[g]:
+                            n1[g] += 1
+                        if n2[g] == min_sim:
+                            st["completed"] += 1
+                        test_free = False
+                    if st["completed"] == n_an:
+                        test = False
+            i += 1
+        if test_free:
+            st["trials"] += 1
+        test = test and st["trials"] < max_trials
+    pv = [(n1[k] + 1.0) / (n2[k] + 1.0) if an[k] else np.nan for k in range(G)]
+    return dict(stat=np.array(observed), pvalue=np.array(pv), n1=np.array(n1), n2=np.array(n2), n_simulated=n_sim)

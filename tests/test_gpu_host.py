@@ -196,6 +196,35 @@ def test_two_data_sets_table_equals_c_abi_run(myo):
     a.close(); b.close()
 
 
+def test_candidate_groups_table_equals_c_abi_run(myo):
+    """analysis=candidates (CoMap.cpp:592-711): input table + Stat + p-value columns."""
+    from comap_b200 import api
+    tmp, _ = myo
+    c = host_inputs(tmp)
+    co = c["coords"]
+    groups = [[3, 17], [40, 41, 90], [5, 100]]
+    with open(os.path.join(tmp, "cand.txt"), "w") as f:
+        f.write("Name\tGroup\n")
+        for k, gsites in enumerate(groups):
+            f.write("g%d\t[%s]\n" % (k, ";".join(str(co[x]) for x in gsites)))
+        f.write("bad\t[%d;999999]\n" % co[0])                       # position that is not analysed -> NA
+    run(tmp, *COMMON, "analysis=candidates", "statistic=Correlation", "candidates.input.file=cand.txt",
+        "candidates.output.file=cand_out.txt", "candidates.null.min=30", "candidates.omega=1.0",
+        "candidates.null.nb_rep_RAM=300", "candidates.nb_max_trials=3")
+    ctx = api.Context(device=0)
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(c["codes"], c["code_mask"]); ctx.map()
+    r = ctx.candidates("correlation", groups + [[0]], omega=1.0, min_sim=30, max_trials=3, rep_ram=300, seed=11,
+                       analysable=[1, 1, 1, 0])
+    hdr, rows = table(os.path.join(tmp, "cand_out.txt"))
+    assert hdr == ["Name", "Group", "Stat", "p-value"] and len(rows) == 4
+    for k in range(3):
+        assert rows[k][2] == g(r["stat"][k]) and rows[k][3] == g(r["pvalue"][k])
+    assert rows[3][2:] == ["NA", "NA"]
+    assert r["n2"][:3].max() >= 1
+    ctx.close()
+
+
 def test_error_exit_code_and_message(myo):
     tmp, _ = myo
     p = subprocess.run([BIN] + COMMON + ["analysis=pairwise", "statistic=Compensation"], cwd=tmp, capture_output=True, text=True)

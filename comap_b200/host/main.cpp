@@ -79,6 +79,8 @@ struct Inputs {
   std::vector<uint8_t> codes; // [T][S], rows in leaf order
   std::vector<uint32_t> code_mask;
   int count_method = CMB_COUNT_UNIFORMIZATION;
+  std::vector<double> weights;   // weighted substitution count (nijt=...(weight=...)); empty = unweighted
+  bool weights_symmetric = true;
 };
 
 std::string data_dir_of(const char* argv0) {
@@ -154,9 +156,8 @@ void prepare(Inputs& in, const char* argv0, const Params* override_params = null
   if (nj.name == "Uniformization") in.count_method = CMB_COUNT_UNIFORMIZATION;
   else if (nj.name == "Decomposition") in.count_method = CMB_COUNT_DECOMPOSITION;
   else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition)");
-  std::string w = get_string(nj.args, "weight", "None");
-  if (w != "None" && w != "none")
-    throw Error("weighted substitution counts (weight=" + w + ") need Bio++'s AAIndex tables, which are not bundled");
+  in.weights = make_count_weights(get_string(nj.args, "weight", "None"), in.alpha, &in.weights_symmetric);
+  if (!in.weights.empty()) display_result("Substitution count weights", get_string(nj.args, "weight", "None"));
   if (!get_bool(P, "nijt.average", true) || !get_bool(P, "nijt.joint", true))
     throw Error("nijt.average=no / nijt.joint=no (benchmark-only variants) are not available in this build");
   display_result("Substitution count", nj.name);
@@ -221,15 +222,21 @@ void dry_run_dump(const Inputs& in) {
   std::cout << "\nDRYRUN count_method " << in.count_method << std::endl;
 }
 
-int stat_id_of(const Params& P) {
+int stat_id_of(const Params& P, const Inputs& in) {
   Procedure st = parse_procedure(get_string(P, "statistic", "Correlation"));
   if (st.name == "Cosinus") return CMB_STAT_COSINUS;
   if (st.name == "Correlation") return CMB_STAT_CORRELATION;
   if (st.name == "Covariance") return CMB_STAT_COVARIANCE;
   if (st.name == "Cosubstitution") return CMB_STAT_COSUBSTITUTION;
-  if (st.name == "Compensation")
-    throw Error("Compensation distance must be used with a mapping procedure allowing weights, e.g. "
-                "'nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))'.");
+  if (st.name == "Compensation") { // CoETools.cpp:564-574
+    if (in.weights.empty())
+      throw Error("Compensation distance must be used with a mapping procedure with weights, e.g. "
+                  "'nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))'.");
+    if (in.weights_symmetric)
+      throw Error("Compensation distance must be used with a mapping procedure allowing non-symmetric weights, e.g. "
+                  "'nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))'.");
+    return CMB_STAT_COMPENSATION;
+  }
   if (st.name == "CorrectedCorrelation") return CMB_STAT_CORRECTED_CORRELATION; // mean vector: CoMap.cpp:350-359
   if (st.name == "MI")
     throw Error("statistic=MI (with nijt=Label) is not available in this build (SURVEY.md s8f)");
@@ -278,7 +285,8 @@ Mapped map_data_set(const Inputs& in, const Params& P, const std::string& suffix
   chk(cmb_ctx_create(-1, nullptr, &m.ctx));
   chk(cmb_set_tree(m.ctx, (int32_t)in.tree.parent.size(), in.tree.parent.data(), in.tree.brlen.data()));
   chk(cmb_set_model(m.ctx, in.model.A, in.model.Q.data(), in.model.pi.data(), (int32_t)in.rdist.rates.size(),
-                    in.rdist.rates.data(), in.rdist.probs.data(), in.count_method, nullptr));
+                    in.rdist.rates.data(), in.rdist.probs.data(), in.count_method,
+                    in.weights.empty() ? nullptr : in.weights.data()));
   chk(cmb_set_alignment(m.ctx, S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
   const std::string in_vec = get_path(P, "input.vectors.file", "none");
   std::string vec_path = get_path(P, "output.vectors.file", "none");
@@ -390,7 +398,7 @@ int main(int argc, char** argv) {
     if (analysis == "none") {
       // mapping only
     } else if (analysis == "pairwise") {
-      const int stat_id = stat_id_of(P);
+      const int stat_id = stat_id_of(P, in);
       const bool null = get_bool(P, "statistic.null", true);
       if (get_path(P, "input.sequence.file2", "none") != "none") {
         // ---- two data sets (CoMap.cpp:236-347): data set 2 on the same topology, rectangle of
@@ -633,7 +641,7 @@ int main(int argc, char** argv) {
       }
     } else if (analysis == "candidates") {
       // ---- candidate groups (CoMap.cpp:592-711)
-      const int stat_id = stat_id_of(P);
+      const int stat_id = stat_id_of(P, in);
       std::string groups_path = get_path(P, "candidates.input.file", "none");
       if (groups_path != "none") {
         display_result("Candidate groups are in file", groups_path);

@@ -237,3 +237,44 @@ RateDist make_rate_distribution(const std::string& desc) {
 }
 
 } // namespace host
+
+// ---------------------------------------------------------------------------------------------
+// Weights of the weighted substitution count (PhylogeneticsApplicationTools::getSubstitutionCount,
+// reference call site CoMap.cpp:152; examples/simple/ProteinPairCompensation/comap.bpp:48).
+// Diff(index1=<AlphabetIndex1>, symmetrical=yes|no) = SimpleIndexDistance: w[x][y] = index[y] -
+// index[x] (absolute value when symmetrical).  Bundled indices (protein alphabet, order
+// A R N D C Q E G H I L K M F P S T W Y V): Grantham (1974) volume and polarity, Klein net charge.
+namespace host {
+namespace {
+const double kGranthamVolume[20] = {31, 124, 56, 54, 55, 85, 83, 3, 96, 111, 111, 119, 105, 132, 32.5, 32, 61, 170, 136, 84};
+const double kGranthamPolarity[20] = {8.1, 10.5, 11.6, 13.0, 5.5, 10.5, 12.3, 9.0, 10.4, 5.2,
+                                      4.9, 11.3, 5.7, 5.2, 8.0, 9.2, 8.6, 5.4, 6.2, 5.9};
+const double kKleinCharge[20] = {0, 1, 0, -1, 0, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0};
+}
+
+std::vector<double> make_count_weights(const std::string& desc, const Alphabet& alpha, bool* symmetric) {
+  if (symmetric) *symmetric = true;
+  if (desc.empty() || desc == "None" || desc == "none") return {};
+  Procedure p = parse_procedure(desc);
+  if (p.name != "Diff")
+    throw Error("weight=" + p.name + " is not available in this build (Diff(index1=Volume|Polarity|Charge, symmetrical=yes|no); "
+                "AAdist needs Bio++'s Grantham / Miyata tables, which are not bundled)");
+  const size_t A = alpha.states.size();
+  if (A != 20) throw Error("weight=Diff(...) needs the protein alphabet (the bundled indices are amino-acid properties)");
+  std::string idx = get_string(p.args, "index1", "None");
+  const double* v = nullptr;
+  if (idx == "Volume" || idx == "GranthamVolume") v = kGranthamVolume;
+  else if (idx == "Polarity" || idx == "GranthamPolarity") v = kGranthamPolarity;
+  else if (idx == "Charge" || idx == "KleinCharge") v = kKleinCharge;
+  else throw Error("weight=Diff(index1=" + idx + "): unknown index (Volume, Polarity, Charge)");
+  const bool sym = get_bool(p.args, "symmetrical", true);
+  if (symmetric) *symmetric = sym;
+  std::vector<double> w(A * A);
+  for (size_t x = 0; x < A; x++)
+    for (size_t y = 0; y < A; y++) {
+      const double d = v[y] - v[x];
+      w[x * A + y] = sym ? std::fabs(d) : d;
+    }
+  return w;
+}
+} // namespace host

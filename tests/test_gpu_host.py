@@ -196,6 +196,32 @@ def test_two_data_sets_table_equals_c_abi_run(myo):
     a.close(); b.close()
 
 
+VOLUME = np.array([31, 124, 56, 54, 55, 85, 83, 3, 96, 111, 111, 119, 105, 132, 32.5, 32, 61, 170, 136, 84.])  # Grantham 1974
+
+
+def test_weighted_counts_and_compensation_statistic(myo):
+    """nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no)) + statistic=Compensation
+    (examples/simple/ProteinPairCompensation/comap.bpp:41-48; CoETools.cpp:564-574): signed
+    volume-change mapping, statistic 1 - |v1+v2| / (|v1|+|v2|), against the oracle."""
+    tmp, _ = myo
+    args = [a for a in COMMON if not a.startswith("nijt=")]
+    run(tmp, *args, "nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))", "analysis=pairwise",
+        "statistic=Compensation", "statistic.null=no", "statistic.output.file=comp.txt", "output.vectors.file=wvec.txt")
+    c = host_inputs(tmp)
+    W = VOLUME[None, :] - VOLUME[:, None]                       # w[x][y] = volume[y] - volume[x]
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"], weights=W)
+    hdr, rows = table(os.path.join(tmp, "wvec.txt"))
+    vec = np.array([[float(x) for x in r[2:]] for r in rows]).T
+    assert (vec < 0).any() and np.allclose(vec, q["n"], rtol=2e-5, atol=1e-9)      # signed counts, 6 printed digits
+    op = O.pairs("compensation", q["n"], q["norm"], q["post_rate"], q["rate_class"])
+    hdr, rows = table(os.path.join(tmp, "comp.txt"))
+    assert len(rows) == len(op["i"]) == 129 * 128 // 2
+    assert np.allclose([float(x[1]) for x in rows], op["stat"], rtol=2e-5, atol=2e-6)
+    p = subprocess.run([BIN] + args + ["nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=yes))", "analysis=pairwise",
+                                       "statistic=Compensation"], cwd=tmp, capture_output=True, text=True)
+    assert p.returncode == 255 and "non-symmetric weights" in p.stdout
+
+
 def test_candidate_groups_table_equals_c_abi_run(myo):
     """analysis=candidates (CoMap.cpp:592-711): input table + Stat + p-value columns."""
     from comap_b200 import api

@@ -62,3 +62,27 @@ def test_infos_vs_golden():
     amb = (m["codes"] >= 20).any(0)
     assert np.array_equal(~amb, g["infos_complete"].astype(bool))
     assert not g["infos_const"].any()
+
+
+def test_weighted_counts_vs_grantham_golden():
+    """Weighted substitution counts (nijt=Uniformization(weight=AAdist(type=grantham, sym=yes)),
+    examples/Proteins/Benchmark/CoMap/analyse.sh -> Myo_unif_grantham.vec).  Bio++'s Grantham table
+    is not in the reference tree; the distance recomputed from Grantham's (1974) composition /
+    polarity / volume properties and rounded differs from the published integers by +-1 in places,
+    so this pins the weighted-count MECHANISM (0.1 % median, every branch and site) rather than the
+    last digits: an unweighted or wrongly weighted count is off by two orders of magnitude."""
+    comp = np.array([0, 0.65, 1.33, 1.38, 2.75, 0.89, 0.92, 0.74, 0.58, 0, 0, 0.33, 0, 0, 0.39, 1.42, 0.71, 0.13, 0.20, 0])
+    pol = np.array([8.1, 10.5, 11.6, 13.0, 5.5, 10.5, 12.3, 9.0, 10.4, 5.2, 4.9, 11.3, 5.7, 5.2, 8.0, 9.2, 8.6, 5.4, 6.2, 5.9])
+    vol = np.array([31, 124, 56, 54, 55, 85, 83, 3, 96, 111, 111, 119, 105, 132, 32.5, 32, 61, 170, 136, 84.])
+    d = lambda v: (v[:, None] - v[None, :]) ** 2
+    W = np.rint(50.723 * np.sqrt(1.833 * d(comp) + 0.1018 * d(pol) + 0.000399 * d(vol)))
+    m = H.myoglobin_inputs()
+    for method, key in (("uniformization", "vec_unif_grantham"), ("decomposition", "vec_decomp_grantham")):
+        r = O.map_sites(m["parent"], m["brlen"], m["Q"], m["pi"], m["rates"], m["probs"], m["codes"], m["code_mask"],
+                        method=method, weights=W)
+        gold = m["golden"][key].T
+        big = gold > 1e-9
+        rel = np.abs(r["n"] - gold)[big] / gold[big]
+        assert np.median(rel) < 2e-3 and rel.max() < 0.1
+        un = O.map_sites(m["parent"], m["brlen"], m["Q"], m["pi"], m["rates"], m["probs"], m["codes"], m["code_mask"], method=method)
+        assert np.median(np.abs(un["n"] - gold)[big] / gold[big]) > 0.9

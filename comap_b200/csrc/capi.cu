@@ -39,6 +39,7 @@ void DevStream::upload(const OpStream& s, cudaStream_t st) {
   CMB_CUDA(cudaMemcpyAsync(nrec.p, s.chunk_nrec.data(), sizeof(uint32_t) * n_chunks, cudaMemcpyHostToDevice, st));
   n_records = s.n_records;
   stack_depth = s.stack_depth;
+  stage_bytes = s.stage_bytes;
   if (!s.aux.empty()) {
     aux.reserve(sizeof(int32_t) * s.aux.size());
     CMB_CUDA(cudaMemcpyAsync(aux.p, s.aux.data(), sizeof(int32_t) * s.aux.size(), cudaMemcpyHostToDevice, st));

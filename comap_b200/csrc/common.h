@@ -49,6 +49,7 @@ void build_model_tables(ModelTables& mt, int A, const double* Q, const double* p
 
 // ---------------------------------------------------------------- tree + op streams
 constexpr int kMaxStack = 20; // per-thread stack depth; log2(#leaves)+2 suffices
+constexpr int kChunkSites = 128; // sites per CTA / per partial chunk of the tensor-core K1 kernels (A = 4)
 
 struct BinNode {
   int left = -1, right = -1, parent = -1;
@@ -83,6 +84,7 @@ struct OpStream {
   uint32_t n_records = 0;
   uint32_t chunk_cap = 0; // largest chunk in bytes
   int stack_depth = 0;    // message stack depth the walk needs (tensor-core down stream)
+  uint32_t stage_bytes = 0; // tensor-core up stream: largest packed stage (record | tip rows | partial chunks)
 };
 constexpr uint32_t kDownTipA = 1, kDownTipB = 2, kDownPush = 4, kDownRoot = 8;
 constexpr uint32_t kUpTipA = 1, kUpTipB = 2, kUpPop = 4, kUpPush = 8, kUpTakeA = 16, kUpTakeB = 32,

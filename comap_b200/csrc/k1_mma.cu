@@ -40,8 +40,8 @@ __device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b)
 struct UpMmaParams {
   const unsigned char* stream;                   // records, one per node
   const uint32_t *rec_off, *rec_bytes;
-  const int4* refs;     // per node 2 x int4: (flags, ref_a, ref_b, 0), (ref_a2, ref_b2, 0, 0)
-  uint32_t n_nodes, rec_cap;
+  const int4* refs;     // per node 2 x int4: (flags, ref_a, ref_b, tips_off), (ref_a2, ref_b2, blk_off, 0)
+  uint32_t n_nodes, stage_bytes; // stage_bytes: largest packed stage (record | tip rows | chunks), 128-aligned
   int n_stages;         // ring depth
 };
 constexpr int kMaxStages = 8;
@@ -198,8 +198,7 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int W = kSG / (8 * NG);                // consumer warps
   constexpr uint32_t kBlock = C * kSG * 32;        // bytes of one child's partial chunk
-  constexpr uint32_t kTipSlot = 4 * kSG;           // four tip rows (a, b, a2, b2)
-  const uint32_t stage_bytes = up.rec_cap + kTipSlot + 2 * kBlock; // record | tip rows | chunk a | chunk b
+  const uint32_t stage_bytes = up.stage_bytes;     // packed per node: record | tip rows (a, b, a2, b2) | chunks
   const int NSTG = up.n_stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_pad = b.n_pad;
@@ -233,12 +232,13 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
         const int ref_a = __shfl_sync(0xffffffffu, r0.y, j), ref_b = __shfl_sync(0xffffffffu, r0.z, j);
         const int ref_a2 = __shfl_sync(0xffffffffu, r1.x, j), ref_b2 = __shfl_sync(0xffffffffu, r1.y, j);
         const uint32_t roff = __shfl_sync(0xffffffffu, off, j), rnb = __shfl_sync(0xffffffffu, nb, j);
+        const uint32_t tips_off = (uint32_t)__shfl_sync(0xffffffffu, r0.w, j), blk_off = (uint32_t)__shfl_sync(0xffffffffu, r1.z, j);
         if (!first) mbar_wait_sleep(&stg_empty[s], ph, 200);
         if (lane == 0) {
           const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB, cha = flags & kUpCherryA, chb = flags & kUpCherryB;
           const bool ina = !(tipa || cha), inb = !(tipb || chb);
           unsigned char* st = stg_ring + (size_t)s * stage_bytes;
-          unsigned char* tp = st + up.rec_cap;
+          unsigned char* tp = st + tips_off;
           const uint32_t nrows = (tipa || cha) + (tipb || chb) + cha + chb;
           mbar_expect_tx(&stg_full[s], rnb + nrows * (uint32_t)kSG + ((uint32_t)ina + (uint32_t)inb) * kBlock);
           tma_bulk_g2s(st, up.stream + roff, rnb, &stg_full[s]);
@@ -246,8 +246,9 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
           if (tipb || chb) tma_bulk_g2s(tp + kSG, b.tips + (size_t)ref_b * n_pad + site0, kSG, &stg_full[s]);
           if (cha) tma_bulk_g2s(tp + 2 * kSG, b.tips + (size_t)ref_a2 * n_pad + site0, kSG, &stg_full[s]);
           if (chb) tma_bulk_g2s(tp + 3 * kSG, b.tips + (size_t)ref_b2 * n_pad + site0, kSG, &stg_full[s]);
-          if (ina) tma_bulk_g2s(tp + kTipSlot, b.D + d_chunk(chunk, ref_a, m.n_slots, C), kBlock, &stg_full[s]);
-          if (inb) tma_bulk_g2s(tp + kTipSlot + kBlock, b.D + d_chunk(chunk, ref_b, m.n_slots, C), kBlock, &stg_full[s]);
+          // stored children, in order a then b, from blk_off
+          if (ina) tma_bulk_g2s(st + blk_off, b.D + d_chunk(chunk, ref_a, m.n_slots, C), kBlock, &stg_full[s]);
+          if (inb) tma_bulk_g2s(st + blk_off + (ina ? kBlock : 0), b.D + d_chunk(chunk, ref_b, m.n_slots, C), kBlock, &stg_full[s]);
         }
         __syncwarp();
         if (++s == (uint32_t)NSTG) { s = 0; ph ^= 1; first = false; }
@@ -294,9 +295,10 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
     p.Pxb = p.Pxa + (kind_a == kCherry ? 2 * C * 16 : 0);
     p.Rta = p.Pxb + (kind_b == kCherry ? 2 * C * 16 : 0); // raw P[C], W[C] of tip a
     p.Rtb = p.Rta + (kind_a == kTip ? 2 * C * 16 : 0);
-    const unsigned char* ts = stage + up.rec_cap + wsite + s8; // tip code of (row, group g): ts[row * kSG + 8 g]
-    p.blk_a = reinterpret_cast<const double*>(stage + up.rec_cap + kTipSlot) + (size_t)wsite * 4;
-    p.blk_b = p.blk_a + kBlock / 8;
+    // h1.y / h1.z: offsets of the tip rows and of the first stored child's chunk in this stage
+    const unsigned char* ts = stage + h1.y + wsite + s8; // tip code of (row, group g): ts[row * kSG + 8 g]
+    p.blk_a = reinterpret_cast<const double*>(stage + h1.z) + (size_t)wsite * 4;
+    p.blk_b = p.blk_a + (kind_a == kInner ? kBlock / 8 : 0);
 
     // ---- tips and cherries: states (or state masks) of this lane's NG sites
     double acc_a[NG], acc_b[NG];
@@ -372,7 +374,7 @@ bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   CMB_CUDA(cudaGetDevice(&dev));
   CMB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   max_smem = max_smem / MINB - 1024 - 1024;      // 1 KB system reserve per CTA, 1 KB static (cmask)
-  const size_t stage = (size_t)s.cap + 4 * (size_t)kSG + 2 * (size_t)C * kSG * 32;
+  const size_t stage = ((size_t)s.stage_bytes + 127) & ~size_t(127);
   const size_t fixed = 128;
   if ((size_t)max_smem < fixed + 2 * stage) return false;
   static const int stage_cap = getenv("CMB_UP_STAGES") ? atoi(getenv("CMB_UP_STAGES")) : kMaxStages;
@@ -382,8 +384,12 @@ bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   up.rec_bytes = s.nbytes.as<uint32_t>();
   up.refs = s.aux.as<int4>();
   up.n_nodes = s.n_records;
-  up.rec_cap = s.cap;
+  up.stage_bytes = (uint32_t)stage;
   up.n_stages = (int)std::min<size_t>(std::min(kMaxStages, stage_cap), ((size_t)max_smem - fixed) / stage);
+  // Shared memory is carved out of the 256 KB it shares with L1, and the consumers' message stack and
+  // register spills live in local memory behind that L1: a third stage at C = 4 (2 x 111 KB of shared
+  // memory, ~28 KB of L1) ran 12.4 ms instead of 10.8 ms.  Keep a CTA's ring within 80 KB.
+  if (MINB > 1) up.n_stages = (int)std::max<size_t>(2, std::min<size_t>(up.n_stages, (80 * 1024) / stage));
   const size_t smem = fixed + (size_t)up.n_stages * stage;
   constexpr int threads = 32 * (kSG / (8 * NG) + 1);
   CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

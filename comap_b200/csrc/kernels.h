@@ -8,6 +8,7 @@ struct DevStream {           // an OpStream uploaded to the device
   DevBuf bytes, off, nbytes, nrec, aux;
   uint32_t n_chunks = 0, cap = 0, n_records = 0;
   int stack_depth = 0;
+  uint32_t stage_bytes = 0;
   void upload(const OpStream& s, cudaStream_t st);
   void release();
 };
@@ -51,8 +52,7 @@ void launch_map_up(const MapModel& m, const MapBuffers& b, const DevStream& s, c
 // A = 4: tensor-core up pass (k1_mma.cu); the stream is build_up_mma_stream's
 void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
 void launch_map_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
-// A = 4 partial layout: 128-site chunks, [chunk][slot][class][site][state]
-constexpr int kChunkSites = 128;
+// A = 4 partial layout: 128-site chunks (common.h kChunkSites), [chunk][slot][class][site][state]
 __host__ __device__ inline size_t d_chunk(int64_t chunk, int slot, int n_slots, int C) {
   return ((size_t)chunk * n_slots + slot) * ((size_t)C * kChunkSites * 4);
 }

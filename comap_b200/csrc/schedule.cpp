@@ -358,8 +358,6 @@ void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
     h.ref_b2 = cb ? t.bin[t.bin[b].right].tip_row : -1;
     h.out_a = t.bin[a].branch;
     h.out_b = t.bin[b].branch;
-    s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.ref_a); s.aux.push_back(h.ref_b); s.aux.push_back(0);
-    s.aux.push_back(h.ref_a2); s.aux.push_back(h.ref_b2); s.aux.push_back(0); s.aux.push_back(0);
     s.n_records++;
     std::vector<unsigned char> rec;
     append(rec, &h, sizeof h);
@@ -403,6 +401,20 @@ void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
         }
     }
     pad16(rec);
+    // Packed stage of this node in the kernel's ring: record | four tip rows (when a child is a
+    // tip or a cherry) | partial chunk of each stored child.  Nodes with two stored children
+    // carry the shortest records and no tip rows, so the largest stage is well below
+    // "largest record + tip rows + two chunks" and a third stage fits at C = 4.
+    const uint32_t tips_off = (uint32_t)((rec.size() + 127) & ~size_t(127));
+    const uint32_t blk_off = tips_off + ((ta || tb || ca || cb) ? 4u * kChunkSites : 0u);
+    const uint32_t n_blk = (uint32_t)(!ta && !ca) + (uint32_t)(!tb && !cb);
+    s.stage_bytes = std::max(s.stage_bytes, blk_off + n_blk * (uint32_t)C * kChunkSites * 32u);
+    UpHdr hc = h; // consumers' view: where the tip rows and chunks sit in the stage
+    hc.ref_a2 = (int32_t)tips_off;
+    hc.ref_b2 = (int32_t)blk_off;
+    std::memcpy(rec.data(), &hc, sizeof hc);
+    s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.ref_a); s.aux.push_back(h.ref_b); s.aux.push_back((int32_t)tips_off);
+    s.aux.push_back(h.ref_a2); s.aux.push_back(h.ref_b2); s.aux.push_back((int32_t)blk_off); s.aux.push_back(0);
     max_rec = std::max(max_rec, rec.size());
     recs.push_back(std::move(rec));
   }

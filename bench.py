@@ -102,7 +102,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------
 # CPU arm: the oracle port on a bounded sample
 # ------------------------------------------------------------------------------------------
-def cpu_sample(cfg, w, aln_codes=None, sample_sites=400, sample_ram=1000, seed=0):
+def cpu_sample(cfg, w, aln_codes=None, sample_sites=800, sample_ram=3000, seed=0):
     """Times the oracle (1 thread) on a sample of the step and extrapolates linearly.
 
     Components timed: (a) simulate+map+paired statistic for 1 outer replicate of

@@ -36,6 +36,11 @@ struct ClusterParams {
   int32_t* wl;          // [2][S] worklist: rows whose cached minimum has to be rescanned
   double* part_val;     // [grid] per-CTA first minimum of the new row a
   int32_t* part_idx;
+  double* scan_val;     // [grid] per-CTA first minimum of its slice of the cached row minima
+  int32_t* scan_idx;
+  double* seg_val;      // [grid] partial minima of row segments (a queued row is rescanned by several CTAs)
+  int32_t* seg_idx;
+  int32_t* seg_cnt;     // [grid] segments of a queued row finished so far
   int32_t* wl_count;    // [2]
   int32_t *left, *right; // [S-1]
   double* height;       // [S-1]
@@ -72,18 +77,18 @@ __device__ Best block_best(Best b, Best* sh) {
 // first minimum of row r over live columns j>r (skipping `skip`).  The loads of a batch of
 // U columns per thread are issued together (liveness byte and matrix entry are independent),
 // so a 160 KB row costs a few L2 round trips instead of one per column.
-__device__ void rescan_row(const ClusterParams& p, int r, int skip, Best* sh) {
+__device__ Best scan_columns(const ClusterParams& p, int r, int skip, int64_t lo, int64_t hi, Best* sh) {
   constexpr int U = 8;
   Best b{0., -1};
   const double* row = p.mat + (size_t)r * p.S;
-  for (int64_t base = r + 1; base < p.S; base += (int64_t)blockDim.x * U) {
+  for (int64_t base = lo; base < hi; base += (int64_t)blockDim.x * U) {
     double v[U];
     uint8_t al[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
       const int64_t j = base + (int64_t)u * blockDim.x + threadIdx.x;
-      al[u] = j < p.S ? p.alive[j] : 0;
-      v[u] = j < p.S ? row[j] : 0.;
+      al[u] = j < hi ? p.alive[j] : 0;
+      v[u] = j < hi ? row[j] : 0.;
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
@@ -91,7 +96,10 @@ __device__ void rescan_row(const ClusterParams& p, int r, int skip, Best* sh) {
       if (al[u] && j != skip && !(v[u] != v[u]) && better(v[u], (int)j, b)) { b.v = v[u]; b.i = (int)j; }
     }
   }
-  b = block_best(b, sh);
+  return block_best(b, sh);
+}
+__device__ void rescan_row(const ClusterParams& p, int r, int skip, Best* sh) {
+  const Best b = scan_columns(p, r, skip, r + 1, p.S, sh);
   if (threadIdx.x == 0) { p.rmin_val[r] = b.v; p.rmin_idx[r] = b.i; }
 }
 
@@ -116,25 +124,27 @@ __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
   const int64_t S = p.S;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
   for (int64_t step = 0; step + 2 < S; step++) {
-    // (1) first global minimum from the cached row minima (every CTA computes it)
+    // (1) first global minimum of the cached row minima: every CTA scans its slice (one batch of
+    //     loads), then all CTAs reduce the per-CTA partials; the extra grid sync (~1.4 us) costs
+    //     less than the five dependent L2 round trips of a full scan per CTA
     Best b{0., -1};
     {
-      constexpr int U = 8;
-      for (int64_t base = 0; base < S; base += (int64_t)blockDim.x * U) {
-        double v[U];
-        int32_t ix[U];
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int64_t i = base + (int64_t)u * blockDim.x + threadIdx.x;
-          ix[u] = i < S ? p.rmin_idx[i] : -1;
-          v[u] = i < S ? p.rmin_val[i] : 0.;
-        }
-#pragma unroll
-        for (int u = 0; u < U; u++) {
-          const int64_t i = base + (int64_t)u * blockDim.x + threadIdx.x;
-          if (ix[u] >= 0 && better(v[u], (int)i, b)) { b.v = v[u]; b.i = (int)i; }
-        }
+      const int64_t per = (S + gridDim.x - 1) / gridDim.x, lo = (int64_t)blockIdx.x * per, hi = lo + per < S ? lo + per : S;
+      for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+        const int ix = p.rmin_idx[i];
+        const double v = p.rmin_val[i];
+        if (ix >= 0 && better(v, (int)i, b)) { b.v = v; b.i = (int)i; }
       }
+      b = block_best(b, sh);
+      if (threadIdx.x == 0) { p.scan_val[blockIdx.x] = b.v; p.scan_idx[blockIdx.x] = b.i; }
+      grid.sync();
+      b = Best{0., -1};
+      for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
+        const int i = p.scan_idx[c];
+        const double v = p.scan_val[c];
+        if (i >= 0 && better(v, i, b)) { b.v = v; b.i = i; }
+      }
+      __syncthreads(); // sh is reused
     }
     b = block_best(b, sh);
     const int a = b.i;
@@ -215,9 +225,37 @@ __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
       __syncthreads();
     }
     const int n_wl = *wlc;
-    // block 0 is busy with the bookkeeping: the rescans start at the other end of the grid
-    for (int w = (int)gridDim.x - 1 - (int)blockIdx.x; w < n_wl; w += gridDim.x) {
-      rescan_row(p, wl[w], bb, sh);
+    // Every queued row is rescanned by nseg CTAs (one batch of loads each instead of up to five
+    // dependent ones); the CTA that finishes a row's last segment combines the partial minima.
+    const int G = (int)gridDim.x;
+    const int nseg = n_wl > 0 && n_wl * 2 <= G ? (G / n_wl < 8 ? G / n_wl : 8) : 1;
+    // block 0 is busy with the bookkeeping: the work starts at the other end of the grid
+    for (int it = G - 1 - (int)blockIdx.x; it < n_wl * nseg; it += G) {
+      const int w = it / nseg, seg = it % nseg;
+      const int r = wl[w];
+      if (nseg == 1) rescan_row(p, r, bb, sh);
+      else {
+        const int64_t L = S - r - 1, lo = r + 1 + L * seg / nseg, hi = r + 1 + L * (seg + 1) / nseg;
+        const Best t = scan_columns(p, r, bb, lo, hi, sh);
+        __shared__ int last;
+        if (threadIdx.x == 0) {
+          p.seg_val[w * nseg + seg] = t.v;
+          p.seg_idx[w * nseg + seg] = t.i;
+          __threadfence();
+          last = atomicAdd(&p.seg_cnt[w], 1) == nseg - 1;
+        }
+        __syncthreads();
+        if (last && threadIdx.x < 32) {
+          __threadfence();
+          Best c{0., -1};
+          if ((int)threadIdx.x < nseg) {
+            c.i = __ldcg(&p.seg_idx[w * nseg + threadIdx.x]);
+            c.v = __ldcg(&p.seg_val[w * nseg + threadIdx.x]);
+          }
+          c = warp_best(c);
+          if (threadIdx.x == 0) { p.rmin_val[r] = c.v; p.rmin_idx[r] = c.i; p.seg_cnt[w] = 0; }
+        }
+      }
       __syncthreads();
     }
     grid.sync();
@@ -277,7 +315,8 @@ int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* l
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
   size_t o_val = 0, o_idx = al(o_val + 8 * S), o_alive = al(o_idx + 4 * S), o_len = al(o_alive + S),
          o_nl = al(o_len + 8 * S), o_node = al(o_nl + 4 * S), o_wl = al(o_node + 4 * S), o_wlc = al(o_wl + 8 * S),
-         o_pv = al(o_wlc + 64), o_pi = al(o_pv + 8 * 1024), o_end = al(o_pi + 4 * 1024);
+         o_pv = al(o_wlc + 64), o_pi = al(o_pv + 8 * 1024), o_sv = al(o_pi + 4 * 1024), o_si = al(o_sv + 8 * 1024),
+         o_gv = al(o_si + 4 * 1024), o_gi = al(o_gv + 8 * 1024), o_gc = al(o_gi + 4 * 1024), o_end = al(o_gc + 4 * 1024);
   work.reserve(o_end);
   unsigned char* w = work.as<unsigned char>();
   ClusterParams p;
@@ -286,6 +325,9 @@ int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* l
   p.len = (double*)(w + o_len); p.nleaves = (int32_t*)(w + o_nl); p.node = (int32_t*)(w + o_node);
   p.wl = (int32_t*)(w + o_wl); p.wl_count = (int32_t*)(w + o_wlc);
   p.part_val = (double*)(w + o_pv); p.part_idx = (int32_t*)(w + o_pi);
+  p.scan_val = (double*)(w + o_sv); p.scan_idx = (int32_t*)(w + o_si);
+  p.seg_val = (double*)(w + o_gv); p.seg_idx = (int32_t*)(w + o_gi); p.seg_cnt = (int32_t*)(w + o_gc);
+  CMB_CUDA(cudaMemsetAsync(p.seg_cnt, 0, 4 * 1024, st));
   p.left = left_dev; p.right = right_dev; p.height = height_dev;
   k4_init_state<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(p);
   CMB_CUDA(cudaGetLastError());

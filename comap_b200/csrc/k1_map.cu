@@ -160,7 +160,7 @@ __device__ __forceinline__ void contract_n(const double* __restrict__ W, const d
 // busiest unit of this kernel (l1tex 85 %: broadcast table reads, the per-thread message
 // stack in local memory, the partial stores), DRAM 44 %.
 template <int A, int NS, int CT>
-__global__ void __launch_bounds__(256) k1_down(MapModel m, MapBuffers b, ChunkMeta cm, int groups, int tips_in_smem) {
+__global__ void __launch_bounds__(256, (A > 4 ? 2 : 1)) k1_down(MapModel m, MapBuffers b, ChunkMeta cm, int groups, int tips_in_smem) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ uint32_t cmask[256];
   constexpr int AA = A * A;
@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(256) k1_down(MapModel m, MapBuffers b, ChunkMe
   // 327 -- the write-through local stores were 44 % of this kernel's L1 -> L2 write traffic.
   double stk[kMaxStack][NS][A], t0[NS][A], t1[NS][A];
   int sp = 0, nc = 0;
+  constexpr bool kRegCache = A <= 4;
 #pragma unroll
   for (int k = 0; k < NS; k++)
 #pragma unroll
@@ -267,13 +268,13 @@ __global__ void __launch_bounds__(256) k1_down(MapModel m, MapBuffers b, ChunkMe
         for (int k = 0; k < NS; k++)
 #pragma unroll
           for (int i = 0; i < A; i++) prod[k][i] *= ma[k][i];
-      } else if (nc == 2) {
+      } else if (kRegCache && nc == 2) {
         nc = 1;
 #pragma unroll
         for (int k = 0; k < NS; k++)
 #pragma unroll
           for (int i = 0; i < A; i++) prod[k][i] *= t1[k][i];
-      } else if (nc == 1) {
+      } else if (kRegCache && nc == 1) {
         nc = 0;
 #pragma unroll
         for (int k = 0; k < NS; k++)
@@ -308,7 +309,10 @@ __global__ void __launch_bounds__(256) k1_down(MapModel m, MapBuffers b, ChunkMe
         }
       }
       if (flags & kDownPush) {
-        if (nc == 2) { // spill the oldest cached entry
+        if (!kRegCache) { // proteins: 2 x 20 doubles of register cache would halve the occupancy
+          matvec_n<A, NS>(tp, cur, stk[sp]);
+          ++sp;
+        } else if (nc == 2) { // spill the oldest cached entry
 #pragma unroll
           for (int k = 0; k < NS; k++)
 #pragma unroll

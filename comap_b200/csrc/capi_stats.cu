@@ -408,7 +408,16 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
   L.o_prmin = (double*)dp(4); L.o_nmin = (double*)dp(5); L.o_pvalue = (double*)dp(6); L.o_nsim = (int64_t*)dp(7);
   L.o_keep = sb + o_keep;
   c.prof_begin("pairs");
-  int nl = launch_tiles(L, c.stream);
+  int nl = 0;
+  // only PValue / Nsim asked for and Stat / Nmin of the same table are resident: no Gram tiles
+  const bool pv_only = use_null && !any_filter && (columns & 0x3Fu) == 0 && c.pairs_rows == total &&
+                       c.pairs_col_off[2] == (int64_t)off[2] && c.pairs_col_off[5] == (int64_t)off[5] &&
+                       c.pairs_stat_id == stat_id && c.pairs_shard_index == shard_index && c.pairs_shard_count == shard_count;
+  if (pv_only) {
+    launch_pvalues(total, (const double*)(sb + off[2]), (const double*)(sb + off[5]), L.K, L.nmax, L.bin_off, L.sorted,
+                   L.o_pvalue, L.o_nsim, c.stream);
+    nl = 1;
+  } else nl = launch_tiles(L, c.stream);
   c.prof_end(nl);
   int64_t kept = total;
   if (any_filter && total > 0) {
@@ -428,6 +437,7 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
   for (int k = 0; k < 8; k++)
     if (columns >> k & 1) c.pairs_col_off[k] = (int64_t)off[k];
   c.pairs_rows = kept;
+  c.pairs_stat_id = stat_id; c.pairs_shard_index = shard_index; c.pairs_shard_count = shard_count;
   if (n_rows) *n_rows = kept;
   CMB_CATCH
 }

@@ -72,6 +72,7 @@ struct Context {
   cudaEvent_t copy_event = nullptr;
   int64_t pairs_col_off[8] = {-1, -1, -1, -1, -1, -1, -1, -1}; // resident pair columns in `pair_table`
   int64_t pairs_rows = -1;
+  int pairs_stat_id = -1, pairs_shard_index = -1, pairs_shard_count = -1; // what the resident columns belong to
   DevBuf pairs_mean, pairs_sd, pairs_norm; // per-site mean / sd / norm for the tile kernels
   // corrected correlation (Statistics.h:176-205): mean vector of the mapped alignment and the
   // per-site mean / sd of the corrected vectors; built on first use after cmb_map

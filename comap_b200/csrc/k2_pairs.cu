@@ -407,6 +407,32 @@ __global__ void k2_diag_rows(TileParams p) {
   p.o_prmin[i] = pi_ < pj ? pi_ : pj;
 }
 
+// p-value columns from the resident Stat / Nmin columns (same epilogue as k2_tiles): used when
+// the null-independent columns were scored before the null existed, so the Gram tiles are not
+// recomputed for PValue / Nsim
+__global__ void k2_pvalues(int64_t n, const double* __restrict__ stat, const double* __restrict__ nmin, int K, double nmax,
+                           const int64_t* __restrict__ bin_off, const double* __restrict__ sorted, double* __restrict__ pvalue,
+                           int64_t* __restrict__ nsim_out) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const double st = stat[r];
+  const int cat = domain_index(nmax, K, nmin[r]);
+  double pv = nan("");
+  int64_t nsim = 0;
+  if (cat >= 0) {
+    const double* sim = sorted + bin_off[cat];
+    nsim = bin_off[cat + 1] - bin_off[cat];
+    int64_t lo = 0, hi = nsim; // count = #{sim < stat} on the ascending bin
+    while (lo < hi) {
+      int64_t mid = (lo + hi) >> 1;
+      if (sim[mid] < st) lo = mid + 1; else hi = mid;
+    }
+    pv = (double)(nsim - lo + 1) / (double)(nsim + 1);
+  }
+  if (pvalue) pvalue[r] = pv;
+  if (nsim_out) nsim_out[r] = nsim;
+}
+
 template <class T>
 __global__ void k2_compact(int64_t n, const uint8_t* keep, const int64_t* pos, const T* src, T* dst) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,6 +538,13 @@ int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
   }
   CMB_CUDA(cudaGetLastError());
   return 1;
+}
+
+void launch_pvalues(int64_t n, const double* stat, const double* nmin, int K, double nmax, const int64_t* bin_off,
+                    const double* sorted, double* pvalue, int64_t* nsim, cudaStream_t st) {
+  if (n == 0) return;
+  k2_pvalues<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, stat, nmin, K, nmax, bin_off, sorted, pvalue, nsim);
+  CMB_CUDA(cudaGetLastError());
 }
 
 int launch_inter_diagonal(const TilesLaunch& L, cudaStream_t st) {

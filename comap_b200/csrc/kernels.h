@@ -112,6 +112,9 @@ struct TilesLaunch {
   int dist_is_stat = 0;
 };
 int launch_tiles(const TilesLaunch& L, cudaStream_t st);
+// PValue / Nsim of rows whose Stat / Nmin columns are already resident (no tile recomputation)
+void launch_pvalues(int64_t n, const double* stat, const double* nmin, int K, double nmax, const int64_t* bin_off,
+                    const double* sorted, double* pvalue, int64_t* nsim, cudaStream_t st);
 int launch_inter_diagonal(const TilesLaunch& L, cudaStream_t st); // site i of data set 1 with site i of data set 2
 int64_t compact_positions(int64_t n, const uint8_t* keep, DevBuf& tmp, int64_t** pos_out, cudaStream_t st);
 template <class T>

@@ -23,7 +23,7 @@ SYMBOLS = [
     "cmb_simulate", "cmb_null_intra", "cmb_null_intra_from_alignments", "cmb_null_samples_dev",
     "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
-    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates",
+    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates", "cmb_set_async",
 ]
 
 
@@ -155,6 +155,10 @@ class Context:
                                                           _p(sim1, C.c_uint8), _p(sim2, C.c_uint8), K,
                                                           C.c_double(nmax), _d(raw)))
         return raw
+
+    def set_async(self, on=True):
+        """null_intra(K=0) returns without waiting for the device (order consumers with sync())."""
+        self._chk(self.lib.cmb_set_async(self.h, int(on)))
 
     def null_samples_dev(self):
         s = C.c_void_p(); m = C.c_void_p(); n = C.c_int64()

@@ -410,6 +410,11 @@ int cmb_load_vectors(cmb_ctx* ctx, const double* n_in, double* norm) {
   CMB_CATCH
 }
 
+int cmb_set_async(cmb_ctx* ctx, int32_t on) {
+  ctx->c.async_null = on != 0;
+  return 0;
+}
+
 int cmb_profile_enable(cmb_ctx* ctx, int32_t on) {
   ctx->c.prof.enabled = on != 0;
   return 0;

@@ -140,7 +140,7 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
     off += n;
   }
   if (K > 0) null_load(c, ns.stat.as<double>(), ns.nmin.as<double>(), total, K, nmax);
-  else CMB_CUDA(cudaStreamSynchronize(c.stream));
+  else if (!c.async_null) CMB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
 

@@ -80,6 +80,7 @@ struct Context {
   bool have_meanvec = false;
   const double* mean_vector();  // device pointer [B]; computes it (and corr_mean / corr_sd) when stale
   Profile prof;
+  bool async_null = false; // cmb_set_async: cmb_null_intra with K = 0 returns without waiting for the device
 
   void require_tree_model() const;
   void ensure_streams();

@@ -133,6 +133,11 @@ int cmb_null_intra_from_alignments(cmb_ctx* ctx, int32_t stat_id, int32_t rep_cp
                                    const uint8_t* sim1, const uint8_t* sim2, int32_t K,
                                    double nmax, double* raw);
 
+/* on = 1: cmb_null_intra with K = 0 (samples left unbinned for an exchange) only enqueues its
+ * work and returns; the caller orders later consumers with cmb_sync.  Lets a second context on
+ * another stream map and score the observed alignment while the null replicates run. */
+int cmb_set_async(cmb_ctx* ctx, int32_t on);
+
 /* Multi-GPU exchange step: the unbinned null samples of this context's shard live in
  * device memory; export them, all-gather with NCCL, then load the union into every rank. */
 int cmb_null_samples_dev(cmb_ctx* ctx, const double** stat_dev, const double** nmin_dev,

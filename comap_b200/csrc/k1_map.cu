@@ -831,7 +831,10 @@ bool try_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStre
 template <int A>
 void run_up(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if constexpr (A == 4) return launch_map_up_mma(m, b, s, st);
-  else if (!try_up<A, 1, 320, 1>(m, b, s, st))
+  // proteins: one site group per CTA (C class warps + 2 producers, <= 255 registers).  Two groups
+  // (320 threads, 168 registers) spill 1 KB per thread of the five live 20-vectors: 12.3 vs 4.9 ms
+  // per 20 000 sites at config 5.
+  else if (!try_up<A, 1, 192, 1>(m, b, s, st) && !try_up<A, 1, 320, 1>(m, b, s, st))
     fail("mapping up pass: no launch shape fits shared memory for A = %d, C = %d", A, m.C);
 }
 

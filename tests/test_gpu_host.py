@@ -251,6 +251,32 @@ def test_candidate_groups_table_equals_c_abi_run(myo):
     ctx.close()
 
 
+def test_rna_example_with_its_own_option_file(tmp_path):
+    """BASELINE configs[2]: examples/RNA/BacteriaSSU/options.comap unchanged -- GTR + Invariant(Gamma4)
+    (five rate classes incl. a rate-0 class), 760 complete variable sites x 40 taxa, pairwise
+    correlation with a 100 x 1000 null -- against the oracle on the inputs the binary used."""
+    from comap_b200 import build as b
+    b.build_host()
+    tmp = str(tmp_path)
+    write_fixture(tmp, "bacteria_ssu")
+    out = run(tmp, "param=options.comap", "--seed=5")
+    assert "Bye bye" in out
+    hdr, rows = table(os.path.join(tmp, "Bacteria_SSU.sged"))
+    assert hdr == ["Group", "Stat", "RCmin", "PRmin", "Nmin", "PValue", "Nsim"] and len(rows) == 760 * 759 // 2
+    p, o = dry_run(BIN, tmp, "param=options.comap")
+    c = decode(o); c["parent"] = c["parent"].astype(np.int32)
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    op = O.pairs("correlation", q["n"], q["norm"], q["post_rate"], q["rate_class"])
+    st = np.array([float(x[1]) for x in rows])           # NaN rows: sites without any expected substitution
+    ok = ~np.isnan(op["stat"])
+    assert np.array_equal(np.isnan(st), ~ok)
+    assert np.allclose(st[ok], op["stat"][ok], rtol=2e-5, atol=2e-6)
+    assert [int(x[2]) for x in rows] == op["rcmin"].tolist()
+    pv = np.array([float(x[5]) if x[5] != "NA" else np.nan for x in rows])
+    assert np.nanmin(pv) > 0 and np.nanmax(pv) <= 1 and (~np.isnan(pv)).mean() > 0.5
+    assert sum(int(x[6]) for x in rows[:2000]) > 0
+
+
 def test_error_exit_code_and_message(myo):
     tmp, _ = myo
     p = subprocess.run([BIN] + COMMON + ["analysis=pairwise", "statistic=Compensation"], cwd=tmp, capture_output=True, text=True)

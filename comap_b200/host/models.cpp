@@ -129,6 +129,10 @@ Model make_model(const std::string& desc, const Alphabet& alpha, const std::stri
   // Bio++ tables are not available offline -- drop e.g. lg08.dat next to it to enable LG08)
   std::string file = n == "jtt92" ? "jtt92_dcmut.dat" : n + ".dat";
   std::string path = data_dir + "/" + file;
+  if (n == "empirical") { // Bio++: model = Empirical(name=..., file=<PAML .dat>)
+    path = get_string(p.args, "file", "none");
+    if (path == "none") throw Error("model Empirical(...) needs file=<PAML exchangeability file>");
+  }
   try {
     read_paml(path, m);
   } catch (const Error&) {

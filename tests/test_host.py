@@ -97,6 +97,20 @@ def test_bacteria_rna_gtr_invariant(binary, tmp_path):
         assert "".join("ACGU"[c] for c in d["codes"][k]) == "".join(s[c - 1] for c in d["coords"])
 
 
+def test_empirical_model_from_a_paml_file(binary, tmp_path):
+    """model = Empirical(file=...) (Bio++ syntax) reads a PAML exchangeability file: the bundled JTT92
+    table through that route equals model = JTT92."""
+    write_fixture(str(tmp_path), "myoglobin")
+    dat = os.path.join(os.path.dirname(os.path.dirname(binary)), "data", "jtt92_dcmut.dat")
+    common = ["param=comap.bpp", "input.sequence.file=Myoglobin.aln.sel.mase", "input.tree.file=Myo.dnd"]
+    p1, o1 = dry_run(binary, str(tmp_path), *common, "model=JTT92")
+    p2, o2 = dry_run(binary, str(tmp_path), *common, "model=Empirical(name=myJTT, file=%s)" % dat)
+    assert p1.returncode == 0 and p2.returncode == 0, p2.stdout
+    assert o1["Q"] == o2["Q"] and o1["pi"] == o2["pi"]
+    p3, _ = dry_run(binary, str(tmp_path), *common, "model=LG08")
+    assert p3.returncode == 255 and "lg08.dat" in p3.stdout
+
+
 def test_mase_site_selection_srk(binary, tmp_path):
     write_fixture(str(tmp_path), "srk")
     p, out = dry_run(binary, str(tmp_path), "alphabet=Protein", "input.sequence.file=SRK.mase",

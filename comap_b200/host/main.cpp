@@ -219,7 +219,10 @@ void dry_run_dump(const Inputs& in) {
   for (uint32_t m : in.code_mask) std::cout << ' ' << m;
   std::cout << "\nDRYRUN codes";
   for (uint8_t c : in.codes) std::cout << ' ' << (int)c;
-  std::cout << "\nDRYRUN count_method " << in.count_method << std::endl;
+  std::cout << "\nDRYRUN count_method " << in.count_method;
+  std::cout << "\nDRYRUN weights";
+  for (double x : in.weights) std::cout << ' ' << x;
+  std::cout << std::endl;
 }
 
 int stat_id_of(const Params& P, const Inputs& in) {
@@ -372,6 +375,14 @@ int main(int argc, char** argv) {
     prepare(in, argv[0]);
     if (dry) {
       dry_run_dump(in);
+      if (get_path(P, "input.sequence.file2", "none") != "none") { // second data set, same dump after a marker
+        const Params P2 = second_data_set_params(P);
+        Inputs in2;
+        in2.app = in.app;
+        prepare(in2, argv[0], &P2, &in.tree);
+        std::cout << "DRYRUN second_data_set 1" << std::endl;
+        dry_run_dump(in2);
+      }
       return 0;
     }
     const int64_t S = (int64_t)in.cols.size();

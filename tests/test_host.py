@@ -111,6 +111,30 @@ def test_empirical_model_from_a_paml_file(binary, tmp_path):
     assert p3.returncode == 255 and "lg08.dat" in p3.stdout
 
 
+def test_count_weights_and_second_data_set_options(binary, tmp_path):
+    """weight=Diff(index1=Volume, symmetrical=no) (examples/simple/ProteinPairCompensation/comap.bpp:48) and the
+    KEY2 options of a second data set (CoETools::readData suffix, CoETools.cpp:91-93; CoMap.cpp:236-262)."""
+    write_fixture(str(tmp_path), "myoglobin")
+    common = ["param=comap.bpp", "input.sequence.file=Myoglobin.aln.sel.mase", "input.tree.file=Myo.dnd"]
+    p, o = dry_run(binary, str(tmp_path), *common, "nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))")
+    assert p.returncode == 0, p.stdout
+    W = np.array(o["weights"], dtype=float).reshape(20, 20)
+    assert W[0, 1] == 124 - 31 and W[1, 0] == 31 - 124 and np.array_equal(W, -W.T)   # A -> R gains 93 A^3 (Grantham 1974)
+    p, o = dry_run(binary, str(tmp_path), *common, "nijt=Decomposition(weight=Diff(index1=Charge, symmetrical=yes))")
+    W = np.array(o["weights"], dtype=float).reshape(20, 20)
+    assert np.array_equal(W, W.T) and W[1, 3] == 2 and o["count_method"] == ["1"]        # R(+1) <-> D(-1)
+    p, o = dry_run(binary, str(tmp_path), *common)
+    assert o["weights"] == []
+    # second data set: same files, all sites instead of the complete ones; the tree is copied
+    p = subprocess.run([binary] + common + ["input.sequence.file2=Myoglobin.aln.sel.mase", "input.sequence.sites_to_use2=all",
+                                            "--dry-run"], cwd=str(tmp_path), capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout
+    first, second = p.stdout.split("DRYRUN second_data_set 1")
+    get = lambda txt, key: [ln.split()[2:] for ln in txt.split("\n") if ln.startswith("DRYRUN " + key + " ")][0]
+    assert get(first, "parent") == get(second, "parent") and get(first, "Q") == get(second, "Q")
+    assert len(get(second, "coords")) > len(get(first, "coords")) == 129
+
+
 def test_mase_site_selection_srk(binary, tmp_path):
     write_fixture(str(tmp_path), "srk")
     p, out = dry_run(binary, str(tmp_path), "alphabet=Protein", "input.sequence.file=SRK.mase",

@@ -1,4 +1,6 @@
-// K1: per-site probabilistic substitution mapping on sm_100a.
+// K1 for proteins (A = 20): per-site probabilistic substitution mapping on sm_100a, thread per
+// site.  (Nucleotides, A = 4, run on the FP64 tensor-core kernels of k1_mma.cu; this file also
+// holds the class-likelihood epilogue k1_finish and the [B][site] <-> [site][B] transpose.)
 //
 // Replaces DRHomogeneousTreeLikelihood::initialize (Felsenstein post-order + pre-order
 // conditional likelihoods) followed by LegacySubstitutionMappingTools::
@@ -12,14 +14,16 @@
 //     class terms through shared memory in a fixed order (deterministic, no atomics);
 //   * the tree walk is a precompiled op stream (schedule.cpp) whose records carry the
 //     branch transition matrices P_c(b) and reward matrices W_c(b) = p_c P o n; the CTA
-//     streams it through shared memory with double-buffered TMA bulk copies, so table
-//     reads are warp-uniform 128-bit shared loads;
+//     streams it through shared memory with double-buffered TMA bulk copies;
 //   * down pass: each inner node's partial is written to HBM exactly once
-//     ([slot][class*A+state][site], site contiguous -> coalesced); the message of the
-//     larger child waits on a <= log2(T)-deep per-thread stack;
+//     ([256-site block][slot][class*A+state][site], site contiguous -> coalesced); the message
+//     of the larger child waits on a <= log2(T)-deep per-thread stack; two CTAs per SM at 128
+//     registers (a register cache of the stack top costs 2 x 20 doubles and halves occupancy);
 //   * up pass: each partial is read exactly once; both children of a node are expanded
 //     together, the contraction sum_x Up[x] sum_y W[x][y] D[y] is fused, and the vector
-//     entry is written as out[branch][site] (site contiguous);
+//     entry is written as out[branch][site] (site contiguous); producer warps stream tables and
+//     partials through shared-memory rings; one site group per CTA at 254 registers (five live
+//     20-vectors per thread: two groups at 168 registers spill 1 KB per thread);
 //   * nothing is accumulated with atomics: results are deterministic.
 #include <algorithm>
 #include <cstdlib>

@@ -1,26 +1,31 @@
-// K1 up pass + contraction for nucleotides (A = 4) on the FP64 tensor cores (DMMA m8n8k4).
+// K1 for nucleotides (A = 4) on the FP64 tensor cores (DMMA m8n8k4): down pass, up pass +
+// contraction.
 //
-// Same contract as k1_up in k1_map.cu (Bio++ computeSubtreeLikelihoodPrefix +
-// LegacySubstitutionMappingTools::computeSubstitutionVectors; reference call sites
-// CoETools.cpp:395-397, AnalysisTools.cpp:597-611), different
-// machine mapping.  The thread-per-site kernel was bound by shared-memory bandwidth: every
-// lane re-reads every 4x4 table as warp-uniform broadcast loads (ncu r1f: LSU 66 %, FP64
-// pipe 21 %).  Here a warp owns 8*NG sites and ALL rate classes; lane = (site s = lane / 4,
-// state q = lane % 4) holds ONE double per 4-vector, and every 4x4 matrix-vector product of
-// 8 sites is one DMMA.8x8x4 whose B operand (the table) is one double per lane:
+// Contract: Bio++ DRHomogeneousTreeLikelihood::initialize (computeSubtreeLikelihoodPostfix /
+// Prefix) + LegacySubstitutionMappingTools::computeSubstitutionVectors; reference call sites
+// CoETools.cpp:209,358-359,395-397, AnalysisTools.cpp:592-611; SURVEY.md s3.3, s8 a1/a4.
+// The first, thread-per-site design (now k1_map.cu, proteins only) was bound by shared-memory
+// bandwidth and issue slots: every lane re-read every 4x4 table as warp-uniform broadcast loads
+// (ncu r1f: LSU 66 %, FP64 pipe 21 %).  Here a warp owns 8*NG sites and ALL rate classes; lane =
+// (site s = lane / 4, state q = lane % 4) holds ONE double per 4-vector, and every 4x4
+// matrix-vector product of 8 sites is one DMMA.8x8x4 whose B operand (the table) is one double
+// per lane:
 //   MMA1/2  D_child (8 sites x 4) x [P | W]      -> lane (s, q): S[q] = (P D)[q], T[q] = (W D)[q]
 //   U_a = G o S_b, U_b = G o S_a;   n_a += U_a . T_a  (per lane product, summed over classes
-//   in registers, then over q with two shuffle stages per node)
+//   in registers, then over q with a two-stage transposing shuffle reduction per node)
 //   MMA3/4  U (8 sites x 4) x P^T                -> lane (s, q): message to an inner child
-// B fragments come precomputed in the op stream (schedule.cpp build_up_mma_stream), so a
-// table costs 256 B of shared-memory reads per warp instead of 32 broadcast rows.  Tips need
-// no special case: their partial is the 0/1 state mask.  DMMA.8x8x4 runs at the FP64 pipe's
-// full rate (tools/dmmabench: 37 TFLOP/s, 4 cycles per SM), so the kernel trades an issue /
-// LSU bound for the FP64 pipe bound: ~3 DMMA per (node, class, 8 sites).
+// B fragments come precomputed in the op stream (schedule.cpp build_up_mma_stream /
+// build_down_mma_stream), so a table costs 256 B of shared-memory reads per warp instead of 32
+// broadcast rows.  Resolved tips are column picks from the raw 4x4 tables (conflict-free);
+// ambiguity codes fall back to 0/1 mask partials through the DMMA.  Node bodies are specialised
+// by what the two children are, so the C x NG independent DMMA chains of a node interleave.
+// DMMA.8x8x4 runs at the FP64 pipe's full rate (tools/dmmabench: 37 TFLOP/s, 4 cycles per SM):
+// ~2-3 DMMA per (node, class, 8 sites).
 //
-// Partials: [128-site chunk][slot][class][site][state] -- a lane reads its double at
-// consecutive addresses (256 B per DMMA A operand) and one TMA bulk copy moves a child's
-// whole chunk (C * 4 KB) into the stage ring.
+// Partials: [128-site chunk][slot][class][site][state] -- a lane reads / writes its double at
+// consecutive addresses (256 B per DMMA A operand) and one TMA bulk copy moves a child's whole
+// chunk (C * 4 KB) into the stage ring.  Measured on B200 at config 4 (517 k sites): down 4.2 ms
+// (5.1 TB/s of stores), up 10.8 ms.
 #include <algorithm>
 #include <cstdlib>
 #include <type_traits>

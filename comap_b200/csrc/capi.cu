@@ -129,6 +129,17 @@ const double* Context::mean_vector() {
   return d_meanvec.as<double>();
 }
 
+const double* Context::mi_counts() {
+  if (!mapped) fail("statistic MI needs a mapped alignment (cmb_map)");
+  if (!have_mi_count) {
+    mi_count.reserve(sizeof(double) * S_pad);
+    launch_count_ge(tree.B, S, S_pad, d_out.as<double>(), mi_threshold, mi_count.as<double>(), stream);
+    prof.total_launches += 1;
+    have_mi_count = true;
+  }
+  return mi_count.as<double>();
+}
+
 void Context::prof_begin(const char* name) {
   if (!prof.enabled) return;
   cudaEvent_t a, b;
@@ -243,7 +254,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
                     &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm,
-                    &c.d_meanvec, &c.corr_mean, &c.corr_sd};
+                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count};
   for (DevBuf* b : bufs) b->release();
   c.down_stream.release();
   c.up_stream.release();
@@ -356,6 +367,7 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   c.pairs_norm.reserve(sizeof(double) * Sp);
   launch_prep(B, S, Sp, b.out, nullptr, c.pairs_mean.as<double>(), c.pairs_sd.as<double>(), c.pairs_norm.as<double>(), c.stream);
   c.have_meanvec = false;
+  c.have_mi_count = false;
   c.prof.total_launches += 1;
   c.h_norm.resize(S);
   CMB_CUDA(cudaMemcpyAsync(c.h_norm.data(), c.pairs_norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
@@ -397,6 +409,7 @@ int cmb_load_vectors(cmb_ctx* ctx, const double* n_in, double* norm) {
               c.pairs_norm.as<double>(), c.stream);
   c.prof.total_launches += 2;
   c.have_meanvec = false;
+  c.have_mi_count = false;
   CMB_CUDA(cudaMemcpyAsync(c.h_norm.data(), c.pairs_norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
   CMB_CUDA(cudaStreamSynchronize(c.stream));
   c.max_norm = 0.;
@@ -408,6 +421,12 @@ int cmb_load_vectors(cmb_ctx* ctx, const double* n_in, double* norm) {
   c.pairs_rows = -1;
   for (auto& o : c.pairs_col_off) o = -1;
   CMB_CATCH
+}
+
+int cmb_set_mi_threshold(cmb_ctx* ctx, double threshold) {
+  ctx->c.mi_threshold = threshold;
+  ctx->c.have_mi_count = false;
+  return 0;
 }
 
 int cmb_set_async(cmb_ctx* ctx, int32_t on) {

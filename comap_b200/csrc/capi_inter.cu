@@ -83,7 +83,7 @@ int cmb_pairs_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, const cmb_fil
   Context& c = ctx1->c;
   Context& d = ctx2->c;
   CMB_CUDA(cudaSetDevice(c.device));
-  if (stat_id < 0 || stat_id > CMB_STAT_CORRECTED_CORRELATION) fail("unknown statistic id %d", stat_id);
+  if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
   check_pair(c, d, "cmb_pairs_inter");
   if (!c.mapped || !d.mapped) fail("cmb_pairs_inter: call cmb_map on both data sets first");
   const int64_t S1 = c.S, S2 = d.S;
@@ -125,6 +125,11 @@ int cmb_pairs_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, const cmb_fil
   L.sd2 = corrected ? d.corr_sd.as<double>() : d.pairs_sd.as<double>();
   L.norm2 = d.pairs_norm.as<double>(); L.post_rate2 = d.d_pr.as<double>(); L.rate_class2 = d.d_rc.as<int32_t>();
   L.mv2 = mv2;
+  if (stat_id == CMB_STAT_MI) {
+    d.mi_threshold = c.mi_threshold; d.have_mi_count = false; // one statistic object upstream: one threshold
+    L.thr = c.mi_threshold; L.mean = c.mi_counts(); L.mean2 = d.mi_counts();
+    order_after(c.stream, d.stream);
+  }
   if (f) {
     L.min_rate_class = f->min_rate_class; L.max_rate_class_diff = f->max_rate_class_diff;
     L.min_rate = f->min_rate; L.max_rate_diff = f->max_rate_diff; L.min_stat = f->min_stat;
@@ -178,7 +183,7 @@ int cmb_null_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, uint64_t seed,
   Context& c = ctx1->c;
   Context& d = ctx2->c;
   CMB_CUDA(cudaSetDevice(c.device));
-  if (stat_id < 0 || stat_id > CMB_STAT_CORRECTED_CORRELATION) fail("unknown statistic id %d", stat_id);
+  if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
   if (rep_ram < 1 || rep_cpu < 0) fail("cmb_null_inter: bad replicate counts");
   if (!raw) fail("cmb_null_inter: raw output buffer required");
   check_pair(c, d, "cmb_null_inter");
@@ -222,7 +227,7 @@ int cmb_null_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, uint64_t seed,
     d.run_map(b2, true, true);
     order_after(c.stream, d.stream);
     c.prof_begin("null_pairs");
-    launch_paired(corrected ? 0 : stat_id, B, n, np1, np2, b1.out, b2.out, mv1, mv2, c.null.stat.as<double>() + off,
+    launch_paired(corrected ? 0 : stat_id, c.mi_threshold, B, n, np1, np2, b1.out, b2.out, mv1, mv2, c.null.stat.as<double>() + off,
                   c.null.nmin.as<double>() + off, c.stream);
     c.prof_end(1);
     c.scratch.reserve(sizeof(double) * 4 * (size_t)n);
@@ -325,7 +330,7 @@ void group_stats(Context& c, int stat_id, const double* out, int64_t n_pad, cons
   if (!pairs.empty()) {
     CMB_CUDA(cudaMemcpyAsync(sb, pairs.data(), pairs.size() * sizeof(int2), cudaMemcpyHostToDevice, c.stream));
     const bool corrected = stat_id == CMB_STAT_CORRECTED_CORRELATION;
-    launch_pair_list(corrected ? 0 : stat_id, B, n_pad, out, corrected ? mv : nullptr, (const int2*)sb, (int64_t)pairs.size(),
+    launch_pair_list(corrected ? 0 : stat_id, c.mi_threshold, B, n_pad, out, corrected ? mv : nullptr, (const int2*)sb, (int64_t)pairs.size(),
                      (double*)(sb + o_stat), c.stream);
     c.prof.total_launches += 1;
     CMB_CUDA(cudaMemcpyAsync(vals.data(), sb + o_stat, pairs.size() * 8, cudaMemcpyDeviceToHost, c.stream));
@@ -353,7 +358,7 @@ extern "C" int cmb_candidates(cmb_ctx* ctx, int32_t stat_id, int32_t n_groups, c
   CMB_TRY
   Context& c = ctx->c;
   CMB_CUDA(cudaSetDevice(c.device));
-  if (stat_id < 0 || stat_id > CMB_STAT_CORRECTED_CORRELATION) fail("unknown statistic id %d", stat_id);
+  if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
   if (!c.mapped) fail("cmb_candidates: call cmb_map first");
   if (n_groups < 1) fail("ERROR!!! No group can be tested!"); // CoMap.cpp:679-680
   if (rep_ram < 1 || min_sim < 1) fail("cmb_candidates: bad simulation counts");

@@ -25,7 +25,7 @@ struct cmb_ctx { Context c; };
 namespace {
 
 void check_stat(int stat_id) {
-  if (stat_id < 0 || stat_id > CMB_STAT_CORRECTED_CORRELATION) fail("unknown statistic id %d", stat_id);
+  if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
 }
 
 // Bytes of device memory one simulated site needs through simulate -> map x2 -> paired.
@@ -125,7 +125,7 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
       c.run_map(b[k], true, sim1 == nullptr);
     }
     c.prof_begin("null_pairs");
-    launch_paired(corrected ? 0 : stat_id, B, n, n_pad, n_pad, b[0].out, b[1].out, mv, mv, ns.stat.as<double>() + off, ns.nmin.as<double>() + off,
+    launch_paired(corrected ? 0 : stat_id, c.mi_threshold, B, n, n_pad, n_pad, b[0].out, b[1].out, mv, mv, ns.stat.as<double>() + off, ns.nmin.as<double>() + off,
                   c.stream);
     c.prof_end(1);
     if (raw) {
@@ -385,6 +385,10 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
   TilesLaunch L;
   L.stat_id = stat_id; L.B = c.tree.B; L.S = S; L.S_pad = c.S_pad; L.out = c.d_out.as<double>();
   L.mean = c.pairs_mean.as<double>(); L.sd = c.pairs_sd.as<double>(); L.norm = c.pairs_norm.as<double>();
+  if (stat_id == CMB_STAT_MI) { // the tile kernel reads the per-site category-1 counts through `mean`
+    L.thr = c.mi_threshold;
+    L.mean = c.mi_counts();
+  }
   if (stat_id == CMB_STAT_CORRECTED_CORRELATION) { // correlation of the mean-vector-corrected rows
     L.mv = c.mean_vector();
     L.stat_id = CMB_STAT_CORRELATION;

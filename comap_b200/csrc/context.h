@@ -79,6 +79,11 @@ struct Context {
   DevBuf d_meanvec, corr_mean, corr_sd;
   bool have_meanvec = false;
   const double* mean_vector();  // device pointer [B]; computes it (and corr_mean / corr_sd) when stale
+  // statistic=MI(threshold=..): per-site number of branches whose entry reaches the threshold
+  double mi_threshold = 0.99;
+  DevBuf mi_count;
+  bool have_mi_count = false;
+  const double* mi_counts();    // device pointer [S_pad] of the mapped alignment; built on first use
   Profile prof;
   bool async_null = false; // cmb_set_async: cmb_null_intra with K = 0 returns without waiting for the device
 

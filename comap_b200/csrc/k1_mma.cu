@@ -56,9 +56,26 @@ constexpr int kSG = kChunkSites; // sites per CTA
 enum : int { kInner = 0, kTip = 1, kCherry = 2 };
 
 struct NodePtrs {       // record and stage pointers of one node, lane offsets NOT applied
-  const double *F1a, *F1b, *F3a, *F3b, *Pxa, *Pxb, *Rta, *Rtb; // tables (shared memory)
+  const double* tab;                               // first table of the record (shared memory)
   const double *blk_a, *blk_b;                     // partial chunks of inner children
 };
+// Offsets (in doubles) of a record's tables given what the two children are (schedule.cpp
+// build_up_mma_stream): F1a[C] F1b[C] | F3a[C] F3b[C] (non-tips) | leaf tables of cherries | raw
+// P, W of tips.  Compile-time constants inside the specialised node bodies: eight pointers less
+// to keep in (or spill from) 96 registers.
+struct RecLayout { int F1a, F1b, F3a, F3b, Pxa, Pxb, Rta, Rtb; };
+__host__ __device__ constexpr RecLayout rec_layout(int C, int ka, int kb) {
+  RecLayout r{};
+  r.F1a = 0;
+  r.F1b = C * 32;
+  r.F3a = 2 * C * 32;
+  r.F3b = r.F3a + (ka != 1 /* kTip */ ? C * 32 : 0);
+  r.Pxa = r.F3b + (kb != 1 ? C * 32 : 0);
+  r.Pxb = r.Pxa + (ka == 2 /* kCherry */ ? 2 * C * 16 : 0);
+  r.Rta = r.Pxb + (kb == 2 ? 2 * C * 16 : 0);
+  r.Rtb = r.Rta + (ka == 1 ? 2 * C * 16 : 0);
+  return r;
+}
 
 // One node, every leaf state below it resolved (no ambiguity codes in this warp's sites):
 // straight-line code over the classes so the C x NG independent DMMA chains interleave.
@@ -71,6 +88,7 @@ __device__ __forceinline__ void node_fast(const NodePtrs& p, int lane, const int
                                           double (*push)[NG], const double (*pop)[NG], double (&acc_a)[NG],
                                           double (&acc_b)[NG]) {
   const int q = lane & 3;
+  constexpr RecLayout L = rec_layout(C, KA, KB);
 #pragma unroll
   for (int c = 0; c < C; c++) {
     double Sa[NG], Ta[NG], Sb[NG], Tb[NG];
@@ -97,8 +115,8 @@ __device__ __forceinline__ void node_fast(const NodePtrs& p, int lane, const int
         for (int g = 0; g < NG; g++) dmma(S[g], T[g], D[g], f);
       }
     };
-    child(std::integral_constant<int, KA>(), p.F1a, p.blk_a, p.Pxa, p.Rta, sa, sa2, Sa, Ta);
-    child(std::integral_constant<int, KB>(), p.F1b, p.blk_b, p.Pxb, p.Rtb, sb, sb2, Sb, Tb);
+    child(std::integral_constant<int, KA>(), p.tab + L.F1a, p.blk_a, p.tab + L.Pxa, p.tab + L.Rta, sa, sa2, Sa, Ta);
+    child(std::integral_constant<int, KB>(), p.tab + L.F1b, p.blk_b, p.tab + L.Pxb, p.tab + L.Rtb, sb, sb2, Sb, Tb);
     double Ua[NG], Ub[NG];
 #pragma unroll
     for (int g = 0; g < NG; g++) {
@@ -110,15 +128,15 @@ __device__ __forceinline__ void node_fast(const NodePtrs& p, int lane, const int
     double unused;
     if constexpr (KA != kTip) {
       if constexpr (KB != kTip) { // both expanded later: b's message waits on the stack
-        const double f3 = p.F3b[c * 32 + lane];
+        const double f3 = p.tab[L.F3b + c * 32 + lane];
 #pragma unroll
         for (int g = 0; g < NG; g++) dmma(push[c][g], unused, Ub[g], f3);
       }
-      const double f3 = p.F3a[c * 32 + lane];
+      const double f3 = p.tab[L.F3a + c * 32 + lane];
 #pragma unroll
       for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ua[g], f3);
     } else if constexpr (KB != kTip) {
-      const double f3 = p.F3b[c * 32 + lane];
+      const double f3 = p.tab[L.F3b + c * 32 + lane];
 #pragma unroll
       for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ub[g], f3);
     } else if (pop) {
@@ -136,6 +154,7 @@ __device__ __forceinline__ void node_masks(const NodePtrs& p, int lane, int kind
                                         double (&G)[C][NG], double (*push)[NG], const double (*pop)[NG],
                                         double (&acc_a)[NG], double (&acc_b)[NG]) {
   const int q = lane & 3;
+  const RecLayout L = rec_layout(C, kind_a, kind_b);
 #pragma unroll
   for (int c = 0; c < C; c++) {
     double Da[NG], Db[NG];
@@ -162,9 +181,9 @@ __device__ __forceinline__ void node_masks(const NodePtrs& p, int lane, int kind
         }
       }
     };
-    child(kind_a, p.blk_a, ma, ma2, p.Pxa, Da);
-    child(kind_b, p.blk_b, mb, mb2, p.Pxb, Db);
-    const double fa = p.F1a[c * 32 + lane], fb = p.F1b[c * 32 + lane];
+    child(kind_a, p.blk_a, ma, ma2, p.tab + L.Pxa, Da);
+    child(kind_b, p.blk_b, mb, mb2, p.tab + L.Pxb, Db);
+    const double fa = p.tab[L.F1a + c * 32 + lane], fb = p.tab[L.F1b + c * 32 + lane];
     double Sa[NG], Ta[NG], Sb[NG], Tb[NG], Ua[NG], Ub[NG];
 #pragma unroll
     for (int g = 0; g < NG; g++) dmma(Sa[g], Ta[g], Da[g], fa);
@@ -180,15 +199,15 @@ __device__ __forceinline__ void node_masks(const NodePtrs& p, int lane, int kind
     double unused;
     if (kind_a != kTip) {
       if (kind_b != kTip) {
-        const double f3 = p.F3b[c * 32 + lane];
+        const double f3 = p.tab[L.F3b + c * 32 + lane];
 #pragma unroll
         for (int g = 0; g < NG; g++) dmma(push[c][g], unused, Ub[g], f3);
       }
-      const double f3 = p.F3a[c * 32 + lane];
+      const double f3 = p.tab[L.F3a + c * 32 + lane];
 #pragma unroll
       for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ua[g], f3);
     } else if (kind_b != kTip) {
-      const double f3 = p.F3b[c * 32 + lane];
+      const double f3 = p.tab[L.F3b + c * 32 + lane];
 #pragma unroll
       for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ub[g], f3);
     } else if (pop) {
@@ -292,14 +311,7 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
     const int kind_a = (flags & kUpTipA) ? kTip : (flags & kUpCherryA) ? kCherry : kInner;
     const int kind_b = (flags & kUpTipB) ? kTip : (flags & kUpCherryB) ? kCherry : kInner;
     NodePtrs p;
-    p.F1a = reinterpret_cast<const double*>(stage + 32);
-    p.F1b = p.F1a + C * 32;
-    p.F3a = p.F1b + C * 32;
-    p.F3b = p.F3a + (kind_a != kTip ? C * 32 : 0);
-    p.Pxa = p.F3b + (kind_b != kTip ? C * 32 : 0); // raw leaf tables of cherry a: P1[C], P2[C]
-    p.Pxb = p.Pxa + (kind_a == kCherry ? 2 * C * 16 : 0);
-    p.Rta = p.Pxb + (kind_b == kCherry ? 2 * C * 16 : 0); // raw P[C], W[C] of tip a
-    p.Rtb = p.Rta + (kind_a == kTip ? 2 * C * 16 : 0);
+    p.tab = reinterpret_cast<const double*>(stage + 32);
     // h1.y / h1.z: offsets of the tip rows and of the first stored child's chunk in this stage
     const unsigned char* ts = stage + h1.y + wsite + s8; // tip code of (row, group g): ts[row * kSG + 8 g]
     p.blk_a = reinterpret_cast<const double*>(stage + h1.z) + (size_t)wsite * 4;
@@ -398,6 +410,8 @@ bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   const size_t smem = fixed + (size_t)up.n_stages * stage;
   constexpr int threads = 32 * (kSG / (8 * NG) + 1);
   CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (getenv("CMB_UP_CARVEOUT"))
+    CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CMB_UP_CARVEOUT"))));
   k1_up_mma<NG, C, MINB><<<(unsigned)(b.n_pad / kSG), threads, smem, st>>>(m, b, up);
   CMB_CUDA(cudaGetLastError());
   return true;

@@ -39,11 +39,31 @@ __device__ __forceinline__ double add_(double a, double b) { return __dadd_rn(a,
 
 // mv (nullable): the observed alignment's mean vector, subtracted from both sites before a
 // correlation (CorrectedCorrelationStatistic, Statistics.h:176-205); the norms stay raw.
-__global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* __restrict__ o1,
+// DiscreteMutualInformationStatistic with the bounds {0, threshold, 10000} of statistic=MI(threshold=..)
+// (CoETools.cpp:590-595, Statistics.h:307-329): every branch entry becomes the category [v >= threshold]
+// and the statistic is [Bio++, from memory] VectorTools::miDiscrete(c1, c2, base = 2.7182818):
+//   sum over the occupied cells (k1, k2) in key order of  (n12 / n) * log(n12 * n / (n1[k1] * n2[k2])) / log(base).
+// n1x / n1y: branches of the first / second site in category 1, n11: in category 1 for both.
+__device__ __forceinline__ double mi_binary(double n, double n1x, double n1y, double n11) {
+  const double cx[2] = {n - n1x, n1x}, cy[2] = {n - n1y, n1y};
+  const double c12[2][2] = {{n - n1x - n1y + n11, n1y - n11}, {n1x - n11, n11}};
+  const double lb = log(2.7182818);
+  double s = 0.;
+#pragma unroll
+  for (int a = 0; a < 2; a++)
+#pragma unroll
+    for (int b = 0; b < 2; b++)
+      if (c12[a][b] > 0.) s = add_(s, mul_(c12[a][b] / n, log(mul_(c12[a][b], n) / mul_(cx[a], cy[b]))) / lb);
+  return s;
+}
+
+template <int STAT>
+__global__ void __launch_bounds__(128) k2_paired(double thr, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* __restrict__ o1,
                           const double* __restrict__ o2, const double* __restrict__ mv, const double* __restrict__ mv2,
                           double* __restrict__ stat, double* __restrict__ nmin) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  constexpr int stat_id = STAT;
   const double nb = (double)B;
   double sx = 0., sy = 0., qx = 0., qy = 0., sxy = 0., s3 = 0., cnt = 0.;
   for (int b = 0; b < B; b++) {
@@ -60,9 +80,11 @@ __global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t 
     if (stat_id == 2) sxy = add_(sxy, mul_(x, y));
     if (stat_id == 3 && x >= 1. && y >= 1.) cnt += 1.;
     if (stat_id == 4) { double t = add_(x, y); s3 = add_(s3, mul_(t, t)); }
+    if (stat_id == 6) { cnt += (x >= thr && y >= thr) ? 1. : 0.; sxy += x >= thr ? 1. : 0.; s3 += y >= thr ? 1. : 0.; }
   }
   double r;
-  if (stat_id == 0 || stat_id == 1) {
+  if (stat_id == 6) r = mi_binary(nb, sxy, s3, cnt);
+  else if (stat_id == 0 || stat_id == 1) {
     const double mx = sx / nb, my = sy / nb;
     double cxy = 0., cxx = 0., cyy = 0.;
     for (int b = 0; b < B; b++) {
@@ -89,7 +111,7 @@ __global__ void k2_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t 
 // statistic of listed column pairs (a, b) of ONE mapping matrix: the group statistics of the
 // candidates analysis (AbstractMinimumStatistic::getValueForGroup, Statistics.h:118-131).  Same
 // operation order as k2_paired; one thread per pair.
-__global__ void k2_pair_list(int stat_id, int B, int64_t n_pad, const double* __restrict__ o, const double* __restrict__ mv,
+__global__ void k2_pair_list(int stat_id, double thr, int B, int64_t n_pad, const double* __restrict__ o, const double* __restrict__ mv,
                              const int2* __restrict__ pairs, int64_t n_pairs, double* __restrict__ stat) {
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= n_pairs) return;
@@ -110,9 +132,11 @@ __global__ void k2_pair_list(int stat_id, int B, int64_t n_pad, const double* __
     if (stat_id == 2) sxy = add_(sxy, mul_(x, y));
     if (stat_id == 3 && x >= 1. && y >= 1.) cnt += 1.;
     if (stat_id == 4) { double u = add_(x, y); s3 = add_(s3, mul_(u, u)); }
+    if (stat_id == 6) { cnt += (x >= thr && y >= thr) ? 1. : 0.; sxy += x >= thr ? 1. : 0.; s3 += y >= thr ? 1. : 0.; }
   }
   double r;
-  if (stat_id == 0 || stat_id == 1) {
+  if (stat_id == 6) r = mi_binary(nb, sxy, s3, cnt);
+  else if (stat_id == 0 || stat_id == 1) {
     const double mx = sx / nb, my = sy / nb;
     double cxy = 0., cxx = 0., cyy = 0.;
     for (int b = 0; b < B; b++) {
@@ -189,6 +213,15 @@ __global__ void k2_prep(int B, int64_t n, int64_t n_pad, const double* __restric
   norm[s] = sqrt(qx);
 }
 
+// branches of each site whose entry reaches the MI threshold (category 1)
+__global__ void k2_count_ge(int B, int64_t n, int64_t n_pad, const double* __restrict__ out, double thr, double* cnt) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  double c = 0.;
+  for (int b = 0; b < B; b++) c += out[(size_t)b * n_pad + s] >= thr ? 1. : 0.;
+  cnt[s] = c;
+}
+
 // mean vector of the mapped alignment: mv[b] = (sum over sites, in site order, of n_b(site)) / S
 // (CoMap.cpp:350-359), one thread per branch
 __global__ void k2_mean_vector(int B, int64_t S, int64_t n_pad, const double* __restrict__ out, double* mv) {
@@ -218,6 +251,7 @@ struct TileParams {
   const int32_t* rate_class2;
   int min_rate_class2;
   double min_rate2;
+  double thr;                 // MI threshold
   int nmin_by_row;            // upstream quirk: min(Nmin) pairs norms1[i] with norms2[i] (CoETools.cpp:803)
   const int2* tiles;          // (ti, tj) with tj >= ti
   const int32_t* rows;        // owned row list (gathered i-dimension) or nullptr = identity
@@ -243,9 +277,10 @@ struct TileParams {
 };
 
 template <int STAT>
-__device__ __forceinline__ double tile_load(double x, double mean) {
+__device__ __forceinline__ double tile_load(double x, double mean, double thr = 0.) {
   if (STAT == 0 || STAT == 1) return add_(x, -mean);
   if (STAT == 3) return x >= 1. ? 1. : 0.;
+  if (STAT == 6) return x >= thr ? 1. : 0.;
   return x;
 }
 
@@ -290,8 +325,8 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
           if (ai[u] >= 0) a = tile_load<STAT>(add_(rowp[ai[u]], -mvk), am[u]);
           if (bj[u] >= 0) b = tile_load<STAT>(add_(colp[bj[u]], -mvk2), bm[u]);
         } else {
-          if (ai[u] >= 0) a = tile_load<STAT>(rowp[ai[u]], am[u]);
-          if (bj[u] >= 0) b = tile_load<STAT>(colp[bj[u]], bm[u]);
+          if (ai[u] >= 0) a = tile_load<STAT>(rowp[ai[u]], am[u], p.thr);
+          if (bj[u] >= 0) b = tile_load<STAT>(colp[bj[u]], bm[u], p.thr);
         }
       }
       As[lk][lc + u] = a;
@@ -334,6 +369,7 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
       else if (STAT == 2) stat = acc[u][v] / mul_(p.norm[i], p.norm2[j]);
       else if (STAT == 3) stat = acc[u][v];
       else if (STAT == 4) stat = add_(1., -(sqrt(acc[u][v]) / add_(p.norm[i], p.norm2[j])));
+      else if (STAT == 6) stat = mi_binary(nb, p.mean[i], p.mean2[j], acc[u][v]); // mean arrays hold the category-1 counts
       else stat = sqrt(acc[u][v]);
       if (p.mode == MODE_DIST) {
         double d = p.dist_is_stat ? stat : p.dist_comp - stat;
@@ -445,15 +481,24 @@ __global__ void k2_keep_to_i64(int64_t n, const uint8_t* keep, int64_t* out) {
 
 } // namespace
 
-void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
+void launch_paired(int stat_id, double thr, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
                    const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st) {
-  k2_paired<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(stat_id, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin);
+  const unsigned g = (unsigned)((n + 127) / 128);
+  switch (stat_id) { // the statistic is a template parameter: no per-branch dispatch in the inner loops
+    case 0: k2_paired<0><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
+    case 1: k2_paired<1><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
+    case 2: k2_paired<2><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
+    case 3: k2_paired<3><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
+    case 4: k2_paired<4><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
+    case 6: k2_paired<6><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
+    default: fail("unknown statistic id %d", stat_id);
+  }
   CMB_CUDA(cudaGetLastError());
 }
-void launch_pair_list(int stat_id, int B, int64_t n_pad, const double* out, const double* mv, const int2* pairs,
+void launch_pair_list(int stat_id, double thr, int B, int64_t n_pad, const double* out, const double* mv, const int2* pairs,
                       int64_t n_pairs, double* stat, cudaStream_t st) {
   if (n_pairs == 0) return;
-  k2_pair_list<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(stat_id, B, n_pad, out, mv, pairs, n_pairs, stat);
+  k2_pair_list<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(stat_id, thr, B, n_pad, out, mv, pairs, n_pairs, stat);
   CMB_CUDA(cudaGetLastError());
 }
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
@@ -464,6 +509,10 @@ void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const in
 void launch_prep(int B, int64_t n, int64_t n_pad, const double* out, const double* mv, double* mean, double* sd,
                  double* norm, cudaStream_t st) {
   k2_prep<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, n, n_pad, out, mv, mean, sd, norm);
+  CMB_CUDA(cudaGetLastError());
+}
+void launch_count_ge(int B, int64_t n, int64_t n_pad, const double* out, double thr, double* cnt, cudaStream_t st) {
+  k2_count_ge<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(B, n, n_pad, out, thr, cnt);
   CMB_CUDA(cudaGetLastError());
 }
 void launch_mean_vector(int B, int64_t S, int64_t n_pad, const double* out, double* mv, cudaStream_t st) {
@@ -518,6 +567,7 @@ int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
   p.mv2 = rect ? L.mv2 : L.mv;
   p.min_rate_class2 = rect ? L.min_rate_class2 : L.min_rate_class; p.min_rate2 = rect ? L.min_rate2 : L.min_rate;
   p.nmin_by_row = rect ? L.nmin_by_row : 0;
+  p.thr = L.thr;
   p.tiles = L.tiles; p.rows = L.rows; p.n_rows = L.n_rows; p.row_off = L.row_off;
   p.min_rate_class = L.min_rate_class; p.max_rate_class_diff = L.max_rate_class_diff; p.min_rate = L.min_rate;
   p.max_rate_diff = L.max_rate_diff; p.min_stat = L.min_stat; p.any_filter = L.any_filter;
@@ -534,6 +584,7 @@ int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
     case 3: k2_tiles<3><<<g, 256, 0, st>>>(p); break;
     case 4: k2_tiles<4><<<g, 256, 0, st>>>(p); break;
     case 5: k2_tiles<5><<<g, 256, 0, st>>>(p); break;
+    case 6: k2_tiles<6><<<g, 256, 0, st>>>(p); break;
     default: fail("unknown statistic id %d", L.stat_id);
   }
   CMB_CUDA(cudaGetLastError());
@@ -556,8 +607,7 @@ int launch_inter_diagonal(const TilesLaunch& L, cudaStream_t st) {
   p.max_rate_class_diff = L.max_rate_class_diff; p.max_rate_diff = L.max_rate_diff; p.min_stat = L.min_stat;
   p.any_filter = L.any_filter;
   p.o_i = L.o_i; p.o_j = L.o_j; p.o_stat = L.o_stat; p.o_rcmin = L.o_rcmin; p.o_prmin = L.o_prmin; p.o_keep = L.o_keep;
-  k2_paired<<<(unsigned)((L.S + 127) / 128), 128, 0, st>>>(L.stat_id, L.B, L.S, L.S_pad, L.S2_pad, L.out, L.out2, L.mv, L.mv2,
-                                                        L.o_stat, L.o_nmin);
+  launch_paired(L.stat_id, L.thr, L.B, L.S, L.S_pad, L.S2_pad, L.out, L.out2, L.mv, L.mv2, L.o_stat, L.o_nmin, st);
   k2_diag_rows<<<(unsigned)((L.S + 127) / 128), 128, 0, st>>>(p);
   CMB_CUDA(cudaGetLastError());
   return 2;

@@ -64,11 +64,12 @@ void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64
 
 // ---- K2
 // mv: mean vector subtracted before a correlation (corrected correlation) or nullptr
-void launch_paired(int stat_id, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
+void launch_paired(int stat_id, double thr, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
                    const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st);
 // statistic of listed column pairs of one [B][n_pad] matrix (candidate-group statistics)
-void launch_pair_list(int stat_id, int B, int64_t n_pad, const double* out, const double* mv, const int2* pairs,
+void launch_pair_list(int stat_id, double thr, int B, int64_t n_pad, const double* out, const double* mv, const int2* pairs,
                       int64_t n_pairs, double* stat, cudaStream_t st);
+void launch_count_ge(int B, int64_t n, int64_t n_pad, const double* out, double thr, double* cnt, cudaStream_t st);
 void launch_mean_vector(int B, int64_t S, int64_t n_pad, const double* out, double* mv, cudaStream_t st);
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
                      const double* pr1, const double* pr2, double* raw, cudaStream_t st);
@@ -89,6 +90,7 @@ struct TilesLaunch {
   const int32_t* rate_class2 = nullptr;
   int64_t S2 = 0, S2_pad = 0;
   int min_rate_class2 = 0, nmin_by_row = 0;
+  double thr = 0.;              // MI threshold (stat 6; `mean` / `mean2` then hold the category-1 counts)
   double min_rate2 = 0.;
   const int32_t* rate_class = nullptr;
   const int2* tiles = nullptr;

@@ -241,8 +241,13 @@ int stat_id_of(const Params& P, const Inputs& in) {
     return CMB_STAT_COMPENSATION;
   }
   if (st.name == "CorrectedCorrelation") return CMB_STAT_CORRECTED_CORRELATION; // mean vector: CoMap.cpp:350-359
-  if (st.name == "MI")
-    throw Error("statistic=MI (with nijt=Label) is not available in this build (SURVEY.md s8f)");
+  if (st.name == "MI") { // CoETools.cpp:576-596
+    std::string nj = get_string(P, "nijt", "Label");
+    if (nj == "Label")
+      throw Error("statistic=MI with nijt=Label (one category per substitution type) is not available in this build; "
+                  "use e.g. nijt=Uniformization, which discretises the counts at MI(threshold=...)");
+    return CMB_STAT_MI;
+  }
   throw Error("Unknown statistic used: " + get_string(P, "statistic", ""));
 }
 
@@ -291,6 +296,10 @@ Mapped map_data_set(const Inputs& in, const Params& P, const std::string& suffix
                     in.rdist.rates.data(), in.rdist.probs.data(), in.count_method,
                     in.weights.empty() ? nullptr : in.weights.data()));
   chk(cmb_set_alignment(m.ctx, S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
+  {
+    Procedure st = parse_procedure(get_string(P, "statistic", "Correlation"));
+    if (st.name == "MI") chk(cmb_set_mi_threshold(m.ctx, get_double(st.args, "threshold", 0.99)));
+  }
   const std::string in_vec = get_path(P, "input.vectors.file", "none");
   std::string vec_path = get_path(P, "output.vectors.file", "none");
   if (in_vec != "none") vec_path = "none"; // CoETools.cpp:374-390: vectors are read OR computed (+ written)

@@ -48,7 +48,9 @@ enum {
   CMB_STAT_COSINUS = 2,
   CMB_STAT_COSUBSTITUTION = 3,
   CMB_STAT_COMPENSATION = 4,
-  CMB_STAT_CORRECTED_CORRELATION = 5 /* Statistics.h:176-205; mean vector as CoMap.cpp:350-359 */
+  CMB_STAT_CORRECTED_CORRELATION = 5, /* Statistics.h:176-205; mean vector as CoMap.cpp:350-359 */
+  CMB_STAT_MI = 6 /* MI(threshold=..) without nijt=Label: DiscreteMutualInformationStatistic over the
+                     bounds {0, threshold, 10000} (CoETools.cpp:590-595, Statistics.h:307-329) */
 };
 /* clustering.distance= : CoMap.cpp:401-427; Distance.h:150-173,316-424 */
 enum { CMB_DIST_CORRELATION = 0, CMB_DIST_COMPENSATION = 1, CMB_DIST_EUCLIDIAN = 2 };
@@ -132,6 +134,10 @@ int cmb_null_intra(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t rep_cpu
 int cmb_null_intra_from_alignments(cmb_ctx* ctx, int32_t stat_id, int32_t rep_cpu, int32_t rep_ram,
                                    const uint8_t* sim1, const uint8_t* sim2, int32_t K,
                                    double nmax, double* raw);
+
+/* Threshold of CMB_STAT_MI (statistic=MI(threshold=0.99), CoETools.cpp:591): a branch entry is in
+ * category 1 when it reaches the threshold. */
+int cmb_set_mi_threshold(cmb_ctx* ctx, double threshold);
 
 /* on = 1: cmb_null_intra with K = 0 (samples left unbinned for an exchange) only enqueues its
  * work and returns; the caller orders later consumers with cmb_sync.  Lets a second context on

@@ -519,8 +519,29 @@ void orc_mean_vector(int64_t S, int B, const double* n, double* mv) {
   for (int b = 0; b < B; b++) mv[b] /= (double)S;
 }
 
+static double g_mi_threshold = 0.99;
+void orc_set_mi_threshold(double threshold) { g_mi_threshold = threshold; }
+
+/* statistic=MI(threshold=t) with nijt != Label (CoETools.cpp:590-595): DiscreteMutualInformationStatistic
+ * with bounds {0, t, 10000} (Statistics.h:307-329): category of a branch = Domain(bounds).getIndex(sum of
+ * its counts) = [v >= t]; then [Bio++ / from memory] VectorTools::miDiscrete(c1, c2, base = 2.7182818):
+ * frequency maps iterated in key order, s += (n12 / n) * log(n12 * n / (n1 * n2)) / log(base). */
+static double mi_discrete_binary(int B, const double* v1, const double* v2, double t) {
+  double c1[2] = {0., 0.}, c2[2] = {0., 0.}, c12[2][2] = {{0., 0.}, {0., 0.}};
+  for (int i = 0; i < B; i++) {
+    int a = v1[i] >= t, b = v2[i] >= t;
+    c1[a]++; c2[b]++; c12[a][b]++;
+  }
+  double s = 0., n = (double)B;
+  for (int a = 0; a < 2; a++)
+    for (int b = 0; b < 2; b++)
+      if (c12[a][b] > 0.) s += (c12[a][b] / n) * log(c12[a][b] * n / (c1[a] * c2[b])) / log(2.7182818);
+  return s;
+}
+
 double orc_stat(int stat_id, int B, const double* v1, const double* v2) {
   switch (stat_id) {
+    case ORC_STAT_MI: return mi_discrete_binary(B, v1, v2, g_mi_threshold);
     case ORC_STAT_CORRECTED_CORRELATION: { /* Statistics.h:188-194: cor(v1 - mean vector, v2 - mean vector) */
       if (g_mean_vector_len != B) return NAN;
       double* a = malloc(sizeof(double) * (size_t)B * 2);

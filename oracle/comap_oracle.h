@@ -43,7 +43,8 @@ enum {
   ORC_STAT_COSINUS = 2,
   ORC_STAT_COSUBSTITUTION = 3,
   ORC_STAT_COMPENSATION = 4,
-  ORC_STAT_CORRECTED_CORRELATION = 5 /* needs orc_set_mean_vector */
+  ORC_STAT_CORRECTED_CORRELATION = 5, /* needs orc_set_mean_vector */
+  ORC_STAT_MI = 6 /* MI(threshold=..) without nijt=Label; threshold from orc_set_mi_threshold (0.99) */
 };
 enum { ORC_DIST_CORRELATION = 0, ORC_DIST_COMPENSATION = 1, ORC_DIST_EUCLIDIAN = 2 };
 enum { ORC_LINK_COMPLETE = 0, ORC_LINK_SINGLE = 1, ORC_LINK_AVERAGE = 2 };
@@ -72,6 +73,7 @@ double orc_stat(int stat_id, int B, const double* v1, const double* v2);
  * both sites, and how CoMap builds it from the mapping (CoMap.cpp:350-359: running sum over
  * sites in site order, divided by the number of sites). */
 void orc_set_mean_vector(int B, const double* mv);
+void orc_set_mi_threshold(double threshold);
 void orc_set_mean_vectors(int B, const double* mv1, const double* mv2);
 double orc_stat2(int stat_id, int B, const double* v1, const double* v2);
 /* CoETools::computeInterStats, CoETools.cpp:732-840 */

@@ -11,7 +11,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(ROOT, "oracle", "liboracle.so")
 
 STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "compensation": 4,
-        "corrected_correlation": 5}
+        "corrected_correlation": 5, "mi": 6}
 DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
 LINK = {"complete": 0, "single": 1, "average": 2}
 COUNT = {"uniformization": 0, "decomposition": 1}
@@ -91,6 +91,10 @@ def map_sites(parent, brlen, Q, pi, rates, probs, codes, code_mask, method="unif
                        len(code_mask), _p(code_mask, C.c_uint32), _d(n), _d(norm), _d(pr),
                        _p(rc, C.c_int32), _d(ll)))
     return dict(n=n, norm=norm, post_rate=pr, rate_class=rc, loglik=ll)
+
+
+def set_mi_threshold(t):
+    lib().orc_set_mi_threshold(C.c_double(t))
 
 
 def mean_vector(n):

@@ -77,6 +77,32 @@ def test_pairs_all_statistics_vs_oracle(ctx, stat):
         assert np.array_equal(g["stat"], o["stat"])  # integer valued: exact
 
 
+def test_mutual_information_statistic(ctx):
+    """statistic=MI(threshold=t) (discretised mutual information, CoETools.cpp:590-595): observed pairs,
+    null and p-values against the oracle.  Device and host `log` may differ in the last bit, so the
+    statistic is compared at 1e-9; counts of the null per bin are exact (they depend on Nmin only)."""
+    c = _case(T=20, S=90, seed=4)
+    for thr in (0.99, 0.3):
+        ctx.set_mi_threshold(thr); O.set_mi_threshold(thr)
+        r = _setup(ctx, c)
+        g, k = ctx.pairs("mi", use_null=False)
+        o = O.pairs("mi", r["n"], r["norm"], r["post_rate"], r["rate_class"])
+        assert k == len(o["i"]) and np.array_equal(g["i"], o["i"]) and np.array_equal(g["j"], o["j"])
+        assert np.allclose(g["stat"], o["stat"], rtol=1e-9, atol=1e-15) and (g["stat"] > 1e-3).any()
+        rep_cpu, rep_ram, K = 2, 150, 4
+        s1 = np.stack([ctx.simulate(5, (2 * i) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+        s2 = np.stack([ctx.simulate(5, (2 * i + 1) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+        nmax = float(r["norm"].max())
+        raw = ctx.null_intra_from_alignments("mi", s1, s2, K=K, nmax=nmax)
+        on = O.null_intra(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], "mi", s1, s2, K, nmax)
+        assert np.allclose(raw[:, 0], on["raw"][:, 0], rtol=1e-9, atol=1e-15)
+        gn = ctx.null_get()
+        assert np.array_equal(gn["bin_offsets"], on["bin_offsets"])
+        gp, k2 = ctx.pairs("mi", use_null=True)
+        assert k2 == k and np.all((gp["pvalue"][~np.isnan(gp["pvalue"])] > 0) & (gp["pvalue"][~np.isnan(gp["pvalue"])] <= 1))
+    ctx.set_mi_threshold(0.99); O.set_mi_threshold(0.99)
+
+
 def test_pairs_filters_and_shards(ctx):
     c = _case(S=203)
     _setup(ctx, c)

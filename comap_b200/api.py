@@ -197,11 +197,11 @@ class Context:
         mk = lambda name, dt: np.empty(cap, dt) if name in cols else None
         oi, oj = mk("i", np.int32), mk("j", np.int32)
         st, rcm, prm, nm = mk("stat", np.float64), mk("rcmin", np.int32), mk("prmin", np.float64), mk("nmin", np.float64)
-        pv, ns = mk("pvalue", np.float64), mk("nsim", np.int64)
+        pv, ns = mk("pvalue", np.float64), mk("nsim", np.int32)
         nr = C.c_int64()
         self._chk(self.lib.cmb_pairs(self.h, STAT[stat], C.byref(f), int(use_null), shard_index, shard_count,
                                      C.c_int64(cap), _i32(oi), _i32(oj), _d(st), _i32(rcm), _d(prm), _d(nm), _d(pv),
-                                     _i64(ns), C.byref(nr)))
+                                     _i32(ns), C.byref(nr)))
         k = nr.value
         out = dict(i=oi, j=oj, stat=st, rcmin=rcm, prmin=prm, nmin=nm, pvalue=pv, nsim=ns)
         return {name: (a[:k] if a is not None else None) for name, a in out.items()}, k
@@ -264,7 +264,7 @@ class Context:
         return raw
 
     COLS = ("i", "j", "stat", "rcmin", "prmin", "nmin", "pvalue", "nsim")
-    COL_DTYPE = (np.int32, np.int32, np.float64, np.int32, np.float64, np.float64, np.float64, np.int64)
+    COL_DTYPE = (np.int32, np.int32, np.float64, np.int32, np.float64, np.float64, np.float64, np.int32)
 
     def pairs_resident(self, stat, use_null=True, filters=None, shard_index=0, shard_count=1, columns=0xFF):
         f = Filters(0, -1, 0.0, -1.0, 0.0)

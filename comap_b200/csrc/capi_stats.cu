@@ -320,7 +320,7 @@ int cmb_null_get(cmb_ctx* ctx, int32_t* K, double* nmax, int64_t* bin_offsets, d
 }
 
 // column ids: 0 i, 1 j, 2 stat, 3 rcmin, 4 prmin, 5 nmin, 6 pvalue, 7 nsim
-static const size_t kColElt[8] = {4, 4, 8, 4, 8, 8, 8, 8};
+static const size_t kColElt[8] = {4, 4, 8, 4, 8, 8, 8, 4}; // Nsim <= 2^31 null samples: int32 (half the D2H)
 
 int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int32_t use_null, int32_t shard_index,
                        int32_t shard_count, uint32_t columns, int64_t* n_rows) {
@@ -409,7 +409,7 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
   }
   auto dp = [&](int k) -> void* { return (columns >> k & 1) ? sb + off[k] : nullptr; };
   L.o_i = (int32_t*)dp(0); L.o_j = (int32_t*)dp(1); L.o_stat = (double*)dp(2); L.o_rcmin = (int32_t*)dp(3);
-  L.o_prmin = (double*)dp(4); L.o_nmin = (double*)dp(5); L.o_pvalue = (double*)dp(6); L.o_nsim = (int64_t*)dp(7);
+  L.o_prmin = (double*)dp(4); L.o_nmin = (double*)dp(5); L.o_pvalue = (double*)dp(6); L.o_nsim = (int32_t*)dp(7);
   L.o_keep = sb + o_keep;
   c.prof_begin("pairs");
   int nl = 0;
@@ -430,7 +430,6 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
     for (int k = 0; k < 8; k++) {
       if (!(columns >> k & 1)) continue;
       if (kColElt[k] == 4) compact_column<int32_t>(total, L.o_keep, pos, (int32_t*)(sb + off[k]), (int32_t*)(sb + off2[k]), c.stream);
-      else if (k == 7) compact_column<int64_t>(total, L.o_keep, pos, (int64_t*)(sb + off[k]), (int64_t*)(sb + off2[k]), c.stream);
       else compact_column<double>(total, L.o_keep, pos, (double*)(sb + off[k]), (double*)(sb + off2[k]), c.stream);
       off[k] = off2[k];
       c.prof.total_launches += 1;
@@ -469,7 +468,7 @@ int cmb_pairs_fetch(cmb_ctx* ctx, int32_t column, void* host, int64_t capacity) 
 
 int cmb_pairs(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int32_t use_null, int32_t shard_index,
               int32_t shard_count, int64_t capacity, int32_t* out_i, int32_t* out_j, double* out_stat, int32_t* out_rcmin,
-              double* out_prmin, double* out_nmin, double* out_pvalue, int64_t* out_nsim, int64_t* n_rows) {
+              double* out_prmin, double* out_nmin, double* out_pvalue, int32_t* out_nsim, int64_t* n_rows) {
   void* host[8] = {out_i, out_j, out_stat, out_rcmin, out_prmin, out_nmin, out_pvalue, out_nsim};
   uint32_t columns = 0;
   for (int k = 0; k < 8; k++) if (host[k]) columns |= 1u << k;

@@ -269,7 +269,7 @@ struct TileParams {
   // outputs (dense upper triangle of the owned rows), all nullable
   int32_t *o_i, *o_j, *o_rcmin;
   double *o_stat, *o_prmin, *o_nmin, *o_pvalue;
-  int64_t* o_nsim;
+  int32_t* o_nsim;
   uint8_t* o_keep;
   double* mat;                // MODE_DIST: [S][S]
   double dist_comp;           // distance = comp - stat (Distance.h:334-337), or stat itself
@@ -410,7 +410,7 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
           pv = (double)(nsim - lo + 1) / (double)(nsim + 1);
         }
         if (p.o_pvalue) p.o_pvalue[idx] = pv;
-        if (p.o_nsim) p.o_nsim[idx] = nsim;
+        if (p.o_nsim) p.o_nsim[idx] = (int32_t)nsim;
       }
     }
   }
@@ -448,7 +448,7 @@ __global__ void k2_diag_rows(TileParams p) {
 // recomputed for PValue / Nsim
 __global__ void k2_pvalues(int64_t n, const double* __restrict__ stat, const double* __restrict__ nmin, int K, double nmax,
                            const int64_t* __restrict__ bin_off, const double* __restrict__ sorted, double* __restrict__ pvalue,
-                           int64_t* __restrict__ nsim_out) {
+                           int32_t* __restrict__ nsim_out) {
   const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const double st = stat[r];
@@ -466,7 +466,7 @@ __global__ void k2_pvalues(int64_t n, const double* __restrict__ stat, const dou
     pv = (double)(nsim - lo + 1) / (double)(nsim + 1);
   }
   if (pvalue) pvalue[r] = pv;
-  if (nsim_out) nsim_out[r] = nsim;
+  if (nsim_out) nsim_out[r] = (int32_t)nsim;
 }
 
 template <class T>
@@ -592,7 +592,7 @@ int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
 }
 
 void launch_pvalues(int64_t n, const double* stat, const double* nmin, int K, double nmax, const int64_t* bin_off,
-                    const double* sorted, double* pvalue, int64_t* nsim, cudaStream_t st) {
+                    const double* sorted, double* pvalue, int32_t* nsim, cudaStream_t st) {
   if (n == 0) return;
   k2_pvalues<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, stat, nmin, K, nmax, bin_off, sorted, pvalue, nsim);
   CMB_CUDA(cudaGetLastError());

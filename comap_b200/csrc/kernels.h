@@ -107,7 +107,7 @@ struct TilesLaunch {
   const double* sorted = nullptr;
   int32_t *o_i = nullptr, *o_j = nullptr, *o_rcmin = nullptr;
   double *o_stat = nullptr, *o_prmin = nullptr, *o_nmin = nullptr, *o_pvalue = nullptr;
-  int64_t* o_nsim = nullptr;
+  int32_t* o_nsim = nullptr;
   uint8_t* o_keep = nullptr;
   double* mat = nullptr;
   double dist_comp = 1.;
@@ -116,7 +116,7 @@ struct TilesLaunch {
 int launch_tiles(const TilesLaunch& L, cudaStream_t st);
 // PValue / Nsim of rows whose Stat / Nmin columns are already resident (no tile recomputation)
 void launch_pvalues(int64_t n, const double* stat, const double* nmin, int K, double nmax, const int64_t* bin_off,
-                    const double* sorted, double* pvalue, int64_t* nsim, cudaStream_t st);
+                    const double* sorted, double* pvalue, int32_t* nsim, cudaStream_t st);
 int launch_inter_diagonal(const TilesLaunch& L, cudaStream_t st); // site i of data set 1 with site i of data set 2
 int64_t compact_positions(int64_t n, const uint8_t* keep, DevBuf& tmp, int64_t** pos_out, cudaStream_t st);
 template <class T>

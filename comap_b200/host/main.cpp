@@ -539,7 +539,7 @@ int main(int argc, char** argv) {
       const int64_t cap = S * (S - 1) / 2;
       std::vector<int32_t> I(cap), J(cap), RC(cap);
       std::vector<double> ST(cap), PR(cap), NM(cap), PV(pvalues ? cap : 0);
-      std::vector<int64_t> NS(pvalues ? cap : 0);
+      std::vector<int32_t> NS(pvalues ? cap : 0);
       int64_t rows = 0;
       chk(cmb_pairs(ctx, stat_id, &f, pvalues ? 1 : 0, 0, 1, cap, I.data(), J.data(), ST.data(), RC.data(), PR.data(),
                     NM.data(), pvalues ? PV.data() : nullptr, pvalues ? NS.data() : nullptr, &rows));

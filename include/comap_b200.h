@@ -164,11 +164,11 @@ int cmb_null_get(cmb_ctx* ctx, int32_t* K, double* nmax, int64_t* bin_offsets, d
 int cmb_pairs(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* filters, int32_t use_null,
               int32_t shard_index, int32_t shard_count, int64_t capacity, int32_t* out_i,
               int32_t* out_j, double* out_stat, int32_t* out_rcmin, double* out_prmin,
-              double* out_nmin, double* out_pvalue, int64_t* out_nsim, int64_t* n_rows);
+              double* out_nmin, double* out_pvalue, int32_t* out_nsim, int64_t* n_rows);
 
 /* Device-resident form of cmb_pairs: computes the columns selected by the bitmask
  * `columns` (bit k = column k: 0 i, 1 j, 2 stat, 3 rcmin, 4 prmin, 5 nmin, 6 pvalue,
- * 7 nsim) into device memory and returns the row count; cmb_pairs_fetch then copies one
+ * 7 nsim, int32) into device memory and returns the row count; cmb_pairs_fetch then copies one
  * column to the host (asynchronously on the context's stream; call cmb_sync). */
 int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* filters, int32_t use_null,
                        int32_t shard_index, int32_t shard_count, uint32_t columns, int64_t* n_rows);

@@ -222,6 +222,25 @@ def test_weighted_counts_and_compensation_statistic(myo):
     assert p.returncode == 255 and "non-symmetric weights" in p.stdout
 
 
+def test_mutual_information_from_the_cli(myo):
+    """statistic=MI(threshold=0.5) with nijt=Uniformization (CoETools.cpp:576-596)."""
+    from comap_b200 import api
+    tmp, _ = myo
+    run(tmp, *COMMON, "analysis=pairwise", "statistic=MI(threshold=0.5)", "statistic.null=no", "statistic.output.file=mi.txt")
+    c = host_inputs(tmp)
+    ctx = api.Context(device=0)
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(c["codes"], c["code_mask"]); ctx.set_mi_threshold(0.5); ctx.map()
+    p, k = ctx.pairs("mi", use_null=False)
+    hdr, rows = table(os.path.join(tmp, "mi.txt"))
+    assert len(rows) == k and [x[1] for x in rows] == [g(v) for v in p["stat"]]
+    assert max(float(x[1]) for x in rows) > 0.05
+    pr = subprocess.run([BIN] + [a for a in COMMON if not a.startswith("nijt=")] + ["nijt=Label", "analysis=pairwise", "statistic=MI"],
+                        cwd=tmp, capture_output=True, text=True)
+    assert pr.returncode == 255
+    ctx.close()
+
+
 def test_candidate_groups_table_equals_c_abi_run(myo):
     """analysis=candidates (CoMap.cpp:592-711): input table + Stat + p-value columns."""
     from comap_b200 import api

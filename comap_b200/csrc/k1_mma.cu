@@ -307,7 +307,6 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
     const int4 h0 = *reinterpret_cast<const int4*>(stage);
     const int4 h1 = *reinterpret_cast<const int4*>(stage + 16);
     const uint32_t flags = (uint32_t)h0.x;
-    const int out_a = h0.w, out_b = h1.x;
     const int kind_a = (flags & kUpTipA) ? kTip : (flags & kUpCherryA) ? kCherry : kInner;
     const int kind_b = (flags & kUpTipB) ? kTip : (flags & kUpCherryB) ? kCherry : kInner;
     NodePtrs p;
@@ -360,6 +359,8 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
     }
     if (flags & kUpPush) ++sp;
     else if (flags & kUpPop) --sp;
+    // the output rows are read again here rather than kept live (or spilled) across the node body
+    const int ob = reinterpret_cast<const volatile int*>(stage)[3 + ((lane >> 1) & 1)]; // q & 2 ? out_b : out_a
     __syncwarp();
     if (lane == 0) mbar_arrive(&stg_empty[cs]);   // the stage has been read
     if (++cs == (uint32_t)NSTG) { cs = 0; cph ^= 1; }
@@ -373,7 +374,6 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
       const double keep = (q & 2) ? acc_b[g] : acc_a[g];
       v[g] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
     }
-    const int ob = (q & 2) ? out_b : out_a;
 #pragma unroll
     for (int j = 0; j < NJ; j++) {
       const double send = (q & 1) ? v[2 * j] : v[2 * j + 1];

@@ -316,9 +316,9 @@ def run_ours(args, cfg):
             achieved = sites_mapped * abytes_site / (map_ms * 1e-3) / 1e9 if map_ms > 0 else 0.0
             n_pass = max(1, prof["map_up"][1])
             # DRAM bytes actually moved, from the committed `ncu --set full` captures of one pass over
-            # 128 256 sites (profiles/r1i_k1_{down,up}_mma.txt: dram__bytes_read.sum + dram__bytes_write.sum);
+            # 128 256 sites (profiles/r1j_k1_{down,up}_mma.txt: dram__bytes_read.sum + dram__bytes_write.sum);
             # below the algorithmic figure because cherry partials are recomputed, not stored
-            traffic_site = (69.0e6 + 5.2977e9 + 5.6353e9 + 1.4929e9) / 128256.0
+            traffic_site = (69.0e6 + 5.2964e9 + 5.6296e9 + 1.4807e9) / 128256.0
             line = dict(metric="site_pairs_scored_per_s_incl_mapping_and_null",
                         value=pairs_per_step * args.steps / (ms * 1e-3), unit="pairs/s", n_gpus=world, steps=args.steps,
                         warmup=max(3, args.warmup), ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong",
@@ -334,7 +334,7 @@ def run_ours(args, cfg):
                                       algorithmic_bytes_per_site=abytes_site, sites_per_step=sites_mapped // args.steps,
                                       avg_pass_ms=map_ms / n_pass, passes=int(n_pass),
                                       traffic=traffic_site * sites_mapped / n_pass, traffic_unit="bytes per pass",
-                                      traffic_source="ncu dram bytes of k1_down_mma + k1_up_mma, profiles/r1i_*.txt, scaled by sites"),
+                                      traffic_source="ncu dram bytes of k1_down_mma + k1_up_mma, profiles/r1j_*.txt, scaled by sites"),
                         kernel_ms_per_step={k: v[0] / args.steps for k, v in prof.items()})
             if world == 1 and not args.no_cpu_baseline:
                 cb = cpu_sample(cfg, w, aln_codes=codes)

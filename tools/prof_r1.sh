@@ -1,6 +1,6 @@
 # ncu evidence for profiles/ (run on the GPU box: bash tools/prof_r1.sh [tag])
 cd $GRAFT_REPO_ROOT
-T=${1:-r1i}
+T=${1:-r1j}
 S="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $S > gpurun_out/${T}_plain.log 2>&1 || exit 1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/${T}_launches.csv $S > gpurun_out/${T}_ncu_launch.log 2>&1

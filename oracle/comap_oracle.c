@@ -190,7 +190,7 @@ static void counts_uniformization(const spectral_t* sp, const double* Q, const d
 static void counts_decomposition(const spectral_t* sp, const double* Q, const double* weights,
                                  double t, double* N) {
   int A = sp->A, AA = A * A;
-  double* Bm = malloc(sizeof(double) * AA);
+  double* Bm = calloc(AA, sizeof(double));
   double* t1 = malloc(sizeof(double) * AA);
   double* t2 = malloc(sizeof(double) * AA);
   double* P = malloc(sizeof(double) * AA);

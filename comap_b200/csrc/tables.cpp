@@ -166,7 +166,7 @@ void build_model_tables(ModelTables& mt, int A, const double* Q, const double* p
                         const double* weights, int B, const double* brlen) {
   if (A < 2 || A > 32) fail("cmb_set_model: A must be in 2..32 (got %d)", A);
   if (C < 1 || C > 32) fail("cmb_set_model: C must be in 1..32 (got %d)", C);
-  if (count_method != 0 && count_method != 1) fail("cmb_set_model: unknown count method %d", count_method);
+  if (count_method < 0 || count_method > 2) fail("cmb_set_model: unknown count method %d", count_method);
   Spectrum sp(A, Q, pi);
   const size_t AA = (size_t)A * A;
   mt.A = A; mt.C = C; mt.B = B;
@@ -184,9 +184,13 @@ void build_model_tables(ModelTables& mt, int A, const double* Q, const double* p
       double* W = &mt.W[((size_t)b * C + c) * AA];
       double* cum = &mt.cumP[((size_t)b * C + c) * AA];
       sp.pmatrix(t, P);
-      if (count_method == 0) uniformization_numerator(A, Q, weights, t, num);
+      if (count_method == 2) { // nijt=Naive: one substitution (or its weight) when the ends differ
+        for (int x = 0; x < A; x++)
+          for (int y = 0; y < A; y++)
+            W[x * A + y] = x == y ? 0. : probs[c] * (P[x * A + y] * (weights ? weights[x * A + y] : 1.));
+      } else if (count_method == 0) uniformization_numerator(A, Q, weights, t, num);
       else decomposition_numerator(sp, Q, weights, t, num);
-      for (size_t i = 0; i < AA; i++) {
+      for (size_t i = 0; count_method != 2 && i < AA; i++) {
         // reference: n = num / P with NaN/Inf -> 0 and (unweighted) negatives -> 0, then
         // the mapping multiplies by P again; W = P * n folds both.
         double n = num[i] / P[i];

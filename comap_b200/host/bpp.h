@@ -102,7 +102,8 @@ struct RateDist {
 RateDist make_rate_distribution(const std::string& desc);
 // nijt=...(weight=Diff(index1=Volume, symmetrical=no)): AlphabetIndex2 weights of the weighted
 // substitution count, A*A row-major w[x][y] (empty: no weights).  *symmetric reports isSymmetric().
-std::vector<double> make_count_weights(const std::string& desc, const Alphabet& alpha, bool* symmetric);
+std::vector<double> make_count_weights(const std::string& desc, const Alphabet& alpha, bool* symmetric,
+                                       const std::string& data_dir);
 
 // regularised lower incomplete gamma P(a, x) and its inverse (used by Gamma(n, alpha))
 double pgamma(double x, double a);

@@ -155,8 +155,9 @@ void prepare(Inputs& in, const char* argv0, const Params* override_params = null
   Procedure nj = parse_procedure(nijt);
   if (nj.name == "Uniformization") in.count_method = CMB_COUNT_UNIFORMIZATION;
   else if (nj.name == "Decomposition") in.count_method = CMB_COUNT_DECOMPOSITION;
-  else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition)");
-  in.weights = make_count_weights(get_string(nj.args, "weight", "None"), in.alpha, &in.weights_symmetric);
+  else if (nj.name == "Naive") in.count_method = CMB_COUNT_NAIVE;
+  else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition, Naive)");
+  in.weights = make_count_weights(get_string(nj.args, "weight", "None"), in.alpha, &in.weights_symmetric, data_dir_of(argv0));
   if (!in.weights.empty()) display_result("Substitution count weights", get_string(nj.args, "weight", "None"));
   if (!get_bool(P, "nijt.average", true) || !get_bool(P, "nijt.joint", true))
     throw Error("nijt.average=no / nijt.joint=no (benchmark-only variants) are not available in this build");

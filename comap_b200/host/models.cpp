@@ -256,14 +256,35 @@ const double kGranthamPolarity[20] = {8.1, 10.5, 11.6, 13.0, 5.5, 10.5, 12.3, 9.
 const double kKleinCharge[20] = {0, 1, 0, -1, 0, 0, -1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0};
 }
 
-std::vector<double> make_count_weights(const std::string& desc, const Alphabet& alpha, bool* symmetric) {
+std::vector<double> make_count_weights(const std::string& desc, const Alphabet& alpha, bool* symmetric,
+                                       const std::string& data_dir) {
   if (symmetric) *symmetric = true;
   if (desc.empty() || desc == "None" || desc == "none") return {};
   Procedure p = parse_procedure(desc);
-  if (p.name != "Diff")
-    throw Error("weight=" + p.name + " is not available in this build (Diff(index1=Volume|Polarity|Charge, symmetrical=yes|no); "
-                "AAdist needs Bio++'s Grantham / Miyata tables, which are not bundled)");
   const size_t A = alpha.states.size();
+  if (p.name == "AAdist") {
+    // AAdist(type=grantham, sym=yes): Grantham's chemical distance (examples/Proteins/Benchmark/CoMap/analyse.sh);
+    // the table in data/grantham.dat was recovered from the reference's golden vectors
+    // (tests/golden/recover_grantham.py).  The signed variant (sym=no) is Bio++-specific and not available.
+    if (A != 20) throw Error("weight=AAdist(...) needs the protein alphabet");
+    if (lower(get_string(p.args, "type", "grantham")) != "grantham")
+      throw Error("weight=AAdist(type=" + get_string(p.args, "type", "") + "): only type=grantham is bundled");
+    if (!get_bool(p.args, "sym", true)) throw Error("weight=AAdist(sym=no) is not available in this build");
+    std::istringstream in(read_file(data_dir + "/grantham.dat"));
+    std::vector<double> w;
+    std::string line;
+    while (std::getline(in, line)) {
+      if (line.empty() || line[0] == '#') continue;
+      std::istringstream ls(line);
+      double v;
+      while (ls >> v) w.push_back(v);
+    }
+    if (w.size() != 400) throw Error("grantham.dat: expected a 20 x 20 table");
+    return w;
+  }
+  if (p.name != "Diff")
+    throw Error("weight=" + p.name + " is not available in this build (Diff(index1=Volume|Polarity|Charge, symmetrical=yes|no), "
+                "AAdist(type=grantham, sym=yes))");
   if (A != 20) throw Error("weight=Diff(...) needs the protein alphabet (the bundled indices are amino-acid properties)");
   std::string idx = get_string(p.args, "index1", "None");
   const double* v = nullptr;

@@ -40,7 +40,7 @@ extern "C" {
 typedef struct cmb_ctx cmb_ctx;
 
 /* nijt= : PhylogeneticsApplicationTools::getSubstitutionCount, CoMap.cpp:152 */
-enum { CMB_COUNT_UNIFORMIZATION = 0, CMB_COUNT_DECOMPOSITION = 1 };
+enum { CMB_COUNT_UNIFORMIZATION = 0, CMB_COUNT_DECOMPOSITION = 1, CMB_COUNT_NAIVE = 2 };
 /* statistic= : CoETools::getStatistic, CoETools.cpp:535-600; Statistics.h:164-295 */
 enum {
   CMB_STAT_CORRELATION = 0,

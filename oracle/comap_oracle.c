@@ -217,17 +217,25 @@ static void counts_decomposition(const spectral_t* sp, const double* Q, const do
   free(Bm); free(t1); free(t2); free(P);
 }
 
+/* nijt=Naive [Bio++ NaiveSubstitutionCount; pinned by Myo_naive.vec / Myo_naive_grantham.vec]: one
+ * substitution (or its weight) whenever the two ends of the branch differ, whatever its length. */
+static void counts_naive(const spectral_t* sp, const double* weights, double* N) {
+  const int A = sp->A;
+  for (int x = 0; x < A; x++)
+    for (int y = 0; y < A; y++) N[x * A + y] = x == y ? 0. : (weights ? weights[x * A + y] : 1.);
+}
+
 static void counts_any(int method, const spectral_t* sp, const double* Q, const double* weights,
                        double t, double* N) {
-  if (method == ORC_COUNT_DECOMPOSITION) counts_decomposition(sp, Q, weights, t, N);
+  if (method == ORC_COUNT_NAIVE) counts_naive(sp, weights, N);
+  else if (method == ORC_COUNT_DECOMPOSITION) counts_decomposition(sp, Q, weights, t, N);
   else counts_uniformization(sp, Q, weights, t, N);
 }
 
 int orc_counts(int method, int A, const double* Q, const double* pi, const double* weights,
                double t, double* N) {
   spectral_t sp;
-  if (method != ORC_COUNT_UNIFORMIZATION && method != ORC_COUNT_DECOMPOSITION)
-    FAIL("orc_counts: unknown method %d", method);
+  if (method < ORC_COUNT_UNIFORMIZATION || method > ORC_COUNT_NAIVE) FAIL("orc_counts: unknown method %d", method);
   if (spectral_init(&sp, A, Q, pi)) return -1;
   counts_any(method, &sp, Q, weights, t, N);
   spectral_free(&sp);

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-enum { ORC_COUNT_UNIFORMIZATION = 0, ORC_COUNT_DECOMPOSITION = 1 };
+enum { ORC_COUNT_UNIFORMIZATION = 0, ORC_COUNT_DECOMPOSITION = 1, ORC_COUNT_NAIVE = 2 };
 enum {
   ORC_STAT_CORRELATION = 0,
   ORC_STAT_COVARIANCE = 1,

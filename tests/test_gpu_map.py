@@ -102,6 +102,30 @@ def test_map_myoglobin_golden(ctx):
     assert np.all(np.abs(r["loglik"] - m["golden"]["infos_logl"]) <= 6e-6 * np.abs(m["golden"]["infos_logl"]))
 
 
+@pytest.mark.parametrize("method,key", [("naive", "vec_naive"), ("naive", "vec_naive_grantham"),
+                                        ("uniformization", "vec_unif_grantham"), ("decomposition", "vec_decomp_grantham")])
+def test_map_count_methods_and_weights_vs_reference_goldens(ctx, method, key):
+    """nijt=Naive and the Grantham-weighted counts on the device against the oracle (1e-9) and against
+    the reference's own golden vectors (examples/Proteins/Benchmark/CoMap/Myo_*.vec, printed precision)."""
+    import os
+    m = H.myoglobin_inputs()
+    W = None
+    if key.endswith("grantham"):
+        path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "comap_b200", "data", "grantham.dat")
+        W = np.array([[float(x) for x in ln.split()] for ln in open(path) if ln.strip() and not ln.startswith("#")])
+    ctx.set_tree(m["parent"], m["brlen"])
+    ctx.set_model(m["Q"], m["pi"], m["rates"], m["probs"], count_method=method, weights=W)
+    ctx.set_alignment(m["codes"], m["code_mask"])
+    r = ctx.map()
+    q = O.map_sites(m["parent"], m["brlen"], m["Q"], m["pi"], m["rates"], m["probs"], m["codes"], m["code_mask"],
+                    method=method, weights=W)
+    assert np.allclose(r["n"], q["n"], rtol=RTOL, atol=1e-15)
+    gold = m["golden"][key].T
+    big = gold > 1e-9
+    rel = np.abs(r["n"] - gold)[big] / gold[big]
+    assert np.median(rel) < 5e-6 and rel.max() < 3e-4
+
+
 def test_errors_are_reported(ctx):
     from comap_b200 import api
     c2 = api.Context()

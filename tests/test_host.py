@@ -123,6 +123,9 @@ def test_count_weights_and_second_data_set_options(binary, tmp_path):
     p, o = dry_run(binary, str(tmp_path), *common, "nijt=Decomposition(weight=Diff(index1=Charge, symmetrical=yes))")
     W = np.array(o["weights"], dtype=float).reshape(20, 20)
     assert np.array_equal(W, W.T) and W[1, 3] == 2 and o["count_method"] == ["1"]        # R(+1) <-> D(-1)
+    p, o = dry_run(binary, str(tmp_path), *common, "nijt=Naive(weight=AAdist(type=grantham, sym=yes))")
+    W = np.array(o["weights"], dtype=float).reshape(20, 20)                              # Grantham 1974
+    assert o["count_method"] == ["2"] and W[0, 1] == 112 and W[4, 17] == 215 and W[9, 10] == 5 and np.array_equal(W, W.T)
     p, o = dry_run(binary, str(tmp_path), *common)
     assert o["weights"] == []
     # second data set: same files, all sites instead of the complete ones; the tree is copied

@@ -575,10 +575,15 @@ int main(int argc, char** argv) {
         int dist_id;
         if (dm == "Euclidian" || dm == "euclidian") dist_id = CMB_DIST_EUCLIDIAN;
         else if (dm == "Correlation" || dm == "cor") dist_id = CMB_DIST_CORRELATION;
-        else if (dm == "Compensation" || dm == "comp")
-          throw Error("Compensation distance must be used with a mapping procedure allowing weights, e.g. "
-                      "'nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))'.");
-        else throw Error("Unknown distance method.");
+        else if (dm == "Compensation" || dm == "comp") { // CoMap.cpp:412-422
+          if (in.weights.empty())
+            throw Error("Compensation distance must be used with a mapping procedure with weights, e.g. "
+                        "'nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))'.");
+          if (in.weights_symmetric)
+            throw Error("Compensation distance must be used with a mapping procedure allowing non-symmetric weights, e.g. "
+                        "'nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))'.");
+          dist_id = CMB_DIST_COMPENSATION;
+        } else throw Error("Unknown distance method.");
         display_result("Distance to use", dm);
         int link;
         if (method == "complete") link = CMB_LINK_COMPLETE;

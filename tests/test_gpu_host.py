@@ -222,6 +222,31 @@ def test_weighted_counts_and_compensation_statistic(myo):
     assert p.returncode == 255 and "non-symmetric weights" in p.stdout
 
 
+def test_clustering_with_the_compensation_distance(myo):
+    """examples/Proteins/GroupsCompensation: clustering.distance=comp on a signed volume-change mapping
+    (CoMap.cpp:412-422; Distance.h:382-422): groups, Dmax and the compensation group statistic."""
+    from comap_b200 import api
+    tmp, _ = myo
+    args = [a for a in COMMON if not a.startswith("nijt=")] + ["nijt=Uniformization(weight=Diff(index1=Volume, symmetrical=no))"]
+    run(tmp, *args, "analysis=clustering", "clustering.distance=comp", "clustering.method=complete",
+        "clustering.output.groups.file=cgroups.txt", "clustering.maximum_group_size=5", "clustering.null=no")
+    c = host_inputs(tmp)
+    W = VOLUME[None, :] - VOLUME[:, None]
+    ctx = api.Context(device=0)
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"], weights=W)
+    ctx.set_alignment(c["codes"], c["code_mask"]); ctx.map()
+    ctx.distance_matrix("compensation"); ctx.cluster("complete")
+    grp = ctx.groups("compensation", 5)
+    hdr, rows = table(os.path.join(tmp, "cgroups.txt"))
+    assert hdr == ["Group", "Size", "IsConstant", "Dmax", "Stat", "Nmin"] and len(rows) == len(grp["members"]) > 10
+    co = c["coords"]
+    assert [r[0] for r in rows] == ["[" + ";".join(str(co[x]) for x in mem) + "]" for mem in grp["members"]]
+    assert [r[4] for r in rows] == [g(v) for v in grp["stat"]] and [r[3] for r in rows] == [g(2 * h) for h in grp["height"]]
+    p = subprocess.run([BIN] + COMMON + ["analysis=clustering", "clustering.distance=comp"], cwd=tmp, capture_output=True, text=True)
+    assert p.returncode == 255 and "with weights" in p.stdout
+    ctx.close()
+
+
 def test_mutual_information_from_the_cli(myo):
     """statistic=MI(threshold=0.5) with nijt=Uniformization (CoETools.cpp:576-596)."""
     from comap_b200 import api

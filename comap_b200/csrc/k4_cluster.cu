@@ -38,6 +38,7 @@ struct ClusterParams {
   int32_t* part_idx;
   double* scan_val;     // [grid] per-CTA first minimum of its slice of the cached row minima
   int32_t* scan_idx;
+  int32_t* scan_col;     // [grid] ... and the column of that minimum (saves a dependent load after the grid sync)
   double* seg_val;      // [grid] partial minima of row segments (a queued row is rescanned by several CTAs)
   int32_t* seg_idx;
   int32_t* seg_cnt;     // [grid] segments of a queued row finished so far
@@ -117,39 +118,69 @@ __global__ void __launch_bounds__(CT) k4_init_rows(ClusterParams p) {
 // cached minimum pointed at a or b for a rescan, and reduces the new row a's own minimum on the
 // fly (per-CTA partial); grid sync; (B) bookkeeping, row a's minimum from the partials, rescans;
 // grid sync.  ncu / clock64 on config 5 (S = 20 000) before this layout: 73 us per merge, of
-// which 21 us in (1) and 47 us in serial rescans of row a and ~40 queued rows.
+// which 21 us in (1) and 47 us in serial rescans of row a and ~40 queued rows.  Now (-DCMB_K4_TIMING,
+// cycles per merge on a mid-grid CTA): scan 3300 | barrier 2800 | combine 3400 | update 1400 |
+// barrier 6400 (waits for CTA 0's 4000) | rescans 2800 (slowest CTA 8200) | barrier 10000.  A barrier
+// costs ~2500 cycles and a round trip to data another SM has just written ~1000, whatever the grid
+// size (16..148 CTAs measured the same).  A two-barrier variant that rescans a queued row inside the
+// CTA that found it (kept as scratch/k4_two_barrier_variant.cu.txt, parity-green) was slower, 29 us per
+// merge: one CTA needs five dependent batches per 160 KB row while the rest of the grid waits.  Per-CTA
+// queue slots instead of the global atomic worklist, and keeping block 0 out of the row update, changed
+// nothing either: the second barrier costs 6000 cycles with or without them (its fence waits for the
+// scattered column-a stores).
 __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
   cg::grid_group grid = cg::this_grid();
   __shared__ Best sh[32];
   const int64_t S = p.S;
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+#ifdef CMB_K4_TIMING
+  long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
+#define K4_T(slot) { t1 = clock64(); tacc[slot] += t1 - t0; t0 = t1; }
+#else
+#define K4_T(slot)
+#endif
   for (int64_t step = 0; step + 2 < S; step++) {
+#ifdef CMB_K4_TIMING
+    t0 = clock64();
+#endif
     // (1) first global minimum of the cached row minima: every CTA scans its slice (one batch of
     //     loads), then all CTAs reduce the per-CTA partials; the extra grid sync (~1.4 us) costs
     //     less than the five dependent L2 round trips of a full scan per CTA
     Best b{0., -1};
+    __shared__ int sh_col;
+    int my_i = -1, my_col = -1; // this thread's candidate row and the column of its minimum
     {
       const int64_t per = (S + gridDim.x - 1) / gridDim.x, lo = (int64_t)blockIdx.x * per, hi = lo + per < S ? lo + per : S;
       for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
         const int ix = p.rmin_idx[i];
         const double v = p.rmin_val[i];
-        if (ix >= 0 && better(v, (int)i, b)) { b.v = v; b.i = (int)i; }
+        if (ix >= 0 && better(v, (int)i, b)) { b.v = v; b.i = (int)i; my_col = ix; }
       }
+      my_i = b.i;
       b = block_best(b, sh);
       if (threadIdx.x == 0) { p.scan_val[blockIdx.x] = b.v; p.scan_idx[blockIdx.x] = b.i; }
+      if (my_i >= 0 && my_i == b.i) p.scan_col[blockIdx.x] = my_col; // a row belongs to one thread: one writer
+      K4_T(0)
       grid.sync();
+      K4_T(1)
+      // the column travels with the partial, so no load depends on the reduced row index
       b = Best{0., -1};
+      my_i = -1;
       for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
         const int i = p.scan_idx[c];
         const double v = p.scan_val[c];
-        if (i >= 0 && better(v, i, b)) { b.v = v; b.i = i; }
+        const int col = p.scan_col[c];
+        if (i >= 0 && better(v, i, b)) { b.v = v; b.i = i; my_col = col; }
       }
+      my_i = b.i;
       __syncthreads(); // sh is reused
     }
     b = block_best(b, sh);
     const int a = b.i;
     if (a < 0) return; // nothing mergeable (NaN distances): host reports the error
-    const int bb = p.rmin_idx[a];
+    if (my_i == a) sh_col = my_col; // rows are unique across the partials: one writer
+    __syncthreads();
+    const int bb = sh_col;
     const double dab = b.v;
     double w1, w2, w4;
     if (p.linkage == 1) { w1 = .5; w2 = .5; w4 = -.5; }
@@ -159,6 +190,7 @@ __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
       w1 = na / (na + nb); w2 = nb / (na + nb); w4 = 0.;
     }
     __syncthreads(); // sh is reused below
+    K4_T(2)
     // (A) new distances to the merged cluster (slot a)
     int32_t* wl = p.wl + (step & 1) * S;
     int32_t* wlc = p.wl_count + (step & 1);
@@ -169,8 +201,12 @@ __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
     double pend_v[kMaxPending];
     int n_pend = 0;
     for (int64_t k = gtid; k < S; k += gsz) {
-      if (k == a || k == bb || !p.alive[k]) continue;
+      // one round trip: everything this row can need is loaded before the first branch
+      const uint8_t live = p.alive[k];
       const double d1 = p.mat[(size_t)a * S + k], d2 = p.mat[(size_t)bb * S + k];
+      const int ci = p.rmin_idx[k];
+      const double cv = p.rmin_val[k];
+      if (k == a || k == bb || !live) continue;
       // left-to-right, unfused, as the reference's C++ expression evaluates
       const double nd = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w1, d1), __dmul_rn(w2, d2)), __dmul_rn(0., dab)),
                                   __dmul_rn(w4, fabs(__dadd_rn(d1, -d2))));
@@ -178,27 +214,28 @@ __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
       p.mat[(size_t)k * S + a] = nd;
       if (k > a) {
         if (!(nd != nd) && better(nd, (int)k, ra)) { ra.v = nd; ra.i = (int)k; }
-        if (k < bb && p.rmin_idx[k] == bb) wl[atomicAdd(wlc, 1)] = (int32_t)k; // lost its minimum's column
+        if (k < bb && ci == bb) wl[atomicAdd(wlc, 1)] = (int32_t)k; // lost its minimum's column
       } else {
-        const int ci = p.rmin_idx[k];
         if (ci == a || ci == bb) wl[atomicAdd(wlc, 1)] = (int32_t)k;            // minimum pointed at a merged slot
-        else {
-          const double cv = p.rmin_val[k];                                       // only column a changed: compare
-          if (!(nd != nd) && (ci < 0 || nd < cv || (nd == cv && a < ci)) && n_pend < kMaxPending) {
-            pend_k[n_pend] = (int)k; pend_v[n_pend] = nd; n_pend++;
-          }
+        else if (!(nd != nd) && (ci < 0 || nd < cv || (nd == cv && a < ci)) && n_pend < kMaxPending) {
+          pend_k[n_pend] = (int)k; pend_v[n_pend] = nd; n_pend++;              // only column a changed: compare
         }
       }
     }
     ra = block_best(ra, sh);
     if (threadIdx.x == 0) { p.part_val[blockIdx.x] = ra.v; p.part_idx[blockIdx.x] = ra.i; }
+    K4_T(3)
     grid.sync();
+    K4_T(4)
     // (B) deferred in-place updates, bookkeeping, row a's cached minimum from the per-CTA
     //     partials, queued rescans
 #pragma unroll
     for (int q = 0; q < kMaxPending; q++)
       if (q < n_pend) { p.rmin_val[pend_k[q]] = pend_v[q]; p.rmin_idx[pend_k[q]] = a; }
     if (blockIdx.x == 0) {
+      // slot state of a and bb, loaded before the reduction of the partials hides their latency
+      double len_a = 0.; int node_a = 0, node_b = 0, nl_a = 0, nl_b = 0;
+      if (threadIdx.x == 0) { len_a = p.len[a]; node_a = p.node[a]; node_b = p.node[bb]; nl_a = p.nleaves[a]; nl_b = p.nleaves[bb]; }
       Best t{0., -1};
       for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
         const int i = p.part_idx[c];
@@ -209,13 +246,13 @@ __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
       if (threadIdx.x == 0) {
         const int32_t parent = (int32_t)(S + step);
         const double half = dab / 2.;
-        const double d0 = half - p.len[a];
-        p.left[step] = p.node[a];
-        p.right[step] = p.node[bb];
-        p.height[step] = p.len[a] + d0;
+        const double d0 = half - len_a;
+        p.left[step] = node_a;
+        p.right[step] = node_b;
+        p.height[step] = len_a + d0;
         p.node[a] = parent;
-        p.len[a] = p.len[a] + d0;
-        p.nleaves[a] += p.nleaves[bb];
+        p.len[a] = len_a + d0;
+        p.nleaves[a] = nl_a + nl_b;
         p.alive[bb] = 0;
         p.rmin_idx[bb] = -1;  // dead rows drop out of (1)
         p.rmin_val[a] = t.v;
@@ -258,8 +295,15 @@ __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
       }
       __syncthreads();
     }
+    K4_T(5)
     grid.sync();
+    K4_T(6)
   }
+#ifdef CMB_K4_TIMING
+  if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == gridDim.x - 1))
+    printf("k4 timing cta %d: scan %lld sync1 %lld combine %lld update %lld sync2 %lld rescans %lld sync3 %lld (cycles per merge)\n",
+           blockIdx.x, tacc[0] / (S - 2), tacc[1] / (S - 2), tacc[2] / (S - 2), tacc[3] / (S - 2), tacc[4] / (S - 2), tacc[5] / (S - 2), tacc[6] / (S - 2));
+#endif
   // finalStep: join the last two clusters at d/2
   if (gtid == 0) {
     int i1 = -1, i2 = -1;
@@ -316,7 +360,8 @@ int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* l
   size_t o_val = 0, o_idx = al(o_val + 8 * S), o_alive = al(o_idx + 4 * S), o_len = al(o_alive + S),
          o_nl = al(o_len + 8 * S), o_node = al(o_nl + 4 * S), o_wl = al(o_node + 4 * S), o_wlc = al(o_wl + 8 * S),
          o_pv = al(o_wlc + 64), o_pi = al(o_pv + 8 * 1024), o_sv = al(o_pi + 4 * 1024), o_si = al(o_sv + 8 * 1024),
-         o_gv = al(o_si + 4 * 1024), o_gi = al(o_gv + 8 * 1024), o_gc = al(o_gi + 4 * 1024), o_end = al(o_gc + 4 * 1024);
+         o_sc = al(o_si + 4 * 1024),
+         o_gv = al(o_sc + 4 * 1024), o_gi = al(o_gv + 8 * 1024), o_gc = al(o_gi + 4 * 1024), o_end = al(o_gc + 4 * 1024);
   work.reserve(o_end);
   unsigned char* w = work.as<unsigned char>();
   ClusterParams p;
@@ -325,7 +370,7 @@ int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* l
   p.len = (double*)(w + o_len); p.nleaves = (int32_t*)(w + o_nl); p.node = (int32_t*)(w + o_node);
   p.wl = (int32_t*)(w + o_wl); p.wl_count = (int32_t*)(w + o_wlc);
   p.part_val = (double*)(w + o_pv); p.part_idx = (int32_t*)(w + o_pi);
-  p.scan_val = (double*)(w + o_sv); p.scan_idx = (int32_t*)(w + o_si);
+  p.scan_val = (double*)(w + o_sv); p.scan_idx = (int32_t*)(w + o_si); p.scan_col = (int32_t*)(w + o_sc);
   p.seg_val = (double*)(w + o_gv); p.seg_idx = (int32_t*)(w + o_gi); p.seg_cnt = (int32_t*)(w + o_gc);
   CMB_CUDA(cudaMemsetAsync(p.seg_cnt, 0, 4 * 1024, st));
   p.left = left_dev; p.right = right_dev; p.height = height_dev;

@@ -72,6 +72,29 @@ def test_cluster_with_ties_matches_reference_order(ctx):
     assert np.array_equal(left, ol) and np.array_equal(right, orr) and np.array_equal(height, oh)
 
 
+@pytest.mark.parametrize("S", [2, 3, 5, 33])
+def test_cluster_tiny_alignments(ctx, S):
+    """Two sites = the final join only; three = one merge + the final join; sizes below one warp."""
+    c = H.random_dna_case(9, 120, 77, mean_brlen=0.15)
+    keep = [s for s in range(120) if len(set(c["codes"][:, s])) > 1][:S]
+    assert len(keep) == S
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(np.ascontiguousarray(c["codes"][:, keep]), c["code_mask"])
+    r = ctx.map()
+    g, k = ctx.pairs("correlation", use_null=False)
+    o = O.pairs("correlation", r["n"], r["norm"], r["post_rate"], r["rate_class"])
+    assert k == S * (S - 1) // 2 and np.array_equal(g["stat"], o["stat"])
+    for linkage in ("complete", "single", "average"):
+        mat = ctx.distance_matrix("correlation")
+        left, right, height = ctx.cluster(linkage)
+        ol, orr, oh = O.hclust(linkage, mat)
+        assert np.array_equal(left, ol) and np.array_equal(right, orr) and np.array_equal(height, oh)
+        gr = ctx.groups("correlation", S)
+        og = O.groups("correlation", r["n"], r["norm"], ol, orr, oh, S)
+        assert len(gr["members"]) == len(og["members"]) == S - 1
+        assert np.array_equal(gr["stat"], og["stat"])
+
+
 @pytest.mark.parametrize("linkage", ["complete", "single", "average"])
 def test_cluster_dsmem_layout_equals_oracle(ctx, linkage, monkeypatch):
     """The opt-in 16-CTA thread-block-cluster kernel (CMB_K4_LAYOUT=cluster, cached minima in

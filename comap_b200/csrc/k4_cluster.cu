@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(CT) k4_init_rows(ClusterParams p) {
 // barrier 6400 (waits for CTA 0's 4000) | rescans 2800 (slowest CTA 8200) | barrier 10000.  A barrier
 // costs ~2500 cycles and a round trip to data another SM has just written ~1000, whatever the grid
 // size (16..148 CTAs measured the same).  A two-barrier variant that rescans a queued row inside the
-// CTA that found it (kept as scratch/k4_two_barrier_variant.cu.txt, parity-green) was slower, 29 us per
+// CTA that found it (kept as tools/experiments/k4_two_barrier_variant.cu.txt, parity-green) was slower, 29 us per
 // merge: one CTA needs five dependent batches per 160 KB row while the rest of the grid waits.  Per-CTA
 // queue slots instead of the global atomic worklist, and keeping block 0 out of the row update, changed
 // nothing either: the second barrier costs 6000 cycles with or without them (its fence waits for the

@@ -195,6 +195,36 @@ void cluster_on_device(Context& c, int linkage, int64_t S) {
     if (c.h_left[k] < 0) fail("clustering stopped early: the distance matrix holds NaN");
 }
 
+// nb dendrograms (replicates of the clustering null) in one cooperative launch; results per problem
+struct DendroHost { std::vector<int32_t> left, right; std::vector<double> height; };
+void cluster_batch_on_device(Context& c, int linkage, int64_t S, int nb, DevBuf* dists, DevBuf* works, DevBuf& staging,
+                             DendroHost* out) {
+  if (linkage < 0 || linkage > 2) fail("unknown clustering method %d", linkage);
+  if (S < 2) fail("clustering needs at least 2 sites");
+  auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
+  const size_t o_r = al(4 * S), o_h = al(o_r + 4 * S), per = al(o_h + 8 * S);
+  staging.reserve(per * nb);
+  unsigned char* sb = staging.as<unsigned char>();
+  double* mats[4]; int32_t* l[4]; int32_t* r[4]; double* h[4];
+  for (int q = 0; q < nb; q++) {
+    mats[q] = dists[q].as<double>();
+    l[q] = (int32_t*)(sb + per * q); r[q] = (int32_t*)(sb + per * q + o_r); h[q] = (double*)(sb + per * q + o_h);
+  }
+  c.prof_begin("cluster");
+  int nl = launch_cluster_batch(nb, S, linkage, mats, works, l, r, h, c.stream);
+  c.prof_end(nl);
+  for (int q = 0; q < nb; q++) {
+    out[q].left.resize(S - 1); out[q].right.resize(S - 1); out[q].height.resize(S - 1);
+    CMB_CUDA(cudaMemcpyAsync(out[q].left.data(), l[q], 4 * (S - 1), cudaMemcpyDeviceToHost, c.stream));
+    CMB_CUDA(cudaMemcpyAsync(out[q].right.data(), r[q], 4 * (S - 1), cudaMemcpyDeviceToHost, c.stream));
+    CMB_CUDA(cudaMemcpyAsync(out[q].height.data(), h[q], 8 * (S - 1), cudaMemcpyDeviceToHost, c.stream));
+  }
+  CMB_CUDA(cudaStreamSynchronize(c.stream));
+  for (int q = 0; q < nb; q++)
+    for (int64_t k = 0; k + 1 < S; k++)
+      if (out[q].left[k] < 0) fail("clustering stopped early: the distance matrix holds NaN");
+}
+
 // One group per inner node of the dendrogram, emitted in post-order with members in DFS
 // leaf order (ClusterTools::getGroups, ClusterTools.cpp:59-113), Nmin = min leaf norm
 // (:296-319), Stat per Distance::setStatisticAsProperty (Distance.h:109-129,346-368,
@@ -550,40 +580,64 @@ int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t se
   MapModel m = c.map_model();
   int64_t rows = 0, mem = 0;
   if (offsets) offsets[0] = 0;
-  DevBuf mean, sd, norm;
-  std::vector<double> h_norm(S);
-  for (int rep = rep_begin; rep < rep_end; rep++) {
-    // ClusterTools.cpp:224-227: simulate sizeOfDataSet sites, re-initialise, map
-    MapBuffers b = sim_buffers(c, 0, S, S_pad);
-    c.prof_begin("simulate");
-    launch_simulate(m, c.sim_stream, seed, (int64_t)rep * S, S, 0, S, S_pad, weighted_classes, c.tree.n_nodes - 1,
-                    c.s_tips[0].as<uint8_t>(), nullptr, c.stream);
-    c.prof_end(1);
-    c.run_map(b, true);
-    mean.reserve(sizeof(double) * S_pad); sd.reserve(sizeof(double) * S_pad); norm.reserve(sizeof(double) * S_pad);
-    launch_prep(B, S, S_pad, b.out, nullptr, mean.as<double>(), sd.as<double>(), norm.as<double>(), c.stream);
-    c.prof.total_launches += 1;
-    CMB_CUDA(cudaMemcpyAsync(h_norm.data(), norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
-    distance_on_device(c, dist_id, b.out, S, S_pad, mean.as<double>(), sd.as<double>(), norm.as<double>());
-    cluster_on_device(c, linkage, S);
-    GroupTable g;
-    groups_of_dendrogram(c, dist_id, max_size, S, S_pad, b.out, h_norm.data(), g);
-    const int64_t ng = (int64_t)g.height.size();
-    if (rows + ng > capacity_rows || mem + (int64_t)g.members.size() > capacity_members)
-      fail("cmb_cluster_null: output capacity exceeded");
-    for (int64_t k = 0; k < ng; k++) {
-      if (row_rep) row_rep[rows + k] = rep;
-      if (row_size) row_size[rows + k] = (int32_t)(g.offsets[k + 1] - g.offsets[k]);
-      if (row_dmax) row_dmax[rows + k] = g.height[k] * 2.; // ClusterTools.cpp:286
-      if (row_stat) row_stat[rows + k] = g.stat[k];
-      if (row_nmin) row_nmin[rows + k] = g.nmin[k];
-      if (offsets) offsets[rows + k + 1] = mem + g.offsets[k + 1];
+  DevBuf mean, sd, norm, staging;
+  // Replicates are clustered in batches: the merge loop is a chain of barrier latencies, so up to four
+  // dendrograms advance through the same barriers (k4_cluster<NP>).  Each needs its own matrix and vectors.
+  size_t free_b = 0, total_b = 0;
+  CMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  const size_t per_rep = sizeof(double) * ((size_t)S * S + (size_t)B * S_pad) + ((size_t)64 << 20);
+  int NB = (int)std::min<size_t>(4, std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / per_rep));
+  if (const char* e = std::getenv("CMB_K4_BATCH")) NB = std::max(1, std::min(4, atoi(e)));
+  DevBuf dists[4], works[4], outs[4];
+  std::vector<double> h_norms[4];
+  DendroHost dendro[4];
+  for (int rep0 = rep_begin; rep0 < rep_end; rep0 += NB) {
+    const int nb = std::min(NB, rep_end - rep0);
+    for (int q = 0; q < nb; q++) {
+      const int rep = rep0 + q;
+      // ClusterTools.cpp:224-227: simulate sizeOfDataSet sites, re-initialise, map
+      MapBuffers b = sim_buffers(c, 0, S, S_pad);
+      c.prof_begin("simulate");
+      launch_simulate(m, c.sim_stream, seed, (int64_t)rep * S, S, 0, S, S_pad, weighted_classes, c.tree.n_nodes - 1,
+                      c.s_tips[0].as<uint8_t>(), nullptr, c.stream);
+      c.prof_end(1);
+      c.run_map(b, true);
+      mean.reserve(sizeof(double) * S_pad); sd.reserve(sizeof(double) * S_pad); norm.reserve(sizeof(double) * S_pad);
+      launch_prep(B, S, S_pad, b.out, nullptr, mean.as<double>(), sd.as<double>(), norm.as<double>(), c.stream);
+      c.prof.total_launches += 1;
+      h_norms[q].resize(S);
+      CMB_CUDA(cudaMemcpyAsync(h_norms[q].data(), norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+      distance_on_device(c, dist_id, b.out, S, S_pad, mean.as<double>(), sd.as<double>(), norm.as<double>());
+      std::swap(c.d_dist, dists[q]); // the matrix stays with this replicate; the next one gets (or allocates) another
+      outs[q].reserve(sizeof(double) * (size_t)B * S_pad); // the group statistics need this replicate's vectors
+      CMB_CUDA(cudaMemcpyAsync(outs[q].p, b.out, sizeof(double) * (size_t)B * S_pad, cudaMemcpyDeviceToDevice, c.stream));
     }
-    if (members && !g.members.empty()) std::memcpy(members + mem, g.members.data(), sizeof(int32_t) * g.members.size());
-    rows += ng;
-    mem += (int64_t)g.members.size();
+    cluster_batch_on_device(c, linkage, S, nb, dists, works, staging, dendro);
+    for (int q = 0; q < nb; q++) {
+      const int rep = rep0 + q;
+      c.h_left.swap(dendro[q].left); c.h_right.swap(dendro[q].right); c.h_height.swap(dendro[q].height);
+      GroupTable g;
+      groups_of_dendrogram(c, dist_id, max_size, S, S_pad, outs[q].as<double>(), h_norms[q].data(), g);
+      const int64_t ng = (int64_t)g.height.size();
+      if (rows + ng > capacity_rows || mem + (int64_t)g.members.size() > capacity_members)
+        fail("cmb_cluster_null: output capacity exceeded");
+      for (int64_t k = 0; k < ng; k++) {
+        if (row_rep) row_rep[rows + k] = rep;
+        if (row_size) row_size[rows + k] = (int32_t)(g.offsets[k + 1] - g.offsets[k]);
+        if (row_dmax) row_dmax[rows + k] = g.height[k] * 2.; // ClusterTools.cpp:286
+        if (row_stat) row_stat[rows + k] = g.stat[k];
+        if (row_nmin) row_nmin[rows + k] = g.nmin[k];
+        if (offsets) offsets[rows + k + 1] = mem + g.offsets[k + 1];
+      }
+      if (members && !g.members.empty()) std::memcpy(members + mem, g.members.data(), sizeof(int32_t) * g.members.size());
+      rows += ng;
+      mem += (int64_t)g.members.size();
+    }
   }
+  for (int q = 0; q < 4; q++) { dists[q].release(); works[q].release(); outs[q].release(); }
+  staging.release();
   mean.release(); sd.release(); norm.release();
+  c.have_dist = false; // the matrices were consumed
   c.have_dendro = false;
   if (n_rows) *n_rows = rows;
   CMB_CATCH

@@ -136,11 +136,37 @@ __global__ void __launch_bounds__(CT) k4_init_rows(ClusterParams p) {
 // 15.5 -> 12 us per merge (scan 1800 | barrier 2700 | combine 2000 | update 730 | barrier 4900 |
 // rescans 2300, slowest CTA 6700 | barrier 8200).  A hand-written barrier (red.release.gpu on a monotone
 // counter + ld.acquire.gpu poll) instead of cooperative_groups' grid.sync() measured the same 2700 cycles.
-__global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
+// NP independent dendrograms (replicates of the clustering null) advance in lock step through the same
+// three barriers: a merge is a chain of barrier and memory latencies, not work, so a second and a
+// fourth problem ride along almost for free.
+constexpr int kMaxBatch = 4;
+struct ClusterBatch { ClusterParams p[kMaxBatch]; };
+
+template <int NP>
+__device__ __forceinline__ void block_best_n(Best (&b)[NP], Best (*sh)[32]) {
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+#pragma unroll
+  for (int q = 0; q < NP; q++) b[q] = warp_best(b[q]);
+  __syncthreads();
+  if (l == 0) {
+#pragma unroll
+    for (int q = 0; q < NP; q++) sh[q][w] = b[q];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int q = 0; q < NP; q++) b[q] = warp_best(l < (int)(blockDim.x >> 5) ? sh[q][l] : Best{0., -1});
+}
+
+template <int NP>
+__global__ void __launch_bounds__(CT) k4_cluster(const __grid_constant__ ClusterBatch B) {
   cg::grid_group grid = cg::this_grid();
-  __shared__ Best sh[32];
-  const int64_t S = p.S;
-  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)gridDim.x * blockDim.x;
+  __shared__ Best sh[NP][32];
+  __shared__ int sh_col[NP];
+  const int64_t S = B.p[0].S;
+  const int linkage = B.p[0].linkage;
+  const int G = (int)gridDim.x;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, gsz = (int64_t)G * blockDim.x;
+  const int64_t per = (S + G - 1) / G, lo = (int64_t)blockIdx.x * per, hi = lo + per < S ? lo + per : S;
 #ifdef CMB_K4_TIMING
   long long tacc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t0 = 0, t1 = 0;
 #define K4_T(slot) { t1 = clock64(); tacc[slot] += t1 - t0; t0 = t1; }
@@ -151,154 +177,207 @@ __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
 #ifdef CMB_K4_TIMING
     t0 = clock64();
 #endif
-    // (1) first global minimum of the cached row minima: every CTA scans its slice (one batch of
-    //     loads), then all CTAs reduce the per-CTA partials; the extra grid sync (~1.4 us) costs
-    //     less than the five dependent L2 round trips of a full scan per CTA
-    Best b{0., -1};
-    __shared__ int sh_col;
-    int my_i = -1, my_col = -1; // this thread's candidate row and the column of its minimum
+    // (1) first global minimum of the cached row minima: every CTA scans its slice (the loads of
+    //     all problems are issued together), publishes (value, row, column), grid barrier, then all
+    //     CTAs reduce the per-CTA partials
+    Best b[NP];
+    int my_i[NP], my_col[NP];
     {
-      const int64_t per = (S + gridDim.x - 1) / gridDim.x, lo = (int64_t)blockIdx.x * per, hi = lo + per < S ? lo + per : S;
-      for (int64_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-        const int ix = p.rmin_idx[i];
-        const double v = p.rmin_val[i];
-        if (ix >= 0 && better(v, (int)i, b)) { b.v = v; b.i = (int)i; my_col = ix; }
+      int ix0[NP]; double v0[NP];
+      const int64_t i0 = lo + threadIdx.x;
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        ix0[q] = -1; v0[q] = 0.;
+        if (i0 < hi) { ix0[q] = B.p[q].rmin_idx[i0]; v0[q] = B.p[q].rmin_val[i0]; }
       }
-      my_i = b.i;
-      b = block_best(b, sh);
-      if (threadIdx.x == 0) { p.scan_val[blockIdx.x] = b.v; p.scan_idx[blockIdx.x] = b.i; }
-      if (my_i >= 0 && my_i == b.i) p.scan_col[blockIdx.x] = my_col; // a row belongs to one thread: one writer
-      K4_T(0)
-      grid.sync();
-      K4_T(1)
-      // the column travels with the partial, so no load depends on the reduced row index
-      b = Best{0., -1};
-      my_i = -1;
-      for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
-        const int i = p.scan_idx[c];
-        const double v = p.scan_val[c];
-        const int col = p.scan_col[c];
-        if (i >= 0 && better(v, i, b)) { b.v = v; b.i = i; my_col = col; }
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        b[q] = Best{0., -1}; my_col[q] = -1;
+        if (ix0[q] >= 0) { b[q].v = v0[q]; b[q].i = (int)i0; my_col[q] = ix0[q]; }
+        for (int64_t i = i0 + blockDim.x; i < hi; i += blockDim.x) { // only above S = grid x block
+          const int ix = B.p[q].rmin_idx[i];
+          const double v = B.p[q].rmin_val[i];
+          if (ix >= 0 && better(v, (int)i, b[q])) { b[q].v = v; b[q].i = (int)i; my_col[q] = ix; }
+        }
+        my_i[q] = b[q].i;
       }
-      my_i = b.i;
-      __syncthreads(); // sh is reused
     }
-    b = block_best(b, sh);
-    const int a = b.i;
-    if (a < 0) return; // nothing mergeable (NaN distances): host reports the error
-    if (my_i == a) sh_col = my_col; // rows are unique across the partials: one writer
+    block_best_n<NP>(b, sh);
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+      if (threadIdx.x == 0) { B.p[q].scan_val[blockIdx.x] = b[q].v; B.p[q].scan_idx[blockIdx.x] = b[q].i; }
+      if (my_i[q] >= 0 && my_i[q] == b[q].i) B.p[q].scan_col[blockIdx.x] = my_col[q]; // a row belongs to one thread
+    }
+    K4_T(0)
+    grid.sync();
+    K4_T(1)
+    // the column travels with the partial, so no load depends on the reduced row index
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+      b[q] = Best{0., -1};
+      for (int c = threadIdx.x; c < G; c += blockDim.x) {
+        const int i = B.p[q].scan_idx[c];
+        const double v = B.p[q].scan_val[c];
+        const int col = B.p[q].scan_col[c];
+        if (i >= 0 && better(v, i, b[q])) { b[q].v = v; b[q].i = i; my_col[q] = col; }
+      }
+      my_i[q] = b[q].i;
+    }
+    block_best_n<NP>(b, sh);
+    int a[NP], bb[NP];
+    double dab[NP], w1[NP], w2[NP], w4[NP];
+    bool none = false;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+      a[q] = b[q].i;
+      none |= a[q] < 0;
+      if (a[q] >= 0 && my_i[q] == a[q]) sh_col[q] = my_col[q]; // rows are unique across the partials: one writer
+    }
+    if (none) return; // nothing mergeable (NaN distances), the same in every CTA: host reports the error
     __syncthreads();
-    const int bb = sh_col;
-    const double dab = b.v;
-    double w1, w2, w4;
-    if (p.linkage == 1) { w1 = .5; w2 = .5; w4 = -.5; }
-    else if (p.linkage == 0) { w1 = .5; w2 = .5; w4 = .5; }
-    else {
-      double na = (double)p.nleaves[a], nb = (double)p.nleaves[bb];
-      w1 = na / (na + nb); w2 = nb / (na + nb); w4 = 0.;
+#pragma unroll
+    for (int q = 0; q < NP; q++) {
+      bb[q] = sh_col[q];
+      dab[q] = b[q].v;
+      if (linkage == 1) { w1[q] = .5; w2[q] = .5; w4[q] = -.5; }
+      else if (linkage == 0) { w1[q] = .5; w2[q] = .5; w4[q] = .5; }
+      else {
+        double na = (double)B.p[q].nleaves[a[q]], nb = (double)B.p[q].nleaves[bb[q]];
+        w1[q] = na / (na + nb); w2[q] = nb / (na + nb); w4[q] = 0.;
+      }
     }
-    __syncthreads(); // sh is reused below
     K4_T(2)
-    // (A) new distances to the merged cluster (slot a)
-    int32_t* wl = p.wl + (step & 1) * S;
-    int32_t* wlc = p.wl_count + (step & 1);
-    Best ra{0., -1}; // first minimum of the new row a over live columns k > a
-    // cached minima are still being read by CTAs that are in (1): in-place updates wait for (B)
-    constexpr int kMaxPending = 4; // rows per thread per merge: S <= 4 * grid threads (300 k at 148 x 512)
-    int pend_k[kMaxPending];
-    double pend_v[kMaxPending];
-    int n_pend = 0;
-    for (int64_t k = gtid; k < S; k += gsz) {
-      // one round trip: everything this row can need is loaded before the first branch
-      const uint8_t live = p.alive[k];
-      const double d1 = p.mat[(size_t)a * S + k], d2 = p.mat[(size_t)bb * S + k];
-      const int ci = p.rmin_idx[k];
-      const double cv = p.rmin_val[k];
-      if (k == a || k == bb || !live) continue;
-      // left-to-right, unfused, as the reference's C++ expression evaluates
-      const double nd = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w1, d1), __dmul_rn(w2, d2)), __dmul_rn(0., dab)),
-                                  __dmul_rn(w4, fabs(__dadd_rn(d1, -d2))));
-      p.mat[(size_t)a * S + k] = nd;
-      p.mat[(size_t)k * S + a] = nd;
-      if (k > a) {
-        if (!(nd != nd) && better(nd, (int)k, ra)) { ra.v = nd; ra.i = (int)k; }
-        if (k < bb && ci == bb) wl[atomicAdd(wlc, 1)] = (int32_t)k; // lost its minimum's column
-      } else {
-        if (ci == a || ci == bb) wl[atomicAdd(wlc, 1)] = (int32_t)k;            // minimum pointed at a merged slot
-        else if (!(nd != nd) && (ci < 0 || nd < cv || (nd == cv && a < ci)) && n_pend < kMaxPending) {
-          pend_k[n_pend] = (int)k; pend_v[n_pend] = nd; n_pend++;              // only column a changed: compare
+    // (A) new distances to the merged cluster (slot a).  After the barrier the cached minimum of row k is
+    //     read and written by the thread that owns k only, so a row that only sees a new column compares in
+    //     place; rows whose minimum pointed at a or bb are queued; the new row a's own minimum is reduced on
+    //     the fly (per-CTA partial)
+    Best ra[NP];
+    {
+      uint8_t live0[NP]; double d10[NP], d20[NP], cv0[NP]; int ci0[NP];
+      const int64_t k0 = gtid;
+#pragma unroll
+      for (int q = 0; q < NP; q++) { // one round trip for all problems
+        live0[q] = 0; d10[q] = d20[q] = cv0[q] = 0.; ci0[q] = -1;
+        if (k0 < S) {
+          live0[q] = B.p[q].alive[k0];
+          d10[q] = B.p[q].mat[(size_t)a[q] * S + k0]; d20[q] = B.p[q].mat[(size_t)bb[q] * S + k0];
+          ci0[q] = B.p[q].rmin_idx[k0]; cv0[q] = B.p[q].rmin_val[k0];
         }
       }
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        const ClusterParams& p = B.p[q];
+        int32_t* wl = p.wl + (step & 1) * S;
+        int32_t* wlc = p.wl_count + (step & 1);
+        ra[q] = Best{0., -1};
+        const int aq = a[q], bq = bb[q];
+        auto row = [&](int64_t k, uint8_t live, double d1, double d2, int ci, double cv) {
+          if (k == aq || k == bq || !live) return;
+          // left-to-right, unfused, as the reference's C++ expression evaluates
+          const double nd = __dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(w1[q], d1), __dmul_rn(w2[q], d2)), __dmul_rn(0., dab[q])),
+                                      __dmul_rn(w4[q], fabs(__dadd_rn(d1, -d2))));
+          p.mat[(size_t)aq * S + k] = nd;
+          p.mat[(size_t)k * S + aq] = nd;
+          if (k > aq) {
+            if (!(nd != nd) && better(nd, (int)k, ra[q])) { ra[q].v = nd; ra[q].i = (int)k; }
+            if (k < bq && ci == bq) wl[atomicAdd(wlc, 1)] = (int32_t)k;  // lost its minimum's column
+          } else {
+            if (ci == aq || ci == bq) wl[atomicAdd(wlc, 1)] = (int32_t)k; // minimum pointed at a merged slot
+            else if (!(nd != nd) && (ci < 0 || nd < cv || (nd == cv && aq < ci))) { p.rmin_val[k] = nd; p.rmin_idx[k] = aq; }
+          }
+        };
+        if (k0 < S) row(k0, live0[q], d10[q], d20[q], ci0[q], cv0[q]);
+        for (int64_t k = k0 + gsz; k < S; k += gsz) // only above S = grid x block
+          row(k, p.alive[k], p.mat[(size_t)aq * S + k], p.mat[(size_t)bq * S + k], p.rmin_idx[k], p.rmin_val[k]);
+      }
     }
-    ra = block_best(ra, sh);
-    if (threadIdx.x == 0) { p.part_val[blockIdx.x] = ra.v; p.part_idx[blockIdx.x] = ra.i; }
+    block_best_n<NP>(ra, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int q = 0; q < NP; q++) { B.p[q].part_val[blockIdx.x] = ra[q].v; B.p[q].part_idx[blockIdx.x] = ra[q].i; }
+    }
     K4_T(3)
     grid.sync();
     K4_T(4)
-    // (B) deferred in-place updates, bookkeeping, row a's cached minimum from the per-CTA
-    //     partials, queued rescans
+    // (B) bookkeeping and row a's cached minimum from the per-CTA partials (block 0), queued rescans
+    int n_wl[NP], n_all = 0;
 #pragma unroll
-    for (int q = 0; q < kMaxPending; q++)
-      if (q < n_pend) { p.rmin_val[pend_k[q]] = pend_v[q]; p.rmin_idx[pend_k[q]] = a; }
+    for (int q = 0; q < NP; q++) n_wl[q] = B.p[q].wl_count[step & 1];
     if (blockIdx.x == 0) {
       // slot state of a and bb, loaded before the reduction of the partials hides their latency
-      double len_a = 0.; int node_a = 0, node_b = 0, nl_a = 0, nl_b = 0;
-      if (threadIdx.x == 0) { len_a = p.len[a]; node_a = p.node[a]; node_b = p.node[bb]; nl_a = p.nleaves[a]; nl_b = p.nleaves[bb]; }
-      Best t{0., -1};
-      for (int c = threadIdx.x; c < (int)gridDim.x; c += blockDim.x) {
-        const int i = p.part_idx[c];
-        const double v = p.part_val[c];
-        if (i >= 0 && better(v, i, t)) { t.v = v; t.i = i; }
+      double len_a[NP]; int node_a[NP], node_b[NP], nl_a[NP], nl_b[NP];
+      Best t[NP];
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        const ClusterParams& p = B.p[q];
+        len_a[q] = 0.; node_a[q] = node_b[q] = nl_a[q] = nl_b[q] = 0;
+        if (threadIdx.x == 0) { len_a[q] = p.len[a[q]]; node_a[q] = p.node[a[q]]; node_b[q] = p.node[bb[q]]; nl_a[q] = p.nleaves[a[q]]; nl_b[q] = p.nleaves[bb[q]]; }
+        t[q] = Best{0., -1};
+        for (int c = threadIdx.x; c < G; c += blockDim.x) {
+          const int i = p.part_idx[c];
+          const double v = p.part_val[c];
+          if (i >= 0 && better(v, i, t[q])) { t[q].v = v; t[q].i = i; }
+        }
       }
-      t = block_best(t, sh);
+      block_best_n<NP>(t, sh);
       if (threadIdx.x == 0) {
-        const int32_t parent = (int32_t)(S + step);
-        const double half = dab / 2.;
-        const double d0 = half - len_a;
-        p.left[step] = node_a;
-        p.right[step] = node_b;
-        p.height[step] = len_a + d0;
-        p.node[a] = parent;
-        p.len[a] = len_a + d0;
-        p.nleaves[a] = nl_a + nl_b;
-        p.alive[bb] = 0;
-        p.rmin_idx[bb] = -1;  // dead rows drop out of (1)
-        p.rmin_val[a] = t.v;
-        p.rmin_idx[a] = t.i;
-        p.wl_count[(step + 1) & 1] = 0;
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+          const ClusterParams& p = B.p[q];
+          const double half = dab[q] / 2.;
+          const double d0 = half - len_a[q];
+          p.left[step] = node_a[q];
+          p.right[step] = node_b[q];
+          p.height[step] = len_a[q] + d0;
+          p.node[a[q]] = (int32_t)(S + step);
+          p.len[a[q]] = len_a[q] + d0;
+          p.nleaves[a[q]] = nl_a[q] + nl_b[q];
+          p.alive[bb[q]] = 0;
+          p.rmin_idx[bb[q]] = -1;  // dead rows drop out of (1)
+          p.rmin_val[a[q]] = t[q].v;
+          p.rmin_idx[a[q]] = t[q].i;
+          p.wl_count[(step + 1) & 1] = 0;
+        }
       }
       __syncthreads();
     }
-    const int n_wl = *wlc;
-    // Every queued row is rescanned by nseg CTAs (one batch of loads each instead of up to five
-    // dependent ones); the CTA that finishes a row's last segment combines the partial minima.
-    const int G = (int)gridDim.x;
-    const int nseg = n_wl > 0 && n_wl * 2 <= G ? (G / n_wl < 8 ? G / n_wl : 8) : 1;
+#pragma unroll
+    for (int q = 0; q < NP; q++) n_all += n_wl[q];
+    // Every queued row (of any problem) is rescanned by nseg CTAs (one batch of loads each instead of up
+    // to five dependent ones); the CTA that finishes a row's last segment combines the partial minima.
+    const int nseg = n_all > 0 && n_all * 2 <= G ? (G / n_all < 8 ? G / n_all : 8) : 1;
     // block 0 is busy with the bookkeeping: the work starts at the other end of the grid
-    for (int it = G - 1 - (int)blockIdx.x; it < n_wl * nseg; it += G) {
-      const int w = it / nseg, seg = it % nseg;
-      const int r = wl[w];
-      if (nseg == 1) rescan_row(p, r, bb, sh);
+    for (int it = G - 1 - (int)blockIdx.x; it < n_all * nseg; it += G) {
+      const int w_all = it / nseg, seg = it % nseg;
+      int q = 0, w = w_all;
+#pragma unroll
+      for (int qq = 0; qq < NP - 1; qq++)
+        if (q == qq && w >= n_wl[qq]) { w -= n_wl[qq]; q = qq + 1; }
+      const ClusterParams& p = B.p[q];
+      const int skip = bb[q];
+      const int r = (p.wl + (step & 1) * S)[w];
+      if (nseg == 1) rescan_row(p, r, skip, sh[0]);
       else {
-        const int64_t L = S - r - 1, lo = r + 1 + L * seg / nseg, hi = r + 1 + L * (seg + 1) / nseg;
-        const Best t = scan_columns(p, r, bb, lo, hi, sh);
+        const ClusterParams& p0 = B.p[0]; // segment scratch of problem 0 serves the whole batch
+        const int64_t L = S - r - 1, slo = r + 1 + L * seg / nseg, shi = r + 1 + L * (seg + 1) / nseg;
+        const Best t = scan_columns(p, r, skip, slo, shi, sh[0]);
         __shared__ int last;
         if (threadIdx.x == 0) {
-          p.seg_val[w * nseg + seg] = t.v;
-          p.seg_idx[w * nseg + seg] = t.i;
+          p0.seg_val[w_all * nseg + seg] = t.v;
+          p0.seg_idx[w_all * nseg + seg] = t.i;
           __threadfence();
-          last = atomicAdd(&p.seg_cnt[w], 1) == nseg - 1;
+          last = atomicAdd(&p0.seg_cnt[w_all], 1) == nseg - 1;
         }
         __syncthreads();
         if (last && threadIdx.x < 32) {
           __threadfence();
           Best c{0., -1};
           if ((int)threadIdx.x < nseg) {
-            c.i = __ldcg(&p.seg_idx[w * nseg + threadIdx.x]);
-            c.v = __ldcg(&p.seg_val[w * nseg + threadIdx.x]);
+            c.i = __ldcg(&p0.seg_idx[w_all * nseg + threadIdx.x]);
+            c.v = __ldcg(&p0.seg_val[w_all * nseg + threadIdx.x]);
           }
           c = warp_best(c);
-          if (threadIdx.x == 0) { p.rmin_val[r] = c.v; p.rmin_idx[r] = c.i; p.seg_cnt[w] = 0; }
+          if (threadIdx.x == 0) { p.rmin_val[r] = c.v; p.rmin_idx[r] = c.i; p0.seg_cnt[w_all] = 0; }
         }
       }
       __syncthreads();
@@ -309,11 +388,12 @@ __global__ void __launch_bounds__(CT) k4_cluster(ClusterParams p) {
   }
 #ifdef CMB_K4_TIMING
   if (threadIdx.x == 0 && (blockIdx.x == 0 || blockIdx.x == 77 || blockIdx.x == gridDim.x - 1))
-    printf("k4 timing cta %d: scan %lld sync1 %lld combine %lld update %lld sync2 %lld rescans %lld sync3 %lld (cycles per merge)\n",
-           blockIdx.x, tacc[0] / (S - 2), tacc[1] / (S - 2), tacc[2] / (S - 2), tacc[3] / (S - 2), tacc[4] / (S - 2), tacc[5] / (S - 2), tacc[6] / (S - 2));
+    printf("k4 timing cta %d: scan %lld sync1 %lld combine %lld update %lld sync2 %lld rescans %lld sync3 %lld (cycles per step of %d merges)\n",
+           blockIdx.x, tacc[0] / (S - 2), tacc[1] / (S - 2), tacc[2] / (S - 2), tacc[3] / (S - 2), tacc[4] / (S - 2), tacc[5] / (S - 2), tacc[6] / (S - 2), NP);
 #endif
   // finalStep: join the last two clusters at d/2
-  if (gtid == 0) {
+  if (gtid < NP) {
+    const ClusterParams& p = B.p[gtid];
     int i1 = -1, i2 = -1;
     for (int64_t i = 0; i < S; i++)
       if (p.alive[i]) { if (i1 < 0) i1 = (int)i; else i2 = (int)i; }
@@ -616,8 +696,9 @@ __global__ void k4_group_compensation(int64_t n_groups, const int32_t* __restric
 
 } // namespace
 
-int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* left_dev, int32_t* right_dev,
-                   double* height_dev, cudaStream_t st) {
+namespace {
+ClusterParams make_params(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* left_dev, int32_t* right_dev,
+                          double* height_dev, cudaStream_t st) {
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
   size_t o_val = 0, o_idx = al(o_val + 8 * S), o_alive = al(o_idx + 4 * S), o_len = al(o_alive + S),
          o_nl = al(o_len + 8 * S), o_node = al(o_nl + 4 * S), o_wl = al(o_node + 4 * S), o_wlc = al(o_wl + 8 * S),
@@ -636,22 +717,47 @@ int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* l
   p.seg_val = (double*)(w + o_gv); p.seg_idx = (int32_t*)(w + o_gi); p.seg_cnt = (int32_t*)(w + o_gc);
   CMB_CUDA(cudaMemsetAsync(p.seg_cnt, 0, 4 * 1024, st));
   p.left = left_dev; p.right = right_dev; p.height = height_dev;
-  k4_init_state<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(p);
-  CMB_CUDA(cudaGetLastError());
-  int dev = 0, sms = 0, per_sm = 0;
+  return p;
+}
+
+template <int NP>
+void launch_batch_kernel(ClusterBatch& B, int grid, cudaStream_t st) {
+  int per_sm = 0;
+  CMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_cluster<NP>, CT, 0));
+  if (per_sm < 1) fail("k4_cluster cannot be made resident");
+  void* args[] = {&B};
+  CMB_CUDA(cudaLaunchCooperativeKernel((void*)k4_cluster<NP>, dim3(grid), dim3(CT), args, 0, st));
+}
+} // namespace
+
+// np (1..4) dendrograms over matrices of the same size, advanced in lock step by one cooperative kernel
+int launch_cluster_batch(int np, int64_t S, int linkage, double* const* mats, DevBuf* works, int32_t* const* left_dev,
+                         int32_t* const* right_dev, double* const* height_dev, cudaStream_t st) {
+  if (np < 1 || np > kMaxBatch) fail("launch_cluster_batch: 1..%d problems per launch", kMaxBatch);
+  int dev = 0, sms = 0;
   CMB_CUDA(cudaGetDevice(&dev));
   CMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
-  CMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k4_cluster, CT, 0));
-  if (per_sm < 1) fail("k4_cluster cannot be made resident");
-  int grid = std::min(sms, 1024); // one CTA per SM
-  if (S > (int64_t)4 * grid * CT) fail("clustering: %lld sites exceed the %lld this device handles per merge pass", (long long)S,
-                                       (long long)4 * grid * CT);
-  k4_init_rows<<<grid, CT, 0, st>>>(p);
-  CMB_CUDA(cudaGetLastError());
-  if (try_cluster_dsm(p, st)) return 3;
-  void* args[] = {&p};
-  CMB_CUDA(cudaLaunchCooperativeKernel((void*)k4_cluster, dim3(grid), dim3(CT), args, 0, st));
-  return 3;
+  const int grid = std::min(sms, 1024); // one CTA per SM
+  ClusterBatch B;
+  for (int q = 0; q < np; q++) {
+    B.p[q] = make_params(S, linkage, mats[q], works[q], left_dev[q], right_dev[q], height_dev[q], st);
+    k4_init_state<<<(unsigned)((S + 255) / 256), 256, 0, st>>>(B.p[q]);
+    CMB_CUDA(cudaGetLastError());
+    k4_init_rows<<<grid, CT, 0, st>>>(B.p[q]);
+    CMB_CUDA(cudaGetLastError());
+  }
+  for (int q = np; q < kMaxBatch; q++) B.p[q] = B.p[0];
+  if (np == 1 && try_cluster_dsm(B.p[0], st)) return 3;
+  if (np == 1) launch_batch_kernel<1>(B, grid, st);
+  else if (np == 2) launch_batch_kernel<2>(B, grid, st);
+  else if (np == 3) launch_batch_kernel<3>(B, grid, st);
+  else launch_batch_kernel<4>(B, grid, st);
+  return 2 * np + 1;
+}
+
+int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* left_dev, int32_t* right_dev,
+                   double* height_dev, cudaStream_t st) {
+  return launch_cluster_batch(1, S, linkage, &mat, &work, &left_dev, &right_dev, &height_dev, st);
 }
 
 void launch_group_compensation(int64_t n_groups, const int32_t* members, const int64_t* offsets, int B,

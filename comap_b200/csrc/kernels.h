@@ -130,6 +130,8 @@ void launch_transpose_out(const double* out, int B, int64_t n, int64_t n_pad, do
 
 
 // ---- K4
+int launch_cluster_batch(int np, int64_t S, int linkage, double* const* mats, DevBuf* works, int32_t* const* left_dev,
+                         int32_t* const* right_dev, double* const* height_dev, cudaStream_t st);
 int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* left_dev, int32_t* right_dev,
                    double* height_dev, cudaStream_t st);
 void launch_group_compensation(int64_t n_groups, const int32_t* members, const int64_t* offsets, int B,

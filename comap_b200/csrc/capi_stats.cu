@@ -589,6 +589,10 @@ int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t se
   int NB = (int)std::min<size_t>(4, std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / per_rep));
   if (const char* e = std::getenv("CMB_K4_BATCH")) NB = std::max(1, std::min(4, atoi(e)));
   DevBuf dists[4], works[4], outs[4];
+  struct Release { // also on the error path (fail() throws)
+    DevBuf *a, *b, *c, *d;
+    ~Release() { for (int q = 0; q < 4; q++) { a[q].release(); b[q].release(); c[q].release(); } d->release(); }
+  } release_guard{dists, works, outs, &staging};
   std::vector<double> h_norms[4];
   DendroHost dendro[4];
   for (int rep0 = rep_begin; rep0 < rep_end; rep0 += NB) {
@@ -634,8 +638,6 @@ int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t se
       mem += (int64_t)g.members.size();
     }
   }
-  for (int q = 0; q < 4; q++) { dists[q].release(); works[q].release(); outs[q].release(); }
-  staging.release();
   mean.release(); sd.release(); norm.release();
   c.have_dist = false; // the matrices were consumed
   c.have_dendro = false;

@@ -212,16 +212,26 @@ __global__ void __launch_bounds__(CT) k4_cluster(const __grid_constant__ Cluster
     grid.sync();
     K4_T(1)
     // the column travels with the partial, so no load depends on the reduced row index
+    {
+      int pi0[NP], pc0[NP]; double pv0[NP];
+      const int c0 = (int)threadIdx.x;
 #pragma unroll
-    for (int q = 0; q < NP; q++) {
-      b[q] = Best{0., -1};
-      for (int c = threadIdx.x; c < G; c += blockDim.x) {
-        const int i = B.p[q].scan_idx[c];
-        const double v = B.p[q].scan_val[c];
-        const int col = B.p[q].scan_col[c];
-        if (i >= 0 && better(v, i, b[q])) { b[q].v = v; b[q].i = i; my_col[q] = col; }
+      for (int q = 0; q < NP; q++) { // one round trip for all problems
+        pi0[q] = -1; pc0[q] = -1; pv0[q] = 0.;
+        if (c0 < G) { pi0[q] = B.p[q].scan_idx[c0]; pv0[q] = B.p[q].scan_val[c0]; pc0[q] = B.p[q].scan_col[c0]; }
       }
-      my_i[q] = b[q].i;
+#pragma unroll
+      for (int q = 0; q < NP; q++) {
+        b[q] = Best{0., -1};
+        if (pi0[q] >= 0) { b[q].v = pv0[q]; b[q].i = pi0[q]; my_col[q] = pc0[q]; }
+        for (int c = c0 + (int)blockDim.x; c < G; c += blockDim.x) { // only on grids above one block's threads
+          const int i = B.p[q].scan_idx[c];
+          const double v = B.p[q].scan_val[c];
+          const int col = B.p[q].scan_col[c];
+          if (i >= 0 && better(v, i, b[q])) { b[q].v = v; b[q].i = i; my_col[q] = col; }
+        }
+        my_i[q] = b[q].i;
+      }
     }
     block_best_n<NP>(b, sh);
     int a[NP], bb[NP];
@@ -254,14 +264,18 @@ __global__ void __launch_bounds__(CT) k4_cluster(const __grid_constant__ Cluster
     Best ra[NP];
     {
       uint8_t live0[NP]; double d10[NP], d20[NP], cv0[NP]; int ci0[NP];
-      const int64_t k0 = gtid;
+      // the CTA that owns the lowest rows is the slowest of this phase (most of the queue atomics are
+      // its): each problem deals its rows to the CTAs with a different rotation
+      int64_t k0[NP];
 #pragma unroll
       for (int q = 0; q < NP; q++) { // one round trip for all problems
+        k0[q] = gtid + (int64_t)q * (G / NP) * blockDim.x;
+        if (k0[q] >= gsz) k0[q] -= gsz;
         live0[q] = 0; d10[q] = d20[q] = cv0[q] = 0.; ci0[q] = -1;
-        if (k0 < S) {
-          live0[q] = B.p[q].alive[k0];
-          d10[q] = B.p[q].mat[(size_t)a[q] * S + k0]; d20[q] = B.p[q].mat[(size_t)bb[q] * S + k0];
-          ci0[q] = B.p[q].rmin_idx[k0]; cv0[q] = B.p[q].rmin_val[k0];
+        if (k0[q] < S) {
+          live0[q] = B.p[q].alive[k0[q]];
+          d10[q] = B.p[q].mat[(size_t)a[q] * S + k0[q]]; d20[q] = B.p[q].mat[(size_t)bb[q] * S + k0[q]];
+          ci0[q] = B.p[q].rmin_idx[k0[q]]; cv0[q] = B.p[q].rmin_val[k0[q]];
         }
       }
 #pragma unroll
@@ -286,8 +300,8 @@ __global__ void __launch_bounds__(CT) k4_cluster(const __grid_constant__ Cluster
             else if (!(nd != nd) && (ci < 0 || nd < cv || (nd == cv && aq < ci))) { p.rmin_val[k] = nd; p.rmin_idx[k] = aq; }
           }
         };
-        if (k0 < S) row(k0, live0[q], d10[q], d20[q], ci0[q], cv0[q]);
-        for (int64_t k = k0 + gsz; k < S; k += gsz) // only above S = grid x block
+        if (k0[q] < S) row(k0[q], live0[q], d10[q], d20[q], ci0[q], cv0[q]);
+        for (int64_t k = k0[q] + gsz; k < S; k += gsz) // only above S = grid x block
           row(k, p.alive[k], p.mat[(size_t)aq * S + k], p.mat[(size_t)bq * S + k], p.rmin_idx[k], p.rmin_val[k]);
       }
     }
@@ -313,10 +327,23 @@ __global__ void __launch_bounds__(CT) k4_cluster(const __grid_constant__ Cluster
         len_a[q] = 0.; node_a[q] = node_b[q] = nl_a[q] = nl_b[q] = 0;
         if (threadIdx.x == 0) { len_a[q] = p.len[a[q]]; node_a[q] = p.node[a[q]]; node_b[q] = p.node[bb[q]]; nl_a[q] = p.nleaves[a[q]]; nl_b[q] = p.nleaves[bb[q]]; }
         t[q] = Best{0., -1};
-        for (int c = threadIdx.x; c < G; c += blockDim.x) {
-          const int i = p.part_idx[c];
-          const double v = p.part_val[c];
-          if (i >= 0 && better(v, i, t[q])) { t[q].v = v; t[q].i = i; }
+      }
+      {
+        int pi0[NP]; double pv0[NP];
+        const int c0 = (int)threadIdx.x;
+#pragma unroll
+        for (int q = 0; q < NP; q++) { // one round trip for all problems
+          pi0[q] = -1; pv0[q] = 0.;
+          if (c0 < G) { pi0[q] = B.p[q].part_idx[c0]; pv0[q] = B.p[q].part_val[c0]; }
+        }
+#pragma unroll
+        for (int q = 0; q < NP; q++) {
+          if (pi0[q] >= 0) { t[q].v = pv0[q]; t[q].i = pi0[q]; }
+          for (int c = c0 + (int)blockDim.x; c < G; c += blockDim.x) {
+            const int i = B.p[q].part_idx[c];
+            const double v = B.p[q].part_val[c];
+            if (i >= 0 && better(v, i, t[q])) { t[q].v = v; t[q].i = i; }
+          }
         }
       }
       block_best_n<NP>(t, sh);

@@ -153,8 +153,20 @@ __device__ __forceinline__ void block_best_n(Best (&b)[NP], Best (*sh)[32]) {
     for (int q = 0; q < NP; q++) sh[q][w] = b[q];
   }
   __syncthreads();
+  if constexpr (NP == 1) { // every warp reduces the warp results itself: no third barrier
+    b[0] = warp_best(l < (int)(blockDim.x >> 5) ? sh[0][l] : Best{0., -1});
+  } else {                 // REDUX issue is the limit with 3 NP per warp: one warp reduces, all read
+    if (w == 0) {
 #pragma unroll
-  for (int q = 0; q < NP; q++) b[q] = warp_best(l < (int)(blockDim.x >> 5) ? sh[q][l] : Best{0., -1});
+      for (int q = 0; q < NP; q++) {
+        const Best t = warp_best(l < (int)(blockDim.x >> 5) ? sh[q][l] : Best{0., -1});
+        if (l == 0) sh[q][0] = t;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < NP; q++) b[q] = sh[q][0];
+  }
 }
 
 template <int NP>

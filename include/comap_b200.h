@@ -230,7 +230,9 @@ int cmb_groups(cmb_ctx* ctx, int32_t dist_id, int32_t max_size, int32_t* members
 /* Replaces ClusterTools::computeGlobalDistanceDistribution (ClusterTools.cpp:200-294):
  * replicates [rep_begin, rep_end) of { simulate S sites, map, distance matrix, cluster,
  * groups <= max_size }.  Rows: rep, size, Dmax = 2*height, Stat, Nmin, and the member
- * matrix indices (flat + offsets).  capacity_rows / capacity_members bound the outputs. */
+ * matrix indices (flat + offsets).  capacity_rows / capacity_members bound the outputs.
+ * Up to four replicates are clustered by one launch (each holds its own S x S matrix on the
+ * device while it does; fewer when memory is short); results do not depend on the batching. */
 int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t seed,
                      int32_t rep_begin, int32_t rep_end, int32_t weighted_classes, int32_t max_size,
                      int64_t capacity_rows, int64_t capacity_members, int32_t* row_rep,

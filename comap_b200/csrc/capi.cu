@@ -335,6 +335,7 @@ int cmb_set_alignment(cmb_ctx* ctx, int64_t S, const uint8_t* codes, int32_t n_c
   CMB_CUDA(cudaStreamSynchronize(c.stream));
   c.have_alignment = true;
   c.mapped = false;
+  if (c.null.nmax_from_map) c.null.ready = false;
   CMB_CATCH
 }
 
@@ -379,16 +380,31 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   }
   if (post_rate) CMB_CUDA(cudaMemcpyAsync(post_rate, c.d_pr.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
   if (rate_class) CMB_CUDA(cudaMemcpyAsync(rate_class, c.d_rc.p, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, c.stream));
-  if (loglik) CMB_CUDA(cudaMemcpyAsync(loglik, c.d_loglik.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+  c.h_loglik.resize(S);
+  CMB_CUDA(cudaMemcpyAsync(c.h_loglik.data(), c.d_loglik.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
   CMB_CUDA(cudaStreamSynchronize(c.stream));
+  if (loglik) std::memcpy(loglik, c.h_loglik.data(), sizeof(double) * S);
   c.max_norm = 0.;
   for (int64_t i = 0; i < S; i++)
     if (c.h_norm[i] > c.max_norm) c.max_norm = c.h_norm[i];
   if (norm) std::memcpy(norm, c.h_norm.data(), sizeof(double) * S);
-  c.mapped = true;
   c.have_dist = false;
   c.pairs_rows = -1; // resident pair columns belong to the previous mapping
   for (auto& o : c.pairs_col_off) o = -1;
+  if (c.null.nmax_from_map) c.null.ready = false; // binned with the previous mapping's max(norm)
+  // A site whose likelihood underflowed to 0 (ln L = -inf) has 1/L = inf and NaN vectors.  The reference stops
+  // there (CoETools.cpp:233-247) or drops those sites and starts over (remove_saturated_sites, :248-262); the
+  // per-site outputs above are filled so the caller can find them, and the mapping is refused.
+  int64_t n_sat = 0, first_sat = -1;
+  for (int64_t i = 0; i < S; i++)
+    if (!std::isfinite(c.h_loglik[i])) { if (!n_sat++) first_sat = i; }
+  if (n_sat) {
+    c.mapped = false;
+    fail("cmb_map: the likelihood is 0 (log = -inf) at %lld site(s), first at site index %lld: computer underflow, "
+         "expected on big data sets (>~500 sequences); remove those sites (input.sequence.remove_saturated_sites = yes)",
+         (long long)n_sat, (long long)first_sat);
+  }
+  c.mapped = true;
   CMB_CATCH
 }
 
@@ -426,6 +442,8 @@ int cmb_load_vectors(cmb_ctx* ctx, const double* n_in, double* norm) {
 int cmb_set_mi_threshold(cmb_ctx* ctx, double threshold) {
   ctx->c.mi_threshold = threshold;
   ctx->c.have_mi_count = false;
+  ctx->c.pairs_rows = -1; // resident Stat columns were scored with the previous threshold
+  for (auto& o : ctx->c.pairs_col_off) o = -1;
   return 0;
 }
 

@@ -93,10 +93,11 @@ int cmb_pairs_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, const cmb_fil
   const double* mv1 = corrected ? c.mean_vector() : nullptr;
   const double* mv2 = corrected ? d.mean_vector() : nullptr;
   order_after(c.stream, d.stream); // the second data set's mapping (and mean vector) is complete
-  const bool any_filter = f && (f->min_rate_class > 0 || f->min_rate > 0. || f->max_rate_class_diff >= 0 ||
-                                f->max_rate_diff >= 0. || f->min_stat > 0. || min_rate_class2 > 0 || min_rate2 > 0.);
+  const bool any_filter = (f && (f->min_rate_class > 0 || f->min_rate > 0. || f->max_rate_class_diff >= 0 ||
+                                 f->max_rate_diff >= 0. || f->min_stat > 0.)) || min_rate_class2 > 0 || min_rate2 > 0.;
   auto al = [](size_t x) { return (x + 255) & ~size_t(255); };
   const int64_t total = independent ? S1 : S1 * S2;
+  if (total > 0x7fffffff) fail("cmb_pairs_inter: %lld pairs exceed the 2^31 - 1 rows one call scores", (long long)total);
   // dense columns i j stat rcmin prmin nmin | keep | compacted copies
   const size_t elt[6] = {4, 4, 8, 4, 8, 8};
   size_t off[6], off2[6], cur = 0;

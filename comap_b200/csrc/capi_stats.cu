@@ -58,13 +58,14 @@ MapBuffers sim_buffers(Context& c, int k, int64_t n, int64_t n_pad) {
 void null_load(Context& c, const double* stat_dev, const double* nmin_dev, int64_t n, int K, double nmax) {
   if (K < 1) fail("statistic.null.nb_rate_classes must be > 0 (Domain.cpp:49)");
   if (K > 4096) fail("too many null bins (%d)", K);
-  if (nmax < 0.) {
+  const bool from_map = nmax < 0.;
+  if (from_map) {
     if (!c.mapped) fail("null binning with nmax < 0 needs a mapped alignment (cmb_map)");
     nmax = c.max_norm;
   }
   if (n > 0x7fffffff) fail("null distribution too large (%lld samples)", (long long)n);
   NullState& ns = c.null;
-  ns.K = K; ns.nmax = nmax;
+  ns.K = K; ns.nmax = nmax; ns.nmax_from_map = from_map;
   ns.sorted.reserve(sizeof(double) * (size_t)std::max<int64_t>(n, 1));
   ns.bin_off_dev.reserve(sizeof(int64_t) * (K + 2));
   c.prof_begin("sort");
@@ -411,6 +412,7 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
   if (c.copy_stream && cur + 256 > c.pair_table.cap) CMB_CUDA(cudaStreamSynchronize(c.copy_stream)); // growing frees the old table
   c.pair_table.reserve(cur + 256);
   unsigned char* sb = c.pair_table.as<unsigned char>();
+  if (total > 0x7fffffff) fail("cmb_pairs: %lld pairs in one shard exceed the 2^31 - 1 rows one call scores; use more shards", (long long)total);
 
   TilesLaunch L;
   L.stat_id = stat_id; L.B = c.tree.B; L.S = S; L.S_pad = c.S_pad; L.out = c.d_out.as<double>();

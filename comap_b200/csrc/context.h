@@ -22,6 +22,7 @@ struct NullState {            // binned, sorted null distribution (device + host
   DevBuf bin_off_dev;         // int64 [K+1]
   std::vector<int64_t> bin_off;
   bool ready = false;
+  bool nmax_from_map = false;  // nmax was taken from the mapped alignment's max(norm) (nmax < 0 at load time)
 };
 
 struct Context {
@@ -49,7 +50,7 @@ struct Context {
   std::vector<uint32_t> code_mask;
   bool have_alignment = false, mapped = false;
   DevBuf d_D, d_Lc, d_invL, d_loglik, d_pr, d_rc, d_out, d_sum, d_sumsq;
-  std::vector<double> h_norm;    // host copies used by null / pairs
+  std::vector<double> h_norm, h_loglik; // host copies used by null / pairs / the saturation check
   double max_norm = 0.;
 
   // scratch for simulated batches

@@ -217,8 +217,37 @@ __device__ __forceinline__ void node_masks(const NodePtrs& p, int lane, int kind
   }
 }
 
-template <int NG, int C, int MINB>
-__global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(MapModel m, MapBuffers b, UpMmaParams up) {
+// One node's copies into ring stage s: record, tip rows, partial chunks of the stored children (one lane).
+template <int C>
+__device__ __forceinline__ void up_issue_node(const MapModel& m, const MapBuffers& b, const UpMmaParams& up, int4 r0, int4 r1,
+                                              uint32_t roff, uint32_t rnb, unsigned char* st, uint64_t* full, int64_t site0) {
+  constexpr uint32_t kBlock = C * kSG * 32;
+  const int64_t n_pad = b.n_pad;
+  const int64_t chunk = site0 / kChunkSites;
+  const uint32_t flags = (uint32_t)r0.x;
+  const int ref_a = r0.y, ref_b = r0.z, ref_a2 = r1.x, ref_b2 = r1.y;
+  const uint32_t tips_off = (uint32_t)r0.w, blk_off = (uint32_t)r1.z;
+  const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB, cha = flags & kUpCherryA, chb = flags & kUpCherryB;
+  const bool ina = !(tipa || cha), inb = !(tipb || chb);
+  unsigned char* tp = st + tips_off;
+  const uint32_t nrows = (tipa || cha) + (tipb || chb) + cha + chb;
+  mbar_expect_tx(full, rnb + nrows * (uint32_t)kSG + ((uint32_t)ina + (uint32_t)inb) * kBlock);
+  tma_bulk_g2s(st, up.stream + roff, rnb, full);
+  if (tipa || cha) tma_bulk_g2s(tp, b.tips + (size_t)ref_a * n_pad + site0, kSG, full);
+  if (tipb || chb) tma_bulk_g2s(tp + kSG, b.tips + (size_t)ref_b * n_pad + site0, kSG, full);
+  if (cha) tma_bulk_g2s(tp + 2 * kSG, b.tips + (size_t)ref_a2 * n_pad + site0, kSG, full);
+  if (chb) tma_bulk_g2s(tp + 3 * kSG, b.tips + (size_t)ref_b2 * n_pad + site0, kSG, full);
+  // stored children, in order a then b, from blk_off
+  if (ina) tma_bulk_g2s(st + blk_off, b.D + d_chunk(chunk, ref_a, m.n_slots, C), kBlock, full);
+  if (inb) tma_bulk_g2s(st + blk_off + (ina ? kBlock : 0), b.D + d_chunk(chunk, ref_b, m.n_slots, C), kBlock, full);
+}
+
+// FOLD: no producer warp.  The CTA is kSG / (8 NG) consumer warps (8 at NG = 2 -> with two CTAs per SM four
+// warps per SM sub-partition and 128 registers per thread, where the ninth warp capped them at 96 with spills);
+// the refill of the stage node n - 1 used (with node n - 1 + NSTG) is issued by warp (n - 1) % W at the top of
+// its iteration n, with the descriptors fetched one iteration earlier.
+template <int NG, int C, int MINB, bool FOLD>
+__global__ void __launch_bounds__(32 * (kSG / (8 * NG) + (FOLD ? 0 : 1)), MINB) k1_up_mma(MapModel m, MapBuffers b, UpMmaParams up) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int W = kSG / (8 * NG);                // consumer warps
   constexpr uint32_t kBlock = C * kSG * 32;        // bytes of one child's partial chunk
@@ -239,46 +268,37 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
   }
   __syncthreads();
 
-  if (warp == W) {
+  if (!FOLD && warp == W) {
     // ---- producer: node n's record, tip rows and the partial chunks of its inner children go
     //      to stage n % NSTG; one mbarrier full / empty pair per stage.  The 32 lanes fetch the
     //      descriptors of 32 nodes at a time; lane 0 issues the copies.
     uint32_t s = 0, ph = 1;
     bool first = true;
-    const int64_t chunk = site0 / kChunkSites;
     for (uint32_t n0 = 0; n0 < up.n_nodes; n0 += 32) {
       const uint32_t mine = min(n0 + lane, up.n_nodes - 1);
       const int4 r0 = __ldg(up.refs + 2 * mine), r1 = __ldg(up.refs + 2 * mine + 1);
       const uint32_t off = __ldg(up.rec_off + mine), nb = __ldg(up.rec_bytes + mine);
       const uint32_t cnt = min(32u, up.n_nodes - n0);
       for (uint32_t j = 0; j < cnt; j++) {
-        const uint32_t flags = (uint32_t)__shfl_sync(0xffffffffu, r0.x, j);
-        const int ref_a = __shfl_sync(0xffffffffu, r0.y, j), ref_b = __shfl_sync(0xffffffffu, r0.z, j);
-        const int ref_a2 = __shfl_sync(0xffffffffu, r1.x, j), ref_b2 = __shfl_sync(0xffffffffu, r1.y, j);
+        int4 q0, q1;
+        q0.x = __shfl_sync(0xffffffffu, r0.x, j); q0.y = __shfl_sync(0xffffffffu, r0.y, j);
+        q0.z = __shfl_sync(0xffffffffu, r0.z, j); q0.w = __shfl_sync(0xffffffffu, r0.w, j);
+        q1.x = __shfl_sync(0xffffffffu, r1.x, j); q1.y = __shfl_sync(0xffffffffu, r1.y, j);
+        q1.z = __shfl_sync(0xffffffffu, r1.z, j); q1.w = 0;
         const uint32_t roff = __shfl_sync(0xffffffffu, off, j), rnb = __shfl_sync(0xffffffffu, nb, j);
-        const uint32_t tips_off = (uint32_t)__shfl_sync(0xffffffffu, r0.w, j), blk_off = (uint32_t)__shfl_sync(0xffffffffu, r1.z, j);
         if (!first) mbar_wait_sleep(&stg_empty[s], ph, 200);
-        if (lane == 0) {
-          const bool tipa = flags & kUpTipA, tipb = flags & kUpTipB, cha = flags & kUpCherryA, chb = flags & kUpCherryB;
-          const bool ina = !(tipa || cha), inb = !(tipb || chb);
-          unsigned char* st = stg_ring + (size_t)s * stage_bytes;
-          unsigned char* tp = st + tips_off;
-          const uint32_t nrows = (tipa || cha) + (tipb || chb) + cha + chb;
-          mbar_expect_tx(&stg_full[s], rnb + nrows * (uint32_t)kSG + ((uint32_t)ina + (uint32_t)inb) * kBlock);
-          tma_bulk_g2s(st, up.stream + roff, rnb, &stg_full[s]);
-          if (tipa || cha) tma_bulk_g2s(tp, b.tips + (size_t)ref_a * n_pad + site0, kSG, &stg_full[s]);
-          if (tipb || chb) tma_bulk_g2s(tp + kSG, b.tips + (size_t)ref_b * n_pad + site0, kSG, &stg_full[s]);
-          if (cha) tma_bulk_g2s(tp + 2 * kSG, b.tips + (size_t)ref_a2 * n_pad + site0, kSG, &stg_full[s]);
-          if (chb) tma_bulk_g2s(tp + 3 * kSG, b.tips + (size_t)ref_b2 * n_pad + site0, kSG, &stg_full[s]);
-          // stored children, in order a then b, from blk_off
-          if (ina) tma_bulk_g2s(st + blk_off, b.D + d_chunk(chunk, ref_a, m.n_slots, C), kBlock, &stg_full[s]);
-          if (inb) tma_bulk_g2s(st + blk_off + (ina ? kBlock : 0), b.D + d_chunk(chunk, ref_b, m.n_slots, C), kBlock, &stg_full[s]);
-        }
+        if (lane == 0) up_issue_node<C>(m, b, up, q0, q1, roff, rnb, stg_ring + (size_t)s * stage_bytes, &stg_full[s], site0);
         __syncwarp();
         if (++s == (uint32_t)NSTG) { s = 0; ph ^= 1; first = false; }
       }
     }
     return;
+  }
+  if (FOLD) { // prologue: the first NSTG nodes, one per warp
+    for (uint32_t n = warp; n < (uint32_t)NSTG && n < up.n_nodes; n += W)
+      if (lane == 0)
+        up_issue_node<C>(m, b, up, __ldg(up.refs + 2 * n), __ldg(up.refs + 2 * n + 1), __ldg(up.rec_off + n), __ldg(up.rec_bytes + n),
+                         stg_ring + (size_t)n * stage_bytes, &stg_full[n], site0);
   }
 
   // ---- consumers
@@ -301,7 +321,25 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
   for (int j = 0; j < NJ; j++) invL[j] = b.invL[site0 + wsite + 8 * (2 * j + (q & 1)) + s8];
 
   uint32_t cs = 0, cph = 0;
+  int4 pre0 = make_int4(0, 0, 0, 0), pre1 = pre0; // FOLD: descriptors of the node this warp issues next
+  uint32_t pre_off = 0, pre_nb = 0;
   for (uint32_t node = 0; node < up.n_nodes; node++) {
+    if (FOLD) {
+      // refill duty of node - 1's stage (all W warps have arrived on its empty barrier before it is reused)
+      if (node >= 1 && warp == (int)((node - 1) % W) && node - 1 + NSTG < up.n_nodes) {
+        const uint32_t ps = cs == 0 ? (uint32_t)NSTG - 1 : cs - 1, pph = cs == 0 ? cph ^ 1 : cph;
+        if (lane == 0) {
+          mbar_wait(&stg_empty[ps], pph);
+          up_issue_node<C>(m, b, up, pre0, pre1, pre_off, pre_nb, stg_ring + (size_t)ps * stage_bytes, &stg_full[ps], site0);
+        }
+        __syncwarp();
+      }
+      if (warp == (int)(node % W) && node + NSTG < up.n_nodes) { // used at the top of the next iteration
+        const uint32_t nn = node + NSTG;
+        pre0 = __ldg(up.refs + 2 * nn); pre1 = __ldg(up.refs + 2 * nn + 1);
+        pre_off = __ldg(up.rec_off + nn); pre_nb = __ldg(up.rec_bytes + nn);
+      }
+    }
     mbar_wait(&stg_full[cs], cph);
     const unsigned char* stage = stg_ring + (size_t)cs * stage_bytes;
     const int4 h0 = *reinterpret_cast<const int4*>(stage);
@@ -384,7 +422,7 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
   }
 }
 
-template <int NG, int C, int MINB>
+template <int NG, int C, int MINB, bool FOLD>
 bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.C != C) return false;
   int dev = 0, max_smem = 0;
@@ -406,13 +444,14 @@ bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   // Shared memory is carved out of the 256 KB it shares with L1, and the consumers' message stack and
   // register spills live in local memory behind that L1: a third stage at C = 4 (2 x 111 KB of shared
   // memory, ~28 KB of L1) ran 12.4 ms instead of 10.8 ms.  Keep a CTA's ring within 80 KB.
-  if (MINB > 1) up.n_stages = (int)std::max<size_t>(2, std::min<size_t>(up.n_stages, (80 * 1024) / stage));
+  static const size_t ring_kb = getenv("CMB_UP_RING_KB") ? (size_t)atoi(getenv("CMB_UP_RING_KB")) : 80;
+  if (MINB > 1) up.n_stages = (int)std::max<size_t>(2, std::min<size_t>(up.n_stages, (ring_kb * 1024) / stage));
   const size_t smem = fixed + (size_t)up.n_stages * stage;
-  constexpr int threads = 32 * (kSG / (8 * NG) + 1);
-  CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int threads = 32 * (kSG / (8 * NG) + (FOLD ? 0 : 1));
+  CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (getenv("CMB_UP_CARVEOUT"))
-    CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CMB_UP_CARVEOUT"))));
-  k1_up_mma<NG, C, MINB><<<(unsigned)(b.n_pad / kSG), threads, smem, st>>>(m, b, up);
+    CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB, FOLD>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CMB_UP_CARVEOUT"))));
+  k1_up_mma<NG, C, MINB, FOLD><<<(unsigned)(b.n_pad / kSG), threads, smem, st>>>(m, b, up);
   CMB_CUDA(cudaGetLastError());
   return true;
 }
@@ -424,10 +463,12 @@ bool up_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   // 4 groups/warp x 2 CTAs/SM (8 warps, 168 regs) 11.2 ms; 2 groups/warp x 1 CTA/SM 12.7 ms
   if constexpr (C == 4) {
     static const int shape = getenv("CMB_UP_SHAPE") ? atoi(getenv("CMB_UP_SHAPE")) : 0; // experiment switch
-    if (shape == 42) return try_up_mma<4, C, 2>(m, b, s, st);
-    if (shape == 21) return try_up_mma<2, C, 1>(m, b, s, st);
+    if (shape == 42) return try_up_mma<4, C, 2, false>(m, b, s, st);
+    if (shape == 21) return try_up_mma<2, C, 1, false>(m, b, s, st);
   }
-  return try_up_mma<2, C, 2>(m, b, s, st) || try_up_mma<2, C, 1>(m, b, s, st);
+  static const int fold = getenv("CMB_UP_FOLD") ? atoi(getenv("CMB_UP_FOLD")) : 1; // experiment switch
+  if (fold) return try_up_mma<2, C, 2, true>(m, b, s, st) || try_up_mma<2, C, 1, true>(m, b, s, st);
+  return try_up_mma<2, C, 2, false>(m, b, s, st) || try_up_mma<2, C, 1, false>(m, b, s, st);
 }
 
 // ------------------------------------------------------------------------------ down

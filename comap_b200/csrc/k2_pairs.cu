@@ -549,7 +549,7 @@ int bin_and_sort(int64_t n, const double* stat, const double* nmin, int K, doubl
   int bits = 1;
   while ((1 << bits) <= K) bits++;
   CMB_CUDA(cub::DeviceRadixSort::SortPairs(ctemp, need, cat2, cat, stat1, sorted, (int)n, 0, bits, st));
-  k2_bin_offsets<<<1, 64, 0, st>>>(n, cat, K, off_dev);
+  k2_bin_offsets<<<(unsigned)((K + 1 + 63) / 64), 64, 0, st>>>(n, cat, K, off_dev);
   CMB_CUDA(cudaGetLastError());
   return 6;
 }

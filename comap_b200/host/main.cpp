@@ -287,9 +287,9 @@ struct Mapped {           // a data set on the device and its per-site results
 
 // cmb_set_* + CoETools::getVectors (CoETools.cpp:364-413) + norms (CoMap.cpp:158-163) + writeInfos
 // (CoETools.cpp:496-531) for one data set; P holds that data set's view of the options
-Mapped map_data_set(const Inputs& in, const Params& P, const std::string& suffix) {
+Mapped map_data_set(Inputs& in, const Params& P, const std::string& suffix) {
   Mapped m;
-  const int64_t S = (int64_t)in.cols.size();
+  int64_t S = (int64_t)in.cols.size();
   const int B = (int)in.tree.parent.size() - 1;
   chk(cmb_ctx_create(-1, nullptr, &m.ctx));
   chk(cmb_set_tree(m.ctx, (int32_t)in.tree.parent.size(), in.tree.parent.data(), in.tree.brlen.data()));
@@ -308,7 +308,43 @@ Mapped map_data_set(const Inputs& in, const Params& P, const std::string& suffix
   std::vector<double> n_out;
   m.norm.resize(S); m.pr.resize(S); m.ll.resize(S); m.rc.resize(S);
   if (vec_path != "none") n_out.resize((size_t)S * B);
-  chk(cmb_map(m.ctx, n_out.empty() ? nullptr : n_out.data(), m.norm.data(), m.pr.data(), m.rc.data(), m.ll.data()));
+  if (cmb_map(m.ctx, n_out.empty() ? nullptr : n_out.data(), m.norm.data(), m.pr.data(), m.rc.data(), m.ll.data())) {
+    // a site likelihood of 0 (CoETools.cpp:233-262): stop with the per-site log-likelihoods written out, or with
+    // input.sequence.remove_saturated_sites = yes drop those sites and map again
+    int64_t n_sat = 0;
+    for (int64_t i = 0; i < S; i++) n_sat += !std::isfinite(m.ll[i]);
+    if (!n_sat) throw Error(cmb_last_error());
+    if (!get_bool(P, "input.sequence.remove_saturated_sites", false)) {
+      std::ofstream debug("DEBUG_likelihoods.txt");
+      for (int64_t i = 0; i < S; i++) debug << "Position " << in.cols[i] + 1 << " = " << m.ll[i] << std::endl;
+      debug.close();
+      std::cerr << "ERROR!!! !!! Site-specific likelihood have been written in file DEBUG_likelihoods.txt ." << std::endl;
+      std::cerr << "ERROR!!! !!! 0 values (inf in log) may be due to computer overflow, particularily if datasets are big (>~500 sequences)." << std::endl;
+      std::cerr << "ERROR!!! !!! You may want to try input.sequence.remove_saturated_sites = yes to ignore positions with likelihood 0." << std::endl;
+      exit(1);
+    }
+    const int64_t T = (int64_t)in.codes.size() / S;
+    std::vector<int64_t> keep;
+    for (int64_t i = S; i > 0; --i)
+      if (!std::isfinite(m.ll[i - 1])) display_result("Ignore saturated site", std::to_string(in.cols[i - 1] + 1));
+    for (int64_t i = 0; i < S; i++)
+      if (std::isfinite(m.ll[i])) keep.push_back(i);
+    const int64_t S2 = (int64_t)keep.size();
+    display_result("Number of sites retained", std::to_string(S2));
+    if (S2 == 0) throw Error("Likelihood is still 0 after saturated sites are removed! Looks like a bug...");
+    std::vector<uint8_t> codes2((size_t)T * S2);
+    std::vector<int> cols2(S2);
+    for (int64_t t = 0; t < T; t++)
+      for (int64_t k = 0; k < S2; k++) codes2[(size_t)t * S2 + k] = in.codes[(size_t)t * S + keep[k]];
+    for (int64_t k = 0; k < S2; k++) cols2[k] = in.cols[keep[k]];
+    in.codes.swap(codes2);
+    in.cols.swap(cols2);
+    S = S2;
+    chk(cmb_set_alignment(m.ctx, S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
+    m.norm.resize(S); m.pr.resize(S); m.ll.resize(S); m.rc.resize(S);
+    if (vec_path != "none") n_out.resize((size_t)S * B);
+    chk(cmb_map(m.ctx, n_out.empty() ? nullptr : n_out.data(), m.norm.data(), m.pr.data(), m.rc.data(), m.ll.data()));
+  }
   if (in_vec != "none") {
     // restart from a mapping file (LegacySubstitutionMappingTools::readFromStream, CoETools.cpp:376-384):
     // header "Branches\tMean\tSite<coord>...", one row per branch: id, length, the branch's entry per site
@@ -395,7 +431,7 @@ int main(int argc, char** argv) {
       }
       return 0;
     }
-    const int64_t S = (int64_t)in.cols.size();
+    int64_t S = (int64_t)in.cols.size();
     const int T = (int)in.tree.leaves.size();
     const int B = (int)in.tree.parent.size() - 1;
     uint64_t seed = in.app.seed;
@@ -410,6 +446,7 @@ int main(int argc, char** argv) {
 
     display_message("\n\n-*- Get substitution vectors -*-\n");
     Mapped m1 = map_data_set(in, P, "");
+    S = (int64_t)in.cols.size(); // saturated sites may have been removed
     cmb_ctx* ctx = m1.ctx;
     std::string analysis = get_string(P, "analysis", "pairwise");
     display_result("Analysis type", analysis);

@@ -91,6 +91,9 @@ constexpr uint32_t kUpTipA = 1, kUpTipB = 2, kUpPop = 4, kUpPush = 8, kUpTakeA =
                    kUpCherryA = 64, kUpCherryB = 128;
 struct DownHdr { uint32_t flags; int32_t row_a, row_b, slot; };
 struct UpHdr { uint32_t flags; int32_t ref_a, ref_b, out_a, out_b, ref_a2, ref_b2, pad2; };
+// tensor-core up stream (k1_mma.cu): out_x1 / out_x2 = output rows of the two leaf branches of a cherry child
+// kase = (kind a * 3 + kind b) | push level << 8 | pop level << 16 (0xff: no pop); kinds 0 inner, 1 tip, 2 cherry
+struct UpMmaHdr { uint32_t kase; int32_t tips_off, blk_off; uint32_t flags; int32_t out_a, out_b, out_a1, out_a2, out_b1, out_b2, ref_a, ref_b; };
 void build_down_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb);
 void build_up_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb);
 // Same walk with the tables packed as DMMA m8n8k4 B-operand fragments (A = 4, all classes).

@@ -55,88 +55,118 @@ constexpr int kSG = kChunkSites; // sites per CTA
 // what a child is, warp-uniform
 enum : int { kInner = 0, kTip = 1, kCherry = 2 };
 
-struct NodePtrs {       // record and stage pointers of one node, lane offsets NOT applied
-  const double* tab;                               // first table of the record (shared memory)
-  const double *blk_a, *blk_b;                     // partial chunks of inner children
-};
-// Offsets (in doubles) of a record's tables given what the two children are (schedule.cpp
-// build_up_mma_stream): F1a[C] F1b[C] | F3a[C] F3b[C] (non-tips) | leaf tables of cherries | raw
-// P, W of tips.  Compile-time constants inside the specialised node bodies: eight pointers less
-// to keep in (or spill from) 96 registers.
-struct RecLayout { int F1a, F1b, F3a, F3b, Pxa, Pxb, Rta, Rtb; };
+// Offsets (in doubles, from the end of the header) of a record's tables given what the two children are
+// (schedule.cpp build_up_mma_stream): F1 / F3 fragments of the non-tip children, then per child the raw 4x4
+// tables: tip P[C] W[C]; cherry P1[C] P2[C] W1[C] W2[C] (its two leaf edges).  Compile-time constants inside
+// the specialised node bodies.
+struct RecLayout { int F1a, F1b, F3a, F3b, Ra, Rb; };
 __host__ __device__ constexpr RecLayout rec_layout(int C, int ka, int kb) {
   RecLayout r{};
   r.F1a = 0;
-  r.F1b = C * 32;
-  r.F3a = 2 * C * 32;
-  r.F3b = r.F3a + (ka != 1 /* kTip */ ? C * 32 : 0);
-  r.Pxa = r.F3b + (kb != 1 ? C * 32 : 0);
-  r.Pxb = r.Pxa + (ka == 2 /* kCherry */ ? 2 * C * 16 : 0);
-  r.Rta = r.Pxb + (kb == 2 ? 2 * C * 16 : 0);
-  r.Rtb = r.Rta + (ka == 1 ? 2 * C * 16 : 0);
+  r.F1b = r.F1a + (ka != 1 /* kTip */ ? C * 32 : 0);
+  r.F3a = r.F1b + (kb != 1 ? C * 32 : 0);
+  r.F3b = r.F3a + (ka != 1 ? C * 32 : 0);
+  r.Ra = r.F3b + (kb != 1 ? C * 32 : 0);
+  r.Rb = r.Ra + (ka == 1 ? 2 * C * 16 : ka == 2 /* kCherry */ ? 4 * C * 16 : 0);
   return r;
 }
 
-// One node, every leaf state below it resolved (no ambiguity codes in this warp's sites):
-// straight-line code over the classes so the C x NG independent DMMA chains interleave.
+// entry `code` of row q of a raw 4x4 table (a resolved state), or the sum of the row's entries over the
+// states an ambiguity code allows (MASK)
+template <bool MASK>
+__device__ __forceinline__ double pick(const double* row, uint32_t code) {
+  if constexpr (!MASK) return row[code];
+  else {
+    double t = 0.;
+#pragma unroll
+    for (int y = 0; y < 4; y++) t += (code >> y) & 1u ? row[y] : 0.;
+    return t;
+  }
+}
+
+// The arithmetic of one node: straight-line code over the classes so the C x NG independent DMMA chains
+// interleave.
 //   inner child : D from the stage, (S, T) = DMMA(D, [P | W])
 //   tip child   : S = P[q][state], T = W[q][state]   (column picks from the raw tables)
-//   cherry child: D = P1[q][s1] * P2[q][s2], then as inner
-template <int NG, int C, int KA, int KB>
-__device__ __forceinline__ void node_fast(const NodePtrs& p, int lane, const int (&sa)[NG], const int (&sa2)[NG],
-                                          const int (&sb)[NG], const int (&sb2)[NG], double (&G)[C][NG],
-                                          double (*push)[NG], const double (*pop)[NG], double (&acc_a)[NG],
-                                          double (&acc_b)[NG]) {
+//   cherry child: D = P1[q][s1] * P2[q][s2], then as inner; its message M = DMMA(U, P^T) stays in registers
+//                 and its two leaf branches are contracted here: n_1 += (M o P2 pick) . W1 pick, n_2 likewise
+// acc: a, b, a1, a2, b1, b2 (the last four only for cherry children).  MASK: the codes are state masks
+// (ambiguity somewhere in the warp's sites).  tab: first table of the record, blk: chunks, lane offsets applied.
+template <int NG, int C, int KA, int KB, bool MASK>
+__device__ __forceinline__ void node_body(const double* tab, const double* blk_a, const double* blk_b, int lane,
+                                          const uint32_t (&sa)[NG], const uint32_t (&sa2)[NG], const uint32_t (&sb)[NG],
+                                          const uint32_t (&sb2)[NG], double (&G)[C][NG], double (*push)[NG],
+                                          const double (*pop)[NG], double (&acc)[6][NG]) {
   const int q = lane & 3;
   constexpr RecLayout L = rec_layout(C, KA, KB);
 #pragma unroll
   for (int c = 0; c < C; c++) {
     double Sa[NG], Ta[NG], Sb[NG], Tb[NG];
-    auto child = [&](auto kind, const double* F1, const double* blk, const double* Px, const double* Rt,
-                     const int (&s1)[NG], const int (&s2)[NG], double (&S)[NG], double (&T)[NG]) {
+    double p1a[NG], p2a[NG], p1b[NG], p2b[NG]; // leaf-edge picks of cherry children
+    auto child = [&](auto kind, const double* F1, const double* blk, const double* R, const uint32_t (&s1)[NG],
+                     const uint32_t (&s2)[NG], double (&S)[NG], double (&T)[NG], double (&p1)[NG], double (&p2)[NG]) {
       constexpr int K = decltype(kind)::value;
       if constexpr (K == kTip) {
 #pragma unroll
         for (int g = 0; g < NG; g++) {
-          S[g] = Rt[c * 16 + q * 4 + s1[g]];
-          T[g] = Rt[(C + c) * 16 + q * 4 + s1[g]];
+          S[g] = pick<MASK>(R + c * 16 + q * 4, s1[g]);
+          T[g] = pick<MASK>(R + (C + c) * 16 + q * 4, s1[g]);
         }
       } else {
         double D[NG];
         if constexpr (K == kInner) {
 #pragma unroll
-          for (int g = 0; g < NG; g++) D[g] = blk[(size_t)c * (kSG * 4) + g * 32 + lane];
+          for (int g = 0; g < NG; g++) D[g] = blk[(size_t)c * (kSG * 4) + g * 32];
         } else {
 #pragma unroll
-          for (int g = 0; g < NG; g++) D[g] = Px[c * 16 + q * 4 + s1[g]] * Px[(C + c) * 16 + q * 4 + s2[g]];
+          for (int g = 0; g < NG; g++) {
+            p1[g] = pick<MASK>(R + c * 16 + q * 4, s1[g]);
+            p2[g] = pick<MASK>(R + (C + c) * 16 + q * 4, s2[g]);
+            D[g] = p1[g] * p2[g];
+          }
         }
         const double f = F1[c * 32 + lane];
 #pragma unroll
         for (int g = 0; g < NG; g++) dmma(S[g], T[g], D[g], f);
       }
     };
-    child(std::integral_constant<int, KA>(), p.tab + L.F1a, p.blk_a, p.tab + L.Pxa, p.tab + L.Rta, sa, sa2, Sa, Ta);
-    child(std::integral_constant<int, KB>(), p.tab + L.F1b, p.blk_b, p.tab + L.Pxb, p.tab + L.Rtb, sb, sb2, Sb, Tb);
+    child(std::integral_constant<int, KA>(), tab + L.F1a, blk_a, tab + L.Ra, sa, sa2, Sa, Ta, p1a, p2a);
+    child(std::integral_constant<int, KB>(), tab + L.F1b, blk_b, tab + L.Rb, sb, sb2, Sb, Tb, p1b, p2b);
     double Ua[NG], Ub[NG];
 #pragma unroll
     for (int g = 0; g < NG; g++) {
       Ua[g] = G[c][g] * Sb[g];
       Ub[g] = G[c][g] * Sa[g];
-      acc_a[g] = c == 0 ? Ua[g] * Ta[g] : fma(Ua[g], Ta[g], acc_a[g]);
-      acc_b[g] = c == 0 ? Ub[g] * Tb[g] : fma(Ub[g], Tb[g], acc_b[g]);
+      acc[0][g] = c == 0 ? Ua[g] * Ta[g] : fma(Ua[g], Ta[g], acc[0][g]);
+      acc[1][g] = c == 0 ? Ub[g] * Tb[g] : fma(Ub[g], Tb[g], acc[1][g]);
     }
     double unused;
-    if constexpr (KA != kTip) {
-      if constexpr (KB != kTip) { // both expanded later: b's message waits on the stack
-        const double f3 = p.tab[L.F3b + c * 32 + lane];
+    // a cherry child's own node, inline: message through its edge, then its two leaf branches
+    auto cherry = [&](const double* F3, const double* R, const uint32_t (&s1)[NG], const uint32_t (&s2)[NG],
+                      const double (&U)[NG], const double (&p1)[NG], const double (&p2)[NG], double (&n1)[NG], double (&n2)[NG]) {
+      const double f3 = F3[c * 32 + lane];
 #pragma unroll
-        for (int g = 0; g < NG; g++) dmma(push[c][g], unused, Ub[g], f3);
+      for (int g = 0; g < NG; g++) {
+        double M;
+        dmma(M, unused, U[g], f3);
+        const double w1 = pick<MASK>(R + (2 * C + c) * 16 + q * 4, s1[g]);
+        const double w2 = pick<MASK>(R + (3 * C + c) * 16 + q * 4, s2[g]);
+        const double u1 = M * p2[g], u2 = M * p1[g];
+        n1[g] = c == 0 ? u1 * w1 : fma(u1, w1, n1[g]);
+        n2[g] = c == 0 ? u2 * w2 : fma(u2, w2, n2[g]);
       }
-      const double f3 = p.tab[L.F3a + c * 32 + lane];
+    };
+    if constexpr (KA == kCherry) cherry(tab + L.F3a, tab + L.Ra, sa, sa2, Ua, p1a, p2a, acc[2], acc[3]);
+    if constexpr (KB == kCherry) cherry(tab + L.F3b, tab + L.Rb, sb, sb2, Ub, p1b, p2b, acc[4], acc[5]);
+    if constexpr (KA == kInner) { // then b is inner too: b's message waits on the stack
+      const double f3b = tab[L.F3b + c * 32 + lane];
 #pragma unroll
-      for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ua[g], f3);
-    } else if constexpr (KB != kTip) {
-      const double f3 = p.tab[L.F3b + c * 32 + lane];
+      for (int g = 0; g < NG; g++) dmma(push[c][g], unused, Ub[g], f3b);
+      const double f3a = tab[L.F3a + c * 32 + lane];
+#pragma unroll
+      for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ua[g], f3a);
+    } else if constexpr (KB == kInner) {
+      const double f3 = tab[L.F3b + c * 32 + lane];
 #pragma unroll
       for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ub[g], f3);
     } else if (pop) {
@@ -146,75 +176,93 @@ __device__ __forceinline__ void node_fast(const NodePtrs& p, int lane, const int
   }
 }
 
-// Same node with ambiguity codes somewhere in the warp's sites (gaps, N, ...): a tip's partial
-// is its 0/1 state mask and goes through the DMMA like an inner child's.
-template <int NG, int C>
-__device__ __forceinline__ void node_masks(const NodePtrs& p, int lane, int kind_a, int kind_b, const uint32_t (&ma)[NG],
-                                        const uint32_t (&ma2)[NG], const uint32_t (&mb)[NG], const uint32_t (&mb2)[NG],
-                                        double (&G)[C][NG], double (*push)[NG], const double (*pop)[NG],
-                                        double (&acc_a)[NG], double (&acc_b)[NG]) {
-  const int q = lane & 3;
-  const RecLayout L = rec_layout(C, kind_a, kind_b);
+// Per-lane constants of a consumer warp.
+struct UpLane {
+  int lane, q, lsite;      // lsite = wsite + s8: this lane's first site inside the CTA (group g adds 8 g)
+  double* out;             // b.out + site0 + wsite + 8 (q & 1) + s8: the lane's store column after the quad reduction
+  int64_t n_pad;
+};
+
+// One node of the walk, specialised by what the two children are: tip codes, arithmetic, release of the
+// stage, then the sums over the four state lanes of a site and the stores.  STATES: the codes are resolved
+// state indices (device-simulated alignments); otherwise they go through the code -> state-mask table and
+// the warp takes the mask path when any of its sites is ambiguous.
+template <int NG, int C, int KA, int KB, bool STATES>
+__device__ __forceinline__ void node_step(const unsigned char* stage, int4 h0, const UpLane& ln, const uint32_t* cmask,
+                                          double (&G)[C][NG], double (*stk)[C][NG], uint64_t* empty_bar) {
+  constexpr uint32_t kBlock = C * kSG * 32;
+  const double* tab = reinterpret_cast<const double*>(stage + sizeof(UpMmaHdr));
+  const unsigned char* ts = stage + h0.y + ln.lsite;   // tip code of (row, group g): ts[row * kSG + 8 g]
+  const double* blk_a = reinterpret_cast<const double*>(stage + h0.z) + ln.lsite * 4 + ln.q;
+  const double* blk_b = blk_a + (KA == kInner ? kBlock / 8 : 0);
+  double (*push)[NG] = stk[(h0.x >> 8) & 0xff];
+  const int pop_level = (h0.x >> 16) & 0xff;
+  const double (*pop)[NG] = (KA != kInner && KB != kInner && pop_level != 0xff) ? stk[pop_level] : nullptr;
+
+  uint32_t sa[NG], sa2[NG], sb[NG], sb2[NG];
 #pragma unroll
-  for (int c = 0; c < C; c++) {
-    double Da[NG], Db[NG];
-    auto child = [&](int kind, const double* blk, const uint32_t (&m1)[NG], const uint32_t (&m2)[NG], const double* Px,
-                     double (&D)[NG]) {
-      if (kind == kInner) {
-#pragma unroll
-        for (int g = 0; g < NG; g++) D[g] = blk[(size_t)c * (kSG * 4) + g * 32 + lane];
-      } else if (kind == kTip) {
-#pragma unroll
-        for (int g = 0; g < NG; g++) D[g] = (m1[g] >> q) & 1u ? 1. : 0.;
-      } else {
-        const double* P1 = Px + c * 16 + q * 4;  // row q of the first leaf's table
-        const double* P2 = P1 + C * 16;
-#pragma unroll
-        for (int g = 0; g < NG; g++) {
-          double u = 0., v = 0.;
-#pragma unroll
-          for (int y = 0; y < 4; y++) {
-            u += (m1[g] >> y) & 1u ? P1[y] : 0.;
-            v += (m2[g] >> y) & 1u ? P2[y] : 0.;
-          }
-          D[g] = u * v;
-        }
-      }
-    };
-    child(kind_a, p.blk_a, ma, ma2, p.tab + L.Pxa, Da);
-    child(kind_b, p.blk_b, mb, mb2, p.tab + L.Pxb, Db);
-    const double fa = p.tab[L.F1a + c * 32 + lane], fb = p.tab[L.F1b + c * 32 + lane];
-    double Sa[NG], Ta[NG], Sb[NG], Tb[NG], Ua[NG], Ub[NG];
-#pragma unroll
-    for (int g = 0; g < NG; g++) dmma(Sa[g], Ta[g], Da[g], fa);
-#pragma unroll
-    for (int g = 0; g < NG; g++) dmma(Sb[g], Tb[g], Db[g], fb);
+  for (int g = 0; g < NG; g++) {
+    sa[g] = KA != kInner ? ts[8 * g] : 0;
+    sa2[g] = KA == kCherry ? ts[2 * kSG + 8 * g] : 0;
+    sb[g] = KB != kInner ? ts[kSG + 8 * g] : 0;
+    sb2[g] = KB == kCherry ? ts[3 * kSG + 8 * g] : 0;
+  }
+  double acc[6][NG];
+  if constexpr (STATES || (KA == kInner && KB == kInner)) {
+    node_body<NG, C, KA, KB, false>(tab, blk_a, blk_b, ln.lane, sa, sa2, sb, sb2, G, push, pop, acc);
+  } else {
+    bool single = true;
 #pragma unroll
     for (int g = 0; g < NG; g++) {
-      Ua[g] = G[c][g] * Sb[g];
-      Ub[g] = G[c][g] * Sa[g];
-      acc_a[g] = c == 0 ? Ua[g] * Ta[g] : fma(Ua[g], Ta[g], acc_a[g]);
-      acc_b[g] = c == 0 ? Ub[g] * Tb[g] : fma(Ub[g], Tb[g], acc_b[g]);
+      sa[g] = KA != kInner ? cmask[sa[g]] : 1u;
+      sa2[g] = KA == kCherry ? cmask[sa2[g]] : 1u;
+      sb[g] = KB != kInner ? cmask[sb[g]] : 1u;
+      sb2[g] = KB == kCherry ? cmask[sb2[g]] : 1u;
+      single = single && __popc(sa[g]) == 1 && __popc(sa2[g]) == 1 && __popc(sb[g]) == 1 && __popc(sb2[g]) == 1;
     }
-    double unused;
-    if (kind_a != kTip) {
-      if (kind_b != kTip) {
-        const double f3 = p.tab[L.F3b + c * 32 + lane];
+    if (__all_sync(0xffffffffu, single)) {
 #pragma unroll
-        for (int g = 0; g < NG; g++) dmma(push[c][g], unused, Ub[g], f3);
+      for (int g = 0; g < NG; g++) {
+        sa[g] = __ffs(sa[g]) - 1; sa2[g] = __ffs(sa2[g]) - 1;
+        sb[g] = __ffs(sb[g]) - 1; sb2[g] = __ffs(sb2[g]) - 1;
       }
-      const double f3 = p.tab[L.F3a + c * 32 + lane];
-#pragma unroll
-      for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ua[g], f3);
-    } else if (kind_b != kTip) {
-      const double f3 = p.tab[L.F3b + c * 32 + lane];
-#pragma unroll
-      for (int g = 0; g < NG; g++) dmma(G[c][g], unused, Ub[g], f3);
-    } else if (pop) {
-#pragma unroll
-      for (int g = 0; g < NG; g++) G[c][g] = pop[c][g];
+      node_body<NG, C, KA, KB, false>(tab, blk_a, blk_b, ln.lane, sa, sa2, sb, sb2, G, push, pop, acc);
+    } else {
+      node_body<NG, C, KA, KB, true>(tab, blk_a, blk_b, ln.lane, sa, sa2, sb, sb2, G, push, pop, acc);
     }
   }
+  // output rows: lanes with q & 2 own the second branch of each pair (b, a2, b2)
+  const int* hdr = reinterpret_cast<const int*>(stage);
+  const int sel = (ln.q >> 1) & 1;
+  const int ob0 = hdr[4 + sel];
+  const int ob1 = KA == kCherry ? hdr[6 + sel] : -1;
+  const int ob2 = KB == kCherry ? hdr[8 + sel] : -1;
+  __syncwarp();
+  if (ln.lane == 0) mbar_arrive(empty_bar);      // the stage has been read
+
+  // ---- sum over the four state lanes of a site: 2 NG values per lane -> NG / 2 complete sums per lane
+  //      (transposing reduction, 3 NG / 2 shuffles instead of 4 NG); lane q ends up with the items
+  //      (branch = q >> 1, groups 2 j + (q & 1)).  1 / L is already in G (folded into the root message).
+  constexpr int NJ = NG / 2;
+  auto reduce_pair = [&](const double (&x)[NG], const double (&y)[NG], int ob) {
+    double v[NG];
+#pragma unroll
+    for (int g = 0; g < NG; g++) {
+      const double send = (ln.q & 2) ? x[g] : y[g];
+      const double keep = (ln.q & 2) ? y[g] : x[g];
+      v[g] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int j = 0; j < NJ; j++) {
+      const double send = (ln.q & 1) ? v[2 * j] : v[2 * j + 1];
+      const double keep = (ln.q & 1) ? v[2 * j + 1] : v[2 * j];
+      const double t = keep + __shfl_xor_sync(0xffffffffu, send, 1);
+      if (ob >= 0) ln.out[(size_t)ob * ln.n_pad + 16 * j] = t;
+    }
+  };
+  reduce_pair(acc[0], acc[1], ob0);
+  if constexpr (KA == kCherry) reduce_pair(acc[2], acc[3], ob1);
+  if constexpr (KB == kCherry) reduce_pair(acc[4], acc[5], ob2);
 }
 
 // One node's copies into ring stage s: record, tip rows, partial chunks of the stored children (one lane).
@@ -242,33 +290,31 @@ __device__ __forceinline__ void up_issue_node(const MapModel& m, const MapBuffer
   if (inb) tma_bulk_g2s(st + blk_off + (ina ? kBlock : 0), b.D + d_chunk(chunk, ref_b, m.n_slots, C), kBlock, full);
 }
 
-// FOLD: no producer warp.  The CTA is kSG / (8 NG) consumer warps (8 at NG = 2 -> with two CTAs per SM four
-// warps per SM sub-partition and 128 registers per thread, where the ninth warp capped them at 96 with spills);
-// the refill of the stage node n - 1 used (with node n - 1 + NSTG) is issued by warp (n - 1) % W at the top of
-// its iteration n, with the descriptors fetched one iteration earlier.
-template <int NG, int C, int MINB, bool FOLD>
-__global__ void __launch_bounds__(32 * (kSG / (8 * NG) + (FOLD ? 0 : 1)), MINB) k1_up_mma(MapModel m, MapBuffers b, UpMmaParams up) {
+// Measured and left out (B200, config 4): folding the producer into the consumer warps (8 warps per CTA, 128
+// registers: 36.3 ms per step against 34.4), L2 prefetch of the chunks 2..8 nodes ahead of their stage copy
+// (33.3-35.6 against 33.1), producer wake-up by suspend-time hint or a 40 ns back-off instead of 200 ns (no change).
+template <int NG, int C, int MINB, bool STATES>
+__global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(MapModel m, MapBuffers b, UpMmaParams up) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int W = kSG / (8 * NG);                // consumer warps
-  constexpr uint32_t kBlock = C * kSG * 32;        // bytes of one child's partial chunk
   const uint32_t stage_bytes = up.stage_bytes;     // packed per node: record | tip rows (a, b, a2, b2) | chunks
   const int NSTG = up.n_stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_pad = b.n_pad;
   const int64_t site0 = (int64_t)blockIdx.x * kSG;
   uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* stg_empty = stg_full + kMaxStages;
   unsigned char* stg_ring = smem + 128;
 
-  __shared__ uint32_t cmask[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) cmask[i] = __ldg(m.code_mask + i);
+  __shared__ uint32_t cmask[STATES ? 1 : 256];
+  if constexpr (!STATES)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) cmask[i] = __ldg(m.code_mask + i);
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTG; i++) { mbar_init(&stg_full[i], 1); mbar_init(&stg_empty[i], W); }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (!FOLD && warp == W) {
+  if (warp == W) {
     // ---- producer: node n's record, tip rows and the partial chunks of its inner children go
     //      to stage n % NSTG; one mbarrier full / empty pair per stage.  The 32 lanes fetch the
     //      descriptors of 32 nodes at a time; lane 0 issues the copies.
@@ -294,135 +340,45 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + (FOLD ? 0 : 1)), MINB) 
     }
     return;
   }
-  if (FOLD) { // prologue: the first NSTG nodes, one per warp
-    for (uint32_t n = warp; n < (uint32_t)NSTG && n < up.n_nodes; n += W)
-      if (lane == 0)
-        up_issue_node<C>(m, b, up, __ldg(up.refs + 2 * n), __ldg(up.refs + 2 * n + 1), __ldg(up.rec_off + n), __ldg(up.rec_bytes + n),
-                         stg_ring + (size_t)n * stage_bytes, &stg_full[n], site0);
-  }
 
   // ---- consumers
-  const int q = lane & 3, s8 = lane >> 2;
-  const int wsite = warp * (8 * NG);             // first site of this warp inside the CTA
+  UpLane ln;
+  ln.lane = lane; ln.q = lane & 3;
+  ln.lsite = warp * (8 * NG) + (lane >> 2);
+  ln.n_pad = b.n_pad;
+  ln.out = b.out + site0 + warp * (8 * NG) + 8 * (lane & 1) + (lane >> 2);
   double G[C][NG];
   double stk[kMaxStack][C][NG];
-  int sp = 0;
   {
-    const double piq = __ldg(m.pi + q);
-#pragma unroll
-    for (int c = 0; c < C; c++)
-#pragma unroll
-      for (int g = 0; g < NG; g++) G[c][g] = piq;
-  }
-  // after the quad reduction lane q owns the items (branch = q >> 1, groups j * 2 + (q & 1))
-  constexpr int NJ = NG / 2;
-  double invL[NJ];
-#pragma unroll
-  for (int j = 0; j < NJ; j++) invL[j] = b.invL[site0 + wsite + 8 * (2 * j + (q & 1)) + s8];
-
-  uint32_t cs = 0, cph = 0;
-  int4 pre0 = make_int4(0, 0, 0, 0), pre1 = pre0; // FOLD: descriptors of the node this warp issues next
-  uint32_t pre_off = 0, pre_nb = 0;
-  for (uint32_t node = 0; node < up.n_nodes; node++) {
-    if (FOLD) {
-      // refill duty of node - 1's stage (all W warps have arrived on its empty barrier before it is reused)
-      if (node >= 1 && warp == (int)((node - 1) % W) && node - 1 + NSTG < up.n_nodes) {
-        const uint32_t ps = cs == 0 ? (uint32_t)NSTG - 1 : cs - 1, pph = cs == 0 ? cph ^ 1 : cph;
-        if (lane == 0) {
-          mbar_wait(&stg_empty[ps], pph);
-          up_issue_node<C>(m, b, up, pre0, pre1, pre_off, pre_nb, stg_ring + (size_t)ps * stage_bytes, &stg_full[ps], site0);
-        }
-        __syncwarp();
-      }
-      if (warp == (int)(node % W) && node + NSTG < up.n_nodes) { // used at the top of the next iteration
-        const uint32_t nn = node + NSTG;
-        pre0 = __ldg(up.refs + 2 * nn); pre1 = __ldg(up.refs + 2 * nn + 1);
-        pre_off = __ldg(up.rec_off + nn); pre_nb = __ldg(up.rec_bytes + nn);
-      }
-    }
-    mbar_wait(&stg_full[cs], cph);
-    const unsigned char* stage = stg_ring + (size_t)cs * stage_bytes;
-    const int4 h0 = *reinterpret_cast<const int4*>(stage);
-    const int4 h1 = *reinterpret_cast<const int4*>(stage + 16);
-    const uint32_t flags = (uint32_t)h0.x;
-    const int kind_a = (flags & kUpTipA) ? kTip : (flags & kUpCherryA) ? kCherry : kInner;
-    const int kind_b = (flags & kUpTipB) ? kTip : (flags & kUpCherryB) ? kCherry : kInner;
-    NodePtrs p;
-    p.tab = reinterpret_cast<const double*>(stage + 32);
-    // h1.y / h1.z: offsets of the tip rows and of the first stored child's chunk in this stage
-    const unsigned char* ts = stage + h1.y + wsite + s8; // tip code of (row, group g): ts[row * kSG + 8 g]
-    p.blk_a = reinterpret_cast<const double*>(stage + h1.z) + (size_t)wsite * 4;
-    p.blk_b = p.blk_a + (kind_a == kInner ? kBlock / 8 : 0);
-
-    // ---- tips and cherries: states (or state masks) of this lane's NG sites
-    double acc_a[NG], acc_b[NG];
-    double (*push)[NG] = stk[sp];
-    const double (*pop)[NG] = (flags & kUpPop) ? stk[sp > 0 ? sp - 1 : 0] : nullptr;
-    int sa[NG], sa2[NG], sb[NG], sb2[NG];
-    uint32_t ma[NG], ma2[NG], mb[NG], mb2[NG];
-    bool fast = true;
-    if (m.states_only) { // device-simulated alignment: the codes are the states
-#pragma unroll
-      for (int g = 0; g < NG; g++) {
-        sa[g] = kind_a != kInner ? ts[8 * g] : 0;
-        sa2[g] = kind_a == kCherry ? ts[2 * kSG + 8 * g] : 0;
-        sb[g] = kind_b != kInner ? ts[kSG + 8 * g] : 0;
-        sb2[g] = kind_b == kCherry ? ts[3 * kSG + 8 * g] : 0;
-      }
-    } else {
-      bool single = true;
-#pragma unroll
-      for (int g = 0; g < NG; g++) {
-        ma[g] = kind_a != kInner ? cmask[ts[8 * g]] : 1u;
-        ma2[g] = kind_a == kCherry ? cmask[ts[2 * kSG + 8 * g]] : 1u;
-        mb[g] = kind_b != kInner ? cmask[ts[kSG + 8 * g]] : 1u;
-        mb2[g] = kind_b == kCherry ? cmask[ts[3 * kSG + 8 * g]] : 1u;
-        single = single && __popc(ma[g]) == 1 && __popc(ma2[g]) == 1 && __popc(mb[g]) == 1 && __popc(mb2[g]) == 1;
-        sa[g] = __ffs(ma[g]) - 1; sa2[g] = __ffs(ma2[g]) - 1;
-        sb[g] = __ffs(mb[g]) - 1; sb2[g] = __ffs(mb2[g]) - 1;
-      }
-      fast = __all_sync(0xffffffffu, single);
-    }
-    if (fast) {
-      switch (kind_a * 3 + kind_b) {
-#define CMB_NODE(KA, KB) \
-  case KA * 3 + KB: node_fast<NG, C, KA, KB>(p, lane, sa, sa2, sb, sb2, G, push, pop, acc_a, acc_b); break;
-        CMB_NODE(kInner, kInner) CMB_NODE(kInner, kTip) CMB_NODE(kInner, kCherry)
-        CMB_NODE(kTip, kInner) CMB_NODE(kTip, kTip) CMB_NODE(kTip, kCherry)
-        CMB_NODE(kCherry, kInner) CMB_NODE(kCherry, kTip) CMB_NODE(kCherry, kCherry)
-#undef CMB_NODE
-      }
-    } else {
-      node_masks<NG, C>(p, lane, kind_a, kind_b, ma, ma2, mb, mb2, G, push, pop, acc_a, acc_b);
-    }
-    if (flags & kUpPush) ++sp;
-    else if (flags & kUpPop) --sp;
-    // the output rows are read again here rather than kept live (or spilled) across the node body
-    const int ob = reinterpret_cast<const volatile int*>(stage)[3 + ((lane >> 1) & 1)]; // q & 2 ? out_b : out_a
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&stg_empty[cs]);   // the stage has been read
-    if (++cs == (uint32_t)NSTG) { cs = 0; cph ^= 1; }
-
-    // ---- sum over the four state lanes of a site: 2 NG values per lane -> NG / 2 complete
-    //      sums per lane (transposing reduction, 3 NG / 2 shuffles instead of 4 NG)
-    double v[NG];
+    // root message pi, with 1 / L of the site folded in: every contraction below is linear in it, so the
+    // stored values are n / L without a multiplication per output
+    const double piq = __ldg(m.pi + ln.q);
 #pragma unroll
     for (int g = 0; g < NG; g++) {
-      const double send = (q & 2) ? acc_a[g] : acc_b[g];
-      const double keep = (q & 2) ? acc_b[g] : acc_a[g];
-      v[g] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-    }
+      const double gi = piq * b.invL[site0 + ln.lsite + 8 * g];
 #pragma unroll
-    for (int j = 0; j < NJ; j++) {
-      const double send = (q & 1) ? v[2 * j] : v[2 * j + 1];
-      const double keep = (q & 1) ? v[2 * j + 1] : v[2 * j];
-      const double t = keep + __shfl_xor_sync(0xffffffffu, send, 1);
-      if (ob >= 0) b.out[(size_t)ob * n_pad + site0 + wsite + 8 * (2 * j + (q & 1)) + s8] = t * invL[j];
+      for (int c = 0; c < C; c++) G[c][g] = gi;
     }
+  }
+
+  uint32_t cs = 0, cph = 0;
+  for (uint32_t node = 0; node < up.n_nodes; node++) {
+    mbar_wait(&stg_full[cs], cph);
+    const unsigned char* stage = stg_ring + (size_t)cs * stage_bytes;
+    const int4 h0 = *reinterpret_cast<const int4*>(stage); // kase | push level << 8 | pop level << 16, tips_off, blk_off, flags
+    // smaller child first: an inner a implies an inner b, a cherry a implies a non-tip b
+    switch (h0.x & 0xff) {
+#define CMB_NODE(KA, KB) \
+  case KA * 3 + KB: node_step<NG, C, KA, KB, STATES>(stage, h0, ln, cmask, G, stk, &stg_empty[cs]); break;
+      CMB_NODE(kInner, kInner) CMB_NODE(kTip, kInner) CMB_NODE(kTip, kTip) CMB_NODE(kTip, kCherry)
+      CMB_NODE(kCherry, kInner) CMB_NODE(kCherry, kCherry)
+#undef CMB_NODE
+    }
+    if (++cs == (uint32_t)NSTG) { cs = 0; cph ^= 1; }
   }
 }
 
-template <int NG, int C, int MINB, bool FOLD>
+template <int NG, int C, int MINB, bool STATES>
 bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.C != C) return false;
   int dev = 0, max_smem = 0;
@@ -443,15 +399,15 @@ bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   up.n_stages = (int)std::min<size_t>(std::min(kMaxStages, stage_cap), ((size_t)max_smem - fixed) / stage);
   // Shared memory is carved out of the 256 KB it shares with L1, and the consumers' message stack and
   // register spills live in local memory behind that L1: a third stage at C = 4 (2 x 111 KB of shared
-  // memory, ~28 KB of L1) ran 12.4 ms instead of 10.8 ms.  Keep a CTA's ring within 80 KB.
+  // memory, ~28 KB of L1) ran 41 ms per step instead of 33.  Keep a CTA's ring within 80 KB.
   static const size_t ring_kb = getenv("CMB_UP_RING_KB") ? (size_t)atoi(getenv("CMB_UP_RING_KB")) : 80;
   if (MINB > 1) up.n_stages = (int)std::max<size_t>(2, std::min<size_t>(up.n_stages, (ring_kb * 1024) / stage));
   const size_t smem = fixed + (size_t)up.n_stages * stage;
-  constexpr int threads = 32 * (kSG / (8 * NG) + (FOLD ? 0 : 1));
-  CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int threads = 32 * (kSG / (8 * NG) + 1);
+  CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB, STATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (getenv("CMB_UP_CARVEOUT"))
-    CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB, FOLD>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CMB_UP_CARVEOUT"))));
-  k1_up_mma<NG, C, MINB, FOLD><<<(unsigned)(b.n_pad / kSG), threads, smem, st>>>(m, b, up);
+    CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB, STATES>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CMB_UP_CARVEOUT"))));
+  k1_up_mma<NG, C, MINB, STATES><<<(unsigned)(b.n_pad / kSG), threads, smem, st>>>(m, b, up);
   CMB_CUDA(cudaGetLastError());
   return true;
 }
@@ -461,13 +417,7 @@ bool up_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   if (m.C != C) return false;
   // B200, config 4 (517 k sites): 2 groups/warp x 2 CTAs/SM (16 consumer warps) 10.8 ms;
   // 4 groups/warp x 2 CTAs/SM (8 warps, 168 regs) 11.2 ms; 2 groups/warp x 1 CTA/SM 12.7 ms
-  if constexpr (C == 4) {
-    static const int shape = getenv("CMB_UP_SHAPE") ? atoi(getenv("CMB_UP_SHAPE")) : 0; // experiment switch
-    if (shape == 42) return try_up_mma<4, C, 2, false>(m, b, s, st);
-    if (shape == 21) return try_up_mma<2, C, 1, false>(m, b, s, st);
-  }
-  static const int fold = getenv("CMB_UP_FOLD") ? atoi(getenv("CMB_UP_FOLD")) : 1; // experiment switch
-  if (fold) return try_up_mma<2, C, 2, true>(m, b, s, st) || try_up_mma<2, C, 1, true>(m, b, s, st);
+  if (m.states_only) return try_up_mma<2, C, 2, true>(m, b, s, st) || try_up_mma<2, C, 1, true>(m, b, s, st);
   return try_up_mma<2, C, 2, false>(m, b, s, st) || try_up_mma<2, C, 1, false>(m, b, s, st);
 }
 

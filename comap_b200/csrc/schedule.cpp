@@ -337,32 +337,46 @@ void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
   const int C = mt.C;
   std::vector<std::vector<unsigned char>> recs;
   size_t max_rec = 0;
+  // Cherries are not nodes of this walk: a cherry child is expanded INSIDE its parent's record (its partial
+  // is recomputed from the two tip rows, its message stays in registers and its two leaf branches are
+  // contracted there), so a third of the node iterations and the stack traffic of their messages go away.
+  // Kinds of a child: inner (stored partial), tip, cherry.  With the smaller child first only
+  // tip-tip, tip-cherry, tip-inner, cherry-cherry, cherry-inner and inner-inner occur.
+  auto kind_of = [&](int x) { return t.bin[x].left < 0 ? 1 : t.bin[x].cherry ? 2 : 0; };
   std::vector<int> st;
-  for (size_t i = 0; i < t.up_order.size(); i++) {
-    const int v = t.up_order[i];
+  int depth = 0;
+  int v = t.bin_root;
+  while (v >= 0) {
     const BinNode& n = t.bin[v];
     int a = n.left, b = n.right;
     if (t.bin[a].leaves > t.bin[b].leaves) std::swap(a, b);
-    const bool ta = t.bin[a].left < 0, tb = t.bin[b].left < 0;
-    const bool ca = t.bin[a].cherry, cb = t.bin[b].cherry;
-    UpHdr h{};
+    const int ka = kind_of(a), kb = kind_of(b);
+    if (ka == 0 && kb != 0) fail("internal: up order must expand the smaller child first");
+    const bool ta = ka == 1, tb = kb == 1, ca = ka == 2, cb = kb == 2;
+    UpMmaHdr h{};
     h.flags = (ta ? kUpTipA : 0) | (tb ? kUpTipB : 0) | (ca ? kUpCherryA : 0) | (cb ? kUpCherryB : 0);
-    if (!ta) {
-      h.flags |= kUpTakeA;
-      if (!tb) { h.flags |= kUpPush; st.push_back(b); }
-    } else if (!tb) h.flags |= kUpTakeB;
-    else if (!st.empty()) { h.flags |= kUpPop; st.pop_back(); }
+    int next = -1;
+    int push_level = 0, pop_level = 0xff; // stack slots the consumers use: no run-time stack pointer
+    if (ka == 0) { h.flags |= kUpTakeA | kUpPush; push_level = (int)st.size(); st.push_back(b); depth = std::max(depth, (int)st.size()); next = a; }
+    else if (kb == 0) { h.flags |= kUpTakeB; next = b; }
+    else if (!st.empty()) { h.flags |= kUpPop; next = st.back(); st.pop_back(); pop_level = (int)st.size(); }
+    h.kase = (uint32_t)(ka * 3 + kb) | (uint32_t)push_level << 8 | (uint32_t)pop_level << 16;
     h.ref_a = ta ? t.bin[a].tip_row : ca ? t.bin[t.bin[a].left].tip_row : t.bin[a].slot;
     h.ref_b = tb ? t.bin[b].tip_row : cb ? t.bin[t.bin[b].left].tip_row : t.bin[b].slot;
-    h.ref_a2 = ca ? t.bin[t.bin[a].right].tip_row : -1;
-    h.ref_b2 = cb ? t.bin[t.bin[b].right].tip_row : -1;
+    const int ref_a2 = ca ? t.bin[t.bin[a].right].tip_row : -1;
+    const int ref_b2 = cb ? t.bin[t.bin[b].right].tip_row : -1;
     h.out_a = t.bin[a].branch;
     h.out_b = t.bin[b].branch;
+    h.out_a1 = ca ? t.bin[t.bin[a].left].branch : -1;
+    h.out_a2 = ca ? t.bin[t.bin[a].right].branch : -1;
+    h.out_b1 = cb ? t.bin[t.bin[b].left].branch : -1;
+    h.out_b2 = cb ? t.bin[t.bin[b].right].branch : -1;
     s.n_records++;
     std::vector<unsigned char> rec;
     append(rec, &h, sizeof h);
     double P[16], W[16], frag[32];
-    for (int e = 0; e < 2; e++) // F1a, F1b
+    for (int e = 0; e < 2; e++) { // F1a, F1b: children whose partial goes through the DMMA
+      if (e ? tb : ta) continue;
       for (int c = 0; c < C; c++) {
         table_of(t, mt, e ? b : a, 0, c, P);
         table_of(t, mt, e ? b : a, 1, c, W);
@@ -372,7 +386,8 @@ void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
         }
         append(rec, frag, sizeof frag);
       }
-    for (int e = 0; e < 2; e++) { // F3a, F3b for inner children
+    }
+    for (int e = 0; e < 2; e++) { // F3a, F3b: messages to non-tip children
       if (e ? tb : ta) continue;
       for (int c = 0; c < C; c++) {
         table_of(t, mt, e ? b : a, 0, c, P);
@@ -383,41 +398,34 @@ void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
         append(rec, frag, sizeof frag);
       }
     }
-    for (int e = 0; e < 2; e++) { // raw leaf tables of cherries
-      if (!(e ? cb : ca)) continue;
-      const BinNode& ch = t.bin[e ? b : a];
-      for (int leaf : {ch.left, ch.right})
-        for (int c = 0; c < C; c++) {
-          table_of(t, mt, leaf, 0, c, P);
-          append(rec, P, sizeof P);
-        }
-    }
-    for (int e = 0; e < 2; e++) { // raw P and W of tip children: conflict-free column picks
-      if (!(e ? tb : ta)) continue;
-      for (int what = 0; what < 2; what++)
-        for (int c = 0; c < C; c++) {
-          table_of(t, mt, e ? b : a, what, c, P);
-          append(rec, P, sizeof P);
-        }
+    for (int e = 0; e < 2; e++) { // raw 4x4 tables for conflict-free column picks
+      const int x = e ? b : a;
+      if (e ? tb : ta) {          // tip: P[C], W[C]
+        for (int what = 0; what < 2; what++)
+          for (int c = 0; c < C; c++) { table_of(t, mt, x, what, c, P); append(rec, P, sizeof P); }
+      } else if (e ? cb : ca) {   // cherry: P1[C], P2[C], W1[C], W2[C] of its two leaf edges
+        for (int what = 0; what < 2; what++)
+          for (int leaf : {t.bin[x].left, t.bin[x].right})
+            for (int c = 0; c < C; c++) { table_of(t, mt, leaf, what, c, P); append(rec, P, sizeof P); }
+      }
     }
     pad16(rec);
     // Packed stage of this node in the kernel's ring: record | four tip rows (when a child is a
-    // tip or a cherry) | partial chunk of each stored child.  Nodes with two stored children
-    // carry the shortest records and no tip rows, so the largest stage is well below
-    // "largest record + tip rows + two chunks" and a third stage fits at C = 4.
+    // tip or a cherry) | partial chunk of each stored child.
     const uint32_t tips_off = (uint32_t)((rec.size() + 127) & ~size_t(127));
     const uint32_t blk_off = tips_off + ((ta || tb || ca || cb) ? 4u * kChunkSites : 0u);
-    const uint32_t n_blk = (uint32_t)(!ta && !ca) + (uint32_t)(!tb && !cb);
+    const uint32_t n_blk = (uint32_t)(ka == 0) + (uint32_t)(kb == 0);
     s.stage_bytes = std::max(s.stage_bytes, blk_off + n_blk * (uint32_t)C * kChunkSites * 32u);
-    UpHdr hc = h; // consumers' view: where the tip rows and chunks sit in the stage
-    hc.ref_a2 = (int32_t)tips_off;
-    hc.ref_b2 = (int32_t)blk_off;
-    std::memcpy(rec.data(), &hc, sizeof hc);
+    h.tips_off = (int32_t)tips_off;
+    h.blk_off = (int32_t)blk_off;
+    std::memcpy(rec.data(), &h, sizeof h);
     s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.ref_a); s.aux.push_back(h.ref_b); s.aux.push_back((int32_t)tips_off);
-    s.aux.push_back(h.ref_a2); s.aux.push_back(h.ref_b2); s.aux.push_back((int32_t)blk_off); s.aux.push_back(0);
+    s.aux.push_back(ref_a2); s.aux.push_back(ref_b2); s.aux.push_back((int32_t)blk_off); s.aux.push_back(0);
     max_rec = std::max(max_rec, rec.size());
     recs.push_back(std::move(rec));
+    v = next;
   }
+  s.stack_depth = depth;
   Packer pk(s, (uint32_t)max_rec);
   for (auto& r : recs) { pk.add(r); pk.flush(); }
 }

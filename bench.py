@@ -220,9 +220,64 @@ def config_dict(cfg, n_gpus):
 # ------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------
-class _DevArr:
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = dict(shape=(n,), typestr="<f8", data=(ptr, False), version=2)
+METRIC = "site_pairs_scored_per_s_incl_mapping_and_null"
+
+
+def load_peaks():
+    """HBM peak: MEASURED_PEAKS.json (driver-written) else the profiling recipe's fallback; FP64 peaks:
+    PEAKS_FP64.json (tools/dmmabench + tools/fp64bench on this pool's B200s, committed)."""
+    out = dict(hbm_gbs=6650.0, hbm_source="fallback 6650 GB/s (B200_PROFILING.md)", fp64_dmma_tflops=37.0,
+               fp64_dfma_tflops=34.0, fp64_source="PEAKS_FP64.json missing: nominal")
+    try:
+        m = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        out["hbm_gbs"] = float(m["hbm_gbs"]); out["hbm_source"] = "MEASURED_PEAKS.json hbm_gbs"
+    except Exception:
+        pass
+    try:
+        f = json.load(open(os.path.join(ROOT, "PEAKS_FP64.json")))
+        out["fp64_dmma_tflops"] = float(f["fp64_dmma_tflops"]); out["fp64_dfma_tflops"] = float(f["fp64_dfma_tflops"])
+        out["fp64_source"] = "PEAKS_FP64.json (%s)" % f.get("how", "")
+    except Exception:
+        pass
+    return out
+
+
+def profile_dram_bytes(pattern):
+    """dram__bytes_read.sum + dram__bytes_write.sum and the grid size of the newest committed `ncu --set full`
+    summary whose file name matches `pattern` (profiles/r*_<kernel>.txt, written by tools/ncu_summary.py)."""
+    import glob
+    import re
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", pattern))):
+        best = path
+    if not best:
+        return None
+    txt = open(best).read()
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    tot = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        m = re.search(r"^%s\s+(\S+)\s+([0-9.eE+-]+)" % re.escape(key), txt, re.M)
+        if not m:
+            return None
+        tot += float(m.group(2)) * unit.get(m.group(1), 1.0)
+    g = re.search(r"^launch__grid_size\s+([0-9.]+)", txt, re.M)
+    d = re.search(r"^gpu__time_duration.sum\s+(\S+)\s+([0-9.eE+-]+)", txt, re.M)
+    return dict(file=os.path.relpath(best, ROOT), dram_bytes=tot, grid=float(g.group(1)) if g else None,
+                ms=float(d.group(2)) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(d.group(1), 1.0) if d else None)
+
+
+def table_checksum(cols, n):
+    """Order-independent 64-bit checksum of the (i, j, Stat, PValue, Nsim) rows: every row is hashed from the bit
+    patterns of its fields and the hashes are summed modulo 2^64, so shards can be added across ranks."""
+    M = np.uint64
+    with np.errstate(over="ignore"):
+        h = cols[0][:n].astype(np.uint64) * M(0x9E3779B97F4A7C15)
+        h ^= cols[1][:n].astype(np.uint64) * M(0xC2B2AE3D27D4EB4F)
+        h ^= cols[2][:n].view(np.uint64) * M(0x165667B19E3779F9)
+        h ^= cols[6][:n].view(np.uint64) * M(0x27D4EB2F165667C5)
+        h ^= cols[7][:n].astype(np.uint64) * M(0x85EBCA77C2B2AE63)
+        h ^= h >> M(29); h *= M(0xBF58476D1CE4E5B9); h ^= h >> M(32)
+        return int(h.sum(dtype=np.uint64))
 
 
 def run_ours(args, cfg):
@@ -241,17 +296,23 @@ def run_ours(args, cfg):
     stream = torch.cuda.Stream()
     w = workload(cfg)
     S, T, R, RC, K = cfg["sites"], cfg["taxa"], cfg["rep_ram"], cfg["rep_cpu"], cfg["null_bins"]
+    A = len(w["pi"])
     B = 2 * T - 3
     stat = cfg["statistic"]
-    # shard of the null replicates / pair rows owned by this rank
-    bounds = par.replicate_bounds(RC, world)
-    r0, r1 = bounds[rank]
-    max_reps = max(e - b for b, e in bounds)
+    r0, r1 = par.replicate_bounds(RC, world)[rank]
 
     with torch.cuda.stream(stream):
         ctx = api.Context(device=local, stream=stream.cuda_stream)
         ctx.set_tree(w["parent"], w["brlen"])
         ctx.set_model(w["Q"], w["pi"], w["rates"], w["probs"])
+        if world > 1:
+            # the library drives NCCL itself (cmb_comm_init + cmb_null_intra_sharded); torch.distributed only
+            # carries the 128-byte id to the other ranks and the timing / checksum reductions
+            uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                uid = torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8).cuda()
+            dist.broadcast(uid, 0)
+            ctx.comm_init(world, rank, uid.cpu().numpy().tobytes())
         codes, _ = ctx.simulate(cfg["aln_seed"], 0, S)     # the synthetic alignment (project's own simulator)
         pin = lambda shape, dt: torch.empty(shape, dtype=dt, pin_memory=True).numpy()
         codes_pin = pin((T, S), torch.uint8); codes_pin[:] = codes
@@ -261,15 +322,7 @@ def run_ours(args, cfg):
                     for dt in api.Context.COL_DTYPE]
 
         def null_dist():
-            if world == 1:
-                ctx.null_intra(stat, cfg["null_seed"], RC, R, K=K, nmax=-1.0)
-            else:
-                ctx.null_intra(stat, cfg["null_seed"], RC, R, K=0, rep_begin=r0, rep_end=r1)
-                sp, mp, n = ctx.null_samples_dev()
-                st_all, nm_all = par.all_gather_null(torch.as_tensor(_DevArr(sp, max(n, 1)), device="cuda"),
-                                                     torch.as_tensor(_DevArr(mp, max(n, 1)), device="cuda"), n, max_reps * R)
-                stream.synchronize()
-                ctx.null_load_dev(st_all.data_ptr(), nm_all.data_ptr(), st_all.numel(), K, -1.0)
+            ctx.null_intra_sharded(stat, cfg["null_seed"], RC, R, K=K, nmax=-1.0)
 
         def step_resident():
             ctx.map(want_vectors=False)
@@ -316,61 +369,261 @@ def run_ours(args, cfg):
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
-        ctx.profile_reset(); ctx.profile_enable(True)
         l0 = ctx.launch_count()
-        ms = timed(step_resident, args.steps)
+        ms = timed(step_resident, args.steps)              # the timed region: no per-kernel events inside
         launches = ctx.launch_count() - l0
-        prof = {k: ctx.profile_get(k) for k in ("map_down", "map_up", "simulate", "null_pairs", "sort", "pairs")}
-        ctx.profile_enable(False)
         ms_e2e = timed(step_e2e, args.steps)
         clocks = sampler.stop() if rank == 0 else None
+        # per-kernel device time: the same steps again with CUDA events around every kernel family
+        # (cmb_profile_*; the events cost host time, so this pass is NOT the one `value` is taken from)
+        ctx.profile_reset(); ctx.profile_enable(True)
+        for _ in range(args.steps):
+            step_resident()
+        names = ("map_down", "map_up", "simulate", "null_pairs", "sort", "pairs")
+        prof = {k: ctx.profile_get(k) for k in names}
+        ctx.profile_enable(False)
 
+        # ---- correctness carried with the number (outside the timed region): checksum of this rank's rows,
+        #      summed over ranks; at N > 1 rank 0 also runs the whole job on its own GPU and must get the same
+        own = table_checksum(cols_pin, n_rows)
+        tot = torch.tensor([own - (1 << 64) if own >= (1 << 63) else own], dtype=torch.int64, device="cuda")
+        nr = torch.tensor([n_rows], dtype=torch.int64, device="cuda")
         lt = torch.tensor([launches], dtype=torch.int64, device="cuda")
         if world > 1:
-            dist.all_reduce(lt)
+            dist.all_reduce(tot); dist.all_reduce(nr); dist.all_reduce(lt)
+        check = dict(rows=int(nr.item()), checksum="%016x" % (int(tot.item()) & ((1 << 64) - 1)),
+                     columns="i j Stat PValue Nsim", how="sum mod 2^64 of per-row hashes over all ranks")
+        if world > 1 and rank == 0:
+            one = api.Context(device=local, stream=stream.cuda_stream)
+            one.set_tree(w["parent"], w["brlen"]); one.set_model(w["Q"], w["pi"], w["rates"], w["probs"])
+            one.set_alignment(codes_pin, w["code_mask"]); one.map(want_vectors=False)
+            one.null_intra(stat, cfg["null_seed"], RC, R, K=K, nmax=-1.0)
+            full, kk = one.pairs(stat, use_null=True)
+            ref = table_checksum([full[c] for c in api.Context.COLS], kk)
+            check["single_gpu_checksum"] = "%016x" % ref
+            check["equal_to_single_gpu"] = bool(ref == (int(tot.item()) & ((1 << 64) - 1)) and kk == int(nr.item()))
+            one.close()
+
         pairs_per_step = S * (S - 1) // 2 + RC * R
         if rank == 0:
-            # roofline of the dominant kernel family: K1 mapping passes
-            map_ms = prof["map_down"][0] + prof["map_up"][0]
+            peaks = load_peaks()
+            C = cfg["classes"]
             sites_mapped = args.steps * (S + 2 * (r1 - r0) * R)
-            abytes_site = algorithmic_bytes_per_site(T, cfg["classes"], 4, B)
-            peaks = {}
-            try:
-                peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-            except Exception:
-                pass
-            peak = float(peaks.get("hbm_gbs", 6650.0))
-            achieved = sites_mapped * abytes_site / (map_ms * 1e-3) / 1e9 if map_ms > 0 else 0.0
-            n_pass = max(1, prof["map_up"][1])
-            # DRAM bytes actually moved, from the committed `ncu --set full` captures of one pass over
-            # 128 256 sites (profiles/r1j_k1_{down,up}_mma.txt: dram__bytes_read.sum + dram__bytes_write.sum);
-            # below the algorithmic figure because cherry partials are recomputed, not stored
-            traffic_site = (69.0e6 + 5.2964e9 + 5.6296e9 + 1.4807e9) / 128256.0
-            line = dict(metric="site_pairs_scored_per_s_incl_mapping_and_null",
-                        value=pairs_per_step * args.steps / (ms * 1e-3), unit="pairs/s", n_gpus=world, steps=args.steps,
-                        warmup=max(3, args.warmup), ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong",
-                        vs_baseline=None, dtype="f64", data="synthetic", config=config_dict(cfg, world), clocks=clocks,
+            passes = max(1, prof["map_up"][1])
+            hbm = peaks["hbm_gbs"]
+
+            def hbm_entry(kernel, bytes_per_site, ms_total, prof_glob, note):
+                ach = sites_mapped * bytes_per_site / (ms_total * 1e-3) / 1e9 if ms_total > 0 else 0.0
+                e = dict(kernel=kernel, bound="hbm", achieved=ach, peak=hbm, unit="GB/s", frac=ach / hbm,
+                         algorithmic_bytes_per_site=bytes_per_site, avg_launch_ms=ms_total / passes,
+                         sites_per_launch=sites_mapped / passes, note=note, traffic=None)
+                pd = profile_dram_bytes(prof_glob)
+                if pd and pd["grid"]:
+                    per_site = pd["dram_bytes"] / (pd["grid"] * 128.0)       # 128 sites per CTA in the A = 4 kernels
+                    e["traffic"] = per_site * sites_mapped / passes
+                    e["traffic_source"] = "%s: dram__bytes_read.sum + dram__bytes_write.sum, scaled by sites" % pd["file"]
+                    e["measured_dram_frac"] = per_site * sites_mapped / (ms_total * 1e-3) / 1e9 / hbm
+                return e
+
+            # SURVEY.md s8(d) K1 bytes per site, split by pass: down = tips + inner partials written once,
+            # up = inner partials read once + output rows + tips (28 B of per-site scalars belong to k1_finish)
+            part = (T - 3) * C * A * 8
+            up = hbm_entry("k1_up_mma" if A == 4 else "k1_up", part + 8 * B + T, prof["map_up"][0], "r2*_k1_up_mma.txt",
+                           "mapping up pass + contraction; cherry partials are recomputed, so DRAM traffic is below the algorithmic bytes")
+            down = hbm_entry("k1_down_mma (+ k1_finish)" if A == 4 else "k1_down", part + T + 28, prof["map_down"][0],
+                             "r2*_k1_down_mma.txt", "mapping down pass; cherry partials are never stored")
+            flops = 2.0 * B * (n_rows * args.steps)
+            tiles_ms = prof["pairs"][0]
+            tiles = dict(kernel="k2_tiles<correlation>", bound="fp64", achieved=flops / (tiles_ms * 1e-3) / 1e12 if tiles_ms > 0 else 0.0,
+                         peak=peaks["fp64_dfma_tflops"], unit="TFLOP/s", algorithmic_flops_per_pair=2 * B,
+                         peak_source=peaks["fp64_source"], avg_launch_ms=tiles_ms / max(1, prof["pairs"][1]),
+                         note="unfused DMUL + DADD in the reference's summation order (bit-exact p-values given vectors): "
+                              "at most half the FMA peak")
+            tiles["frac"] = tiles["achieved"] / tiles["peak"]
+            paired_bytes = 2.0 * B * 8 * ((r1 - r0) * R * args.steps)
+            paired = dict(kernel="k2_paired<correlation>", bound="hbm", achieved=paired_bytes / (prof["null_pairs"][0] * 1e-3) / 1e9
+                          if prof["null_pairs"][0] > 0 else 0.0, peak=hbm, unit="GB/s", algorithmic_bytes_per_pair=2 * B * 8)
+            paired["frac"] = paired["achieved"] / hbm
+            kernel_ms = {k: v[0] / args.steps for k, v in prof.items()}
+            line = dict(metric=METRIC, value=pairs_per_step * args.steps / (ms * 1e-3), unit="pairs/s", n_gpus=world,
+                        steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms / args.steps, higher_is_better=True,
+                        scaling="strong", vs_baseline=None, dtype="f64", data="synthetic", config=config_dict(cfg, world),
+                        clocks=clocks,
                         e2e=dict(value=pairs_per_step * args.steps / (ms_e2e * 1e-3), unit="pairs/s",
-                                 ms_per_step=ms_e2e / args.steps,
-                                 h2d_bytes_per_step=int(T * S + 4 * 256),
+                                 ms_per_step=ms_e2e / args.steps, h2d_bytes_per_step=int(T * S + 4 * 256),
                                  d2h_bytes_per_step=int(sum(c.itemsize for c in cols_pin) * n_rows + S * 8 * 4)),
                         gpu_launches=int(lt.item()),
-                        roofline=dict(bound="hbm", kernel="K1 mapping pass (k1_down + k1_finish + k1_up over one batch of sites)",
-                                      achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                                      peak_source="MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)",
-                                      algorithmic_bytes_per_site=abytes_site, sites_per_step=sites_mapped // args.steps,
-                                      avg_pass_ms=map_ms / n_pass, passes=int(n_pass),
-                                      traffic=traffic_site * sites_mapped / n_pass, traffic_unit="bytes per pass",
-                                      traffic_source="ncu dram bytes of k1_down_mma + k1_up_mma, profiles/r1j_*.txt, scaled by sites"),
-                        kernel_ms_per_step={k: v[0] / args.steps for k, v in prof.items()})
+                        roofline=dict(up, peak_source=peaks["hbm_source"],
+                                      why="dominant kernel: %.0f %% of the step's device time" %
+                                          (100.0 * kernel_ms["map_up"] / max(1e-9, sum(kernel_ms.values())))),
+                        rooflines=[down, up, paired, tiles],
+                        kernel_ms_per_step=kernel_ms, kernel_ms_sum=sum(kernel_ms.values()),
+                        host_gap_frac=(ms / args.steps - sum(kernel_ms.values())) / (ms / args.steps),
+                        table_check=check)
             if world == 1 and not args.no_cpu_baseline:
                 cb = cpu_sample_all_cores(cfg, w, aln_codes=codes)
+                one = cpu_sample(cfg, w, aln_codes=codes, seed=12345)
                 line["cpu_baseline"] = dict(value=cb["value"], unit="pairs/s", cores=cb["cores"], kind="port", sample=cb["sample"],
-                                            host_cores=os.cpu_count(), sample_pairs_per_s=cb["sample_pairs_per_s"])
+                                            host_cores=os.cpu_count(), sample_pairs_per_s=cb["sample_pairs_per_s"],
+                                            one_thread_value=one["value"],
+                                            one_thread_sample_pairs_per_s=one["sample_pairs_per_s"])
             print(json.dumps(line), flush=True)
         ctx.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------
+# other workloads (N = 1): BASELINE.json configs[1] (proteins, pairwise + null) and configs[4] (clustering)
+# ------------------------------------------------------------------------------------------
+PROTEINS = dict(sites=129, taxa=100, alpha=0.985435, classes=4, mean_brlen=0.05, tree_seed=7, aln_seed=1, null_seed=2,
+                rep_cpu=100, rep_ram=1000, null_bins=10, statistic="correlation")
+CLUSTERING = dict(sites=20000, taxa=200, alpha=1.0, classes=4, mean_brlen=0.05, tree_seed=2, aln_seed=1, null_seed=7,
+                  null_reps=4, max_group=10)
+
+
+def _timed_gpu(torch, stream, fn, steps):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(steps):
+        fn()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1)
+
+
+def run_proteins(args):
+    """configs[1]-shaped: Myoglobin-sized protein alignment (100 taxa, 129 sites) under JTT92 + Gamma(4),
+    all-pairs correlation with the default 100 x 1000 simulated null (CoETools.cpp:853-854).  The protein
+    mapping kernels (A = 20) are FP64-bound: roofline against the measured DMMA peak."""
+    import torch
+    from comap_b200 import api
+    cfg = dict(PROTEINS)
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    S, T, R, RC, K = cfg["sites"], cfg["taxa"], cfg["rep_ram"], cfg["rep_cpu"], cfg["null_bins"]
+    B, C, A = 2 * T - 3, cfg["classes"], 20
+    parent, brlen = syn.random_tree(T, cfg["tree_seed"], cfg["mean_brlen"])
+    Q, pi = syn.jtt92()
+    rates, probs = syn.gamma_rates(cfg["alpha"], C)
+    with torch.cuda.stream(stream):
+        ctx = api.Context(device=0, stream=stream.cuda_stream)
+        ctx.set_tree(parent, brlen); ctx.set_model(Q, pi, rates, probs)
+        codes, _ = ctx.simulate(cfg["aln_seed"], 0, S)
+        mask = syn.identity_code_mask(A)
+
+        def step():
+            ctx.set_alignment(codes, mask)
+            ctx.map(want_vectors=False)
+            ctx.null_intra(cfg["statistic"], cfg["null_seed"], RC, R, K=K, nmax=-1.0)
+            return ctx.pairs(cfg["statistic"], use_null=True)[1]
+
+        for _ in range(max(3, args.warmup)):
+            n_rows = step()
+        sampler = ClockSampler(0); sampler.start()
+        l0 = ctx.launch_count()
+        ms = _timed_gpu(torch, stream, step, args.steps)
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop()
+        ctx.profile_reset(); ctx.profile_enable(True)
+        for _ in range(args.steps):
+            step()
+        prof = {k: ctx.profile_get(k) for k in ("map_down", "map_up", "simulate", "null_pairs", "sort", "pairs")}
+        ctx.profile_enable(False)
+        peaks = load_peaks()
+        sites_mapped = args.steps * (S + 2 * RC * R)
+        k1_ms = prof["map_down"][0] + prof["map_up"][0]
+        flops_site = 6.0 * B * C * A * A                     # SURVEY.md s8(d): down 2, up 2, contraction 2 x B C A^2
+        ach = sites_mapped * flops_site / (k1_ms * 1e-3) / 1e12
+        pairs_per_step = S * (S - 1) // 2 + RC * R
+        kernel_ms = {k: v[0] / args.steps for k, v in prof.items()}
+        line = dict(metric=METRIC, value=pairs_per_step * args.steps / (ms * 1e-3), unit="pairs/s", n_gpus=1, steps=args.steps,
+                    warmup=max(3, args.warmup), ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong",
+                    vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload="configs[1]-shaped: synthetic %d-site x %d-taxon protein alignment, JTT92+Gamma4, all-pairs "
+                                         "correlation + %dx%d null" % (S, T, RC, R), sites=S, taxa=T, branches=B, rate_classes=C,
+                                rep_cpu=RC, rep_ram=R, null_bins=K, pairs_per_step=pairs_per_step,
+                                l2="null batch working set (GBs of partials) exceeds the 126 MB L2; no explicit flush"),
+                    clocks=clocks, gpu_launches=launches,
+                    e2e=dict(value=pairs_per_step * args.steps / (ms * 1e-3), unit="pairs/s", ms_per_step=ms / args.steps,
+                             h2d_bytes_per_step=int(T * S), d2h_bytes_per_step=int(n_rows * 44),
+                             note="this workload's step already runs through the host-buffer C ABI"),
+                    roofline=dict(kernel="K1 protein mapping (down + up, A = 20)", bound="fp64", achieved=ach,
+                                  peak=peaks["fp64_dmma_tflops"], unit="TFLOP/s", frac=ach / peaks["fp64_dmma_tflops"],
+                                  algorithmic_flops_per_site=flops_site, peak_source=peaks["fp64_source"], traffic=None),
+                    kernel_ms_per_step=kernel_ms, kernel_ms_sum=sum(kernel_ms.values()))
+        print(json.dumps(line), flush=True)
+        ctx.close()
+
+
+def run_clustering(args):
+    """configs[4]: synthetic 20,000-site x 200-taxon protein alignment (JTT92 + Gamma4), clustering analysis:
+    map -> correlation distance matrix -> complete-linkage dendrogram -> groups <= 10, plus a short clustering
+    null.  pairs per step = (1 + nrep) S (S - 1) / 2."""
+    import torch
+    from comap_b200 import api
+    cfg = dict(CLUSTERING)
+    if args.sites:
+        cfg["sites"] = args.sites
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    S, T, C, A = cfg["sites"], cfg["taxa"], cfg["classes"], 20
+    B = 2 * T - 3
+    nrep = cfg["null_reps"]
+    parent, brlen = syn.random_tree(T, cfg["tree_seed"], cfg["mean_brlen"])
+    Q, pi = syn.jtt92()
+    rates, probs = syn.gamma_rates(cfg["alpha"], C)
+    with torch.cuda.stream(stream):
+        ctx = api.Context(device=0, stream=stream.cuda_stream)
+        ctx.set_tree(parent, brlen); ctx.set_model(Q, pi, rates, probs)
+        codes, _ = ctx.simulate(cfg["aln_seed"], 0, S)
+        mask = syn.identity_code_mask(A)
+        out = {}
+
+        def step():
+            ctx.set_alignment(codes, mask)
+            ctx.map(want_vectors=False)
+            ctx.distance_matrix("correlation", want=False)
+            out["dendro"] = ctx.cluster("complete")
+            out["groups"] = ctx.groups("correlation", cfg["max_group"])
+            out["null"] = ctx.cluster_null("correlation", "complete", cfg["null_seed"], 0, nrep, cfg["max_group"])
+
+        for _ in range(max(1, min(2, args.warmup))):
+            step()
+        sampler = ClockSampler(0); sampler.start()
+        l0 = ctx.launch_count()
+        ms = _timed_gpu(torch, stream, step, args.steps)
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop()
+        ctx.profile_reset(); ctx.profile_enable(True)
+        step()
+        prof = {k: ctx.profile_get(k) for k in ("map_down", "map_up", "simulate", "distance", "cluster")}
+        ctx.profile_enable(False)
+        peaks = load_peaks()
+        pairs_per_step = (1 + nrep) * S * (S - 1) // 2
+        n_dendro = 1 + nrep
+        cl_ms = prof["cluster"][0] / n_dendro
+        ach = 8.0 * S * S / (cl_ms * 1e-3) / 1e9        # SURVEY.md s8(d) K4b: O(S^2) bytes = one pass over the matrix
+        line = dict(metric=METRIC, value=pairs_per_step * args.steps / (ms * 1e-3), unit="pairs/s", n_gpus=1, steps=args.steps,
+                    warmup=max(1, min(2, args.warmup)), ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong",
+                    vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload="configs[4]: synthetic %d-site x %d-taxon protein alignment, JTT92+Gamma4, clustering "
+                                         "(cor distance, complete linkage, groups <= %d) + %d null replicates"
+                                         % (S, T, cfg["max_group"], nrep), sites=S, taxa=T, branches=B, rate_classes=C,
+                                null_reps=nrep, pairs_per_step=pairs_per_step,
+                                l2="a 3.2 GB distance matrix per dendrogram: far beyond L2; no explicit flush"),
+                    clocks=clocks, gpu_launches=launches,
+                    e2e=dict(value=pairs_per_step * args.steps / (ms * 1e-3), unit="pairs/s", ms_per_step=ms / args.steps,
+                             h2d_bytes_per_step=int(T * S), d2h_bytes_per_step=int(n_dendro * (S - 1) * 16),
+                             note="this workload's step already runs through the host-buffer C ABI"),
+                    roofline=dict(kernel="k4 agglomeration (one dendrogram)", bound="hbm", achieved=ach, peak=peaks["hbm_gbs"],
+                                  unit="GB/s", frac=ach / peaks["hbm_gbs"], algorithmic_bytes_per_dendrogram=8.0 * S * S,
+                                  ms_per_dendrogram=cl_ms, peak_source=peaks["hbm_source"], traffic=None),
+                    kernel_ms_per_step={k: v[0] for k, v in prof.items()},
+                    groups=len(out["groups"]["members"]), null_rows=len(out["null"]["rep"]))
+        print(json.dumps(line), flush=True)
+        ctx.close()
 
 
 def main():
@@ -379,6 +632,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="nucleotides", choices=["nucleotides", "proteins", "clustering"],
+                    help="nucleotides = BASELINE.json configs[3] (the metric's configuration, default); proteins = "
+                         "configs[1]-shaped; clustering = configs[4] (both N = 1, ours only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     for k in ("sites", "taxa", "rep_cpu", "rep_ram"):
         ap.add_argument("--" + k.replace("_", "-"), type=int, default=None)
@@ -389,6 +645,10 @@ def main():
             cfg[k] = getattr(args, k)
     if args.impl == "reference":
         run_reference(args, cfg)
+    elif args.workload == "proteins":
+        run_proteins(args)
+    elif args.workload == "clustering":
+        run_clustering(args)
     else:
         run_ours(args, cfg)
 

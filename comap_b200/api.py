@@ -24,6 +24,8 @@ SYMBOLS = [
     "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
     "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates", "cmb_set_async", "cmb_set_mi_threshold",
+    "cmb_comm_unique_id", "cmb_comm_init", "cmb_comm_init_all", "cmb_comm_set", "cmb_comm_destroy", "cmb_comm_rank",
+    "cmb_comm_group_start", "cmb_comm_group_end", "cmb_null_intra_sharded",
 ]
 
 
@@ -66,6 +68,23 @@ def _i64(a):
 
 def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def comm_unique_id():
+    """128-byte NCCL id (rank 0 creates it, the launcher hands it to every rank)."""
+    buf = (C.c_char * 128)()
+    lib = load()
+    if lib.cmb_comm_unique_id(buf) != 0:
+        raise RuntimeError("comap_b200: " + lib.cmb_last_error().decode())
+    return bytes(buf)
+
+
+def comm_init_all(contexts):
+    """One process, several contexts on distinct devices: joins them in one communicator."""
+    lib = load()
+    arr = (C.c_void_p * len(contexts))(*[c.h for c in contexts])
+    if lib.cmb_comm_init_all(arr, len(contexts)) != 0:
+        raise RuntimeError("comap_b200: " + lib.cmb_last_error().decode())
 
 
 class Context:
@@ -159,6 +178,26 @@ class Context:
     def set_mi_threshold(self, threshold):
         """Threshold of statistic 'mi' (MI(threshold=0.99) upstream)."""
         self._chk(self.lib.cmb_set_mi_threshold(self.h, C.c_double(threshold)))
+
+    # ------------------------------------------------------------------ multi-GPU
+    def comm_init(self, n_ranks, rank, unique_id):
+        """Joins the NCCL communicator named by the 128-byte id of comm_unique_id() (one process per GPU)."""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._chk(self.lib.cmb_comm_init(self.h, int(n_ranks), int(rank), buf))
+
+    def comm_destroy(self):
+        self._chk(self.lib.cmb_comm_destroy(self.h))
+
+    def comm_rank(self):
+        r = C.c_int32(); n = C.c_int32()
+        self._chk(self.lib.cmb_comm_rank(self.h, C.byref(r), C.byref(n)))
+        return r.value, n.value
+
+    def null_intra_sharded(self, stat, seed, rep_cpu, rep_ram, K=10, nmax=-1.0, weighted_classes=False):
+        """This rank's share of the null replicates, ncclAllGather of the samples on the context's stream,
+        binning + sort of the union (cmb_null_intra_sharded)."""
+        self._chk(self.lib.cmb_null_intra_sharded(self.h, STAT[stat], C.c_uint64(seed), rep_cpu, rep_ram,
+                                                  int(weighted_classes), K, C.c_double(nmax)))
 
     def set_async(self, on=True):
         """null_intra(K=0) returns without waiting for the device (order consumers with sync())."""

@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcomap_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 CU = ["capi.cu", "capi_stats.cu", "capi_inter.cu", "k1_map.cu", "k1_mma.cu", "k2_pairs.cu", "k3_simulate.cu", "k4_cluster.cu"]
-CPP = ["tables.cpp", "schedule.cpp"]
+CPP = ["tables.cpp", "schedule.cpp", "comm.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]
 
@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("nvcc failed")
     if force or procs or _stale(OUT, objs):
-        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart"]
+        cmd = [NVCC] + ARCH + ["-shared", "-o", OUT] + objs + ["-lcudart", "-ldl"]
         subprocess.check_call(cmd)
     return OUT
 

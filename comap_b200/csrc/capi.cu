@@ -245,6 +245,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
   Context& c = ctx->c;
   cudaSetDevice(c.device);
   cudaStreamSynchronize(c.stream);
+  cmb_comm_destroy(ctx);
   if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); }
   if (c.copy_event) cudaEventDestroy(c.copy_event);
   for (auto& t : c.prof.pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
@@ -254,7 +255,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
                     &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm,
-                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count};
+                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv};
   for (DevBuf* b : bufs) b->release();
   c.down_stream.release();
   c.up_stream.release();

@@ -79,6 +79,10 @@ void null_load(Context& c, const double* stat_dev, const double* nmin_dev, int64
   ns.ready = true;
 }
 
+// The two simulated alignments of a batch of outer replicates (AnalysisTools.cpp:591-611) live side by side in
+// ONE set of mapping buffers -- columns [0, n) hold batch 1, [half, half + n) batch 2 -- so one down / up launch
+// pair maps both (twice the CTAs per launch: a 125-replicate shard of an 8-GPU run fills 6.6 waves of the grid
+// instead of 2 x 3.3), and the paired statistic reads the two halves of the same output matrix.
 void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram, int rep_begin, int rep_end,
                int weighted, int K, double nmax, double* raw, const uint8_t* sim1, const uint8_t* sim2) {
   check_stat(stat_id);
@@ -93,13 +97,16 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
   ns.stat.reserve(sizeof(double) * (size_t)std::max<int64_t>(total, 1));
   ns.nmin.reserve(sizeof(double) * (size_t)std::max<int64_t>(total, 1));
   ns.n_samples = total;
-  // batch as many outer replicates as fit comfortably in free HBM
-  size_t freeb = 0, totalb = 0;
-  CMB_CUDA(cudaMemGetInfo(&freeb, &totalb));
-  size_t held = c.s_D.cap + c.s_out[0].cap + c.s_out[1].cap + c.s_tips[0].cap + c.s_tips[1].cap;
-  size_t budget = (size_t)((freeb + held) * 0.6);
-  int64_t max_sites = std::max<int64_t>(R, (int64_t)(budget / null_bytes_per_site(c)));
-  max_sites = std::min<int64_t>(max_sites, (int64_t)1 << 20);
+  // batch as many outer replicates as fit comfortably in free HBM (the answer is cached: cudaMemGetInfo
+  // costs a host round trip per call)
+  if (c.null_budget_sites <= 0) {
+    size_t freeb = 0, totalb = 0;
+    CMB_CUDA(cudaMemGetInfo(&freeb, &totalb));
+    size_t held = c.s_D.cap + c.s_out[0].cap + c.s_tips[0].cap;
+    size_t budget = (size_t)((freeb + held) * 0.6);
+    c.null_budget_sites = std::max<int64_t>(1, (int64_t)(budget / null_bytes_per_site(c)));
+  }
+  int64_t max_sites = std::max<int64_t>(R, std::min<int64_t>(c.null_budget_sites, (int64_t)1 << 20));
   int64_t rpb = std::max<int64_t>(1, max_sites / R);
   MapModel m = c.map_model();
   // the corrected correlation scores simulated pairs with the OBSERVED alignment's mean vector
@@ -108,31 +115,38 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
   const double* mv = corrected ? c.mean_vector() : nullptr;
   int64_t off = 0;
   for (int64_t r0 = rep_begin; r0 < rep_end; r0 += rpb) {
-    const int64_t nb = std::min<int64_t>(rpb, rep_end - r0), n = nb * R, n_pad = pad_sites(n);
-    MapBuffers b[2];
+    const int64_t nb = std::min<int64_t>(rpb, rep_end - r0), n = nb * R;
+    const int64_t half = (n + 255) / 256 * 256, n_pad = pad_sites(half + n);
+    MapBuffers bb = sim_buffers(c, 0, half + n, n_pad);
+    uint8_t* tips = c.s_tips[0].as<uint8_t>();
+    // the columns between and after the two batches are mapped too (their results are never read): give them
+    // a valid state once per buffer geometry
+    if (c.s_tips_ptr != tips || c.s_tips_pad != n_pad || c.s_tips_n != n) {
+      CMB_CUDA(cudaMemsetAsync(tips, 0, (size_t)T * n_pad, c.stream));
+      c.s_tips_ptr = tips; c.s_tips_pad = n_pad; c.s_tips_n = n;
+    }
     for (int k = 0; k < 2; k++) {
-      b[k] = sim_buffers(c, k, n, n_pad);
       if (sim1) {
         const uint8_t* src = k == 0 ? sim1 : sim2;
         for (int64_t r = 0; r < nb; r++)
-          CMB_CUDA(cudaMemcpy2DAsync(c.s_tips[k].as<uint8_t>() + r * R, n_pad, src + (size_t)(r0 + r) * T * R, R, R, T,
+          CMB_CUDA(cudaMemcpy2DAsync(tips + k * half + r * R, n_pad, src + (size_t)(r0 + r) * T * R, R, R, T,
                                      cudaMemcpyHostToDevice, c.stream));
       } else {
         c.prof_begin("simulate");
         launch_simulate(m, c.sim_stream, seed, (2 * r0 + k) * R, R, 2 * R, n, n_pad, weighted, c.tree.n_nodes - 1,
-                        c.s_tips[k].as<uint8_t>(), nullptr, c.stream);
+                        tips + k * half, nullptr, c.stream);
         c.prof_end(1);
       }
-      c.run_map(b[k], true, sim1 == nullptr);
     }
+    c.run_map(bb, true, sim1 == nullptr);
     c.prof_begin("null_pairs");
-    launch_paired(corrected ? 0 : stat_id, c.mi_threshold, B, n, n_pad, n_pad, b[0].out, b[1].out, mv, mv, ns.stat.as<double>() + off, ns.nmin.as<double>() + off,
-                  c.stream);
+    launch_paired(corrected ? 0 : stat_id, c.mi_threshold, B, n, n_pad, n_pad, bb.out, bb.out + half, mv, mv,
+                  ns.stat.as<double>() + off, ns.nmin.as<double>() + off, c.stream);
     c.prof_end(1);
     if (raw) {
       c.scratch.reserve(sizeof(double) * 4 * (size_t)n);
-      launch_raw_rows(n, ns.stat.as<double>() + off, ns.nmin.as<double>() + off, b[0].rate_class, b[1].rate_class,
-                      b[0].post_rate, b[1].post_rate, c.scratch.as<double>(), c.stream);
+      launch_raw_rows(n, ns.stat.as<double>() + off, ns.nmin.as<double>() + off, bb.rate_class, bb.rate_class + half,
+                      bb.post_rate, bb.post_rate + half, c.scratch.as<double>(), c.stream);
       c.prof.total_launches += 1;
       CMB_CUDA(cudaMemcpyAsync(raw + off * 4, c.scratch.p, sizeof(double) * 4 * (size_t)n, cudaMemcpyDeviceToHost,
                                c.stream));
@@ -144,6 +158,17 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
   else if (!c.async_null) CMB_CUDA(cudaStreamSynchronize(c.stream));
 }
 
+// This rank's share of the outer replicates: contiguous ranges, the first rep_cpu % n_ranks ranks get one more.
+void replicate_range(int rep_cpu, int n_ranks, int rank, int& begin, int& end) {
+  const int q = rep_cpu / n_ranks, r = rep_cpu % n_ranks;
+  begin = rank * q + std::min(rank, r);
+  end = begin + q + (rank < r ? 1 : 0);
+}
+
+__global__ void k_fill_nan(double* p, int64_t n) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = nan("");
+}
 
 struct GroupTable {
   std::vector<int32_t> members;
@@ -305,6 +330,51 @@ int cmb_null_intra(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t rep_cpu
                    int32_t rep_end, int32_t weighted_classes, int32_t K, double nmax, double* raw) {
   CMB_TRY
   null_core(ctx->c, stat_id, seed, rep_cpu, rep_ram, rep_begin, rep_end, weighted_classes, K, nmax, raw, nullptr, nullptr);
+  CMB_CATCH
+}
+
+int cmb_null_intra_sharded(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t rep_cpu, int32_t rep_ram,
+                           int32_t weighted_classes, int32_t K, double nmax) {
+  CMB_TRY
+  Context& c = ctx->c;
+  if (K < 1) fail("cmb_null_intra_sharded: K must be positive");
+  if (c.comm_size == 1) { // no communicator: the whole null on this GPU
+    null_core(c, stat_id, seed, rep_cpu, rep_ram, 0, rep_cpu, weighted_classes, K, nmax, nullptr, nullptr, nullptr);
+    return 0;
+  }
+  int r0, r1;
+  replicate_range(rep_cpu, c.comm_size, c.comm_rank, r0, r1);
+  const bool was_async = c.async_null;
+  c.async_null = true; // no host wait between the last null kernel and the exchange
+  struct Restore { Context& c; bool v; ~Restore() { c.async_null = v; } } restore{c, was_async};
+  null_core(c, stat_id, seed, rep_cpu, rep_ram, r0, r1, weighted_classes, 0, 0., nullptr, nullptr, nullptr);
+  // every rank contributes one block [stat (cap) | nmin (cap)], cap = the largest shard; unused entries carry
+  // Nmin = NaN, which Domain::getIndex rejects, so they fall out of the binning like out-of-range samples
+  const int64_t R = rep_ram, n = (int64_t)(r1 - r0) * R;
+  const int64_t cap = ((int64_t)(rep_cpu + c.comm_size - 1) / c.comm_size) * R;
+  c.gather_send.reserve(sizeof(double) * 2 * (size_t)cap);
+  c.gather_recv.reserve(sizeof(double) * 2 * (size_t)cap * c.comm_size);
+  double* send = c.gather_send.as<double>();
+  if (n < cap) {
+    k_fill_nan<<<(unsigned)((2 * cap + 255) / 256), 256, 0, c.stream>>>(send, 2 * cap);
+    CMB_CUDA(cudaGetLastError());
+    c.prof.total_launches += 1;
+  }
+  if (n > 0) {
+    CMB_CUDA(cudaMemcpyAsync(send, c.null.stat.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+    CMB_CUDA(cudaMemcpyAsync(send + cap, c.null.nmin.p, sizeof(double) * n, cudaMemcpyDeviceToDevice, c.stream));
+  }
+  comm_all_gather(c, send, c.gather_recv.as<double>(), 2 * (size_t)cap);
+  // blocks [stat | nmin] per rank -> two contiguous arrays of comm_size * cap samples
+  const int64_t tot = cap * c.comm_size;
+  c.null.stat.reserve(sizeof(double) * (size_t)tot);
+  c.null.nmin.reserve(sizeof(double) * (size_t)tot);
+  CMB_CUDA(cudaMemcpy2DAsync(c.null.stat.p, sizeof(double) * cap, c.gather_recv.p, sizeof(double) * 2 * cap,
+                             sizeof(double) * cap, c.comm_size, cudaMemcpyDeviceToDevice, c.stream));
+  CMB_CUDA(cudaMemcpy2DAsync(c.null.nmin.p, sizeof(double) * cap, c.gather_recv.as<double>() + cap, sizeof(double) * 2 * cap,
+                             sizeof(double) * cap, c.comm_size, cudaMemcpyDeviceToDevice, c.stream));
+  c.null.n_samples = tot;
+  null_load(c, c.null.stat.as<double>(), c.null.nmin.as<double>(), tot, K, nmax);
   CMB_CATCH
 }
 

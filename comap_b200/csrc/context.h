@@ -56,6 +56,9 @@ struct Context {
   // scratch for simulated batches
   DevBuf s_tips[2], s_D, s_Lc, s_invL, s_loglik, s_pr[2], s_rc[2], s_out[2], s_sum[2], s_sumsq[2], s_cls;
   DevBuf d_identity_mask;
+  int64_t null_budget_sites = 0;  // simulated sites the null may hold at once (from free memory, cached)
+  const void* s_tips_ptr = nullptr;
+  int64_t s_tips_pad = -1, s_tips_n = -1; // geometry the simulated tip buffer's padding columns were cleared for
 
   NullState null;
 
@@ -85,6 +88,11 @@ struct Context {
   DevBuf mi_count;
   bool have_mi_count = false;
   const double* mi_counts();    // device pointer [S_pad] of the mapped alignment; built on first use
+  // multi-GPU: NCCL communicator of this context's rank (comm.cpp); comm_size = 1 without one
+  void* comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  bool own_comm = false;
+  DevBuf gather_send, gather_recv; // padded [stat | nmin] blocks of the null all-gather
   Profile prof;
   bool async_null = false; // cmb_set_async: cmb_null_intra with K = 0 returns without waiting for the device
 
@@ -100,5 +108,6 @@ struct Context {
 };
 
 int64_t pad_sites(int64_t n);
+void comm_all_gather(Context& c, const double* send, double* recv, size_t count);
 
 } // namespace cmb

@@ -7,16 +7,24 @@ The path shards twice and exchanges once:
     1000 x 1000 -- after which every rank bins and sorts the union itself;
   * pair rows: row i goes to rank r when i mod 2N is r or 2N-1-r, which pairs a long row
     with a short one (row i holds S-1-i pairs).
-Nothing here touches the device: the arrays are torch tensors (CUDA under NCCL, CPU under
-gloo in the tests), the compute entry points are the C ABI's shard arguments.
+The product path does all of this inside the library (cmb_comm_* / cmb_null_intra_sharded: NCCL
+on the context's stream).  This module states the same sharding rules for the launcher and the
+CPU (gloo) tests of the host logic, plus an exchange over torch.distributed for callers that
+bring their own plumbing; nothing here touches the device.
 """
 import numpy as np
 
 
 def replicate_bounds(rep_cpu, world):
-    """[r0, r1) of every rank: contiguous, sizes differ by at most one."""
-    b = np.linspace(0, rep_cpu, world + 1).astype(np.int64)
-    return [(int(b[r]), int(b[r + 1])) for r in range(world)]
+    """[r0, r1) of every rank: contiguous, the first rep_cpu % world ranks hold one more
+    (the rule cmb_null_intra_sharded applies inside the library)."""
+    q, r = divmod(int(rep_cpu), int(world))
+    out, b = [], 0
+    for k in range(world):
+        e = b + q + (1 if k < r else 0)
+        out.append((b, e))
+        b = e
+    return out
 
 
 def owned_rows(n_sites, rank, world):

@@ -16,9 +16,11 @@
  *   - All pointers are caller-allocated HOST buffers (pinned memory makes copies faster;
  *     cmb_host_alloc provides it) unless the name ends in _dev.  Any output pointer
  *     documented "nullable" may be NULL.
- *   - A cmb_ctx is bound to one GPU and one CUDA stream; it is not thread-safe.  One
- *     process per GPU; multi-GPU runs shard work with the shard_* arguments and exchange
- *     null samples through the *_dev entry points (NCCL is the caller's plumbing).
+ *   - A cmb_ctx is bound to one GPU and one CUDA stream; it is not thread-safe.  Multi-GPU
+ *     runs use one context per GPU (one process each, or one thread each in one process),
+ *     shard work with the shard_* arguments and exchange the null samples with NCCL through
+ *     cmb_comm_* / cmb_null_intra_sharded (or, with the caller's own plumbing, the *_dev
+ *     entry points).
  *   - tree  : n_nodes nodes, ids in Newick post-order (children before parent), root =
  *             n_nodes-1 with parent -1.  Branch b = edge above node b, B = n_nodes-1.
  *             Leaf k (k-th childless node in id order) is row k of every alignment.
@@ -128,6 +130,32 @@ int cmb_simulate(cmb_ctx* ctx, uint64_t seed, int64_t first_site, int64_t n,
 int cmb_null_intra(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t rep_cpu, int32_t rep_ram,
                    int32_t rep_begin, int32_t rep_end, int32_t weighted_classes, int32_t K,
                    double nmax, double* raw);
+
+/* Multi-GPU: one cmb_ctx per GPU, joined by an NCCL communicator that the library drives on
+ * the context's stream (libnccl.so.2 is bound at run time; single-GPU use needs no NCCL).
+ *   cmb_comm_unique_id / cmb_comm_init : one process per GPU -- rank 0 obtains the 128-byte id, the launcher
+ *                        broadcasts it (MPI, torch.distributed, a file ...), every rank joins
+ *   cmb_comm_init_all  : one process, n contexts on n distinct devices (the comap_b200 command line with
+ *                        comap_b200.gpus=n); collective calls must then be issued from one thread per context
+ *                        or between cmb_comm_group_start / _end
+ *   cmb_comm_set       : adopt an ncclComm_t the caller already owns
+ * The reference has no counterpart: it is single-threaded (CMakeLists.txt:5-19). */
+int cmb_comm_unique_id(void* id128);
+int cmb_comm_init(cmb_ctx* ctx, int32_t n_ranks, int32_t rank, const void* id128);
+int cmb_comm_init_all(cmb_ctx** ctxs, int32_t n);
+int cmb_comm_set(cmb_ctx* ctx, void* nccl_comm, int32_t n_ranks, int32_t rank);
+int cmb_comm_destroy(cmb_ctx* ctx);
+int cmb_comm_rank(cmb_ctx* ctx, int32_t* rank, int32_t* n_ranks);
+int cmb_comm_group_start(void);
+int cmb_comm_group_end(void);
+
+/* cmb_null_intra over the communicator (AnalysisTools.cpp:564-658 sharded by outer replicate): this rank
+ * simulates, maps and scores its contiguous share of the rep_cpu replicates (global site indices: the samples
+ * do not depend on the rank count), the (Stat, Nmin) samples are all-gathered with ncclAllGather on the
+ * context's stream, and every rank bins and sorts the union, so cmb_pairs on any shard of rows sees the same
+ * null distribution as a single-GPU run.  Without a communicator it is cmb_null_intra over all replicates. */
+int cmb_null_intra_sharded(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t rep_cpu, int32_t rep_ram,
+                           int32_t weighted_classes, int32_t K, double nmax);
 
 /* Parity hook: same as cmb_null_intra with the RNG bypassed.  sim1/sim2 are
  * [rep_cpu][T][rep_ram] state codes under the identity code table. */

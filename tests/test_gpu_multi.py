@@ -1,5 +1,8 @@
 """Two-GPU parity (skipped on a one-GPU box): null replicates and pair rows sharded over two
-ranks with one NCCL all-gather must reproduce the single-GPU tables bit for bit."""
+ranks with one NCCL all-gather -- issued by the library on the context's stream
+(cmb_comm_init + cmb_null_intra_sharded) -- must reproduce the single-GPU tables bit for bit;
+once with one process per GPU (torchrun), once with two contexts in one process
+(cmb_comm_init_all, the comap_b200 command line's comap_b200.gpus=2)."""
 import os
 import subprocess
 import sys
@@ -33,14 +36,13 @@ def setup():
     c.set_alignment(codes, syn.identity_code_mask(4)); c.map(want_vectors=False)
     return c
 ctx = setup()
-r0, r1 = par.replicate_bounds(RC, world)[rank]
-maxr = max(e - b for b, e in par.replicate_bounds(RC, world))
-ctx.null_intra("correlation", 17, RC, R, K=0, rep_begin=r0, rep_end=r1)
-sp, mp, n = ctx.null_samples_dev()
-st, nm = par.all_gather_null(torch.as_tensor(DevArr(sp, max(n, 1)), device="cuda"),
-                             torch.as_tensor(DevArr(mp, max(n, 1)), device="cuda"), n, maxr * R)
-torch.cuda.synchronize()
-ctx.null_load_dev(st.data_ptr(), nm.data_ptr(), st.numel(), K, -1.0)
+uid = torch.zeros(128, dtype=torch.uint8)
+if rank == 0:
+    uid = torch.frombuffer(bytearray(api.comm_unique_id()), dtype=torch.uint8).clone()
+uid = uid.cuda(); dist.broadcast(uid, 0)
+ctx.comm_init(world, rank, uid.cpu().numpy().tobytes())
+assert ctx.comm_rank() == (rank, world)
+ctx.null_intra_sharded("correlation", 17, RC, R, K=K)
 p, k = ctx.pairs("correlation", use_null=True, shard_index=rank, shard_count=world)
 assert k == par.owned_pairs(S, rank, world)
 cols = ["i", "j", "stat", "pvalue", "nsim"]
@@ -79,3 +81,49 @@ def test_two_gpu_sharding_is_bit_identical(tmp_path):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", script], capture_output=True, text=True,
                        timeout=600)
     assert p.returncode == 0 and "MULTI_GPU_OK 2" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
+
+
+def test_two_contexts_one_process_bit_identical():
+    """comap_b200.gpus=2 flow: two contexts in one process, one thread each, communicator from
+    cmb_comm_init_all; the union of the two row shards equals the single-GPU table."""
+    import threading
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    sys.path.insert(0, ROOT)
+    from comap_b200 import api, synthetic as syn
+    parent, brlen = syn.random_tree(24, 4, 0.06)
+    Q, pi = syn.hky85(2.5, [0.3, 0.2, 0.2, 0.3]); rates, probs = syn.gamma_rates(0.5, 4)
+    S, RC, R, K = 301, 5, 128, 6
+
+    def setup(dev):
+        c = api.Context(device=dev)
+        c.set_tree(parent, brlen); c.set_model(Q, pi, rates, probs)
+        codes, _ = c.simulate(3, 0, S)
+        c.set_alignment(codes, syn.identity_code_mask(4)); c.map(want_vectors=False)
+        return c
+
+    ctxs = [setup(0), setup(1)]
+    api.comm_init_all(ctxs)
+    out, err = [None, None], []
+
+    def work(r):
+        try:
+            ctxs[r].null_intra_sharded("correlation", 17, RC, R, K=K)
+            out[r] = ctxs[r].pairs("correlation", use_null=True, shard_index=r, shard_count=2)[0]
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(2)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert not err, err
+    cols = ["i", "j", "stat", "pvalue", "nsim"]
+    rows = np.concatenate([np.stack([o[c].astype(np.float64) for c in cols], 1) for o in out])
+    rows = rows[np.lexsort((rows[:, 1], rows[:, 0]))]
+    one = setup(0)
+    one.null_intra("correlation", 17, RC, R, K=K)
+    q, kk = one.pairs("correlation", use_null=True)
+    ref = np.stack([q[c].astype(np.float64) for c in cols], 1)
+    assert kk == len(rows) and np.array_equal(rows, ref, equal_nan=True)
+    for c in ctxs + [one]:
+        c.close()

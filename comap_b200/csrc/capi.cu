@@ -40,6 +40,7 @@ void DevStream::upload(const OpStream& s, cudaStream_t st) {
   n_records = s.n_records;
   stack_depth = s.stack_depth;
   stage_bytes = s.stage_bytes;
+  for (int k = 0; k < 3; k++) blk_off_max[k] = s.blk_off_max[k];
   if (!s.aux.empty()) {
     aux.reserve(sizeof(int32_t) * s.aux.size());
     CMB_CUDA(cudaMemcpyAsync(aux.p, s.aux.data(), sizeof(int32_t) * s.aux.size(), cudaMemcpyHostToDevice, st));

@@ -85,6 +85,7 @@ struct OpStream {
   uint32_t chunk_cap = 0; // largest chunk in bytes
   int stack_depth = 0;    // message stack depth the walk needs (tensor-core down stream)
   uint32_t stage_bytes = 0; // tensor-core up stream: largest packed stage (record | tip rows | partial chunks)
+  uint32_t blk_off_max[3] = {0, 0, 0}; // ... largest chunk offset among the nodes with 0 / 1 / 2 stored children
 };
 constexpr uint32_t kDownTipA = 1, kDownTipB = 2, kDownPush = 4, kDownRoot = 8;
 constexpr uint32_t kUpTipA = 1, kUpTipB = 2, kUpPop = 4, kUpPush = 8, kUpTakeA = 16, kUpTakeB = 32,

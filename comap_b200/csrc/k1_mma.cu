@@ -50,7 +50,10 @@ struct UpMmaParams {
   int n_stages;         // ring depth
 };
 constexpr int kMaxStages = 8;
-constexpr int kSG = kChunkSites; // sites per CTA
+// Sites per CTA: a whole 128-site chunk of the partial layout, or a quarter of one when the batch is too small to
+// give every SM a CTA (the observed alignment: 5000 sites = 40 chunks on 148 SMs; a narrow CTA walks the tree
+// about five times faster because its two warps have the SM to themselves)
+constexpr int kWideSG = kChunkSites, kNarrowSG = 32;
 
 // what a child is, warp-uniform
 enum : int { kInner = 0, kTip = 1, kCherry = 2 };
@@ -92,7 +95,7 @@ __device__ __forceinline__ double pick(const double* row, uint32_t code) {
 //                 and its two leaf branches are contracted here: n_1 += (M o P2 pick) . W1 pick, n_2 likewise
 // acc: a, b, a1, a2, b1, b2 (the last four only for cherry children).  MASK: the codes are state masks
 // (ambiguity somewhere in the warp's sites).  tab: first table of the record, blk: chunks, lane offsets applied.
-template <int NG, int C, int KA, int KB, bool MASK>
+template <int NG, int C, int SG, int KA, int KB, bool MASK>
 __device__ __forceinline__ void node_body(const double* tab, const double* blk_a, const double* blk_b, int lane,
                                           const uint32_t (&sa)[NG], const uint32_t (&sa2)[NG], const uint32_t (&sb)[NG],
                                           const uint32_t (&sb2)[NG], double (&G)[C][NG], double (*push)[NG],
@@ -116,7 +119,7 @@ __device__ __forceinline__ void node_body(const double* tab, const double* blk_a
         double D[NG];
         if constexpr (K == kInner) {
 #pragma unroll
-          for (int g = 0; g < NG; g++) D[g] = blk[(size_t)c * (kSG * 4) + g * 32];
+          for (int g = 0; g < NG; g++) D[g] = blk[(size_t)c * (SG * 4) + g * 32];
         } else {
 #pragma unroll
           for (int g = 0; g < NG; g++) {
@@ -187,12 +190,12 @@ struct UpLane {
 // stage, then the sums over the four state lanes of a site and the stores.  STATES: the codes are resolved
 // state indices (device-simulated alignments); otherwise they go through the code -> state-mask table and
 // the warp takes the mask path when any of its sites is ambiguous.
-template <int NG, int C, int KA, int KB, bool STATES>
+template <int NG, int C, int SG, int KA, int KB, bool STATES>
 __device__ __forceinline__ void node_step(const unsigned char* stage, int4 h0, const UpLane& ln, const uint32_t* cmask,
                                           double (&G)[C][NG], double (*stk)[C][NG], uint64_t* empty_bar) {
-  constexpr uint32_t kBlock = C * kSG * 32;
+  constexpr uint32_t kBlock = C * SG * 32;
   const double* tab = reinterpret_cast<const double*>(stage + sizeof(UpMmaHdr));
-  const unsigned char* ts = stage + h0.y + ln.lsite;   // tip code of (row, group g): ts[row * kSG + 8 g]
+  const unsigned char* ts = stage + h0.y + ln.lsite;   // tip code of (row, group g): ts[row * SG + 8 g]
   const double* blk_a = reinterpret_cast<const double*>(stage + h0.z) + ln.lsite * 4 + ln.q;
   const double* blk_b = blk_a + (KA == kInner ? kBlock / 8 : 0);
   double (*push)[NG] = stk[(h0.x >> 8) & 0xff];
@@ -203,13 +206,13 @@ __device__ __forceinline__ void node_step(const unsigned char* stage, int4 h0, c
 #pragma unroll
   for (int g = 0; g < NG; g++) {
     sa[g] = KA != kInner ? ts[8 * g] : 0;
-    sa2[g] = KA == kCherry ? ts[2 * kSG + 8 * g] : 0;
-    sb[g] = KB != kInner ? ts[kSG + 8 * g] : 0;
-    sb2[g] = KB == kCherry ? ts[3 * kSG + 8 * g] : 0;
+    sa2[g] = KA == kCherry ? ts[2 * SG + 8 * g] : 0;
+    sb[g] = KB != kInner ? ts[SG + 8 * g] : 0;
+    sb2[g] = KB == kCherry ? ts[3 * SG + 8 * g] : 0;
   }
   double acc[6][NG];
   if constexpr (STATES || (KA == kInner && KB == kInner)) {
-    node_body<NG, C, KA, KB, false>(tab, blk_a, blk_b, ln.lane, sa, sa2, sb, sb2, G, push, pop, acc);
+    node_body<NG, C, SG, KA, KB, false>(tab, blk_a, blk_b, ln.lane, sa, sa2, sb, sb2, G, push, pop, acc);
   } else {
     bool single = true;
 #pragma unroll
@@ -226,9 +229,9 @@ __device__ __forceinline__ void node_step(const unsigned char* stage, int4 h0, c
         sa[g] = __ffs(sa[g]) - 1; sa2[g] = __ffs(sa2[g]) - 1;
         sb[g] = __ffs(sb[g]) - 1; sb2[g] = __ffs(sb2[g]) - 1;
       }
-      node_body<NG, C, KA, KB, false>(tab, blk_a, blk_b, ln.lane, sa, sa2, sb, sb2, G, push, pop, acc);
+      node_body<NG, C, SG, KA, KB, false>(tab, blk_a, blk_b, ln.lane, sa, sa2, sb, sb2, G, push, pop, acc);
     } else {
-      node_body<NG, C, KA, KB, true>(tab, blk_a, blk_b, ln.lane, sa, sa2, sb, sb2, G, push, pop, acc);
+      node_body<NG, C, SG, KA, KB, true>(tab, blk_a, blk_b, ln.lane, sa, sa2, sb, sb2, G, push, pop, acc);
     }
   }
   // output rows: lanes with q & 2 own the second branch of each pair (b, a2, b2)
@@ -266,10 +269,10 @@ __device__ __forceinline__ void node_step(const unsigned char* stage, int4 h0, c
 }
 
 // One node's copies into ring stage s: record, tip rows, partial chunks of the stored children (one lane).
-template <int C>
+template <int C, int SG>
 __device__ __forceinline__ void up_issue_node(const MapModel& m, const MapBuffers& b, const UpMmaParams& up, int4 r0, int4 r1,
                                               uint32_t roff, uint32_t rnb, unsigned char* st, uint64_t* full, int64_t site0) {
-  constexpr uint32_t kBlock = C * kSG * 32;
+  constexpr uint32_t kBlock = C * SG * 32;
   const int64_t n_pad = b.n_pad;
   const int64_t chunk = site0 / kChunkSites;
   const uint32_t flags = (uint32_t)r0.x;
@@ -279,28 +282,37 @@ __device__ __forceinline__ void up_issue_node(const MapModel& m, const MapBuffer
   const bool ina = !(tipa || cha), inb = !(tipb || chb);
   unsigned char* tp = st + tips_off;
   const uint32_t nrows = (tipa || cha) + (tipb || chb) + cha + chb;
-  mbar_expect_tx(full, rnb + nrows * (uint32_t)kSG + ((uint32_t)ina + (uint32_t)inb) * kBlock);
+  mbar_expect_tx(full, rnb + nrows * (uint32_t)SG + ((uint32_t)ina + (uint32_t)inb) * kBlock);
   tma_bulk_g2s(st, up.stream + roff, rnb, full);
-  if (tipa || cha) tma_bulk_g2s(tp, b.tips + (size_t)ref_a * n_pad + site0, kSG, full);
-  if (tipb || chb) tma_bulk_g2s(tp + kSG, b.tips + (size_t)ref_b * n_pad + site0, kSG, full);
-  if (cha) tma_bulk_g2s(tp + 2 * kSG, b.tips + (size_t)ref_a2 * n_pad + site0, kSG, full);
-  if (chb) tma_bulk_g2s(tp + 3 * kSG, b.tips + (size_t)ref_b2 * n_pad + site0, kSG, full);
-  // stored children, in order a then b, from blk_off
-  if (ina) tma_bulk_g2s(st + blk_off, b.D + d_chunk(chunk, ref_a, m.n_slots, C), kBlock, full);
-  if (inb) tma_bulk_g2s(st + blk_off + (ina ? kBlock : 0), b.D + d_chunk(chunk, ref_b, m.n_slots, C), kBlock, full);
+  if (tipa || cha) tma_bulk_g2s(tp, b.tips + (size_t)ref_a * n_pad + site0, SG, full);
+  if (tipb || chb) tma_bulk_g2s(tp + SG, b.tips + (size_t)ref_b * n_pad + site0, SG, full);
+  if (cha) tma_bulk_g2s(tp + 2 * SG, b.tips + (size_t)ref_a2 * n_pad + site0, SG, full);
+  if (chb) tma_bulk_g2s(tp + 3 * SG, b.tips + (size_t)ref_b2 * n_pad + site0, SG, full);
+  // stored children, in order a then b, from blk_off: the whole chunk, or this CTA's sites of every class
+  auto child = [&](unsigned char* dst, int slot) {
+    const double* src = b.D + d_chunk(chunk, slot, m.n_slots, C);
+    if constexpr (SG == kChunkSites) tma_bulk_g2s(dst, src, kBlock, full);
+    else {
+      const int sub = (int)(site0 % kChunkSites);
+#pragma unroll
+      for (int c = 0; c < C; c++) tma_bulk_g2s(dst + c * (SG * 32), src + (size_t)c * (kChunkSites * 4) + sub * 4, SG * 32, full);
+    }
+  };
+  if (ina) child(st + blk_off, ref_a);
+  if (inb) child(st + blk_off + (ina ? kBlock : 0), ref_b);
 }
 
 // Measured and left out (B200, config 4): folding the producer into the consumer warps (8 warps per CTA, 128
 // registers: 36.3 ms per step against 34.4), L2 prefetch of the chunks 2..8 nodes ahead of their stage copy
 // (33.3-35.6 against 33.1), producer wake-up by suspend-time hint or a 40 ns back-off instead of 200 ns (no change).
-template <int NG, int C, int MINB, bool STATES>
-__global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(MapModel m, MapBuffers b, UpMmaParams up) {
+template <int NG, int C, int SG, int MINB, bool STATES>
+__global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_up_mma(MapModel m, MapBuffers b, UpMmaParams up) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int W = kSG / (8 * NG);                // consumer warps
+  constexpr int W = SG / (8 * NG);                 // consumer warps
   const uint32_t stage_bytes = up.stage_bytes;     // packed per node: record | tip rows (a, b, a2, b2) | chunks
   const int NSTG = up.n_stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t site0 = (int64_t)blockIdx.x * kSG;
+  const int64_t site0 = (int64_t)blockIdx.x * SG;
   uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* stg_empty = stg_full + kMaxStages;
   unsigned char* stg_ring = smem + 128;
@@ -333,7 +345,7 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
         q1.z = __shfl_sync(0xffffffffu, r1.z, j); q1.w = 0;
         const uint32_t roff = __shfl_sync(0xffffffffu, off, j), rnb = __shfl_sync(0xffffffffu, nb, j);
         if (!first) mbar_wait_sleep(&stg_empty[s], ph, 200);
-        if (lane == 0) up_issue_node<C>(m, b, up, q0, q1, roff, rnb, stg_ring + (size_t)s * stage_bytes, &stg_full[s], site0);
+        if (lane == 0) up_issue_node<C, SG>(m, b, up, q0, q1, roff, rnb, stg_ring + (size_t)s * stage_bytes, &stg_full[s], site0);
         __syncwarp();
         if (++s == (uint32_t)NSTG) { s = 0; ph ^= 1; first = false; }
       }
@@ -369,7 +381,7 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
     // smaller child first: an inner a implies an inner b, a cherry a implies a non-tip b
     switch (h0.x & 0xff) {
 #define CMB_NODE(KA, KB) \
-  case KA * 3 + KB: node_step<NG, C, KA, KB, STATES>(stage, h0, ln, cmask, G, stk, &stg_empty[cs]); break;
+  case KA * 3 + KB: node_step<NG, C, SG, KA, KB, STATES>(stage, h0, ln, cmask, G, stk, &stg_empty[cs]); break;
       CMB_NODE(kInner, kInner) CMB_NODE(kTip, kInner) CMB_NODE(kTip, kTip) CMB_NODE(kTip, kCherry)
       CMB_NODE(kCherry, kInner) CMB_NODE(kCherry, kCherry)
 #undef CMB_NODE
@@ -378,14 +390,18 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_up_mma(Map
   }
 }
 
-template <int NG, int C, int MINB, bool STATES>
+template <int NG, int C, int SG, int MINB, bool STATES>
 bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.C != C) return false;
   int dev = 0, max_smem = 0;
   CMB_CUDA(cudaGetDevice(&dev));
   CMB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   max_smem = max_smem / MINB - 1024 - 1024;      // 1 KB system reserve per CTA, 1 KB static (cmask)
-  const size_t stage = ((size_t)s.stage_bytes + 127) & ~size_t(127);
+  // largest packed stage at SG sites per CTA: nodes with k stored children need blk_off + k chunks
+  size_t stage = 0;
+  for (int k = 0; k < 3; k++)
+    if (s.blk_off_max[k] || k == 0) stage = std::max(stage, (size_t)s.blk_off_max[k] + (size_t)k * C * SG * 32);
+  stage = (stage + 127) & ~size_t(127);
   const size_t fixed = 128;
   if ((size_t)max_smem < fixed + 2 * stage) return false;
   static const int stage_cap = getenv("CMB_UP_STAGES") ? atoi(getenv("CMB_UP_STAGES")) : kMaxStages;
@@ -403,13 +419,26 @@ bool try_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   static const size_t ring_kb = getenv("CMB_UP_RING_KB") ? (size_t)atoi(getenv("CMB_UP_RING_KB")) : 80;
   if (MINB > 1) up.n_stages = (int)std::max<size_t>(2, std::min<size_t>(up.n_stages, (ring_kb * 1024) / stage));
   const size_t smem = fixed + (size_t)up.n_stages * stage;
-  constexpr int threads = 32 * (kSG / (8 * NG) + 1);
-  CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB, STATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  constexpr int threads = 32 * (SG / (8 * NG) + 1);
+  CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, SG, MINB, STATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (getenv("CMB_UP_CARVEOUT"))
-    CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, MINB, STATES>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CMB_UP_CARVEOUT"))));
-  k1_up_mma<NG, C, MINB, STATES><<<(unsigned)(b.n_pad / kSG), threads, smem, st>>>(m, b, up);
+    CMB_CUDA(cudaFuncSetAttribute(k1_up_mma<NG, C, SG, MINB, STATES>, cudaFuncAttributePreferredSharedMemoryCarveout, atoi(getenv("CMB_UP_CARVEOUT"))));
+  k1_up_mma<NG, C, SG, MINB, STATES><<<(unsigned)(b.n_pad / SG), threads, smem, st>>>(m, b, up);
   CMB_CUDA(cudaGetLastError());
   return true;
+}
+
+// batches that cannot give every SM a 128-site CTA run 32-site CTAs
+bool narrow_batch(const MapBuffers& b) {
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    CMB_CUDA(cudaGetDevice(&dev));
+    CMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  static const int force = getenv("CMB_K1_NARROW") ? atoi(getenv("CMB_K1_NARROW")) : -1; // experiment switch
+  if (force >= 0) return force != 0;
+  return b.n_pad / kWideSG < sms;
 }
 
 template <int C>
@@ -417,8 +446,11 @@ bool up_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   if (m.C != C) return false;
   // B200, config 4 (517 k sites): 2 groups/warp x 2 CTAs/SM (16 consumer warps) 10.8 ms;
   // 4 groups/warp x 2 CTAs/SM (8 warps, 168 regs) 11.2 ms; 2 groups/warp x 1 CTA/SM 12.7 ms
-  if (m.states_only) return try_up_mma<2, C, 2, true>(m, b, s, st) || try_up_mma<2, C, 1, true>(m, b, s, st);
-  return try_up_mma<2, C, 2, false>(m, b, s, st) || try_up_mma<2, C, 1, false>(m, b, s, st);
+  if (narrow_batch(b)) {
+    if (m.states_only ? try_up_mma<2, C, kNarrowSG, 2, true>(m, b, s, st) : try_up_mma<2, C, kNarrowSG, 2, false>(m, b, s, st)) return true;
+  }
+  if (m.states_only) return try_up_mma<2, C, kWideSG, 2, true>(m, b, s, st) || try_up_mma<2, C, kWideSG, 1, true>(m, b, s, st);
+  return try_up_mma<2, C, kWideSG, 2, false>(m, b, s, st) || try_up_mma<2, C, kWideSG, 1, false>(m, b, s, st);
 }
 
 // ------------------------------------------------------------------------------ down
@@ -438,16 +470,16 @@ struct DownMmaParams {
 };
 constexpr int kDownStages = 8;
 
-template <int NG, int C, int MINB>
-__global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_down_mma(MapModel m, MapBuffers b, DownMmaParams dp) {
+template <int NG, int C, int SG, int MINB>
+__global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(MapModel m, MapBuffers b, DownMmaParams dp) {
   extern __shared__ __align__(128) unsigned char smem[];
-  constexpr int W = kSG / (8 * NG);
-  constexpr uint32_t kEntry = C * kSG * 32;        // one stack level of the CTA
-  const uint32_t stage_bytes = dp.rec_cap + 2 * kSG;
+  constexpr int W = SG / (8 * NG);
+  constexpr uint32_t kEntry = C * SG * 32;         // one stack level of the CTA
+  const uint32_t stage_bytes = dp.rec_cap + 2 * kWideSG;
   const int NSTG = dp.n_stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_pad = b.n_pad;
-  const int64_t site0 = (int64_t)blockIdx.x * kSG;
+  const int64_t site0 = (int64_t)blockIdx.x * SG;
   uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* stg_empty = stg_full + kDownStages;
   unsigned char* stg_ring = smem + 128;
@@ -478,10 +510,10 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_down_mma(M
         if (lane == 0) {
           const bool tipa = flags & kDownTipA, tipb = flags & kDownTipB;
           unsigned char* st = stg_ring + (size_t)s * stage_bytes;
-          mbar_expect_tx(&stg_full[s], rnb + ((uint32_t)tipa + (uint32_t)tipb) * (uint32_t)kSG);
+          mbar_expect_tx(&stg_full[s], rnb + ((uint32_t)tipa + (uint32_t)tipb) * (uint32_t)SG);
           tma_bulk_g2s(st, dp.stream + roff, rnb, &stg_full[s]);
-          if (tipa) tma_bulk_g2s(st + dp.rec_cap, b.tips + (size_t)row_a * n_pad + site0, kSG, &stg_full[s]);
-          if (tipb) tma_bulk_g2s(st + dp.rec_cap + kSG, b.tips + (size_t)row_b * n_pad + site0, kSG, &stg_full[s]);
+          if (tipa) tma_bulk_g2s(st + dp.rec_cap, b.tips + (size_t)row_a * n_pad + site0, SG, &stg_full[s]);
+          if (tipb) tma_bulk_g2s(st + dp.rec_cap + SG, b.tips + (size_t)row_b * n_pad + site0, SG, &stg_full[s]);
         }
         __syncwarp();
         if (++s == (uint32_t)NSTG) { s = 0; ph ^= 1; first = false; }
@@ -500,8 +532,8 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_down_mma(M
   for (int c = 0; c < C; c++)
 #pragma unroll
     for (int g = 0; g < NG; g++) cur[c][g] = 0.;
-  double* my_stack = stack + (size_t)wsite * 4 + lane; // + level * kEntry / 8 + c * kSG * 4 + g * 32
-  double* my_D = b.D + d_chunk(site0 / kChunkSites, 0, m.n_slots, C) + (size_t)wsite * 4 + lane;
+  double* my_stack = stack + (size_t)wsite * 4 + lane; // + level * kEntry / 8 + c * SG * 4 + g * 32
+  double* my_D = b.D + d_chunk(site0 / kChunkSites, 0, m.n_slots, C) + (size_t)(site0 % kChunkSites + wsite) * 4 + lane;
   const size_t slot_stride = (size_t)C * kChunkSites * 4;
 
   uint32_t cs = 0, cph = 0;
@@ -567,10 +599,10 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_down_mma(M
     double Ma[C][NG], Mb[C][NG];
     if (tipa) {                       // cherry
       tip_message(ts, Ra, Ma);
-      tip_message(ts + kSG, Rb, Mb);
+      tip_message(ts + SG, Rb, Mb);
     } else if (tipb) {                // a's partial is the running one
       edge_message(F, Ma);
-      tip_message(ts + kSG, Rb, Mb);
+      tip_message(ts + SG, Rb, Mb);
     } else {                          // a's message waits on the stack, b's partial is the running one
       edge_message(F, Mb);
       --sp;
@@ -579,7 +611,7 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_down_mma(M
 #pragma unroll
         for (int c = 0; c < C; c++)
 #pragma unroll
-          for (int g = 0; g < NG; g++) Ma[c][g] = e[c * (kSG * 4) + g * 32];
+          for (int g = 0; g < NG; g++) Ma[c][g] = e[c * (SG * 4) + g * 32];
       } else {
 #pragma unroll
         for (int c = 0; c < C; c++)
@@ -606,7 +638,7 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_down_mma(M
 #pragma unroll
         for (int c = 0; c < C; c++)
 #pragma unroll
-          for (int g = 0; g < NG; g++) e[c * (kSG * 4) + g * 32] = M[c][g];
+          for (int g = 0; g < NG; g++) e[c * (SG * 4) + g * 32] = M[c][g];
       } else {
 #pragma unroll
         for (int c = 0; c < C; c++)
@@ -632,14 +664,14 @@ __global__ void __launch_bounds__(32 * (kSG / (8 * NG) + 1), MINB) k1_down_mma(M
     }
 }
 
-template <int NG, int C, int MINB>
+template <int NG, int C, int SG, int MINB>
 bool try_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.C != C) return false;
   int dev = 0, max_smem = 0;
   CMB_CUDA(cudaGetDevice(&dev));
   CMB_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
   max_smem = max_smem / MINB - 1024 - 1024;      // 1 KB system reserve per CTA, 1 KB static (cmask)
-  const size_t stage = (size_t)s.cap + 2 * (size_t)kSG, entry = (size_t)C * kSG * 32;
+  const size_t stage = (size_t)s.cap + 2 * (size_t)kWideSG, entry = (size_t)C * SG * 32;
   DownMmaParams dp;
   dp.stream = s.bytes.as<unsigned char>();
   dp.rec_off = s.off.as<uint32_t>();
@@ -654,9 +686,9 @@ bool try_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cu
   dp.smem_levels = (int)std::min<size_t>((size_t)s.stack_depth, ((size_t)max_smem - 128 - dp.n_stages * stage) / entry);
   if (MINB > 1 && dp.smem_levels < s.stack_depth) return false; // prefer one CTA per SM with the whole stack
   const size_t smem = 128 + dp.n_stages * stage + (size_t)dp.smem_levels * entry;
-  constexpr int threads = 32 * (kSG / (8 * NG) + 1);
-  CMB_CUDA(cudaFuncSetAttribute(k1_down_mma<NG, C, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k1_down_mma<NG, C, MINB><<<(unsigned)(b.n_pad / kSG), threads, smem, st>>>(m, b, dp);
+  constexpr int threads = 32 * (SG / (8 * NG) + 1);
+  CMB_CUDA(cudaFuncSetAttribute(k1_down_mma<NG, C, SG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1_down_mma<NG, C, SG, MINB><<<(unsigned)(b.n_pad / SG), threads, smem, st>>>(m, b, dp);
   CMB_CUDA(cudaGetLastError());
   return true;
 }
@@ -664,20 +696,15 @@ bool try_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cu
 template <int C>
 bool down_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.C != C) return false;
-  if constexpr (C == 4) {
-    static const int shape = getenv("CMB_DOWN_SHAPE") ? atoi(getenv("CMB_DOWN_SHAPE")) : 0; // experiment switch
-    if (shape == 21) return try_down_mma<2, C, 1>(m, b, s, st);
-    if (shape == 11) return try_down_mma<1, C, 1>(m, b, s, st);
-    if (shape == 12) return try_down_mma<1, C, 2>(m, b, s, st);
-  }
-  return try_down_mma<2, C, 2>(m, b, s, st) || try_down_mma<2, C, 1>(m, b, s, st);
+  if (narrow_batch(b) && try_down_mma<2, C, kNarrowSG, 2>(m, b, s, st)) return true;
+  return try_down_mma<2, C, kWideSG, 2>(m, b, s, st) || try_down_mma<2, C, kWideSG, 1>(m, b, s, st);
 }
 
 } // namespace
 
 void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.A != 4) fail("internal: the tensor-core up pass is built for A = 4");
-  if (b.n_pad % kSG) fail("internal: n_pad must be a multiple of %d", kSG);
+  if (b.n_pad % kWideSG) fail("internal: n_pad must be a multiple of %d", kWideSG);
   const bool done = up_mma_for<1>(m, b, s, st) || up_mma_for<2>(m, b, s, st) || up_mma_for<3>(m, b, s, st) ||
                     up_mma_for<4>(m, b, s, st) || up_mma_for<5>(m, b, s, st) || up_mma_for<6>(m, b, s, st) ||
                     up_mma_for<7>(m, b, s, st) || up_mma_for<8>(m, b, s, st);
@@ -689,7 +716,7 @@ void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& 
 namespace cmb {
 void launch_map_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.A != 4) fail("internal: the tensor-core down pass is built for A = 4");
-  if (b.n_pad % kSG) fail("internal: n_pad must be a multiple of %d", kSG);
+  if (b.n_pad % kWideSG) fail("internal: n_pad must be a multiple of %d", kWideSG);
   const bool done = down_mma_for<1>(m, b, s, st) || down_mma_for<2>(m, b, s, st) || down_mma_for<3>(m, b, s, st) ||
                     down_mma_for<4>(m, b, s, st) || down_mma_for<5>(m, b, s, st) || down_mma_for<6>(m, b, s, st) ||
                     down_mma_for<7>(m, b, s, st) || down_mma_for<8>(m, b, s, st);

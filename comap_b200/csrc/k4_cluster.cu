@@ -773,6 +773,11 @@ void launch_batch_kernel(ClusterBatch& B, int grid, cudaStream_t st) {
 int launch_cluster_batch(int np, int64_t S, int linkage, double* const* mats, DevBuf* works, int32_t* const* left_dev,
                          int32_t* const* right_dev, double* const* height_dev, cudaStream_t st) {
   if (np < 1 || np > kMaxBatch) fail("launch_cluster_batch: 1..%d problems per launch", kMaxBatch);
+  if (cluster_rnn_selected(S, linkage)) { // rounds of reciprocal pairs: bandwidth, not a chain of barriers; no batching needed
+    int n = 0;
+    for (int q = 0; q < np; q++) n += launch_cluster_rnn(S, linkage, mats[q], works[q], left_dev[q], right_dev[q], height_dev[q], st);
+    return n;
+  }
   int dev = 0, sms = 0;
   CMB_CUDA(cudaGetDevice(&dev));
   CMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));

@@ -9,6 +9,7 @@ struct DevStream {           // an OpStream uploaded to the device
   uint32_t n_chunks = 0, cap = 0, n_records = 0;
   int stack_depth = 0;
   uint32_t stage_bytes = 0;
+  uint32_t blk_off_max[3] = {0, 0, 0};
   void upload(const OpStream& s, cudaStream_t st);
   void release();
 };
@@ -134,6 +135,10 @@ int launch_cluster_batch(int np, int64_t S, int linkage, double* const* mats, De
                          int32_t* const* right_dev, double* const* height_dev, cudaStream_t st);
 int launch_cluster(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* left_dev, int32_t* right_dev,
                    double* height_dev, cudaStream_t st);
+// large matrices, complete / average linkage: rounds of reciprocal nearest neighbours (k4_rnn.cu)
+bool cluster_rnn_selected(int64_t S, int linkage);
+int launch_cluster_rnn(int64_t S, int linkage, double* mat, DevBuf& work, int32_t* left_dev, int32_t* right_dev,
+                       double* height_dev, cudaStream_t st);
 void launch_group_compensation(int64_t n_groups, const int32_t* members, const int64_t* offsets, int B,
                                int64_t S_pad, const double* out, double* stat, cudaStream_t st);
 

@@ -416,6 +416,7 @@ void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
     const uint32_t blk_off = tips_off + ((ta || tb || ca || cb) ? 4u * kChunkSites : 0u);
     const uint32_t n_blk = (uint32_t)(ka == 0) + (uint32_t)(kb == 0);
     s.stage_bytes = std::max(s.stage_bytes, blk_off + n_blk * (uint32_t)C * kChunkSites * 32u);
+    s.blk_off_max[n_blk] = std::max(s.blk_off_max[n_blk], blk_off);
     h.tips_off = (int32_t)tips_off;
     h.blk_off = (int32_t)blk_off;
     std::memcpy(rec.data(), &h, sizeof h);

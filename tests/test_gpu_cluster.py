@@ -107,6 +107,45 @@ def test_cluster_dsmem_layout_equals_oracle(ctx, linkage, monkeypatch):
     assert np.array_equal(left, ol) and np.array_equal(right, orr) and np.array_equal(height, oh)
 
 
+@pytest.mark.parametrize("linkage", ["complete", "average"])
+@pytest.mark.parametrize("keep_constant", [False, True])
+def test_cluster_reciprocal_rounds_vs_oracle(ctx, linkage, keep_constant, monkeypatch):
+    """The large-matrix algorithm (rounds of reciprocal first minima, k4_rnn.cu), forced on a matrix the
+    oracle can still cluster: same merges in the same creation order -- exact ties included: with
+    keep_constant the constant columns stay in, whose identical vectors tie massively (cliques at distance
+    0 and NaN rows for zero-variance vectors are excluded by the remove_const step otherwise) -- and heights
+    to 1e-12 (an entry between two clusters merged in different rounds can nest its Lance-Williams updates
+    in another order than the sequential replay: last-bit differences, see k4_rnn.cu)."""
+    monkeypatch.setenv("CMB_K4_ALGO", "rnn")
+    c = H.random_dna_case(24, 900, 31, mean_brlen=0.1)
+    codes = c["codes"]
+    var = np.array([len(set(codes[:, s])) > 1 for s in range(codes.shape[1])])
+    if keep_constant:
+        # duplicate some variable columns: cliques of identical sites (distance exactly 0 inside, identical rows)
+        dup = np.flatnonzero(var)[:40]
+        codes = np.concatenate([codes[:, var], codes[:, dup], codes[:, dup[:15]]], axis=1)
+    else:
+        codes = codes[:, var]
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(np.ascontiguousarray(codes), c["code_mask"])
+    r = ctx.map()
+    mat = ctx.distance_matrix("correlation")
+    assert not np.isnan(mat).any()
+    left, right, height = ctx.cluster(linkage)
+    ol, orr, oh = O.hclust(linkage, mat)
+    assert np.array_equal(left, ol) and np.array_equal(right, orr)
+    assert np.allclose(height, oh, rtol=1e-12, atol=1e-15)
+    g = ctx.groups("correlation", 10)
+    og = O.groups("correlation", r["n"], r["norm"], ol, orr, oh, 10)
+    assert len(g["members"]) == len(og["members"]) > 0
+    for a, b in zip(g["members"], og["members"]):
+        assert np.array_equal(a, b)
+    monkeypatch.setenv("CMB_K4_ALGO", "exact")
+    ctx.distance_matrix("correlation")
+    l2, r2, h2 = ctx.cluster(linkage)
+    assert np.array_equal(l2, ol) and np.array_equal(r2, orr) and np.array_equal(h2, oh)   # the exact replay: bit for bit
+
+
 def test_cluster_vs_scipy_heights(ctx):
     from scipy.cluster.hierarchy import linkage as sl
     from scipy.spatial.distance import squareform

@@ -193,11 +193,17 @@ class Context:
         self._chk(self.lib.cmb_comm_rank(self.h, C.byref(r), C.byref(n)))
         return r.value, n.value
 
-    def null_intra_sharded(self, stat, seed, rep_cpu, rep_ram, K=10, nmax=-1.0, weighted_classes=False):
+    def null_intra_sharded(self, stat, seed, rep_cpu, rep_ram, K=10, nmax=-1.0, weighted_classes=False, want_raw=False):
         """This rank's share of the null replicates, ncclAllGather of the samples on the context's stream,
-        binning + sort of the union (cmb_null_intra_sharded)."""
+        binning + sort of the union (cmb_null_intra_sharded).  want_raw: the rows of this rank's replicates."""
+        raw = None
+        if want_raw:
+            rank, n = self.comm_rank()
+            q, m = divmod(rep_cpu, n)
+            raw = np.empty(((q + (1 if rank < m else 0)) * rep_ram, 4))
         self._chk(self.lib.cmb_null_intra_sharded(self.h, STAT[stat], C.c_uint64(seed), rep_cpu, rep_ram,
-                                                  int(weighted_classes), K, C.c_double(nmax)))
+                                                  int(weighted_classes), K, C.c_double(nmax), _d(raw)))
+        return raw
 
     def set_async(self, on=True):
         """null_intra(K=0) returns without waiting for the device (order consumers with sync())."""

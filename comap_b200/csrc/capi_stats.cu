@@ -334,12 +334,12 @@ int cmb_null_intra(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t rep_cpu
 }
 
 int cmb_null_intra_sharded(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t rep_cpu, int32_t rep_ram,
-                           int32_t weighted_classes, int32_t K, double nmax) {
+                           int32_t weighted_classes, int32_t K, double nmax, double* raw) {
   CMB_TRY
   Context& c = ctx->c;
   if (K < 1) fail("cmb_null_intra_sharded: K must be positive");
   if (c.comm_size == 1) { // no communicator: the whole null on this GPU
-    null_core(c, stat_id, seed, rep_cpu, rep_ram, 0, rep_cpu, weighted_classes, K, nmax, nullptr, nullptr, nullptr);
+    null_core(c, stat_id, seed, rep_cpu, rep_ram, 0, rep_cpu, weighted_classes, K, nmax, raw, nullptr, nullptr);
     return 0;
   }
   int r0, r1;
@@ -347,7 +347,7 @@ int cmb_null_intra_sharded(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t
   const bool was_async = c.async_null;
   c.async_null = true; // no host wait between the last null kernel and the exchange
   struct Restore { Context& c; bool v; ~Restore() { c.async_null = v; } } restore{c, was_async};
-  null_core(c, stat_id, seed, rep_cpu, rep_ram, r0, r1, weighted_classes, 0, 0., nullptr, nullptr, nullptr);
+  null_core(c, stat_id, seed, rep_cpu, rep_ram, r0, r1, weighted_classes, 0, 0., raw, nullptr, nullptr);
   // every rank contributes one block [stat (cap) | nmin (cap)], cap = the largest shard; unused entries carry
   // Nmin = NaN, which Domain::getIndex rejects, so they fall out of the binning like out-of-range samples
   const int64_t R = rep_ram, n = (int64_t)(r1 - r0) * R;

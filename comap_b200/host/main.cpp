@@ -279,6 +279,21 @@ std::string dendrogram_newick(const std::vector<int32_t>& left, const std::vecto
   return txt[2 * S - 2] + ";";
 }
 
+// comap_b200.gpus = N: N contexts on devices 0..N-1 joined by one NCCL communicator (cmb_comm_init_all), driven by
+// one host thread each.  Context 0 is the data set's own; the others hold the same tree / model / alignment and
+// map it themselves (a 5000-site mapping is cheaper than shipping its 40 MB).
+template <class F> void on_all(int n, F f) {
+  std::vector<std::thread> th;
+  std::vector<std::string> err(n);
+  for (int r = 0; r < n; r++)
+    th.emplace_back([&, r] {
+      try { f(r); } catch (const std::exception& e) { err[r] = e.what(); if (err[r].empty()) err[r] = "error"; }
+    });
+  for (auto& t : th) t.join();
+  for (auto& e : err)
+    if (!e.empty()) throw Error(e);
+}
+
 struct Mapped {           // a data set on the device and its per-site results
   cmb_ctx* ctx = nullptr;
   std::vector<double> norm, pr, ll;
@@ -448,6 +463,27 @@ int main(int argc, char** argv) {
     Mapped m1 = map_data_set(in, P, "");
     S = (int64_t)in.cols.size(); // saturated sites may have been removed
     cmb_ctx* ctx = m1.ctx;
+    const int n_gpus = (int)get_int(P, "comap_b200.gpus", 1);
+    if (n_gpus < 1) throw Error("comap_b200.gpus must be at least 1");
+    std::vector<cmb_ctx*> ctxs{ctx};
+    if (n_gpus > 1) {
+      display_result("GPUs", n_gpus);
+      ctxs.resize(n_gpus, nullptr);
+      on_all(n_gpus, [&](int r) {
+        if (r == 0) return;
+        chk(cmb_ctx_create(r, nullptr, &ctxs[r]));
+        chk(cmb_set_tree(ctxs[r], (int32_t)in.tree.parent.size(), in.tree.parent.data(), in.tree.brlen.data()));
+        chk(cmb_set_model(ctxs[r], in.model.A, in.model.Q.data(), in.model.pi.data(), (int32_t)in.rdist.rates.size(),
+                          in.rdist.rates.data(), in.rdist.probs.data(), in.count_method, in.weights.empty() ? nullptr : in.weights.data()));
+        chk(cmb_set_alignment(ctxs[r], S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
+        Procedure st = parse_procedure(get_string(P, "statistic", "Correlation"));
+        if (st.name == "MI") chk(cmb_set_mi_threshold(ctxs[r], get_double(st.args, "threshold", 0.99)));
+        chk(cmb_map(ctxs[r], nullptr, nullptr, nullptr, nullptr, nullptr));
+      });
+      if (get_path(P, "input.vectors.file", "none") != "none")
+        throw Error("comap_b200.gpus > 1 cannot be combined with input.vectors.file");
+      chk(cmb_comm_init_all(ctxs.data(), n_gpus));
+    }
     std::string analysis = get_string(P, "analysis", "pairwise");
     display_result("Analysis type", analysis);
     if (get_string(P, "asr.method", "none") != "none")
@@ -556,8 +592,15 @@ int main(int argc, char** argv) {
           display_message("WARNING!!! statistic.null.compute_pvalue=no without an output file: nothing to do.");
         std::vector<double> raw;
         if (null_path != "none") raw.resize((size_t)rep_cpu * rep_ram * 4);
-        chk(cmb_null_intra(ctx, stat_id, seed, rep_cpu, rep_ram, 0, rep_cpu, weighted_classes ? 1 : 0, K, -1.,
-                           raw.empty() ? nullptr : raw.data()));
+        if (n_gpus == 1)
+          chk(cmb_null_intra(ctx, stat_id, seed, rep_cpu, rep_ram, 0, rep_cpu, weighted_classes ? 1 : 0, K, -1.,
+                             raw.empty() ? nullptr : raw.data()));
+        else // outer replicates sharded over the GPUs; rank r's rows start at its first replicate
+          on_all(n_gpus, [&](int r) {
+            const int q = rep_cpu / n_gpus, m = rep_cpu % n_gpus, r0 = r * q + std::min(r, m);
+            chk(cmb_null_intra_sharded(ctxs[r], stat_id, seed, rep_cpu, rep_ram, weighted_classes ? 1 : 0, K, -1.,
+                                       raw.empty() ? nullptr : raw.data() + (size_t)r0 * rep_ram * 4));
+          });
         if (null_path != "none") {
           std::ofstream out(null_path);
           out << "Stat\tRCmin\tPRmin\tNmin\n"; // AnalysisTools.cpp:580,642
@@ -579,8 +622,48 @@ int main(int argc, char** argv) {
       std::vector<double> ST(cap), PR(cap), NM(cap), PV(pvalues ? cap : 0);
       std::vector<int32_t> NS(pvalues ? cap : 0);
       int64_t rows = 0;
-      chk(cmb_pairs(ctx, stat_id, &f, pvalues ? 1 : 0, 0, 1, cap, I.data(), J.data(), ST.data(), RC.data(), PR.data(),
-                    NM.data(), pvalues ? PV.data() : nullptr, pvalues ? NS.data() : nullptr, &rows));
+      if (n_gpus == 1)
+        chk(cmb_pairs(ctx, stat_id, &f, pvalues ? 1 : 0, 0, 1, cap, I.data(), J.data(), ST.data(), RC.data(), PR.data(),
+                      NM.data(), pvalues ? PV.data() : nullptr, pvalues ? NS.data() : nullptr, &rows));
+      else {
+        // rows i with i mod 2N in {r, 2N - 1 - r} are scored by GPU r; the shards are merged back into the
+        // reference's order (i ascending, then j)
+        struct Shard { std::vector<int32_t> I, J, RC, NS; std::vector<double> ST, PR, NM, PV; int64_t rows = 0; };
+        std::vector<Shard> sh(n_gpus);
+        on_all(n_gpus, [&](int r) {
+          int64_t c = 0;
+          for (int64_t i = 0; i < S; i++) {
+            const int64_t md = i % (2 * n_gpus);
+            if (md == r || md == 2 * n_gpus - 1 - r) c += S - 1 - i;
+          }
+          Shard& h = sh[r];
+          h.I.resize(c); h.J.resize(c); h.RC.resize(c); h.ST.resize(c); h.PR.resize(c); h.NM.resize(c);
+          if (pvalues) { h.PV.resize(c); h.NS.resize(c); }
+          chk(cmb_pairs(ctxs[r], stat_id, &f, pvalues ? 1 : 0, r, n_gpus, c, h.I.data(), h.J.data(), h.ST.data(), h.RC.data(),
+                        h.PR.data(), h.NM.data(), pvalues ? h.PV.data() : nullptr, pvalues ? h.NS.data() : nullptr, &h.rows));
+        });
+        std::vector<int64_t> cur(n_gpus, 0);
+        for (int64_t i = 0; i + 1 < S; i++) {
+          const int64_t md = i % (2 * n_gpus);
+          const int r = (int)(md < n_gpus ? md : 2 * n_gpus - 1 - md);
+          Shard& h = sh[r];
+          int64_t a = cur[r], b = a;
+          while (b < h.rows && h.I[b] == i) b++;
+          const int64_t n = b - a;
+          std::copy(h.I.begin() + a, h.I.begin() + b, I.begin() + rows);
+          std::copy(h.J.begin() + a, h.J.begin() + b, J.begin() + rows);
+          std::copy(h.ST.begin() + a, h.ST.begin() + b, ST.begin() + rows);
+          std::copy(h.RC.begin() + a, h.RC.begin() + b, RC.begin() + rows);
+          std::copy(h.PR.begin() + a, h.PR.begin() + b, PR.begin() + rows);
+          std::copy(h.NM.begin() + a, h.NM.begin() + b, NM.begin() + rows);
+          if (pvalues) {
+            std::copy(h.PV.begin() + a, h.PV.begin() + b, PV.begin() + rows);
+            std::copy(h.NS.begin() + a, h.NS.begin() + b, NS.begin() + rows);
+          }
+          cur[r] = b;
+          rows += n;
+        }
+      }
       std::ofstream out(stat_path);
       out << "Group\tStat\tRCmin\tPRmin\tNmin";
       if (null) out << "\tPValue\tNsim";
@@ -684,21 +767,32 @@ int main(int argc, char** argv) {
             out.open(sim_path);
             out << "Rep\tGroup\tSize\tDmax\tStat\tNmin\n"; // ClusterTools.cpp:219
           }
-          // replicates in batches so the host buffers stay small
-          const int batch = std::max(1, (int)std::min<int64_t>(nrep, (int64_t)(1 << 22) / std::max<int64_t>(1, S)));
+          // replicates in batches so the host buffers stay small; with several GPUs a batch is dealt to them in
+          // contiguous replicate ranges (replicas only: no exchange) and written in replicate order
+          const int batch = std::max(1, (int)std::min<int64_t>(nrep, (int64_t)n_gpus * (1 << 22) / std::max<int64_t>(1, S)));
+          struct NullRows {
+            std::vector<int32_t> rep, size, mem; std::vector<double> dmax, st, nm; std::vector<int64_t> off; int64_t nr = 0;
+          };
           for (int r0 = 0; r0 < nrep; r0 += batch) {
             const int r1 = std::min(nrep, r0 + batch);
-            const int64_t cap_rows = (int64_t)(r1 - r0) * (S - 1), cap_mem = cap_rows * max_size;
-            std::vector<int32_t> rep(cap_rows), size(cap_rows), mem((size_t)std::max<int64_t>(1, cap_mem));
-            std::vector<double> dmax(cap_rows), st(cap_rows), nm(cap_rows);
-            std::vector<int64_t> off(cap_rows + 1);
-            int64_t nr = 0;
-            chk(cmb_cluster_null(ctx, dist_id, link, seed, r0, r1, weighted_classes ? 1 : 0, max_size, cap_rows, cap_mem,
-                                 rep.data(), size.data(), dmax.data(), st.data(), nm.data(), mem.data(), off.data(), &nr));
+            std::vector<NullRows> part(n_gpus);
+            on_all(n_gpus, [&](int g) {
+              const int nb = r1 - r0, q = nb / n_gpus, m = nb % n_gpus;
+              const int a = r0 + g * q + std::min(g, m), b = a + q + (g < m ? 1 : 0);
+              if (a == b) return;
+              NullRows& x = part[g];
+              const int64_t cap_rows = (int64_t)(b - a) * (S - 1), cap_mem = cap_rows * max_size;
+              x.rep.resize(cap_rows); x.size.resize(cap_rows); x.mem.resize((size_t)std::max<int64_t>(1, cap_mem));
+              x.dmax.resize(cap_rows); x.st.resize(cap_rows); x.nm.resize(cap_rows); x.off.resize(cap_rows + 1);
+              chk(cmb_cluster_null(ctxs[g], dist_id, link, seed, a, b, weighted_classes ? 1 : 0, max_size, cap_rows, cap_mem,
+                                   x.rep.data(), x.size.data(), x.dmax.data(), x.st.data(), x.nm.data(), x.mem.data(),
+                                   x.off.data(), &x.nr));
+            });
             if (out.is_open())
-              for (int64_t k = 0; k < nr; k++) // Group holds matrix indices here (ClusterTools.cpp:284)
-                out << rep[k] << "\t" << group_string(&mem[off[k]], off[k + 1] - off[k], nullptr) << "\t" << size[k]
-                    << "\t" << dmax[k] << "\t" << st[k] << "\t" << nm[k] << "\n";
+              for (const NullRows& x : part)
+                for (int64_t k = 0; k < x.nr; k++) // Group holds matrix indices here (ClusterTools.cpp:284)
+                  out << x.rep[k] << "\t" << group_string(&x.mem[x.off[k]], x.off[k + 1] - x.off[k], nullptr) << "\t" << x.size[k]
+                      << "\t" << x.dmax[k] << "\t" << x.st[k] << "\t" << x.nm[k] << "\n";
           }
         }
       }
@@ -812,6 +906,7 @@ int main(int argc, char** argv) {
       }
     } else throw Error("Unknown analysis type: " + analysis);
 
+    for (size_t r = 1; r < ctxs.size(); r++) chk(cmb_ctx_destroy(ctxs[r]));
     chk(cmb_ctx_destroy(ctx));
     double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count();
     std::cout << "Total execution time: " << secs << "s" << std::endl;

@@ -153,9 +153,11 @@ int cmb_comm_group_end(void);
  * simulates, maps and scores its contiguous share of the rep_cpu replicates (global site indices: the samples
  * do not depend on the rank count), the (Stat, Nmin) samples are all-gathered with ncclAllGather on the
  * context's stream, and every rank bins and sorts the union, so cmb_pairs on any shard of rows sees the same
- * null distribution as a single-GPU run.  Without a communicator it is cmb_null_intra over all replicates. */
+ * null distribution as a single-GPU run.  Without a communicator it is cmb_null_intra over all replicates.
+ * raw (nullable): the rows of THIS rank's replicates, [(r1 - r0) * rep_ram][4] with r0 = rank * q + min(rank, m),
+ * r1 = r0 + q + (rank < m), q = rep_cpu / n_ranks, m = rep_cpu % n_ranks. */
 int cmb_null_intra_sharded(cmb_ctx* ctx, int32_t stat_id, uint64_t seed, int32_t rep_cpu, int32_t rep_ram,
-                           int32_t weighted_classes, int32_t K, double nmax);
+                           int32_t weighted_classes, int32_t K, double nmax, double* raw);
 
 /* Parity hook: same as cmb_null_intra with the RNG bypassed.  sim1/sim2 are
  * [rep_cpu][T][rep_ram] state codes under the identity code table. */

@@ -327,3 +327,25 @@ def test_error_exit_code_and_message(myo):
     assert p.returncode == 255 and "Compensation distance must be used with a mapping procedure" in p.stdout
     p = subprocess.run([BIN] + COMMON + ["analysis=bogus"], cwd=tmp, capture_output=True, text=True)
     assert p.returncode == 255 and "Unknown analysis type" in p.stdout
+
+
+def test_two_gpus_write_the_same_tables(myo):
+    """comap_b200.gpus=2 (null replicates and pair rows sharded over two contexts of one process, NCCL
+    all-gather inside the library; clustering-null replicates dealt to the GPUs): every output file is
+    byte-identical to the one-GPU run."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    tmp, golden = myo
+    pair = ["analysis=pairwise", "statistic=Correlation", "statistic.null=yes", "statistic.null.nb_rep_CPU=5",
+            "statistic.null.nb_rep_RAM=200", "statistic.null.nb_rate_classes=4"]
+    run(tmp, *COMMON, *pair, "statistic.output.file=one.txt", "statistic.null.output.file=one_null.txt")
+    run(tmp, *COMMON, *pair, "statistic.output.file=two.txt", "statistic.null.output.file=two_null.txt", "comap_b200.gpus=2")
+    for a, b in (("one.txt", "two.txt"), ("one_null.txt", "two_null.txt")):
+        assert open(os.path.join(tmp, a), "rb").read() == open(os.path.join(tmp, b), "rb").read(), a
+    clu = ["analysis=clustering", "clustering.distance=cor", "clustering.method=complete", "clustering.null=yes",
+           "clustering.null.number=3", "clustering.maximum_group_size=5"]
+    run(tmp, *COMMON, *clu, "clustering.output.groups.file=g1.txt", "clustering.null.output.file=n1.txt")
+    run(tmp, *COMMON, *clu, "clustering.output.groups.file=g2.txt", "clustering.null.output.file=n2.txt", "comap_b200.gpus=2")
+    for a, b in (("g1.txt", "g2.txt"), ("n1.txt", "n2.txt")):
+        assert open(os.path.join(tmp, a), "rb").read() == open(os.path.join(tmp, b), "rb").read(), a

@@ -4,6 +4,7 @@
 #include "context.h"
 #include <cmath>
 #include <cstring>
+#include <string>
 
 namespace cmb {
 
@@ -75,12 +76,20 @@ void Context::ensure_streams() {
   // cherries are recomputed instead of stored when their two extra tables per record are
   // small (nucleotides); for A = 20 the records would outgrow the shared-memory budget
   assign_slots(tree, A <= 4);
+  // proteins: tensor-core kernels (k1_mma20.cu) unless the tree is so deep that the down pass' shared-memory
+  // message stack (10 KB per level) does not fit, or CMB_K1_PROTEIN=scalar asks for the thread-per-site ones
+  {
+    const char* e = getenv("CMB_K1_PROTEIN");
+    protein_mma = A == 20 && !(e && std::string(e) == "scalar") && tree.down_depth <= 12;
+  }
   {
     OpStream os;
     if (A == 4) build_down_mma_stream(os, tree, tables); // tensor-core passes (k1_mma.cu)
+    else if (protein_mma) build_down_mma20_stream(os, tree, tables);
     else build_down_stream(os, tree, tables, 0, C);
     down_stream.upload(os, stream);
     if (A == 4) build_up_mma_stream(os, tree, tables); // tensor-core up pass (k1_mma.cu)
+    else if (protein_mma) build_up_mma20_stream(os, tree, tables, kChunkSites20);
     else build_up_stream(os, tree, tables, 0, C);
     up_stream.upload(os, stream);
   }
@@ -177,12 +186,20 @@ void Context::run_map(const MapBuffers& b, bool simulated, bool states_only) {
   if (simulated) m.code_mask = d_identity_mask.as<uint32_t>();
   m.states_only = simulated && states_only;
   prof_begin("map_down");
-  launch_map_down(m, b, down_stream, stream);
+  if (protein_mma) {
+    if (!launch_map_down_mma20(m, b, down_stream, stream)) fail("mapping down pass: no launch shape fits shared memory for A = 20, C = %d", m.C);
+  } else launch_map_down(m, b, down_stream, stream);
   launch_map_finish(m, b, stream);
   prof_end(2);
   prof_begin("map_up");
-  launch_map_up(m, b, up_stream, stream);
-  prof_end(1);
+  if (protein_mma) {
+    k1_part.reserve(sizeof(double) * (size_t)m.C * m.B * b.n_pad);
+    if (!launch_map_up_mma20(m, b, up_stream, k1_part.as<double>(), stream)) fail("mapping up pass: no launch shape fits shared memory for A = 20, C = %d", m.C);
+    prof_end(2);
+  } else {
+    launch_map_up(m, b, up_stream, stream);
+    prof_end(1);
+  }
 }
 
 } // namespace cmb
@@ -256,7 +273,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
                     &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm,
-                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv};
+                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part};
   for (DevBuf* b : bufs) b->release();
   c.down_stream.release();
   c.up_stream.release();

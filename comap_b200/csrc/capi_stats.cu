@@ -33,7 +33,8 @@ size_t null_bytes_per_site(const Context& c) {
   size_t D = (size_t)c.tree.n_slots * c.C * c.A * 8;
   size_t out = (size_t)c.tree.B * 8 * 2;
   size_t tips = (size_t)c.tree.n_leaves * 2;
-  return D + out + tips + (size_t)c.C * 8 + 16 * 8;
+  const size_t part = c.protein_mma ? (size_t)c.C * c.tree.B * 8 : 0; // per-class partial outputs of k1_mma20.cu
+  return D + out + tips + part + (size_t)c.C * 8 + 16 * 8;
 }
 
 MapBuffers sim_buffers(Context& c, int k, int64_t n, int64_t n_pad) {

@@ -100,6 +100,10 @@ void build_up_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, 
 // Same walk with the tables packed as DMMA m8n8k4 B-operand fragments (A = 4, all classes).
 void build_up_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt);
 void build_down_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt);
+// proteins (A = 20) on the FP64 tensor cores (k1_mma20.cu): one record per (node, class)
+constexpr int kChunkSites20 = 64; // sites per CTA / per partial chunk of the protein tensor-core kernels
+void build_up_mma20_stream(OpStream& s, const Tree& t, const ModelTables& mt, int sites_per_cta);
+void build_down_mma20_stream(OpStream& s, const Tree& t, const ModelTables& mt);
 // Simulation walk: per inner bin node (pre-order, smaller first), cumulative tables of
 // all classes.  Same header as UpHdr with ref = tip row / unused, out = original node id.
 void build_sim_stream(OpStream& s, const Tree& t, const ModelTables& mt);

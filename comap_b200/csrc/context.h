@@ -43,6 +43,8 @@ struct Context {
   DevBuf d_code_mask, d_pi, d_rates, d_probs;
   DevStream down_stream, up_stream, sim_stream;
   bool streams_ready = false;
+  bool protein_mma = false;      // A = 20 on the tensor-core kernels (k1_mma20.cu); else the thread-per-site ones
+  DevBuf k1_part;                // their per-class partial outputs [C][B][n_pad]
 
   // observed alignment + its mapping
   int64_t S = 0, S_pad = 0;

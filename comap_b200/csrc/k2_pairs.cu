@@ -13,6 +13,7 @@
 //    sorts (library code, not a hot step: 1e6 keys).
 #include "kernels.h"
 #include <cub/cub.cuh>
+#include <cstdlib>
 
 namespace cmb {
 namespace {
@@ -284,6 +285,155 @@ __device__ __forceinline__ double tile_load(double x, double mean, double thr = 
   return x;
 }
 
+// One pair (row ri of the owned rows = site i, column site j) from its accumulated sum: statistic, filters,
+// Domain bin, p-value, stores.  Shared by the unfused and the tensor-core tile kernels.
+template <int STAT>
+__device__ __forceinline__ void pair_epilogue(const TileParams& p, int64_t ri, int64_t i, int64_t j, double a) {
+  const double nb = (double)p.B;
+  double stat;
+  if (STAT == 0) stat = (a / nb * nb / (nb - 1.)) / mul_(p.sd[i], p.sd2[j]);
+  else if (STAT == 1) stat = a / nb * nb / (nb - 1.);
+  else if (STAT == 2) stat = a / mul_(p.norm[i], p.norm2[j]);
+  else if (STAT == 3) stat = a;
+  else if (STAT == 4) stat = add_(1., -(sqrt(a) / add_(p.norm[i], p.norm2[j])));
+  else if (STAT == 6) stat = mi_binary(nb, p.mean[i], p.mean2[j], a); // mean arrays hold the category-1 counts
+  else stat = sqrt(a);
+  if (p.mode == MODE_DIST) {
+    double d = p.dist_is_stat ? stat : p.dist_comp - stat;
+    p.mat[(size_t)i * p.S + j] = d;
+    p.mat[(size_t)j * p.S + i] = d;
+    return;
+  }
+  const int64_t idx = p.mode == MODE_RECT ? i * p.S2 + j : p.row_off[ri] + (j - i - 1);
+  const int ci = p.rate_class[i], cj = p.rate_class2[j];
+  const double pi_ = p.post_rate[i], pj = p.post_rate2[j];
+  const double ni = p.norm[i], nj = p.norm2[p.nmin_by_row && i < p.S2 ? i : j];
+  if (p.any_filter) {
+    bool keep = ci >= p.min_rate_class && cj >= p.min_rate_class2 && !(pi_ < p.min_rate) && !(pj < p.min_rate2);
+    if (p.max_rate_class_diff >= 0 && abs(cj - ci) > p.max_rate_class_diff) keep = false;
+    if (p.max_rate_diff >= 0. && fabs(pj - pi_) > p.max_rate_diff) keep = false;
+    if (fabs(stat) < p.min_stat) keep = false;
+    p.o_keep[idx] = keep ? 1 : 0;
+  }
+  const double nm = ni < nj ? ni : nj;
+  if (p.o_i) p.o_i[idx] = (int32_t)i;
+  if (p.o_j) p.o_j[idx] = (int32_t)j;
+  if (p.o_stat) p.o_stat[idx] = stat;
+  if (p.o_rcmin) p.o_rcmin[idx] = ci < cj ? ci : cj;
+  if (p.o_prmin) p.o_prmin[idx] = pi_ < pj ? pi_ : pj;
+  if (p.o_nmin) p.o_nmin[idx] = nm;
+  if (p.K > 0 && (p.o_pvalue || p.o_nsim)) {
+    int cat = domain_index(p.nmax, p.K, nm);
+    double pv = nan("");
+    int64_t nsim = 0;
+    if (cat >= 0) {
+      const double* sim = p.sorted + p.bin_off[cat];
+      nsim = p.bin_off[cat + 1] - p.bin_off[cat];
+      int64_t lo = 0, hi = nsim; // count = #{sim < stat} on the ascending bin
+      while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if (sim[mid] < stat) lo = mid + 1; else hi = mid;
+      }
+      pv = (double)(nsim - lo + 1) / (double)(nsim + 1);
+    }
+    if (p.o_pvalue) p.o_pvalue[idx] = pv;
+    if (p.o_nsim) p.o_nsim[idx] = (int32_t)nsim;
+  }
+}
+
+
+// Opt-in tensor-core flavour of the correlation / covariance / cosinus Gram tiles (CMB_K2_DMMA=1): the same
+// 64 x 64 tile, centred in the tile load, accumulated by DMMA m8n8k4 (warp = 32 x 16 outputs = 4 x 2 MMA tiles,
+// 8 DMMAs per 4 branches).  It is NOT the default: the tensor core fuses and reorders the sums, so given the
+// same vectors the statistics differ from the reference's summation order in the last bits and the p-value
+// counts of tied pairs move (measured in DESIGN.md s4, K2), while the tile kernel is 6 % of the step.
+__device__ __forceinline__ void dmma_acc(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+template <int STAT>
+__global__ void __launch_bounds__(256) k2_tiles_dmma(TileParams p) {
+  constexpr int LD = TS + 4;                     // row stride = 4 mod 16 doubles: conflict-free fragment loads
+  __shared__ __align__(16) double As[BK][LD];
+  __shared__ __align__(16) double Bs[BK][LD];
+  const int2 t = p.tiles[blockIdx.x];
+  const int64_t i0 = (int64_t)t.x * TS, j0 = (int64_t)t.y * TS;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int r0 = (warp >> 2) * 32, c0 = (warp & 3) * 16;   // warp tile
+  const int lk = tid >> 4, lc = (tid & 15) * 4;
+  int64_t ai[4], bj[4];
+  double am[4], bm[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    int64_t ri = i0 + lc + u;
+    ai[u] = ri < p.n_rows ? (p.rows ? p.rows[ri] : ri) : -1;
+    int64_t cj = j0 + lc + u;
+    bj[u] = cj < p.S2 ? cj : -1;
+    am[u] = ai[u] >= 0 ? p.mean[ai[u]] : 0.;
+    bm[u] = bj[u] >= 0 ? p.mean2[bj[u]] : 0.;
+  }
+  double acc[4][2][2];
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 2; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.;
+  for (int k0 = 0; k0 < p.B; k0 += BK) {
+    const int k = k0 + lk;
+    const double* rowp = p.out + (size_t)k * p.S_pad;
+    const double* colp = p.out2 + (size_t)k * p.S2_pad;
+    const double mvk = (STAT == 0 && p.mv && k < p.B) ? p.mv[k] : 0.;
+    const double mvk2 = (STAT == 0 && p.mv && k < p.B) ? p.mv2[k] : 0.;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      double a = 0., b = 0.;
+      if (k < p.B) {
+        if (STAT == 0 && p.mv) {
+          if (ai[u] >= 0) a = tile_load<STAT>(add_(rowp[ai[u]], -mvk), am[u]);
+          if (bj[u] >= 0) b = tile_load<STAT>(add_(colp[bj[u]], -mvk2), bm[u]);
+        } else {
+          if (ai[u] >= 0) a = tile_load<STAT>(rowp[ai[u]], am[u], p.thr);
+          if (bj[u] >= 0) b = tile_load<STAT>(colp[bj[u]], bm[u], p.thr);
+        }
+      }
+      As[lk][lc + u] = a;
+      Bs[lk][lc + u] = b;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int ks = 0; ks < BK / 4; ks++) {
+      double af[4], bf[2];
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++) af[mi] = As[ks * 4 + (lane & 3)][r0 + 8 * mi + (lane >> 2)];
+#pragma unroll
+      for (int ni = 0; ni < 2; ni++) bf[ni] = Bs[ks * 4 + (lane & 3)][c0 + 8 * ni + (lane >> 2)];
+#pragma unroll
+      for (int mi = 0; mi < 4; mi++)
+#pragma unroll
+        for (int ni = 0; ni < 2; ni++) dmma_acc(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int mi = 0; mi < 4; mi++) {
+    const int64_t ri = i0 + r0 + 8 * mi + (lane >> 2);
+    if (ri >= p.n_rows) continue;
+    const int64_t i = p.rows ? p.rows[ri] : ri;
+#pragma unroll
+    for (int ni = 0; ni < 2; ni++)
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int64_t j = j0 + c0 + 8 * ni + (lane & 3) * 2 + h;
+        if (j >= p.S2 || (p.mode != MODE_RECT && j <= i)) continue;
+        pair_epilogue<STAT>(p, ri, i, j, acc[mi][ni][h]);
+      }
+  }
+  if (p.mode == MODE_DIST && t.x == t.y) { // zero diagonal
+    for (int d = tid; d < TS; d += blockDim.x) {
+      int64_t i = i0 + d;
+      if (i < p.S) p.mat[(size_t)i * p.S + i] = 0.;
+    }
+  }
+}
+
 template <int STAT>
 __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
   __shared__ __align__(16) double As[BK][TS];
@@ -353,7 +503,6 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
     __syncthreads();
   }
 
-  const double nb = (double)p.B;
 #pragma unroll
   for (int u = 0; u < 4; u++) {
     const int64_t ri = i0 + ty * 4 + u;
@@ -363,55 +512,7 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
     for (int v = 0; v < 4; v++) {
       const int64_t j = j0 + tx * 4 + v;
       if (j >= p.S2 || (p.mode != MODE_RECT && j <= i)) continue;
-      double stat;
-      if (STAT == 0) stat = (acc[u][v] / nb * nb / (nb - 1.)) / mul_(p.sd[i], p.sd2[j]);
-      else if (STAT == 1) stat = acc[u][v] / nb * nb / (nb - 1.);
-      else if (STAT == 2) stat = acc[u][v] / mul_(p.norm[i], p.norm2[j]);
-      else if (STAT == 3) stat = acc[u][v];
-      else if (STAT == 4) stat = add_(1., -(sqrt(acc[u][v]) / add_(p.norm[i], p.norm2[j])));
-      else if (STAT == 6) stat = mi_binary(nb, p.mean[i], p.mean2[j], acc[u][v]); // mean arrays hold the category-1 counts
-      else stat = sqrt(acc[u][v]);
-      if (p.mode == MODE_DIST) {
-        double d = p.dist_is_stat ? stat : p.dist_comp - stat;
-        p.mat[(size_t)i * p.S + j] = d;
-        p.mat[(size_t)j * p.S + i] = d;
-        continue;
-      }
-      const int64_t idx = p.mode == MODE_RECT ? i * p.S2 + j : p.row_off[ri] + (j - i - 1);
-      const int ci = p.rate_class[i], cj = p.rate_class2[j];
-      const double pi_ = p.post_rate[i], pj = p.post_rate2[j];
-      const double ni = p.norm[i], nj = p.norm2[p.nmin_by_row && i < p.S2 ? i : j];
-      if (p.any_filter) {
-        bool keep = ci >= p.min_rate_class && cj >= p.min_rate_class2 && !(pi_ < p.min_rate) && !(pj < p.min_rate2);
-        if (p.max_rate_class_diff >= 0 && abs(cj - ci) > p.max_rate_class_diff) keep = false;
-        if (p.max_rate_diff >= 0. && fabs(pj - pi_) > p.max_rate_diff) keep = false;
-        if (fabs(stat) < p.min_stat) keep = false;
-        p.o_keep[idx] = keep ? 1 : 0;
-      }
-      const double nm = ni < nj ? ni : nj;
-      if (p.o_i) p.o_i[idx] = (int32_t)i;
-      if (p.o_j) p.o_j[idx] = (int32_t)j;
-      if (p.o_stat) p.o_stat[idx] = stat;
-      if (p.o_rcmin) p.o_rcmin[idx] = ci < cj ? ci : cj;
-      if (p.o_prmin) p.o_prmin[idx] = pi_ < pj ? pi_ : pj;
-      if (p.o_nmin) p.o_nmin[idx] = nm;
-      if (p.K > 0 && (p.o_pvalue || p.o_nsim)) {
-        int cat = domain_index(p.nmax, p.K, nm);
-        double pv = nan("");
-        int64_t nsim = 0;
-        if (cat >= 0) {
-          const double* sim = p.sorted + p.bin_off[cat];
-          nsim = p.bin_off[cat + 1] - p.bin_off[cat];
-          int64_t lo = 0, hi = nsim; // count = #{sim < stat} on the ascending bin
-          while (lo < hi) {
-            int64_t mid = (lo + hi) >> 1;
-            if (sim[mid] < stat) lo = mid + 1; else hi = mid;
-          }
-          pv = (double)(nsim - lo + 1) / (double)(nsim + 1);
-        }
-        if (p.o_pvalue) p.o_pvalue[idx] = pv;
-        if (p.o_nsim) p.o_nsim[idx] = (int32_t)nsim;
-      }
+      pair_epilogue<STAT>(p, ri, i, j, acc[u][v]);
     }
   }
   if (p.mode == MODE_DIST && t.x == t.y) { // zero diagonal
@@ -577,6 +678,14 @@ int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
   p.dist_is_stat = L.dist_is_stat;
   if (L.n_tiles == 0) return 0;
   unsigned g = (unsigned)L.n_tiles;
+  const char* dm = getenv("CMB_K2_DMMA"); // opt-in tensor-core Gram tiles (not bit-exact with the reference's summation order)
+  if (dm && atoi(dm) && L.stat_id <= 2) {
+    if (L.stat_id == 0) k2_tiles_dmma<0><<<g, 256, 0, st>>>(p);
+    else if (L.stat_id == 1) k2_tiles_dmma<1><<<g, 256, 0, st>>>(p);
+    else k2_tiles_dmma<2><<<g, 256, 0, st>>>(p);
+    CMB_CUDA(cudaGetLastError());
+    return 1;
+  }
   switch (L.stat_id) {
     case 0: k2_tiles<0><<<g, 256, 0, st>>>(p); break;
     case 1: k2_tiles<1><<<g, 256, 0, st>>>(p); break;

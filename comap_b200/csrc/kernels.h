@@ -53,6 +53,10 @@ void launch_map_up(const MapModel& m, const MapBuffers& b, const DevStream& s, c
 // A = 4: tensor-core up pass (k1_mma.cu); the stream is build_up_mma_stream's
 void launch_map_up_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
 void launch_map_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
+// A = 20: tensor-core passes (k1_mma20.cu); the streams are build_*_mma20_stream's; part: [C][B][n_pad] scratch.
+// false = no launch shape fits (the caller reports it)
+bool launch_map_down_mma20(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
+bool launch_map_up_mma20(const MapModel& m, const MapBuffers& b, const DevStream& s, double* part, cudaStream_t st);
 // A = 4 partial layout: 128-site chunks (common.h kChunkSites), [chunk][slot][class][site][state]
 __host__ __device__ inline size_t d_chunk(int64_t chunk, int slot, int n_slots, int C) {
   return ((size_t)chunk * n_slots + slot) * ((size_t)C * kChunkSites * 4);

@@ -503,6 +503,161 @@ void build_down_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
   for (auto& r : recs) { pk.add(r); pk.flush(); }
 }
 
+// ---- tensor-core (DMMA m8n8k4) streams for proteins, A = 20 (k1_mma20.cu) ------------------------------------
+// A 20-vector of a site lives in five registers of the quad of lanes that owns the site: lane q holds states
+// 4 kt + q, kt = 0..4 (the A-operand layout of a k-tile).  A 20 x 20 matrix-vector product y = M x is 3 n-tiles x
+// 5 k-tiles of DMMA m8n8k4; the B operand of (nt, kt) is one double per lane, lane = 4 n + k -> M[xo(n)][4 kt + k]
+// with the output columns permuted, xo(n) = 4 (2 nt + (n & 1)) + (n >> 1), so that the C fragment of a lane (its two
+// columns 2 q and 2 q + 1) is states 4 (2 nt) + q and 4 (2 nt + 1) + q: k-tiles 2 nt and 2 nt + 1 of y in the very
+// layout the next product reads -- chained products need no shuffle.  15 fragments of 256 B per matrix.
+// One record per (node, class): a CTA works on ONE rate class, so a record is the class's tables only.
+namespace {
+void table_of_a(const Tree& t, const ModelTables& mt, int v, int what, int c, std::vector<double>& tab) {
+  const int A = mt.A, br = t.bin[v].branch;
+  tab.resize((size_t)A * A);
+  for (int x = 0; x < A; x++)
+    for (int y = 0; y < A; y++) {
+      if (br >= 0) tab[x * A + y] = (what == 0 ? mt.P : mt.W)[(((size_t)br * mt.C + c) * A + x) * A + y];
+      else tab[x * A + y] = what == 0 ? (x == y ? 1. : 0.) : 0.; // virtual edge: P = I, W = 0
+    }
+}
+// fragments of y = M x (transposed = false) or y = M^T x (true), M row-major 20 x 20
+void append_frags20(std::vector<unsigned char>& rec, const std::vector<double>& M, bool transposed) {
+  double frag[32];
+  for (int nt = 0; nt < 3; nt++)
+    for (int kt = 0; kt < 5; kt++) {
+      for (int l = 0; l < 32; l++) {
+        const int k = l & 3, n = l >> 2;
+        const int xo = 4 * (2 * nt + (n & 1)) + (n >> 1), xi = 4 * kt + k;
+        frag[l] = xo < 20 ? (transposed ? M[xi * 20 + xo] : M[xo * 20 + xi]) : 0.;
+      }
+      append(rec, frag, sizeof frag);
+    }
+}
+// raw table for column picks of a resolved tip, transposed: [state][xo] = M[xo][state]
+void append_raw20_t(std::vector<unsigned char>& rec, const std::vector<double>& M) {
+  double tab[400];
+  for (int st = 0; st < 20; st++)
+    for (int xo = 0; xo < 20; xo++) tab[st * 20 + xo] = M[xo * 20 + st];
+  append(rec, tab, sizeof tab);
+}
+} // namespace
+
+// Up stream: pre-order, smaller child first; kinds inner (0) / tip (1) only (cherries keep their stored partial).
+// Record (node, class) = UpMmaHdr | child a: inner FP[15] FW[15] FM[15] (S = P D, T = W D, message = P^T U),
+// tip PT[400] WT[400] | child b likewise.  Records are laid out node-major: index node * C + class.
+void build_up_mma20_stream(OpStream& s, const Tree& t, const ModelTables& mt, int sites_per_cta) {
+  if (mt.A != 20) fail("internal: the protein tensor-core up stream is built for A = 20");
+  s = OpStream();
+  const int C = mt.C;
+  std::vector<int> st;
+  int depth = 0;
+  std::vector<double> P, W;
+  Packer pk(s, 1u << 30);
+  size_t max_rec = 0;
+  for (size_t idx = 0; idx < t.up_order.size(); idx++) {
+    const int v = t.up_order[idx];
+    const BinNode& n = t.bin[v];
+    int a = n.left, b = n.right;
+    if (t.bin[a].leaves > t.bin[b].leaves) std::swap(a, b);
+    const bool ta = t.bin[a].left < 0, tb = t.bin[b].left < 0;
+    if (!ta && tb) fail("internal: up order must expand the smaller child first");
+    UpMmaHdr h{};
+    h.flags = (ta ? kUpTipA : 0) | (tb ? kUpTipB : 0);
+    int push_level = 0, pop_level = 0xff;
+    if (!ta) { h.flags |= kUpTakeA | kUpPush; push_level = (int)st.size(); st.push_back(b); depth = std::max(depth, (int)st.size()); }
+    else if (!tb) h.flags |= kUpTakeB;
+    else if (!st.empty()) { h.flags |= kUpPop; st.pop_back(); pop_level = (int)st.size(); }
+    h.kase = (uint32_t)((ta ? 1 : 0) * 3 + (tb ? 1 : 0)) | (uint32_t)push_level << 8 | (uint32_t)pop_level << 16;
+    h.ref_a = ta ? t.bin[a].tip_row : t.bin[a].slot;
+    h.ref_b = tb ? t.bin[b].tip_row : t.bin[b].slot;
+    h.out_a = t.bin[a].branch; h.out_b = t.bin[b].branch;
+    h.out_a1 = h.out_a2 = h.out_b1 = h.out_b2 = -1;
+    const uint32_t rec_bytes = (uint32_t)(sizeof h + ((ta ? 2 * 3200 : 3 * 3840) + (tb ? 2 * 3200 : 3 * 3840)));
+    const uint32_t tips_off = (rec_bytes + 127) & ~127u;
+    const uint32_t blk_off = tips_off + ((ta || tb) ? 2u * (uint32_t)sites_per_cta : 0u);
+    const uint32_t n_blk = (uint32_t)!ta + (uint32_t)!tb;
+    s.stage_bytes = std::max(s.stage_bytes, blk_off + n_blk * (uint32_t)sites_per_cta * 160u);
+    h.tips_off = (int32_t)tips_off; h.blk_off = (int32_t)blk_off;
+    s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.ref_a); s.aux.push_back(h.ref_b); s.aux.push_back((int32_t)tips_off);
+    s.aux.push_back(-1); s.aux.push_back(-1); s.aux.push_back((int32_t)blk_off); s.aux.push_back(0);
+    s.n_records++;
+    for (int c = 0; c < C; c++) {
+      std::vector<unsigned char> rec;
+      append(rec, &h, sizeof h);
+      for (int e = 0; e < 2; e++) {
+        const int x = e ? b : a;
+        table_of_a(t, mt, x, 0, c, P);
+        table_of_a(t, mt, x, 1, c, W);
+        if (e ? tb : ta) { append_raw20_t(rec, P); append_raw20_t(rec, W); }
+        else { append_frags20(rec, P, false); append_frags20(rec, W, false); append_frags20(rec, P, true); }
+      }
+      if (rec.size() != rec_bytes) fail("internal: protein up record size");
+      max_rec = std::max(max_rec, rec.size());
+      pk.add(rec); pk.flush();
+    }
+  }
+  s.stack_depth = depth;
+  s.chunk_cap = (uint32_t)max_rec;
+}
+
+// Down stream: post-order, larger child (a) first; record (node, class) = DownHdr | tables:
+//   a tip, b tip    : PT_a[400] PT_b[400]
+//   a inner, b tip  : FP_a[15] (a's partial is the running one), PT_b[400]
+//   a inner, b inner: FP_b[15] (b's partial is the running one; a's message waits on the stack)
+//   + FP_v[15] when v's own message goes to the stack (kDownPush)
+void build_down_mma20_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
+  if (mt.A != 20) fail("internal: the protein tensor-core down stream is built for A = 20");
+  s = OpStream();
+  const int C = mt.C;
+  auto larger_first = [&](int v, int& a, int& b) {
+    a = t.bin[v].left; b = t.bin[v].right;
+    if (t.bin[b].leaves > t.bin[a].leaves) std::swap(a, b);
+  };
+  int depth = 0, sp = 0;
+  std::vector<double> P;
+  Packer pk(s, 1u << 30);
+  size_t max_rec = 0;
+  for (int v : t.down_order) {
+    const BinNode& n = t.bin[v];
+    int a, b;
+    larger_first(v, a, b);
+    const bool ta = t.bin[a].left < 0, tb = t.bin[b].left < 0;
+    if (ta && !tb) fail("internal: down order must expand the larger child first");
+    DownHdr h{};
+    h.flags = (ta ? kDownTipA : 0) | (tb ? kDownTipB : 0);
+    h.row_a = ta ? t.bin[a].tip_row : -1;
+    h.row_b = tb ? t.bin[b].tip_row : -1;
+    h.slot = n.slot;
+    int pop_level = 0xff, push_level = 0xff;
+    if (!ta && !tb) pop_level = --sp; // pops a's message
+    bool push = false;
+    if (v == t.bin_root) h.flags |= kDownRoot;
+    else {
+      int pa, pb;
+      larger_first(n.parent, pa, pb);
+      push = pa == v && t.bin[pb].left >= 0;
+    }
+    if (push) { h.flags |= kDownPush; push_level = sp; depth = std::max(depth, ++sp); }
+    h.flags |= (uint32_t)pop_level << 16 | (uint32_t)push_level << 24; // stack slots: no run-time stack pointer
+    s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.row_a); s.aux.push_back(h.row_b); s.aux.push_back(0);
+    s.n_records++;
+    for (int c = 0; c < C; c++) {
+      std::vector<unsigned char> rec;
+      append(rec, &h, sizeof h);
+      if (!ta) { table_of_a(t, mt, tb ? a : b, 0, c, P); append_frags20(rec, P, false); }
+      if (ta) { table_of_a(t, mt, a, 0, c, P); append_raw20_t(rec, P); }
+      if (tb) { table_of_a(t, mt, b, 0, c, P); append_raw20_t(rec, P); }
+      if (push) { table_of_a(t, mt, v, 0, c, P); append_frags20(rec, P, false); }
+      pad16(rec);
+      max_rec = std::max(max_rec, rec.size());
+      pk.add(rec); pk.flush();
+    }
+  }
+  s.stack_depth = depth;
+  s.chunk_cap = (uint32_t)max_rec;
+}
+
 void build_up_stream(OpStream& s, const Tree& t, const ModelTables& mt, int c0, int cb) {
   up_like_stream(s, t, mt, c0, cb, false);
 }

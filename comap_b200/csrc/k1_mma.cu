@@ -470,7 +470,7 @@ struct DownMmaParams {
 };
 constexpr int kDownStages = 8;
 
-template <int NG, int C, int SG, int MINB>
+template <int NG, int C, int SG, int MINB, bool STATES>
 __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(MapModel m, MapBuffers b, DownMmaParams dp) {
   extern __shared__ __align__(128) unsigned char smem[];
   constexpr int W = SG / (8 * NG);
@@ -485,8 +485,9 @@ __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(Ma
   unsigned char* stg_ring = smem + 128;
   double* stack = reinterpret_cast<double*>(stg_ring + (size_t)NSTG * stage_bytes);
 
-  __shared__ uint32_t cmask[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) cmask[i] = __ldg(m.code_mask + i);
+  __shared__ uint32_t cmask[STATES ? 1 : 256];
+  if constexpr (!STATES)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) cmask[i] = __ldg(m.code_mask + i);
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTG; i++) { mbar_init(&stg_full[i], 1); mbar_init(&stg_empty[i], W); }
     mbar_fence_init();
@@ -526,8 +527,6 @@ __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(Ma
   const int q = lane & 3, s8 = lane >> 2;
   const int wsite = warp * (8 * NG);
   double cur[C][NG];
-  double stk_l[kMaxStack][C][NG];                  // levels beyond the shared-memory stack
-  int sp = 0;
 #pragma unroll
   for (int c = 0; c < C; c++)
 #pragma unroll
@@ -540,7 +539,7 @@ __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(Ma
   for (uint32_t node = 0; node < dp.n_nodes; node++) {
     mbar_wait(&stg_full[cs], cph);
     const unsigned char* stage = stg_ring + (size_t)cs * stage_bytes;
-    const int4 h = *reinterpret_cast<const int4*>(stage);
+    const int4 h = *reinterpret_cast<const int4*>(stage); // flags | pop level << 16 | push level << 24, rows, slot
     const uint32_t flags = (uint32_t)h.x;
     const bool tipa = flags & kDownTipA, tipb = flags & kDownTipB;
     const double* F = reinterpret_cast<const double*>(stage + 16);              // fragment of the running child
@@ -553,14 +552,13 @@ __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(Ma
     auto tip_message = [&](const unsigned char* codes, const double* R, double (&M)[C][NG]) {
       bool fast = true;
       uint32_t mk[NG];
-      if (m.states_only) {
 #pragma unroll
-        for (int g = 0; g < NG; g++) mk[g] = codes[8 * g];
-      } else {
+      for (int g = 0; g < NG; g++) mk[g] = codes[8 * g];
+      if constexpr (!STATES) {
         bool single = true;
 #pragma unroll
         for (int g = 0; g < NG; g++) {
-          mk[g] = cmask[codes[8 * g]];
+          mk[g] = cmask[mk[g]];
           single = single && __popc(mk[g]) == 1;
         }
         fast = __all_sync(0xffffffffu, single);
@@ -605,19 +603,11 @@ __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(Ma
       tip_message(ts + SG, Rb, Mb);
     } else {                          // a's message waits on the stack, b's partial is the running one
       edge_message(F, Mb);
-      --sp;
-      if (sp < dp.smem_levels) {
-        const double* e = my_stack + (size_t)sp * (kEntry / 8);
+      const double* e = my_stack + (size_t)((flags >> 16) & 0xff) * (kEntry / 8);
 #pragma unroll
-        for (int c = 0; c < C; c++)
+      for (int c = 0; c < C; c++)
 #pragma unroll
-          for (int g = 0; g < NG; g++) Ma[c][g] = e[c * (SG * 4) + g * 32];
-      } else {
-#pragma unroll
-        for (int c = 0; c < C; c++)
-#pragma unroll
-          for (int g = 0; g < NG; g++) Ma[c][g] = stk_l[sp - dp.smem_levels][c][g];
-      }
+        for (int g = 0; g < NG; g++) Ma[c][g] = e[c * (SG * 4) + g * 32];
     }
 #pragma unroll
     for (int c = 0; c < C; c++)
@@ -633,19 +623,11 @@ __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(Ma
     if (flags & kDownPush) {
       double M[C][NG];
       edge_message(Fv, M);
-      if (sp < dp.smem_levels) {
-        double* e = my_stack + (size_t)sp * (kEntry / 8);
+      double* e = my_stack + (size_t)((flags >> 24) & 0xff) * (kEntry / 8);
 #pragma unroll
-        for (int c = 0; c < C; c++)
+      for (int c = 0; c < C; c++)
 #pragma unroll
-          for (int g = 0; g < NG; g++) e[c * (SG * 4) + g * 32] = M[c][g];
-      } else {
-#pragma unroll
-        for (int c = 0; c < C; c++)
-#pragma unroll
-          for (int g = 0; g < NG; g++) stk_l[sp - dp.smem_levels][c][g] = M[c][g];
-      }
-      ++sp;
+        for (int g = 0; g < NG; g++) e[c * (SG * 4) + g * 32] = M[c][g];
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&stg_empty[cs]);
@@ -664,7 +646,7 @@ __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(Ma
     }
 }
 
-template <int NG, int C, int SG, int MINB>
+template <int NG, int C, int SG, int MINB, bool STATES>
 bool try_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.C != C) return false;
   int dev = 0, max_smem = 0;
@@ -682,13 +664,13 @@ bool try_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cu
   dp.n_stages = kDownStages;
   while (dp.n_stages > 2 && 128 + dp.n_stages * stage + entry > (size_t)max_smem) dp.n_stages /= 2;
   if (128 + dp.n_stages * stage > (size_t)max_smem) return false;
-  // as many stack levels in shared memory as fit; deeper ones (rare) spill to local memory
-  dp.smem_levels = (int)std::min<size_t>((size_t)s.stack_depth, ((size_t)max_smem - 128 - dp.n_stages * stage) / entry);
-  if (MINB > 1 && dp.smem_levels < s.stack_depth) return false; // prefer one CTA per SM with the whole stack
+  // the whole message stack lives in shared memory (its levels are in the records: no run-time stack pointer)
+  dp.smem_levels = s.stack_depth;
+  if (128 + dp.n_stages * stage + (size_t)s.stack_depth * entry > (size_t)max_smem) return false;
   const size_t smem = 128 + dp.n_stages * stage + (size_t)dp.smem_levels * entry;
   constexpr int threads = 32 * (SG / (8 * NG) + 1);
-  CMB_CUDA(cudaFuncSetAttribute(k1_down_mma<NG, C, SG, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k1_down_mma<NG, C, SG, MINB><<<(unsigned)(b.n_pad / SG), threads, smem, st>>>(m, b, dp);
+  CMB_CUDA(cudaFuncSetAttribute(k1_down_mma<NG, C, SG, MINB, STATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k1_down_mma<NG, C, SG, MINB, STATES><<<(unsigned)(b.n_pad / SG), threads, smem, st>>>(m, b, dp);
   CMB_CUDA(cudaGetLastError());
   return true;
 }
@@ -696,8 +678,14 @@ bool try_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cu
 template <int C>
 bool down_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st) {
   if (m.C != C) return false;
-  if (narrow_batch(b) && try_down_mma<2, C, kNarrowSG, 2>(m, b, s, st)) return true;
-  return try_down_mma<2, C, kWideSG, 2>(m, b, s, st) || try_down_mma<2, C, kWideSG, 1>(m, b, s, st);
+  if (m.states_only) {
+    if (narrow_batch(b) && try_down_mma<2, C, kNarrowSG, 2, true>(m, b, s, st)) return true;
+    return try_down_mma<2, C, kWideSG, 2, true>(m, b, s, st) || try_down_mma<2, C, kWideSG, 1, true>(m, b, s, st) ||
+           try_down_mma<2, C, kNarrowSG, 1, true>(m, b, s, st);
+  }
+  if (narrow_batch(b) && try_down_mma<2, C, kNarrowSG, 2, false>(m, b, s, st)) return true;
+  return try_down_mma<2, C, kWideSG, 2, false>(m, b, s, st) || try_down_mma<2, C, kWideSG, 1, false>(m, b, s, st) ||
+         try_down_mma<2, C, kNarrowSG, 1, false>(m, b, s, st);
 }
 
 } // namespace

@@ -460,7 +460,8 @@ void build_down_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
     h.row_a = ta ? t.bin[a].tip_row : -1;
     h.row_b = tb ? t.bin[b].tip_row : -1;
     h.slot = n.slot;
-    if (!ta && !tb) sp--; // pops a's message
+    int pop_level = 0xff, push_level = 0xff; // stack slots in the record: no run-time stack pointer
+    if (!ta && !tb) pop_level = --sp; // pops a's message
     bool push = false;
     if (v == t.bin_root) h.flags |= kDownRoot;
     else {
@@ -468,7 +469,8 @@ void build_down_mma_stream(OpStream& s, const Tree& t, const ModelTables& mt) {
       larger_first(n.parent, pa, pb);
       push = pa == v && t.bin[pb].left >= 0;
     }
-    if (push) { h.flags |= kDownPush; depth = std::max(depth, ++sp); }
+    if (push) { h.flags |= kDownPush; push_level = sp; depth = std::max(depth, ++sp); }
+    h.flags |= (uint32_t)pop_level << 16 | (uint32_t)push_level << 24;
     s.aux.push_back((int32_t)h.flags); s.aux.push_back(h.row_a); s.aux.push_back(h.row_b); s.aux.push_back(0);
     s.n_records++;
     std::vector<unsigned char> rec;

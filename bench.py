@@ -325,7 +325,7 @@ def run_ours(args, cfg):
             ctx.null_intra_sharded(stat, cfg["null_seed"], RC, R, K=K, nmax=-1.0)
 
         def step_resident():
-            ctx.map(want_vectors=False)
+            ctx.map_async()              # enqueued on a side stream: the null replicates overlap it
             null_dist()
             return ctx.pairs_resident(stat, use_null=True, shard_index=rank, shard_count=world)
 

@@ -151,6 +151,11 @@ class Context:
         self._chk(self.lib.cmb_map(self.h, _d(n), _d(norm), _d(pr), _i32(rc), _d(ll)))
         return dict(n=n, norm=norm, post_rate=pr, rate_class=rc, loglik=ll)
 
+    def map_async(self):
+        """cmb_map without host outputs: enqueued on a side stream; the next call that needs the mapping
+        (pairs, the null's binning, ...) completes it."""
+        self._chk(self.lib.cmb_map(self.h, None, None, None, None, None))
+
     # ------------------------------------------------------------------ simulation / null
     def simulate(self, seed, first_site, n, weighted_classes=False):
         states = np.empty((self.T, n), np.uint8); cls = np.empty(n, np.int32)

@@ -123,6 +123,7 @@ MapModel Context::map_model() const {
 }
 
 const double* Context::mean_vector() {
+  finish_map();
   if (!mapped) fail("the corrected correlation needs a mapped alignment (cmb_map) for its mean vector");
   if (!have_meanvec) {
     const int B = tree.B;
@@ -140,6 +141,7 @@ const double* Context::mean_vector() {
 }
 
 const double* Context::mi_counts() {
+  finish_map();
   if (!mapped) fail("statistic MI needs a mapped alignment (cmb_map)");
   if (!have_mi_count) {
     mi_count.reserve(sizeof(double) * S_pad);
@@ -180,6 +182,38 @@ void Context::prof_collect() {
   prof.pending.clear();
 }
 
+void Context::wait_map() {
+  if (map_pending) CMB_CUDA(cudaEventSynchronize(map_done));
+}
+
+// max(norm) for the null's Domain and the saturated-site check of a finished mapping (host copies are in place)
+void Context::finalize_map_host() {
+  max_norm = 0.;
+  for (int64_t i = 0; i < S; i++)
+    if (h_norm[i] > max_norm) max_norm = h_norm[i];
+  // A site whose likelihood underflowed to 0 (ln L = -inf) has 1/L = inf and NaN vectors.  The reference stops
+  // there (CoETools.cpp:233-247) or drops those sites and starts over (remove_saturated_sites, :248-262); the
+  // per-site outputs are filled so the caller can find them, and the mapping is refused.
+  int64_t n_sat = 0, first_sat = -1;
+  for (int64_t i = 0; i < S; i++)
+    if (!std::isfinite(h_loglik[i])) { if (!n_sat++) first_sat = i; }
+  if (n_sat) {
+    mapped = false;
+    fail("cmb_map: the likelihood is 0 (log = -inf) at %lld site(s), first at site index %lld: computer underflow, "
+         "expected on big data sets (>~500 sequences); remove those sites (input.sequence.remove_saturated_sites = yes)",
+         (long long)n_sat, (long long)first_sat);
+  }
+  mapped = true;
+}
+
+void Context::finish_map() {
+  if (!map_pending) return;
+  CMB_CUDA(cudaEventSynchronize(map_done));
+  map_pending = false;
+  CMB_CUDA(cudaStreamWaitEvent(stream, map_done, 0)); // later work on the main stream sees the mapping
+  finalize_map_host();
+}
+
 // Down pass for every class block, site likelihoods, then up pass + contraction.
 void Context::run_map(const MapBuffers& b, bool simulated, bool states_only) {
   MapModel m = map_model();
@@ -193,8 +227,9 @@ void Context::run_map(const MapBuffers& b, bool simulated, bool states_only) {
   prof_end(2);
   prof_begin("map_up");
   if (protein_mma) {
-    k1_part.reserve(sizeof(double) * (size_t)m.C * m.B * b.n_pad);
-    if (!launch_map_up_mma20(m, b, up_stream, k1_part.as<double>(), stream)) fail("mapping up pass: no launch shape fits shared memory for A = 20, C = %d", m.C);
+    DevBuf& part = simulated ? k1_part : k1_part_obs; // the observed mapping may run beside a simulated one
+    part.reserve(sizeof(double) * (size_t)m.C * m.B * b.n_pad);
+    if (!launch_map_up_mma20(m, b, up_stream, part.as<double>(), stream)) fail("mapping up pass: no launch shape fits shared memory for A = 20, C = %d", m.C);
     prof_end(2);
   } else {
     launch_map_up(m, b, up_stream, stream);
@@ -264,6 +299,9 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
   cudaSetDevice(c.device);
   cudaStreamSynchronize(c.stream);
   cmb_comm_destroy(ctx);
+  if (c.map_stream) { cudaStreamSynchronize(c.map_stream); cudaStreamDestroy(c.map_stream); cudaEventDestroy(c.map_begin); cudaEventDestroy(c.map_done); }
+  if (c.h_norm) cudaFreeHost(c.h_norm);
+  if (c.h_loglik) cudaFreeHost(c.h_loglik);
   if (c.copy_stream) { cudaStreamSynchronize(c.copy_stream); cudaStreamDestroy(c.copy_stream); }
   if (c.copy_event) cudaEventDestroy(c.copy_event);
   for (auto& t : c.prof.pending) { cudaEventDestroy(std::get<1>(t)); cudaEventDestroy(std::get<2>(t)); }
@@ -273,7 +311,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
                     &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm,
-                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part};
+                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part, &c.k1_part_obs};
   for (DevBuf* b : bufs) b->release();
   c.down_stream.release();
   c.up_stream.release();
@@ -287,6 +325,7 @@ int cmb_sync(cmb_ctx* ctx) {
   CMB_TRY
   CMB_CUDA(cudaStreamSynchronize(ctx->c.stream));
   if (ctx->c.copy_stream) CMB_CUDA(cudaStreamSynchronize(ctx->c.copy_stream));
+  if (ctx->c.map_stream) CMB_CUDA(cudaStreamSynchronize(ctx->c.map_stream));
   CMB_CATCH
 }
 
@@ -294,6 +333,7 @@ int cmb_set_tree(cmb_ctx* ctx, int32_t n_nodes, const int32_t* parent, const dou
   CMB_TRY
   Context& c = ctx->c;
   CMB_CUDA(cudaSetDevice(c.device));
+  c.wait_map(); c.map_pending = false;
   build_tree(c.tree, n_nodes, parent, brlen);
   c.have_tree = true;
   c.streams_ready = false;
@@ -311,6 +351,7 @@ int cmb_set_model(cmb_ctx* ctx, int32_t A, const double* Q, const double* pi, in
   if (A < 2 || A > 32) fail("cmb_set_model: A must be in 2..32 (got %d)", A);
   if (C < 1 || C > 32) fail("cmb_set_model: C must be in 1..32 (got %d)", C);
   check_map_support(A, C);
+  c.wait_map(); c.map_pending = false;
   c.A = A; c.C = C; c.count_method = count_method;
   c.Q.assign(Q, Q + (size_t)A * A);
   c.pi.assign(pi, pi + A);
@@ -334,6 +375,7 @@ int cmb_set_alignment(cmb_ctx* ctx, int64_t S, const uint8_t* codes, int32_t n_c
   if (S < 1) fail("cmb_set_alignment: empty alignment");
   if (n_codes < 1 || n_codes > 256) fail("cmb_set_alignment: n_codes must be in 1..256");
   const int T = c.tree.n_leaves;
+  c.wait_map(); c.map_pending = false;
   {
     uint8_t worst = 0; // branch-free max over the T*S codes (vectorises); the slow scan only names the culprit
     for (int64_t i = 0; i < (int64_t)T * S; i++) worst = codes[i] > worst ? codes[i] : worst;
@@ -363,6 +405,9 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   Context& c = ctx->c;
   CMB_CUDA(cudaSetDevice(c.device));
   if (!c.have_alignment) fail("cmb_map: call cmb_set_alignment first");
+  c.wait_map();
+  c.map_pending = false;
+  c.mapped = false;
   c.ensure_streams();
   const int64_t S = c.S, Sp = c.S_pad;
   const int A = c.A, C = c.C, B = c.tree.B;
@@ -373,6 +418,32 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   c.d_pr.reserve(sizeof(double) * Sp);
   c.d_rc.reserve(sizeof(int32_t) * Sp);
   c.d_out.reserve(sizeof(double) * (size_t)B * Sp);
+  c.pairs_mean.reserve(sizeof(double) * Sp);
+  c.pairs_sd.reserve(sizeof(double) * Sp);
+  c.pairs_norm.reserve(sizeof(double) * Sp);
+  if ((size_t)S > c.h_cap) {
+    if (c.h_norm) cudaFreeHost(c.h_norm);
+    if (c.h_loglik) cudaFreeHost(c.h_loglik);
+    c.h_norm = c.h_loglik = nullptr; c.h_cap = 0;
+    CMB_CUDA(cudaMallocHost((void**)&c.h_norm, sizeof(double) * S));
+    CMB_CUDA(cudaMallocHost((void**)&c.h_loglik, sizeof(double) * S));
+    c.h_cap = (size_t)S;
+  }
+  // no host output asked for: the mapping is only enqueued, on a side stream ordered after what the main
+  // stream holds now; the first call that needs it completes it (Context::finish_map)
+  const bool deferred = !n_out && !norm && !post_rate && !rate_class && !loglik;
+  cudaStream_t main_stream = c.stream;
+  struct Restore { Context& c; cudaStream_t s; ~Restore() { c.stream = s; } } restore{c, main_stream};
+  if (deferred) {
+    if (!c.map_stream) {
+      CMB_CUDA(cudaStreamCreateWithFlags(&c.map_stream, cudaStreamNonBlocking));
+      CMB_CUDA(cudaEventCreateWithFlags(&c.map_begin, cudaEventDisableTiming));
+      CMB_CUDA(cudaEventCreateWithFlags(&c.map_done, cudaEventDisableTiming));
+    }
+    CMB_CUDA(cudaEventRecord(c.map_begin, main_stream));
+    CMB_CUDA(cudaStreamWaitEvent(c.map_stream, c.map_begin, 0));
+    c.stream = c.map_stream;
+  }
   MapBuffers b;
   b.n = S; b.n_pad = Sp;
   b.tips = c.d_tips.as<uint8_t>();
@@ -382,15 +453,11 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   c.run_map(b, false);
   // per-site mean / sd / norm in the reference's summation order (k2_prep); norms are needed
   // on the host by the null (Domain upper bound) and for the caller
-  c.pairs_mean.reserve(sizeof(double) * Sp);
-  c.pairs_sd.reserve(sizeof(double) * Sp);
-  c.pairs_norm.reserve(sizeof(double) * Sp);
   launch_prep(B, S, Sp, b.out, nullptr, c.pairs_mean.as<double>(), c.pairs_sd.as<double>(), c.pairs_norm.as<double>(), c.stream);
   c.have_meanvec = false;
   c.have_mi_count = false;
   c.prof.total_launches += 1;
-  c.h_norm.resize(S);
-  CMB_CUDA(cudaMemcpyAsync(c.h_norm.data(), c.pairs_norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaMemcpyAsync(c.h_norm, c.pairs_norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
   if (n_out) {
     c.scratch.reserve(sizeof(double) * (size_t)S * B);
     launch_transpose_out(b.out, B, S, Sp, c.scratch.as<double>(), c.stream);
@@ -399,31 +466,20 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
   }
   if (post_rate) CMB_CUDA(cudaMemcpyAsync(post_rate, c.d_pr.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
   if (rate_class) CMB_CUDA(cudaMemcpyAsync(rate_class, c.d_rc.p, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, c.stream));
-  c.h_loglik.resize(S);
-  CMB_CUDA(cudaMemcpyAsync(c.h_loglik.data(), c.d_loglik.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
-  CMB_CUDA(cudaStreamSynchronize(c.stream));
-  if (loglik) std::memcpy(loglik, c.h_loglik.data(), sizeof(double) * S);
-  c.max_norm = 0.;
-  for (int64_t i = 0; i < S; i++)
-    if (c.h_norm[i] > c.max_norm) c.max_norm = c.h_norm[i];
-  if (norm) std::memcpy(norm, c.h_norm.data(), sizeof(double) * S);
+  CMB_CUDA(cudaMemcpyAsync(c.h_loglik, c.d_loglik.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
   c.have_dist = false;
   c.pairs_rows = -1; // resident pair columns belong to the previous mapping
   for (auto& o : c.pairs_col_off) o = -1;
   if (c.null.nmax_from_map) c.null.ready = false; // binned with the previous mapping's max(norm)
-  // A site whose likelihood underflowed to 0 (ln L = -inf) has 1/L = inf and NaN vectors.  The reference stops
-  // there (CoETools.cpp:233-247) or drops those sites and starts over (remove_saturated_sites, :248-262); the
-  // per-site outputs above are filled so the caller can find them, and the mapping is refused.
-  int64_t n_sat = 0, first_sat = -1;
-  for (int64_t i = 0; i < S; i++)
-    if (!std::isfinite(c.h_loglik[i])) { if (!n_sat++) first_sat = i; }
-  if (n_sat) {
-    c.mapped = false;
-    fail("cmb_map: the likelihood is 0 (log = -inf) at %lld site(s), first at site index %lld: computer underflow, "
-         "expected on big data sets (>~500 sequences); remove those sites (input.sequence.remove_saturated_sites = yes)",
-         (long long)n_sat, (long long)first_sat);
+  if (deferred) {
+    CMB_CUDA(cudaEventRecord(c.map_done, c.map_stream));
+    c.map_pending = true;
+    return 0;
   }
-  c.mapped = true;
+  CMB_CUDA(cudaStreamSynchronize(c.stream));
+  if (loglik) std::memcpy(loglik, c.h_loglik, sizeof(double) * S);
+  if (norm) std::memcpy(norm, c.h_norm, sizeof(double) * S);
+  c.finalize_map_host();
   CMB_CATCH
 }
 
@@ -431,6 +487,7 @@ int cmb_load_vectors(cmb_ctx* ctx, const double* n_in, double* norm) {
   CMB_TRY
   Context& c = ctx->c;
   CMB_CUDA(cudaSetDevice(c.device));
+  c.finish_map();
   if (!c.mapped) fail("cmb_load_vectors: call cmb_map first (site likelihoods and rates come from the alignment)");
   if (!n_in) fail("cmb_load_vectors: no vectors given");
   const int64_t S = c.S, Sp = c.S_pad;
@@ -445,12 +502,12 @@ int cmb_load_vectors(cmb_ctx* ctx, const double* n_in, double* norm) {
   c.prof.total_launches += 2;
   c.have_meanvec = false;
   c.have_mi_count = false;
-  CMB_CUDA(cudaMemcpyAsync(c.h_norm.data(), c.pairs_norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaMemcpyAsync(c.h_norm, c.pairs_norm.p, sizeof(double) * S, cudaMemcpyDeviceToHost, c.stream));
   CMB_CUDA(cudaStreamSynchronize(c.stream));
   c.max_norm = 0.;
   for (int64_t i = 0; i < S; i++)
     if (c.h_norm[i] > c.max_norm) c.max_norm = c.h_norm[i];
-  if (norm) std::memcpy(norm, c.h_norm.data(), sizeof(double) * S);
+  if (norm) std::memcpy(norm, c.h_norm, sizeof(double) * S);
   c.have_dist = false;
   c.null.ready = false;
   c.pairs_rows = -1;

@@ -85,6 +85,7 @@ int cmb_pairs_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, const cmb_fil
   CMB_CUDA(cudaSetDevice(c.device));
   if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
   check_pair(c, d, "cmb_pairs_inter");
+  c.finish_map(); d.finish_map();
   if (!c.mapped || !d.mapped) fail("cmb_pairs_inter: call cmb_map on both data sets first");
   const int64_t S1 = c.S, S2 = d.S;
   if (independent && S1 != S2)
@@ -360,6 +361,7 @@ extern "C" int cmb_candidates(cmb_ctx* ctx, int32_t stat_id, int32_t n_groups, c
   Context& c = ctx->c;
   CMB_CUDA(cudaSetDevice(c.device));
   if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
+  c.finish_map();
   if (!c.mapped) fail("cmb_candidates: call cmb_map first");
   if (n_groups < 1) fail("ERROR!!! No group can be tested!"); // CoMap.cpp:679-680
   if (rep_ram < 1 || min_sim < 1) fail("cmb_candidates: bad simulation counts");

@@ -61,6 +61,7 @@ void null_load(Context& c, const double* stat_dev, const double* nmin_dev, int64
   if (K > 4096) fail("too many null bins (%d)", K);
   const bool from_map = nmax < 0.;
   if (from_map) {
+    c.finish_map();
     if (!c.mapped) fail("null binning with nmax < 0 needs a mapped alignment (cmb_map)");
     nmax = c.max_norm;
   }
@@ -430,6 +431,7 @@ int cmb_pairs_resident(cmb_ctx* ctx, int32_t stat_id, const cmb_filters* f, int3
   Context& c = ctx->c;
   CMB_CUDA(cudaSetDevice(c.device));
   check_stat(stat_id);
+  c.finish_map();
   if (!c.mapped) fail("cmb_pairs: call cmb_map first");
   if (use_null && !c.null.ready) fail("cmb_pairs: no null distribution (cmb_null_intra / cmb_null_load_dev)");
   if (shard_count < 1 || shard_index < 0 || shard_index >= shard_count) fail("cmb_pairs: bad shard");
@@ -593,6 +595,7 @@ int cmb_distance_matrix(cmb_ctx* ctx, int32_t dist_id, double* mat) {
   CMB_TRY
   Context& c = ctx->c;
   CMB_CUDA(cudaSetDevice(c.device));
+  c.finish_map();
   if (!c.mapped) fail("cmb_distance_matrix: call cmb_map first");
   distance_on_device(c, dist_id, c.d_out.as<double>(), c.S, c.S_pad, c.pairs_mean.as<double>(),
                      c.pairs_sd.as<double>(), c.pairs_norm.as<double>());
@@ -627,7 +630,7 @@ int cmb_groups(cmb_ctx* ctx, int32_t dist_id, int32_t max_size, int32_t* members
   CMB_CUDA(cudaSetDevice(c.device));
   if (!c.have_dendro) fail("cmb_groups: call cmb_cluster first");
   GroupTable g;
-  groups_of_dendrogram(c, dist_id, max_size, c.S, c.S_pad, c.d_out.as<double>(), c.h_norm.data(), g);
+  groups_of_dendrogram(c, dist_id, max_size, c.S, c.S_pad, c.d_out.as<double>(), c.h_norm, g);
   const int64_t ng = (int64_t)g.height.size();
   if (members && !g.members.empty()) std::memcpy(members, g.members.data(), sizeof(int32_t) * g.members.size());
   if (offsets) std::memcpy(offsets, g.offsets.data(), sizeof(int64_t) * (ng + 1));

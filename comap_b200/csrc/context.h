@@ -52,7 +52,17 @@ struct Context {
   std::vector<uint32_t> code_mask;
   bool have_alignment = false, mapped = false;
   DevBuf d_D, d_Lc, d_invL, d_loglik, d_pr, d_rc, d_out, d_sum, d_sumsq;
-  std::vector<double> h_norm, h_loglik; // host copies used by null / pairs / the saturation check
+  double *h_norm = nullptr, *h_loglik = nullptr; // pinned host copies [S] used by null / pairs / the saturation check
+  size_t h_cap = 0;
+  // cmb_map without host outputs is deferred: enqueued on a side stream so that what the caller enqueues next
+  // (the null replicates) overlaps it -- a 5000-site mapping is one latency-bound tree walk on a few SMs
+  cudaStream_t map_stream = nullptr;
+  cudaEvent_t map_begin = nullptr, map_done = nullptr;
+  bool map_pending = false;
+  DevBuf k1_part_obs;            // per-class partial outputs of the observed alignment's protein mapping
+  void wait_map();               // block until a deferred mapping has left the device (no checks)
+  void finish_map();             // ... and complete it: max norm, saturated sites (throws), ordering of the main stream
+  void finalize_map_host();
   double max_norm = 0.;
 
   // scratch for simulated batches

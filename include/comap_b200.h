@@ -101,7 +101,12 @@ int cmb_set_alignment(cmb_ctx* ctx, int64_t S, const uint8_t* codes, int32_t n_c
  * (CoETools.cpp:395-397), the norms loop (CoMap.cpp:158-163) and the per-site columns of
  * writeInfos (CoETools.cpp:507-510).  n_out is site-major [S][B] (mapping[i] is site i's
  * branch vector, Statistics.h:154-160); all outputs nullable.  The vectors stay resident
- * on the device for cmb_pairs / cmb_distance_matrix. */
+ * on the device for cmb_pairs / cmb_distance_matrix.
+ * With EVERY output NULL the mapping is only enqueued (on a side stream, so that work enqueued next -- the
+ * null replicates -- overlaps it: a 5000-site mapping is one latency-bound tree walk on a few SMs); the first
+ * call that needs it waits for it and reports a saturated alignment (likelihood 0 at some site,
+ * CoETools.cpp:233-262) then.  With any output requested the call completes the mapping and fails on
+ * saturated sites after filling the per-site outputs. */
 int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_t* rate_class,
             double* loglik);
 

@@ -241,3 +241,27 @@ def test_pair_columns_in_two_calls_overlapping_the_null(ctx):
         ctx.map()
         ctx.pairs_resident("correlation", use_null=False, columns=0x04)
         ctx.pairs_fetch(0, bufs[0])
+
+
+def test_deferred_mapping_overlaps_and_equals_the_blocking_one(ctx):
+    """cmb_map with every output NULL is only enqueued (side stream); the null and the pair table computed
+    after it equal the blocking flow bit for bit, and a saturated alignment is reported by the first call
+    that needs the mapping."""
+    c = _case(S=211)
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(c["codes"], c["code_mask"])
+    ctx.map()
+    ctx.null_intra("correlation", 5, 3, 160, K=5)
+    ref, k = ctx.pairs("correlation", use_null=True)
+    ctx.set_alignment(c["codes"], c["code_mask"])
+    ctx.map_async()
+    ctx.null_intra("correlation", 5, 3, 160, K=5)      # nmax = -1: completes the mapping for its max norm
+    got, k2 = ctx.pairs("correlation", use_null=True)
+    assert k == k2
+    for name in ctx.COLS:
+        assert _eq(got[name], ref[name]), name
+    ctx.map_async(); ctx.map_async()                    # re-enqueueing waits for the one in flight
+    with pytest.raises(RuntimeError):                   # the null was binned with the previous mapping's max norm
+        ctx.pairs("correlation", use_null=True)
+    got, _ = ctx.pairs("correlation", use_null=False)
+    assert _eq(got["stat"], ref["stat"])

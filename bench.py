@@ -142,6 +142,10 @@ def cpu_sample(cfg, w, aln_codes=None, sample_sites=800, sample_ram=3000, seed=0
     pr = O.pairs(cfg["statistic"], m["n"], m["norm"], m["post_rate"], m["rate_class"], null=(K, nmax, offs, srt))
     t_pairs = time.perf_counter() - t0
     n_pairs_s = len(pr["i"])
+    sub = min(sample_sites, 200)      # statistic alone on a subset: splits the pair cost into base + p-value scan
+    t0 = time.perf_counter()
+    O.pairs(cfg["statistic"], m["n"][:sub], m["norm"][:sub], m["post_rate"][:sub], m["rate_class"][:sub])
+    per_pair_base = (time.perf_counter() - t0) / max(1, sub * (sub - 1) // 2)
     per_null_site = (t_sim + t_null) / (2 * sample_ram)   # simulate + map (+ paired stat) per simulated site
     per_obs_site = t_map / sample_sites
     per_obs_pair = t_pairs / max(1, n_pairs_s)
@@ -149,13 +153,46 @@ def cpu_sample(cfg, w, aln_codes=None, sample_sites=800, sample_ram=3000, seed=0
     total_pairs = S * (S - 1) // 2 + RC * R
     sample_pairs = n_pairs_s + sample_ram
     sample_time = t_sim + t_null + t_map + t_pairs
-    return dict(value=total_pairs / full, full_step_seconds=full, sample_seconds=sample_time,
+    mean_nsim = float(np.mean(pr["nsim"])) if n_pairs_s else 1.0
+    fit = dict(per_null_site=per_null_site, per_obs_site=per_obs_site, per_pair_base=per_pair_base,
+               per_pair_scan_per_sample=max(0.0, per_obs_pair - per_pair_base) / max(1.0, mean_nsim))
+    return dict(value=total_pairs / full, full_step_seconds=full, sample_seconds=sample_time, fit=fit,
                 sample_pairs_per_s=sample_pairs / sample_time,
                 sample=("oracle port, 1 thread: simulate+map+pair %d null site pairs (%.2fs), map %d observed sites "
                         "(%.2fs), score their %d pairs with p-value scan against a %d-sample null (%.2fs); "
                         "extrapolated linearly to %d null pairs + %d observed sites + %d pairs"
                         % (sample_ram, t_sim + t_null, sample_sites, t_map, n_pairs_s, RC * R, t_pairs, RC * R, S,
                            S * (S - 1) // 2)))
+
+
+def cpu_validation(cfg, w, fit, sites=400, rep_cpu=10, rep_ram=1000, seed=777):
+    """One COMPLETE reduced-size job on the CPU oracle, nothing extrapolated: map `sites` observed sites, simulate +
+    map + score rep_cpu x rep_ram null pairs, bin + sort, score all pairs with p-values -- timed, and compared with
+    what the linear model fitted on the bounded sample (`fit` = cpu_sample's per-unit costs) predicts for it."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_binding as O
+    K = cfg["null_bins"]
+    t0 = time.perf_counter()
+    aln, _ = O.simulate(w["parent"], w["brlen"], w["Q"], w["pi"], w["rates"], w["probs"], cfg["aln_seed"], 0, sites)
+    m = O.map_sites(w["parent"], w["brlen"], w["Q"], w["pi"], w["rates"], w["probs"], aln, w["code_mask"])
+    s1 = np.stack([O.simulate(w["parent"], w["brlen"], w["Q"], w["pi"], w["rates"], w["probs"], seed, (2 * i) * rep_ram, rep_ram)[0]
+                   for i in range(rep_cpu)])
+    s2 = np.stack([O.simulate(w["parent"], w["brlen"], w["Q"], w["pi"], w["rates"], w["probs"], seed, (2 * i + 1) * rep_ram, rep_ram)[0]
+                   for i in range(rep_cpu)])
+    nmax = float(m["norm"].max())
+    nl = O.null_intra(w["parent"], w["brlen"], w["Q"], w["pi"], w["rates"], w["probs"], cfg["statistic"], s1, s2, K, nmax)
+    pr = O.pairs(cfg["statistic"], m["n"], m["norm"], m["post_rate"], m["rate_class"],
+                 null=(K, nmax, nl["bin_offsets"], nl["sorted"]))
+    measured = time.perf_counter() - t0
+    n_pairs = len(pr["i"])
+    # the reference counts #{sim < stat} by scanning the sorted bin (CoETools.cpp:712-716): the scan term scales
+    # with the samples per bin
+    scan = fit["per_pair_scan_per_sample"] * float(np.mean(pr["nsim"])) if n_pairs else 0.0
+    predicted = (fit["per_null_site"] * 2 * rep_cpu * rep_ram + fit["per_obs_site"] * (sites + 0) +
+                 (fit["per_pair_base"] + scan) * n_pairs)
+    return dict(job="%d observed sites, %dx%d null, %d pairs with p-values, complete (not extrapolated)"
+                    % (sites, rep_cpu, rep_ram, n_pairs), measured_seconds=measured, predicted_seconds=predicted,
+                measured_over_predicted=measured / predicted, pairs_per_s=(n_pairs + rep_cpu * rep_ram) / measured)
 
 
 def _cpu_worker(job):
@@ -466,7 +503,8 @@ def run_ours(args, cfg):
                 line["cpu_baseline"] = dict(value=cb["value"], unit="pairs/s", cores=cb["cores"], kind="port", sample=cb["sample"],
                                             host_cores=os.cpu_count(), sample_pairs_per_s=cb["sample_pairs_per_s"],
                                             one_thread_value=one["value"],
-                                            one_thread_sample_pairs_per_s=one["sample_pairs_per_s"])
+                                            one_thread_sample_pairs_per_s=one["sample_pairs_per_s"],
+                                            validation=cpu_validation(cfg, w, one["fit"]))
             print(json.dumps(line), flush=True)
         ctx.close()
     if world > 1:

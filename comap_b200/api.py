@@ -25,7 +25,7 @@ SYMBOLS = [
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
     "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates", "cmb_set_async", "cmb_set_mi_threshold",
     "cmb_comm_unique_id", "cmb_comm_init", "cmb_comm_init_all", "cmb_comm_set", "cmb_comm_destroy", "cmb_comm_rank",
-    "cmb_comm_group_start", "cmb_comm_group_end", "cmb_null_intra_sharded",
+    "cmb_comm_group_start", "cmb_comm_group_end", "cmb_null_intra_sharded", "cmb_set_continuous_rates",
 ]
 
 
@@ -209,6 +209,11 @@ class Context:
         self._chk(self.lib.cmb_null_intra_sharded(self.h, STAT[stat], C.c_uint64(seed), rep_cpu, rep_ram,
                                                   int(weighted_classes), K, C.c_double(nmax), _d(raw)))
         return raw
+
+    def set_continuous_rates(self, kind, alpha=1.0, p_invariant=0.0):
+        """simulations.continuous: kind 'off' | 'constant' | 'gamma' | 'invariant' (+ gamma)."""
+        k = {"off": 0, "constant": 1, "gamma": 2, "invariant": 3}[kind]
+        self._chk(self.lib.cmb_set_continuous_rates(self.h, k, C.c_double(alpha), C.c_double(p_invariant)))
 
     def set_async(self, on=True):
         """null_intra(K=0) returns without waiting for the device (order consumers with sync())."""

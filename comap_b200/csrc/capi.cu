@@ -98,6 +98,17 @@ void Context::ensure_streams() {
     build_sim_stream(os, tree, tables);
     sim_stream.upload(os, stream);
   }
+  {
+    std::vector<double> ev, R, L, spec;
+    build_spectrum(A, Q.data(), pi.data(), ev, R, L);
+    spec.insert(spec.end(), ev.begin(), ev.end());
+    spec.insert(spec.end(), R.begin(), R.end());
+    spec.insert(spec.end(), L.begin(), L.end());
+    spec.insert(spec.end(), tree.brlen.begin(), tree.brlen.end());
+    d_spec.reserve(sizeof(double) * spec.size());
+    CMB_CUDA(cudaMemcpyAsync(d_spec.p, spec.data(), sizeof(double) * spec.size(), cudaMemcpyHostToDevice, stream));
+    CMB_CUDA(cudaStreamSynchronize(stream));
+  }
   d_pi.reserve(sizeof(double) * A);
   d_rates.reserve(sizeof(double) * C);
   d_probs.reserve(sizeof(double) * C);
@@ -119,6 +130,8 @@ MapModel Context::map_model() const {
   m.pi = d_pi.as<double>();
   m.rates = d_rates.as<double>();
   m.probs = d_probs.as<double>();
+  m.cont_kind = cont_kind; m.cont_alpha = cont_alpha; m.cont_pinv = cont_pinv;
+  m.spec = d_spec.as<double>();
   return m;
 }
 
@@ -311,7 +324,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
                     &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm,
-                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part, &c.k1_part_obs};
+                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part, &c.k1_part_obs, &c.d_spec};
   for (DevBuf* b : bufs) b->release();
   c.down_stream.release();
   c.up_stream.release();
@@ -521,6 +534,15 @@ int cmb_set_mi_threshold(cmb_ctx* ctx, double threshold) {
   ctx->c.pairs_rows = -1; // resident Stat columns were scored with the previous threshold
   for (auto& o : ctx->c.pairs_col_off) o = -1;
   return 0;
+}
+
+int cmb_set_continuous_rates(cmb_ctx* ctx, int32_t kind, double alpha, double p_invariant) {
+  CMB_TRY
+  if (kind < 0 || kind > 3) fail("cmb_set_continuous_rates: kind must be 0 (off), 1 (constant), 2 (gamma) or 3 (invariant + gamma)");
+  if (kind >= 2 && !(alpha > 0.)) fail("cmb_set_continuous_rates: alpha must be positive");
+  if (kind == 3 && !(p_invariant >= 0. && p_invariant < 1.)) fail("cmb_set_continuous_rates: p must be in [0, 1)");
+  ctx->c.cont_kind = kind; ctx->c.cont_alpha = alpha; ctx->c.cont_pinv = p_invariant;
+  CMB_CATCH
 }
 
 int cmb_set_async(cmb_ctx* ctx, int32_t on) {

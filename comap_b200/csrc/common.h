@@ -47,6 +47,9 @@ void build_model_tables(ModelTables& mt, int A, const double* Q, const double* p
                         const double* rates, const double* probs, int count_method,
                         const double* weights, int B, const double* brlen);
 
+// eigen-decomposition of a reversible generator, Q = R diag(ev) L (tables.cpp); R, L row-major A x A
+void build_spectrum(int A, const double* Q, const double* pi, std::vector<double>& ev, std::vector<double>& R, std::vector<double>& L);
+
 // ---------------------------------------------------------------- tree + op streams
 constexpr int kMaxStack = 20; // per-thread stack depth; log2(#leaves)+2 suffices
 constexpr int kChunkSites = 128; // sites per CTA / per partial chunk of the tensor-core K1 kernels (A = 4)

@@ -42,6 +42,9 @@ struct Context {
   // device-resident model + op streams
   DevBuf d_code_mask, d_pi, d_rates, d_probs;
   DevStream down_stream, up_stream, sim_stream;
+  int cont_kind = 0;             // continuous-rate simulation (cmb_set_continuous_rates)
+  double cont_alpha = 1., cont_pinv = 0.;
+  DevBuf d_spec;                 // ev | R | L | brlen for it
   bool streams_ready = false;
   bool protein_mma = false;      // A = 20 on the tensor-core kernels (k1_mma20.cu); else the thread-per-site ones
   DevBuf k1_part;                // their per-class partial outputs [C][B][n_pad]

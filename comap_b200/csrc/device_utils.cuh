@@ -147,4 +147,37 @@ __host__ __device__ __forceinline__ void philox_u01x2(uint64_t seed, uint64_t si
   u1 = (double)((((uint64_t)c[2] << 32) | c[3]) >> 11) * (1.0 / 9007199254740992.0);
 }
 
+// Continuous site rate (simulations.continuous = yes; NonHomogeneousSequenceSimulator::enableContinuousRates,
+// CoMap.cpp:209-219 -> rDist->randC()): Gamma(alpha, beta = alpha) by Marsaglia & Tsang's squeeze method with
+// Box-Muller normals, every uniform from the site's Philox stream (node = root, tags 98.. ), so a site's rate
+// depends only on (seed, site).  kind: 1 constant rate 1, 2 gamma, 3 invariant (rate 0 with probability p_inv)
+// + gamma / (1 - p_inv).
+__host__ __device__ __forceinline__ double continuous_rate(int kind, double alpha, double p_inv, uint64_t seed,
+                                                           uint64_t site, uint32_t node) {
+  if (kind == 1) return 1.;
+  double scale = 1.;
+  if (kind == 3) {
+    if (philox_u01(seed, site, node, 98) < p_inv) return 0.;
+    scale = 1. / (1. - p_inv);
+  }
+  double a = alpha, boost = 1.;
+  if (a < 1.) { // G(a) = G(a + 1) U^(1/a)
+    boost = pow(1. - philox_u01(seed, site, node, 99), 1. / a);
+    a += 1.;
+  }
+  const double d = a - 1. / 3., c = 1. / sqrt(9. * d);
+  double g = d;
+  for (uint32_t k = 0; k < 64; k++) {
+    double u1, u2;
+    philox_u01x2(seed, site, node, 100 + 2 * k, u1, u2);
+    const double x = sqrt(-2. * log(1. - u1)) * cos(6.283185307179586 * u2);
+    double v = 1. + c * x;
+    if (v <= 0.) continue;
+    v = v * v * v;
+    const double u = 1. - philox_u01(seed, site, node, 101 + 2 * k);
+    if (u < 1. - 0.0331 * (x * x) * (x * x) || log(u) < 0.5 * x * x + d * (1. - v + log(v))) { g = d * v; break; }
+  }
+  return g * boost / alpha * scale;
+}
+
 } // namespace cmb

@@ -119,6 +119,93 @@ __global__ void __launch_bounds__(NT) k3_simulate(SimParams p) {
   }
 }
 
+// Continuous rates: the site's rate r is drawn once (continuous_rate), the transition probabilities of a branch
+// are P(d_b r) = R exp(ev d_b r) L evaluated for the parent's state only (A exponentials + A^2 multiply-adds per
+// branch), the child state is drawn by the same linear inverse-CDF and the same Philox blocks as the discrete walk.
+struct ContParams { int kind; double alpha, p_inv; const double* spec; int n_nodes; };
+
+template <int AMAX>
+__global__ void __launch_bounds__(NT) k3_simulate_cont(SimParams p, ContParams cp) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int A = p.A, AA = A * A;
+  double* sp = reinterpret_cast<double*>(smem);          // ev | R | L
+  for (int i = threadIdx.x; i < A + 2 * AA; i += NT) sp[i] = __ldg(cp.spec + i);
+  const double* ev = sp;
+  const double* R = sp + A;
+  const double* L = sp + A + AA;
+  const double* brlen = cp.spec + A + 2 * AA;
+  unsigned char* ring = smem + ((sizeof(double) * (A + 2 * AA) + 127) & ~size_t(127));
+  const int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x;
+  const bool live = idx < p.n;
+  const int64_t ii = live ? idx : p.n - 1;
+  const uint64_t site = (uint64_t)(p.base + (ii / p.group) * p.stride + ii % p.group);
+  ChunkStream cs{p.src, p.off, p.bytes, p.n_chunks, p.cap, nullptr, nullptr};
+  cs.start(ring + 128, reinterpret_cast<uint64_t*>(ring));   // includes the __syncthreads that publishes sp
+  int st;
+  {
+    double r = philox_u01(p.seed, site, (uint32_t)p.root_node, 0);
+    st = A - 1;
+    double cpi = 0.;
+    bool done = false;
+    for (int i = 0; i < A; i++) {
+      cpi += __ldg(p.pi + i);
+      if (!done && r <= cpi) { st = i; done = true; }
+    }
+  }
+  const double rate = continuous_rate(cp.kind, cp.alpha, cp.p_inv, p.seed, site, (uint32_t)p.root_node);
+  if (live && p.classes) p.classes[idx] = -1;
+  auto draw = [&](int x, int node, double u) {
+    if (rate == 0.) return x;                       // invariant site: P = I
+    const double t = __ldg(brlen + node) * rate;
+    double ek[AMAX];
+#pragma unroll
+    for (int k = 0; k < AMAX; k++) ek[k] = k < A ? R[x * A + k] * exp(ev[k] * t) : 0.;
+    double cum = 0.;
+    int y = A - 1;
+    bool done = false;
+    for (int j = 0; j < A; j++) {
+      double pj = 0.;
+#pragma unroll
+      for (int k = 0; k < AMAX; k++) if (k < A) pj += ek[k] * L[k * A + j];
+      cum += pj;
+      if (!done && u < cum) { y = j; done = true; }
+    }
+    return y;
+  };
+  uint8_t stk[kMaxStack];
+  int spt = 0;
+  const size_t tab = (size_t)p.C * AA;
+  for (uint32_t k = 0; k < p.n_chunks; k++) {
+    const unsigned char* rp = cs.wait(k);
+    const uint32_t nrec = __ldg(p.nrec + k);
+    for (uint32_t r = 0; r < nrec; r++) {
+      const int4 h0 = *reinterpret_cast<const int4*>(rp);
+      const int4 h1 = *reinterpret_cast<const int4*>(rp + 16);
+      const uint32_t flags = (uint32_t)h0.x;
+      rp += (32 + 2 * tab * sizeof(double) + 15) & ~size_t(15);
+      int sa = st, sb = st;
+      double u0 = 0., u1 = 0.;
+      if (h0.w >= 0) {
+        philox_u01x2(p.seed, site, (uint32_t)h1.w, 2u + ((uint32_t)h1.y >> 1), u0, u1);
+        sa = draw(st, h0.w, (h1.y & 1) ? u1 : u0);
+      }
+      if (h1.x >= 0) {
+        if (h0.w < 0 || (h1.y >> 1) != (h1.z >> 1))
+          philox_u01x2(p.seed, site, (uint32_t)h1.w, 2u + ((uint32_t)h1.z >> 1), u0, u1);
+        sb = draw(st, h1.x, (h1.z & 1) ? u1 : u0);
+      }
+      if ((flags & kUpTipA) && live) p.tips[(size_t)h0.y * p.n_pad + idx] = (uint8_t)sa;
+      if ((flags & kUpTipB) && live) p.tips[(size_t)h0.z * p.n_pad + idx] = (uint8_t)sb;
+      if (flags & kUpTakeA) {
+        if (flags & kUpPush) stk[spt++] = (uint8_t)sb;
+        st = sa;
+      } else if (flags & kUpTakeB) st = sb;
+      else if (flags & kUpPop) st = stk[--spt];
+    }
+    cs.release(k);
+  }
+}
+
 } // namespace
 
 void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,
@@ -131,6 +218,20 @@ void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64
   p.base = base; p.group = group; p.stride = stride; p.n = n; p.n_pad = n_pad;
   p.pi = m.pi; p.probs = m.probs; p.tips = tips; p.classes = classes;
   size_t smem = 128 + 2 * (size_t)s.cap;
+  if (m.cont_kind != 0) {
+    if (!m.spec) fail("internal: continuous simulation without the generator's spectrum");
+    ContParams cp{m.cont_kind, m.cont_alpha, m.cont_pinv, m.spec, 0};
+    smem += (sizeof(double) * (m.A + 2 * (size_t)m.A * m.A) + 127) & ~size_t(127);
+    if (m.A <= 4) {
+      CMB_CUDA(cudaFuncSetAttribute(k3_simulate_cont<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k3_simulate_cont<4><<<(unsigned)((n + NT - 1) / NT), NT, smem, st>>>(p, cp);
+    } else if (m.A <= 20) {
+      CMB_CUDA(cudaFuncSetAttribute(k3_simulate_cont<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      k3_simulate_cont<20><<<(unsigned)((n + NT - 1) / NT), NT, smem, st>>>(p, cp);
+    } else fail("continuous simulation supports up to 20 states");
+    CMB_CUDA(cudaGetLastError());
+    return;
+  }
   CMB_CUDA(cudaFuncSetAttribute(k3_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k3_simulate<<<(unsigned)((n + NT - 1) / NT), NT, smem, st>>>(p);
   CMB_CUDA(cudaGetLastError());

@@ -44,6 +44,10 @@ struct MapModel {            // device-resident model constants
   const double* pi = nullptr;          // [A]
   const double* rates = nullptr;       // [C]
   const double* probs = nullptr;       // [C]
+  // continuous-rate simulation (cmb_set_continuous_rates): 0 = discrete classes
+  int cont_kind = 0;
+  double cont_alpha = 1., cont_pinv = 0.;
+  const double* spec = nullptr;        // device: ev[A] | R[A][A] | L[A][A] | brlen[n_nodes]  (Q = R diag(ev) L)
 };
 
 void check_map_support(int A, int C); // throws when no kernel is built for (A, C)

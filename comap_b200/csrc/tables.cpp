@@ -161,6 +161,11 @@ void decomposition_numerator(const Spectrum& sp, const double* Q, const double* 
 
 } // namespace
 
+void build_spectrum(int A, const double* Q, const double* pi, std::vector<double>& ev, std::vector<double>& R, std::vector<double>& L) {
+  Spectrum sp(A, Q, pi);
+  ev = sp.ev; R = sp.R; L = sp.L;
+}
+
 void build_model_tables(ModelTables& mt, int A, const double* Q, const double* pi, int C,
                         const double* rates, const double* probs, int count_method,
                         const double* weights, int B, const double* brlen) {

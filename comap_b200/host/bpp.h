@@ -98,6 +98,9 @@ Model make_model(const std::string& desc, const Alphabet& alpha, const std::stri
 struct RateDist {
   std::string name;
   std::vector<double> rates, probs;
+  // the continuous distribution behind the classes (simulations.continuous = yes): 1 constant, 2 gamma, 3 invariant + gamma
+  int cont_kind = 1;
+  double alpha = 1., p_inv = 0.;
 };
 RateDist make_rate_distribution(const std::string& desc);
 // nijt=...(weight=Diff(index1=Volume, symmetrical=no)): AlphabetIndex2 weights of the weighted

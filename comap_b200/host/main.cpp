@@ -456,13 +456,15 @@ int main(int argc, char** argv) {
     (void)B;
     const bool weighted_classes = get_bool(P, "simulations.weighted_classes", false);
     display_result("Rate distribution for simulations", get_bool(P, "simulations.continuous", false) ? "continuous" : "discrete");
-    if (get_bool(P, "simulations.continuous", false))
-      throw Error("simulations.continuous=yes is not available in this build (discrete rate classes only)");
+    const bool continuous_sim = get_bool(P, "simulations.continuous", false);
+    if (continuous_sim && in.rdist.cont_kind == 0)
+      throw Error("simulations.continuous=yes is available for Constant, Gamma and Invariant(dist=Gamma) rate distributions");
 
     display_message("\n\n-*- Get substitution vectors -*-\n");
     Mapped m1 = map_data_set(in, P, "");
     S = (int64_t)in.cols.size(); // saturated sites may have been removed
     cmb_ctx* ctx = m1.ctx;
+    if (continuous_sim) chk(cmb_set_continuous_rates(ctx, in.rdist.cont_kind, in.rdist.alpha, in.rdist.p_inv));
     const int n_gpus = (int)get_int(P, "comap_b200.gpus", 1);
     if (n_gpus < 1) throw Error("comap_b200.gpus must be at least 1");
     std::vector<cmb_ctx*> ctxs{ctx};
@@ -478,6 +480,7 @@ int main(int argc, char** argv) {
         chk(cmb_set_alignment(ctxs[r], S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
         Procedure st = parse_procedure(get_string(P, "statistic", "Correlation"));
         if (st.name == "MI") chk(cmb_set_mi_threshold(ctxs[r], get_double(st.args, "threshold", 0.99)));
+        if (continuous_sim) chk(cmb_set_continuous_rates(ctxs[r], in.rdist.cont_kind, in.rdist.alpha, in.rdist.p_inv));
         chk(cmb_map(ctxs[r], nullptr, nullptr, nullptr, nullptr, nullptr));
       });
       if (get_path(P, "input.vectors.file", "none") != "none")
@@ -503,6 +506,10 @@ int main(int argc, char** argv) {
         prepare(in2, argv[0], &P2, &in.tree);
         display_message("\n... and get its substitution vectors.\n");
         Mapped m2 = map_data_set(in2, P2, "2");
+        if (continuous_sim) {
+          if (in2.rdist.cont_kind == 0) throw Error("simulations.continuous=yes: unsupported rate distribution for data set 2");
+          chk(cmb_set_continuous_rates(m2.ctx, in2.rdist.cont_kind, in2.rdist.alpha, in2.rdist.p_inv));
+        }
         const int64_t S2 = (int64_t)in2.cols.size();
         display_message("\n\n-*- Compute statistics -*-\n");
         display_message("Compares data set 1 with data set 2.");

@@ -221,6 +221,7 @@ RateDist make_rate_distribution(const std::string& desc) {
       r.rates.push_back((double)k * (e[i + 1] - e[i]));
       r.probs.push_back(1. / k);
     }
+    r.cont_kind = 2; r.alpha = alpha;
     return r;
   }
   if (n == "invariant") {
@@ -235,6 +236,8 @@ RateDist make_rate_distribution(const std::string& desc) {
       r.rates.push_back(d.rates[i] / (1. - pi));
       r.probs.push_back(d.probs[i] * (1. - pi));
     }
+    r.cont_kind = d.cont_kind == 2 ? 3 : (pi > 0. ? 0 : 1); // Invariant + Constant has no continuous sampler here
+    r.alpha = d.alpha; r.p_inv = pi;
     return r;
   }
   throw Error("rate distribution '" + desc + "' is not supported (Constant, Gamma, Invariant)");

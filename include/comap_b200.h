@@ -123,6 +123,14 @@ int cmb_load_vectors(cmb_ctx* ctx, const double* n_in, double* norm);
 int cmb_simulate(cmb_ctx* ctx, uint64_t seed, int64_t first_site, int64_t n,
                  int32_t weighted_classes, uint8_t* states, int32_t* classes);
 
+/* simulations.continuous = yes (CoMap.cpp:146,209-219: NonHomogeneousSequenceSimulator::enableContinuousRates):
+ * every later simulation (cmb_simulate, the null distributions, the clustering null, the candidates sampler)
+ * draws one rate per site from the continuous distribution -- kind 1 Constant, 2 Gamma(alpha, beta = alpha),
+ * 3 Invariant(p) + Gamma(alpha) / (1 - p) -- and evolves the site with P(d_b r) computed on the fly, instead of
+ * picking one of the discrete classes; classes are then reported as -1.  kind 0 restores the discrete classes.
+ * The mapping of the simulated sites uses the discrete model either way, as upstream. */
+int cmb_set_continuous_rates(cmb_ctx* ctx, int32_t kind, double alpha, double p_invariant);
+
 /* Replaces AnalysisTools::getNullDistributionIntraDR (AnalysisTools.cpp:564-658) + the
  * per-bin sort (CoETools.cpp:650-652): rep_cpu x { simulate 2 x rep_ram sites, map both,
  * paired statistic j<->j, bin by Nmin in Domain(0, nmax, K) }.  Outer replicates

@@ -813,6 +813,88 @@ int orc_simulate(int n_nodes, const int32_t* parent, const double* brlen, int A,
   return 0;
 }
 
+/* Continuous site rates (simulations.continuous = yes; CoMap.cpp:146,209-219 -> NonHomogeneousSequenceSimulator::
+ * enableContinuousRates -> rDist->randC()): one rate per site, Gamma(alpha, beta = alpha) by Marsaglia & Tsang with
+ * Box-Muller normals from the site's Philox stream (node = root, tags 98..), P(d_b r) evaluated per branch from the
+ * generator's spectrum, child states by the same inverse-CDF and Philox blocks as orc_simulate.  The reference's
+ * generator is unseeded, so only the distribution is common ground: parity unpinned. */
+static double continuous_rate(int kind, double alpha, double p_inv, uint64_t seed, uint64_t site, uint32_t node) {
+  if (kind == 1) return 1.;
+  double scale = 1.;
+  if (kind == 3) {
+    if (philox_u01(seed, site, node, 98) < p_inv) return 0.;
+    scale = 1. / (1. - p_inv);
+  }
+  double a = alpha, boost = 1.;
+  if (a < 1.) {
+    boost = pow(1. - philox_u01(seed, site, node, 99), 1. / a);
+    a += 1.;
+  }
+  const double d = a - 1. / 3., c = 1. / sqrt(9. * d);
+  double g = d;
+  for (uint32_t k = 0; k < 64; k++) {
+    double u1, u2;
+    philox_u01x2(seed, site, node, 100 + 2 * k, &u1, &u2);
+    const double x = sqrt(-2. * log(1. - u1)) * cos(6.283185307179586 * u2);
+    double v = 1. + c * x;
+    if (v <= 0.) continue;
+    v = v * v * v;
+    const double u = 1. - philox_u01(seed, site, node, 101 + 2 * k);
+    if (u < 1. - 0.0331 * (x * x) * (x * x) || log(u) < 0.5 * x * x + d * (1. - v + log(v))) { g = d * v; break; }
+  }
+  return g * boost / alpha * scale;
+}
+
+int orc_simulate_continuous(int n_nodes, const int32_t* parent, const double* brlen, int A, const double* Q,
+                            const double* pi, int kind, double alpha, double p_inv, uint64_t seed,
+                            int64_t first_site, int64_t n, uint8_t* states, double* rates_out) {
+  tree_t tr;
+  spectral_t sp;
+  if (tree_init(&tr, n_nodes, parent, brlen)) { tree_free(&tr); return -1; }
+  if (spectral_init(&sp, A, Q, pi)) { tree_free(&tr); return -1; }
+  uint8_t* st = malloc(tr.n);
+  int* rank = calloc(tr.n, sizeof(int));
+  {
+    int* seen = calloc(tr.n, sizeof(int));
+    for (int v = 0; v < tr.n - 1; v++) rank[v] = seen[tr.parent[v]]++;
+    free(seen);
+  }
+  double* ek = malloc(sizeof(double) * A);
+  for (int64_t j = 0; j < n; j++) {
+    uint64_t site = (uint64_t)(first_site + j);
+    double r = philox_u01(seed, site, (uint32_t)tr.root, 0);
+    int x0 = A - 1;
+    double cp = 0.;
+    for (int i = 0; i < A; i++) { cp += pi[i]; if (r <= cp) { x0 = i; break; } }
+    const double rate = continuous_rate(kind, alpha, p_inv, seed, site, (uint32_t)tr.root);
+    if (rates_out) rates_out[j] = rate;
+    st[tr.root] = (uint8_t)x0;
+    for (int v = tr.n - 2; v >= 0; v--) {
+      int x = st[tr.parent[v]];
+      double u0, u1;
+      philox_u01x2(seed, site, (uint32_t)tr.parent[v], 2u + ((uint32_t)rank[v] >> 1), &u0, &u1);
+      double u = (rank[v] & 1) ? u1 : u0;
+      int y = x;
+      if (rate != 0.) {
+        const double t = tr.len[v] * rate;
+        for (int k = 0; k < A; k++) ek[k] = sp.R[x * A + k] * exp(sp.ev[k] * t);
+        double cum = 0.;
+        y = A - 1;
+        for (int jj = 0; jj < A; jj++) {
+          double pj = 0.;
+          for (int k = 0; k < A; k++) pj += ek[k] * sp.L[k * A + jj];
+          cum += pj;
+          if (u < cum) { y = jj; break; }
+        }
+      }
+      st[v] = (uint8_t)y;
+      if (tr.leaf_row[v] >= 0) states[(size_t)tr.leaf_row[v] * n + j] = (uint8_t)y;
+    }
+  }
+  free(ek); free(rank); free(st); spectral_free(&sp); tree_free(&tr);
+  return 0;
+}
+
 /* ------------------------------------------------------------------------------------ */
 /* null distribution  (AnalysisTools.cpp:564-658 + sort at CoETools.cpp:650-652)         */
 /* ------------------------------------------------------------------------------------ */

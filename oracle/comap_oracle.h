@@ -143,4 +143,9 @@ int orc_groups(int dist_id, int64_t S, int B, const double* n, const double* nor
 #ifdef __cplusplus
 }
 #endif
+/* simulations.continuous = yes: one continuous rate per site (kind 1 constant, 2 gamma, 3 invariant + gamma) */
+int orc_simulate_continuous(int n_nodes, const int32_t* parent, const double* brlen, int A, const double* Q,
+                            const double* pi, int kind, double alpha, double p_inv, uint64_t seed,
+                            int64_t first_site, int64_t n, uint8_t* states, double* rates_out);
+
 #endif

@@ -186,6 +186,19 @@ def simulate(parent, brlen, Q, pi, rates, probs, seed, first_site, n, weighted_c
     return states, cls
 
 
+def simulate_continuous(parent, brlen, Q, pi, kind, alpha, p_inv, seed, first_site, n):
+    """simulations.continuous = yes: (states [T][n], rate per site)."""
+    ta, keep1 = _tree_args(parent, brlen)
+    Q, pi = _f64(Q), _f64(pi)
+    from comap_b200.synthetic import n_leaves_of
+    T = n_leaves_of(np.asarray(parent))
+    states = np.empty((T, n), dtype=np.uint8); rates = np.empty(n)
+    k = {"constant": 1, "gamma": 2, "invariant": 3}[kind]
+    _chk(lib().orc_simulate_continuous(*ta, len(pi), _d(Q), _d(pi), k, C.c_double(alpha), C.c_double(p_inv),
+                                       C.c_uint64(seed), C.c_int64(first_site), C.c_int64(n), _p(states, C.c_uint8), _d(rates)))
+    return states, rates
+
+
 def null_intra(parent, brlen, Q, pi, rates, probs, stat_name, sim1, sim2, K, nmax,
                method="uniformization", weights=None):
     ta, keep1 = _tree_args(parent, brlen)

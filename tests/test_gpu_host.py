@@ -349,3 +349,19 @@ def test_two_gpus_write_the_same_tables(myo):
     run(tmp, *COMMON, *clu, "clustering.output.groups.file=g2.txt", "clustering.null.output.file=n2.txt", "comap_b200.gpus=2")
     for a, b in (("g1.txt", "g2.txt"), ("n1.txt", "n2.txt")):
         assert open(os.path.join(tmp, a), "rb").read() == open(os.path.join(tmp, b), "rb").read(), a
+
+
+def test_continuous_simulations_from_the_command_line(myo):
+    """simulations.continuous = yes (CoMap.cpp:146) is accepted for Gamma rate distributions and changes the null."""
+    tmp, golden = myo
+    pair = ["analysis=pairwise", "statistic=Correlation", "statistic.null=yes", "statistic.null.nb_rep_CPU=3",
+            "statistic.null.nb_rep_RAM=200", "statistic.null.nb_rate_classes=3"]
+    out = run(tmp, *COMMON, *pair, "statistic.output.file=d.txt", "statistic.null.output.file=d_null.txt")
+    assert "discrete" in out
+    out = run(tmp, *COMMON, *pair, "statistic.output.file=c.txt", "statistic.null.output.file=c_null.txt",
+              "simulations.continuous=yes")
+    assert "continuous" in out
+    hd, rd = table(os.path.join(tmp, "d_null.txt")); hc, rc = table(os.path.join(tmp, "c_null.txt"))
+    assert hd == hc and len(rd) == len(rc) == 600 and rd != rc
+    hs, rs = table(os.path.join(tmp, "c.txt"))
+    assert hs[-2:] == ["PValue", "Nsim"] and len(rs) == 129 * 128 // 2

@@ -265,3 +265,44 @@ def test_deferred_mapping_overlaps_and_equals_the_blocking_one(ctx):
         ctx.pairs("correlation", use_null=True)
     got, _ = ctx.pairs("correlation", use_null=False)
     assert _eq(got["stat"], ref["stat"])
+
+
+@pytest.mark.parametrize("kind,alpha,pinv", [("gamma", 0.5, 0.0), ("gamma", 2.0, 0.0), ("invariant", 1.0, 0.3), ("constant", 1.0, 0.0)])
+def test_continuous_rate_simulation_vs_oracle(ctx, kind, alpha, pinv):
+    """simulations.continuous = yes (CoMap.cpp:146,209-219): one continuous rate per site, P(d r) on the fly.
+    Device and oracle run the same sampler on the same Philox stream; their exp / log / cos differ in the last
+    bits, so a draw that lands within an ulp of a cumulative probability may differ: at most 1 column in 1000."""
+    c = _case(T=40, S=10)
+    _setup(ctx, c)
+    try:
+        ctx.set_continuous_rates(kind, alpha, pinv)
+        a, cls = ctx.simulate(321, 7, 4000)
+        b, rates = O.simulate_continuous(c["parent"], c["brlen"], c["Q"], c["pi"], kind, alpha, pinv, 321, 7, 4000)
+        assert np.all(cls == -1)
+        differing = (a != b).any(axis=0).mean()
+        assert differing <= 1e-3, differing
+        w, _ = ctx.simulate(321, 1007, 100)          # counter based: a window equals the same sites alone
+        assert np.array_equal(w, a[:, 1000:1100])
+        # the null distribution runs on the continuous simulator and equals the exported alignments' null
+        raw = ctx.null_intra("correlation", 5, 2, 128, K=3, nmax=2.0, want_raw=True)
+        s1 = np.stack([ctx.simulate(5, (2 * i) * 128, 128)[0] for i in range(2)])
+        s2 = np.stack([ctx.simulate(5, (2 * i + 1) * 128, 128)[0] for i in range(2)])
+        raw2 = ctx.null_intra_from_alignments("correlation", s1, s2, K=3, nmax=2.0)
+        assert np.array_equal(np.nan_to_num(raw), np.nan_to_num(raw2))
+    finally:
+        ctx.set_continuous_rates("off")
+    d, cls = ctx.simulate(321, 7, 50)                # back to the discrete classes
+    e, _ = O.simulate(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], 321, 7, 50)
+    assert np.array_equal(d, e) and np.all(cls >= 0)
+
+
+def test_continuous_rate_simulation_protein(ctx):
+    m = H.myoglobin_inputs()
+    ctx.set_tree(m["parent"], m["brlen"]); ctx.set_model(m["Q"], m["pi"], m["rates"], m["probs"])
+    try:
+        ctx.set_continuous_rates("gamma", 0.985435)
+        a, _ = ctx.simulate(7, 5, 600)
+        b, r = O.simulate_continuous(m["parent"], m["brlen"], m["Q"], m["pi"], "gamma", 0.985435, 0.0, 7, 5, 600)
+        assert (a != b).any(axis=0).mean() <= 5e-3
+    finally:
+        ctx.set_continuous_rates("off")

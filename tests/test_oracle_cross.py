@@ -198,3 +198,23 @@ def test_groups_compensation_and_euclid():
         assert abs(s - (1 - np.linalg.norm(n[m].sum(0)) / norm[m].sum())) < 1e-13
     me = O.distance_matrix("euclidian", n)
     assert abs(me[i, j] - np.linalg.norm(n[i] - n[j])) < 1e-13
+
+
+def test_continuous_rate_simulator_distribution():
+    """simulations.continuous = yes (oracle side): site rates follow Gamma(alpha, beta = alpha) -- mean 1,
+    variance 1 / alpha, and the invariant mixture keeps mean 1 with a mass p at 0; faster sites differ more
+    from the root state than slow ones."""
+    from scipy import stats
+    parent, brlen = syn.random_tree(12, 3, 0.2)
+    Q, pi = syn.hky85(2.0, [0.3, 0.2, 0.2, 0.3])
+    for alpha in (0.5, 2.0):
+        st, r = O.simulate_continuous(parent, brlen, Q, pi, "gamma", alpha, 0.0, 11, 0, 20000)
+        assert abs(r.mean() - 1.0) < 0.03 and abs(r.var() - 1.0 / alpha) < 0.12 / alpha
+        assert stats.kstest(r, "gamma", args=(alpha, 0, 1.0 / alpha)).pvalue > 1e-3
+        var_sites = (st != st[0]).any(axis=0)
+        assert var_sites[r > np.median(r)].mean() > var_sites[r <= np.median(r)].mean() + 0.1
+    st, r = O.simulate_continuous(parent, brlen, Q, pi, "invariant", 1.0, 0.3, 5, 0, 20000)
+    assert abs((r == 0).mean() - 0.3) < 0.02 and abs(r.mean() - 1.0) < 0.04
+    assert not (st[:, r == 0] != st[0, r == 0]).any()          # invariant sites never change
+    st, r = O.simulate_continuous(parent, brlen, Q, pi, "constant", 1.0, 0.0, 5, 0, 100)
+    assert np.all(r == 1.0)

@@ -629,8 +629,8 @@ def run_clustering(args):
             ctx.map(want_vectors=False)
             ctx.distance_matrix("correlation", want=False)
             out["dendro"] = ctx.cluster("complete")
-            out["groups"] = ctx.groups("correlation", cfg["max_group"])
-            out["null"] = ctx.cluster_null("correlation", "complete", cfg["null_seed"], 0, nrep, cfg["max_group"])
+            out["groups"] = ctx.groups("correlation", cfg["max_group"], as_lists=False)
+            out["null"] = ctx.cluster_null("correlation", "complete", cfg["null_seed"], 0, nrep, cfg["max_group"], as_lists=False)
 
         for _ in range(max(1, min(2, args.warmup))):
             step()
@@ -664,7 +664,7 @@ def run_clustering(args):
                                   unit="GB/s", frac=ach / peaks["hbm_gbs"], algorithmic_bytes_per_dendrogram=8.0 * S * S,
                                   ms_per_dendrogram=cl_ms, peak_source=peaks["hbm_source"], traffic=None),
                     kernel_ms_per_step={k: v[0] for k, v in prof.items()},
-                    groups=len(out["groups"]["members"]), null_rows=len(out["null"]["rep"]))
+                    groups=len(out["groups"]["height"]), null_rows=len(out["null"]["rep"]))
         print(json.dumps(line), flush=True)
         ctx.close()
 

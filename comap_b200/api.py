@@ -348,17 +348,20 @@ class Context:
         self._chk(self.lib.cmb_cluster(self.h, LINK[linkage], _i32(left), _i32(right), _d(height)))
         return left, right, height
 
-    def groups(self, dist, max_size):
+    def groups(self, dist, max_size, as_lists=True):
+        """as_lists=False returns the flat member array and its offsets instead of one array per group."""
         S = self.S
         members = np.empty(max(1, (S - 1) * max_size), np.int32); offs = np.zeros(S + 1, np.int64)
         gh = np.empty(S); gs = np.empty(S); gn = np.empty(S); ng = C.c_int64()
         self._chk(self.lib.cmb_groups(self.h, DIST[dist], max_size, _i32(members), _i64(offs), _d(gh), _d(gs),
                                       _d(gn), C.byref(ng)))
         k = ng.value
+        if not as_lists:
+            return dict(members_flat=members[:offs[k]], offsets=offs[:k + 1], height=gh[:k], stat=gs[:k], nmin=gn[:k])
         return dict(members=[members[offs[g]:offs[g + 1]].copy() for g in range(k)], height=gh[:k], stat=gs[:k],
                     nmin=gn[:k])
 
-    def cluster_null(self, dist, linkage, seed, rep_begin, rep_end, max_size, weighted_classes=False):
+    def cluster_null(self, dist, linkage, seed, rep_begin, rep_end, max_size, weighted_classes=False, as_lists=True):
         S = self.S
         nrep = rep_end - rep_begin
         cap_rows = nrep * (S - 1); cap_mem = cap_rows * max_size
@@ -370,6 +373,9 @@ class Context:
                                             _i32(rep), _i32(size), _d(dmax), _d(st), _d(nm), _i32(members), _i64(offs),
                                             C.byref(nr)))
         k = nr.value
+        if not as_lists:
+            return dict(rep=rep[:k], size=size[:k], dmax=dmax[:k], stat=st[:k], nmin=nm[:k], members_flat=members[:offs[k]],
+                        offsets=offs[:k + 1])
         return dict(rep=rep[:k], size=size[:k], dmax=dmax[:k], stat=st[:k], nmin=nm[:k],
                     members=[members[offs[g]:offs[g + 1]].copy() for g in range(k)])
 

@@ -183,12 +183,16 @@ void distance_on_device(Context& c, int dist_id, const double* out, int64_t S, i
                         const double* sd, const double* norm) {
   if (dist_id < 0 || dist_id > 2) fail("unknown distance id %d", dist_id);
   constexpr int TS = 64;
-  std::vector<int2> tiles;
   const int64_t nt = (S + TS - 1) / TS;
-  for (int64_t ti = 0; ti < nt; ti++)
-    for (int64_t tj = ti; tj < nt; tj++) tiles.push_back(make_int2((int)ti, (int)tj));
-  c.scratch.reserve(tiles.size() * 8 + 256);
-  CMB_CUDA(cudaMemcpyAsync(c.scratch.p, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice, c.stream));
+  if (c.dist_tiles_S != S) { // the tile list depends on the site count only
+    std::vector<int2> tiles;
+    for (int64_t ti = 0; ti < nt; ti++)
+      for (int64_t tj = ti; tj < nt; tj++) tiles.push_back(make_int2((int)ti, (int)tj));
+    c.dist_tiles.reserve(tiles.size() * 8 + 256);
+    CMB_CUDA(cudaMemcpyAsync(c.dist_tiles.p, tiles.data(), tiles.size() * 8, cudaMemcpyHostToDevice, c.stream));
+    CMB_CUDA(cudaStreamSynchronize(c.stream)); // the host vector goes out of scope
+    c.dist_tiles_S = S; c.dist_tiles_n = (int64_t)tiles.size();
+  }
   c.d_dist.reserve(sizeof(double) * (size_t)S * S);
   TilesLaunch L;
   L.dist_mode = true;
@@ -196,11 +200,10 @@ void distance_on_device(Context& c, int dist_id, const double* out, int64_t S, i
   L.dist_is_stat = dist_id == 2;
   L.dist_comp = 1.; // StatisticBasedDistance(cor, 1.) (CoMap.cpp:410); CompensationDistance = 1 - stat
   L.B = c.tree.B; L.S = S; L.S_pad = S_pad; L.out = out; L.mean = mean; L.sd = sd; L.norm = norm;
-  L.tiles = c.scratch.as<int2>(); L.n_tiles = (int64_t)tiles.size(); L.n_rows = S; L.mat = c.d_dist.as<double>();
+  L.tiles = c.dist_tiles.as<int2>(); L.n_tiles = c.dist_tiles_n; L.n_rows = S; L.mat = c.d_dist.as<double>();
   c.prof_begin("distance");
   int nl = launch_tiles(L, c.stream);
   c.prof_end(nl);
-  CMB_CUDA(cudaStreamSynchronize(c.stream)); // tiles vector goes out of scope
 }
 
 void cluster_on_device(Context& c, int linkage, int64_t S) {
@@ -656,19 +659,17 @@ int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t se
   MapModel m = c.map_model();
   int64_t rows = 0, mem = 0;
   if (offsets) offsets[0] = 0;
-  DevBuf mean, sd, norm, staging;
-  // Replicates are clustered in batches: the merge loop is a chain of barrier latencies, so up to four
+  DevBuf &mean = c.cn_mean, &sd = c.cn_sd, &norm = c.cn_norm, &staging = c.cn_staging;
+  // Replicates are clustered in batches: the exact merge loop is a chain of barrier latencies, so up to four
   // dendrograms advance through the same barriers (k4_cluster<NP>).  Each needs its own matrix and vectors.
   size_t free_b = 0, total_b = 0;
   CMB_CUDA(cudaMemGetInfo(&free_b, &total_b));
+  size_t held = 0;
+  for (int q = 0; q < 4; q++) held += c.cn_dists[q].cap + c.cn_outs[q].cap + c.cn_works[q].cap;
   const size_t per_rep = sizeof(double) * ((size_t)S * S + (size_t)B * S_pad) + ((size_t)64 << 20);
-  int NB = (int)std::min<size_t>(4, std::max<size_t>(1, (size_t)(0.6 * (double)free_b) / per_rep));
+  int NB = (int)std::min<size_t>(4, std::max<size_t>(1, (size_t)(0.6 * (double)(free_b + held)) / per_rep));
   if (const char* e = std::getenv("CMB_K4_BATCH")) NB = std::max(1, std::min(4, atoi(e)));
-  DevBuf dists[4], works[4], outs[4];
-  struct Release { // also on the error path (fail() throws)
-    DevBuf *a, *b, *c, *d;
-    ~Release() { for (int q = 0; q < 4; q++) { a[q].release(); b[q].release(); c[q].release(); } d->release(); }
-  } release_guard{dists, works, outs, &staging};
+  DevBuf *dists = c.cn_dists, *works = c.cn_works, *outs = c.cn_outs;
   std::vector<double> h_norms[4];
   DendroHost dendro[4];
   for (int rep0 = rep_begin; rep0 < rep_end; rep0 += NB) {
@@ -714,7 +715,6 @@ int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t se
       mem += (int64_t)g.members.size();
     }
   }
-  mean.release(); sd.release(); norm.release();
   c.have_dist = false; // the matrices were consumed
   c.have_dendro = false;
   if (n_rows) *n_rows = rows;

@@ -79,6 +79,11 @@ struct Context {
 
   // clustering
   DevBuf d_dist;                 // [S][S]
+  DevBuf dist_tiles;             // upper-triangle tile list of the distance kernel, cached per site count
+  int64_t dist_tiles_S = -1, dist_tiles_n = 0;
+  // clustering null: per-replicate matrices / vectors / work areas, kept between calls (a 20 000-site replicate
+  // holds 3.2 GB; allocating and freeing four of them per call cost tens of ms)
+  DevBuf cn_dists[4], cn_works[4], cn_outs[4], cn_mean, cn_sd, cn_norm, cn_staging;
   bool have_dist = false;
   int dist_id = 0;
   std::vector<int32_t> h_left, h_right;

@@ -287,8 +287,10 @@ __global__ void __launch_bounds__(RT) k4r_rounds(RnnParams p) {
     };
     const long long tag = (long long)round << 32;
     for (int64_t it = blockIdx.x; it < (int64_t)n_pairs * n_blk; it += G) {
-      const int q = (int)(it / n_blk);
-      const int64_t k0 = (it % n_blk) * CW;
+      // block-major: CTAs that run together work on the same block of rows k, so the scattered mirror writes
+      // mat[k][i] of a round stay inside the same ~1000 rows (TLB reach) instead of touching every row per pair
+      const int q = (int)(it % n_pairs);
+      const int64_t k0 = (it / n_pairs) * CW;
       const int i = single ? s_i : p.pair_i[q], j = single ? s_j : p.pair_j[q];
       LW wq;
       wq.dab = single ? s_d : p.pair_d[q]; wq.w1 = single ? s_w1 : p.pair_w1[q]; wq.w2 = single ? s_w2 : p.pair_w2[q]; wq.w4 = w4;

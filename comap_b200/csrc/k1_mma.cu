@@ -449,6 +449,12 @@ bool up_mma_for(const MapModel& m, const MapBuffers& b, const DevStream& s, cuda
   if (narrow_batch(b)) {
     if (m.states_only ? try_up_mma<2, C, kNarrowSG, 2, true>(m, b, s, st) : try_up_mma<2, C, kNarrowSG, 2, false>(m, b, s, st)) return true;
   }
+  // device-simulated batches: 64-site CTAs, three per SM (12 consumer warps at 128 registers, a 3-stage ring each):
+  // 26.6 ms per config-4 step against 27.7 for 128-site CTAs x 2 (CMB_UP_SG=128 selects those)
+  {
+    static const int sg = getenv("CMB_UP_SG") ? atoi(getenv("CMB_UP_SG")) : 64; // experiment switch
+    if (m.states_only && sg == 64 && try_up_mma<2, C, 64, 3, true>(m, b, s, st)) return true;
+  }
   if (m.states_only) return try_up_mma<2, C, kWideSG, 2, true>(m, b, s, st) || try_up_mma<2, C, kWideSG, 1, true>(m, b, s, st);
   return try_up_mma<2, C, kWideSG, 2, false>(m, b, s, st) || try_up_mma<2, C, kWideSG, 1, false>(m, b, s, st);
 }

@@ -324,7 +324,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
                     &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm,
-                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part, &c.k1_part_obs, &c.d_spec, &c.dist_tiles, &c.cn_mean, &c.cn_sd, &c.cn_norm, &c.cn_staging,
+                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part, &c.k1_part_obs, &c.d_spec, &c.dist_tiles, &c.s_cols, &c.s_counts, &c.cn_mean, &c.cn_sd, &c.cn_norm, &c.cn_staging,
                     &c.cn_dists[0], &c.cn_dists[1], &c.cn_dists[2], &c.cn_dists[3], &c.cn_works[0], &c.cn_works[1], &c.cn_works[2],
                     &c.cn_works[3], &c.cn_outs[0], &c.cn_outs[1], &c.cn_outs[2], &c.cn_outs[3]};
   for (DevBuf* b : bufs) b->release();
@@ -561,11 +561,30 @@ int cmb_profile_reset(cmb_ctx* ctx) {
   ctx->c.prof_collect();
   ctx->c.prof.entries.clear();
   ctx->c.prof.total_launches = 0;
+  ctx->c.prof.sites_simulated = 0;
+  ctx->c.s_batches = 0;
   CMB_CATCH
 }
 int cmb_profile_get(cmb_ctx* ctx, const char* name, double* ms, int64_t* launches) {
   CMB_TRY
   ctx->c.prof_collect();
+  if (std::string(name) == "sites_simulated" || std::string(name) == "sites_mapped_null") {
+    // counters, returned through `ms`: simulated sites handed to the null's mapping since the reset, and how many
+    // of them (varied columns + the A constant patterns per batch) the mapping kernels actually walked
+    Context& c = ctx->c;
+    double v = (double)c.prof.sites_simulated;
+    if (std::string(name) == "sites_mapped_null") {
+      if (c.s_batches > 0 && c.s_counts.p) {
+        std::vector<int32_t> h(2 * (size_t)c.s_batches);
+        CMB_CUDA(cudaMemcpy(h.data(), c.s_counts.p, sizeof(int32_t) * h.size(), cudaMemcpyDeviceToHost));
+        v = 0.;
+        for (int k = 0; k < c.s_batches; k++) v += h[2 * k];
+      }
+    }
+    if (ms) *ms = v;
+    if (launches) *launches = c.s_batches;
+    return 0;
+  }
   auto it = ctx->c.prof.entries.find(name);
   if (ms) *ms = it == ctx->c.prof.entries.end() ? 0. : it->second.ms;
   if (launches) *launches = it == ctx->c.prof.entries.end() ? 0 : it->second.launches;

@@ -140,21 +140,46 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
         c.prof_end(1);
       }
     }
+    // Pattern compression (nucleotides): columns whose tips all carry the same state -- 16 % of the simulated
+    // sites of config 4 -- are mapped once per state, as Bio++ maps distinct site patterns and copies
+    // (LegacySubstitutionMappingTools::computeSubstitutionVectors over getNumberOfDistinctSites()).  The varied
+    // columns are packed to the front of a second tip buffer with the A constant patterns behind them, the
+    // mapping kernels stop at the packed count (a device scalar: no host round trip), and the paired statistic
+    // reads each site's vector through a column index.
+    const bool dedup_on = !(getenv("CMB_NULL_DEDUP") && atoi(getenv("CMB_NULL_DEDUP")) == 0);
+    const bool dedup = dedup_on && c.A == 4;
+    const int32_t *col1 = nullptr, *col2 = nullptr;
+    if (dedup) {
+      c.s_tips[1].reserve((size_t)T * n_pad);
+      c.s_cols.reserve(sizeof(int32_t) * (size_t)n_pad + 256);
+      c.s_counts.reserve(sizeof(int32_t) * 2 * 4096);
+      if (c.s_batches >= 4096) c.s_batches = 0;
+      int32_t* counts = c.s_counts.as<int32_t>() + 2 * c.s_batches;
+      c.prof_begin("compress");
+      const int nl = launch_compress_constant(c.A, T, n, half, n_pad, tips, c.s_tips[1].as<uint8_t>(), c.s_cols.as<int32_t>(), counts,
+                                              c.scratch2, c.stream);
+      c.prof_end(nl);
+      bb.tips = c.s_tips[1].as<uint8_t>();
+      bb.n_active = counts;
+      col1 = c.s_cols.as<int32_t>(); col2 = col1 + half;
+      c.s_batches++;
+    }
     c.run_map(bb, true, sim1 == nullptr);
     c.prof_begin("null_pairs");
-    launch_paired(corrected ? 0 : stat_id, c.mi_threshold, B, n, n_pad, n_pad, bb.out, bb.out + half, mv, mv,
-                  ns.stat.as<double>() + off, ns.nmin.as<double>() + off, c.stream);
+    launch_paired(corrected ? 0 : stat_id, c.mi_threshold, B, n, n_pad, n_pad, bb.out, dedup ? bb.out : bb.out + half, mv, mv,
+                  ns.stat.as<double>() + off, ns.nmin.as<double>() + off, c.stream, col1, col2);
     c.prof_end(1);
     if (raw) {
       c.scratch.reserve(sizeof(double) * 4 * (size_t)n);
-      launch_raw_rows(n, ns.stat.as<double>() + off, ns.nmin.as<double>() + off, bb.rate_class, bb.rate_class + half,
-                      bb.post_rate, bb.post_rate + half, c.scratch.as<double>(), c.stream);
+      launch_raw_rows(n, ns.stat.as<double>() + off, ns.nmin.as<double>() + off, bb.rate_class, dedup ? bb.rate_class : bb.rate_class + half,
+                      bb.post_rate, dedup ? bb.post_rate : bb.post_rate + half, c.scratch.as<double>(), c.stream, col1, col2);
       c.prof.total_launches += 1;
       CMB_CUDA(cudaMemcpyAsync(raw + off * 4, c.scratch.p, sizeof(double) * 4 * (size_t)n, cudaMemcpyDeviceToHost,
                                c.stream));
       CMB_CUDA(cudaStreamSynchronize(c.stream));
     }
     off += n;
+    c.prof.sites_simulated += 2 * n;
   }
   if (K > 0) null_load(c, ns.stat.as<double>(), ns.nmin.as<double>(), total, K, nmax);
   else if (!c.async_null) CMB_CUDA(cudaStreamSynchronize(c.stream));

@@ -11,6 +11,7 @@ struct Profile {
   std::vector<std::tuple<std::string, cudaEvent_t, cudaEvent_t, int>> pending;
   bool enabled = false;
   int64_t total_launches = 0;
+  int64_t sites_simulated = 0;   // simulated sites handed to the null's mapping
 };
 
 struct NullState {            // binned, sorted null distribution (device + host mirror)
@@ -71,6 +72,8 @@ struct Context {
   // scratch for simulated batches
   DevBuf s_tips[2], s_D, s_Lc, s_invL, s_loglik, s_pr[2], s_rc[2], s_out[2], s_sum[2], s_sumsq[2], s_cls;
   DevBuf d_identity_mask;
+  DevBuf s_cols, s_counts;       // pattern compression of simulated batches: column of every site, {sites to map, varied} per batch
+  int s_batches = 0;
   int64_t null_budget_sites = 0;  // simulated sites the null may hold at once (from free memory, cached)
   const void* s_tips_ptr = nullptr;
   int64_t s_tips_pad = -1, s_tips_n = -1; // geometry the simulated tip buffer's padding columns were cleared for

@@ -313,6 +313,7 @@ __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_up_mma(MapM
   const int NSTG = up.n_stages;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t site0 = (int64_t)blockIdx.x * SG;
+  if (b.n_active && site0 >= (int64_t)__ldg(b.n_active)) return; // pattern-compressed batch: nothing behind the packed columns
   uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* stg_empty = stg_full + kMaxStages;
   unsigned char* stg_ring = smem + 128;
@@ -486,6 +487,7 @@ __global__ void __launch_bounds__(32 * (SG / (8 * NG) + 1), MINB) k1_down_mma(Ma
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_pad = b.n_pad;
   const int64_t site0 = (int64_t)blockIdx.x * SG;
+  if (b.n_active && site0 >= (int64_t)__ldg(b.n_active)) return; // pattern-compressed batch
   uint64_t* stg_full = reinterpret_cast<uint64_t*>(smem);
   uint64_t* stg_empty = stg_full + kDownStages;
   unsigned char* stg_ring = smem + 128;

@@ -61,9 +61,13 @@ __device__ __forceinline__ double mi_binary(double n, double n1x, double n1y, do
 template <int STAT>
 __global__ void __launch_bounds__(128) k2_paired(double thr, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* __restrict__ o1,
                           const double* __restrict__ o2, const double* __restrict__ mv, const double* __restrict__ mv2,
-                          double* __restrict__ stat, double* __restrict__ nmin) {
+                          double* __restrict__ stat, double* __restrict__ nmin, const int32_t* __restrict__ col1,
+                          const int32_t* __restrict__ col2) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  // pattern-compressed mappings: the vectors of pair j live in columns col1[j] / col2[j]
+  o1 += col1 ? col1[j] - j : 0;
+  o2 += col2 ? col2[j] - j : 0;
   constexpr int stat_id = STAT;
   const double nb = (double)B;
   double sx = 0., sy = 0., qx = 0., qy = 0., sxy = 0., s3 = 0., cnt = 0.;
@@ -160,13 +164,61 @@ __global__ void k2_pair_list(int stat_id, double thr, int B, int64_t n_pad, cons
 }
 
 __global__ void k2_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1,
-                            const int32_t* rc2, const double* pr1, const double* pr2, double* raw) {
+                            const int32_t* rc2, const double* pr1, const double* pr2, double* raw, const int32_t* col1,
+                            const int32_t* col2) {
   const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= n) return;
+  const int64_t a = col1 ? col1[j] : j, b = col2 ? col2[j] : j;
   raw[j * 4 + 0] = stat[j];
-  raw[j * 4 + 1] = (double)(rc1[j] < rc2[j] ? rc1[j] : rc2[j]);
-  raw[j * 4 + 2] = pr1[j] < pr2[j] ? pr1[j] : pr2[j];
+  raw[j * 4 + 1] = (double)(rc1[a] < rc2[b] ? rc1[a] : rc2[b]);
+  raw[j * 4 + 2] = pr1[a] < pr2[b] ? pr1[a] : pr2[b];
   raw[j * 4 + 3] = nmin[j];
+}
+
+// ---------------------------------------------------------------------------- pattern compression
+// state of a column whose tips all agree, else -1; sites outside the two batches: -2 (not mapped at all)
+__global__ void k2_classify_columns(int T, int64_t n, int64_t half, int64_t n_pad, const uint8_t* __restrict__ tips,
+                                    int32_t* __restrict__ cls, int32_t* __restrict__ varied) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_pad) return;
+  const bool real = s < n || (s >= half && s < half + n);
+  int c = -2;
+  if (real) {
+    const uint8_t s0 = tips[s];
+    bool same = true;
+#pragma unroll 16
+    for (int t = 1; t < T; t++) same &= tips[(size_t)t * n_pad + s] == s0; // independent loads: 16 in flight
+    c = same ? (int)s0 : -1;
+  }
+  cls[s] = c;
+  varied[s] = c == -1 ? 1 : 0;
+}
+__global__ void k2_compress_counts(int A, int64_t n_pad, const int32_t* pos, const int32_t* varied, int32_t* counts) {
+  const int32_t nv = pos[n_pad - 1] + varied[n_pad - 1];
+  counts[1] = nv;
+  counts[0] = nv + A;
+}
+__global__ void k2_compact_columns(int A, int T, int64_t n_pad, const uint8_t* __restrict__ tips, const int32_t* __restrict__ cls,
+                                   const int32_t* __restrict__ pos, const int32_t* __restrict__ counts, uint8_t* __restrict__ tips_c,
+                                   int32_t* __restrict__ col) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n_pad) return;
+  const int32_t nv = counts[1];
+  const int c = cls[s];
+  if (c == -1) {
+    const int32_t d = pos[s];
+#pragma unroll 16
+    for (int t = 0; t < T; t++) tips_c[(size_t)t * n_pad + d] = tips[(size_t)t * n_pad + s];
+    col[s] = d;
+  } else col[s] = c >= 0 ? nv + c : 0;
+  // the A constant patterns behind the varied columns, then one CTA's worth of valid filler
+  if (s < A + 256) {
+    const int64_t d = (int64_t)nv + s;
+    if (d < n_pad) {
+      const uint8_t v = s < A ? (uint8_t)s : 0;
+      for (int t = 0; t < T; t++) tips_c[(size_t)t * n_pad + d] = v;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------- binning
@@ -591,15 +643,16 @@ __global__ void k2_keep_to_i64(int64_t n, const uint8_t* keep, int64_t* out) {
 } // namespace
 
 void launch_paired(int stat_id, double thr, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
-                   const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st) {
+                   const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st, const int32_t* col1,
+                   const int32_t* col2) {
   const unsigned g = (unsigned)((n + 127) / 128);
   switch (stat_id) { // the statistic is a template parameter: no per-branch dispatch in the inner loops
-    case 0: k2_paired<0><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
-    case 1: k2_paired<1><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
-    case 2: k2_paired<2><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
-    case 3: k2_paired<3><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
-    case 4: k2_paired<4><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
-    case 6: k2_paired<6><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin); break;
+    case 0: k2_paired<0><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
+    case 1: k2_paired<1><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
+    case 2: k2_paired<2><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
+    case 3: k2_paired<3><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
+    case 4: k2_paired<4><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
+    case 6: k2_paired<6><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
     default: fail("unknown statistic id %d", stat_id);
   }
   CMB_CUDA(cudaGetLastError());
@@ -610,9 +663,31 @@ void launch_pair_list(int stat_id, double thr, int B, int64_t n_pad, const doubl
   k2_pair_list<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(stat_id, thr, B, n_pad, out, mv, pairs, n_pairs, stat);
   CMB_CUDA(cudaGetLastError());
 }
+int launch_compress_constant(int A, int T, int64_t n, int64_t half, int64_t n_pad, const uint8_t* tips, uint8_t* tips_c,
+                             int32_t* col, int32_t* counts, DevBuf& tmp, cudaStream_t st) {
+  if (n_pad > 0x7fffffff) fail("internal: batch too large for 32-bit column indices");
+  size_t need = 0;
+  cub::DeviceScan::ExclusiveSum(nullptr, need, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_pad, st);
+  const size_t a = ((size_t)n_pad * 4 + 255) & ~size_t(255);
+  tmp.reserve(3 * a + need + 256);
+  unsigned char* base = tmp.as<unsigned char>();
+  int32_t* cls = (int32_t*)base;
+  int32_t* varied = (int32_t*)(base + a);
+  int32_t* pos = (int32_t*)(base + 2 * a);
+  void* ctemp = base + 3 * a;
+  const unsigned g = (unsigned)((n_pad + 255) / 256);
+  k2_classify_columns<<<g, 256, 0, st>>>(T, n, half, n_pad, tips, cls, varied);
+  CMB_CUDA(cub::DeviceScan::ExclusiveSum(ctemp, need, varied, pos, (int)n_pad, st));
+  k2_compress_counts<<<1, 1, 0, st>>>(A, n_pad, pos, varied, counts);
+  k2_compact_columns<<<g, 256, 0, st>>>(A, T, n_pad, tips, cls, pos, counts, tips_c, col);
+  CMB_CUDA(cudaGetLastError());
+  return 4;
+}
+
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
-                     const double* pr1, const double* pr2, double* raw, cudaStream_t st) {
-  k2_raw_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, stat, nmin, rc1, rc2, pr1, pr2, raw);
+                     const double* pr1, const double* pr2, double* raw, cudaStream_t st, const int32_t* col1,
+                     const int32_t* col2) {
+  k2_raw_rows<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(n, stat, nmin, rc1, rc2, pr1, pr2, raw, col1, col2);
   CMB_CUDA(cudaGetLastError());
 }
 void launch_prep(int B, int64_t n, int64_t n_pad, const double* out, const double* mv, double* mean, double* sd,

@@ -35,6 +35,7 @@ struct MapBuffers {          // per-batch device arrays, n_pad sites (multiple o
   double* post_rate = nullptr;     // [n_pad]
   int32_t* rate_class = nullptr;   // [n_pad]
   double* out = nullptr;           // [B][n_pad]
+  const int32_t* n_active = nullptr; // device scalar: only sites [0, *n_active) are mapped (nullptr: all n_pad); A = 4 kernels
 };
 
 struct MapModel {            // device-resident model constants
@@ -73,15 +74,25 @@ void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64
 
 // ---- K2
 // mv: mean vector subtracted before a correlation (corrected correlation) or nullptr
+// col1 / col2 (nullable): column of pair j's first / second site in o1 / o2 (pattern-compressed mappings); else j
 void launch_paired(int stat_id, double thr, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* o1, const double* o2,
-                   const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st);
+                   const double* mv, const double* mv2, double* stat, double* nmin, cudaStream_t st,
+                   const int32_t* col1 = nullptr, const int32_t* col2 = nullptr);
+// Pattern compression of a simulated alignment (what Bio++ does through its distinct-site patterns): columns whose
+// tips all carry the same state are mapped ONCE per state.  cls[site] = state or -1 (varied) for the sites of
+// the two batches [0, n) and [half, half + n); tips_c receives the varied columns packed from 0 and the A constant
+// patterns after them; col[site] = where the site's vector will be; counts[0] = sites to map (varied + A),
+// counts[1] = varied sites.  tmp: scan scratch.
+int launch_compress_constant(int A, int T, int64_t n, int64_t half, int64_t n_pad, const uint8_t* tips, uint8_t* tips_c,
+                             int32_t* col, int32_t* counts, DevBuf& tmp, cudaStream_t st);
 // statistic of listed column pairs of one [B][n_pad] matrix (candidate-group statistics)
 void launch_pair_list(int stat_id, double thr, int B, int64_t n_pad, const double* out, const double* mv, const int2* pairs,
                       int64_t n_pairs, double* stat, cudaStream_t st);
 void launch_count_ge(int B, int64_t n, int64_t n_pad, const double* out, double thr, double* cnt, cudaStream_t st);
 void launch_mean_vector(int B, int64_t S, int64_t n_pad, const double* out, double* mv, cudaStream_t st);
 void launch_raw_rows(int64_t n, const double* stat, const double* nmin, const int32_t* rc1, const int32_t* rc2,
-                     const double* pr1, const double* pr2, double* raw, cudaStream_t st);
+                     const double* pr1, const double* pr2, double* raw, cudaStream_t st,
+                     const int32_t* col1 = nullptr, const int32_t* col2 = nullptr);
 void launch_prep(int B, int64_t n, int64_t n_pad, const double* out, const double* mv, double* mean, double* sd,
                  double* norm, cudaStream_t st);
 int bin_and_sort(int64_t n, const double* stat, const double* nmin, int K, double nmax, DevBuf& tmp,

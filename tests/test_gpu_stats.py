@@ -306,3 +306,23 @@ def test_continuous_rate_simulation_protein(ctx):
         assert (a != b).any(axis=0).mean() <= 5e-3
     finally:
         ctx.set_continuous_rates("off")
+
+
+def test_pattern_compression_of_the_null_is_bit_identical(ctx, monkeypatch):
+    """Constant simulated columns are mapped once per state and batch (as Bio++ maps distinct site patterns):
+    raw null rows, bin occupancy and the sorted null equal the uncompressed run bit for bit -- on a slow model
+    where most columns are constant, and across several batches."""
+    c = H.random_dna_case(30, 64, 19, mean_brlen=0.01, C=4)
+    _setup(ctx, c)
+    out = {}
+    for flag in ("0", "1"):
+        monkeypatch.setenv("CMB_NULL_DEDUP", flag)
+        ctx.profile_reset()
+        raw = ctx.null_intra("correlation", 77, 6, 700, K=4, nmax=1.0, want_raw=True)
+        g = ctx.null_get()
+        out[flag] = (raw, g, ctx.profile_get("sites_simulated")[0], ctx.profile_get("sites_mapped_null")[0])
+    a, b = out["0"], out["1"]
+    assert np.array_equal(np.isnan(a[0]), np.isnan(b[0])) and np.array_equal(np.nan_to_num(a[0]), np.nan_to_num(b[0]))
+    assert np.array_equal(a[1]["bin_offsets"], b[1]["bin_offsets"])
+    assert np.array_equal(np.nan_to_num(a[1]["sorted"]), np.nan_to_num(b[1]["sorted"]))
+    assert a[2] == b[2] == 2 * 6 * 700 and a[3] == a[2] and b[3] < 0.8 * b[2]    # most columns were constant

@@ -127,18 +127,18 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
       CMB_CUDA(cudaMemsetAsync(tips, 0, (size_t)T * n_pad, c.stream));
       c.s_tips_ptr = tips; c.s_tips_pad = n_pad; c.s_tips_n = n;
     }
-    for (int k = 0; k < 2; k++) {
-      if (sim1) {
+    if (sim1) {
+      for (int k = 0; k < 2; k++) {
         const uint8_t* src = k == 0 ? sim1 : sim2;
         for (int64_t r = 0; r < nb; r++)
           CMB_CUDA(cudaMemcpy2DAsync(tips + k * half + r * R, n_pad, src + (size_t)(r0 + r) * T * R, R, R, T,
                                      cudaMemcpyHostToDevice, c.stream));
-      } else {
-        c.prof_begin("simulate");
-        launch_simulate(m, c.sim_stream, seed, (2 * r0 + k) * R, R, 2 * R, n, n_pad, weighted, c.tree.n_nodes - 1,
-                        tips + k * half, nullptr, c.stream);
-        c.prof_end(1);
       }
+    } else { // both batches in one launch: threads >= n simulate the second alignment's sites into the columns from `half`
+      c.prof_begin("simulate");
+      launch_simulate(m, c.sim_stream, seed, 2 * r0 * R, R, 2 * R, 2 * n, n_pad, weighted, c.tree.n_nodes - 1, tips, nullptr,
+                      c.stream, n, half, R);
+      c.prof_end(1);
     }
     // Pattern compression (nucleotides): columns whose tips all carry the same state -- 16 % of the simulated
     // sites of config 4 -- are mapped once per state, as Bio++ maps distinct site patterns and copies

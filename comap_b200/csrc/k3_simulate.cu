@@ -27,6 +27,8 @@ struct SimParams {
   uint64_t seed;
   int64_t base, group, stride; // site id = base + (idx / group) * stride + idx % group
   int64_t n, n_pad;
+  int64_t half_n, half_col, half_shift; // two batches in one launch: threads >= half_n simulate site ids shifted by
+                                        // half_shift and write columns from half_col (half_n = 0: one batch)
   const double *pi, *probs;
   uint8_t* tips;
   int32_t* classes;
@@ -45,10 +47,13 @@ __device__ __forceinline__ int draw_state(const double* __restrict__ row, int A,
 
 __global__ void __launch_bounds__(NT) k3_simulate(SimParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x;
-  const bool live = idx < p.n;
-  const int64_t ii = live ? idx : p.n - 1;
-  const uint64_t site = (uint64_t)(p.base + (ii / p.group) * p.stride + ii % p.group);
+  const int64_t tid = (int64_t)blockIdx.x * NT + threadIdx.x;
+  const bool live = tid < p.n;
+  const int64_t tt = live ? tid : p.n - 1;
+  const bool second = p.half_n > 0 && tt >= p.half_n;
+  const int64_t ii = second ? tt - p.half_n : tt;                   // index inside its batch
+  const int64_t idx = second ? p.half_col + ii : ii;                // column of the tip matrix
+  const uint64_t site = (uint64_t)(p.base + (second ? p.half_shift : 0) + (ii / p.group) * p.stride + ii % p.group);
   ChunkStream cs{p.src, p.off, p.bytes, p.n_chunks, p.cap, nullptr, nullptr};
   cs.start(smem + 128, reinterpret_cast<uint64_t*>(smem));
   const int A = p.A, C = p.C, AA = A * A;
@@ -135,10 +140,13 @@ __global__ void __launch_bounds__(NT) k3_simulate_cont(SimParams p, ContParams c
   const double* L = sp + A + AA;
   const double* brlen = cp.spec + A + 2 * AA;
   unsigned char* ring = smem + ((sizeof(double) * (A + 2 * AA) + 127) & ~size_t(127));
-  const int64_t idx = (int64_t)blockIdx.x * NT + threadIdx.x;
-  const bool live = idx < p.n;
-  const int64_t ii = live ? idx : p.n - 1;
-  const uint64_t site = (uint64_t)(p.base + (ii / p.group) * p.stride + ii % p.group);
+  const int64_t tid = (int64_t)blockIdx.x * NT + threadIdx.x;
+  const bool live = tid < p.n;
+  const int64_t tt = live ? tid : p.n - 1;
+  const bool second = p.half_n > 0 && tt >= p.half_n;
+  const int64_t ii = second ? tt - p.half_n : tt;
+  const int64_t idx = second ? p.half_col + ii : ii;
+  const uint64_t site = (uint64_t)(p.base + (second ? p.half_shift : 0) + (ii / p.group) * p.stride + ii % p.group);
   ChunkStream cs{p.src, p.off, p.bytes, p.n_chunks, p.cap, nullptr, nullptr};
   cs.start(ring + 128, reinterpret_cast<uint64_t*>(ring));   // includes the __syncthreads that publishes sp
   int st;
@@ -210,8 +218,9 @@ __global__ void __launch_bounds__(NT) k3_simulate_cont(SimParams p, ContParams c
 
 void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,
                      int64_t stride, int64_t n, int64_t n_pad, int weighted, int root_node, uint8_t* tips,
-                     int32_t* classes, cudaStream_t st) {
+                     int32_t* classes, cudaStream_t st, int64_t half_n, int64_t half_col, int64_t half_shift) {
   SimParams p;
+  p.half_n = half_n; p.half_col = half_col; p.half_shift = half_shift;
   p.src = s.bytes.as<unsigned char>(); p.off = s.off.as<uint32_t>(); p.bytes = s.nbytes.as<uint32_t>();
   p.nrec = s.nrec.as<uint32_t>(); p.n_chunks = s.n_chunks; p.cap = s.cap;
   p.A = m.A; p.C = m.C; p.root_node = root_node; p.weighted = weighted; p.seed = seed;

@@ -70,7 +70,7 @@ __host__ __device__ inline size_t d_chunk(int64_t chunk, int slot, int n_slots, 
 // site id of thread idx = base + (idx / group) * stride + idx % group
 void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,
                      int64_t stride, int64_t n, int64_t n_pad, int weighted, int root_node, uint8_t* tips,
-                     int32_t* classes, cudaStream_t st);
+                     int32_t* classes, cudaStream_t st, int64_t half_n = 0, int64_t half_col = 0, int64_t half_shift = 0);
 
 // ---- K2
 // mv: mean vector subtracted before a correlation (corrected correlation) or nullptr

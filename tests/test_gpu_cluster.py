@@ -177,3 +177,28 @@ def test_cluster_null_vs_oracle(ctx):
         assert np.array_equal(res["stat"][sel], og["stat"]) and np.array_equal(res["nmin"][sel], og["nmin"])
         assert np.array_equal(res["size"][sel], [len(b) for b in og["members"]])
     ctx.set_alignment(c["codes"], c["code_mask"])
+
+
+@pytest.mark.parametrize("algo", ["exact", "rnn"])
+def test_cluster_with_nan_rows(ctx, algo, monkeypatch):
+    """A zero vector has no correlation with anything: its row of the distance matrix is NaN.  One such site is
+    joined last (finalStep joins the last two clusters whatever their distance: height NaN), as in the
+    reference's loop; with two of them no finite distance is left while three clusters live, and the call fails."""
+    monkeypatch.setenv("CMB_K4_ALGO", algo)
+    c, r = _setup(ctx, T=16, S=260, seed=12)
+    S = ctx.S
+    n = r["n"].copy()
+    n[5] = 0.0
+    ctx.load_vectors(n)
+    mat = ctx.distance_matrix("correlation")
+    assert np.isnan(mat[5, 6]) and np.isnan(mat[:, 5]).sum() == S - 1
+    left, right, height = ctx.cluster("complete")
+    ol, orr, oh = O.hclust("complete", mat)
+    assert np.array_equal(left, ol) and np.array_equal(right, orr)
+    assert np.isnan(height[-1]) and 5 in (left[-1], right[-1])
+    assert np.allclose(height[:-1], oh[:-1], rtol=1e-12, atol=1e-15)
+    n[9] = 0.0
+    ctx.load_vectors(n)
+    ctx.distance_matrix("correlation")
+    with pytest.raises(RuntimeError, match="NaN"):
+        ctx.cluster("complete")

@@ -46,29 +46,12 @@ __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity, 
     __nanosleep(ns);
   }
 }
-// Wait with a suspend-time hint: the thread is parked by the hardware for up to `ns` and woken when the phase
-// completes, so neither the polling instructions nor the wake-up granularity of nanosleep are paid.
-__device__ __forceinline__ void mbar_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n selp.u32 %0, 1, 0, p;\n}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
-        : "memory");
-  } while (!ok);
-}
 // TMA 1-D bulk copy global -> shared, completion signalled on an mbarrier.
 __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
-}
-// L2 prefetch of a contiguous global range (no shared memory, no completion): the later bulk copy of the same
-// bytes then hits L2 instead of paying the HBM latency inside the stage ring.
-__device__ __forceinline__ void tma_prefetch_l2(const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

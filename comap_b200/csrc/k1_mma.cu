@@ -473,7 +473,7 @@ struct DownMmaParams {
   const uint32_t *rec_off, *rec_bytes;
   const int4* refs;     // per node (flags, row_a, row_b, 0)
   uint32_t n_nodes, rec_cap;
-  int n_stages, smem_levels;
+  int n_stages;
 };
 constexpr int kDownStages = 8;
 
@@ -673,9 +673,8 @@ bool try_down_mma(const MapModel& m, const MapBuffers& b, const DevStream& s, cu
   while (dp.n_stages > 2 && 128 + dp.n_stages * stage + entry > (size_t)max_smem) dp.n_stages /= 2;
   if (128 + dp.n_stages * stage > (size_t)max_smem) return false;
   // the whole message stack lives in shared memory (its levels are in the records: no run-time stack pointer)
-  dp.smem_levels = s.stack_depth;
   if (128 + dp.n_stages * stage + (size_t)s.stack_depth * entry > (size_t)max_smem) return false;
-  const size_t smem = 128 + dp.n_stages * stage + (size_t)dp.smem_levels * entry;
+  const size_t smem = 128 + dp.n_stages * stage + (size_t)s.stack_depth * entry;
   constexpr int threads = 32 * (SG / (8 * NG) + 1);
   CMB_CUDA(cudaFuncSetAttribute(k1_down_mma<NG, C, SG, MINB, STATES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   k1_down_mma<NG, C, SG, MINB, STATES><<<(unsigned)(b.n_pad / SG), threads, smem, st>>>(m, b, dp);

@@ -299,7 +299,9 @@ def profile_dram_bytes(pattern):
         tot += float(m.group(2)) * unit.get(m.group(1), 1.0)
     g = re.search(r"^launch__grid_size\s+([0-9.]+)", txt, re.M)
     d = re.search(r"^gpu__time_duration.sum\s+(\S+)\s+([0-9.eE+-]+)", txt, re.M)
+    sg = re.search(r"k1_(?:up|down)_mma<\d+, \d+, (\d+),", txt)      # sites per CTA: third template argument
     return dict(file=os.path.relpath(best, ROOT), dram_bytes=tot, grid=float(g.group(1)) if g else None,
+                sites_per_cta=int(sg.group(1)) if sg else 128,
                 ms=float(d.group(2)) * {"ms": 1.0, "us": 1e-3, "s": 1e3, "ns": 1e-6}.get(d.group(1), 1.0) if d else None)
 
 
@@ -464,7 +466,7 @@ def run_ours(args, cfg):
                          sites_per_launch=sites_mapped / passes, note=note, traffic=None)
                 pd = profile_dram_bytes(prof_glob)
                 if pd and pd["grid"]:
-                    per_site = pd["dram_bytes"] / (pd["grid"] * 128.0)       # 128 sites per CTA in the A = 4 kernels
+                    per_site = pd["dram_bytes"] / (pd["grid"] * pd["sites_per_cta"])   # captured without pattern compression
                     e["traffic"] = per_site * sites_mapped / passes
                     e["traffic_source"] = "%s: dram__bytes_read.sum + dram__bytes_write.sum, scaled by sites" % pd["file"]
                     e["measured_dram_frac"] = per_site * sites_mapped / (ms_total * 1e-3) / 1e9 / hbm

@@ -339,8 +339,60 @@ __device__ __forceinline__ double tile_load(double x, double mean, double thr = 
 
 // One pair (row ri of the owned rows = site i, column site j) from its accumulated sum: statistic, filters,
 // Domain bin, p-value, stores.  Shared by the unfused and the tensor-core tile kernels.
-template <int STAT>
-__device__ __forceinline__ void pair_epilogue(const TileParams& p, int64_t ri, int64_t i, int64_t j, double a) {
+// #{sim < stat} in the pair's Nmin bin for NV pairs at once: the binary searches advance in lock step so that their
+// loads -- dependent L2 round trips, 17 per pair at 10^5 samples per bin -- overlap instead of queueing behind each
+// other (ncu r2m: 29 % of the tile kernel's stalls were these loads).  Same counts as one search after the other.
+template <int NV>
+__device__ __forceinline__ void pvalues_interleaved(const TileParams& p, const bool (&valid)[NV], const int64_t (&idx)[NV],
+                                                    const double (&stat)[NV], const double (&nm)[NV]) {
+  const double* sim[NV];
+  int32_t lo[NV], hi[NV], nsim[NV];
+  bool any = false;
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    sim[v] = p.sorted; lo[v] = hi[v] = nsim[v] = 0;
+    if (!valid[v]) continue;
+    const int cat = domain_index(p.nmax, p.K, nm[v]);
+    if (cat >= 0) {
+      sim[v] = p.sorted + p.bin_off[cat];
+      nsim[v] = (int32_t)(p.bin_off[cat + 1] - p.bin_off[cat]);
+      hi[v] = nsim[v];
+      any |= nsim[v] > 0;
+    } else nsim[v] = -1; // outside [0, nmax): "NA\t0"
+  }
+  while (any) {
+    double x[NV];
+    int32_t mid[NV];
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      mid[v] = (int32_t)(((int64_t)lo[v] + hi[v]) >> 1);
+      x[v] = lo[v] < hi[v] ? sim[v][mid[v]] : 0.;
+    }
+    any = false;
+#pragma unroll
+    for (int v = 0; v < NV; v++) {
+      if (lo[v] < hi[v]) {
+        if (x[v] < stat[v]) lo[v] = mid[v] + 1; else hi[v] = mid[v];
+      }
+      any |= lo[v] < hi[v];
+    }
+  }
+#pragma unroll
+  for (int v = 0; v < NV; v++) {
+    if (!valid[v]) continue;
+    const bool in = nsim[v] >= 0;
+    const int32_t ns = in ? nsim[v] : 0;
+    if (p.o_pvalue) p.o_pvalue[idx[v]] = in ? (double)(ns - lo[v] + 1) / (double)(ns + 1) : nan("");
+    if (p.o_nsim) p.o_nsim[idx[v]] = ns;
+  }
+}
+
+// One pair (row ri of the owned rows = site i, column site j) from its accumulated sum: statistic, filters,
+// stores; the p-value either here (one search) or deferred to pvalues_interleaved (idx / stat / Nmin returned).
+// Shared by the unfused and the tensor-core tile kernels.
+template <int STAT, bool DEFER = false>
+__device__ __forceinline__ void pair_epilogue(const TileParams& p, int64_t ri, int64_t i, int64_t j, double a,
+                                              int64_t* idx_out = nullptr, double* stat_out = nullptr, double* nm_out = nullptr) {
   const double nb = (double)p.B;
   double stat;
   if (STAT == 0) stat = (a / nb * nb / (nb - 1.)) / mul_(p.sd[i], p.sd2[j]);
@@ -374,6 +426,10 @@ __device__ __forceinline__ void pair_epilogue(const TileParams& p, int64_t ri, i
   if (p.o_rcmin) p.o_rcmin[idx] = ci < cj ? ci : cj;
   if (p.o_prmin) p.o_prmin[idx] = pi_ < pj ? pi_ : pj;
   if (p.o_nmin) p.o_nmin[idx] = nm;
+  if constexpr (DEFER) {
+    *idx_out = idx; *stat_out = stat; *nm_out = nm;
+    return;
+  }
   if (p.K > 0 && (p.o_pvalue || p.o_nsim)) {
     int cat = domain_index(p.nmax, p.K, nm);
     double pv = nan("");
@@ -392,7 +448,6 @@ __device__ __forceinline__ void pair_epilogue(const TileParams& p, int64_t ri, i
     if (p.o_nsim) p.o_nsim[idx] = (int32_t)nsim;
   }
 }
-
 
 // Opt-in tensor-core flavour of the correlation / covariance / cosinus Gram tiles (CMB_K2_DMMA=1): the same
 // 64 x 64 tile, centred in the tile load, accumulated by DMMA m8n8k4 (warp = 32 x 16 outputs = 4 x 2 MMA tiles,
@@ -563,17 +618,23 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
     __syncthreads();
   }
 
+  const bool want_pv = p.mode != MODE_DIST && p.K > 0 && (p.o_pvalue || p.o_nsim);
 #pragma unroll
   for (int u = 0; u < 4; u++) {
     const int64_t ri = i0 + ty * 4 + u;
     if (ri >= p.n_rows) continue;
     const int64_t i = p.rows ? p.rows[ri] : ri;
+    bool valid[4];
+    int64_t idx[4];
+    double st[4], nm[4];
 #pragma unroll
     for (int v = 0; v < 4; v++) {
       const int64_t j = j0 + tx * 4 + v;
-      if (j >= p.S2 || (p.mode != MODE_RECT && j <= i)) continue;
-      pair_epilogue<STAT>(p, ri, i, j, acc[u][v]);
+      valid[v] = !(j >= p.S2 || (p.mode != MODE_RECT && j <= i));
+      idx[v] = 0; st[v] = nm[v] = 0.;
+      if (valid[v]) pair_epilogue<STAT, true>(p, ri, i, j, acc[u][v], &idx[v], &st[v], &nm[v]);
     }
+    if (want_pv) pvalues_interleaved<4>(p, valid, idx, st, nm);
   }
   if (p.mode == MODE_DIST && t.x == t.y) { // zero diagonal
     for (int d = tid; d < TS; d += blockDim.x) {

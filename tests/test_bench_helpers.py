@@ -37,7 +37,7 @@ def test_table_checksum_is_shard_additive_and_order_independent():
 def test_profile_parser_reads_the_committed_summaries():
     d = bench.profile_dram_bytes("r2*_k1_up_mma.txt")
     assert d is not None and d["file"].startswith("profiles/") and d["grid"] > 0 and d["ms"] > 0
-    per_site = d["dram_bytes"] / (d["grid"] * 128.0)
+    per_site = d["dram_bytes"] / (d["grid"] * d["sites_per_cta"])
     assert 30e3 < per_site < 80e3      # inner partials read once + output rows: tens of KB per site at config 4
     assert bench.profile_dram_bytes("no_such_profile_*.txt") is None
     p = bench.load_peaks()

@@ -10,7 +10,7 @@ summ() {
 }
 SS="python bench.py --steps 1 --warmup 3 --no-cpu-baseline --rep-cpu 128"
 for k in k1_up_mma k1_down_mma; do
-  ncu --set full --clock-control none --import-source on -k regex:$k -s 7 -c 1 -f -o $O/${T}_$k $SS > $O/${T}_ncu_$k.log 2>&1
+  ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $O/${T}_$k $SS > $O/${T}_ncu_$k.log 2>&1
   summ ${T}_$k
 done
 SP="python bench.py --workload proteins --steps 1 --warmup 3"

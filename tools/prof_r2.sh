@@ -1,7 +1,7 @@
 # ncu evidence for profiles/ (run on the GPU box: bash tools/prof_r2.sh [tag]).  Reports are summarised on the box
 # (tools/ncu_summary.py, tools/ncu_src.py) and deleted: only text comes back through gpurun_out/ (64 MiB limit).
 cd $GRAFT_REPO_ROOT
-T=${1:-r2h}
+T=${1:-r2m}
 O=gpurun_out
 S="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"
 $S > $O/${T}_plain.log 2>&1 || exit 1

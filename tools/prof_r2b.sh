@@ -1,6 +1,6 @@
 # second part of the r2 evidence: the wide (128-site) A = 4 mapping kernels and the protein tensor-core kernels
 cd $GRAFT_REPO_ROOT
-T=${1:-r2h}
+T=${1:-r2m}
 O=gpurun_out
 summ() {
   python tools/ncu_summary.py kernel $O/$1.ncu-rep $O/$1.txt

@@ -390,18 +390,21 @@ __device__ __forceinline__ void pvalues_interleaved(const TileParams& p, const b
 // One pair (row ri of the owned rows = site i, column site j) from its accumulated sum: statistic, filters,
 // stores; the p-value either here (one search) or deferred to pvalues_interleaved (idx / stat / Nmin returned).
 // Shared by the unfused and the tensor-core tile kernels.
+template <int STAT>
+__device__ __forceinline__ double pair_stat(const TileParams& p, int64_t i, int64_t j, double a) {
+  const double nb = (double)p.B;
+  if (STAT == 0) return (a / nb * nb / (nb - 1.)) / mul_(p.sd[i], p.sd2[j]);
+  else if (STAT == 1) return a / nb * nb / (nb - 1.);
+  else if (STAT == 2) return a / mul_(p.norm[i], p.norm2[j]);
+  else if (STAT == 3) return a;
+  else if (STAT == 4) return add_(1., -(sqrt(a) / add_(p.norm[i], p.norm2[j])));
+  else if (STAT == 6) return mi_binary(nb, p.mean[i], p.mean2[j], a); // mean arrays hold the category-1 counts
+  else return sqrt(a);
+}
 template <int STAT, bool DEFER = false>
 __device__ __forceinline__ void pair_epilogue(const TileParams& p, int64_t ri, int64_t i, int64_t j, double a,
                                               int64_t* idx_out = nullptr, double* stat_out = nullptr, double* nm_out = nullptr) {
-  const double nb = (double)p.B;
-  double stat;
-  if (STAT == 0) stat = (a / nb * nb / (nb - 1.)) / mul_(p.sd[i], p.sd2[j]);
-  else if (STAT == 1) stat = a / nb * nb / (nb - 1.);
-  else if (STAT == 2) stat = a / mul_(p.norm[i], p.norm2[j]);
-  else if (STAT == 3) stat = a;
-  else if (STAT == 4) stat = add_(1., -(sqrt(a) / add_(p.norm[i], p.norm2[j])));
-  else if (STAT == 6) stat = mi_binary(nb, p.mean[i], p.mean2[j], a); // mean arrays hold the category-1 counts
-  else stat = sqrt(a);
+  const double stat = pair_stat<STAT>(p, i, j, a);
   if (p.mode == MODE_DIST) {
     double d = p.dist_is_stat ? stat : p.dist_comp - stat;
     p.mat[(size_t)i * p.S + j] = d;
@@ -543,12 +546,13 @@ __global__ void __launch_bounds__(256) k2_tiles_dmma(TileParams p) {
 
 template <int STAT>
 __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
-  __shared__ __align__(16) double As[BK][TS];
-  __shared__ __align__(16) double Bs[BK][TS];
+  __shared__ __align__(16) double stage[2][BK][TS];
+  double (*As)[TS] = stage[0];
+  double (*Bs)[TS] = stage[1];
   const int2 t = p.tiles[blockIdx.x];
   const int64_t i0 = (int64_t)t.x * TS, j0 = (int64_t)t.y * TS;
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4; // thread tile: rows ty*4.., cols tx*4..
+  const int tx = tid & 15, ty = tid >> 4; // thread tile: rows u*16+ty, cols v*16+tx (u, v < 4)
   // loader mapping: 4 elements per thread per operand: k = tid / 16, cols (tid % 16) * 4 ..
   const int lk = tid >> 4, lc = (tid & 15) * 4;
   int64_t ai[4], bj[4];
@@ -595,17 +599,21 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
   fetch(0);
   for (int k0 = 0; k0 < p.B; k0 += BK) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) { As[lk][lc + u] = ra[u]; Bs[lk][lc + u] = rb[u]; }
+    for (int u = 0; u < 4; u += 2) {
+      *reinterpret_cast<double2*>(&As[lk][lc + u]) = make_double2(ra[u], ra[u + 1]);
+      *reinterpret_cast<double2*>(&Bs[lk][lc + u]) = make_double2(rb[u], rb[u + 1]);
+    }
     __syncthreads();
     if (k0 + BK < p.B) fetch(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; kk++) {
+      // rows u*16+ty, columns v*16+tx: every operand read is one 64-bit LDS whose 32 lanes touch one 128-byte
+      // line (a: two addresses, b: sixteen, the other half-warp broadcast) = 1 wavefront.  The 4x4 blocked
+      // mapping (rows ty*4.., cols tx*4.. as 128-bit loads) cost 24 wavefronts per kk against 16 cycles of
+      // FP64 issue (ncu r2m: l1tex 81 %, FP64 pipe 45 %); this one costs 8.
       double a[4], b[4];
-      const double2* ap = reinterpret_cast<const double2*>(&As[kk][ty * 4]);
-      const double2* bp = reinterpret_cast<const double2*>(&Bs[kk][tx * 4]);
-      double2 a0 = ap[0], a1 = ap[1], b0 = bp[0], b1 = bp[1];
-      a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y;
-      b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
+#pragma unroll
+      for (int u = 0; u < 4; u++) { a[u] = As[kk][u * 16 + ty]; b[u] = Bs[kk][u * 16 + tx]; }
 #pragma unroll
       for (int u = 0; u < 4; u++)
 #pragma unroll
@@ -618,10 +626,50 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
     __syncthreads();
   }
 
-  const bool want_pv = p.mode != MODE_DIST && p.K > 0 && (p.o_pvalue || p.o_nsim);
+  if (p.mode == MODE_DIST) {
+    // d(i,j) goes to both triangles.  The upper one is written from the registers (16 lanes = 128 contiguous
+    // bytes); the mirror image is transposed through the (now free) stage memory, 16 tile rows at a time, so that
+    // it leaves as 128-byte row segments too instead of one 8-byte store per matrix row.
+    static_assert(sizeof(stage) >= TS * 17 * sizeof(double), "transpose buffer");
+    double (*T)[17] = reinterpret_cast<double (*)[17]>(&stage[0][0][0]);
+    const int c = tid & 15, r = tid >> 4;
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const int64_t ri = i0 + u * 16 + ty;
+      const int64_t i = ri < p.n_rows ? (p.rows ? p.rows[ri] : ri) : -1;
+#pragma unroll
+      for (int v = 0; v < 4; v++) {
+        const int64_t j = j0 + v * 16 + tx;
+        double d = 0.;
+        if (i >= 0 && j < p.S2 && j > i) {
+          const double stat = pair_stat<STAT>(p, i, j, acc[u][v]);
+          d = p.dist_is_stat ? stat : p.dist_comp - stat;
+          p.mat[(size_t)i * p.S + j] = d;
+        }
+        T[v * 16 + tx][ty] = d;
+      }
+      __syncthreads();
+      const int64_t mri = i0 + u * 16 + c;
+      const int64_t mi = mri < p.n_rows ? (p.rows ? p.rows[mri] : mri) : -1;
+#pragma unroll
+      for (int rr = 0; rr < 4; rr++) {
+        const int64_t j = j0 + rr * 16 + r;
+        if (mi >= 0 && j < p.S2 && j > mi) p.mat[(size_t)j * p.S + mi] = T[rr * 16 + r][c];
+      }
+      __syncthreads();
+    }
+    if (t.x == t.y) { // zero diagonal
+      for (int d = tid; d < TS; d += blockDim.x) {
+        int64_t i = i0 + d;
+        if (i < p.S) p.mat[(size_t)i * p.S + i] = 0.;
+      }
+    }
+    return;
+  }
+  const bool want_pv = p.K > 0 && (p.o_pvalue || p.o_nsim);
 #pragma unroll
   for (int u = 0; u < 4; u++) {
-    const int64_t ri = i0 + ty * 4 + u;
+    const int64_t ri = i0 + u * 16 + ty;
     if (ri >= p.n_rows) continue;
     const int64_t i = p.rows ? p.rows[ri] : ri;
     bool valid[4];
@@ -629,18 +677,12 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
     double st[4], nm[4];
 #pragma unroll
     for (int v = 0; v < 4; v++) {
-      const int64_t j = j0 + tx * 4 + v;
+      const int64_t j = j0 + v * 16 + tx;
       valid[v] = !(j >= p.S2 || (p.mode != MODE_RECT && j <= i));
       idx[v] = 0; st[v] = nm[v] = 0.;
       if (valid[v]) pair_epilogue<STAT, true>(p, ri, i, j, acc[u][v], &idx[v], &st[v], &nm[v]);
     }
     if (want_pv) pvalues_interleaved<4>(p, valid, idx, st, nm);
-  }
-  if (p.mode == MODE_DIST && t.x == t.y) { // zero diagonal
-    for (int d = tid; d < TS; d += blockDim.x) {
-      int64_t i = i0 + d;
-      if (i < p.S) p.mat[(size_t)i * p.S + i] = 0.;
-    }
   }
 }
 

@@ -14,7 +14,14 @@ STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "c
         "corrected_correlation": 5, "mi": 6}
 DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
 LINK = {"complete": 0, "single": 1, "average": 2}
-COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2}
+COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2, "laplace": 3}
+
+
+def count_id(method):
+    """'uniformization' | 'decomposition' | 'naive' | 'laplace' | ('laplace', trunc) -> count_method word."""
+    if isinstance(method, tuple):
+        return COUNT[method[0]] | (int(method[1]) << 8)
+    return COUNT[method]
 
 # every symbol include/comap_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = [
@@ -131,7 +138,7 @@ class Context:
         w = None if weights is None else _f64(weights)
         self.A, self.C = len(pi), len(rates)
         self._chk(self.lib.cmb_set_model(self.h, len(pi), _d(Q), _d(pi), len(rates), _d(rates), _d(probs),
-                                         COUNT[count_method], _d(w)))
+                                         count_id(count_method), _d(w)))
 
     def set_alignment(self, codes, code_mask):
         codes = np.ascontiguousarray(codes, dtype=np.uint8)

@@ -156,7 +156,13 @@ void prepare(Inputs& in, const char* argv0, const Params* override_params = null
   if (nj.name == "Uniformization") in.count_method = CMB_COUNT_UNIFORMIZATION;
   else if (nj.name == "Decomposition") in.count_method = CMB_COUNT_DECOMPOSITION;
   else if (nj.name == "Naive") in.count_method = CMB_COUNT_NAIVE;
-  else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition, Naive)");
+  else if (nj.name == "Laplace") { // Laplace(trunc=10): LaplaceSubstitutionCount, unweighted
+    int trunc = atoi(get_string(nj.args, "trunc", "10").c_str());
+    if (trunc < 2 || trunc > 20) throw Error("nijt=Laplace: trunc must be in 2..20");
+    if (get_string(nj.args, "weight", "None") != "None") throw Error("nijt=Laplace does not take weights");
+    in.count_method = CMB_COUNT_LAPLACE_TRUNC(trunc);
+  }
+  else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition, Naive, Laplace)");
   in.weights = make_count_weights(get_string(nj.args, "weight", "None"), in.alpha, &in.weights_symmetric, data_dir_of(argv0));
   if (!in.weights.empty()) display_result("Substitution count weights", get_string(nj.args, "weight", "None"));
   if (!get_bool(P, "nijt.average", true) || !get_bool(P, "nijt.joint", true))

@@ -42,7 +42,10 @@ extern "C" {
 typedef struct cmb_ctx cmb_ctx;
 
 /* nijt= : PhylogeneticsApplicationTools::getSubstitutionCount, CoMap.cpp:152 */
-enum { CMB_COUNT_UNIFORMIZATION = 0, CMB_COUNT_DECOMPOSITION = 1, CMB_COUNT_NAIVE = 2 };
+enum { CMB_COUNT_UNIFORMIZATION = 0, CMB_COUNT_DECOMPOSITION = 1, CMB_COUNT_NAIVE = 2,
+       CMB_COUNT_LAPLACE = 3 /* Laplace(trunc=10): unweighted; pinned by Myo_laplace.vec */ };
+/* nijt=Laplace(trunc=k), k in 2..20: the truncation order rides in the upper bits of count_method */
+#define CMB_COUNT_LAPLACE_TRUNC(k) (CMB_COUNT_LAPLACE | ((k) << 8))
 /* statistic= : CoETools::getStatistic, CoETools.cpp:535-600; Statistics.h:164-295 */
 enum {
   CMB_STAT_CORRELATION = 0,

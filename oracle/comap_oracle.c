@@ -225,9 +225,65 @@ static void counts_naive(const spectral_t* sp, const double* weights, double* N)
     for (int y = 0; y < A; y++) N[x * A + y] = x == y ? 0. : (weights ? weights[x * A + y] : 1.);
 }
 
+/* [Bio++] MatrixTools::pow as the library that wrote Myo_laplace.vec evaluated it: 0, 1 and 2 directly,
+ * above that by halving -- odd p: pow(p/2) squared; even p: pow((p-1)/2) squared, times A.  That is NOT
+ * A^p from p = 3 on (it yields A^2, A^3, A^4, A^5, A^4, A^5, A^6 for p = 3..9); the golden is only
+ * reproduced with it (exact powers: off by up to 0.68; these: 1.3e-5 = printed precision). */
+static void mat_pow_bpp(int A, const double* M, int p, double* O) {
+  int AA = A * A;
+  if (p == 0) { for (int i = 0; i < AA; i++) O[i] = (i / A == i % A); return; }
+  if (p == 1) { memcpy(O, M, sizeof(double) * AA); return; }
+  if (p == 2) { mat_mul(A, M, M, O); return; }
+  double* tmp = malloc(sizeof(double) * AA);
+  if (p % 2) {
+    mat_pow_bpp(A, M, p / 2, tmp);
+    mat_mul(A, tmp, tmp, O);
+  } else {
+    double* sq = malloc(sizeof(double) * AA);
+    mat_pow_bpp(A, M, (p - 1) / 2, tmp);
+    mat_mul(A, tmp, tmp, sq);
+    mat_mul(A, M, sq, O);
+    free(sq);
+  }
+  free(tmp);
+}
+
+/* nijt=Laplace(trunc=k) [Bio++ LaplaceSubstitutionCount::computeCounts; pinned by
+ * examples/Proteins/Benchmark/CoMap/Myo_laplace.vec, analyse.sh:12-15]:
+ *   m = sum_{n=1}^{k-1} t^n / n!  sum_{p=0}^{n-1} pow(Q,p) QL pow(Q,n-p-1),  QL = Q with a zero diagonal,
+ *   counts = m / P(t), entry by entry, no clean-up (zeroing negatives breaks the golden). */
+static void counts_laplace(const spectral_t* sp, const double* Q, int trunc, double t, double* N) {
+  int A = sp->A, AA = A * A;
+  double* QL = malloc(sizeof(double) * AA);
+  double* M2 = malloc(sizeof(double) * AA);
+  double* M3 = malloc(sizeof(double) * AA);
+  double* M4 = malloc(sizeof(double) * AA);
+  double* M5 = malloc(sizeof(double) * AA);
+  double* P = malloc(sizeof(double) * AA);
+  for (int i = 0; i < AA; i++) { QL[i] = (i / A == i % A) ? 0. : Q[i]; N[i] = 0.; }
+  double fact = 1.;
+  for (int n = 1; n < trunc; n++) {
+    fact *= n;
+    for (int i = 0; i < AA; i++) M2[i] = 0.;
+    for (int p = 0; p < n; p++) {
+      mat_pow_bpp(A, Q, p, M3);
+      mat_mul(A, M3, QL, M4);
+      mat_pow_bpp(A, Q, n - p - 1, M3);
+      mat_mul(A, M4, M3, M5);
+      for (int i = 0; i < AA; i++) M2[i] += M5[i];
+    }
+    double f = pow(t, (double)n) / fact;
+    for (int i = 0; i < AA; i++) N[i] += M2[i] * f;
+  }
+  spectral_pmatrix(sp, t, P);
+  for (int i = 0; i < AA; i++) N[i] /= P[i];
+  free(QL); free(M2); free(M3); free(M4); free(M5); free(P);
+}
+
 static void counts_any(int method, const spectral_t* sp, const double* Q, const double* weights,
                        double t, double* N) {
-  if (method == ORC_COUNT_NAIVE) counts_naive(sp, weights, N);
+  if ((method & 0xff) == ORC_COUNT_LAPLACE) counts_laplace(sp, Q, (method >> 8) ? (method >> 8) : 10, t, N);
+  else if (method == ORC_COUNT_NAIVE) counts_naive(sp, weights, N);
   else if (method == ORC_COUNT_DECOMPOSITION) counts_decomposition(sp, Q, weights, t, N);
   else counts_uniformization(sp, Q, weights, t, N);
 }
@@ -235,7 +291,7 @@ static void counts_any(int method, const spectral_t* sp, const double* Q, const 
 int orc_counts(int method, int A, const double* Q, const double* pi, const double* weights,
                double t, double* N) {
   spectral_t sp;
-  if (method < ORC_COUNT_UNIFORMIZATION || method > ORC_COUNT_NAIVE) FAIL("orc_counts: unknown method %d", method);
+  if ((method & 0xff) < ORC_COUNT_UNIFORMIZATION || (method & 0xff) > ORC_COUNT_LAPLACE) FAIL("orc_counts: unknown method %d", method);
   if (spectral_init(&sp, A, Q, pi)) return -1;
   counts_any(method, &sp, Q, weights, t, N);
   spectral_free(&sp);

@@ -36,7 +36,8 @@
 extern "C" {
 #endif
 
-enum { ORC_COUNT_UNIFORMIZATION = 0, ORC_COUNT_DECOMPOSITION = 1, ORC_COUNT_NAIVE = 2 };
+enum { ORC_COUNT_UNIFORMIZATION = 0, ORC_COUNT_DECOMPOSITION = 1, ORC_COUNT_NAIVE = 2,
+       ORC_COUNT_LAPLACE = 3 /* | trunc << 8; trunc 0 = 10 */ };
 enum {
   ORC_STAT_CORRELATION = 0,
   ORC_STAT_COVARIANCE = 1,

@@ -20,7 +20,7 @@ def load_vec(p):
 def main():
     bm = REF + "/examples/Proteins/Benchmark/CoMap/"
     out = {}
-    for k in ("unif", "decomp", "naive", "unif_grantham", "decomp_grantham", "naive_grantham"):
+    for k in ("unif", "decomp", "naive", "laplace", "unif_grantham", "decomp_grantham", "naive_grantham"):
         coords, mean, M = load_vec(bm + "Myo_%s.vec" % k)
         out["vec_" + k] = M            # [branch][site], 6 significant digits
     out["vec_coords"] = coords

@@ -14,7 +14,14 @@ STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "c
         "corrected_correlation": 5, "mi": 6}
 DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
 LINK = {"complete": 0, "single": 1, "average": 2}
-COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2}
+COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2, "laplace": 3}
+
+
+def count_id(method):
+    """'uniformization' | 'decomposition' | 'naive' | 'laplace' | ('laplace', trunc) -> count_method word."""
+    if isinstance(method, tuple):
+        return COUNT[method[0]] | (int(method[1]) << 8)
+    return COUNT[method]
 
 _lib = None
 
@@ -60,7 +67,7 @@ def counts(Q, pi, t, method="uniformization", weights=None):
     A = len(pi)
     N = np.empty((A, A))
     w = None if weights is None else _f64(weights)
-    _chk(lib().orc_counts(COUNT[method], A, _d(_f64(Q)), _d(_f64(pi)), _d(w), C.c_double(t), _d(N)))
+    _chk(lib().orc_counts(count_id(method), A, _d(_f64(Q)), _d(_f64(pi)), _d(w), C.c_double(t), _d(N)))
     return N
 
 
@@ -87,7 +94,7 @@ def map_sites(parent, brlen, Q, pi, rates, probs, codes, code_mask, method="unif
     norm = np.empty(S) if want_vectors else None
     pr = np.empty(S); rc = np.empty(S, dtype=np.int32); ll = np.empty(S)
     w = None if weights is None else _f64(weights)
-    _chk(lib().orc_map(*ta, *ma, COUNT[method], _d(w), C.c_int64(S), _p(codes, C.c_uint8),
+    _chk(lib().orc_map(*ta, *ma, count_id(method), _d(w), C.c_int64(S), _p(codes, C.c_uint8),
                        len(code_mask), _p(code_mask, C.c_uint32), _d(n), _d(norm), _d(pr),
                        _p(rc, C.c_int32), _d(ll)))
     return dict(n=n, norm=norm, post_rate=pr, rate_class=rc, loglik=ll)
@@ -208,7 +215,7 @@ def null_intra(parent, brlen, Q, pi, rates, probs, stat_name, sim1, sim2, K, nma
     tot = rep_cpu * rep_ram
     raw = np.empty((tot, 4)); offs = np.zeros(K + 1, dtype=np.int64); srt = np.empty(tot)
     w = None if weights is None else _f64(weights)
-    _chk(lib().orc_null_intra(*ta, *ma, COUNT[method], _d(w), STAT[stat_name], rep_cpu, rep_ram,
+    _chk(lib().orc_null_intra(*ta, *ma, count_id(method), _d(w), STAT[stat_name], rep_cpu, rep_ram,
                               _p(sim1, C.c_uint8), _p(sim2, C.c_uint8), K, C.c_double(nmax),
                               _d(raw), _p(offs, C.c_int64), _d(srt)))
     return dict(raw=raw, bin_offsets=offs, sorted=srt[:offs[-1]])

@@ -51,6 +51,17 @@ COMMON = ["param=comap.bpp", "input.sequence.file=Myoglobin.aln.sel.mase", "inpu
           "nijt=Uniformization", "--seed=11"]
 
 
+def test_laplace_count_from_the_command_line_matches_its_golden(myo):
+    """examples/Proteins/Benchmark/CoMap/analyse.sh:12-15: comap param=comap.bpp nijt=Laplace -> Myo_laplace.vec."""
+    tmp, golden = myo
+    run(tmp, *[a for a in COMMON if not a.startswith("nijt=")], "nijt=Laplace", "analysis=none", "output.vectors.file=Myo_laplace.vec")
+    _, rows = table(os.path.join(tmp, "Myo_laplace.vec"))
+    vec = np.array([[float(x) for x in r[2:]] for r in rows])
+    assert vec.shape == (197, 129)
+    err = np.abs(vec - golden["vec_laplace"])
+    assert err.max() < 3e-5 and np.median(err / np.abs(golden["vec_laplace"])) < 1e-5
+
+
 def test_mapping_only_matches_reference_golden_files(myo):
     tmp, golden = myo
     run(tmp, *COMMON, "analysis=none", "output.vectors.file=Myo.vec", "output.infos=Myo.infos")

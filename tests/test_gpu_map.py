@@ -102,7 +102,7 @@ def test_map_myoglobin_golden(ctx):
     assert np.all(np.abs(r["loglik"] - m["golden"]["infos_logl"]) <= 6e-6 * np.abs(m["golden"]["infos_logl"]))
 
 
-@pytest.mark.parametrize("method,key", [("naive", "vec_naive"), ("naive", "vec_naive_grantham"),
+@pytest.mark.parametrize("method,key", [("naive", "vec_naive"), ("naive", "vec_naive_grantham"), ("laplace", "vec_laplace"),
                                         ("uniformization", "vec_unif_grantham"), ("decomposition", "vec_decomp_grantham")])
 def test_map_count_methods_and_weights_vs_reference_goldens(ctx, method, key):
     """nijt=Naive and the Grantham-weighted counts on the device against the oracle (1e-9) and against
@@ -124,6 +124,12 @@ def test_map_count_methods_and_weights_vs_reference_goldens(ctx, method, key):
     big = gold > 1e-9
     rel = np.abs(r["n"] - gold)[big] / gold[big]
     assert np.median(rel) < 5e-6 and rel.max() < 3e-4
+    if method == "laplace":  # Laplace(trunc=10) is the default order; weights are refused as Bio++ has none for it
+        ctx.set_model(m["Q"], m["pi"], m["rates"], m["probs"], count_method=("laplace", 10))
+        ctx.set_alignment(m["codes"], m["code_mask"])
+        assert np.array_equal(ctx.map()["n"], r["n"])
+        with pytest.raises(RuntimeError, match="Laplace"):
+            ctx.set_model(m["Q"], m["pi"], m["rates"], m["probs"], count_method="laplace", weights=np.ones((20, 20)))
 
 
 def test_errors_are_reported(ctx):

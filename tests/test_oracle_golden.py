@@ -79,6 +79,22 @@ def test_naive_count_vs_golden():
     assert np.median(rel) < 5e-6 and rel.max() < 2e-4 and (rel > 1e-5).mean() < 0.1
 
 
+def test_laplace_count_vs_golden():
+    """nijt=Laplace (trunc = 10, analyse.sh:12-15 -> Myo_laplace.vec).  The golden is only reproduced with the
+    matrix powers of the Bio++ that wrote it (oracle: mat_pow_bpp); it differs from the converged counts
+    (Myo_unif.vec) by up to 0.69, so the test also shows that the series is NOT simply the exact count."""
+    m, r = _run("laplace")
+    gold = m["golden"]["vec_laplace"].T
+    err = np.abs(r["n"] - gold)
+    assert err.max() < 2e-5 and np.median(err / np.abs(gold)) < 5e-6
+    assert np.abs(gold - m["golden"]["vec_unif"].T).max() > 0.6
+    # the truncation order rides in the count word: trunc = 10 is the default, another order moves the vectors
+    _, r10 = _run(("laplace", 10))
+    assert np.array_equal(r10["n"], r["n"])
+    _, r6 = _run(("laplace", 6))
+    assert np.abs(r6["n"] - gold).max() > 1e-2
+
+
 def test_weighted_counts_vs_grantham_goldens():
     """Weighted substitution counts, nijt=<method>(weight=AAdist(type=grantham, sym=yes)) -> Myo_{unif,decomp,
     naive}_grantham.vec.  The Grantham table (comap_b200/data/grantham.dat) is itself recovered from

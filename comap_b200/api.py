@@ -11,10 +11,10 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcomap_b200.so")
 
 STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "compensation": 4,
-        "corrected_correlation": 5, "mi": 6}
+        "corrected_correlation": 5, "mi": 6, "mi_label": 7}
 DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
 LINK = {"complete": 0, "single": 1, "average": 2}
-COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2, "laplace": 3}
+COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2, "laplace": 3, "label": 4}
 
 
 def count_id(method):
@@ -30,7 +30,7 @@ SYMBOLS = [
     "cmb_simulate", "cmb_null_intra", "cmb_null_intra_from_alignments", "cmb_null_samples_dev",
     "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
-    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates", "cmb_set_async", "cmb_set_mi_threshold",
+    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates", "cmb_set_async", "cmb_set_mi_threshold", "cmb_set_map_mode",
     "cmb_comm_unique_id", "cmb_comm_init", "cmb_comm_init_all", "cmb_comm_set", "cmb_comm_destroy", "cmb_comm_rank",
     "cmb_comm_group_start", "cmb_comm_group_end", "cmb_null_intra_sharded", "cmb_set_continuous_rates",
 ]
@@ -186,6 +186,10 @@ class Context:
                                                           _p(sim1, C.c_uint8), _p(sim2, C.c_uint8), K,
                                                           C.c_double(nmax), _d(raw)))
         return raw
+
+    def set_map_mode(self, average=True, joint=True):
+        """nijt.average / nijt.joint (CoETools.cpp:393-407): which mapping function fills the vectors from now on."""
+        self._chk(self.lib.cmb_set_map_mode(self.h, int(bool(average)), int(bool(joint))))
 
     def set_mi_threshold(self, threshold):
         """Threshold of statistic 'mi' (MI(threshold=0.99) upstream)."""

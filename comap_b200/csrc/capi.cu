@@ -72,6 +72,7 @@ void Context::ensure_streams() {
   if (streams_ready) return;
   build_model_tables(tables, A, Q.data(), pi.data(), C, rates.data(), probs.data(), count_method,
                      have_weights ? weights.data() : nullptr, tree.B, tree.brlen.data());
+  var_ready = false;
   check_map_support(A, C);
   // cherries are recomputed instead of stored when their two extra tables per record are
   // small (nucleotides); for A = 20 the records would outgrow the shared-memory budget
@@ -227,8 +228,34 @@ void Context::finish_map() {
   finalize_map_host();
 }
 
+VariantTables Context::variant_tables() {
+  const int n = tree.n_nodes;
+  if (!var_ready) {
+    std::vector<int32_t> h((size_t)4 * n + 1, 0);
+    int32_t *par = h.data(), *off = par + n, *ch = off + n + 1, *leaf = ch + n - 1;
+    for (int v = 0; v < n; v++) { par[v] = tree.parent[v]; leaf[v] = tree.leaf_row[v]; }
+    for (int v = 0; v < n - 1; v++) off[tree.parent[v] + 1]++;
+    for (int v = 0; v < n; v++) off[v + 1] += off[v];
+    std::vector<int32_t> fill(off, off + n);
+    for (int v = 0; v < n - 1; v++) ch[fill[tree.parent[v]]++] = v; // children in id (= Newick) order
+    var_tree.reserve(sizeof(int32_t) * h.size());
+    CMB_CUDA(cudaMemcpyAsync(var_tree.p, h.data(), sizeof(int32_t) * h.size(), cudaMemcpyHostToDevice, stream));
+    const size_t nt = tables.P.size();
+    var_tabs.reserve(sizeof(double) * 2 * nt);
+    CMB_CUDA(cudaMemcpyAsync(var_tabs.p, tables.P.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, stream));
+    CMB_CUDA(cudaMemcpyAsync(var_tabs.as<double>() + nt, tables.N.data(), sizeof(double) * nt, cudaMemcpyHostToDevice, stream));
+    CMB_CUDA(cudaStreamSynchronize(stream)); // h goes out of scope
+    var_ready = true;
+  }
+  VariantTables vt;
+  vt.n_nodes = n;
+  vt.parent = var_tree.as<int32_t>(); vt.ch_off = vt.parent + n; vt.ch = vt.ch_off + n + 1; vt.leaf_row = vt.ch + n - 1;
+  vt.P = var_tabs.as<double>(); vt.N = vt.P + tables.P.size();
+  return vt;
+}
+
 // Down pass for every class block, site likelihoods, then up pass + contraction.
-void Context::run_map(const MapBuffers& b, bool simulated, bool states_only) {
+void Context::run_map(const MapBuffers& b, bool simulated, bool states_only, bool variants) {
   MapModel m = map_model();
   if (simulated) m.code_mask = d_identity_mask.as<uint32_t>();
   m.states_only = simulated && states_only;
@@ -247,6 +274,12 @@ void Context::run_map(const MapBuffers& b, bool simulated, bool states_only) {
   } else {
     launch_map_up(m, b, up_stream, stream);
     prof_end(1);
+  }
+  if (variants && map_mode) { // nijt.average = no / nijt.joint = no: the vectors are replaced (k1_variants.cu)
+    if (b.n_active) fail("internal: mapping variants need uncompressed batches");
+    const VariantTables vt = variant_tables();
+    prof_begin("map_variant");
+    prof_end(launch_map_variant(m, b, vt, map_mode, simulated ? var_scratch : var_scratch_obs, stream));
   }
 }
 
@@ -324,7 +357,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
                     &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm,
-                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part, &c.k1_part_obs, &c.d_spec, &c.dist_tiles, &c.s_cols, &c.s_counts, &c.cn_mean, &c.cn_sd, &c.cn_norm, &c.cn_staging,
+                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part, &c.k1_part_obs, &c.var_tree, &c.var_tabs, &c.var_scratch, &c.var_scratch_obs, &c.d_spec, &c.dist_tiles, &c.s_cols, &c.s_counts, &c.cn_mean, &c.cn_sd, &c.cn_norm, &c.cn_staging,
                     &c.cn_dists[0], &c.cn_dists[1], &c.cn_dists[2], &c.cn_dists[3], &c.cn_works[0], &c.cn_works[1], &c.cn_works[2],
                     &c.cn_works[3], &c.cn_outs[0], &c.cn_outs[1], &c.cn_outs[2], &c.cn_outs[3]};
   for (DevBuf* b : bufs) b->release();
@@ -412,6 +445,16 @@ int cmb_set_alignment(cmb_ctx* ctx, int64_t S, const uint8_t* codes, int32_t n_c
   c.have_alignment = true;
   c.mapped = false;
   if (c.null.nmax_from_map) c.null.ready = false;
+  CMB_CATCH
+}
+
+int cmb_set_map_mode(cmb_ctx* ctx, int32_t average, int32_t joint) {
+  CMB_TRY
+  Context& c = ctx->c;
+  c.wait_map(); c.map_pending = false;
+  const int mode = (average ? 0 : 2) + (joint ? 0 : 1);
+  if (mode != c.map_mode) { c.mapped = false; c.null.ready = false; c.pairs_rows = -1; c.have_dist = false; }
+  c.map_mode = mode;
   CMB_CATCH
 }
 

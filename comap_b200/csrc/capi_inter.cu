@@ -83,7 +83,7 @@ int cmb_pairs_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, const cmb_fil
   Context& c = ctx1->c;
   Context& d = ctx2->c;
   CMB_CUDA(cudaSetDevice(c.device));
-  if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
+  if (stat_id < 0 || stat_id > CMB_STAT_MI_LABEL) fail("unknown statistic id %d", stat_id);
   check_pair(c, d, "cmb_pairs_inter");
   c.finish_map(); d.finish_map();
   if (!c.mapped || !d.mapped) fail("cmb_pairs_inter: call cmb_map on both data sets first");
@@ -185,7 +185,7 @@ int cmb_null_inter(cmb_ctx* ctx1, cmb_ctx* ctx2, int32_t stat_id, uint64_t seed,
   Context& c = ctx1->c;
   Context& d = ctx2->c;
   CMB_CUDA(cudaSetDevice(c.device));
-  if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
+  if (stat_id < 0 || stat_id > CMB_STAT_MI_LABEL) fail("unknown statistic id %d", stat_id);
   if (rep_ram < 1 || rep_cpu < 0) fail("cmb_null_inter: bad replicate counts");
   if (!raw) fail("cmb_null_inter: raw output buffer required");
   check_pair(c, d, "cmb_null_inter");
@@ -360,7 +360,7 @@ extern "C" int cmb_candidates(cmb_ctx* ctx, int32_t stat_id, int32_t n_groups, c
   CMB_TRY
   Context& c = ctx->c;
   CMB_CUDA(cudaSetDevice(c.device));
-  if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
+  if (stat_id < 0 || stat_id > CMB_STAT_MI_LABEL) fail("unknown statistic id %d", stat_id);
   c.finish_map();
   if (!c.mapped) fail("cmb_candidates: call cmb_map first");
   if (n_groups < 1) fail("ERROR!!! No group can be tested!"); // CoMap.cpp:679-680

@@ -25,7 +25,7 @@ struct cmb_ctx { Context c; };
 namespace {
 
 void check_stat(int stat_id) {
-  if (stat_id < 0 || stat_id > CMB_STAT_MI) fail("unknown statistic id %d", stat_id);
+  if (stat_id < 0 || stat_id > CMB_STAT_MI_LABEL) fail("unknown statistic id %d", stat_id);
 }
 
 // Bytes of device memory one simulated site needs through simulate -> map x2 -> paired.
@@ -147,7 +147,7 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
     // mapping kernels stop at the packed count (a device scalar: no host round trip), and the paired statistic
     // reads each site's vector through a column index.
     const bool dedup_on = !(getenv("CMB_NULL_DEDUP") && atoi(getenv("CMB_NULL_DEDUP")) == 0);
-    const bool dedup = dedup_on && c.A == 4;
+    const bool dedup = dedup_on && c.A == 4 && !c.map_mode; // the variant kernels walk every column
     const int32_t *col1 = nullptr, *col2 = nullptr;
     if (dedup) {
       c.s_tips[1].reserve((size_t)T * n_pad);
@@ -707,7 +707,7 @@ int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t se
       launch_simulate(m, c.sim_stream, seed, (int64_t)rep * S, S, 0, S, S_pad, weighted_classes, c.tree.n_nodes - 1,
                       c.s_tips[0].as<uint8_t>(), nullptr, c.stream);
       c.prof_end(1);
-      c.run_map(b, true);
+      c.run_map(b, true, false, false); // ClusterTools.cpp:227: always computeSubstitutionVectors
       mean.reserve(sizeof(double) * S_pad); sd.reserve(sizeof(double) * S_pad); norm.reserve(sizeof(double) * S_pad);
       launch_prep(B, S, S_pad, b.out, nullptr, mean.as<double>(), sd.as<double>(), norm.as<double>(), c.stream);
       c.prof.total_launches += 1;

@@ -41,6 +41,7 @@ struct ModelTables {
   std::vector<double> pi, rates, probs;
   std::vector<double> P;    // [B][C][A][A]
   std::vector<double> W;    // [B][C][A][A], includes p_c
+  std::vector<double> N;    // [B][C][A][A] the counts themselves (mapping variants, k1_variants.cu)
   std::vector<double> cumP; // [B][C][A][A] running row sums of P (simulator)
 };
 void build_model_tables(ModelTables& mt, int A, const double* Q, const double* pi, int C,

@@ -49,6 +49,11 @@ struct Context {
   bool streams_ready = false;
   bool protein_mma = false;      // A = 20 on the tensor-core kernels (k1_mma20.cu); else the thread-per-site ones
   DevBuf k1_part;                // their per-class partial outputs [C][B][n_pad]
+  // nijt.average / nijt.joint (cmb_set_map_mode): 0 = average + joint (default), 1 marginal, 2 no averaging, 3 neither
+  int map_mode = 0;
+  DevBuf var_tree, var_tabs, var_scratch, var_scratch_obs;
+  bool var_ready = false;
+  VariantTables variant_tables(); // device copies of the original tree and of the P / count tables, built on first use
 
   // observed alignment + its mapping
   int64_t S = 0, S_pad = 0;
@@ -124,7 +129,8 @@ struct Context {
   MapModel map_model() const;
   // maps n sites whose tips are at `tips` ([T][n_pad]); buffers given explicitly
   // simulated: codes are state indices (identity mask); states_only: ... and known to be < A
-  void run_map(const MapBuffers& b, bool simulated, bool states_only = false);
+  // variants: honour map_mode (everything but the clustering null, ClusterTools.cpp:227)
+  void run_map(const MapBuffers& b, bool simulated, bool states_only = false, bool variants = true);
   void prof_begin(const char* name);
   void prof_end(int launches);
   void prof_collect();

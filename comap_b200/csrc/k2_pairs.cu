@@ -58,6 +58,62 @@ __device__ __forceinline__ double mi_binary(double n, double n1x, double n1y, do
   return s;
 }
 
+// statistic=MI with nijt=Label and nijt.average=no (CoETools.cpp:577-589): the bounds -0.5, 0.5, ..., A(A-1)+0.5 make
+// the category of a branch its substitution label (0 = no substitution) and the statistic is the same
+// [Bio++, from memory] miDiscrete over every occupied cell of the joint table.  Most branches of a site carry no
+// substitution, so only the branches where either site has one are listed (packed keys); the (0, 0) cell and the
+// marginals of category 0 follow from the list.  A pair with more than kMiList such branches re-reads its columns.
+constexpr int kMiList = 64;
+__device__ __forceinline__ int label_of(double v) {
+  if (!(v >= -0.5)) return 0;          // below the first bound the reference's Domain throws; labels never are
+  int k = (int)floor(v);
+  if (v >= (double)k + 0.5) k++;
+  return k > 65535 ? 65535 : k;
+}
+__device__ __forceinline__ double mi_term(double n, double lb, double c12, double c1, double c2) {
+  return mul_(c12 / n, log(mul_(c12, n) / mul_(c1, c2))) / lb;
+}
+__device__ __noinline__ double mi_labels(const double* __restrict__ x, size_t sx, const double* __restrict__ y, size_t sy, int B) {
+  int keys[kMiList];
+  int m = 0, n1 = 0, n2 = 0;
+  for (int b = 0; b < B; b++) {
+    const int a = label_of(x[(size_t)b * sx]), c = label_of(y[(size_t)b * sy]);
+    if (a | c) {
+      if (m < kMiList) keys[m] = a << 16 | c;
+      m++; n1 += a != 0; n2 += c != 0;
+    }
+  }
+  const double n = (double)B, lb = log(2.7182818);
+  const double c10 = (double)(B - n1), c20 = (double)(B - n2);
+  double s = 0.;
+  if (B - m > 0) s = mi_term(n, lb, (double)(B - m), c10, c20);
+  if (m <= kMiList) {
+    for (int e = 0; e < m; e++) {
+      const int key = keys[e], a = key >> 16, c = key & 0xffff;
+      bool first = true;
+      for (int f = 0; f < e; f++) first = first && keys[f] != key;
+      if (!first) continue;
+      int c12 = 0, c1 = 0, c2 = 0;
+      for (int f = 0; f < m; f++) { c12 += keys[f] == key; c1 += (keys[f] >> 16) == a; c2 += (keys[f] & 0xffff) == c; }
+      s = add_(s, mi_term(n, lb, (double)c12, a ? (double)c1 : c10, c ? (double)c2 : c20));
+    }
+  } else {
+    for (int b = 0; b < B; b++) {
+      const int a = label_of(x[(size_t)b * sx]), c = label_of(y[(size_t)b * sy]);
+      if (!(a | c)) continue;
+      int c12 = 0, c1 = 0, c2 = 0;
+      bool first = true;
+      for (int f = 0; f < B; f++) {
+        const int a2 = label_of(x[(size_t)f * sx]), c2v = label_of(y[(size_t)f * sy]);
+        if (a2 == a && c2v == c) { c12++; if (f < b) first = false; }
+        c1 += a2 == a; c2 += c2v == c;
+      }
+      if (first) s = add_(s, mi_term(n, lb, (double)c12, (double)c1, (double)c2));
+    }
+  }
+  return s;
+}
+
 template <int STAT>
 __global__ void __launch_bounds__(128) k2_paired(double thr, int B, int64_t n, int64_t n_pad, int64_t n_pad2, const double* __restrict__ o1,
                           const double* __restrict__ o2, const double* __restrict__ mv, const double* __restrict__ mv2,
@@ -89,6 +145,7 @@ __global__ void __launch_bounds__(128) k2_paired(double thr, int B, int64_t n, i
   }
   double r;
   if (stat_id == 6) r = mi_binary(nb, sxy, s3, cnt);
+  else if (stat_id == 7) r = mi_labels(o1 + j, (size_t)n_pad, o2 + j, (size_t)n_pad2, B);
   else if (stat_id == 0 || stat_id == 1) {
     const double mx = sx / nb, my = sy / nb;
     double cxy = 0., cxx = 0., cyy = 0.;
@@ -141,6 +198,7 @@ __global__ void k2_pair_list(int stat_id, double thr, int B, int64_t n_pad, cons
   }
   double r;
   if (stat_id == 6) r = mi_binary(nb, sxy, s3, cnt);
+  else if (stat_id == 7) r = mi_labels(o + ja, (size_t)n_pad, o + jb, (size_t)n_pad, B);
   else if (stat_id == 0 || stat_id == 1) {
     const double mx = sx / nb, my = sy / nb;
     double cxy = 0., cxx = 0., cyy = 0.;
@@ -334,6 +392,7 @@ __device__ __forceinline__ double tile_load(double x, double mean, double thr = 
   if (STAT == 0 || STAT == 1) return add_(x, -mean);
   if (STAT == 3) return x >= 1. ? 1. : 0.;
   if (STAT == 6) return x >= thr ? 1. : 0.;
+  if (STAT == 7) return 0.; // the label statistic reads its two columns in the epilogue (mi_labels)
   return x;
 }
 
@@ -399,6 +458,7 @@ __device__ __forceinline__ double pair_stat(const TileParams& p, int64_t i, int6
   else if (STAT == 3) return a;
   else if (STAT == 4) return add_(1., -(sqrt(a) / add_(p.norm[i], p.norm2[j])));
   else if (STAT == 6) return mi_binary(nb, p.mean[i], p.mean2[j], a); // mean arrays hold the category-1 counts
+  else if (STAT == 7) return mi_labels(p.out + i, (size_t)p.S_pad, p.out2 + j, (size_t)p.S2_pad, p.B); // from the columns themselves
   else return sqrt(a);
 }
 template <int STAT, bool DEFER = false>
@@ -756,6 +816,7 @@ void launch_paired(int stat_id, double thr, int B, int64_t n, int64_t n_pad, int
     case 3: k2_paired<3><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
     case 4: k2_paired<4><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
     case 6: k2_paired<6><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
+    case 7: k2_paired<7><<<g, 128, 0, st>>>(thr, B, n, n_pad, n_pad2, o1, o2, mv, mv2, stat, nmin, col1, col2); break;
     default: fail("unknown statistic id %d", stat_id);
   }
   CMB_CUDA(cudaGetLastError());
@@ -880,6 +941,7 @@ int launch_tiles(const TilesLaunch& L, cudaStream_t st) {
     case 4: k2_tiles<4><<<g, 256, 0, st>>>(p); break;
     case 5: k2_tiles<5><<<g, 256, 0, st>>>(p); break;
     case 6: k2_tiles<6><<<g, 256, 0, st>>>(p); break;
+    case 7: k2_tiles<7><<<g, 256, 0, st>>>(p); break;
     default: fail("unknown statistic id %d", L.stat_id);
   }
   CMB_CUDA(cudaGetLastError());

@@ -62,6 +62,14 @@ void launch_map_down_mma(const MapModel& m, const MapBuffers& b, const DevStream
 // false = no launch shape fits (the caller reports it)
 bool launch_map_down_mma20(const MapModel& m, const MapBuffers& b, const DevStream& s, cudaStream_t st);
 bool launch_map_up_mma20(const MapModel& m, const MapBuffers& b, const DevStream& s, double* part, cudaStream_t st);
+// nijt.average = no / nijt.joint = no (k1_variants.cu): thread-per-site walk of the original tree
+struct VariantTables {
+  int n_nodes = 0;
+  const int32_t *parent = nullptr, *ch_off = nullptr, *ch = nullptr, *leaf_row = nullptr;
+  const double *P = nullptr, *N = nullptr; // [branch][C][A][A]
+};
+// mode 1 marginal, 2 no averaging, 3 no averaging + marginal states; overwrites b.out for sites [0, b.n); returns launches
+int launch_map_variant(const MapModel& m, const MapBuffers& b, const VariantTables& vt, int mode, DevBuf& scratch, cudaStream_t st);
 // A = 4 partial layout: 128-site chunks (common.h kChunkSites), [chunk][slot][class][site][state]
 __host__ __device__ inline size_t d_chunk(int64_t chunk, int slot, int n_slots, int C) {
   return ((size_t)chunk * n_slots + slot) * ((size_t)C * kChunkSites * 4);

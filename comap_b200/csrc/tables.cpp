@@ -231,7 +231,8 @@ void build_model_tables(ModelTables& mt, int A, const double* Q, const double* p
   // nijt=Laplace carries its truncation order in the upper bits (CMB_COUNT_LAPLACE_TRUNC)
   const int laplace_trunc = (count_method & 0xff) == 3 ? ((count_method >> 8) ? (count_method >> 8) : 10) : 0;
   count_method &= 0xff;
-  if (count_method < 0 || count_method > 3) fail("cmb_set_model: unknown count method %d", count_method);
+  if (count_method < 0 || count_method > 4) fail("cmb_set_model: unknown count method %d", count_method);
+  if (count_method == 4 && weights) fail("cmb_set_model: nijt=Label takes no weights");
   if (count_method == 3 && (laplace_trunc < 2 || laplace_trunc > 20))
     fail("cmb_set_model: nijt=Laplace needs trunc in 2..20 (got %d)", laplace_trunc);
   if (count_method == 3 && weights) fail("cmb_set_model: nijt=Laplace takes no weights (LaplaceSubstitutionCount is not a weighted count)");
@@ -245,6 +246,7 @@ void build_model_tables(ModelTables& mt, int A, const double* Q, const double* p
   mt.probs.assign(probs, probs + C);
   mt.P.assign((size_t)B * C * AA, 0.);
   mt.W.assign((size_t)B * C * AA, 0.);
+  mt.N.assign((size_t)B * C * AA, 0.);
   mt.cumP.assign((size_t)B * C * AA, 0.);
   Mat num;
   for (int b = 0; b < B; b++)
@@ -252,22 +254,31 @@ void build_model_tables(ModelTables& mt, int A, const double* Q, const double* p
       double t = brlen[b] * rates[c];
       double* P = &mt.P[((size_t)b * C + c) * AA];
       double* W = &mt.W[((size_t)b * C + c) * AA];
+      double* N = &mt.N[((size_t)b * C + c) * AA];
       double* cum = &mt.cumP[((size_t)b * C + c) * AA];
       sp.pmatrix(t, P);
       if (count_method == 2) { // nijt=Naive: one substitution (or its weight) when the ends differ
         for (int x = 0; x < A; x++)
           for (int y = 0; y < A; y++)
-            W[x * A + y] = x == y ? 0. : probs[c] * (P[x * A + y] * (weights ? weights[x * A + y] : 1.));
+            W[x * A + y] = x == y ? 0. : probs[c] * (P[x * A + y] * (N[x * A + y] = weights ? weights[x * A + y] : 1.));
+      } else if (count_method == 4) { // nijt=Label: substitution x -> y carries the label 1 + its rank among the off-diagonal entries
+        int label = 0;
+        for (int x = 0; x < A; x++)
+          for (int y = 0; y < A; y++) {
+            N[x * A + y] = x == y ? 0. : (double)++label;
+            W[x * A + y] = probs[c] * (P[x * A + y] * N[x * A + y]);
+          }
       } else if (count_method == 0) uniformization_numerator(A, Q, weights, t, num);
       else if (count_method == 3) {
         lap.numerator(t, num);
-        for (size_t i = 0; i < AA; i++) W[i] = probs[c] * (P[i] * (num[i] / P[i])); // no clean-up (see LaplaceSeries)
+        for (size_t i = 0; i < AA; i++) W[i] = probs[c] * (P[i] * (N[i] = num[i] / P[i])); // no clean-up (see LaplaceSeries)
       } else decomposition_numerator(sp, Q, weights, t, num);
       for (size_t i = 0; count_method < 2 && i < AA; i++) {
         // reference: n = num / P with NaN/Inf -> 0 and (unweighted) negatives -> 0, then
         // the mapping multiplies by P again; W = P * n folds both.
         double n = num[i] / P[i];
         if (std::isnan(n) || std::isinf(n) || (!weights && n < 0.)) n = 0.;
+        N[i] = n;
         W[i] = probs[c] * (P[i] * n);
       }
       for (int x = 0; x < A; x++) {

@@ -79,6 +79,7 @@ struct Inputs {
   std::vector<uint8_t> codes; // [T][S], rows in leaf order
   std::vector<uint32_t> code_mask;
   int count_method = CMB_COUNT_UNIFORMIZATION;
+  bool average = true, joint = true; // nijt.average / nijt.joint (CoETools.cpp:393-394)
   std::vector<double> weights;   // weighted substitution count (nijt=...(weight=...)); empty = unweighted
   bool weights_symmetric = true;
 };
@@ -162,11 +163,16 @@ void prepare(Inputs& in, const char* argv0, const Params* override_params = null
     if (get_string(nj.args, "weight", "None") != "None") throw Error("nijt=Laplace does not take weights");
     in.count_method = CMB_COUNT_LAPLACE_TRUNC(trunc);
   }
-  else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition, Naive, Laplace)");
+  else if (nj.name == "Label") { // LabelSubstitutionCount: one label per substitution type (for statistic=MI)
+    if (get_string(nj.args, "weight", "None") != "None") throw Error("nijt=Label does not take weights");
+    in.count_method = CMB_COUNT_LABEL;
+  }
+  else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition, Naive, Laplace, Label)");
   in.weights = make_count_weights(get_string(nj.args, "weight", "None"), in.alpha, &in.weights_symmetric, data_dir_of(argv0));
   if (!in.weights.empty()) display_result("Substitution count weights", get_string(nj.args, "weight", "None"));
-  if (!get_bool(P, "nijt.average", true) || !get_bool(P, "nijt.joint", true))
-    throw Error("nijt.average=no / nijt.joint=no (benchmark-only variants) are not available in this build");
+  in.average = get_bool(P, "nijt.average", true); // "really for benchmarking only" upstream; k1_variants.cu here
+  in.joint = get_bool(P, "nijt.joint", true);
+  if (!in.average || !in.joint) display_result("Mapping variant", std::string(in.average ? "average" : "no averaging") + (in.joint ? ", joint pair" : ", marginal"));
   display_result("Substitution count", nj.name);
   // leaf rows: sequence of every leaf, in leaf id order
   std::map<std::string, int> row;
@@ -227,6 +233,7 @@ void dry_run_dump(const Inputs& in) {
   std::cout << "\nDRYRUN codes";
   for (uint8_t c : in.codes) std::cout << ' ' << (int)c;
   std::cout << "\nDRYRUN count_method " << in.count_method;
+  std::cout << "\nDRYRUN map_mode " << in.average << " " << in.joint;
   std::cout << "\nDRYRUN weights";
   for (double x : in.weights) std::cout << ' ' << x;
   std::cout << std::endl;
@@ -249,10 +256,11 @@ int stat_id_of(const Params& P, const Inputs& in) {
   }
   if (st.name == "CorrectedCorrelation") return CMB_STAT_CORRECTED_CORRELATION; // mean vector: CoMap.cpp:350-359
   if (st.name == "MI") { // CoETools.cpp:576-596
-    std::string nj = get_string(P, "nijt", "Label");
-    if (nj == "Label")
-      throw Error("statistic=MI with nijt=Label (one category per substitution type) is not available in this build; "
-                  "use e.g. nijt=Uniformization, which discretises the counts at MI(threshold=...)");
+    std::string nj = get_string(P, "nijt", "Label"); // upstream compares the raw option string, default "Label"
+    if (nj == "Label") {
+      if (in.average) throw Error("MI distance with 'nijt=Label' can't be used with 'nijt.average=yes'.");
+      return CMB_STAT_MI_LABEL; // bounds -0.5, 0.5, ...: one category per substitution label
+    }
     return CMB_STAT_MI;
   }
   throw Error("Unknown statistic used: " + get_string(P, "statistic", ""));
@@ -317,6 +325,7 @@ Mapped map_data_set(Inputs& in, const Params& P, const std::string& suffix) {
   chk(cmb_set_model(m.ctx, in.model.A, in.model.Q.data(), in.model.pi.data(), (int32_t)in.rdist.rates.size(),
                     in.rdist.rates.data(), in.rdist.probs.data(), in.count_method,
                     in.weights.empty() ? nullptr : in.weights.data()));
+  chk(cmb_set_map_mode(m.ctx, in.average, in.joint));
   chk(cmb_set_alignment(m.ctx, S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
   {
     Procedure st = parse_procedure(get_string(P, "statistic", "Correlation"));
@@ -483,6 +492,7 @@ int main(int argc, char** argv) {
         chk(cmb_set_tree(ctxs[r], (int32_t)in.tree.parent.size(), in.tree.parent.data(), in.tree.brlen.data()));
         chk(cmb_set_model(ctxs[r], in.model.A, in.model.Q.data(), in.model.pi.data(), (int32_t)in.rdist.rates.size(),
                           in.rdist.rates.data(), in.rdist.probs.data(), in.count_method, in.weights.empty() ? nullptr : in.weights.data()));
+        chk(cmb_set_map_mode(ctxs[r], in.average, in.joint));
         chk(cmb_set_alignment(ctxs[r], S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
         Procedure st = parse_procedure(get_string(P, "statistic", "Correlation"));
         if (st.name == "MI") chk(cmb_set_mi_threshold(ctxs[r], get_double(st.args, "threshold", 0.99)));

@@ -43,7 +43,8 @@ typedef struct cmb_ctx cmb_ctx;
 
 /* nijt= : PhylogeneticsApplicationTools::getSubstitutionCount, CoMap.cpp:152 */
 enum { CMB_COUNT_UNIFORMIZATION = 0, CMB_COUNT_DECOMPOSITION = 1, CMB_COUNT_NAIVE = 2,
-       CMB_COUNT_LAPLACE = 3 /* Laplace(trunc=10): unweighted; pinned by Myo_laplace.vec */ };
+       CMB_COUNT_LAPLACE = 3 /* Laplace(trunc=10): unweighted; pinned by Myo_laplace.vec */,
+       CMB_COUNT_LABEL = 4 /* Label: substitution x -> y counts as its label 1..A(A-1) (for MI, CoETools.cpp:577-589) */ };
 /* nijt=Laplace(trunc=k), k in 2..20: the truncation order rides in the upper bits of count_method */
 #define CMB_COUNT_LAPLACE_TRUNC(k) (CMB_COUNT_LAPLACE | ((k) << 8))
 /* statistic= : CoETools::getStatistic, CoETools.cpp:535-600; Statistics.h:164-295 */
@@ -54,8 +55,10 @@ enum {
   CMB_STAT_COSUBSTITUTION = 3,
   CMB_STAT_COMPENSATION = 4,
   CMB_STAT_CORRECTED_CORRELATION = 5, /* Statistics.h:176-205; mean vector as CoMap.cpp:350-359 */
-  CMB_STAT_MI = 6 /* MI(threshold=..) without nijt=Label: DiscreteMutualInformationStatistic over the
+  CMB_STAT_MI = 6, /* MI(threshold=..) without nijt=Label: DiscreteMutualInformationStatistic over the
                      bounds {0, threshold, 10000} (CoETools.cpp:590-595, Statistics.h:307-329) */
+  CMB_STAT_MI_LABEL = 7 /* MI with nijt=Label and nijt.average=no: one category per substitution label, bounds
+                           -0.5, 0.5, ..., A(A-1) + 0.5 (CoETools.cpp:577-589) */
 };
 /* clustering.distance= : CoMap.cpp:401-427; Distance.h:150-173,316-424 */
 enum { CMB_DIST_CORRELATION = 0, CMB_DIST_COMPENSATION = 1, CMB_DIST_EUCLIDIAN = 2 };
@@ -112,6 +115,14 @@ int cmb_set_alignment(cmb_ctx* ctx, int64_t S, const uint8_t* codes, int32_t n_c
  * saturated sites after filling the per-site outputs. */
 int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_t* rate_class,
             double* loglik);
+
+/* nijt.average / nijt.joint (CoETools.cpp:393-407 for the observed mapping, AnalysisTools.cpp:597-633 and
+ * CoETools.cpp:1067-1082 for the simulated ones): which LegacySubstitutionMappingTools function fills the vectors
+ * of every later mapping -- cmb_map, the null distributions, the candidates sampler; the clustering null always
+ * averages (ClusterTools.cpp:227).  (1, 1) computeSubstitutionVectors (default, tensor-core kernels);
+ * (1, 0) ...Marginal; (0, 1) ...NoAveraging; (0, 0) ...NoAveragingMarginal (thread-per-site kernels,
+ * k1_variants.cu).  Invalidates the current mapping and null. */
+int cmb_set_map_mode(cmb_ctx* ctx, int32_t average, int32_t joint);
 
 /* Restart path, input.vectors.file (CoETools.cpp:374-385): replaces the mapping computed by
  * cmb_map with vectors read from a file (site-major [S][B], as LegacySubstitutionMappingTools::

@@ -280,9 +280,20 @@ static void counts_laplace(const spectral_t* sp, const double* Q, int trunc, dou
   free(QL); free(M2); free(M3); free(M4); free(M5); free(P);
 }
 
+/* nijt=Label [Bio++ LabelSubstitutionCount, from memory; no golden]: every substitution x -> y carries its own
+ * label, 1 .. A(A-1) in row-major order of the off-diagonal, whatever the branch length; 0 on the diagonal.
+ * Used with nijt.average=no and statistic=MI (CoETools.cpp:577-589: bounds -0.5, 0.5, ... around the labels). */
+static void counts_label(const spectral_t* sp, double* N) {
+  const int A = sp->A;
+  int count = 0;
+  for (int x = 0; x < A; x++)
+    for (int y = 0; y < A; y++) N[x * A + y] = x == y ? 0. : (double)++count;
+}
+
 static void counts_any(int method, const spectral_t* sp, const double* Q, const double* weights,
                        double t, double* N) {
   if ((method & 0xff) == ORC_COUNT_LAPLACE) counts_laplace(sp, Q, (method >> 8) ? (method >> 8) : 10, t, N);
+  else if (method == ORC_COUNT_LABEL) counts_label(sp, N);
   else if (method == ORC_COUNT_NAIVE) counts_naive(sp, weights, N);
   else if (method == ORC_COUNT_DECOMPOSITION) counts_decomposition(sp, Q, weights, t, N);
   else counts_uniformization(sp, Q, weights, t, N);
@@ -291,7 +302,7 @@ static void counts_any(int method, const spectral_t* sp, const double* Q, const 
 int orc_counts(int method, int A, const double* Q, const double* pi, const double* weights,
                double t, double* N) {
   spectral_t sp;
-  if ((method & 0xff) < ORC_COUNT_UNIFORMIZATION || (method & 0xff) > ORC_COUNT_LAPLACE) FAIL("orc_counts: unknown method %d", method);
+  if ((method & 0xff) < ORC_COUNT_UNIFORMIZATION || (method & 0xff) > ORC_COUNT_LABEL) FAIL("orc_counts: unknown method %d", method);
   if (spectral_init(&sp, A, Q, pi)) return -1;
   counts_any(method, &sp, Q, weights, t, N);
   spectral_free(&sp);
@@ -393,6 +404,45 @@ static void tables_free(tables_t* tb) { spectral_free(&tb->sp); free(tb->P); fre
  * RC = first argmax_c L_sc (not weighted by p_c).
  * computeNormForSite (CoMap.cpp:158-163, AnalysisTools.cpp:343-350): sqrt(sum_b n_b^2).
  */
+/* [Bio++] DRHomogeneousTreeLikelihood::computeLikelihoodAtNode: conditional likelihood of all the data given
+ * state x at node v and class c = product of the arrays of all its neighbours (sons in order, then the father's,
+ * or the root frequencies at the root). */
+static double node_lik(const tree_t* tr, const tables_t* tb, const double* down, const double* up, size_t per_node,
+                       size_t CA, int v, int64_t s, int c, int x) {
+  const int A = tb->A, C = tb->C;
+  const size_t AA = (size_t)A * A;
+  double l = 1.;
+  if (tr->nch[v] == 0) l = down[per_node * v + s * CA + c * A + x];
+  for (int k = 0; k < tr->nch[v]; k++) {
+    const int w = tr->ch[tr->ch_off[v] + k];
+    const double* P = tb->P + ((size_t)w * C + c) * AA;
+    const double* dw = down + per_node * w + s * CA + c * A;
+    double m = 0.;
+    for (int y = 0; y < A; y++) m += P[x * A + y] * dw[y];
+    l *= m;
+  }
+  if (v == tr->root) return l * tb->pi[x];
+  const double* P = tb->P + ((size_t)v * C + c) * AA;
+  const double* uv = up + per_node * v + s * CA + c * A;
+  double m = 0.;
+  for (int z = 0; z < A; z++) m += uv[z] * P[z * A + x];
+  return l * m;
+}
+
+/* nijt.average / nijt.joint (CoETools.cpp:393-407; AnalysisTools.cpp:597-633 for the null): which of the four
+ * LegacySubstitutionMappingTools functions fills the vectors.  [Bio++ / from memory, no golden: parity unpinned]
+ *   average, joint   computeSubstitutionVectors: sum over (x, y) of the joint posterior times the count
+ *   average, !joint  ...Marginal: product of the two nodes' marginal posteriors per (state, class) instead of
+ *                    the joint one (getPosteriorProbabilitiesPerStatePerRate; a leaf's is its 0/1 array x p_c)
+ *   !average, joint  ...NoAveraging: the pair (x, y) of largest joint probability summed over the classes
+ *                    (MatrixTools::whichMax: first maximum, rows then columns) and its count averaged over the
+ *                    classes with that pair's posterior class weights
+ *   !average, !joint ...NoAveragingMarginal: the marginal reconstruction of both nodes
+ *                    (MarginalAncestralStateReconstruction: first arg-max of sum_c p_c L_c(x) / L; a leaf's first
+ *                    compatible state) and the count of that pair averaged over the classes with p_c */
+static int g_map_average = 1, g_map_joint = 1;
+void orc_set_map_mode(int average, int joint) { g_map_average = average != 0; g_map_joint = joint != 0; }
+
 static int map_core(const tree_t* tr, const tables_t* tb, int64_t S, const uint8_t* codes,
                     int n_codes, const uint32_t* code_mask, double* n_out, double* norm,
                     double* post_rate, int32_t* rate_class, double* loglik) {
@@ -501,8 +551,74 @@ static int map_core(const tree_t* tr, const tables_t* tb, int64_t S, const uint8
             for (int x = 0; x < A; x++) uv[s * CA + c * A + x] *= tb->pi[x];
       }
     }
+    /* marginal reconstruction of every node (variants without averaging and without the joint pair) */
+    int32_t* anc = NULL;
+    const int variant = (g_map_average ? 0 : 2) + (g_map_joint ? 0 : 1); /* 0 avg+joint, 1 marginal, 2 no-avg, 3 no-avg marginal */
+    if (variant == 3) {
+      anc = malloc(sizeof(int32_t) * (size_t)n * S);
+      for (int v = 0; v < n; v++)
+        for (int64_t s = 0; s < S; s++) {
+          int best = 0;
+          if (tr->nch[v] == 0) { /* whichMax of the leaf's 0/1 array */
+            const double* dv = down + per_node * v + s * CA;
+            for (int x = 1; x < A; x++) if (dv[x] > dv[best]) best = x;
+          } else {
+            double bv = -INFINITY;
+            for (int x = 0; x < A; x++) {
+              double l = 0.;
+              for (int c = 0; c < C; c++) l += node_lik(tr, tb, down, up, per_node, CA, v, s, c, x) * tb->probs[c] / Ls[s];
+              if (l > bv) { bv = l; best = x; }
+            }
+          }
+          anc[(size_t)v * S + s] = best;
+        }
+    }
     /* mapping */
-    for (int v = 0; v < B; v++) {
+    for (int v = 0; v < B && variant; v++) {
+      const double* dv = down + per_node * v;
+      const double* uv = up + per_node * v;
+      const int f = tr->parent[v];
+      for (int64_t s = 0; s < S; s++) {
+        double res = 0.;
+        if (variant == 2) {
+          double best = -INFINITY; int bx = 0, by = 0;
+          for (int x = 0; x < A; x++)
+            for (int y = 0; y < A; y++) {
+              double pr = 0.;
+              for (int c = 0; c < C; c++)
+                pr += tb->probs[c] * uv[s * CA + c * A + x] * tb->P[((size_t)v * C + c) * AA + x * A + y] * dv[s * CA + c * A + y];
+              if (pr > best) { best = pr; bx = x; by = y; }
+            }
+          double sc = 0.;
+          for (int c = 0; c < C; c++)
+            sc += tb->probs[c] * uv[s * CA + c * A + bx] * tb->P[((size_t)v * C + c) * AA + bx * A + by] * dv[s * CA + c * A + by]
+                  * tb->N[((size_t)v * C + c) * AA + bx * A + by];
+          res = sc / best;
+        } else if (variant == 3) {
+          const int x = anc[(size_t)f * S + s], y = anc[(size_t)v * S + s];
+          for (int c = 0; c < C; c++) res += tb->N[((size_t)v * C + c) * AA + x * A + y] * tb->probs[c];
+        } else { /* marginal posteriors of the father and of the node, per (class, state) */
+          double Lf = 0., Lv = 0.;
+          for (int c = 0; c < C; c++)
+            for (int x = 0; x < A; x++) {
+              Lf += node_lik(tr, tb, down, up, per_node, CA, f, s, c, x) * tb->probs[c];
+              if (tr->nch[v]) Lv += node_lik(tr, tb, down, up, per_node, CA, v, s, c, x) * tb->probs[c];
+            }
+          for (int c = 0; c < C; c++)
+            for (int x = 0; x < A; x++) {
+              const double pf = node_lik(tr, tb, down, up, per_node, CA, f, s, c, x) * tb->probs[c] / Lf;
+              for (int y = 0; y < A; y++) {
+                const double pv = tr->nch[v] ? node_lik(tr, tb, down, up, per_node, CA, v, s, c, y) * tb->probs[c] / Lv
+                                             : dv[s * CA + c * A + y] * tb->probs[c];
+                res += pf * pv * tb->N[((size_t)v * C + c) * AA + x * A + y];
+              }
+            }
+        }
+        n_out[s * B + v] = res;
+      }
+    }
+    free(anc);
+    for (int v = 0; v < B && !variant; v++) {
       const double* dv = down + per_node * v;
       const double* uv = up + per_node * v;
       for (int64_t s = 0; s < S; s++) {
@@ -603,8 +719,30 @@ static double mi_discrete_binary(int B, const double* v1, const double* v2, doub
   return s;
 }
 
+/* statistic=MI with nijt=Label (CoETools.cpp:577-589): bounds -0.5, 0.5, ..., A(A-1) + 0.5, i.e. category of a
+ * branch = its label; the same [Bio++ / from memory] miDiscrete over all the categories present. */
+static int g_mi_label_states = 0;
+void orc_set_mi_label(int n_states) { g_mi_label_states = n_states; }
+static double mi_discrete_labels(int B, const double* v1, const double* v2, int A) {
+  const int K = A * (A - 1) + 1;
+  double* c1 = calloc((size_t)K * 2 + (size_t)K * K, sizeof(double));
+  double *c2 = c1 + K, *c12 = c2 + K;
+  for (int i = 0; i < B; i++) {
+    int a = orc_domain_index(-0.5, (double)K - 0.5, K, v1[i]), b = orc_domain_index(-0.5, (double)K - 0.5, K, v2[i]);
+    if (a < 0 || b < 0) { free(c1); return NAN; } /* Domain::getIndex throws: cannot happen with labels */
+    c1[a]++; c2[b]++; c12[(size_t)a * K + b]++;
+  }
+  double s = 0., n = (double)B;
+  for (int a = 0; a < K; a++)
+    for (int b = 0; b < K; b++)
+      if (c12[(size_t)a * K + b] > 0.) s += (c12[(size_t)a * K + b] / n) * log(c12[(size_t)a * K + b] * n / (c1[a] * c2[b])) / log(2.7182818);
+  free(c1);
+  return s;
+}
+
 double orc_stat(int stat_id, int B, const double* v1, const double* v2) {
   switch (stat_id) {
+    case ORC_STAT_MI_LABEL: return mi_discrete_labels(B, v1, v2, g_mi_label_states);
     case ORC_STAT_MI: return mi_discrete_binary(B, v1, v2, g_mi_threshold);
     case ORC_STAT_CORRECTED_CORRELATION: { /* Statistics.h:188-194: cor(v1 - mean vector, v2 - mean vector) */
       if (g_mean_vector_len != B) return NAN;

@@ -37,7 +37,7 @@ extern "C" {
 #endif
 
 enum { ORC_COUNT_UNIFORMIZATION = 0, ORC_COUNT_DECOMPOSITION = 1, ORC_COUNT_NAIVE = 2,
-       ORC_COUNT_LAPLACE = 3 /* | trunc << 8; trunc 0 = 10 */ };
+       ORC_COUNT_LAPLACE = 3 /* | trunc << 8; trunc 0 = 10 */, ORC_COUNT_LABEL = 4 };
 enum {
   ORC_STAT_CORRELATION = 0,
   ORC_STAT_COVARIANCE = 1,
@@ -45,7 +45,8 @@ enum {
   ORC_STAT_COSUBSTITUTION = 3,
   ORC_STAT_COMPENSATION = 4,
   ORC_STAT_CORRECTED_CORRELATION = 5, /* needs orc_set_mean_vector */
-  ORC_STAT_MI = 6 /* MI(threshold=..) without nijt=Label; threshold from orc_set_mi_threshold (0.99) */
+  ORC_STAT_MI = 6, /* MI(threshold=..) without nijt=Label; threshold from orc_set_mi_threshold (0.99) */
+  ORC_STAT_MI_LABEL = 7 /* MI with nijt=Label: one category per label; alphabet size from orc_set_mi_label */
 };
 enum { ORC_DIST_CORRELATION = 0, ORC_DIST_COMPENSATION = 1, ORC_DIST_EUCLIDIAN = 2 };
 enum { ORC_LINK_COMPLETE = 0, ORC_LINK_SINGLE = 1, ORC_LINK_AVERAGE = 2 };
@@ -75,6 +76,9 @@ double orc_stat(int stat_id, int B, const double* v1, const double* v2);
  * sites in site order, divided by the number of sites). */
 void orc_set_mean_vector(int B, const double* mv);
 void orc_set_mi_threshold(double threshold);
+void orc_set_mi_label(int n_states);
+/* nijt.average / nijt.joint for every later mapping (orc_map, orc_null_intra, ...); default 1, 1 */
+void orc_set_map_mode(int average, int joint);
 void orc_set_mean_vectors(int B, const double* mv1, const double* mv2);
 double orc_stat2(int stat_id, int B, const double* v1, const double* v2);
 /* CoETools::computeInterStats, CoETools.cpp:732-840 */

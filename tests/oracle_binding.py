@@ -11,10 +11,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 _SO = os.path.join(ROOT, "oracle", "liboracle.so")
 
 STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "compensation": 4,
-        "corrected_correlation": 5, "mi": 6}
+        "corrected_correlation": 5, "mi": 6, "mi_label": 7}
 DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
 LINK = {"complete": 0, "single": 1, "average": 2}
-COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2, "laplace": 3}
+COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2, "laplace": 3, "label": 4}
 
 
 def count_id(method):
@@ -102,6 +102,16 @@ def map_sites(parent, brlen, Q, pi, rates, probs, codes, code_mask, method="unif
 
 def set_mi_threshold(t):
     lib().orc_set_mi_threshold(C.c_double(t))
+
+
+def set_mi_label(n_states):
+    """statistic=MI with nijt=Label (CoETools.cpp:577-589): one category per substitution label."""
+    lib().orc_set_mi_label(int(n_states))
+
+
+def set_map_mode(average=True, joint=True):
+    """nijt.average / nijt.joint (CoETools.cpp:393-407) for every later mapping; reset with set_map_mode()."""
+    lib().orc_set_map_mode(int(bool(average)), int(bool(joint)))
 
 
 def mean_vector(n):

@@ -277,6 +277,36 @@ def test_mutual_information_from_the_cli(myo):
     ctx.close()
 
 
+def test_label_mutual_information_and_mapping_variants_from_the_cli(myo):
+    """statistic=MI nijt=Label nijt.average=no (CoETools.cpp:577-589) and the nijt.average / nijt.joint switches of
+    CoETools::getVectors (CoETools.cpp:393-407): the command line against the C ABI on the same inputs."""
+    from comap_b200 import api
+    tmp, _ = myo
+    base = [a for a in COMMON if not a.startswith("nijt=")]
+    run(tmp, *base, "nijt=Label", "nijt.average=no", "analysis=pairwise", "statistic=MI", "statistic.null=no",
+        "statistic.output.file=mil.txt", "output.vectors.file=label.vec")
+    c = host_inputs(tmp)
+    ctx = api.Context(device=0)
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"], count_method="label")
+    ctx.set_alignment(c["codes"], c["code_mask"]); ctx.set_map_mode(False, True)
+    r = ctx.map()
+    p, k = ctx.pairs("mi_label", use_null=False)
+    hdr, rows = table(os.path.join(tmp, "mil.txt"))
+    assert len(rows) == k == 129 * 128 // 2 and [x[1] for x in rows] == [g(v) for v in p["stat"]]
+    _, vrows = table(os.path.join(tmp, "label.vec"))
+    vec = np.array([[float(x) for x in r_[2:]] for r_ in vrows])
+    assert np.array_equal(vec, np.rint(r["n"].T)) and vec.max() > 100      # labels 0..380 of the 20-state alphabet
+    # the three variants with the ordinary counts: vectors written by the CLI == C ABI
+    for av, jo in (("yes", "no"), ("no", "yes"), ("no", "no")):
+        run(tmp, *COMMON, "nijt.average=" + av, "nijt.joint=" + jo, "analysis=none", "output.vectors.file=v.vec")
+        ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"]); ctx.set_alignment(c["codes"], c["code_mask"])
+        ctx.set_map_mode(av == "yes", jo == "yes")
+        n = ctx.map()["n"]
+        _, vrows = table(os.path.join(tmp, "v.vec"))
+        assert [x[2:] for x in vrows] == [[g(v) for v in row] for row in n.T]
+    ctx.close()
+
+
 def test_candidate_groups_table_equals_c_abi_run(myo):
     """analysis=candidates (CoMap.cpp:592-711): input table + Stat + p-value columns."""
     from comap_b200 import api

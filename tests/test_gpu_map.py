@@ -141,3 +141,64 @@ def test_errors_are_reported(ctx):
     with pytest.raises(RuntimeError, match="post-order"):
         c2.set_tree(np.array([1, 0, -1], np.int32), np.array([0.1, 0.1, 0.0]))
     c2.close()
+
+
+def _variant_mismatch(r, q):
+    """Entries of two mappings that differ beyond 1e-9: for the variants that pick a most probable state or pair,
+    device and oracle tables differ in the last bits (different eigen-solvers), so an arg-max between two states
+    of (numerically) equal probability may fall the other way."""
+    bad = ~np.isclose(r, q, rtol=RTOL, atol=1e-14)
+    return int(bad.sum()), bad
+
+
+@pytest.mark.parametrize("average,joint", [(True, False), (False, True), (False, False)])
+def test_map_variants_vs_oracle(ctx, average, joint):
+    """nijt.average = no / nijt.joint = no (CoETools.cpp:393-407): ...Marginal, ...NoAveraging and
+    ...NoAveragingMarginal on the device (k1_variants.cu) against the oracle's restatement, nucleotides with
+    unknown characters and polytomies, and the Myoglobin proteins; likelihood columns are those of the normal path."""
+    cases = [H.random_dna_case(14, 333, 7, ambiguity=0.05), H.random_dna_case(60, 130, 8, C=3), H.myoglobin_inputs()]
+    try:
+        for c in cases:
+            _setup(ctx, c)
+            ctx.set_map_mode(average, joint)
+            r = ctx.map()
+            O.set_map_mode(average, joint)
+            q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+            nbad, bad = _variant_mismatch(r["n"], q["n"])
+            if average:
+                assert nbad == 0
+            else:
+                assert nbad <= 2e-4 * r["n"].size, nbad
+            ok = ~bad.any(axis=1)
+            assert np.allclose(r["norm"][ok], q["norm"][ok], rtol=RTOL)
+            assert np.allclose(r["loglik"], q["loglik"], rtol=1e-12) and np.array_equal(r["rate_class"], q["rate_class"])
+            # the variant really is another mapping, and switching back restores the tensor-core one
+            O.set_map_mode()
+            base = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+            assert np.abs(q["n"] - base["n"]).max() > 1e-3
+            ctx.set_map_mode()
+            assert np.allclose(ctx.map()["n"], base["n"], rtol=RTOL, atol=1e-14)
+    finally:
+        O.set_map_mode()
+        ctx.set_map_mode()
+
+
+def test_label_counts_without_averaging_are_labels(ctx):
+    """nijt=Label with nijt.average=no (what statistic=MI needs, CoETools.cpp:577-589): every entry of the mapping
+    is the label of ONE substitution type, 0..A(A-1), on the device as in the oracle."""
+    c = H.random_dna_case(20, 400, 11, mean_brlen=0.1)
+    try:
+        for joint in (True, False):
+            ctx.set_tree(c["parent"], c["brlen"])
+            ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"], count_method="label")
+            ctx.set_alignment(c["codes"], c["code_mask"])
+            ctx.set_map_mode(False, joint)
+            r = ctx.map()
+            O.set_map_mode(False, joint)
+            q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"], method="label")
+            lab = np.rint(r["n"])
+            assert np.abs(r["n"] - lab).max() < 1e-9 and lab.min() == 0 and 1 <= lab.max() <= 12 and (lab > 0).mean() > 0.01
+            assert (np.rint(q["n"]) != lab).sum() <= 2e-4 * lab.size
+    finally:
+        O.set_map_mode()
+        ctx.set_map_mode()

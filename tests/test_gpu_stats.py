@@ -326,3 +326,53 @@ def test_pattern_compression_of_the_null_is_bit_identical(ctx, monkeypatch):
     assert np.array_equal(a[1]["bin_offsets"], b[1]["bin_offsets"])
     assert np.array_equal(np.nan_to_num(a[1]["sorted"]), np.nan_to_num(b[1]["sorted"]))
     assert a[2] == b[2] == 2 * 6 * 700 and a[3] == a[2] and b[3] < 0.8 * b[2]    # most columns were constant
+
+
+def test_label_mutual_information_pairs_null_and_pvalues(ctx):
+    """statistic=MI with nijt=Label, nijt.average=no (CoETools.cpp:577-589): labels mapped on the device, the
+    statistic of every pair against the oracle given the same vectors (1e-9: device and host log differ in the last
+    bit), the null built from exported alignments against the oracle running the same variant, p-values
+    self-consistent against the device's own sorted null."""
+    c = _case(T=18, S=150, seed=21)
+    try:
+        ctx.set_tree(c["parent"], c["brlen"])
+        ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"], count_method="label")
+        ctx.set_alignment(c["codes"], c["code_mask"])
+        ctx.set_map_mode(False, True)
+        r = ctx.map()
+        O.set_map_mode(False, True); O.set_mi_label(4)
+        g, k = ctx.pairs("mi_label", use_null=False)
+        o = O.pairs("mi_label", r["n"], r["norm"], r["post_rate"], r["rate_class"])
+        assert k == len(o["i"]) == 150 * 149 // 2
+        assert np.allclose(g["stat"], o["stat"], rtol=1e-9, atol=1e-12) and g["stat"].max() > 0.05
+        # sites with more substitutions than the kernel's in-register list take the column re-reading path
+        dense = np.tile(np.arange(1, 13, dtype=float), 20)[: r["n"].shape[1]]
+        n2 = r["n"].copy(); n2[0] = dense; n2[1] = dense[::-1]; n2[2] = np.roll(dense, 5)
+        ctx.load_vectors(n2)
+        g2, _ = ctx.pairs("mi_label", use_null=False)
+        nrm = np.sqrt((n2 ** 2).sum(1))
+        o2 = O.pairs("mi_label", n2, nrm, r["post_rate"], r["rate_class"])
+        assert np.allclose(g2["stat"], o2["stat"], rtol=1e-9, atol=1e-12)
+        ctx.map()
+        # null: same exported alignments -> same statistics and bins
+        rep_cpu, rep_ram, K = 3, 200, 4
+        s1 = np.stack([ctx.simulate(5, (2 * i) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+        s2 = np.stack([ctx.simulate(5, (2 * i + 1) * rep_ram, rep_ram)[0] for i in range(rep_cpu)])
+        nmax = float(r["norm"].max())
+        raw = ctx.null_intra_from_alignments("mi_label", s1, s2, K=K, nmax=nmax)
+        on = O.null_intra(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], "mi_label", s1, s2, K, nmax,
+                          method="label")
+        same = np.isclose(raw[:, 0], on["raw"][:, 0], rtol=1e-9, atol=1e-12)
+        assert same.mean() > 0.995                       # an arg-max tie may pick another label at a site
+        assert np.allclose(raw[same, 3], on["raw"][same, 3], rtol=1e-9)
+        # device RNG path == exported alignments, and p-values against the device's own null
+        raw2 = ctx.null_intra("mi_label", 5, rep_cpu, rep_ram, K=K, nmax=nmax, want_raw=True)
+        assert np.array_equal(raw2, raw)
+        gn = ctx.null_get()
+        gp, k2 = ctx.pairs("mi_label", use_null=True)
+        op = O.pairs("mi_label", r["n"], r["norm"], r["post_rate"], r["rate_class"], null=(K, gn["nmax"], gn["bin_offsets"], gn["sorted"]))
+        assert k2 == k and np.array_equal(gp["nsim"], op["nsim"])
+        fin = ~np.isnan(op["pvalue"])
+        assert (np.abs(gp["pvalue"][fin] - op["pvalue"][fin]) > 1e-12).mean() < 0.01   # 1e-9 statistics at exact ties
+    finally:
+        O.set_map_mode(); ctx.set_map_mode()

@@ -218,3 +218,91 @@ def test_continuous_rate_simulator_distribution():
     assert not (st[:, r == 0] != st[0, r == 0]).any()          # invariant sites never change
     st, r = O.simulate_continuous(parent, brlen, Q, pi, "constant", 1.0, 0.0, 5, 0, 100)
     assert np.all(r == 1.0)
+
+
+def test_mapping_variants_equal_brute_force_enumeration():
+    """nijt.average / nijt.joint (CoETools.cpp:393-407): the three other mapping functions as restated in the oracle
+    ([Bio++ / from memory]) against an explicit enumeration of every ancestral-state assignment of a 5-taxon tree
+    with two rate classes -- joint and marginal posteriors by summation, not by recursion."""
+    import itertools
+    #        leaves 0 1 | inner 2 = (0,1) | leaves 3 4 | inner 5 = (3,4) | leaf 6 | root 7 = (2,5,6)
+    parent = np.array([2, 2, 7, 5, 5, 7, 7, -1], np.int32)
+    brlen = np.array([0.3, 0.15, 0.2, 0.4, 0.05, 0.6, 0.25, 0.0])
+    Q, pi = syn.hky85(3.0, [0.1, 0.2, 0.3, 0.4])
+    rates, probs = np.array([0.3, 1.7]), np.array([0.5, 0.5])
+    codes = np.array([[0, 1, 2, 3], [0, 3, 2, 1], [1, 3, 2, 4], [1, 0, 2, 2], [2, 0, 3, 2]], np.uint8)  # code 4 = unknown
+    mask = np.array([1, 2, 4, 8, 15], np.uint32)
+    leaves, inner = [0, 1, 3, 4, 6], [2, 5, 7]
+    B, S, A, C = 7, codes.shape[1], 4, 2
+    P = np.array([[O.pmatrix(Q, pi, brlen[v] * r) for r in rates] for v in range(B)])
+    N = np.array([[O.counts(Q, pi, brlen[v] * r) for r in rates] for v in range(B)])
+    tipvec = ((mask[codes][:, :, None] >> np.arange(A)) & 1).astype(float)            # [leaf row][site][state]
+    # weight of (class, states of the inner nodes) given the data, per site
+    Wt = np.zeros((S, C, A, A, A))
+    for s, c, x2, x5, x7 in itertools.product(range(S), range(C), range(A), range(A), range(A)):
+        st = {2: x2, 5: x5, 7: x7}
+        w = probs[c] * pi[x7]
+        for v in range(B):
+            f = st[parent[v]]
+            w *= P[v, c, f, st[v]] if v in st else P[v, c, f] @ tipvec[leaves.index(v), s]
+        Wt[s, c, x2, x5, x7] = w
+    L = Wt.sum(axis=(1, 2, 3, 4))
+    ax = {2: 2, 5: 3, 7: 4}
+
+    def marg(s, v):  # [class][state] weight of inner node v
+        other = tuple(a for n_, a in ax.items() if n_ != v)
+        return Wt[s].sum(axis=tuple(o - 1 for o in other))
+
+    exp = {k: np.zeros((S, B)) for k in ((1, 0), (0, 1), (0, 0))}
+    for s in range(S):
+        anc = {v: int(np.argmax((marg(s, v) / L[s]).sum(0))) for v in inner}
+        for v in range(B):
+            f = parent[v]
+            mf = marg(s, f)
+            if v in ax:  # joint weights of (class, x at f, y at v)
+                keep = [0, ax[f] - 1, ax[v] - 1]
+                J = Wt[s].sum(axis=tuple(i for i in range(4) if i not in keep))
+                if ax[f] > ax[v]: J = J.transpose(0, 2, 1)
+                mv = marg(s, v) / marg(s, v).sum()
+                yv = anc[v]
+            else:        # leaf: joint weight with each compatible tip state
+                t = tipvec[leaves.index(v), s]
+                up = np.array([[mf[c, x] / max(P[v, c, x] @ t, 1e-300) for x in range(A)] for c in range(C)])
+                J = up[:, :, None] * P[v] * t[None, None, :]
+                mv = t[None, :] * probs[:, None]
+                yv = int(np.argmax(t))
+            pf = mf / mf.sum()
+            exp[(1, 0)][s, v] = sum(pf[c, x] * mv[c, y] * N[v, c, x, y] for c in range(C) for x in range(A) for y in range(A))
+            Jc = J.sum(0)
+            bx, by = np.unravel_index(np.argmax(Jc), Jc.shape)
+            exp[(0, 1)][s, v] = (J[:, bx, by] * N[v, :, bx, by]).sum() / Jc[bx, by]
+            exp[(0, 0)][s, v] = (N[v, :, anc[f], yv] * probs).sum()
+    try:
+        for (av, jo), e in exp.items():
+            O.set_map_mode(av, jo)
+            r = O.map_sites(parent, brlen, Q, pi, rates, probs, codes, mask)
+            assert np.allclose(r["n"], e, rtol=1e-10, atol=1e-13), (av, jo, np.abs(r["n"] - e).max())
+            assert np.allclose(r["loglik"], np.log(L), rtol=1e-12)
+    finally:
+        O.set_map_mode()
+
+
+def test_label_count_and_label_mutual_information():
+    """nijt=Label (one label per substitution type) and statistic=MI over those labels (CoETools.cpp:577-589):
+    numpy restatement of the joint-table formula on random label vectors."""
+    Q, pi = syn.hky85(2.0, [0.25, 0.25, 0.25, 0.25])
+    Nl = O.counts(Q, pi, 0.3, method="label")
+    assert np.array_equal(Nl, np.array([[0, 1, 2, 3], [4, 0, 5, 6], [7, 8, 0, 9], [10, 11, 12, 0]], float))
+    rng = np.random.default_rng(5)
+    O.set_mi_label(4)
+    for B in (7, 60, 400):
+        a = rng.choice(13, size=B, p=[0.7] + [0.025] * 12).astype(float)
+        b = np.where(rng.random(B) < 0.5, a, rng.choice(13, size=B)).astype(float)
+        e = 0.0
+        for u in np.unique(a):
+            for w in np.unique(b):
+                n12 = np.sum((a == u) & (b == w))
+                if n12:
+                    e += n12 / B * np.log(n12 * B / (np.sum(a == u) * np.sum(b == w))) / np.log(2.7182818)
+        assert abs(O.stat("mi_label", a, b) - e) < 1e-12
+        assert abs(O.stat("mi_label", a + 1e-13, b - 1e-13) - e) < 1e-12   # labels recovered through the +-0.5 bounds

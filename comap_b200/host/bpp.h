@@ -92,6 +92,7 @@ struct Model {
   std::string name;
   int A = 0;
   std::vector<double> Q, pi; // generator row-major, normalised to one substitution per unit time
+  std::string warning;       // printed by the front-end after "Substitution model" (e.g. an unverified bundled table)
 };
 Model make_model(const std::string& desc, const Alphabet& alpha, const std::string& data_dir);
 

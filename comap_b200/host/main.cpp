@@ -144,6 +144,7 @@ void prepare(Inputs& in, const char* argv0, const Params* override_params = null
     throw Error("nonhomogeneous models are outside the B200 hot path (SURVEY.md s2.1); use nonhomogeneous=no");
   in.model = make_model(get_string(P, "model", "JC69"), in.alpha, data_dir_of(argv0));
   display_result("Substitution model", in.model.name);
+  if (!in.model.warning.empty()) display_message(in.model.warning);
   in.rdist = make_rate_distribution(get_string(P, "rate_distribution", "Constant()"));
   display_result("Rate distribution", in.rdist.name);
   display_result("Number of classes", in.rdist.rates.size());

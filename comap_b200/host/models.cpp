@@ -125,14 +125,18 @@ Model make_model(const std::string& desc, const Alphabet& alpha, const std::stri
     from_exchangeabilities(m, std::vector<double>(400, 1.));
     return m;
   }
-  // empirical protein matrices: PAML files under comap_b200/data (JTT92 is bundled; the
-  // Bio++ tables are not available offline -- drop e.g. lg08.dat next to it to enable LG08)
+  // empirical protein matrices: PAML files under comap_b200/data.  JTT92 is bundled and validated by the reference's
+  // goldens; LG08 (examples/simple/*/comap.bpp:33) is bundled UNVERIFIED (re-typed from memory, no golden exists for
+  // it) and says so at every use; any other Bio++ table: drop <name>.dat next to them or use Empirical(file=...)
   std::string file = n == "jtt92" ? "jtt92_dcmut.dat" : n + ".dat";
   std::string path = data_dir + "/" + file;
   if (n == "empirical") { // Bio++: model = Empirical(name=..., file=<PAML .dat>)
     path = get_string(p.args, "file", "none");
     if (path == "none") throw Error("model Empirical(...) needs file=<PAML exchangeability file>");
   }
+  if (n == "lg08")
+    m.warning = "WARNING!!! model=LG08 uses the bundled table " + path + ", re-typed from memory and NOT validated against Bio++ "
+                "(no golden output exists for it): replace it with PAML's lg.dat or use model=Empirical(file=...) for production.";
   try {
     read_paml(path, m);
   } catch (const Error&) {

@@ -36,6 +36,10 @@ def main():
     out["mase"] = np.frombuffer(open(d + "Myoglobin.aln.sel.mase", "rb").read(), dtype=np.uint8)
     out["dnd"] = np.frombuffer(open(d + "Myo.dnd", "rb").read(), dtype=np.uint8)
     out["options"] = np.frombuffer(open(bm + "comap.bpp", "rb").read(), dtype=np.uint8)
+    # BASELINE configs[0] and its siblings: the option files of examples/simple/* (same alignment and tree)
+    for ex in ("ProteinPairCorrelation", "ProteinPairCompensation", "ProteinGroupCorrelation", "ProteinGroupCompensation",
+               "ProteinMappingOnly"):
+        out["simple_" + ex] = np.frombuffer(open(REF + "/examples/simple/" + ex + "/comap.bpp", "rb").read(), dtype=np.uint8)
     np.savez_compressed(os.path.join(HERE, "myoglobin.npz"), **out)
     r = REF + "/examples/RNA/BacteriaSSU/"
     np.savez_compressed(os.path.join(HERE, "bacteria_ssu.npz"),

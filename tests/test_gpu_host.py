@@ -362,6 +362,44 @@ def test_rna_example_with_its_own_option_file(tmp_path):
     assert sum(int(x[6]) for x in rows[:2000]) > 0
 
 
+def test_simple_examples_run_with_their_own_option_files(myo):
+    """BASELINE configs[0] = examples/simple/ProteinPairCorrelation/comap.bpp as shipped (model = LG08, Gamma(4, 0.5),
+    optimization = FullD -> parameters used as given, with a warning; 100 x 1000 null), and its siblings
+    ProteinPairCompensation (weighted counts), ProteinGroupCorrelation / ProteinGroupCompensation (clustering, null cut
+    to 3 replicates on the command line) and ProteinMappingOnly.  The LG08 table is bundled unverified (see
+    comap_b200/data/lg08.dat), so the check is against the oracle on the inputs the binary used, not against Bio++."""
+    tmp, golden = myo
+    for ex in ("ProteinPairCorrelation", "ProteinPairCompensation", "ProteinGroupCorrelation", "ProteinGroupCompensation",
+               "ProteinMappingOnly"):
+        with open(os.path.join(tmp, ex + ".bpp"), "wb") as f:
+            f.write(bytes(golden["simple_" + ex]))
+    out = run(tmp, "param=ProteinPairCorrelation.bpp", "--seed=3")
+    assert "NOT validated" in out and "outside the B200 hot path" in out and "Bye bye" in out
+    hdr, rows = table(os.path.join(tmp, "Myo.results.txt"))
+    assert hdr == ["Group", "Stat", "RCmin", "PRmin", "Nmin", "PValue", "Nsim"] and len(rows) == 129 * 128 // 2
+    p, o = dry_run(BIN, tmp, "param=ProteinPairCorrelation.bpp")
+    c = decode(o); c["parent"] = c["parent"].astype(np.int32)
+    q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    op = O.pairs("correlation", q["n"], q["norm"], q["post_rate"], q["rate_class"])
+    st = np.array([float(x[1]) for x in rows])
+    assert np.allclose(st, op["stat"], rtol=2e-5, atol=2e-6) and [int(x[2]) for x in rows] == op["rcmin"].tolist()
+    assert sum(int(x[6]) for x in rows) > 50000 * 100     # 100 000 null samples over 10 bins, most pairs scored
+    pv = np.array([float(x[5]) if x[5] != "NA" else np.nan for x in rows])
+    assert np.nanmin(pv) > 0 and np.nanmax(pv) <= 1
+    out = run(tmp, "param=ProteinPairCompensation.bpp", "--seed=3", "statistic.output.file=comp.txt")
+    _, rows = table(os.path.join(tmp, "comp.txt"))
+    assert len(rows) == 129 * 128 // 2 and all(float(x[1]) <= 1 + 1e-12 for x in rows)
+    for ex in ("ProteinGroupCorrelation", "ProteinGroupCompensation"):
+        run(tmp, "param=" + ex + ".bpp", "--seed=3", "clustering.null.number=3")
+        hdr, rows = table(os.path.join(tmp, "Myo_stats.csv"))
+        assert hdr[:2] == ["Group", "Size"] and len(rows) > 20
+        hdr, rows = table(os.path.join(tmp, "Myo_null.csv"))
+        assert hdr[0] == "Rep" and {int(x[0]) for x in rows} == {0, 1, 2}
+    out = run(tmp, "param=ProteinMappingOnly.bpp")
+    _, rows = table(os.path.join(tmp, "Myo_counts.txt"))
+    assert len(rows) == 197
+
+
 def test_error_exit_code_and_message(myo):
     tmp, _ = myo
     p = subprocess.run([BIN] + COMMON + ["analysis=pairwise", "statistic=Compensation"], cwd=tmp, capture_output=True, text=True)

@@ -107,8 +107,14 @@ def test_empirical_model_from_a_paml_file(binary, tmp_path):
     p2, o2 = dry_run(binary, str(tmp_path), *common, "model=Empirical(name=myJTT, file=%s)" % dat)
     assert p1.returncode == 0 and p2.returncode == 0, p2.stdout
     assert o1["Q"] == o2["Q"] and o1["pi"] == o2["pi"]
-    p3, _ = dry_run(binary, str(tmp_path), *common, "model=LG08")
-    assert p3.returncode == 255 and "lg08.dat" in p3.stdout
+    # LG08 (what examples/simple/* ask for) is bundled but unverified (re-typed from memory): it runs with a warning
+    p3, o3 = dry_run(binary, str(tmp_path), *common, "model=LG08")
+    assert p3.returncode == 0 and "NOT validated" in p3.stdout and "lg08.dat" in p3.stdout
+    Q3, pi3 = np.array(o3["Q"], float).reshape(20, 20), np.array(o3["pi"], float)
+    assert abs(pi3.sum() - 1) < 1e-12 and np.allclose(Q3.sum(1), 0, atol=1e-12) and abs((pi3 * np.diag(Q3)).sum() + 1) < 1e-12
+    assert np.allclose(pi3[:, None] * Q3, (pi3[:, None] * Q3).T, atol=1e-15) and o3["Q"] != o1["Q"]
+    p4, _ = dry_run(binary, str(tmp_path), *common, "model=WAG01")
+    assert p4.returncode == 255 and "wag01.dat" in p4.stdout
 
 
 def test_count_weights_and_second_data_set_options(binary, tmp_path):

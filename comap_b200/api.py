@@ -30,7 +30,7 @@ SYMBOLS = [
     "cmb_simulate", "cmb_null_intra", "cmb_null_intra_from_alignments", "cmb_null_samples_dev",
     "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
-    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates", "cmb_set_async", "cmb_set_mi_threshold", "cmb_set_map_mode",
+    "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates", "cmb_set_async", "cmb_set_mi_threshold", "cmb_set_map_mode", "cmb_ancestral_states",
     "cmb_comm_unique_id", "cmb_comm_init", "cmb_comm_init_all", "cmb_comm_set", "cmb_comm_destroy", "cmb_comm_rank",
     "cmb_comm_group_start", "cmb_comm_group_end", "cmb_null_intra_sharded", "cmb_set_continuous_rates",
 ]
@@ -190,6 +190,12 @@ class Context:
     def set_map_mode(self, average=True, joint=True):
         """nijt.average / nijt.joint (CoETools.cpp:393-407): which mapping function fills the vectors from now on."""
         self._chk(self.lib.cmb_set_map_mode(self.h, int(bool(average)), int(bool(joint))))
+
+    def ancestral_states(self):
+        """asr.method = marginal (CoMap.cpp:168-198): [n_nodes][S] state of largest marginal posterior probability."""
+        out = np.empty((self.B + 1, self.S), dtype=np.uint8)
+        self._chk(self.lib.cmb_ancestral_states(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
+        return out
 
     def set_mi_threshold(self, threshold):
         """Threshold of statistic 'mi' (MI(threshold=0.99) upstream)."""

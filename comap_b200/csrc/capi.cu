@@ -458,6 +458,25 @@ int cmb_set_map_mode(cmb_ctx* ctx, int32_t average, int32_t joint) {
   CMB_CATCH
 }
 
+int cmb_ancestral_states(cmb_ctx* ctx, uint8_t* states) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (!c.have_alignment) fail("cmb_ancestral_states: call cmb_set_alignment first");
+  if (!states) fail("cmb_ancestral_states: states is NULL");
+  c.finish_map();
+  c.ensure_streams();
+  const int n = c.tree.n_nodes;
+  MapBuffers b;
+  b.n = c.S; b.n_pad = c.S_pad; b.tips = c.d_tips.as<uint8_t>();
+  c.scratch2.reserve((size_t)n * c.S_pad);
+  const VariantTables vt = c.variant_tables();
+  c.prof.total_launches += launch_map_variant(c.map_model(), b, vt, 4, c.var_scratch_obs, c.stream, c.scratch2.as<uint8_t>());
+  CMB_CUDA(cudaMemcpy2DAsync(states, (size_t)c.S, c.scratch2.p, (size_t)c.S_pad, (size_t)c.S, (size_t)n, cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaStreamSynchronize(c.stream));
+  CMB_CATCH
+}
+
 int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_t* rate_class, double* loglik) {
   CMB_TRY
   Context& c = ctx->c;

@@ -21,7 +21,8 @@ namespace cmb {
 namespace {
 
 struct VarArgs {
-  int n_nodes, C, mode;       // mode: 1 marginal, 2 no averaging (joint pair), 3 no averaging, marginal states
+  int n_nodes, C, mode;       // mode: 1 marginal, 2 no averaging (joint pair), 3 no averaging, marginal states, 4 states only
+  uint8_t* anc_out;           // mode 4: [n_nodes][n_pad] marginal state of every node (leaves: first compatible state)
   const int32_t* parent;      // [n_nodes]
   const int32_t* ch_off;      // [n_nodes + 1]
   const int32_t* ch;          // children lists in id order
@@ -117,7 +118,7 @@ __global__ void __launch_bounds__(128) k1_variant(VarArgs a) {
     L = add(L, mul(l, __ldg(a.probs + c)));
   }
   // ---- marginal state of the root (mode 3)
-  if (a.mode == 3) {
+  if (a.mode >= 3) {
     double bv = -INFINITY; int best = 0;
     for (int x = 0; x < A; x++) {
       double l = 0.;
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(128) k1_variant(VarArgs a) {
       if (l > bv) { bv = l; best = x; }
     }
     a.anc[(size_t)root * row + t] = (uint8_t)best;
+    if (a.mode == 4) a.anc_out[(size_t)root * a.n_pad + site] = (uint8_t)best;
   }
   // ---- prefix pass + the branch above every node (parents carry larger ids: walk the ids downwards)
   for (int v = n - 2; v >= 0; v--) {
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(128) k1_variant(VarArgs a) {
         sc = add(sc, mul(mul(mul(mul(__ldg(a.probs + c), uu[(size_t)(c * A + bx) * row]), __ldg(Pv + c * AA + bx * A + by)), dn[(size_t)(c * A + by) * row]),
                          __ldg(Nv + c * AA + bx * A + by)));
       res = sc / best;
-    } else if (a.mode == 3) {
+    } else if (a.mode >= 3) {
       int y = 0;
       if (leaf) { // whichMax of the leaf's 0/1 array: its first compatible state
         const uint32_t m = __ldg(a.code_mask + a.tips[(size_t)a.leaf_row[v] * a.n_pad + site]) & (A >= 32 ? 0xffffffffu : (1u << A) - 1u);
@@ -201,6 +203,7 @@ __global__ void __launch_bounds__(128) k1_variant(VarArgs a) {
         }
       }
       a.anc[(size_t)v * row + t] = (uint8_t)y;
+      if (a.mode == 4) { a.anc_out[(size_t)v * a.n_pad + site] = (uint8_t)y; continue; }
       const int x = a.anc[(size_t)f * row + t];
       for (int c = 0; c < C; c++) res = add(res, mul(__ldg(Nv + c * AA + x * A + y), __ldg(a.probs + c)));
     } else {
@@ -246,8 +249,9 @@ static size_t map_variant_scratch_bytes(int n_nodes, int A, int C, int64_t chunk
   return (size_t)2 * n_nodes * C * A * chunk * sizeof(double) + (size_t)n_nodes * chunk;
 }
 
-int launch_map_variant(const MapModel& m, const MapBuffers& b, const VariantTables& vt, int mode, DevBuf& scratch, cudaStream_t st) {
-  if (mode < 1 || mode > 3) fail("internal: mapping variant %d", mode);
+int launch_map_variant(const MapModel& m, const MapBuffers& b, const VariantTables& vt, int mode, DevBuf& scratch, cudaStream_t st,
+                       uint8_t* states_out) {
+  if (mode < 1 || mode > 4 || (mode == 4) != (states_out != nullptr)) fail("internal: mapping variant %d", mode);
   // scratch budget 1 GiB: sites per launch, a multiple of 128
   const size_t per_site = map_variant_scratch_bytes(vt.n_nodes, m.A, m.C, 1);
   int64_t chunk = (int64_t)(((size_t)1 << 30) / per_site) / 128 * 128;
@@ -263,6 +267,7 @@ int launch_map_variant(const MapModel& m, const MapBuffers& b, const VariantTabl
   a.up = a.down + (size_t)vt.n_nodes * m.C * m.A * chunk;
   a.anc = reinterpret_cast<uint8_t*>(a.up + (size_t)vt.n_nodes * m.C * m.A * chunk);
   a.out = b.out;
+  a.anc_out = states_out;
   int launches = 0;
   for (int64_t s0 = 0; s0 < b.n; s0 += chunk, launches++) {
     a.site0 = s0; a.n = std::min<int64_t>(chunk, b.n - s0);

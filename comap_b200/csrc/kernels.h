@@ -69,7 +69,9 @@ struct VariantTables {
   const double *P = nullptr, *N = nullptr; // [branch][C][A][A]
 };
 // mode 1 marginal, 2 no averaging, 3 no averaging + marginal states; overwrites b.out for sites [0, b.n); returns launches
-int launch_map_variant(const MapModel& m, const MapBuffers& b, const VariantTables& vt, int mode, DevBuf& scratch, cudaStream_t st);
+// mode 4: only the marginal state of every node into states_out [n_nodes][n_pad] (asr.method = marginal); b.out untouched
+int launch_map_variant(const MapModel& m, const MapBuffers& b, const VariantTables& vt, int mode, DevBuf& scratch, cudaStream_t st,
+                       uint8_t* states_out = nullptr);
 // A = 4 partial layout: 128-site chunks (common.h kChunkSites), [chunk][slot][class][site][state]
 __host__ __device__ inline size_t d_chunk(int64_t chunk, int slot, int n_slots, int C) {
   return ((size_t)chunk * n_slots + slot) * ((size_t)C * kChunkSites * 4);

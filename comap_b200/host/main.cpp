@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstring>
 #include <fstream>
+#include <functional>
 #include <iostream>
 #include <random>
 #include <sstream>
@@ -506,8 +507,70 @@ int main(int argc, char** argv) {
     }
     std::string analysis = get_string(P, "analysis", "pairwise");
     display_result("Analysis type", analysis);
-    if (get_string(P, "asr.method", "none") != "none")
-      throw Error("asr.method (side output, not used by the analysis) is not available in this build");
+    // Ancestral sequences, a side output "not used in the analysis" (CoMap.cpp:168-198): marginal reconstruction of
+    // every inner node for the selected sites, the existing sequences appended, written as output.sequence.file
+    {
+      const std::string rec = get_string(P, "asr.method", "none");
+      display_result("Ancestral state reconstruction method", rec);
+      if (rec == "marginal") {
+        const int n_nodes = (int)in.tree.parent.size();
+        std::vector<uint8_t> anc((size_t)n_nodes * S);
+        chk(cmb_ancestral_states(ctx, anc.data()));
+        const std::string seq_out = get_path(P, "output.sequence.file", "none");
+        if (seq_out != "none") {
+          const std::string fmt = get_string(P, "output.sequence.format", "Fasta");
+          if (lower(parse_procedure(fmt).name) != "fasta") throw Error("output.sequence.format '" + fmt + "' is not supported (Fasta)");
+          std::ofstream out(seq_out);
+          auto put = [&](const std::string& name, const std::string& seq) {
+            out << ">" << name << "\n";
+            for (size_t k = 0; k < seq.size(); k += 100) out << seq.substr(k, 100) << "\n";
+          };
+          std::vector<bool> is_leaf(n_nodes, false);
+          for (int v : in.tree.leaves) is_leaf[v] = true;
+          for (int v = 0; v < n_nodes; v++) {
+            if (is_leaf[v]) continue;
+            std::string seq((size_t)S, '?');
+            for (int64_t j = 0; j < S; j++) seq[j] = in.alpha.states[anc[(size_t)v * S + j]];
+            put(std::to_string(v), seq); // unnamed inner nodes are called by their id
+          }
+          for (size_t r = 0; r < in.aln.names.size(); r++) {
+            std::string seq((size_t)S, '?');
+            for (int64_t j = 0; j < S; j++) seq[j] = in.aln.seqs[r][in.cols[j]];
+            put(in.aln.names[r], seq);
+          }
+          display_result("Output sequence file", seq_out);
+        }
+      } else if (rec != "none") throw Error("Unknown ancestral state reconstruction method: " + rec);
+    }
+    // output.tags.file (CoETools.cpp:314-345): the tree with every node named by its id, and the leaf names' translation
+    {
+      const std::string tags = get_path(P, "output.tags.file", "none");
+      display_result("Tagged tree file", tags);
+      if (tags != "none") {
+        const int n_nodes = (int)in.tree.parent.size();
+        std::string tln = get_path(P, "output.tags.translation", "tags_translation.txt");
+        display_result("Tagged tree names translation", tln);
+        if (tln != "none") {
+          std::ofstream t(tln);
+          t << "Name\tId" << std::endl;
+          for (int v : in.tree.leaves) t << in.tree.name[v] << "\t" << v << std::endl;
+        }
+        std::vector<std::vector<int>> kids(n_nodes);
+        for (int v = 0; v < n_nodes - 1; v++) kids[in.tree.parent[v]].push_back(v);
+        std::function<void(int, std::ostream&)> wr = [&](int v, std::ostream& o) {
+          if (!kids[v].empty()) {
+            o << "(";
+            for (size_t k = 0; k < kids[v].size(); k++) { if (k) o << ","; wr(kids[v][k], o); }
+            o << ")";
+          }
+          o << v;
+          if (v != n_nodes - 1) o << ":" << in.tree.brlen[v];
+        };
+        std::ofstream o(tags);
+        wr(n_nodes - 1, o);
+        o << ";" << std::endl;
+      }
+    }
 
     if (analysis == "none") {
       // mapping only

@@ -124,6 +124,12 @@ int cmb_map(cmb_ctx* ctx, double* n_out, double* norm, double* post_rate, int32_
  * k1_variants.cu).  Invalidates the current mapping and null. */
 int cmb_set_map_mode(cmb_ctx* ctx, int32_t average, int32_t joint);
 
+/* asr.method = marginal (CoMap.cpp:168-198, a side output "not used in the analysis"): the state of largest marginal
+ * posterior probability at every node of the tree for every site of the alignment -- LegacyMarginalAncestralState
+ * Reconstruction::getAllAncestralStates [Bio++ / from memory: first arg-max over the states of sum_c p_c L_c(x) / L;
+ * a leaf gets its first compatible state].  states is [n_nodes][S], node ids as in cmb_set_tree. */
+int cmb_ancestral_states(cmb_ctx* ctx, uint8_t* states);
+
 /* Restart path, input.vectors.file (CoETools.cpp:374-385): replaces the mapping computed by
  * cmb_map with vectors read from a file (site-major [S][B], as LegacySubstitutionMappingTools::
  * readFromStream yields them); site likelihoods, rates and rate classes stay those of the

@@ -441,6 +441,7 @@ static double node_lik(const tree_t* tr, const tables_t* tb, const double* down,
  *                    (MarginalAncestralStateReconstruction: first arg-max of sum_c p_c L_c(x) / L; a leaf's first
  *                    compatible state) and the count of that pair averaged over the classes with p_c */
 static int g_map_average = 1, g_map_joint = 1;
+static uint8_t* g_anc_out = NULL; /* orc_ancestral_states: where the marginal reconstruction goes */
 void orc_set_map_mode(int average, int joint) { g_map_average = average != 0; g_map_joint = joint != 0; }
 
 static int map_core(const tree_t* tr, const tables_t* tb, int64_t S, const uint8_t* codes,
@@ -571,6 +572,7 @@ static int map_core(const tree_t* tr, const tables_t* tb, int64_t S, const uint8
             }
           }
           anc[(size_t)v * S + s] = best;
+          if (g_anc_out) g_anc_out[(size_t)v * S + s] = (uint8_t)best;
         }
     }
     /* mapping */
@@ -647,6 +649,24 @@ static int map_core(const tree_t* tr, const tables_t* tb, int64_t S, const uint8
   }
   free(down); free(up); free(Lsc); free(Ls);
   return 0;
+}
+
+/* asr.method = marginal (CoMap.cpp:168-198) [Bio++ LegacyMarginalAncestralStateReconstruction::getAllAncestralStates,
+ * from memory]: per node and site the first arg-max over the states of sum_c p_c L_c(x) / L (computeLikelihoodAtNode);
+ * a leaf: whichMax of its 0/1 array.  states: [n_nodes][S]. */
+int orc_ancestral_states(int n_nodes, const int32_t* parent, const double* brlen, int A, const double* Q,
+                         const double* pi, int C, const double* rates, const double* probs, int64_t S,
+                         const uint8_t* codes, int n_codes, const uint32_t* code_mask, uint8_t* states) {
+  tree_t tr; tables_t tb;
+  if (tree_init(&tr, n_nodes, parent, brlen)) { tree_free(&tr); return -1; }
+  if (tables_init(&tb, &tr, A, Q, pi, C, rates, probs, ORC_COUNT_NAIVE, NULL, 1)) { tree_free(&tr); return -1; }
+  double* n_out = malloc(sizeof(double) * (size_t)S * (n_nodes - 1));
+  const int av = g_map_average, jo = g_map_joint;
+  g_map_average = 0; g_map_joint = 0; g_anc_out = states;
+  int rc = map_core(&tr, &tb, S, codes, n_codes, code_mask, n_out, NULL, NULL, NULL, NULL);
+  g_map_average = av; g_map_joint = jo; g_anc_out = NULL;
+  free(n_out); tables_free(&tb); tree_free(&tr);
+  return rc;
 }
 
 int orc_map(int n_nodes, const int32_t* parent, const double* brlen, int A, const double* Q,

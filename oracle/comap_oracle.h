@@ -79,6 +79,10 @@ void orc_set_mi_threshold(double threshold);
 void orc_set_mi_label(int n_states);
 /* nijt.average / nijt.joint for every later mapping (orc_map, orc_null_intra, ...); default 1, 1 */
 void orc_set_map_mode(int average, int joint);
+/* asr.method = marginal: states [n_nodes][S] */
+int orc_ancestral_states(int n_nodes, const int32_t* parent, const double* brlen, int A, const double* Q,
+                         const double* pi, int C, const double* rates, const double* probs, int64_t S,
+                         const uint8_t* codes, int n_codes, const uint32_t* code_mask, uint8_t* states);
 void orc_set_mean_vectors(int B, const double* mv1, const double* mv2);
 double orc_stat2(int stat_id, int B, const double* v1, const double* v2);
 /* CoETools::computeInterStats, CoETools.cpp:732-840 */

@@ -100,6 +100,19 @@ def map_sites(parent, brlen, Q, pi, rates, probs, codes, code_mask, method="unif
     return dict(n=n, norm=norm, post_rate=pr, rate_class=rc, loglik=ll)
 
 
+def ancestral_states(parent, brlen, Q, pi, rates, probs, codes, code_mask):
+    """asr.method = marginal (CoMap.cpp:168-198): [n_nodes][S] marginal reconstruction."""
+    ta, keep1 = _tree_args(parent, brlen)
+    ma, keep2 = _model_args(Q, pi, rates, probs)
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    T, S = codes.shape
+    code_mask = np.ascontiguousarray(code_mask, dtype=np.uint32)
+    out = np.empty((len(parent), S), dtype=np.uint8)
+    _chk(lib().orc_ancestral_states(*ta, *ma, C.c_int64(S), _p(codes, C.c_uint8), len(code_mask), _p(code_mask, C.c_uint32),
+                                    _p(out, C.c_uint8)))
+    return out
+
+
 def set_mi_threshold(t):
     lib().orc_set_mi_threshold(C.c_double(t))
 

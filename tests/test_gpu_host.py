@@ -398,6 +398,23 @@ def test_simple_examples_run_with_their_own_option_files(myo):
     out = run(tmp, "param=ProteinMappingOnly.bpp")
     _, rows = table(os.path.join(tmp, "Myo_counts.txt"))
     assert len(rows) == 197
+    # its side outputs: marginal ancestral sequences (inner nodes by id, then the 100 observed sequences) and the tagged tree
+    fa = open(os.path.join(tmp, "Myo_ancestors.fasta")).read().split(">")[1:]
+    names = [x.split("\n", 1)[0] for x in fa]
+    seqs = ["".join(x.split("\n")[1:]) for x in fa]
+    p, o = dry_run(BIN, tmp, "param=ProteinMappingOnly.bpp")
+    c = decode(o); c["parent"] = c["parent"].astype(np.int32)
+    inner = [v for v in range(len(c["parent"])) if v in set(c["parent"].tolist())]
+    assert names[:len(inner)] == [str(v) for v in inner] and len(names) == len(inner) + c["codes"].shape[0]
+    assert all(len(x) == 129 for x in seqs)
+    anc = O.ancestral_states(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+    aa = "ARNDCQEGHILKMFPSTWYV"
+    exp = ["".join(aa[k] for k in anc[v]) for v in inner]
+    assert sum(a != b for x, y in zip(seqs, exp) for a, b in zip(x, y)) <= 2
+    tree = open(os.path.join(tmp, "Myo_tags.dnd")).read().strip()
+    assert tree.endswith(")%d;" % (len(c["parent"]) - 1)) and tree.count("(") == len(inner)
+    tl = open(os.path.join(tmp, "Myo_tags_tln.txt")).read().split("\n")
+    assert tl[0] == "Name\tId" and len([x for x in tl[1:] if x]) == c["codes"].shape[0]
 
 
 def test_error_exit_code_and_message(myo):

@@ -203,3 +203,21 @@ def test_label_counts_without_averaging_are_labels(ctx):
     finally:
         O.set_map_mode()
         ctx.set_map_mode()
+
+
+def test_marginal_ancestral_states_vs_oracle(ctx):
+    """asr.method = marginal (CoMap.cpp:168-198): state of largest marginal posterior at every node, device vs oracle;
+    the leaves of resolved columns come back as observed."""
+    for c in (H.random_dna_case(25, 300, 31, ambiguity=0.04), H.myoglobin_inputs()):
+        _setup(ctx, c)
+        ctx.map()
+        a = ctx.ancestral_states()
+        q = O.ancestral_states(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"])
+        assert a.shape == q.shape == (len(c["parent"]), c["codes"].shape[1])
+        assert (a != q).mean() < 2e-4
+        has_child = np.zeros(len(c["parent"]), bool); has_child[c["parent"][c["parent"] >= 0]] = True
+        leaves = a[~has_child]
+        A = len(c["pi"])
+        res = c["codes"] < A
+        assert np.array_equal(leaves[res], c["codes"][res])
+        assert a.max() < A and len(np.unique(a[has_child])) > 1

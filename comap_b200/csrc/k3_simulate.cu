@@ -25,6 +25,7 @@ struct SimParams {
   uint32_t n_chunks, cap;
   int A, C, root_node, weighted;
   uint64_t seed;
+  uint32_t rk[20];             // Philox round keys of `seed` (k0, k1 per round): constant-bank operands of the XORs
   int64_t base, group, stride; // site id = base + (idx / group) * stride + idx % group
   int64_t n, n_pad;
   int64_t half_n, half_col, half_shift; // two batches in one launch: threads >= half_n simulate site ids shifted by
@@ -33,6 +34,24 @@ struct SimParams {
   uint8_t* tips;
   int32_t* classes;
 };
+
+// Philox4x32-10 with the key schedule taken from the launch parameters: the round keys depend on the seed only,
+// so they sit in the constant bank and fold into the XORs (LOP3 with a uniform operand); high and low product
+// words through __umulhi / mul.lo (the 64-bit product form left one add of a zero carry per multiply).  42
+// instructions per block instead of 91 (cuobjdump); the same function of (seed, counter) as philox4x32_10.
+__device__ __forceinline__ void philox_rk(const SimParams& p, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                          double& u0, double& u1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+    c0 = h1 ^ c1 ^ p.rk[2 * r];
+    c2 = h0 ^ c3 ^ p.rk[2 * r + 1];
+    c1 = l1; c3 = l0;
+  }
+  u0 = (double)((((uint64_t)c0 << 32) | c1) >> 11) * (1.0 / 9007199254740992.0);
+  u1 = (double)((((uint64_t)c2 << 32) | c3) >> 11) * (1.0 / 9007199254740992.0);
+}
 
 __device__ __forceinline__ int draw_state(const double* __restrict__ row, int A, double u) {
   if (A == 4) { // nucleotides: the cumulative row is two 128-bit shared loads
@@ -45,7 +64,9 @@ __device__ __forceinline__ int draw_state(const double* __restrict__ row, int A,
   return y;
 }
 
-__global__ void __launch_bounds__(NT) k3_simulate(SimParams p) {
+// AT = 4 / 20: the alphabet size at compile time (table strides become shifts / immediates); 0 = read it from p
+template <int AT>
+__global__ void __launch_bounds__(NT) k3_simulate(const __grid_constant__ SimParams p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int64_t tid = (int64_t)blockIdx.x * NT + threadIdx.x;
   const bool live = tid < p.n;
@@ -56,11 +77,13 @@ __global__ void __launch_bounds__(NT) k3_simulate(SimParams p) {
   const uint64_t site = (uint64_t)(p.base + (second ? p.half_shift : 0) + (ii / p.group) * p.stride + ii % p.group);
   ChunkStream cs{p.src, p.off, p.bytes, p.n_chunks, p.cap, nullptr, nullptr};
   cs.start(smem + 128, reinterpret_cast<uint64_t*>(smem));
-  const int A = p.A, C = p.C, AA = A * A;
+  const int A = AT > 0 ? AT : p.A, C = p.C, AA = A * A;
+  const uint32_t site_lo = (uint32_t)site, site_hi = (uint32_t)(site >> 32);
 
   int st;
   {
-    double r = philox_u01(p.seed, site, (uint32_t)p.root_node, 0);
+    double r, r_unused;
+    philox_rk(p, site_lo, site_hi, (uint32_t)p.root_node, 0u, r, r_unused);
     st = A - 1;
     double cp = 0.;
     bool done = false;
@@ -71,7 +94,8 @@ __global__ void __launch_bounds__(NT) k3_simulate(SimParams p) {
   }
   int c;
   {
-    double r = philox_u01(p.seed, site, (uint32_t)p.root_node, 1);
+    double r, r_unused;
+    philox_rk(p, site_lo, site_hi, (uint32_t)p.root_node, 1u, r, r_unused);
     if (p.weighted) {
       c = C - 1;
       double cq = 0.;
@@ -89,6 +113,8 @@ __global__ void __launch_bounds__(NT) k3_simulate(SimParams p) {
 
   uint8_t stk[kMaxStack];
   int sp = 0;
+  uint8_t* const tip_col = p.tips + idx;
+  const uint32_t npad32 = (uint32_t)p.n_pad;
   const size_t tab = (size_t)C * AA;
   for (uint32_t k = 0; k < p.n_chunks; k++) {
     const unsigned char* rp = cs.wait(k);
@@ -104,16 +130,17 @@ __global__ void __launch_bounds__(NT) k3_simulate(SimParams p) {
       // h1.y / h1.z = (block index << 1 | half) of child a / b among the children of node h1.w
       double u0 = 0., u1 = 0.;
       if (h0.w >= 0) {
-        philox_u01x2(p.seed, site, (uint32_t)h1.w, 2u + ((uint32_t)h1.y >> 1), u0, u1);
+        philox_rk(p, site_lo, site_hi, (uint32_t)h1.w, 2u + ((uint32_t)h1.y >> 1), u0, u1);
         sa = draw_state(cumA + ((size_t)c * A + st) * A, A, (h1.y & 1) ? u1 : u0);
       }
       if (h1.x >= 0) {
         if (h0.w < 0 || (h1.y >> 1) != (h1.z >> 1))
-          philox_u01x2(p.seed, site, (uint32_t)h1.w, 2u + ((uint32_t)h1.z >> 1), u0, u1);
+          philox_rk(p, site_lo, site_hi, (uint32_t)h1.w, 2u + ((uint32_t)h1.z >> 1), u0, u1);
         sb = draw_state(cumB + ((size_t)c * A + st) * A, A, (h1.z & 1) ? u1 : u0);
       }
-      if ((flags & kUpTipA) && live) p.tips[(size_t)h0.y * p.n_pad + idx] = (uint8_t)sa;
-      if ((flags & kUpTipB) && live) p.tips[(size_t)h0.z * p.n_pad + idx] = (uint8_t)sb;
+      // row * n_pad as one 32 x 32 -> 64 bit multiply (rows and padded site counts are below 2^32)
+      if ((flags & kUpTipA) && live) tip_col[(uint64_t)(uint32_t)h0.y * npad32] = (uint8_t)sa;
+      if ((flags & kUpTipB) && live) tip_col[(uint64_t)(uint32_t)h0.z * npad32] = (uint8_t)sb;
       if (flags & kUpTakeA) {
         if (flags & kUpPush) stk[sp++] = (uint8_t)sb;
         st = sa;
@@ -219,11 +246,16 @@ __global__ void __launch_bounds__(NT) k3_simulate_cont(SimParams p, ContParams c
 void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,
                      int64_t stride, int64_t n, int64_t n_pad, int weighted, int root_node, uint8_t* tips,
                      int32_t* classes, cudaStream_t st, int64_t half_n, int64_t half_col, int64_t half_shift) {
+  if (n_pad >= ((int64_t)1 << 32)) fail("internal: simulated batch of %lld padded sites", (long long)n_pad);
   SimParams p;
   p.half_n = half_n; p.half_col = half_col; p.half_shift = half_shift;
   p.src = s.bytes.as<unsigned char>(); p.off = s.off.as<uint32_t>(); p.bytes = s.nbytes.as<uint32_t>();
   p.nrec = s.nrec.as<uint32_t>(); p.n_chunks = s.n_chunks; p.cap = s.cap;
   p.A = m.A; p.C = m.C; p.root_node = root_node; p.weighted = weighted; p.seed = seed;
+  for (int r = 0; r < 10; r++) { // Philox4x32 key schedule: both halves bumped by their Weyl constants every round
+    p.rk[2 * r] = (uint32_t)seed + (uint32_t)r * 0x9E3779B9u;
+    p.rk[2 * r + 1] = (uint32_t)(seed >> 32) + (uint32_t)r * 0xBB67AE85u;
+  }
   p.base = base; p.group = group; p.stride = stride; p.n = n; p.n_pad = n_pad;
   p.pi = m.pi; p.probs = m.probs; p.tips = tips; p.classes = classes;
   size_t smem = 128 + 2 * (size_t)s.cap;
@@ -241,8 +273,17 @@ void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64
     CMB_CUDA(cudaGetLastError());
     return;
   }
-  CMB_CUDA(cudaFuncSetAttribute(k3_simulate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  k3_simulate<<<(unsigned)((n + NT - 1) / NT), NT, smem, st>>>(p);
+  const unsigned grid = (unsigned)((n + NT - 1) / NT);
+  if (m.A == 4) {
+    CMB_CUDA(cudaFuncSetAttribute(k3_simulate<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k3_simulate<4><<<grid, NT, smem, st>>>(p);
+  } else if (m.A == 20) {
+    CMB_CUDA(cudaFuncSetAttribute(k3_simulate<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k3_simulate<20><<<grid, NT, smem, st>>>(p);
+  } else {
+    CMB_CUDA(cudaFuncSetAttribute(k3_simulate<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k3_simulate<0><<<grid, NT, smem, st>>>(p);
+  }
   CMB_CUDA(cudaGetLastError());
 }
 

@@ -39,6 +39,8 @@ struct SimParams {
 // so they sit in the constant bank and fold into the XORs (LOP3 with a uniform operand); high and low product
 // words through __umulhi / mul.lo (the 64-bit product form left one add of a zero carry per multiply).  42
 // instructions per block instead of 91 (cuobjdump); the same function of (seed, counter) as philox4x32_10.
+// Measured and left out: 53-bit integer uniforms against integer thresholds ceil(cum 2^53) instead of the
+// conversion to double + DSETP (the same draws, 5.8 vs 5.6 ms per config-4 step: no gain).
 __device__ __forceinline__ void philox_rk(const SimParams& p, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                           double& u0, double& u1) {
 #pragma unroll

@@ -63,3 +63,15 @@ def test_cpu_model_validation_on_a_small_job():
     assert set(one["fit"]) == {"per_null_site", "per_obs_site", "per_pair_base", "per_pair_scan_per_sample"}
     v = bench.cpu_validation(cfg, w, one["fit"], sites=100, rep_cpu=3, rep_ram=200)
     assert v["measured_seconds"] > 0 and 0.3 < v["measured_over_predicted"] < 3.0
+
+
+def test_cpu_sample_keeps_the_composition_of_the_step():
+    """The CPU arm scores a bounded sample with the step's own ratio of null pairs to observed pairs, so its value is
+    sample pairs / sample seconds (measured), not an extrapolation."""
+    cfg = dict(bench.CFG); cfg.update(taxa=20, sites=300, rep_cpu=10, rep_ram=100)
+    w = bench.workload(cfg)
+    r = bench.cpu_sample(cfg, w, sample_sites=60, seed=1)
+    total = 300 * 299 // 2 + 1000
+    assert abs(r["sample_fraction"] - (60 * 59 // 2 + round(1000 * (60 * 59 / 2) / (300 * 299 / 2))) / total) < 1e-12  # 1770 + 39 pairs
+    assert r["value"] == r["sample_pairs"] / r["sample_seconds"] and r["full_step_seconds"] == total / r["value"]
+    assert 0.2 < r["extrapolated_value"] / r["value"] < 5.0

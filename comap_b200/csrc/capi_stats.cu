@@ -127,6 +127,10 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
       CMB_CUDA(cudaMemsetAsync(tips, 0, (size_t)T * n_pad, c.stream));
       c.s_tips_ptr = tips; c.s_tips_pad = n_pad; c.s_tips_n = n;
     }
+    const bool dedup_on = !(getenv("CMB_NULL_DEDUP") && atoi(getenv("CMB_NULL_DEDUP")) == 0);
+    const bool dedup = dedup_on && c.A == 4 && !c.map_mode; // the variant kernels walk every column
+    int32_t *col_class = nullptr, *col_varied = nullptr;
+    bool classified = false;
     if (sim1) {
       for (int k = 0; k < 2; k++) {
         const uint8_t* src = k == 0 ? sim1 : sim2;
@@ -135,9 +139,13 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
                                      cudaMemcpyHostToDevice, c.stream));
       }
     } else { // both batches in one launch: threads >= n simulate the second alignment's sites into the columns from `half`
+      if (dedup && m.cont_kind == 0) { // the simulator classifies its columns while it writes them
+        compress_class_buffers(n_pad, c.scratch2, &col_class, &col_varied);
+        classified = true;
+      }
       c.prof_begin("simulate");
       launch_simulate(m, c.sim_stream, seed, 2 * r0 * R, R, 2 * R, 2 * n, n_pad, weighted, c.tree.n_nodes - 1, tips, nullptr,
-                      c.stream, n, half, R);
+                      c.stream, n, half, R, col_class, col_varied);
       c.prof_end(1);
     }
     // Pattern compression (nucleotides): columns whose tips all carry the same state -- 16 % of the simulated
@@ -146,8 +154,6 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
     // columns are packed to the front of a second tip buffer with the A constant patterns behind them, the
     // mapping kernels stop at the packed count (a device scalar: no host round trip), and the paired statistic
     // reads each site's vector through a column index.
-    const bool dedup_on = !(getenv("CMB_NULL_DEDUP") && atoi(getenv("CMB_NULL_DEDUP")) == 0);
-    const bool dedup = dedup_on && c.A == 4 && !c.map_mode; // the variant kernels walk every column
     const int32_t *col1 = nullptr, *col2 = nullptr;
     if (dedup) {
       c.s_tips[1].reserve((size_t)T * n_pad);
@@ -157,7 +163,7 @@ void null_core(Context& c, int stat_id, uint64_t seed, int rep_cpu, int rep_ram,
       int32_t* counts = c.s_counts.as<int32_t>() + 2 * c.s_batches;
       c.prof_begin("compress");
       const int nl = launch_compress_constant(c.A, T, n, half, n_pad, tips, c.s_tips[1].as<uint8_t>(), c.s_cols.as<int32_t>(), counts,
-                                              c.scratch2, c.stream);
+                                              c.scratch2, c.stream, classified);
       c.prof_end(nl);
       bb.tips = c.s_tips[1].as<uint8_t>();
       bb.n_active = counts;

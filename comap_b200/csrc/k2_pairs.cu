@@ -236,10 +236,11 @@ __global__ void k2_raw_rows(int64_t n, const double* stat, const double* nmin, c
 // ---------------------------------------------------------------------------- pattern compression
 // state of a column whose tips all agree, else -1; sites outside the two batches: -2 (not mapped at all)
 __global__ void k2_classify_columns(int T, int64_t n, int64_t half, int64_t n_pad, const uint8_t* __restrict__ tips,
-                                    int32_t* __restrict__ cls, int32_t* __restrict__ varied) {
+                                    int32_t* __restrict__ cls, int32_t* __restrict__ varied, int classified) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= n_pad) return;
   const bool real = s < n || (s >= half && s < half + n);
+  if (real && classified) return; // k3_simulate wrote these while it produced the column
   int c = -2;
   if (real) {
     const uint8_t s0 = tips[s];
@@ -827,20 +828,34 @@ void launch_pair_list(int stat_id, double thr, int B, int64_t n_pad, const doubl
   k2_pair_list<<<(unsigned)((n_pairs + 127) / 128), 128, 0, st>>>(stat_id, thr, B, n_pad, out, mv, pairs, n_pairs, stat);
   CMB_CUDA(cudaGetLastError());
 }
-int launch_compress_constant(int A, int T, int64_t n, int64_t half, int64_t n_pad, const uint8_t* tips, uint8_t* tips_c,
-                             int32_t* col, int32_t* counts, DevBuf& tmp, cudaStream_t st) {
+namespace {
+size_t compress_reserve(int64_t n_pad, DevBuf& tmp, size_t* scan_bytes) {
   if (n_pad > 0x7fffffff) fail("internal: batch too large for 32-bit column indices");
   size_t need = 0;
-  cub::DeviceScan::ExclusiveSum(nullptr, need, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_pad, st);
+  cub::DeviceScan::ExclusiveSum(nullptr, need, (const int32_t*)nullptr, (int32_t*)nullptr, (int)n_pad, nullptr);
   const size_t a = ((size_t)n_pad * 4 + 255) & ~size_t(255);
   tmp.reserve(3 * a + need + 256);
+  *scan_bytes = need;
+  return a;
+}
+} // namespace
+void compress_class_buffers(int64_t n_pad, DevBuf& tmp, int32_t** col_class, int32_t** col_varied) {
+  size_t need;
+  const size_t a = compress_reserve(n_pad, tmp, &need);
+  *col_class = (int32_t*)tmp.as<unsigned char>();
+  *col_varied = (int32_t*)(tmp.as<unsigned char>() + a);
+}
+int launch_compress_constant(int A, int T, int64_t n, int64_t half, int64_t n_pad, const uint8_t* tips, uint8_t* tips_c,
+                             int32_t* col, int32_t* counts, DevBuf& tmp, cudaStream_t st, bool classified) {
+  size_t need = 0;
+  const size_t a = compress_reserve(n_pad, tmp, &need);
   unsigned char* base = tmp.as<unsigned char>();
   int32_t* cls = (int32_t*)base;
   int32_t* varied = (int32_t*)(base + a);
   int32_t* pos = (int32_t*)(base + 2 * a);
   void* ctemp = base + 3 * a;
   const unsigned g = (unsigned)((n_pad + 255) / 256);
-  k2_classify_columns<<<g, 256, 0, st>>>(T, n, half, n_pad, tips, cls, varied);
+  k2_classify_columns<<<g, 256, 0, st>>>(T, n, half, n_pad, tips, cls, varied, classified ? 1 : 0);
   CMB_CUDA(cub::DeviceScan::ExclusiveSum(ctemp, need, varied, pos, (int)n_pad, st));
   k2_compress_counts<<<1, 1, 0, st>>>(A, n_pad, pos, varied, counts);
   k2_compact_columns<<<g, 256, 0, st>>>(A, T, n_pad, tips, cls, pos, counts, tips_c, col);

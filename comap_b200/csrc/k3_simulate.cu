@@ -33,6 +33,9 @@ struct SimParams {
   const double *pi, *probs;
   uint8_t* tips;
   int32_t* classes;
+  // pattern compression of the null (k2_pairs.cu launch_compress_constant), fused: per column the state all its tips
+  // share (or -1) and the "varied" flag, written while the column is produced instead of re-read (nullable)
+  int32_t *col_class, *col_varied;
 };
 
 // Philox4x32-10 with the key schedule taken from the launch parameters: the round keys depend on the seed only,
@@ -115,6 +118,8 @@ __global__ void __launch_bounds__(NT) k3_simulate(const __grid_constant__ SimPar
 
   uint8_t stk[kMaxStack];
   int sp = 0;
+  int first = -1;
+  bool same = true;
   uint8_t* const tip_col = p.tips + idx;
   const uint32_t npad32 = (uint32_t)p.n_pad;
   const size_t tab = (size_t)C * AA;
@@ -141,8 +146,16 @@ __global__ void __launch_bounds__(NT) k3_simulate(const __grid_constant__ SimPar
         sb = draw_state(cumB + ((size_t)c * A + st) * A, A, (h1.z & 1) ? u1 : u0);
       }
       // row * n_pad as one 32 x 32 -> 64 bit multiply (rows and padded site counts are below 2^32)
-      if ((flags & kUpTipA) && live) tip_col[(uint64_t)(uint32_t)h0.y * npad32] = (uint8_t)sa;
-      if ((flags & kUpTipB) && live) tip_col[(uint64_t)(uint32_t)h0.z * npad32] = (uint8_t)sb;
+      if (flags & kUpTipA) {
+        if (live) tip_col[(uint64_t)(uint32_t)h0.y * npad32] = (uint8_t)sa;
+        same = same && (first < 0 || sa == first);
+        first = first < 0 ? sa : first;
+      }
+      if (flags & kUpTipB) {
+        if (live) tip_col[(uint64_t)(uint32_t)h0.z * npad32] = (uint8_t)sb;
+        same = same && (first < 0 || sb == first);
+        first = first < 0 ? sb : first;
+      }
       if (flags & kUpTakeA) {
         if (flags & kUpPush) stk[sp++] = (uint8_t)sb;
         st = sa;
@@ -150,6 +163,10 @@ __global__ void __launch_bounds__(NT) k3_simulate(const __grid_constant__ SimPar
       else if (flags & kUpPop) st = stk[--sp];
     }
     cs.release(k);
+  }
+  if (live && p.col_class) {
+    p.col_class[idx] = same ? first : -1;
+    p.col_varied[idx] = same ? 0 : 1;
   }
 }
 
@@ -247,7 +264,8 @@ __global__ void __launch_bounds__(NT) k3_simulate_cont(SimParams p, ContParams c
 
 void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,
                      int64_t stride, int64_t n, int64_t n_pad, int weighted, int root_node, uint8_t* tips,
-                     int32_t* classes, cudaStream_t st, int64_t half_n, int64_t half_col, int64_t half_shift) {
+                     int32_t* classes, cudaStream_t st, int64_t half_n, int64_t half_col, int64_t half_shift,
+                     int32_t* col_class, int32_t* col_varied) {
   if (n_pad >= ((int64_t)1 << 32)) fail("internal: simulated batch of %lld padded sites", (long long)n_pad);
   SimParams p;
   p.half_n = half_n; p.half_col = half_col; p.half_shift = half_shift;
@@ -260,6 +278,8 @@ void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64
   }
   p.base = base; p.group = group; p.stride = stride; p.n = n; p.n_pad = n_pad;
   p.pi = m.pi; p.probs = m.probs; p.tips = tips; p.classes = classes;
+  p.col_class = col_class; p.col_varied = col_varied;
+  if (col_class && m.cont_kind != 0) fail("internal: fused column classes need the discrete simulator");
   size_t smem = 128 + 2 * (size_t)s.cap;
   if (m.cont_kind != 0) {
     if (!m.spec) fail("internal: continuous simulation without the generator's spectrum");

@@ -80,7 +80,8 @@ __host__ __device__ inline size_t d_chunk(int64_t chunk, int slot, int n_slots, 
 // site id of thread idx = base + (idx / group) * stride + idx % group
 void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64_t base, int64_t group,
                      int64_t stride, int64_t n, int64_t n_pad, int weighted, int root_node, uint8_t* tips,
-                     int32_t* classes, cudaStream_t st, int64_t half_n = 0, int64_t half_col = 0, int64_t half_shift = 0);
+                     int32_t* classes, cudaStream_t st, int64_t half_n = 0, int64_t half_col = 0, int64_t half_shift = 0,
+                     int32_t* col_class = nullptr, int32_t* col_varied = nullptr);
 
 // ---- K2
 // mv: mean vector subtracted before a correlation (corrected correlation) or nullptr
@@ -93,8 +94,11 @@ void launch_paired(int stat_id, double thr, int B, int64_t n, int64_t n_pad, int
 // the two batches [0, n) and [half, half + n); tips_c receives the varied columns packed from 0 and the A constant
 // patterns after them; col[site] = where the site's vector will be; counts[0] = sites to map (varied + A),
 // counts[1] = varied sites.  tmp: scan scratch.
+// classified: the simulator already wrote the class / varied flag of every simulated column (compress_class_buffers of
+// the same tmp and n_pad handed to launch_simulate); only the columns outside the two batches are filled in here
 int launch_compress_constant(int A, int T, int64_t n, int64_t half, int64_t n_pad, const uint8_t* tips, uint8_t* tips_c,
-                             int32_t* col, int32_t* counts, DevBuf& tmp, cudaStream_t st);
+                             int32_t* col, int32_t* counts, DevBuf& tmp, cudaStream_t st, bool classified = false);
+void compress_class_buffers(int64_t n_pad, DevBuf& tmp, int32_t** col_class, int32_t** col_varied);
 // statistic of listed column pairs of one [B][n_pad] matrix (candidate-group statistics)
 void launch_pair_list(int stat_id, double thr, int B, int64_t n_pad, const double* out, const double* mv, const int2* pairs,
                       int64_t n_pairs, double* stat, cudaStream_t st);

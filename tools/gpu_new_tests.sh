@@ -1,3 +1,3 @@
 set -x
-( time timeout 900 python bench.py --impl reference ) > gpurun_out/r2q_ref_arm.log 2>&1; echo "ref rc=$?"; tail -5 gpurun_out/r2q_ref_arm.log | cut -c1-1500
-( time timeout 900 python bench.py ) > gpurun_out/r2q_default.log 2>&1; echo "ours rc=$?"; tail -5 gpurun_out/r2q_default.log | cut -c1-300; grep -o '"cpu_baseline".*' gpurun_out/r2q_default.log | cut -c1-1500
+timeout 900 python -m pytest tests/test_gpu_stats.py tests/test_gpu_chain.py tests/test_gpu_cluster.py tests/test_gpu_inter.py -x -q > gpurun_out/r2q_sim_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/r2q_sim_tests.log
+bash tools/ab.sh "CMB_X=0" "CMB_NULL_DEDUP=0"

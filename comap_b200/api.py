@@ -14,7 +14,7 @@ STAT = {"correlation": 0, "covariance": 1, "cosinus": 2, "cosubstitution": 3, "c
         "corrected_correlation": 5, "mi": 6, "mi_label": 7}
 DIST = {"correlation": 0, "compensation": 1, "euclidian": 2}
 LINK = {"complete": 0, "single": 1, "average": 2}
-COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2, "laplace": 3, "label": 4}
+COUNT = {"uniformization": 0, "decomposition": 1, "naive": 2, "laplace": 3, "label": 4, "one_jump": 5}
 
 
 def count_id(method):

@@ -231,8 +231,9 @@ void build_model_tables(ModelTables& mt, int A, const double* Q, const double* p
   // nijt=Laplace carries its truncation order in the upper bits (CMB_COUNT_LAPLACE_TRUNC)
   const int laplace_trunc = (count_method & 0xff) == 3 ? ((count_method >> 8) ? (count_method >> 8) : 10) : 0;
   count_method &= 0xff;
-  if (count_method < 0 || count_method > 4) fail("cmb_set_model: unknown count method %d", count_method);
+  if (count_method < 0 || count_method > 5) fail("cmb_set_model: unknown count method %d", count_method);
   if (count_method == 4 && weights) fail("cmb_set_model: nijt=Label takes no weights");
+  if (count_method == 5 && weights) fail("cmb_set_model: nijt=ProbOneJump takes no weights");
   if (count_method == 3 && (laplace_trunc < 2 || laplace_trunc > 20))
     fail("cmb_set_model: nijt=Laplace needs trunc in 2..20 (got %d)", laplace_trunc);
   if (count_method == 3 && weights) fail("cmb_set_model: nijt=Laplace takes no weights (LaplaceSubstitutionCount is not a weighted count)");
@@ -261,6 +262,13 @@ void build_model_tables(ModelTables& mt, int A, const double* Q, const double* p
         for (int x = 0; x < A; x++)
           for (int y = 0; y < A; y++)
             W[x * A + y] = x == y ? 0. : probs[c] * (P[x * A + y] * (N[x * A + y] = weights ? weights[x * A + y] : 1.));
+      } else if (count_method == 5) { // nijt=ProbOneJump [Bio++ OneJumpSubstitutionCount, from memory]: probability of
+        // at least one substitution on the branch given its two ends: 1 when they differ, 1 - exp(Q_xx t) / P_xx(t) else
+        for (int x = 0; x < A; x++)
+          for (int y = 0; y < A; y++) {
+            N[x * A + y] = x == y ? 1. - std::exp(Q[x * A + x] * t) / P[x * A + x] : 1.;
+            W[x * A + y] = probs[c] * (P[x * A + y] * N[x * A + y]);
+          }
       } else if (count_method == 4) { // nijt=Label: substitution x -> y carries the label 1 + its rank among the off-diagonal entries
         int label = 0;
         for (int x = 0; x < A; x++)

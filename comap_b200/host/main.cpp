@@ -169,7 +169,11 @@ void prepare(Inputs& in, const char* argv0, const Params* override_params = null
     if (get_string(nj.args, "weight", "None") != "None") throw Error("nijt=Label does not take weights");
     in.count_method = CMB_COUNT_LABEL;
   }
-  else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition, Naive, Laplace, Label)");
+  else if (nj.name == "ProbOneJump") { // OneJumpSubstitutionCount: P(at least one substitution on the branch | its ends)
+    if (get_string(nj.args, "weight", "None") != "None") throw Error("nijt=ProbOneJump does not take weights");
+    in.count_method = CMB_COUNT_ONE_JUMP;
+  }
+  else throw Error("nijt=" + nj.name + " is not available in this build (Uniformization, Decomposition, Naive, Laplace, Label, ProbOneJump)");
   in.weights = make_count_weights(get_string(nj.args, "weight", "None"), in.alpha, &in.weights_symmetric, data_dir_of(argv0));
   if (!in.weights.empty()) display_result("Substitution count weights", get_string(nj.args, "weight", "None"));
   in.average = get_bool(P, "nijt.average", true); // "really for benchmarking only" upstream; k1_variants.cu here

@@ -44,7 +44,8 @@ typedef struct cmb_ctx cmb_ctx;
 /* nijt= : PhylogeneticsApplicationTools::getSubstitutionCount, CoMap.cpp:152 */
 enum { CMB_COUNT_UNIFORMIZATION = 0, CMB_COUNT_DECOMPOSITION = 1, CMB_COUNT_NAIVE = 2,
        CMB_COUNT_LAPLACE = 3 /* Laplace(trunc=10): unweighted; pinned by Myo_laplace.vec */,
-       CMB_COUNT_LABEL = 4 /* Label: substitution x -> y counts as its label 1..A(A-1) (for MI, CoETools.cpp:577-589) */ };
+       CMB_COUNT_LABEL = 4 /* Label: substitution x -> y counts as its label 1..A(A-1) (for MI, CoETools.cpp:577-589) */,
+       CMB_COUNT_ONE_JUMP = 5 /* ProbOneJump: probability of at least one substitution on the branch given its ends */ };
 /* nijt=Laplace(trunc=k), k in 2..20: the truncation order rides in the upper bits of count_method */
 #define CMB_COUNT_LAPLACE_TRUNC(k) (CMB_COUNT_LAPLACE | ((k) << 8))
 /* statistic= : CoETools::getStatistic, CoETools.cpp:535-600; Statistics.h:164-295 */

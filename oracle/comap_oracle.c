@@ -290,10 +290,22 @@ static void counts_label(const spectral_t* sp, double* N) {
     for (int y = 0; y < A; y++) N[x * A + y] = x == y ? 0. : (double)++count;
 }
 
+/* nijt=ProbOneJump [Bio++ OneJumpSubstitutionCount, from memory; no golden]: probability that at least one
+ * substitution happened on a branch of length t given its two ends: 1 if they differ, else 1 - exp(Q_xx t) / P_xx(t). */
+static void counts_one_jump(const spectral_t* sp, const double* Q, double t, double* N) {
+  const int A = sp->A;
+  double* P = malloc(sizeof(double) * A * A);
+  spectral_pmatrix(sp, t, P);
+  for (int x = 0; x < A; x++)
+    for (int y = 0; y < A; y++) N[x * A + y] = x == y ? 1. - exp(Q[x * A + x] * t) / P[x * A + x] : 1.;
+  free(P);
+}
+
 static void counts_any(int method, const spectral_t* sp, const double* Q, const double* weights,
                        double t, double* N) {
   if ((method & 0xff) == ORC_COUNT_LAPLACE) counts_laplace(sp, Q, (method >> 8) ? (method >> 8) : 10, t, N);
   else if (method == ORC_COUNT_LABEL) counts_label(sp, N);
+  else if (method == ORC_COUNT_ONE_JUMP) counts_one_jump(sp, Q, t, N);
   else if (method == ORC_COUNT_NAIVE) counts_naive(sp, weights, N);
   else if (method == ORC_COUNT_DECOMPOSITION) counts_decomposition(sp, Q, weights, t, N);
   else counts_uniformization(sp, Q, weights, t, N);
@@ -302,7 +314,7 @@ static void counts_any(int method, const spectral_t* sp, const double* Q, const 
 int orc_counts(int method, int A, const double* Q, const double* pi, const double* weights,
                double t, double* N) {
   spectral_t sp;
-  if ((method & 0xff) < ORC_COUNT_UNIFORMIZATION || (method & 0xff) > ORC_COUNT_LABEL) FAIL("orc_counts: unknown method %d", method);
+  if ((method & 0xff) < ORC_COUNT_UNIFORMIZATION || (method & 0xff) > ORC_COUNT_ONE_JUMP) FAIL("orc_counts: unknown method %d", method);
   if (spectral_init(&sp, A, Q, pi)) return -1;
   counts_any(method, &sp, Q, weights, t, N);
   spectral_free(&sp);

@@ -37,7 +37,7 @@ extern "C" {
 #endif
 
 enum { ORC_COUNT_UNIFORMIZATION = 0, ORC_COUNT_DECOMPOSITION = 1, ORC_COUNT_NAIVE = 2,
-       ORC_COUNT_LAPLACE = 3 /* | trunc << 8; trunc 0 = 10 */, ORC_COUNT_LABEL = 4 };
+       ORC_COUNT_LAPLACE = 3 /* | trunc << 8; trunc 0 = 10 */, ORC_COUNT_LABEL = 4, ORC_COUNT_ONE_JUMP = 5 };
 enum {
   ORC_STAT_CORRELATION = 0,
   ORC_STAT_COVARIANCE = 1,

@@ -205,6 +205,18 @@ def test_label_counts_without_averaging_are_labels(ctx):
         ctx.set_map_mode()
 
 
+def test_prob_one_jump_count_on_the_device(ctx):
+    """nijt=ProbOneJump (OneJumpSubstitutionCount): device vs oracle, nucleotides and proteins."""
+    for c in (H.random_dna_case(30, 280, 41, ambiguity=0.03), H.myoglobin_inputs()):
+        ctx.set_tree(c["parent"], c["brlen"])
+        ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"], count_method="one_jump")
+        ctx.set_alignment(c["codes"], c["code_mask"])
+        r = ctx.map()
+        q = O.map_sites(c["parent"], c["brlen"], c["Q"], c["pi"], c["rates"], c["probs"], c["codes"], c["code_mask"], method="one_jump")
+        assert np.allclose(r["n"], q["n"], rtol=RTOL, atol=1e-14)
+        assert r["n"].min() >= -1e-12 and r["n"].max() <= 1 + 1e-12     # every entry is a probability
+
+
 def test_marginal_ancestral_states_vs_oracle(ctx):
     """asr.method = marginal (CoMap.cpp:168-198): state of largest marginal posterior at every node, device vs oracle;
     the leaves of resolved columns come back as observed."""

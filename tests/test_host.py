@@ -139,6 +139,8 @@ def test_count_weights_and_second_data_set_options(binary, tmp_path):
     assert p.returncode == 0 and o["count_method"] == [str(3 | 10 << 8)]
     p, o = dry_run(binary, str(tmp_path), *common, "nijt=Laplace(trunc=6)")
     assert o["count_method"] == [str(3 | 6 << 8)]
+    p, o = dry_run(binary, str(tmp_path), *common, "nijt=ProbOneJump")
+    assert p.returncode == 0 and o["count_method"] == ["5"]
     p, _ = dry_run(binary, str(tmp_path), *common, "nijt=Laplace(weight=Diff(index1=Volume, symmetrical=no))")
     assert p.returncode == 255 and "does not take weights" in p.stdout
     # second data set: same files, all sites instead of the complete ones; the tree is copied
@@ -222,7 +224,7 @@ def test_rooted_tree_is_unrooted_and_errors_are_reported(binary, tmp_path):
     assert p.returncode == 0 and "Tree has been unrooted" in p.stdout
     d = decode(out)
     assert len(d["parent"]) == 6 and (d["parent"] == -1).sum() == 1 and np.isclose(d["brlen"].sum(), 0.1 + 0.2 + 0.3 + 0.4 + 0.12)
-    for bad, msg in (("model=LG08", "not supported for nucleotides"), ("nijt=ProbOneJump", "not available"),
+    for bad, msg in (("model=LG08", "not supported for nucleotides"), ("nijt=Bogus", "not available"),
                      ("input.tree.file=missing.dnd", "cannot open"), ("alphabet=Codon", "not supported"),
                      ("rate_distribution=Gamma(n=0,alpha=1)", "n must be positive")):
         p, out = dry_run(binary, str(tmp_path), "param=o.bpp", bad)

@@ -306,3 +306,20 @@ def test_label_count_and_label_mutual_information():
                     e += n12 / B * np.log(n12 * B / (np.sum(a == u) * np.sum(b == w))) / np.log(2.7182818)
         assert abs(O.stat("mi_label", a, b) - e) < 1e-12
         assert abs(O.stat("mi_label", a + 1e-13, b - 1e-13) - e) < 1e-12   # labels recovered through the +-0.5 bounds
+
+
+def test_prob_one_jump_count():
+    """nijt=ProbOneJump: 1 when the ends differ; for equal ends 1 - P(no event on the branch) / P_xx(t), which the
+    converged uniformization series confirms: P(no event | x -> x) = exp(Q_xx t) / P_xx(t)."""
+    Q, pi = syn.hky85(2.5, [0.3, 0.2, 0.2, 0.3])
+    for t in (1e-6, 0.05, 0.7, 3.0):
+        N = O.counts(Q, pi, t, method="one_jump")
+        P = O.pmatrix(Q, pi, t)
+        off = ~np.eye(4, dtype=bool)
+        assert np.all(N[off] == 1.0)
+        assert np.allclose(np.diag(N), 1 - np.exp(np.diag(Q) * t) / np.diag(P), rtol=1e-12, atol=1e-15)
+        assert np.all((np.diag(N) >= -1e-15) & (np.diag(N) < 1))
+    # more substitutions are expected than the probability of at least one, and they agree on short branches
+    Nu = O.counts(Q, pi, 1e-3)
+    N1 = O.counts(Q, pi, 1e-3, method="one_jump")
+    assert np.all(Nu >= N1 - 1e-12) and np.allclose(Nu[off], N1[off], atol=2e-3)

@@ -671,7 +671,9 @@ __global__ void __launch_bounds__(256) k2_tiles(TileParams p) {
       // rows u*16+ty, columns v*16+tx: every operand read is one 64-bit LDS whose 32 lanes touch one 128-byte
       // line (a: two addresses, b: sixteen, the other half-warp broadcast) = 1 wavefront.  The 4x4 blocked
       // mapping (rows ty*4.., cols tx*4.. as 128-bit loads) cost 24 wavefronts per kk against 16 cycles of
-      // FP64 issue (ncu r2m: l1tex 81 %, FP64 pipe 45 %); this one costs 8.
+      // FP64 issue (ncu r2m: l1tex 81 %, FP64 pipe 45 %); this one costs 8.  Three CTAs per SM instead of two
+      // (__launch_bounds__(256, 3): 80 registers, ~150 B of spills) measured slower: pairs 3.3 vs 2.95 ms, the
+      // 20 000-site distance matrix 15.9 vs 13.9 ms.
       double a[4], b[4];
 #pragma unroll
       for (int u = 0; u < 4; u++) { a[u] = As[kk][u * 16 + ty]; b[u] = Bs[kk][u * 16 + tx]; }

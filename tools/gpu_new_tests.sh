@@ -1,3 +1,5 @@
 set -x
-timeout 900 python -m pytest tests/test_gpu_stats.py tests/test_gpu_chain.py tests/test_gpu_cluster.py tests/test_gpu_inter.py -x -q > gpurun_out/r2q_sim_tests.log 2>&1; echo "tests rc=$?"; tail -4 gpurun_out/r2q_sim_tests.log
-bash tools/ab.sh "CMB_X=0" "CMB_NULL_DEDUP=0"
+bash tools/ab.sh "CMB_X=0" "CMB_X=1"
+python bench.py --workload clustering --steps 2 --warmup 1 2>&1 | tail -1 | python -c "
+import sys, json
+l = json.loads(sys.stdin.readline()); print('clustering ms/step %.1f kernels %s' % (l['ms_per_step'], {k: round(v, 1) for k, v in l['kernel_ms_per_step'].items()}))"

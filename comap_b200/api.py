@@ -31,6 +31,7 @@ SYMBOLS = [
     "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
     "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates", "cmb_set_async", "cmb_set_mi_threshold", "cmb_set_map_mode", "cmb_ancestral_states",
+    "cmb_mica_sites", "cmb_mica_pairs", "cmb_mica_pair_list", "cmb_mica_null_parametric", "cmb_null_load",
     "cmb_comm_unique_id", "cmb_comm_init", "cmb_comm_init_all", "cmb_comm_set", "cmb_comm_destroy", "cmb_comm_rank",
     "cmb_comm_group_start", "cmb_comm_group_end", "cmb_null_intra_sharded", "cmb_set_continuous_rates",
 ]
@@ -196,6 +197,45 @@ class Context:
         out = np.empty((self.B + 1, self.S), dtype=np.uint8)
         self._chk(self.lib.cmb_ancestral_states(self.h, out.ctypes.data_as(C.POINTER(C.c_uint8))))
         return out
+
+    # ------------------------------------------------------------------ Mica (CoMap/Mica.cpp)
+    def mica_sites(self):
+        """Entropy of every site and its average MI with all the others (Mica.cpp:341-361)."""
+        h = np.empty(self.S); a = np.empty(self.S)
+        self._chk(self.lib.cmb_mica_sites(self.h, _d(h), _d(a)))
+        return h, a
+
+    def mica_pairs(self, key="nmin", use_null=False):
+        """All pairs in mica's order: MI, Hjoint, Hmin, Nmin and the bootstrap p-value / Nsim (Mica.cpp:646-689)."""
+        n = self.S * (self.S - 1) // 2
+        r = dict(i=np.empty(n, np.int32), j=np.empty(n, np.int32), mi=np.empty(n), hjoint=np.empty(n), hmin=np.empty(n),
+                 nmin=np.empty(n), pvalue=np.full(n, np.nan), nsim=np.zeros(n, np.int32))
+        k = C.c_int64(0)
+        self._chk(self.lib.cmb_mica_pairs(self.h, {"nmin": 1, "hmin": 2}[key], int(bool(use_null)), C.c_int64(n),
+                                          r["i"].ctypes.data_as(C.POINTER(C.c_int32)), r["j"].ctypes.data_as(C.POINTER(C.c_int32)),
+                                          _d(r["mi"]), _d(r["hjoint"]), _d(r["hmin"]), _d(r["nmin"]), _d(r["pvalue"]),
+                                          r["nsim"].ctypes.data_as(C.POINTER(C.c_int32)), C.byref(k)))
+        assert k.value == n
+        return r
+
+    def mica_pair_list(self, site1, site2):
+        a = np.ascontiguousarray(site1, dtype=np.int32); b = np.ascontiguousarray(site2, dtype=np.int32)
+        mi = np.empty(len(a)); hj = np.empty(len(a))
+        self._chk(self.lib.cmb_mica_pair_list(self.h, C.c_int64(len(a)), a.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              b.ctypes.data_as(C.POINTER(C.c_int32)), _d(mi), _d(hj)))
+        return mi, hj
+
+    def mica_null_parametric(self, seed, rep_cpu, rep_ram, K=10, nmax=-1.0, weighted_classes=False):
+        """null.method = parametric-bootstrap (Mica.cpp:470-545); returns the [n][3] rows MI, Hjoint, Nmin."""
+        raw = np.empty((rep_cpu * rep_ram, 3))
+        self._chk(self.lib.cmb_mica_null_parametric(self.h, C.c_uint64(seed), int(rep_cpu), int(rep_ram), int(bool(weighted_classes)),
+                                                    int(K), C.c_double(nmax), _d(raw)))
+        return raw
+
+    def null_load(self, stat, key, K, kmax):
+        """A null distribution from host arrays: statistics and the key they are binned by."""
+        s = np.ascontiguousarray(stat, dtype=np.float64); k = np.ascontiguousarray(key, dtype=np.float64)
+        self._chk(self.lib.cmb_null_load(self.h, _d(s), _d(k), C.c_int64(len(s)), int(K), C.c_double(kmax)))
 
     def set_mi_threshold(self, threshold):
         """Threshold of statistic 'mi' (MI(threshold=0.99) upstream)."""

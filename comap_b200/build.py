@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libcomap_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-CU = ["capi.cu", "capi_stats.cu", "capi_inter.cu", "k1_map.cu", "k1_mma.cu", "k1_mma20.cu", "k1_variants.cu", "k2_pairs.cu", "k3_simulate.cu", "k4_cluster.cu", "k4_rnn.cu"]
+CU = ["capi.cu", "capi_stats.cu", "capi_inter.cu", "capi_mica.cu", "k5_mica.cu", "k1_map.cu", "k1_mma.cu", "k1_mma20.cu", "k1_variants.cu", "k2_pairs.cu", "k3_simulate.cu", "k4_cluster.cu", "k4_rnn.cu"]
 CPP = ["tables.cpp", "schedule.cpp", "comm.cpp"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler", "-ffp-contract=off"]

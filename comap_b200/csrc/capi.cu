@@ -357,7 +357,7 @@ int cmb_ctx_destroy(cmb_ctx* ctx) {
                     &c.s_out[0], &c.s_out[1], &c.s_sum[0], &c.s_sum[1], &c.s_sumsq[0], &c.s_sumsq[1], &c.s_cls,
                     &c.d_identity_mask, &c.null.stat, &c.null.nmin, &c.null.sorted, &c.null.bin_off_dev,
                     &c.d_dist, &c.scratch, &c.scratch2, &c.staging, &c.pair_table, &c.pairs_mean, &c.pairs_sd, &c.pairs_norm,
-                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part, &c.k1_part_obs, &c.var_tree, &c.var_tabs, &c.var_scratch, &c.var_scratch_obs, &c.d_spec, &c.dist_tiles, &c.s_cols, &c.s_counts, &c.cn_mean, &c.cn_sd, &c.cn_norm, &c.cn_staging,
+                    &c.d_meanvec, &c.corr_mean, &c.corr_sd, &c.mi_count, &c.gather_send, &c.gather_recv, &c.k1_part, &c.k1_part_obs, &c.var_tree, &c.var_tabs, &c.var_scratch, &c.var_scratch_obs, &c.mica_sites, &c.mica_table, &c.d_spec, &c.dist_tiles, &c.s_cols, &c.s_counts, &c.cn_mean, &c.cn_sd, &c.cn_norm, &c.cn_staging,
                     &c.cn_dists[0], &c.cn_dists[1], &c.cn_dists[2], &c.cn_dists[3], &c.cn_works[0], &c.cn_works[1], &c.cn_works[2],
                     &c.cn_works[3], &c.cn_outs[0], &c.cn_outs[1], &c.cn_outs[2], &c.cn_outs[3]};
   for (DevBuf* b : bufs) b->release();
@@ -444,6 +444,7 @@ int cmb_set_alignment(cmb_ctx* ctx, int64_t S, const uint8_t* codes, int32_t n_c
   CMB_CUDA(cudaStreamSynchronize(c.stream));
   c.have_alignment = true;
   c.mapped = false;
+  c.mica_ready = false;
   if (c.null.nmax_from_map) c.null.ready = false;
   CMB_CATCH
 }

@@ -338,6 +338,14 @@ void groups_of_dendrogram(Context& c, int dist_id, int max_size, int64_t S, int6
 
 } // namespace
 
+// shared with capi_mica.cu
+namespace cmb {
+MapBuffers sim_batch_buffers(Context& c, int64_t n, int64_t n_pad) { return sim_buffers(c, 0, n, n_pad); }
+void load_null_distribution(Context& c, const double* stat_dev, const double* key_dev, int64_t n, int K, double kmax) {
+  null_load(c, stat_dev, key_dev, n, K, kmax);
+}
+} // namespace cmb
+
 extern "C" {
 
 int cmb_simulate(cmb_ctx* ctx, uint64_t seed, int64_t first_site, int64_t n, int32_t weighted_classes,

@@ -99,6 +99,9 @@ struct Context {
   bool have_dendro = false;
 
   DevBuf scratch, scratch2, staging;
+  // Mica (capi_mica.cu): entropy [S_pad] | average MI [S_pad] | dense MI / Hjoint / Hmin / Nmin / PValue columns, i, j, Nsim
+  DevBuf mica_sites, mica_table;
+  bool mica_ready = false;       // the dense MI / Hjoint columns belong to the current alignment
   DevBuf pair_table;            // resident pair columns (fixed layout, see cmb_pairs_resident)
   cudaStream_t copy_stream = nullptr; // D2H of pair columns overlaps later kernels
   cudaEvent_t copy_event = nullptr;

@@ -83,6 +83,19 @@ void launch_simulate(const MapModel& m, const DevStream& s, uint64_t seed, int64
                      int32_t* classes, cudaStream_t st, int64_t half_n = 0, int64_t half_col = 0, int64_t half_shift = 0,
                      int32_t* col_class = nullptr, int32_t* col_varied = nullptr);
 
+// ---- K5: Mica's column statistics (k5_mica.cu)
+void launch_mica_entropy(int A, int T, int64_t n, int64_t n_pad, const uint8_t* tips, const uint32_t* cmask, double* entropy,
+                         cudaStream_t st);
+void launch_mica_pairs(int A, int T, int64_t S, int64_t n_pad, const uint8_t* tips, const uint32_t* cmask, double* mi, double* hj,
+                       cudaStream_t st);
+// site a[r] of tip matrix t1 against site b[r] of t2 (a / b nullptr: r itself)
+void launch_mica_listed(int A, int T, int64_t n, const uint8_t* t1, int64_t np1, const uint8_t* t2, int64_t np2, const int32_t* a,
+                        const int32_t* b, const uint32_t* cmask, double* mi, double* hj, cudaStream_t st);
+void launch_mica_average(int64_t S, const double* mi, double* avg, cudaStream_t st);
+void launch_mica_rows(int64_t S, const double* entropy, const double* norm, int32_t* oi, int32_t* oj, double* hmin, double* nmin,
+                      cudaStream_t st);
+void launch_min2(int64_t n, const double* a, const double* b, double* out, cudaStream_t st);
+
 // ---- K2
 // mv: mean vector subtracted before a correlation (corrected correlation) or nullptr
 // col1 / col2 (nullable): column of pair j's first / second site in o1 / o2 (pattern-compressed mappings); else j

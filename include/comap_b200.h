@@ -303,6 +303,29 @@ int cmb_cluster_null(cmb_ctx* ctx, int32_t dist_id, int32_t linkage, uint64_t se
                      int32_t* row_size, double* row_dmax, double* row_stat, double* row_nmin,
                      int32_t* members, int64_t* offsets, int64_t* n_rows);
 
+/* ---- Mica (CoMap/Mica.cpp): mutual information between alignment COLUMNS, conditioned like the pairwise analysis ----
+ * SiteTools::entropy / mutualInformation / jointEntropy(site, resolveUnknowns = true) are Bio++ bpp-seq code that is not
+ * in the reference tree and no output of mica ships with it: restated from memory, parity unpinned. */
+enum { CMB_MICA_KEY_NMIN = 1 /* use_model = yes: bins of min(norm), Mica.cpp:397 */, CMB_MICA_KEY_HMIN = 2 /* bins of min(entropy), :399 */ };
+/* Mica.cpp:341-361: entropy of every site and its average MI with all the other sites (nullable outputs, [S]). */
+int cmb_mica_sites(cmb_ctx* ctx, double* entropy, double* average_mi);
+/* The table loop, Mica.cpp:646-689: all pairs i < j in that order -- MI, joint entropy, Hmin = min(entropy), Nmin = min
+ * norm of the mapped alignment (NaN without cmb_map) and, with use_null, the p-value (nsim - #{sim < MI} + 1)/(nsim + 1)
+ * in the bin of `key` (NaN / 0 where mica prints "NA 0").  APC and RCW are averageMI[i] averageMI[j] / mean(averageMI)
+ * and / 2 (:661-662): one multiplication per row, left to the caller. */
+int cmb_mica_pairs(cmb_ctx* ctx, int32_t key, int32_t use_null, int64_t capacity, int32_t* out_i, int32_t* out_j, double* mi,
+                   double* hjoint, double* hmin, double* nmin, double* pvalue, int32_t* nsim, int64_t* n_rows);
+/* MI / joint entropy of listed site pairs of the alignment: the nonparametric bootstrap's resampled pairs (Mica.cpp:423-431). */
+int cmb_mica_pair_list(cmb_ctx* ctx, int64_t n, const int32_t* site1, const int32_t* site2, double* mi, double* hjoint);
+/* null.method = parametric-bootstrap (Mica.cpp:470-545): per outer replicate two simulated alignments of rep_ram sites,
+ * mapped for their norms (computeSubstitutionVectors), MI of site j with site j, binned by min norm over [0, nmax)
+ * (nmax < 0: the mapped alignment's largest norm).  raw: nullable [rep_cpu * rep_ram][3] = MI, Hjoint, Nmin. */
+int cmb_mica_null_parametric(cmb_ctx* ctx, uint64_t seed, int32_t rep_cpu, int32_t rep_ram, int32_t weighted_classes, int32_t K,
+                             double nmax, double* raw);
+/* A null distribution from host arrays -- n statistics and the key they are conditioned on, K bins over [0, kmax) -- for
+ * the null methods whose samples the caller builds (Mica.cpp:401-468 nonparametric bootstrap, :546-606 z-score). */
+int cmb_null_load(cmb_ctx* ctx, const double* stat, const double* key, int64_t n, int32_t K, double kmax);
+
 /* Measurement: device time (CUDA events on the context's stream) and launch counts per
  * kernel family since the last reset.  name in {"map_down","map_up","simulate","pairs",
  * "null_pairs","sort","distance","cluster","other"}. */

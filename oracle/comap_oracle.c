@@ -1323,3 +1323,93 @@ int orc_groups(int dist_id, int64_t S, int B, const double* n, const double* nor
   free(stack); free(state); free(first); free(dfs);
   return 0;
 }
+
+
+/* ------------------------------------------------------------------------------------ */
+/* Mica (CoMap/Mica.cpp): mutual information between alignment columns                   */
+/* ------------------------------------------------------------------------------------ */
+
+/* [Bio++ bpp-seq, from memory; no output of mica ships with the reference: parity unpinned]
+ * SymbolListTools::getCounts / getFrequencies with resolveUnknowns = true: a character compatible with k states adds
+ * 1/k to each of them (a pair of characters 1/(k1 k2) to every combination); frequencies = counts / number of
+ * sequences.  SiteTools::getSitesToAnalyse turns gaps into unknown characters, so a column holds no gap; a character
+ * outside the alphabet (mask 0) counts for nothing and the "correction for gaps" of mutualInformation / jointEntropy
+ * (division by the total of the joint table) absorbs it. */
+static int popcount32(uint32_t m) { int k = 0; while (m) { k += m & 1u; m >>= 1; } return k; }
+
+/* SiteTools::entropy(site, true): - sum_x p_x ln p_x   (Mica.cpp:357) */
+double orc_site_entropy(int T, const uint8_t* col, int A, int n_codes, const uint32_t* code_mask) {
+  double* cnt = calloc(A, sizeof(double));
+  uint32_t full = (A >= 32) ? 0xffffffffu : ((1u << A) - 1u);
+  for (int t = 0; t < T; t++) {
+    uint32_t m = col[t] < n_codes ? code_mask[col[t]] & full : 0;
+    int k = popcount32(m);
+    if (!k) continue;
+    for (int x = 0; x < A; x++)
+      if ((m >> x) & 1u) cnt[x] += 1. / (double)k;
+  }
+  double h = 0.;
+  for (int x = 0; x < A; x++) {
+    double f = cnt[x] / (double)T;
+    if (f != 0.) h += f * log(f);
+  }
+  free(cnt);
+  return -h;
+}
+
+/* SiteTools::mutualInformation(site1, site2, true) and jointEntropy(site1, site2, true) (Mica.cpp:92,354,430):
+ * joint frequencies p12, tot = their sum over the alphabet's states, marginals from the joint table, then
+ * MI = sum p ln(p / (p1 p2)), Hjoint = - sum p ln p with p = p12 / tot, rows then columns. */
+void orc_site_pair(int T, const uint8_t* c1, const uint8_t* c2, int A, int n_codes, const uint32_t* code_mask,
+                   double* mi_out, double* hjoint_out) {
+  double* cnt = calloc((size_t)A * A + 2 * A, sizeof(double));
+  double *p1 = cnt + (size_t)A * A, *p2 = p1 + A;
+  uint32_t full = (A >= 32) ? 0xffffffffu : ((1u << A) - 1u);
+  for (int t = 0; t < T; t++) {
+    uint32_t m1 = c1[t] < n_codes ? code_mask[c1[t]] & full : 0, m2 = c2[t] < n_codes ? code_mask[c2[t]] & full : 0;
+    int k1 = popcount32(m1), k2 = popcount32(m2);
+    if (!k1 || !k2) continue;
+    double w = 1. / ((double)k1 * (double)k2);
+    for (int x = 0; x < A; x++)
+      if ((m1 >> x) & 1u)
+        for (int y = 0; y < A; y++)
+          if ((m2 >> y) & 1u) cnt[x * A + y] += w;
+  }
+  double tot = 0.;
+  for (int x = 0; x < A; x++)
+    for (int y = 0; y < A; y++) {
+      double pxy = cnt[x * A + y] / (double)T;
+      tot += pxy; p1[x] += pxy; p2[y] += pxy;
+    }
+  for (int x = 0; x < A; x++) { p1[x] /= tot; p2[x] /= tot; }
+  double mi = 0., h = 0.;
+  for (int x = 0; x < A; x++)
+    for (int y = 0; y < A; y++) {
+      double pxy = cnt[x * A + y] / (double)T / tot;
+      if (pxy > 0.) { mi += pxy * log(pxy / (p1[x] * p2[y])); h += pxy * log(pxy); }
+    }
+  free(cnt);
+  if (mi_out) *mi_out = mi;
+  if (hjoint_out) *hjoint_out = -h;
+}
+
+/* Mica.cpp:341-361: entropy of every site and its average MI with all the others (sum over j != i, j ascending,
+ * divided by S - 1).  codes: [T][S] tip-major. */
+void orc_mica_sites(int64_t S, int T, const uint8_t* codes, int A, int n_codes, const uint32_t* code_mask,
+                    double* entropy, double* average_mi) {
+  uint8_t* cols = malloc((size_t)S * T);
+  for (int64_t s = 0; s < S; s++)
+    for (int t = 0; t < T; t++) cols[s * T + t] = codes[(size_t)t * S + s];
+  for (int64_t i = 0; i < S; i++) {
+    double sum = 0.;
+    for (int64_t j = 0; j < S; j++)
+      if (j != i) {
+        double mi;
+        orc_site_pair(T, cols + i * T, cols + j * T, A, n_codes, code_mask, &mi, NULL);
+        sum += mi;
+      }
+    if (entropy) entropy[i] = orc_site_entropy(T, cols + i * T, A, n_codes, code_mask);
+    if (average_mi) average_mi[i] = sum / (double)(S - 1);
+  }
+  free(cols);
+}

@@ -157,4 +157,12 @@ int orc_simulate_continuous(int n_nodes, const int32_t* parent, const double* br
                             const double* pi, int kind, double alpha, double p_inv, uint64_t seed,
                             int64_t first_site, int64_t n, uint8_t* states, double* rates_out);
 
+/* Mica (CoMap/Mica.cpp): SiteTools::entropy / mutualInformation / jointEntropy with resolveUnknowns = true [Bio++ bpp-seq,
+ * from memory]; columns are T codes, code_mask as everywhere else */
+double orc_site_entropy(int T, const uint8_t* col, int A, int n_codes, const uint32_t* code_mask);
+void orc_site_pair(int T, const uint8_t* c1, const uint8_t* c2, int A, int n_codes, const uint32_t* code_mask,
+                   double* mi_out, double* hjoint_out);
+void orc_mica_sites(int64_t S, int T, const uint8_t* codes, int A, int n_codes, const uint32_t* code_mask,
+                    double* entropy, double* average_mi);
+
 #endif

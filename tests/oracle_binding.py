@@ -113,6 +113,30 @@ def ancestral_states(parent, brlen, Q, pi, rates, probs, codes, code_mask):
     return out
 
 
+def site_entropy(col, A, code_mask):
+    col = np.ascontiguousarray(col, dtype=np.uint8); m = np.ascontiguousarray(code_mask, dtype=np.uint32)
+    lib().orc_site_entropy.restype = C.c_double
+    return lib().orc_site_entropy(len(col), _p(col, C.c_uint8), A, len(m), _p(m, C.c_uint32))
+
+
+def site_pair(c1, c2, A, code_mask):
+    """(MI, Hjoint) of two alignment columns: SiteTools::mutualInformation / jointEntropy(.., true) (Mica.cpp)."""
+    c1 = np.ascontiguousarray(c1, dtype=np.uint8); c2 = np.ascontiguousarray(c2, dtype=np.uint8)
+    m = np.ascontiguousarray(code_mask, dtype=np.uint32)
+    mi = C.c_double(); hj = C.c_double()
+    lib().orc_site_pair(len(c1), _p(c1, C.c_uint8), _p(c2, C.c_uint8), A, len(m), _p(m, C.c_uint32), C.byref(mi), C.byref(hj))
+    return mi.value, hj.value
+
+
+def mica_sites(codes, A, code_mask):
+    """Entropy and average MI of every site (Mica.cpp:341-361); codes [T][S]."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8); m = np.ascontiguousarray(code_mask, dtype=np.uint32)
+    T, S = codes.shape
+    h = np.empty(S); a = np.empty(S)
+    lib().orc_mica_sites(C.c_int64(S), T, _p(codes, C.c_uint8), A, len(m), _p(m, C.c_uint32), _d(h), _d(a))
+    return h, a
+
+
 def set_mi_threshold(t):
     lib().orc_set_mi_threshold(C.c_double(t))
 

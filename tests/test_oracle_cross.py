@@ -323,3 +323,41 @@ def test_prob_one_jump_count():
     Nu = O.counts(Q, pi, 1e-3)
     N1 = O.counts(Q, pi, 1e-3, method="one_jump")
     assert np.all(Nu >= N1 - 1e-12) and np.allclose(Nu[off], N1[off], atol=2e-3)
+
+
+def _np_pair(c1, c2, A, mask):
+    """numpy restatement of mutualInformation / jointEntropy with unknowns resolved (joint table by outer products)."""
+    P = np.zeros((A, A))
+    for a, b in zip(c1, c2):
+        v1 = ((mask[a] >> np.arange(A)) & 1).astype(float); v2 = ((mask[b] >> np.arange(A)) & 1).astype(float)
+        if v1.sum() and v2.sum():
+            P += np.outer(v1 / v1.sum(), v2 / v2.sum())
+    P /= P.sum()
+    p1, p2 = P.sum(1), P.sum(0)
+    nz = P > 0
+    return float((P[nz] * np.log(P[nz] / np.outer(p1, p2)[nz])).sum()), float(-(P[nz] * np.log(P[nz])).sum())
+
+
+def test_mica_site_statistics_vs_numpy():
+    """Mica (CoMap/Mica.cpp:92,341-361): entropy, MI and joint entropy of alignment columns, unknown characters resolved
+    over their compatible states."""
+    rng = np.random.default_rng(3)
+    mask = np.array([1, 2, 4, 8, 15, 5, 0], np.uint32)       # A C G T N R(A|G) and a character outside the alphabet
+    codes = rng.choice(7, size=(40, 12), p=[0.3, 0.25, 0.2, 0.15, 0.05, 0.04, 0.01]).astype(np.uint8)
+    codes[:, 3] = codes[:, 2]                                  # identical columns: MI = H = Hjoint
+    codes[:, 5] = 1                                            # constant column: MI = 0 with everything
+    for i, j in ((0, 1), (2, 3), (5, 7), (4, 9), (11, 0)):
+        mi, hj = O.site_pair(codes[:, i], codes[:, j], 4, mask)
+        emi, ehj = _np_pair(codes[:, i], codes[:, j], 4, mask)
+        assert abs(mi - emi) < 1e-12 and abs(hj - ehj) < 1e-12
+    mi, hj = O.site_pair(codes[:, 5], codes[:, 7], 4, mask)
+    assert abs(mi) < 1e-15
+    res = codes[:, 2] < 4                                      # entropy of the resolved part by hand
+    col = np.where(codes[:, 2] < 4, codes[:, 2], 0)
+    h = O.site_entropy(col, 4, mask)
+    f = np.bincount(col, minlength=4) / len(col)
+    assert abs(h + (f[f > 0] * np.log(f[f > 0])).sum()) < 1e-13
+    H, avg = O.mica_sites(codes, 4, mask)
+    assert abs(H[2] - O.site_entropy(codes[:, 2], 4, mask)) == 0
+    e = np.mean([O.site_pair(codes[:, 4], codes[:, j], 4, mask)[0] for j in range(12) if j != 4])
+    assert abs(avg[4] - e) < 1e-13

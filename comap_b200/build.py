@@ -67,6 +67,11 @@ def build_host(force=False):
         cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-Wall", "-Wextra", "-pthread", "-o", HOST_BIN] + srcs + \
               ["-L" + HERE, "-lcomap_b200", "-Wl,-rpath,$ORIGIN/..", "-Wl,-rpath-link," + "/usr/local/cuda/lib64"]
         subprocess.check_call(cmd)
+    # `mica` (CoMap/Mica.cpp) is the same executable under its own name (main() dispatches on argv[0])
+    mica = os.path.join(os.path.dirname(HOST_BIN), "mica_b200")
+    if force or _stale(mica, [HOST_BIN]):
+        import shutil
+        shutil.copy2(HOST_BIN, mica)
     return HOST_BIN
 
 

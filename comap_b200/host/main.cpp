@@ -114,12 +114,16 @@ Params second_data_set_params(const Params& P) {
   return Q;
 }
 
-void prepare(Inputs& in, const char* argv0, const Params* override_params = nullptr, const Tree* first_tree = nullptr) {
+// with_model = false (mica without use_model, Mica.cpp:186-199): no tree, model or counts are read; the alignment's
+// sequences hang off a star tree so that the library knows the rows
+void prepare(Inputs& in, const char* argv0, const Params* override_params = nullptr, const Tree* first_tree = nullptr,
+             bool with_model = true) {
   const Params& P = override_params ? *override_params : in.app.params;
   display_message(first_tree ? "\nLoading second dataset...\n" : "\n\n-*- Retrieve data and model -*-\n");
   // tree (PhylogeneticsApplicationTools::getTree, CoMap.cpp:125-129; second data set: CoMap.cpp:238-252)
   std::string tree_path = get_path(P, "input.tree.file", "none");
-  if (tree_path == "none" && first_tree) in.tree = *first_tree; // "Copy tree."
+  if (!with_model) {
+  } else if (tree_path == "none" && first_tree) in.tree = *first_tree; // "Copy tree."
   else {
     if (tree_path == "none") throw Error("input.tree.file is not set");
     std::string tfmt = get_string(P, "input.tree.format", "Newick");
@@ -129,9 +133,11 @@ void prepare(Inputs& in, const char* argv0, const Params* override_params = null
     if (first_tree && in.tree.parent != first_tree->parent)
       throw Error("The second tree must have the same topology as the first tree.");
   }
-  display_result("Number of leaves", in.tree.leaves.size());
-  display_result("Number of sons at root", in.tree.n_root_children);
-  if (in.tree.was_unrooted) display_message("WARNING!!! Tree has been unrooted.");
+  if (with_model) {
+    display_result("Number of leaves", in.tree.leaves.size());
+    display_result("Number of sons at root", in.tree.n_root_children);
+    if (in.tree.was_unrooted) display_message("WARNING!!! Tree has been unrooted.");
+  }
   // data (CoETools::readData, CoETools.cpp:78-124)
   in.alpha = make_alphabet(get_string(P, "alphabet", "DNA"));
   display_result("Alphabet type ", in.alpha.name);
@@ -141,8 +147,19 @@ void prepare(Inputs& in, const char* argv0, const Params* override_params = null
   in.aln = read_alignment(seq_path, sfmt);
   display_result("Sequence file ", seq_path);
   in.cols = select_sites(in.aln, in.alpha, P, sfmt, &in.all_cols);
-  if (get_string(P, "nonhomogeneous", "no") != "no")
+  if (!with_model) {
+    const int T = (int)in.aln.names.size();
+    if (T < 2) throw Error("at least two sequences are needed");
+    in.tree = Tree();
+    in.tree.parent.assign(T + 1, T); in.tree.parent[T] = -1;
+    in.tree.brlen.assign(T + 1, 0.1); in.tree.brlen[T] = 0.;
+    in.tree.name = in.aln.names; in.tree.name.push_back("");
+    for (int v = 0; v < T; v++) in.tree.leaves.push_back(v);
+    in.tree.n_root_children = T;
+  }
+  if (with_model && get_string(P, "nonhomogeneous", "no") != "no")
     throw Error("nonhomogeneous models are outside the B200 hot path (SURVEY.md s2.1); use nonhomogeneous=no");
+  if (with_model) {
   in.model = make_model(get_string(P, "model", "JC69"), in.alpha, data_dir_of(argv0));
   display_result("Substitution model", in.model.name);
   if (!in.model.warning.empty()) display_message(in.model.warning);
@@ -180,6 +197,7 @@ void prepare(Inputs& in, const char* argv0, const Params* override_params = null
   in.joint = get_bool(P, "nijt.joint", true);
   if (!in.average || !in.joint) display_result("Mapping variant", std::string(in.average ? "average" : "no averaging") + (in.joint ? ", joint pair" : ", marginal"));
   display_result("Substitution count", nj.name);
+  }
   // leaf rows: sequence of every leaf, in leaf id order
   std::map<std::string, int> row;
   for (size_t i = 0; i < in.aln.names.size(); i++) row[in.aln.names[i]] = (int)i;
@@ -434,6 +452,179 @@ Mapped map_data_set(Inputs& in, const Params& P, const std::string& suffix) {
   return m;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// mica param=FILE key=value ...   (CoMap/Mica.cpp:132-704): mutual information between alignment columns, optionally
+// conditioned on the norms of a substitution mapping (use_model = yes), with a null distribution by parametric or
+// nonparametric bootstrap, by the z-score method, or none.  Same option keys, messages where cheap, same table.
+// null.method = permutations (Mica.cpp:84-118) is not built: it is a sequential early-stopping shuffle test per pair
+// whose result depends on an unseeded generator.
+int mica_main(Inputs& in, const char* argv0) {
+  const Params& P = in.app.params;
+  const bool with_model = get_bool(P, "use_model", false);
+  prepare(in, argv0, nullptr, nullptr, with_model);
+  display_result("Number of sequences", in.aln.names.size());
+  display_result("Number of sites", in.cols.size());
+  display_message(std::string("Model of sequence evolution............: ") + (with_model ? "yes" : "no"));
+  const int64_t S = (int64_t)in.cols.size();
+  if (S < 2) throw Error("at least two sites are needed");
+  uint64_t seed = in.app.seed;
+  if (!in.app.seed_given) seed = ((uint64_t)std::random_device{}() << 32) ^ std::random_device{}();
+  cmb_ctx* ctx = nullptr;
+  chk(cmb_ctx_create(-1, nullptr, &ctx));
+  chk(cmb_set_tree(ctx, (int32_t)in.tree.parent.size(), in.tree.parent.data(), in.tree.brlen.data()));
+  std::vector<double> norms;
+  if (with_model) { // Mica.cpp:303-339: likelihood, then the mapping (Uniformization, total counts) for the norms
+    chk(cmb_set_model(ctx, in.model.A, in.model.Q.data(), in.model.pi.data(), (int32_t)in.rdist.rates.size(),
+                      in.rdist.rates.data(), in.rdist.probs.data(), CMB_COUNT_UNIFORMIZATION, nullptr));
+  } else { // the library wants a model before it takes an alignment; a uniform one, never used
+    const int A = (int)in.alpha.states.size();
+    std::vector<double> Q((size_t)A * A, 1. / (A - 1)), pi(A, 1. / A);
+    for (int x = 0; x < A; x++) Q[(size_t)x * A + x] = -1.;
+    const double one = 1.;
+    chk(cmb_set_model(ctx, A, Q.data(), pi.data(), 1, &one, &one, CMB_COUNT_NAIVE, nullptr));
+  }
+  chk(cmb_set_alignment(ctx, S, in.codes.data(), (int32_t)in.code_mask.size(), in.code_mask.data()));
+  if (with_model) {
+    norms.resize(S);
+    chk(cmb_map(ctx, nullptr, norms.data(), nullptr, nullptr, nullptr));
+  }
+  const std::string path = get_path(P, "output.file", "none");
+  if (path == "none") throw Error("output.file is not set");
+  display_result("Output file", path);
+  display_message("Computing average MIs..................: ");
+  std::vector<double> entropy(S), average(S);
+  chk(cmb_mica_sites(ctx, entropy.data(), average.data()));
+  double full_average = 0.;
+  for (double a : average) full_average += a;
+  full_average /= (double)S; // VectorTools::mean
+  const int64_t n_pairs = S * (S - 1) / 2;
+  std::vector<int32_t> I(n_pairs), J(n_pairs), nsim(n_pairs, 0);
+  std::vector<double> mi(n_pairs), hj(n_pairs), hm(n_pairs), nm(n_pairs), pv(n_pairs);
+  int64_t rows = 0;
+  const int key = with_model ? CMB_MICA_KEY_NMIN : CMB_MICA_KEY_HMIN;
+
+  // null distribution (Mica.cpp:369-628)
+  const std::string method = get_string(P, "null.method", "none");
+  display_result("Null distribution", method);
+  bool compute_p = false;
+  if (method != "none") {
+    if (method == "z-score") compute_p = true;
+    else if (method == "permutations")
+      throw Error("null.method=permutations is not available in this build (nonparametric-bootstrap, parametric-bootstrap, z-score, none)");
+    else compute_p = get_bool(P, "null.compute_pvalues", true);
+    int K = 0;
+    double kmax = 0.;
+    if (compute_p) {
+      K = (int)get_int(P, "null.nb_rate_classes", 10);
+      display_result("Number of sub-distributions", K);
+      if (K < 1) throw Error("Domain: number of classes must be > 0"); // Domain.cpp:49
+      const std::vector<double>& v = with_model ? norms : entropy;
+      for (double x : v) kmax = x > kmax ? x : kmax;
+    }
+    const std::string simpath = get_path(P, "null.output.file", "none");
+    const bool to_file = simpath != "none" && !simpath.empty();
+    const int rep_cpu = (int)get_int(P, "null.nb_rep_CPU", 10), rep_ram = (int)get_int(P, "null.nb_rep_RAM", 100);
+    if (method == "nonparametric-bootstrap") { // :401-468: pairs of sites resampled with replacement
+      display_message("Computing null distribution............: ");
+      const int64_t n = (int64_t)rep_cpu * rep_ram;
+      std::mt19937_64 gen(seed);
+      std::vector<int32_t> a(n), b(n);
+      for (int r = 0; r < rep_cpu; r++) { // sampleSites twice per outer replicate
+        for (int j = 0; j < rep_ram; j++) a[(size_t)r * rep_ram + j] = (int32_t)(gen() % (uint64_t)S);
+        for (int j = 0; j < rep_ram; j++) b[(size_t)r * rep_ram + j] = (int32_t)(gen() % (uint64_t)S);
+      }
+      std::vector<double> smi(n), shj(n), skey(n);
+      chk(cmb_mica_pair_list(ctx, n, a.data(), b.data(), smi.data(), shj.data()));
+      std::vector<double> shm(n), snm(n);
+      for (int64_t r = 0; r < n; r++) {
+        shm[r] = std::min(entropy[a[r]], entropy[b[r]]);
+        if (with_model) snm[r] = std::min(norms[a[r]], norms[b[r]]);
+        skey[r] = with_model ? snm[r] : shm[r];
+      }
+      if (to_file) {
+        display_result("Null output file", simpath);
+        std::ofstream so(simpath);
+        so << "MI\tHjoint\tHmin" << (with_model ? "\tNmin" : "") << std::endl;
+        for (int64_t r = 0; r < n; r++) {
+          so << smi[r] << "\t" << shj[r] << "\t" << shm[r];
+          if (with_model) so << "\t" << snm[r];
+          so << std::endl;
+        }
+      }
+      if (compute_p) chk(cmb_null_load(ctx, smi.data(), skey.data(), n, K, kmax));
+    } else if (method == "parametric-bootstrap") { // :470-545
+      if (!with_model) throw Error("You need to specify a model of sequence evolution in order to use a parametric bootstrap approach!");
+      const bool continuous_sim = get_bool(P, "simulations.continuous", false);
+      display_result("Rate distribution for simulations", continuous_sim ? "continuous" : "discrete");
+      if (continuous_sim) {
+        if (in.rdist.cont_kind == 0) throw Error("simulations.continuous=yes is available for Constant, Gamma and Invariant(dist=Gamma) rate distributions");
+        chk(cmb_set_continuous_rates(ctx, in.rdist.cont_kind, in.rdist.alpha, in.rdist.p_inv));
+      }
+      display_message("Computing null distribution............: ");
+      const int64_t n = (int64_t)rep_cpu * rep_ram;
+      std::vector<double> raw(to_file ? (size_t)n * 3 : 0);
+      chk(cmb_mica_null_parametric(ctx, seed, rep_cpu, rep_ram, get_bool(P, "simulations.weighted_classes", false) ? 1 : 0,
+                                   compute_p ? K : 0, kmax, to_file ? raw.data() : nullptr));
+      if (to_file) {
+        display_result("Null output file", simpath);
+        std::ofstream so(simpath);
+        so << "MI\tHjoint\tHmin\tNmin" << std::endl;
+        for (int64_t r = 0; r < n; r++) { // upstream indexes the OBSERVED entropies by (replicate, site in replicate), Mica.cpp:526
+          const int64_t i = r / rep_ram, j = r % rep_ram;
+          const double h = (i < S && j < S) ? std::min(entropy[i], entropy[j]) : std::nan("");
+          so << raw[r * 3] << "\t" << raw[r * 3 + 1] << "\t" << h << "\t" << raw[r * 3 + 2] << std::endl;
+        }
+      }
+    } else if (method == "z-score") { // :546-606: the distribution of all the observed pairs, corrected or not
+      const std::string zs = get_string(P, "null.method_zscore.stat", "MIp");
+      display_result("Compute p-value for", zs);
+      if (zs != "MIp" && zs != "MIc" && zs != "MI") throw Error("Unkown statistic, should be 'MI', 'MIp' or 'MIc'.");
+      display_message("Computing total distribution...........: ");
+      chk(cmb_mica_pairs(ctx, key, 0, n_pairs, I.data(), J.data(), mi.data(), hj.data(), hm.data(), nm.data(), nullptr, nullptr, &rows));
+      std::vector<double> st(n_pairs), kk(n_pairs);
+      for (int64_t r = 0; r < n_pairs; r++) {
+        const double apc = average[I[r]] * average[J[r]] / full_average, rcw = average[I[r]] * average[J[r]] / 2.;
+        st[r] = zs == "MIp" ? mi[r] - apc : zs == "MIc" ? mi[r] / rcw : mi[r];
+        kk[r] = with_model ? nm[r] : hm[r];
+      }
+      chk(cmb_null_load(ctx, st.data(), kk.data(), n_pairs, K, kmax));
+    } else throw Error("Unvalid null distribution method specified: " + method);
+  }
+
+  // the table (Mica.cpp:630-689)
+  display_message("Computing all MI scores................: ");
+  chk(cmb_mica_pairs(ctx, key, compute_p ? 1 : 0, n_pairs, I.data(), J.data(), mi.data(), hj.data(), hm.data(), nm.data(),
+                     compute_p ? pv.data() : nullptr, compute_p ? nsim.data() : nullptr, &rows));
+  {
+    std::ofstream out(path);
+    std::string header = "Group\tMI\tAPC\tRCW\tHjoint\tHmin";
+    if (with_model) header += "\tNmin";
+    if (compute_p) header += "\tBs.p.value\tBs.nb";
+    header += "\n";
+    out.write(header.data(), (std::streamsize)header.size());
+    write_rows_parallel(out, rows, 200, [&](int64_t r, char* p) {
+      const double apc = average[I[r]] * average[J[r]] / full_average, rcw = average[I[r]] * average[J[r]] / 2.;
+      char* q = p;
+      q += snprintf(q, 40, "[%d;%d]\t", in.cols[I[r]] + 1, in.cols[J[r]] + 1);
+      q += fmt_g(q, mi[r]); *q++ = '\t';
+      q += fmt_g(q, apc); *q++ = '\t';
+      q += fmt_g(q, rcw); *q++ = '\t';
+      q += fmt_g(q, hj[r]); *q++ = '\t';
+      q += fmt_g(q, hm[r]);
+      if (with_model) { *q++ = '\t'; q += fmt_g(q, nm[r]); }
+      if (compute_p) {
+        if (std::isnan(pv[r])) q += snprintf(q, 8, "\tNA\t0");
+        else { *q++ = '\t'; q += fmt_g(q, pv[r]); q += snprintf(q, 16, "\t%d", nsim[r]); }
+      }
+      *q++ = '\n';
+      return (int)(q - p);
+    });
+  }
+  chk(cmb_ctx_destroy(ctx));
+  display_message("\nBye bye ;-)");
+  return 0;
+}
+
 } // namespace
 
 int main(int argc, char** argv) {
@@ -454,6 +645,11 @@ int main(int argc, char** argv) {
     bool dry = false;
     for (int i = 1; i < argc; i++) dry |= std::string(argv[i]) == "--dry-run";
     const Params& P = in.app.params;
+    { // the same executable serves `mica` (CoMap/Mica.cpp) when it is invoked under that name or with comap_b200.program=mica
+      std::string prog = argv[0];
+      prog = prog.substr(prog.find_last_of('/') == std::string::npos ? 0 : prog.find_last_of('/') + 1);
+      if (!dry && (prog.rfind("mica", 0) == 0 || get_string(P, "comap_b200.program", "comap") == "mica")) return mica_main(in, argv[0]);
+    }
     prepare(in, argv[0]);
     if (dry) {
       dry_run_dump(in);

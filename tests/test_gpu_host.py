@@ -417,6 +417,55 @@ def test_simple_examples_run_with_their_own_option_files(myo):
     assert tl[0] == "Name\tId" and len([x for x in tl[1:] if x]) == c["codes"].shape[0]
 
 
+def test_mica_command_line(myo):
+    """mica param=... (CoMap/Mica.cpp): the table with a model (norm-conditioned parametric bootstrap) equals the C ABI
+    on the inputs the binary used; the z-score and nonparametric-bootstrap methods without a model run and fill their
+    columns; APC / RCW are the products of the average MIs (Mica.cpp:661-662)."""
+    from comap_b200 import api
+    tmp, _ = myo
+    mica = os.path.join(os.path.dirname(BIN), "mica_b200")
+    common = ["alphabet=Protein", "input.sequence.file=Myoglobin.aln.sel.mase", "input.sequence.format=Mase",
+              "input.sequence.sites_to_use=nogap", "input.remove_const=yes"]
+    model = ["use_model=yes", "input.tree.file=Myo.dnd", "model=JTT92", "rate_distribution=Gamma(n=4, alpha=0.985435)"]
+    p = subprocess.run([mica] + common + model + ["output.file=mica.txt", "null.method=parametric-bootstrap", "null.nb_rep_CPU=4",
+                                                  "null.nb_rep_RAM=200", "null.nb_rate_classes=3", "null.output.file=mica.null.txt",
+                                                  "--seed=9"], cwd=tmp, capture_output=True, text=True)
+    assert p.returncode == 0, p.stdout[-2000:]
+    hdr, rows = table(os.path.join(tmp, "mica.txt"))
+    assert hdr == ["Group", "MI", "APC", "RCW", "Hjoint", "Hmin", "Nmin", "Bs.p.value", "Bs.nb"] and len(rows) == 129 * 128 // 2
+    c = host_inputs(tmp)
+    ctx = api.Context(device=0)
+    ctx.set_tree(c["parent"], c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(c["codes"], c["code_mask"]); ctx.map()
+    h, avg = ctx.mica_sites()
+    ctx.mica_null_parametric(9, 4, 200, K=3)
+    q = ctx.mica_pairs("nmin", use_null=True)
+    co = c["coords"]
+    assert [r[0] for r in rows] == ["[%d;%d]" % (co[i], co[j]) for i, j in zip(q["i"], q["j"])]
+    assert [r[1] for r in rows] == [g(v) for v in q["mi"]] and [r[4] for r in rows] == [g(v) for v in q["hjoint"]]
+    assert [r[5] for r in rows] == [g(v) for v in q["hmin"]] and [r[6] for r in rows] == [g(v) for v in q["nmin"]]
+    assert [r[2] for r in rows] == [g(avg[i] * avg[j] / avg.mean()) for i, j in zip(q["i"], q["j"])]
+    assert [r[3] for r in rows] == [g(avg[i] * avg[j] / 2.0) for i, j in zip(q["i"], q["j"])]
+    assert [r[7] for r in rows] == ["NA" if np.isnan(v) else g(v) for v in q["pvalue"]] and [int(r[8]) for r in rows] == q["nsim"].tolist()
+    nh, nrows = table(os.path.join(tmp, "mica.null.txt"))
+    assert nh == ["MI", "Hjoint", "Hmin", "Nmin"] and len(nrows) == 800
+    ctx.close()
+    for method, extra in (("z-score", ["null.method_zscore.stat=MIp"]), ("nonparametric-bootstrap", ["null.nb_rep_CPU=5", "null.nb_rep_RAM=300"]),
+                          ("none", [])):
+        p = subprocess.run([mica] + common + ["output.file=m2.txt", "null.method=" + method, "null.nb_rate_classes=4", "--seed=3"] + extra,
+                           cwd=tmp, capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout[-2000:]
+        hdr, rows2 = table(os.path.join(tmp, "m2.txt"))
+        want = ["Group", "MI", "APC", "RCW", "Hjoint", "Hmin"] + ([] if method == "none" else ["Bs.p.value", "Bs.nb"])
+        assert hdr == want and len(rows2) == len(rows)
+        assert [r[1] for r in rows2] == [r[1] for r in rows]            # the statistic does not depend on the model
+        if method != "none":
+            pv = np.array([float(r[6]) if r[6] != "NA" else np.nan for r in rows2])
+            assert np.nanmin(pv) > 0 and np.nanmax(pv) <= 1 and (~np.isnan(pv)).mean() > 0.9
+    p = subprocess.run([mica] + common + ["output.file=m3.txt", "null.method=parametric-bootstrap"], cwd=tmp, capture_output=True, text=True)
+    assert p.returncode == 255 and "You need to specify a model" in p.stdout
+
+
 def test_error_exit_code_and_message(myo):
     tmp, _ = myo
     p = subprocess.run([BIN] + COMMON + ["analysis=pairwise", "statistic=Compensation"], cwd=tmp, capture_output=True, text=True)

@@ -707,15 +707,123 @@ def run_clustering(args):
         ctx.close()
 
 
+MICA = dict(sites=760, taxa=40, mean_brlen=0.12, tree_seed=11, aln_seed=1, perm_seed=3, max_perm=1000)
+
+
+def profile_metric(pattern, key):
+    """One metric of the newest committed ncu summary whose file name matches `pattern` (tools/ncu_summary.py format)."""
+    import glob
+    import re
+    paths = sorted(glob.glob(os.path.join(ROOT, "profiles", pattern)))
+    if not paths:
+        return None, None
+    m = re.search(r"^%s\s+(\S*)\s+([0-9.eE+,-]+)\s*$" % re.escape(key), open(paths[-1]).read(), re.M)
+    return (float(m.group(2).replace(",", "")) if m else None), os.path.relpath(paths[-1], ROOT)
+
+
+def run_mica(args):
+    """mica with null.method = permutations (examples/RNA/BacteriaSSU/options_perm.mica: 760 complete variable sites x
+    40 taxa, at most 1000 shuffles per pair): one step = alignment H2D -> entropies, dense MI / joint entropy, average
+    MI -> the other columns of the table -> the permutation test of all 288,420 pairs -> table D2H.  The dominant kernel
+    (k5_permutations) moves almost no memory -- private column copies in shared memory, 12 bytes out per pair -- and is
+    bound by instruction issue; its roofline is warp instructions per second against 4 per SM per clock."""
+    import torch
+    from comap_b200 import api
+    cfg = dict(MICA)
+    if args.sites:
+        cfg["sites"] = args.sites
+    if args.taxa:
+        cfg["taxa"] = args.taxa
+    torch.cuda.set_device(0)
+    stream = torch.cuda.Stream()
+    S, T, A = cfg["sites"], cfg["taxa"], 4
+    parent, brlen = syn.random_tree(T, cfg["tree_seed"], cfg["mean_brlen"])
+    Q, pi = syn.hky85(CFG["kappa"], CFG["pi"])
+    rates, probs = syn.gamma_rates(CFG["alpha"], CFG["classes"])
+    with torch.cuda.stream(stream):
+        ctx = api.Context(device=0, stream=stream.cuda_stream)
+        ctx.set_tree(parent, brlen); ctx.set_model(Q, pi, rates, probs)
+        codes, _ = ctx.simulate(cfg["aln_seed"], 0, S)
+        mask = syn.identity_code_mask(A)
+        out = {}
+
+        def step():
+            ctx.set_alignment(codes, mask)
+            out["sites"] = ctx.mica_sites()
+            out["pairs"] = ctx.mica_pairs("hmin")
+            out["perm"] = ctx.mica_permutations(cfg["perm_seed"], cfg["max_perm"])
+
+        W = max(3, args.warmup)
+        for _ in range(W):
+            step()
+        sampler = ClockSampler(0); sampler.start()
+        l0 = ctx.launch_count()
+        ms = _timed_gpu(torch, stream, step, args.steps)
+        launches = ctx.launch_count() - l0
+        clocks = sampler.stop()
+        ctx.profile_reset(); ctx.profile_enable(True)
+        for _ in range(args.steps):
+            step()
+        prof = {k: ctx.profile_get(k) for k in ("mica_pairs", "mica_perm")}
+        ctx.profile_enable(False)
+        pv, nb = out["perm"]
+        n_pairs = S * (S - 1) // 2
+        evaluations = int(nb.sum()) + n_pairs                       # shuffled MIs + the observed one of every pair
+        perm_ms = prof["mica_perm"][0] / args.steps
+        inst, src = profile_metric("r2*_k5_permutations.txt", "smsp__inst_executed.sum")
+        inst_pairs, _ = profile_metric("r2*_k5_permutations.txt", "launch__grid_size")
+        sm_mhz = clocks.get("sm_mhz") or 1900.0
+        peak = 148 * 4 * sm_mhz * 1e6 / 1e9                          # warp instructions per ns-second: 4 schedulers per SM
+        roof = dict(kernel="k5_permutations<4>", bound="issue", unit="Gwarp-inst/s", peak=peak,
+                    peak_source="148 SMs x 4 warp schedulers x %.0f MHz (median SM clock during the timed region)" % sm_mhz,
+                    ms_per_launch=perm_ms, evaluations_per_launch=evaluations, traffic=None,
+                    algorithmic_bytes_per_launch=n_pairs * (2 * T + 12))
+        if inst:
+            roof.update(achieved=inst / (perm_ms * 1e-3) / 1e9, frac=inst / (perm_ms * 1e-3) / 1e9 / peak,
+                        warp_instructions_per_launch=inst, profile=src)
+            dr = profile_dram_bytes("r2*_k5_permutations.txt")
+            if dr:
+                roof["traffic"] = dr["dram_bytes"]
+        else:
+            roof.update(achieved=None, frac=None, note="no committed ncu summary of k5_permutations yet")
+        line = dict(metric="mica_site_pairs_per_s_incl_permutation_test", value=n_pairs * args.steps / (ms * 1e-3), unit="pairs/s",
+                    n_gpus=1, steps=args.steps, warmup=W, ms_per_step=ms / args.steps, higher_is_better=True, scaling="strong",
+                    vs_baseline=None, dtype="f64", data="synthetic",
+                    config=dict(workload="examples/RNA/BacteriaSSU/options_perm.mica-shaped: synthetic %d-site x %d-taxon nucleotide "
+                                         "alignment, MI of all pairs + permutation test (at most %d shuffles per pair)"
+                                         % (S, T, cfg["max_perm"]), sites=S, taxa=T, max_permutations=cfg["max_perm"],
+                                pairs_per_step=n_pairs, mi_evaluations_per_step=evaluations, mean_shuffles_per_pair=float(nb.mean()),
+                                l2="the alignment (30 KB) lives in L1 / shared memory; outputs are written once: no flush needed"),
+                    clocks=clocks, gpu_launches=launches,
+                    e2e=dict(value=n_pairs * args.steps / (ms * 1e-3), unit="pairs/s", ms_per_step=ms / args.steps,
+                             h2d_bytes_per_step=int(T * S), d2h_bytes_per_step=int(n_pairs * (8 + 4 * 8 + 12) + 16 * S),
+                             note="this workload's step already runs through the host-buffer C ABI"),
+                    roofline=roof, kernel_ms_per_step={k: v[0] / args.steps for k, v in prof.items()})
+        if not args.no_cpu_baseline:     # the oracle's miTest on the first pairs of the same table, one thread
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import oracle_binding as O
+            sub = 90                                                 # 4005 pairs of the first 90 sites
+            t0 = time.perf_counter()
+            opv, onb, _ = O.mica_permutations(codes[:, :sub], A, mask, cfg["perm_seed"], cfg["max_perm"])
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = dict(value=len(opv) / dt, unit="pairs/s", cores=1, kind="port",
+                                        sample="the permutation test of the %d pairs among the first %d sites (%.1f s, %d MI "
+                                               "evaluations), CPU oracle restatement; MI of the pairs included, table output not"
+                                               % (len(opv), sub, dt, int(onb.sum()) + len(opv)))
+        print(json.dumps(line), flush=True)
+        ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="nucleotides", choices=["nucleotides", "proteins", "clustering"],
+    ap.add_argument("--workload", default="nucleotides", choices=["nucleotides", "proteins", "clustering", "mica"],
                     help="nucleotides = BASELINE.json configs[3] (the metric's configuration, default); proteins = "
-                         "configs[1]-shaped; clustering = configs[4] (both N = 1, ours only)")
+                         "configs[1]-shaped; clustering = configs[4]; mica = the permutation test of "
+                         "examples/RNA/BacteriaSSU/options_perm.mica (all three N = 1, ours only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     for k in ("sites", "taxa", "rep_cpu", "rep_ram"):
         ap.add_argument("--" + k.replace("_", "-"), type=int, default=None)
@@ -730,6 +838,8 @@ def main():
         run_proteins(args)
     elif args.workload == "clustering":
         run_clustering(args)
+    elif args.workload == "mica":
+        run_mica(args)
     else:
         run_ours(args, cfg)
 

@@ -31,7 +31,7 @@ SYMBOLS = [
     "cmb_null_load_dev", "cmb_null_get", "cmb_pairs", "cmb_pairs_resident", "cmb_pairs_fetch", "cmb_distance_matrix", "cmb_cluster",
     "cmb_groups", "cmb_cluster_null", "cmb_profile_enable", "cmb_profile_reset", "cmb_profile_get",
     "cmb_launch_count", "cmb_pairs_inter", "cmb_null_inter", "cmb_load_vectors", "cmb_candidates", "cmb_set_async", "cmb_set_mi_threshold", "cmb_set_map_mode", "cmb_ancestral_states",
-    "cmb_mica_sites", "cmb_mica_pairs", "cmb_mica_pair_list", "cmb_mica_null_parametric", "cmb_null_load",
+    "cmb_mica_sites", "cmb_mica_pairs", "cmb_mica_pair_list", "cmb_mica_permutations", "cmb_mica_null_parametric", "cmb_null_load",
     "cmb_comm_unique_id", "cmb_comm_init", "cmb_comm_init_all", "cmb_comm_set", "cmb_comm_destroy", "cmb_comm_rank",
     "cmb_comm_group_start", "cmb_comm_group_end", "cmb_null_intra_sharded", "cmb_set_continuous_rates",
 ]
@@ -224,6 +224,16 @@ class Context:
         self._chk(self.lib.cmb_mica_pair_list(self.h, C.c_int64(len(a)), a.ctypes.data_as(C.POINTER(C.c_int32)),
                                               b.ctypes.data_as(C.POINTER(C.c_int32)), _d(mi), _d(hj)))
         return mi, hj
+
+    def mica_permutations(self, seed, max_permutations=1000):
+        """null.method = permutations (miTest, Mica.cpp:92-118): Perm.p.value and Perm.nb of every pair, mica's order."""
+        n = self.S * (self.S - 1) // 2
+        pv = np.empty(n); nb = np.empty(n, np.int32)
+        k = C.c_int64(0)
+        self._chk(self.lib.cmb_mica_permutations(self.h, C.c_uint64(seed), int(max_permutations), C.c_int64(n), _d(pv),
+                                                 nb.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(k)))
+        assert k.value == n
+        return pv, nb
 
     def mica_null_parametric(self, seed, rep_cpu, rep_ram, K=10, nmax=-1.0, weighted_classes=False):
         """null.method = parametric-bootstrap (Mica.cpp:470-545); returns the [n][3] rows MI, Hjoint, Nmin."""

@@ -138,6 +138,32 @@ int cmb_mica_pair_list(cmb_ctx* ctx, int64_t n, const int32_t* site1, const int3
   CMB_CATCH
 }
 
+int cmb_mica_permutations(cmb_ctx* ctx, uint64_t seed, int32_t max_permutations, int64_t capacity, double* pvalue, int32_t* nperm,
+                          int64_t* n_rows) {
+  CMB_TRY
+  Context& c = ctx->c;
+  CMB_CUDA(cudaSetDevice(c.device));
+  if (!c.have_alignment) fail("cmb_mica_permutations: call cmb_set_alignment first");
+  if (c.S < 2) fail("mica: at least two sites are needed");
+  if (max_permutations < 1) fail("Permutation number should be greater than 0!"); // Mica.cpp:611-614
+  const int64_t n = c.S * (c.S - 1) / 2;
+  if (capacity < n) fail("cmb_mica_permutations: capacity %lld < %lld pairs", (long long)capacity, (long long)n);
+  const size_t d = al(sizeof(double) * (size_t)n), w = al(sizeof(int32_t) * (size_t)n);
+  c.scratch.reserve(d + w + 256);
+  double* pv = c.scratch.as<double>();
+  int32_t* np = (int32_t*)(c.scratch.as<unsigned char>() + d);
+  unsigned long long* next = (unsigned long long*)(c.scratch.as<unsigned char>() + d + w); // the kernel's work counter
+  c.prof_begin("mica_perm");
+  launch_mica_permutations(c.A, c.tree.n_leaves, c.S, c.S_pad, c.d_tips.as<uint8_t>(), c.d_code_mask.as<uint32_t>(), seed,
+                           max_permutations, next, pv, np, c.stream);
+  c.prof_end(2);
+  if (pvalue) CMB_CUDA(cudaMemcpyAsync(pvalue, pv, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+  if (nperm) CMB_CUDA(cudaMemcpyAsync(nperm, np, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, c.stream));
+  CMB_CUDA(cudaStreamSynchronize(c.stream));
+  if (n_rows) *n_rows = n;
+  CMB_CATCH
+}
+
 int cmb_mica_null_parametric(cmb_ctx* ctx, uint64_t seed, int32_t rep_cpu, int32_t rep_ram, int32_t weighted_classes, int32_t K,
                              double nmax, double* raw) {
   CMB_TRY

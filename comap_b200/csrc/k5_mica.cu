@@ -12,20 +12,91 @@
 // per column (coalesced over the 32 pairs of a warp, which share site i and walk consecutive sites j), A^2 updates
 // and A^2 logarithms per pair.  Not a tiled kernel: the work per pair is a histogram, not a dot product.
 #include "kernels.h"
+#include <algorithm>
+#include <cstdlib>
 #include "device_utils.cuh"
 
 namespace cmb {
 namespace {
 
+// a column of codes, strided in global memory (the tip matrix)
+struct Col {
+  const uint8_t* p;
+  size_t stride;
+  __device__ __forceinline__ uint32_t operator[](int t) const { return p[(size_t)t * stride]; }
+};
+// a lane's private column in shared memory (the permutation test): four characters per 32-bit word, words of one lane
+// `stride4` bytes apart, so a lane always stays in its own bank whatever character it touches
+struct LaneCol {
+  uint8_t* p;
+  int stride4;
+  __device__ __forceinline__ uint32_t operator[](int t) const { return p[(t >> 2) * stride4 + (t & 3)]; }
+  __device__ __forceinline__ uint8_t& at(int t) const { return p[(t >> 2) * stride4 + (t & 3)]; }
+};
+
+// MI and joint entropy from the joint table (orc_site_pair's order: rows, then columns).  cell(x, y) returns the count.
+// Loops stay rolled: one copy of the two logarithms and three divisions per kernel, not A^2 of them (unrolled over its
+// 16 cells the permutation kernel's loop body was 70 KB of SASS and ncu put 27 % of its stalls on instruction fetches).
+// p1 / p2 are register arrays for A <= 4, read and written through compile-time-indexed selects.
 template <int A>
-__device__ __forceinline__ void pair_stats(const uint8_t* __restrict__ c1, size_t s1, const uint8_t* __restrict__ c2, size_t s2,
-                                           int T, const uint32_t* __restrict__ cmask, double& mi, double& hj) {
+__device__ __forceinline__ double pick(const double (&v)[A], int k) {
+  if constexpr (A <= 4) {
+    double r = v[0];
+#pragma unroll
+    for (int i = 1; i < A; i++) r = k == i ? v[i] : r;
+    return r;
+  } else return v[k];
+}
+template <int A>
+__device__ __forceinline__ void put(double (&v)[A], int k, double val) {
+  if constexpr (A <= 4) {
+#pragma unroll
+    for (int i = 0; i < A; i++) v[i] = k == i ? val : v[i];
+  } else v[k] = val;
+}
+template <int A, class Cell>
+__device__ __forceinline__ void table_stats(Cell cell, int T, double& mi, double& hj) {
+  double p1[A], p2[A];
+#pragma unroll
+  for (int x = 0; x < A; x++) { p1[x] = 0.; p2[x] = 0.; }
+  double tot = 0.;
+  const double n = (double)T;
+#pragma unroll 1
+  for (int x = 0; x < A; x++)
+#pragma unroll 1
+    for (int y = 0; y < A; y++) {
+      const double pxy = cell(x, y) / n;
+      tot += pxy;
+      put<A>(p1, x, pick<A>(p1, x) + pxy);
+      put<A>(p2, y, pick<A>(p2, y) + pxy);
+    }
+#pragma unroll
+  for (int x = 0; x < (A <= 4 ? A : 0); x++) { p1[x] /= tot; p2[x] /= tot; }
+  if constexpr (A > 4) {
+#pragma unroll 1
+    for (int x = 0; x < A; x++) { p1[x] /= tot; p2[x] /= tot; }
+  }
+  double m = 0., h = 0.;
+#pragma unroll 1
+  for (int x = 0; x < A; x++)
+#pragma unroll 1
+    for (int y = 0; y < A; y++) {
+      const double pxy = cell(x, y) / n / tot;
+      if (pxy > 0.) { m += pxy * log(pxy / (pick<A>(p1, x) * pick<A>(p2, y))); h += pxy * log(pxy); }
+    }
+  mi = m; hj = -h;
+}
+
+// The joint table in local memory, filled in sequence order exactly as the oracle does: any alphabet, any character.
+template <int A, class C1, class C2>
+__device__ __noinline__ void pair_stats_generic(const C1 c1, const C2 c2, int T, const uint32_t* __restrict__ cmask, double& mi,
+                                                double& hj) {
   constexpr uint32_t full = A >= 32 ? 0xffffffffu : (1u << A) - 1u;
   double cnt[A * A];
-#pragma unroll
+#pragma unroll 1
   for (int k = 0; k < A * A; k++) cnt[k] = 0.;
   for (int t = 0; t < T; t++) {
-    const uint32_t m1 = __ldg(cmask + c1[(size_t)t * s1]) & full, m2 = __ldg(cmask + c2[(size_t)t * s2]) & full;
+    const uint32_t m1 = cmask[c1[t]] & full, m2 = cmask[c2[t]] & full;
     const int k1 = __popc(m1), k2 = __popc(m2);
     if (k1 == 1 && k2 == 1) cnt[(__ffs(m1) - 1) * A + __ffs(m2) - 1] += 1.;
     else if (k1 && k2) {
@@ -36,24 +107,41 @@ __device__ __forceinline__ void pair_stats(const uint8_t* __restrict__ c1, size_
             if ((m2 >> y) & 1u) cnt[x * A + y] += w;
     }
   }
-  double p1[A], p2[A];
+  table_stats<A>([&](int x, int y) { return cnt[x * A + y]; }, T, mi, hj);
+}
+
+// A <= 4 and no ambiguous character in either column (almost every pair of a real alignment, every pair of a simulated
+// one): the joint table never leaves the registers.  Counts sit in packed 16-bit fields, one 64-bit word per state of the
+// first column, so no register is indexed by data; integers convert exactly, so the result is bit for bit the generic
+// path's.  A pair that does hold an ambiguous character takes the generic path.
+template <int A, class C1, class C2>
+__device__ __forceinline__ void pair_stats(const C1 c1, const C2 c2, int T, const uint32_t* __restrict__ cmask, double& mi, double& hj) {
+  if constexpr (A <= 4) {
+    constexpr uint32_t full = (1u << A) - 1u;
+    unsigned long long w[A];
 #pragma unroll
-  for (int x = 0; x < A; x++) { p1[x] = 0.; p2[x] = 0.; }
-  double tot = 0.;
-  const double n = (double)T;
-  for (int x = 0; x < A; x++)
-    for (int y = 0; y < A; y++) {
-      const double pxy = cnt[x * A + y] / n;
-      tot += pxy; p1[x] += pxy; p2[y] += pxy;
+    for (int x = 0; x < A; x++) w[x] = 0ull;
+    bool ambiguous = false;
+    for (int t = 0; t < T; t++) {
+      const uint32_t m1 = cmask[c1[t]] & full, m2 = cmask[c2[t]] & full;
+      const int k1 = __popc(m1), k2 = __popc(m2);
+      if (k1 == 1 && k2 == 1) {
+        const unsigned long long inc = 1ull << (16 * (__ffs(m2) - 1));
+#pragma unroll
+        for (int x = 0; x < A; x++) w[x] += (m1 >> x) & 1u ? inc : 0ull;
+      } else if (k1 && k2) ambiguous = true;
     }
-  for (int x = 0; x < A; x++) { p1[x] /= tot; p2[x] /= tot; }
-  double m = 0., h = 0.;
-  for (int x = 0; x < A; x++)
-    for (int y = 0; y < A; y++) {
-      const double pxy = cnt[x * A + y] / n / tot;
-      if (pxy > 0.) { m += pxy * log(pxy / (p1[x] * p2[y])); h += pxy * log(pxy); }
+    if (!ambiguous) {
+      table_stats<A>([&](int x, int y) {
+        unsigned long long r = w[0];
+#pragma unroll
+        for (int i = 1; i < A; i++) r = x == i ? w[i] : r;
+        return (double)(unsigned)((r >> (16 * y)) & 0xffffull);
+      }, T, mi, hj);
+      return;
     }
-  mi = m; hj = -h;
+  }
+  pair_stats_generic<A, C1, C2>(c1, c2, T, cmask, mi, hj);
 }
 
 template <int A>
@@ -90,7 +178,7 @@ __global__ void __launch_bounds__(128) k5_pairs(int T, int64_t S, int64_t n_pad,
   const int64_t j = i + 1 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= S) return;
   double m, h;
-  pair_stats<A>(tips + i, (size_t)n_pad, tips + j, (size_t)n_pad, T, cmask, m, h);
+  pair_stats<A>(Col{tips + i, (size_t)n_pad}, Col{tips + j, (size_t)n_pad}, T, cmask, m, h);
   const int64_t idx = i * S - i * (i + 1) / 2 + (j - i - 1);
   mi[idx] = m;
   if (hj) hj[idx] = h;
@@ -106,9 +194,117 @@ __global__ void __launch_bounds__(128) k5_listed(int T, int64_t n, const uint8_t
   if (r >= n) return;
   const int64_t s1 = a ? a[r] : r, s2 = b ? b[r] : r;
   double m, h;
-  pair_stats<A>(t1 + s1, (size_t)np1, t2 + s2, (size_t)np2, T, cmask, m, h);
+  pair_stats<A>(Col{t1 + s1, (size_t)np1}, Col{t2 + s2, (size_t)np2}, T, cmask, m, h);
   mi[r] = m;
   if (hj) hj[r] = h;
+}
+
+// null.method = permutations (miTest, Mica.cpp:92-118): per pair, both columns are shuffled until 5 shuffled MIs reach the
+// observed one or max_perm shuffles were drawn; p = (count + 1) / (shuffles + 1); a pair with a constant column (unknown
+// characters ignored) gets p = 1 after 0 shuffles.
+//
+// Upstream shuffles its two copies in place, again and again, with an unseeded generator.  A uniformly random
+// permutation applied to any arrangement gives a uniformly random arrangement independent of the one it started from,
+// so shuffle q is drawn here from the ORIGINAL columns: same distribution of (count, shuffles), and the shuffles of
+// a pair no longer form a chain.  That is the whole design: pairs stop after anything between 5 and max_perm
+// shuffles, and with one pair per lane (the first version, 85 ms on the BacteriaSSU shape; 41 ms with a work queue)
+// the few lanes holding a 1000-shuffle pair outlive everything else -- ncu counted 7.9 active threads per warp.
+// One WARP per pair instead: lane l of trip k scores shuffle 32 k + l - 1 (lane 0 of the first trip scores the
+// observed columns), a ballot of `rep >= mi` and a population count find the shuffle at which upstream's loop would
+// have stopped, and at most 31 evaluations per pair are wasted.  Every branch but the ambiguous-character path is
+// warp-uniform.
+// Shuffle q of pair idx: inside-out Fisher-Yates (s[0] = c[0]; for k = 1 .. T-1: j = floor(w (k + 1) / 2^32),
+// s[k] = s[j], s[j] = c[k]), the words w taken in order from Philox4x32-10 blocks with counter (idx lo, idx hi, q, block)
+// and key = seed, column 1's T - 1 draws first -- restated word for word in the oracle (orc_mica_permutation_test).
+// The observed and the shuffled MIs come from the same call site of pair_stats, so equal joint tables give equal bits
+// and `rep >= mi` sees the exact ties a discrete statistic produces.
+template <int A, int MIN_CTAS>
+__global__ void __launch_bounds__(128, MIN_CTAS) k5_permutations(int T, int64_t S, int64_t n_pairs, int64_t n_pad,
+                                                       const uint8_t* __restrict__ tips, const uint32_t* __restrict__ cmask,
+                                                       uint64_t seed, int max_perm, unsigned long long* __restrict__ next,
+                                                       double* __restrict__ pvalue, int32_t* __restrict__ nperm) {
+  extern __shared__ __align__(16) unsigned char k5_smem[];
+  const int nt = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, T4 = (T + 3) >> 2;
+  uint32_t* s_mask = reinterpret_cast<uint32_t*>(k5_smem);                     // [256]
+  uint8_t* o1 = k5_smem + 1024 + (size_t)warp * 8 * T4;                        // the warp's pair: [2][4 T4]
+  uint8_t* o2 = o1 + 4 * T4;
+  uint8_t* priv = k5_smem + 1024 + (size_t)(nt >> 5) * 8 * T4;                 // [2][T4][nt] words
+  const LaneCol s1{priv + 4 * threadIdx.x, 4 * nt}, s2{priv + (size_t)4 * T4 * nt + 4 * threadIdx.x, 4 * nt};
+  for (int k = threadIdx.x; k < 256; k += nt) s_mask[k] = cmask[k];
+  __syncthreads();
+  constexpr uint32_t full = A >= 32 ? 0xffffffffu : (1u << A) - 1u;
+  constexpr unsigned ALL = 0xffffffffu;
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+  const int nd = 2 * (T - 1);
+  for (;;) {
+    __syncwarp();
+    unsigned long long got = 0;
+    if (lane == 0) got = atomicAdd(next, 1ull);
+    const int64_t idx = (int64_t)__shfl_sync(ALL, got, 0);
+    if (idx >= n_pairs) break;
+    // idx = i S - i (i + 1) / 2 + (j - i - 1): row i from the root of the quadratic, then one step either way
+    const double b = 2. * (double)S - 1.;
+    int64_t i = (int64_t)((b - sqrt(b * b - 8. * (double)idx)) * 0.5);
+    if (i < 0) i = 0;
+    if (i > S - 2) i = S - 2;
+    while (i > 0 && i * S - i * (i + 1) / 2 > idx) i--;
+    while (i < S - 2 && (i + 1) * S - (i + 1) * (i + 2) / 2 <= idx) i++;
+    const int64_t j = i + 1 + (idx - (i * S - i * (i + 1) / 2));
+    // SiteTools::isConstant(site, ignoreUnknown = true): the characters that are not fully unknown are all the same
+    uint32_t lo1 = 0xffffffffu, hi1 = 0u, lo2 = 0xffffffffu, hi2 = 0u;
+    for (int t = lane; t < T; t += 32) {
+      const uint32_t a = tips[(size_t)t * n_pad + i], c = tips[(size_t)t * n_pad + j];
+      o1[t] = (uint8_t)a; o2[t] = (uint8_t)c;
+      if ((s_mask[a] & full) != full) { lo1 = min(lo1, a); hi1 = max(hi1, a); }
+      if ((s_mask[c] & full) != full) { lo2 = min(lo2, c); hi2 = max(hi2, c); }
+    }
+    lo1 = __reduce_min_sync(ALL, lo1); hi1 = __reduce_max_sync(ALL, hi1);
+    lo2 = __reduce_min_sync(ALL, lo2); hi2 = __reduce_max_sync(ALL, hi2);
+    __syncwarp();
+    if (lo1 >= hi1 || lo2 >= hi2) {              // one character at most (none: lo = 2^32 - 1 > hi = 0)
+      if (lane == 0) { pvalue[idx] = 1.; nperm[idx] = 0; }
+      continue;
+    }
+    int count = 0, shuffles = max_perm;
+    double mi = 0.;
+    for (int base = -1; base < max_perm; base += 32) {
+      const int q = base + lane;
+      if (q < 0) {
+        for (int t = 0; t < T; t++) { s1.at(t) = o1[t]; s2.at(t) = o2[t]; }
+      } else {
+        s1.at(0) = o1[0]; s2.at(0) = o2[0];
+        int d = 0;
+        for (uint32_t blk = 0; d < nd; blk++) {
+          uint32_t c[4] = {(uint32_t)idx, (uint32_t)((uint64_t)idx >> 32), (uint32_t)q, blk};
+          philox4x32_10(c, k0, k1);
+#pragma unroll
+          for (int u = 0; u < 4; u++, d++)
+            if (d < nd) {
+              const bool first = d < T - 1;
+              const LaneCol& col = first ? s1 : s2;
+              const int k = first ? d + 1 : d - (T - 1) + 1;
+              const int p = (int)__umulhi(c[u], (uint32_t)(k + 1));
+              col.at(k) = col.at(p);
+              col.at(p) = first ? o1[k] : o2[k];
+            }
+        }
+      }
+      double m, h;
+      pair_stats<A>(s1, s2, T, s_mask, m, h);
+      if (base < 0) mi = __shfl_sync(ALL, m, 0);
+      const unsigned hits = __ballot_sync(ALL, q >= 0 && q < max_perm && m >= mi);
+      const int c = __popc(hits);
+      if (count + c >= 5) {                      // the shuffle that brought the count to 5
+        unsigned r = hits;
+        for (int k = count; k < 4; k++) r &= r - 1;
+        shuffles = base + (__ffs(r) - 1) + 1;
+        count = 5;
+        break;
+      }
+      count += c;
+    }
+    if (lane == 0) { pvalue[idx] = (double)(count + 1) / (double)(shuffles + 1); nperm[idx] = shuffles; }
+  }
 }
 
 // Mica.cpp:341-361: average MI of every site with all the others, j ascending
@@ -172,6 +368,35 @@ void launch_mica_listed(int A, int T, int64_t n, const uint8_t* t1, int64_t np1,
   if (A == 4) k5_listed<4><<<g, 128, 0, st>>>(T, n, t1, np1, t2, np2, a, b, cmask, mi, hj);
   else if (A == 20) k5_listed<20><<<g, 128, 0, st>>>(T, n, t1, np1, t2, np2, a, b, cmask, mi, hj);
   else fail("mica kernels are built for A = 4 and A = 20 (got %d)", A);
+  CMB_CUDA(cudaGetLastError());
+}
+void launch_mica_permutations(int A, int T, int64_t S, int64_t n_pad, const uint8_t* tips, const uint32_t* cmask, uint64_t seed,
+                              int max_perm, unsigned long long* next, double* pvalue, int32_t* nperm, cudaStream_t st) {
+  if (S < 2) return;
+  if (T < 2) fail("mica permutations: at least two sequences are needed");
+  if (T > 65535) fail("mica: %d sequences exceed the 16-bit cells of the joint table", T);
+  const int64_t n_pairs = S * (S - 1) / 2;
+  const size_t T4 = ((size_t)T + 3) / 4;
+  auto bytes = [&](int nt) { return 1024 + (size_t)(nt / 32) * 8 * T4 + 8 * T4 * nt; };  // masks | warps' pairs | private copies
+  int nt = 128;
+  while (nt > 32 && bytes(nt) > 64 * 1024) nt >>= 1;
+  const size_t smem = bytes(nt);
+  if (smem > 200 * 1024) fail("mica permutations: %d sequences exceed the shared memory of a one-warp CTA", T);
+  // registers per thread: 64 (8 CTAs of 128 per SM, a few spilled words), 80 (6) or 96 (5); CMB_K5_CTAS picks one for A/B runs
+  static const int want = [] { const char* e = getenv("CMB_K5_CTAS"); return e ? atoi(e) : 8; }();
+  auto kernel = A == 4 ? (want <= 5 ? k5_permutations<4, 5> : want <= 6 ? k5_permutations<4, 6> : k5_permutations<4, 8>)
+                : A == 20 ? k5_permutations<20, 5> : nullptr;
+  if (!kernel) fail("mica kernels are built for A = 4 and A = 20 (got %d)", A);
+  CMB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int dev = 0, sms = 0, per_sm = 0;
+  CMB_CUDA(cudaGetDevice(&dev));
+  CMB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  CMB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem));
+  if (per_sm < 1) fail("mica permutations: the kernel does not fit an SM (T = %d)", T);
+  // persistent warps, one wave; pairs are handed out by a counter: no more warps than pairs
+  const int64_t ctas = std::min<int64_t>((int64_t)sms * per_sm, (n_pairs + nt / 32 - 1) / (nt / 32));
+  CMB_CUDA(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
+  kernel<<<(unsigned)ctas, nt, smem, st>>>(T, S, n_pairs, n_pad, tips, cmask, seed, max_perm, next, pvalue, nperm);
   CMB_CUDA(cudaGetLastError());
 }
 void launch_mica_average(int64_t S, const double* mi, double* avg, cudaStream_t st) {

@@ -242,6 +242,8 @@ void dry_run_dump(const Inputs& in) {
   for (double b : in.tree.brlen) std::cout << ' ' << b;
   std::cout << "\nDRYRUN leaves";
   for (int l : in.tree.leaves) std::cout << ' ' << in.tree.name[l];
+  std::cout << "\nDRYRUN sequences";          // the alignment's own order (mica without a model keeps it)
+  for (auto& n : in.aln.names) std::cout << ' ' << n;
   std::cout << "\nDRYRUN A " << in.model.A << "\nDRYRUN Q";
   for (double q : in.model.Q) std::cout << ' ' << q;
   std::cout << "\nDRYRUN pi";
@@ -456,8 +458,8 @@ Mapped map_data_set(Inputs& in, const Params& P, const std::string& suffix) {
 // mica param=FILE key=value ...   (CoMap/Mica.cpp:132-704): mutual information between alignment columns, optionally
 // conditioned on the norms of a substitution mapping (use_model = yes), with a null distribution by parametric or
 // nonparametric bootstrap, by the z-score method, or none.  Same option keys, messages where cheap, same table.
-// null.method = permutations (Mica.cpp:84-118) is not built: it is a sequential early-stopping shuffle test per pair
-// whose result depends on an unseeded generator.
+// null.method = permutations (miTest, Mica.cpp:92-118) runs on the device too (cmb_mica_permutations); upstream's shuffles
+// come from an unseeded generator, here they are a function of --seed.
 int mica_main(Inputs& in, const char* argv0) {
   const Params& P = in.app.params;
   const bool with_model = get_bool(P, "use_model", false);
@@ -507,10 +509,10 @@ int mica_main(Inputs& in, const char* argv0) {
   const std::string method = get_string(P, "null.method", "none");
   display_result("Null distribution", method);
   bool compute_p = false;
+  int64_t max_perm = 0;
   if (method != "none") {
     if (method == "z-score") compute_p = true;
-    else if (method == "permutations")
-      throw Error("null.method=permutations is not available in this build (nonparametric-bootstrap, parametric-bootstrap, z-score, none)");
+    else if (method == "permutations") compute_p = false;
     else compute_p = get_bool(P, "null.compute_pvalues", true);
     int K = 0;
     double kmax = 0.;
@@ -588,6 +590,10 @@ int mica_main(Inputs& in, const char* argv0) {
         kk[r] = with_model ? nm[r] : hm[r];
       }
       chk(cmb_null_load(ctx, st.data(), kk.data(), n_pairs, K, kmax));
+    } else if (method == "permutations") { // :608-619, miTest :92-118
+      max_perm = get_int(P, "null.max_number_of_permutations", 1000);
+      if (max_perm <= 0) throw Error("Permutation number should be greater than 0!");
+      display_result("Maximum number of permutations", max_perm);
     } else throw Error("Unvalid null distribution method specified: " + method);
   }
 
@@ -595,14 +601,21 @@ int mica_main(Inputs& in, const char* argv0) {
   display_message("Computing all MI scores................: ");
   chk(cmb_mica_pairs(ctx, key, compute_p ? 1 : 0, n_pairs, I.data(), J.data(), mi.data(), hj.data(), hm.data(), nm.data(),
                      compute_p ? pv.data() : nullptr, compute_p ? nsim.data() : nullptr, &rows));
+  std::vector<double> perm_p;
+  std::vector<int32_t> perm_nb;
+  if (max_perm > 0) {
+    perm_p.resize(n_pairs); perm_nb.resize(n_pairs);
+    chk(cmb_mica_permutations(ctx, seed, (int32_t)std::min<int64_t>(max_perm, INT32_MAX), n_pairs, perm_p.data(), perm_nb.data(), nullptr));
+  }
   {
     std::ofstream out(path);
     std::string header = "Group\tMI\tAPC\tRCW\tHjoint\tHmin";
     if (with_model) header += "\tNmin";
+    if (max_perm > 0) header += "\tPerm.p.value\tPerm.nb";
     if (compute_p) header += "\tBs.p.value\tBs.nb";
     header += "\n";
     out.write(header.data(), (std::streamsize)header.size());
-    write_rows_parallel(out, rows, 200, [&](int64_t r, char* p) {
+    write_rows_parallel(out, rows, 256, [&](int64_t r, char* p) {
       const double apc = average[I[r]] * average[J[r]] / full_average, rcw = average[I[r]] * average[J[r]] / 2.;
       char* q = p;
       q += snprintf(q, 40, "[%d;%d]\t", in.cols[I[r]] + 1, in.cols[J[r]] + 1);
@@ -612,6 +625,7 @@ int mica_main(Inputs& in, const char* argv0) {
       q += fmt_g(q, hj[r]); *q++ = '\t';
       q += fmt_g(q, hm[r]);
       if (with_model) { *q++ = '\t'; q += fmt_g(q, nm[r]); }
+      if (max_perm > 0) { *q++ = '\t'; q += fmt_g(q, perm_p[r]); q += snprintf(q, 16, "\t%d", perm_nb[r]); }
       if (compute_p) {
         if (std::isnan(pv[r])) q += snprintf(q, 8, "\tNA\t0");
         else { *q++ = '\t'; q += fmt_g(q, pv[r]); q += snprintf(q, 16, "\t%d", nsim[r]); }

@@ -317,6 +317,12 @@ int cmb_mica_pairs(cmb_ctx* ctx, int32_t key, int32_t use_null, int64_t capacity
                    double* hjoint, double* hmin, double* nmin, double* pvalue, int32_t* nsim, int64_t* n_rows);
 /* MI / joint entropy of listed site pairs of the alignment: the nonparametric bootstrap's resampled pairs (Mica.cpp:423-431). */
 int cmb_mica_pair_list(cmb_ctx* ctx, int64_t n, const int32_t* site1, const int32_t* site2, double* mi, double* hjoint);
+/* null.method = permutations (miTest, Mica.cpp:92-118; table columns Perm.p.value / Perm.nb, :666-667): for every pair, in
+ * the order of cmb_mica_pairs, both columns are shuffled until 5 shuffled MIs reach the observed one or max_permutations
+ * were drawn; pvalue = (count + 1) / (shuffles + 1), nperm = shuffles; 1 and 0 when a column is constant.  Upstream's
+ * generator is unseeded: the shuffles here are a function of (seed, pair, shuffle number) only. */
+int cmb_mica_permutations(cmb_ctx* ctx, uint64_t seed, int32_t max_permutations, int64_t capacity, double* pvalue, int32_t* nperm,
+                          int64_t* n_rows);
 /* null.method = parametric-bootstrap (Mica.cpp:470-545): per outer replicate two simulated alignments of rep_ram sites,
  * mapped for their norms (computeSubstitutionVectors), MI of site j with site j, binned by min norm over [0, nmax)
  * (nmax < 0: the mapped alignment's largest norm).  raw: nullable [rep_cpu * rep_ram][3] = MI, Hjoint, Nmin. */

@@ -1413,3 +1413,75 @@ void orc_mica_sites(int64_t S, int T, const uint8_t* codes, int A, int n_codes, 
   }
   free(cols);
 }
+
+/* null.method = permutations: miTest (Mica.cpp:92-118).  mi = MI of the two columns; unless one of them is constant
+ * (SiteTools::isConstant(site, true): unknown characters ignored [Bio++ / from memory]), both columns are shuffled
+ * and re-scored while count < 5 and i < max_perm, count = #{rep >= mi}; pvalue = (count + 1) / (i + 1),
+ * nbPermutations = i.  Upstream shuffles its two copies in place, over and over, with Bio++'s global, unseeded
+ * generator.  A uniformly random permutation of any arrangement is a uniformly random arrangement independent of the
+ * one it started from, so here -- as on the device -- shuffle i is drawn from the ORIGINAL columns: the same
+ * distribution of (count, i), and shuffles that do not depend on each other.  The shuffle used on both sides:
+ * inside-out Fisher-Yates (s[0] = c[0]; for k = 1 .. T-1: j = floor(w (k + 1) / 2^32), s[k] = s[j], s[j] = c[k]), the
+ * words w taken in order from Philox4x32-10 blocks with counter (pair lo, pair hi, i, block) and key = seed,
+ * column 1's T - 1 draws first.  closest (nullable) = the smallest |rep - mi| met, so a test can tell a count that
+ * hinges on a rounding tie. */
+void orc_mica_permutation_test(int T, const uint8_t* c1, const uint8_t* c2, int A, int n_codes, const uint32_t* code_mask,
+                               uint64_t seed, uint64_t pair, int max_perm, double* mi_out, double* pvalue, int* nperm,
+                               double* closest) {
+  uint32_t full = (A >= 32) ? 0xffffffffu : ((1u << A) - 1u);
+  int const1 = 1, const2 = 1, f1 = -1, f2 = -1;
+  for (int t = 0; t < T; t++) {
+    uint32_t m1 = c1[t] < n_codes ? code_mask[c1[t]] & full : 0, m2 = c2[t] < n_codes ? code_mask[c2[t]] & full : 0;
+    if (m1 != full) { if (f1 < 0) f1 = c1[t]; else if (c1[t] != f1) const1 = 0; }
+    if (m2 != full) { if (f2 < 0) f2 = c2[t]; else if (c2[t] != f2) const2 = 0; }
+  }
+  double mi;
+  orc_site_pair(T, c1, c2, A, n_codes, code_mask, &mi, NULL);
+  if (mi_out) *mi_out = mi;
+  if (closest) *closest = INFINITY;
+  if (const1 || const2) { *pvalue = 1.; *nperm = 0; return; }
+  uint8_t* s1 = malloc(2 * (size_t)T);
+  uint8_t* s2 = s1 + T;
+  int count = 0, i;
+  const int nd = 2 * (T - 1);
+  for (i = 0; count < 5 && i < max_perm; i++) {
+    int d = 0;
+    s1[0] = c1[0]; s2[0] = c2[0];
+    for (uint32_t blk = 0; d < nd; blk++) {
+      uint32_t c[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)i, blk};
+      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+      for (int u = 0; u < 4 && d < nd; u++, d++) {
+        const int first = d < T - 1;
+        uint8_t* col = first ? s1 : s2;
+        const uint8_t* src = first ? c1 : c2;
+        int k = first ? d + 1 : d - (T - 1) + 1;
+        int p = (int)(((uint64_t)c[u] * (uint64_t)(k + 1)) >> 32);
+        col[k] = col[p]; col[p] = src[k];
+      }
+    }
+    double rep;
+    orc_site_pair(T, s1, s2, A, n_codes, code_mask, &rep, NULL);
+    if (rep >= mi) count++;
+    if (closest && fabs(rep - mi) < *closest) *closest = fabs(rep - mi);
+  }
+  free(s1);
+  *pvalue = (double)(count + 1) / (double)(i + 1);
+  *nperm = i;
+}
+
+/* every pair i < j of an alignment, mica's order; codes: [T][S] tip-major */
+void orc_mica_permutations(int64_t S, int T, const uint8_t* codes, int A, int n_codes, const uint32_t* code_mask, uint64_t seed,
+                           int max_perm, double* pvalue, int32_t* nperm, double* closest) {
+  uint8_t* cols = malloc((size_t)S * T);
+  for (int64_t s = 0; s < S; s++)
+    for (int t = 0; t < T; t++) cols[s * T + t] = codes[(size_t)t * S + s];
+  int64_t idx = 0;
+  for (int64_t i = 0; i + 1 < S; i++)
+    for (int64_t j = i + 1; j < S; j++, idx++) {
+      int np;
+      orc_mica_permutation_test(T, cols + i * T, cols + j * T, A, n_codes, code_mask, seed, (uint64_t)idx, max_perm, NULL,
+                                pvalue + idx, &np, closest ? closest + idx : NULL);
+      nperm[idx] = np;
+    }
+  free(cols);
+}

@@ -165,4 +165,11 @@ void orc_site_pair(int T, const uint8_t* c1, const uint8_t* c2, int A, int n_cod
 void orc_mica_sites(int64_t S, int T, const uint8_t* codes, int A, int n_codes, const uint32_t* code_mask,
                     double* entropy, double* average_mi);
 
+/* null.method = permutations: miTest (Mica.cpp:92-118) of one pair / of every pair i < j in mica's order */
+void orc_mica_permutation_test(int T, const uint8_t* c1, const uint8_t* c2, int A, int n_codes, const uint32_t* code_mask,
+                               uint64_t seed, uint64_t pair, int max_perm, double* mi_out, double* pvalue, int* nperm,
+                               double* closest);
+void orc_mica_permutations(int64_t S, int T, const uint8_t* codes, int A, int n_codes, const uint32_t* code_mask, uint64_t seed,
+                           int max_perm, double* pvalue, int32_t* nperm, double* closest);
+
 #endif

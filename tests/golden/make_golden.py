@@ -17,6 +17,15 @@ def load_vec(p):
     M = np.array([[float(x) for x in r[1:]] for r in rows])
     return np.array([int(h[4:]) for h in hdr[2:]]), M[:, 0], M[:, 1:]
 
+def pack_bacteria():
+    """examples/RNA/BacteriaSSU: alignment, tree, comap's option file and mica's four option files, as shipped."""
+    r = REF + "/examples/RNA/BacteriaSSU/"
+    rd = lambda fn: np.frombuffer(open(r + fn, "rb").read(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(HERE, "bacteria_ssu.npz"), phy=rd("Bacteria_SSU.40.phy"), dnd=rd("Bacteria_SSU.ML.dnd"),
+                        options=rd("options.comap"), mica_pbs=rd("options_pbs.mica"), mica_npbs=rd("options_npbs.mica"),
+                        mica_perm=rd("options_perm.mica"), mica_zscore=rd("options_zscore.mica"))
+
+
 def main():
     bm = REF + "/examples/Proteins/Benchmark/CoMap/"
     out = {}
@@ -41,11 +50,7 @@ def main():
                "ProteinMappingOnly"):
         out["simple_" + ex] = np.frombuffer(open(REF + "/examples/simple/" + ex + "/comap.bpp", "rb").read(), dtype=np.uint8)
     np.savez_compressed(os.path.join(HERE, "myoglobin.npz"), **out)
-    r = REF + "/examples/RNA/BacteriaSSU/"
-    np.savez_compressed(os.path.join(HERE, "bacteria_ssu.npz"),
-        phy=np.frombuffer(open(r + "Bacteria_SSU.40.phy", "rb").read(), dtype=np.uint8),
-        dnd=np.frombuffer(open(r + "Bacteria_SSU.ML.dnd", "rb").read(), dtype=np.uint8),
-        options=np.frombuffer(open(r + "options.comap", "rb").read(), dtype=np.uint8))
+    pack_bacteria()
     s = REF + "/examples/Data/Proteins/SRK/"
     np.savez_compressed(os.path.join(HERE, "srk.npz"),
         mase=np.frombuffer(open(s + "SRK.mase", "rb").read(), dtype=np.uint8),

@@ -137,6 +137,18 @@ def mica_sites(codes, A, code_mask):
     return h, a
 
 
+def mica_permutations(codes, A, code_mask, seed, max_perm):
+    """miTest of every pair (Mica.cpp:92-118) with the device's shuffle stream: p-value, number of shuffles, and the
+    smallest |shuffled MI - MI| met on the way; codes [T][S]."""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8); m = np.ascontiguousarray(code_mask, dtype=np.uint32)
+    T, S = codes.shape
+    n = S * (S - 1) // 2
+    pv = np.empty(n); nb = np.empty(n, np.int32); cl = np.empty(n)
+    lib().orc_mica_permutations(C.c_int64(S), T, _p(codes, C.c_uint8), A, len(m), _p(m, C.c_uint32), C.c_uint64(seed),
+                                int(max_perm), _d(pv), _p(nb, C.c_int32), _d(cl))
+    return pv, nb, cl
+
+
 def set_mi_threshold(t):
     lib().orc_set_mi_threshold(C.c_double(t))
 

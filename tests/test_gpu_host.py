@@ -466,6 +466,47 @@ def test_mica_command_line(myo):
     assert p.returncode == 255 and "You need to specify a model" in p.stdout
 
 
+def test_mica_examples_run_with_their_own_option_files(tmp_path):
+    """examples/RNA/BacteriaSSU/options_{perm,npbs,pbs,zscore}.mica as shipped (README.md there): 760 complete variable
+    sites x 40 taxa.  The permutation table is checked against the C ABI on the inputs the binary used."""
+    from comap_b200 import api, build as b
+    b.build_host()
+    tmp = str(tmp_path)
+    write_fixture(tmp, "bacteria_ssu")
+    mica = os.path.join(os.path.dirname(BIN), "mica_b200")
+    n = 760 * 759 // 2
+    p = subprocess.run([mica, "param=options_perm.mica", "--seed=21"], cwd=tmp, capture_output=True, text=True)
+    assert p.returncode == 0 and "Maximum number of permutations" in p.stdout, p.stdout[-2000:]
+    hdr, rows = table(os.path.join(tmp, "Bacteria_SSU.MI_perm.sged"))
+    assert hdr == ["Group", "MI", "APC", "RCW", "Hjoint", "Hmin", "Perm.p.value", "Perm.nb"] and len(rows) == n
+    _, o = dry_run(BIN, tmp, "param=options_perm.mica")
+    c = decode(o)
+    # without a model mica keeps the alignment's sequence order (the dry run lists the rows in the tree's): the
+    # statistics do not depend on it, the shuffles start from it
+    row = {name: k for k, name in enumerate(o["leaves"])}
+    c["codes"] = np.ascontiguousarray(c["codes"][[row[name] for name in o["sequences"]]])
+    ctx = api.Context(device=0)
+    ctx.set_tree(c["parent"].astype(np.int32), c["brlen"]); ctx.set_model(c["Q"], c["pi"], c["rates"], c["probs"])
+    ctx.set_alignment(c["codes"], c["code_mask"])
+    pv, nb = ctx.mica_permutations(21, 1000)
+    q = ctx.mica_pairs("hmin")
+    ctx.close()
+    assert [r[1] for r in rows] == [g(v) for v in q["mi"]]
+    assert [r[6] for r in rows] == [g(v) for v in pv] and [int(r[7]) for r in rows] == nb.tolist()
+    assert nb.max() == 1000 and np.median(nb) < 200           # most pairs stop early, coevolving stems do not
+    for opt, out, cols in (("options_npbs.mica", "Bacteria_SSU.MI_NPBS.sged", ["Bs.p.value", "Bs.nb"]),
+                           ("options_zscore.mica", "Bacteria_SSU.MI_zscore.sged", ["Bs.p.value", "Bs.nb"]),
+                           ("options_pbs.mica", "Bacteria_SSU.MI_PBS.sged", ["Nmin", "Bs.p.value", "Bs.nb"])):
+        p = subprocess.run([mica, "param=" + opt, "--seed=21"], cwd=tmp, capture_output=True, text=True)
+        assert p.returncode == 0, p.stdout[-2000:]
+        hdr, rows2 = table(os.path.join(tmp, out))
+        assert hdr == ["Group", "MI", "APC", "RCW", "Hjoint", "Hmin"] + cols and len(rows2) == n
+        assert [r[1] for r in rows2] == [r[1] for r in rows]
+        pcol = len(hdr) - 2
+        pv2 = np.array([float(r[pcol]) if r[pcol] != "NA" else np.nan for r in rows2])
+        assert np.nanmin(pv2) > 0 and np.nanmax(pv2) <= 1 and (~np.isnan(pv2)).mean() > 0.5
+
+
 def test_error_exit_code_and_message(myo):
     tmp, _ = myo
     p = subprocess.run([BIN] + COMMON + ["analysis=pairwise", "statistic=Compensation"], cwd=tmp, capture_output=True, text=True)

@@ -87,3 +87,50 @@ def test_parametric_bootstrap_null_and_pvalues(ctx):
     q = ctx.mica_pairs("hmin", use_null=True)
     g = ctx.null_get()
     assert g["bin_offsets"][-1] == np.sum(p["hmin"] < h.max()) and np.nanmin(q["pvalue"]) > 0
+
+
+@pytest.mark.parametrize("case", ["dna", "protein"])
+def test_permutation_test_vs_oracle(ctx, case):
+    """null.method = permutations (miTest, Mica.cpp:92-118): Perm.p.value / Perm.nb of every pair against the oracle's
+    own replay of the same shuffle stream.  The early stop hangs on `rep >= mi` between logarithm sums, so a pair whose
+    shuffles came within rounding of its MI may stop elsewhere on the host: those are counted and must be such ties."""
+    if case == "dna":
+        c = H.random_dna_case(26, 60, 11, mean_brlen=0.2, ambiguity=0.05)
+        c["codes"][:, 7] = 2; c["codes"][3, 7] = 4            # constant once the unknown character is ignored
+        c["codes"][:, 19] = 4                                 # nothing but unknown characters
+        max_perm = 300
+    else:
+        c = H.myoglobin_inputs()
+        max_perm = 60
+    A = len(c["pi"])
+    _setup(ctx, c)
+    pv, nb = ctx.mica_permutations(12345, max_perm)
+    opv, onb, closest = O.mica_permutations(c["codes"], A, c["code_mask"], 12345, max_perm)
+    S = c["codes"].shape[1]
+    ii, jj = np.triu_indices(S, 1)
+    assert len(pv) == len(ii) and nb.min() >= 0 and nb.max() <= max_perm and pv.min() > 0 and pv.max() <= 1
+    diff = (nb != onb) | (pv != opv)
+    mi = ctx.mica_pairs("hmin")["mi"]
+    assert np.all(closest[diff] <= 1e-12 * np.maximum(1.0, np.abs(mi[diff]))), "a count differs without a rounding tie"
+    assert diff.mean() < 0.02, "pairs that differ: %d of %d" % (diff.sum(), len(diff))
+    print("permutation test, %s: %d of %d pairs stop elsewhere than the oracle (rounding ties)" % (case, diff.sum(), len(diff)))
+    # the stopping rule: 5 shuffles reached the MI, or the budget ran out
+    stopped = nb < max_perm
+    live = nb > 0
+    assert np.all(pv[stopped & live] == 6.0 / (nb[stopped & live] + 1.0))
+    if case == "dna":
+        const = (ii == 7) | (jj == 7) | (ii == 19) | (jj == 19)
+        assert np.all(nb[const] == 0) and np.all(pv[const] == 1.0)
+    # same seed, same table; another seed, another stream
+    pv2, nb2 = ctx.mica_permutations(12345, max_perm)
+    assert np.array_equal(pv, pv2) and np.array_equal(nb, nb2)
+    pv3, nb3 = ctx.mica_permutations(777, max_perm)
+    assert not np.array_equal(nb, nb3)
+    # significant pairs use their whole budget: a column against its copy can only be matched by chance
+    if case == "dna":
+        c2 = dict(c); c2["codes"] = c["codes"].copy(); c2["codes"][:, 1] = c2["codes"][:, 0]
+        _setup(ctx, c2)
+        pv4, nb4 = ctx.mica_permutations(5, 200)
+        h = ctx.mica_sites()[0]
+        if h[0] > 0.8:
+            assert nb4[0] == 200 and pv4[0] <= 5.0 / 201

@@ -34,7 +34,9 @@ def dry_run(binary, cwd, *args):
 def write_fixture(tmp, name):
     g = H.golden(name)
     files = {"myoglobin": {"Myoglobin.aln.sel.mase": "mase", "Myo.dnd": "dnd", "comap.bpp": "options"},
-             "bacteria_ssu": {"Bacteria_SSU.40.phy": "phy", "Bacteria_SSU.ML.dnd": "dnd", "options.comap": "options"},
+             "bacteria_ssu": {"Bacteria_SSU.40.phy": "phy", "Bacteria_SSU.ML.dnd": "dnd", "options.comap": "options",
+                              "options_pbs.mica": "mica_pbs", "options_npbs.mica": "mica_npbs", "options_perm.mica": "mica_perm",
+                              "options_zscore.mica": "mica_zscore"},
              "srk": {"SRK.mase": "mase", "SRK.dnd": "dnd"}}[name]
     for fn, key in files.items():
         with open(os.path.join(tmp, fn), "wb") as f:

@@ -361,3 +361,64 @@ def test_mica_site_statistics_vs_numpy():
     assert abs(H[2] - O.site_entropy(codes[:, 2], 4, mask)) == 0
     e = np.mean([O.site_pair(codes[:, 4], codes[:, j], 4, mask)[0] for j in range(12) if j != 4])
     assert abs(avg[4] - e) < 1e-13
+
+
+def _philox(c, k0, k1):
+    c = list(c)
+    for _ in range(10):
+        p0, p1 = 0xD2511F53 * c[0], 0xCD9E8D57 * c[2]
+        c = [((p1 >> 32) ^ c[1] ^ k0) & 0xffffffff, p1 & 0xffffffff, ((p0 >> 32) ^ c[3] ^ k1) & 0xffffffff, p0 & 0xffffffff]
+        k0 = (k0 + 0x9E3779B9) & 0xffffffff; k1 = (k1 + 0xBB67AE85) & 0xffffffff
+    return c
+
+
+def _py_mi_test(c1, c2, A, mask, seed, pair, max_perm):
+    """miTest (Mica.cpp:92-118) in plain Python: the stopping rule and the shuffle stream the device and the oracle share
+    (inside-out Fisher-Yates of the original columns, see orc_mica_permutation_test)."""
+    full = (1 << A) - 1
+    def constant(c):
+        seen = {int(x) for x in c if (int(mask[x]) & full) != full}
+        return len(seen) <= 1
+    mi = O.site_pair(c1, c2, A, mask)[0]
+    if constant(c1) or constant(c2):
+        return 1.0, 0
+    T = len(c1)
+    count = i = 0
+    while count < 5 and i < max_perm:
+        words = []
+        for blk in range((2 * (T - 1) + 3) // 4):
+            words += _philox([pair & 0xffffffff, pair >> 32, i, blk], seed & 0xffffffff, seed >> 32)
+        d = 0
+        s = []
+        for src in (c1, c2):                                   # every shuffle starts from the original column
+            col = [int(src[0])] + [0] * (T - 1)
+            for k in range(1, T):
+                p = (words[d] * (k + 1)) >> 32
+                col[k] = col[p]; col[p] = int(src[k])
+                d += 1
+            assert sorted(col) == sorted(int(x) for x in src)
+            s.append(col)
+        rep = O.site_pair(np.array(s[0], np.uint8), np.array(s[1], np.uint8), A, mask)[0]
+        count += rep >= mi
+        i += 1
+    return (count + 1) / (i + 1), i
+
+
+def test_mica_permutation_test_vs_python():
+    """null.method = permutations: the oracle's miTest against a plain-Python restatement of the same stopping rule,
+    constant-column rule and Philox-driven Fisher-Yates shuffles; the shuffles keep the column's composition."""
+    rng = np.random.default_rng(8)
+    mask = np.array([1, 2, 4, 8, 15, 5], np.uint32)
+    codes = rng.choice(6, size=(18, 9), p=[0.3, 0.25, 0.2, 0.15, 0.06, 0.04]).astype(np.uint8)
+    codes[:, 4] = 3; codes[2, 4] = 4                           # constant but for an unknown character
+    codes[:, 6] = codes[:, 5]                                  # a perfectly coupled pair: needs its whole budget
+    pv, nb, closest = O.mica_permutations(codes, 4, mask, 99, 40)
+    ii, jj = np.triu_indices(9, 1)
+    for t in range(len(ii)):
+        epv, enb = _py_mi_test(codes[:, ii[t]], codes[:, jj[t]], 4, mask, 99, t, 40)
+        assert pv[t] == epv and nb[t] == enb, (t, pv[t], epv, nb[t], enb)
+    const = (ii == 4) | (jj == 4)
+    assert np.all(nb[const] == 0) and np.all(pv[const] == 1.0) and np.all(nb[~const] >= 5)
+    t56 = int(np.where((ii == 5) & (jj == 6))[0][0])
+    assert nb[t56] == 40 and pv[t56] < 0.2
+    assert np.all(pv[~const] == np.where(nb[~const] < 40, 6.0 / (nb[~const] + 1.0), pv[~const]))

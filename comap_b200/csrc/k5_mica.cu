@@ -34,7 +34,7 @@ struct LaneCol {
   __device__ __forceinline__ uint8_t& at(int t) const { return p[(t >> 2) * stride4 + (t & 3)]; }
 };
 
-// MI and joint entropy from the joint table (orc_site_pair's order: rows, then columns).  cell(x, y) returns the count.
+// MI and joint entropy from the joint table (orc_site_pair's order: rows, then columns).  freq(x, y) returns count / n.
 // Loops stay rolled: one copy of the two logarithms and three divisions per kernel, not A^2 of them (unrolled over its
 // 16 cells the permutation kernel's loop body was 70 KB of SASS and ncu put 27 % of its stalls on instruction fetches).
 // p1 / p2 are register arrays for A <= 4, read and written through compile-time-indexed selects.
@@ -54,18 +54,17 @@ __device__ __forceinline__ void put(double (&v)[A], int k, double val) {
     for (int i = 0; i < A; i++) v[i] = k == i ? val : v[i];
   } else v[k] = val;
 }
-template <int A, class Cell>
-__device__ __forceinline__ void table_stats(Cell cell, int T, double& mi, double& hj) {
+template <int A, class Freq>
+__device__ __forceinline__ void table_stats(Freq freq, double& mi, double& hj) {
   double p1[A], p2[A];
 #pragma unroll
   for (int x = 0; x < A; x++) { p1[x] = 0.; p2[x] = 0.; }
   double tot = 0.;
-  const double n = (double)T;
 #pragma unroll 1
   for (int x = 0; x < A; x++)
 #pragma unroll 1
     for (int y = 0; y < A; y++) {
-      const double pxy = cell(x, y) / n;
+      const double pxy = freq(x, y);
       tot += pxy;
       put<A>(p1, x, pick<A>(p1, x) + pxy);
       put<A>(p2, y, pick<A>(p2, y) + pxy);
@@ -81,7 +80,7 @@ __device__ __forceinline__ void table_stats(Cell cell, int T, double& mi, double
   for (int x = 0; x < A; x++)
 #pragma unroll 1
     for (int y = 0; y < A; y++) {
-      const double pxy = cell(x, y) / n / tot;
+      const double pxy = freq(x, y) / tot;
       if (pxy > 0.) { m += pxy * log(pxy / (pick<A>(p1, x) * pick<A>(p2, y))); h += pxy * log(pxy); }
     }
   mi = m; hj = -h;
@@ -107,7 +106,8 @@ __device__ __noinline__ void pair_stats_generic(const C1 c1, const C2 c2, int T,
             if ((m2 >> y) & 1u) cnt[x * A + y] += w;
     }
   }
-  table_stats<A>([&](int x, int y) { return cnt[x * A + y]; }, T, mi, hj);
+  const double n = (double)T;
+  table_stats<A>([&](int x, int y) { return cnt[x * A + y] / n; }, mi, hj);
 }
 
 // A <= 4 and no ambiguous character in either column (almost every pair of a real alignment, every pair of a simulated
@@ -132,16 +132,49 @@ __device__ __forceinline__ void pair_stats(const C1 c1, const C2 c2, int T, cons
       } else if (k1 && k2) ambiguous = true;
     }
     if (!ambiguous) {
+      const double n = (double)T;
       table_stats<A>([&](int x, int y) {
         unsigned long long r = w[0];
 #pragma unroll
         for (int i = 1; i < A; i++) r = x == i ? w[i] : r;
-        return (double)(unsigned)((r >> (16 * y)) & 0xffffull);
-      }, T, mi, hj);
+        return (double)(unsigned)((r >> (16 * y)) & 0xffffull) / n;
+      }, mi, hj);
       return;
     }
   }
   pair_stats_generic<A, C1, C2>(c1, c2, T, cmask, mi, hj);
+}
+
+// The permutation test's evaluation when neither column holds an ambiguous character: the private copies carry state
+// indices, so the histogram needs no mask table, and count / n comes from a table of the T + 1 possible quotients
+// (the same correctly rounded divisions, done once per CTA).  Same table_stats, same bits as pair_stats on the same table.
+template <int A>
+__device__ __forceinline__ void indexed_stats(const LaneCol s1, const LaneCol s2, int T, const double* __restrict__ quot, double& mi,
+                                              double& hj) {
+  if constexpr (A <= 4) {
+    unsigned long long w[A];
+#pragma unroll
+    for (int x = 0; x < A; x++) w[x] = 0ull;
+    for (int t = 0; t < T; t++) {
+      const uint32_t a = s1[t];
+      const unsigned long long inc = 1ull << (16 * s2[t]);
+#pragma unroll
+      for (int x = 0; x < A; x++)
+        if (a == (uint32_t)x) w[x] += inc;
+    }
+    table_stats<A>([&](int x, int y) {
+      unsigned long long r = w[0];
+#pragma unroll
+      for (int i = 1; i < A; i++) r = x == i ? w[i] : r;
+      return quot[(unsigned)((r >> (16 * y)) & 0xffffull)];
+    }, mi, hj);
+  } else {
+    uint16_t cnt[A * A];
+#pragma unroll 1
+    for (int k = 0; k < A * A; k++) cnt[k] = 0;
+    for (int t = 0; t < T; t++) cnt[s1[t] * A + s2[t]]++;
+    table_stats<A>([&](int x, int y) { return quot[cnt[x * A + y]]; }, mi, hj);
+  }
 }
 
 template <int A>
@@ -213,11 +246,13 @@ __global__ void __launch_bounds__(128) k5_listed(int T, int64_t n, const uint8_t
 // observed columns), a ballot of `rep >= mi` and a population count find the shuffle at which upstream's loop would
 // have stopped, and at most 31 evaluations per pair are wasted.  Every branch but the ambiguous-character path is
 // warp-uniform.
-// Shuffle q of pair idx: inside-out Fisher-Yates (s[0] = c[0]; for k = 1 .. T-1: j = floor(w (k + 1) / 2^32),
-// s[k] = s[j], s[j] = c[k]), the words w taken in order from Philox4x32-10 blocks with counter (idx lo, idx hi, q, block)
-// and key = seed, column 1's T - 1 draws first -- restated word for word in the oracle (orc_mica_permutation_test).
-// The observed and the shuffled MIs come from the same call site of pair_stats, so equal joint tables give equal bits
-// and `rep >= mi` sees the exact ties a discrete statistic produces.
+// Shuffle q of pair idx, column c: inside-out Fisher-Yates (s[0] = c[0]; for k = 1 .. T-1: j = floor(w (k + 1) / 2^32),
+// s[k] = s[j], s[j] = c[k]), the words w taken in order from Philox4x32-10 blocks with counter (idx lo, idx hi, q,
+// c << 24 | block) and key = seed.  When T <= 256 a word serves two draws: after the first, w <- w (k + 1) mod 2^32 (the
+// fraction the first draw left over) feeds the next k -- half the generator calls for a bias below 2^-16.  Restated
+// word for word in the oracle (orc_mica_permutation_test).
+// The observed and the shuffled MIs come from the same call site, so equal joint tables give equal bits and
+// `rep >= mi` sees the exact ties a discrete statistic produces.
 template <int A, int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS) k5_permutations(int T, int64_t S, int64_t n_pairs, int64_t n_pad,
                                                        const uint8_t* __restrict__ tips, const uint32_t* __restrict__ cmask,
@@ -226,16 +261,19 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k5_permutations(int T, int64_t 
   extern __shared__ __align__(16) unsigned char k5_smem[];
   const int nt = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, T4 = (T + 3) >> 2;
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(k5_smem);                     // [256]
-  uint8_t* o1 = k5_smem + 1024 + (size_t)warp * 8 * T4;                        // the warp's pair: [2][4 T4]
+  double* quot = reinterpret_cast<double*>(k5_smem + 1024);                    // [T + 1]: c / T
+  const size_t q_bytes = ((size_t)(T + 1) * 8 + 15) & ~(size_t)15;
+  uint8_t* o1 = k5_smem + 1024 + q_bytes + (size_t)warp * 8 * T4;              // the warp's pair: [2][4 T4]
   uint8_t* o2 = o1 + 4 * T4;
-  uint8_t* priv = k5_smem + 1024 + (size_t)(nt >> 5) * 8 * T4;                 // [2][T4][nt] words
+  uint8_t* priv = k5_smem + 1024 + q_bytes + (size_t)(nt >> 5) * 8 * T4;       // [2][T4][nt] words
   const LaneCol s1{priv + 4 * threadIdx.x, 4 * nt}, s2{priv + (size_t)4 * T4 * nt + 4 * threadIdx.x, 4 * nt};
   for (int k = threadIdx.x; k < 256; k += nt) s_mask[k] = cmask[k];
+  for (int k = threadIdx.x; k <= T; k += nt) quot[k] = (double)k / (double)T;
   __syncthreads();
   constexpr uint32_t full = A >= 32 ? 0xffffffffu : (1u << A) - 1u;
   constexpr unsigned ALL = 0xffffffffu;
   const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-  const int nd = 2 * (T - 1);
+  const bool two_per_word = T <= 256;            // ranges <= 256: the second draw of a word is biased by < 2^-16
   for (;;) {
     __syncwarp();
     unsigned long long got = 0;
@@ -250,21 +288,30 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k5_permutations(int T, int64_t 
     while (i > 0 && i * S - i * (i + 1) / 2 > idx) i--;
     while (i < S - 2 && (i + 1) * S - (i + 1) * (i + 2) / 2 <= idx) i++;
     const int64_t j = i + 1 + (idx - (i * S - i * (i + 1) / 2));
-    // SiteTools::isConstant(site, ignoreUnknown = true): the characters that are not fully unknown are all the same
+    // SiteTools::isConstant(site, ignoreUnknown = true): the characters that are not fully unknown are all the same.
+    // Resolved characters are kept as state indices; one ambiguous character sends the pair down the generic path.
     uint32_t lo1 = 0xffffffffu, hi1 = 0u, lo2 = 0xffffffffu, hi2 = 0u;
+    bool amb = false;
     for (int t = lane; t < T; t += 32) {
       const uint32_t a = tips[(size_t)t * n_pad + i], c = tips[(size_t)t * n_pad + j];
-      o1[t] = (uint8_t)a; o2[t] = (uint8_t)c;
-      if ((s_mask[a] & full) != full) { lo1 = min(lo1, a); hi1 = max(hi1, a); }
-      if ((s_mask[c] & full) != full) { lo2 = min(lo2, c); hi2 = max(hi2, c); }
+      const uint32_t ma = s_mask[a] & full, mc = s_mask[c] & full;
+      if (ma != full) { lo1 = min(lo1, a); hi1 = max(hi1, a); }
+      if (mc != full) { lo2 = min(lo2, c); hi2 = max(hi2, c); }
+      amb |= __popc(ma) != 1 || __popc(mc) != 1;
     }
     lo1 = __reduce_min_sync(ALL, lo1); hi1 = __reduce_max_sync(ALL, hi1);
     lo2 = __reduce_min_sync(ALL, lo2); hi2 = __reduce_max_sync(ALL, hi2);
-    __syncwarp();
+    amb = __any_sync(ALL, amb);
     if (lo1 >= hi1 || lo2 >= hi2) {              // one character at most (none: lo = 2^32 - 1 > hi = 0)
       if (lane == 0) { pvalue[idx] = 1.; nperm[idx] = 0; }
       continue;
     }
+    for (int t = lane; t < T; t += 32) {
+      const uint32_t a = tips[(size_t)t * n_pad + i], c = tips[(size_t)t * n_pad + j];
+      o1[t] = (uint8_t)(amb ? a : __ffs(s_mask[a] & full) - 1);
+      o2[t] = (uint8_t)(amb ? c : __ffs(s_mask[c] & full) - 1);
+    }
+    __syncwarp();
     int count = 0, shuffles = max_perm;
     double mi = 0.;
     for (int base = -1; base < max_perm; base += 32) {
@@ -272,25 +319,39 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k5_permutations(int T, int64_t 
       if (q < 0) {
         for (int t = 0; t < T; t++) { s1.at(t) = o1[t]; s2.at(t) = o2[t]; }
       } else {
-        s1.at(0) = o1[0]; s2.at(0) = o2[0];
-        int d = 0;
-        for (uint32_t blk = 0; d < nd; blk++) {
-          uint32_t c[4] = {(uint32_t)idx, (uint32_t)((uint64_t)idx >> 32), (uint32_t)q, blk};
-          philox4x32_10(c, k0, k1);
+#pragma unroll 1
+        for (int column = 0; column < 2; column++) {
+          const LaneCol& col = column ? s2 : s1;
+          const uint8_t* src = column ? o2 : o1;
+          col.at(0) = src[0];
+          int k = 1;
+          for (uint32_t blk = 0; k < T; blk++) {
+            uint32_t c[4] = {(uint32_t)idx, (uint32_t)((uint64_t)idx >> 32), (uint32_t)q, ((uint32_t)column << 24) | blk};
+            philox4x32_10(c, k0, k1);
 #pragma unroll
-          for (int u = 0; u < 4; u++, d++)
-            if (d < nd) {
-              const bool first = d < T - 1;
-              const LaneCol& col = first ? s1 : s2;
-              const int k = first ? d + 1 : d - (T - 1) + 1;
-              const int p = (int)__umulhi(c[u], (uint32_t)(k + 1));
-              col.at(k) = col.at(p);
-              col.at(p) = first ? o1[k] : o2[k];
+            for (int u = 0; u < 4; u++) {
+              uint32_t w = c[u];
+              if (k < T) {
+                const unsigned long long pr = (unsigned long long)w * (uint32_t)(k + 1);
+                const int p = (int)(pr >> 32);
+                col.at(k) = col.at(p);
+                col.at(p) = src[k];
+                w = (uint32_t)pr;                 // the fraction left over: uniform enough for one more small range
+                k++;
+              }
+              if (two_per_word && k < T) {
+                const int p = (int)__umulhi(w, (uint32_t)(k + 1));
+                col.at(k) = col.at(p);
+                col.at(p) = src[k];
+                k++;
+              }
             }
+          }
         }
       }
       double m, h;
-      pair_stats<A>(s1, s2, T, s_mask, m, h);
+      if (amb) pair_stats_generic<A>(s1, s2, T, s_mask, m, h);
+      else indexed_stats<A>(s1, s2, T, quot, m, h);
       if (base < 0) mi = __shfl_sync(ALL, m, 0);
       const unsigned hits = __ballot_sync(ALL, q >= 0 && q < max_perm && m >= mi);
       const int c = __popc(hits);
@@ -377,7 +438,8 @@ void launch_mica_permutations(int A, int T, int64_t S, int64_t n_pad, const uint
   if (T > 65535) fail("mica: %d sequences exceed the 16-bit cells of the joint table", T);
   const int64_t n_pairs = S * (S - 1) / 2;
   const size_t T4 = ((size_t)T + 3) / 4;
-  auto bytes = [&](int nt) { return 1024 + (size_t)(nt / 32) * 8 * T4 + 8 * T4 * nt; };  // masks | warps' pairs | private copies
+  const size_t q_bytes = ((size_t)(T + 1) * 8 + 15) & ~(size_t)15;
+  auto bytes = [&](int nt) { return 1024 + q_bytes + (size_t)(nt / 32) * 8 * T4 + 8 * T4 * nt; };  // masks | c / T | warps' pairs | private copies
   int nt = 128;
   while (nt > 32 && bytes(nt) > 64 * 1024) nt >>= 1;
   const size_t smem = bytes(nt);

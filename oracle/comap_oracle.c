@@ -1422,8 +1422,9 @@ void orc_mica_sites(int64_t S, int T, const uint8_t* codes, int A, int n_codes, 
  * one it started from, so here -- as on the device -- shuffle i is drawn from the ORIGINAL columns: the same
  * distribution of (count, i), and shuffles that do not depend on each other.  The shuffle used on both sides:
  * inside-out Fisher-Yates (s[0] = c[0]; for k = 1 .. T-1: j = floor(w (k + 1) / 2^32), s[k] = s[j], s[j] = c[k]), the
- * words w taken in order from Philox4x32-10 blocks with counter (pair lo, pair hi, i, block) and key = seed,
- * column 1's T - 1 draws first.  closest (nullable) = the smallest |rep - mi| met, so a test can tell a count that
+ * words w taken in order from Philox4x32-10 blocks with counter (pair lo, pair hi, i, column << 24 | block) and
+ * key = seed; when T <= 256 a word serves two draws, w <- w (k + 1) mod 2^32 in between (the fraction the first draw
+ * left over: bias below 2^-16).  closest (nullable) = the smallest |rep - mi| met, so a test can tell a count that
  * hinges on a rounding tie. */
 void orc_mica_permutation_test(int T, const uint8_t* c1, const uint8_t* c2, int A, int n_codes, const uint32_t* code_mask,
                                uint64_t seed, uint64_t pair, int max_perm, double* mi_out, double* pvalue, int* nperm,
@@ -1443,20 +1444,31 @@ void orc_mica_permutation_test(int T, const uint8_t* c1, const uint8_t* c2, int 
   uint8_t* s1 = malloc(2 * (size_t)T);
   uint8_t* s2 = s1 + T;
   int count = 0, i;
-  const int nd = 2 * (T - 1);
+  const int two_per_word = T <= 256;
   for (i = 0; count < 5 && i < max_perm; i++) {
-    int d = 0;
-    s1[0] = c1[0]; s2[0] = c2[0];
-    for (uint32_t blk = 0; d < nd; blk++) {
-      uint32_t c[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)i, blk};
-      philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
-      for (int u = 0; u < 4 && d < nd; u++, d++) {
-        const int first = d < T - 1;
-        uint8_t* col = first ? s1 : s2;
-        const uint8_t* src = first ? c1 : c2;
-        int k = first ? d + 1 : d - (T - 1) + 1;
-        int p = (int)(((uint64_t)c[u] * (uint64_t)(k + 1)) >> 32);
-        col[k] = col[p]; col[p] = src[k];
+    for (int column = 0; column < 2; column++) {
+      uint8_t* col = column ? s2 : s1;
+      const uint8_t* src = column ? c2 : c1;
+      col[0] = src[0];
+      int k = 1;
+      for (uint32_t blk = 0; k < T; blk++) {
+        uint32_t c[4] = {(uint32_t)pair, (uint32_t)(pair >> 32), (uint32_t)i, ((uint32_t)column << 24) | blk};
+        philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+        for (int u = 0; u < 4; u++) {
+          uint32_t w = c[u];
+          if (k < T) {
+            uint64_t pr = (uint64_t)w * (uint64_t)(k + 1);
+            int p = (int)(pr >> 32);
+            col[k] = col[p]; col[p] = src[k];
+            w = (uint32_t)pr;
+            k++;
+          }
+          if (two_per_word && k < T) {
+            int p = (int)(((uint64_t)w * (uint64_t)(k + 1)) >> 32);
+            col[k] = col[p]; col[p] = src[k];
+            k++;
+          }
+        }
       }
     }
     double rep;

@@ -99,6 +99,23 @@ def test_bacteria_rna_gtr_invariant(binary, tmp_path):
         assert "".join("ACGU"[c] for c in d["codes"][k]) == "".join(s[c - 1] for c in d["coords"])
 
 
+def test_mica_option_files_parse_as_shipped(binary, tmp_path):
+    """examples/RNA/BacteriaSSU/options_{pbs,npbs,perm,zscore}.mica: mica's option files select the same 760 sites as
+    CoMap's; the parametric bootstrap's file carries the GTR + Invariant(Gamma4) model, the others none; the dry run lists
+    the sequences in the alignment's own order (mica without a model keeps it)."""
+    write_fixture(str(tmp_path), "bacteria_ssu")
+    names, _ = H.read_phylip_sequential_extended(H.text(H.golden("bacteria_ssu")["phy"]))
+    ref = decode(dry_run(binary, str(tmp_path), "param=options.comap")[1])
+    for opt in ("options_pbs.mica", "options_npbs.mica", "options_perm.mica", "options_zscore.mica"):
+        p, out = dry_run(binary, str(tmp_path), "param=" + opt)
+        assert p.returncode == 0, p.stdout
+        d = decode(out)
+        assert d["codes"].shape == (40, 760) and np.array_equal(d["coords"], ref["coords"])
+        assert np.array_equal(d["codes"], ref["codes"]) and out["sequences"] == names
+        if opt == "options_pbs.mica":
+            assert np.allclose(d["Q"], ref["Q"]) and np.allclose(d["rates"], ref["rates"]) and len(d["rates"]) == 5
+
+
 def test_empirical_model_from_a_paml_file(binary, tmp_path):
     """model = Empirical(file=...) (Bio++ syntax) reads a PAML exchangeability file: the bundled JTT92
     table through that route equals model = JTT92."""

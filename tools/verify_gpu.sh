@@ -6,6 +6,4 @@ timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')
 timeout 600 python bench.py > gpurun_out/final_bench.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/final_bench.log | cut -c1-600
 timeout 600 python bench.py --impl reference > gpurun_out/final_bench_ref.log 2>&1; echo "ref rc=$?"; tail -1 gpurun_out/final_bench_ref.log | cut -c1-400
 timeout 300 python bench.py --workload mica > gpurun_out/final_mica.log 2>&1; echo "mica rc=$?"; tail -1 gpurun_out/final_mica.log | cut -c1-300; tail -1 gpurun_out/final_mica.log | grep -o '"roofline.*' | cut -c1-900
-for tool in memcheck racecheck; do
-  timeout 400 compute-sanitizer --tool $tool python tools/k5_sanitize.py > gpurun_out/final_k5_$tool.log 2>&1; echo "$tool rc=$?"; tail -4 gpurun_out/final_k5_$tool.log
-done
+# compute-sanitizer is closed on this pool (tools/k5_sanitize.py is the small pass it would run over mica's kernels)

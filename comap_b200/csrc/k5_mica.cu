@@ -149,25 +149,59 @@ __device__ __forceinline__ void pair_stats(const C1 c1, const C2 c2, int T, cons
 // indices, so the histogram needs no mask table, and count / n comes from a table of the T + 1 possible quotients
 // (the same correctly rounded divisions, done once per CTA).  Same table_stats, same bits as pair_stats on the same table.
 template <int A>
+__device__ __forceinline__ void packed_histogram(const LaneCol s1, const LaneCol s2, int T, unsigned long long (&w)[A]) {
+#pragma unroll
+  for (int x = 0; x < A; x++) w[x] = 0ull;
+  for (int t = 0; t < T; t++) {
+    const uint32_t a = s1[t];
+    const unsigned long long inc = 1ull << (16 * s2[t]);
+#pragma unroll
+    for (int x = 0; x < A; x++)
+      if (a == (uint32_t)x) w[x] += inc;
+  }
+}
+template <int A>
+__device__ __forceinline__ unsigned packed_cell(const unsigned long long (&w)[A], int x, int y) {
+  unsigned long long r = w[0];
+#pragma unroll
+  for (int i = 1; i < A; i++) r = x == i ? w[i] : r;
+  return (unsigned)((r >> (16 * y)) & 0xffffull);
+}
+// one copy per kernel (not inlined): the observed table and every shuffled one go through the very same instructions
+template <int A>
+struct Packed { unsigned long long w[A]; };      // by value: the caller's words stay in registers
+template <int A>
+__device__ __noinline__ double2 packed_stats_call(const Packed<A> p, const double* __restrict__ quot) {
+  double2 r;
+  table_stats<A>([&](int x, int y) { return quot[packed_cell<A>(p.w, x, y)]; }, r.x, r.y);
+  return r;
+}
+template <int A>
+__device__ __forceinline__ void packed_stats(const unsigned long long (&w)[A], const double* __restrict__ quot, double& mi, double& hj) {
+  Packed<A> p;
+#pragma unroll
+  for (int x = 0; x < A; x++) p.w[x] = w[x];
+  const double2 r = packed_stats_call<A>(p, quot);
+  mi = r.x; hj = r.y;
+}
+// sum of (c / T) ln(c / T) over the cells, from a table: MI differs from it by a term the shuffles cannot change (the
+// marginal entropies), so it orders shuffled and observed tables as MI does in real arithmetic
+template <int A>
+__device__ __forceinline__ double packed_filter(const unsigned long long (&w)[A], const double* __restrict__ plogp) {
+  double f = 0.;
+#pragma unroll 1
+  for (int x = 0; x < A; x++)
+#pragma unroll
+    for (int y = 0; y < A; y++) f += plogp[packed_cell<A>(w, x, y)];
+  return f;
+}
+template <int A>
 __device__ __forceinline__ void indexed_stats(const LaneCol s1, const LaneCol s2, int T, const double* __restrict__ quot, double& mi,
                                               double& hj) {
   if constexpr (A <= 4) {
     unsigned long long w[A];
-#pragma unroll
-    for (int x = 0; x < A; x++) w[x] = 0ull;
-    for (int t = 0; t < T; t++) {
-      const uint32_t a = s1[t];
-      const unsigned long long inc = 1ull << (16 * s2[t]);
-#pragma unroll
-      for (int x = 0; x < A; x++)
-        if (a == (uint32_t)x) w[x] += inc;
-    }
-    table_stats<A>([&](int x, int y) {
-      unsigned long long r = w[0];
-#pragma unroll
-      for (int i = 1; i < A; i++) r = x == i ? w[i] : r;
-      return quot[(unsigned)((r >> (16 * y)) & 0xffffull)];
-    }, mi, hj);
+    packed_histogram<A>(s1, s2, T, w);
+    packed_stats<A>(w, quot, mi, hj);
   } else {
     uint16_t cnt[A * A];
 #pragma unroll 1
@@ -256,19 +290,25 @@ __global__ void __launch_bounds__(128) k5_listed(int T, int64_t n, const uint8_t
 template <int A, int MIN_CTAS>
 __global__ void __launch_bounds__(128, MIN_CTAS) k5_permutations(int T, int64_t S, int64_t n_pairs, int64_t n_pad,
                                                        const uint8_t* __restrict__ tips, const uint32_t* __restrict__ cmask,
-                                                       uint64_t seed, int max_perm, unsigned long long* __restrict__ next,
-                                                       double* __restrict__ pvalue, int32_t* __restrict__ nperm) {
+                                                       uint64_t seed, int max_perm, int use_filter,
+                                                       unsigned long long* __restrict__ next, double* __restrict__ pvalue,
+                                                       int32_t* __restrict__ nperm) {
   extern __shared__ __align__(16) unsigned char k5_smem[];
   const int nt = blockDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5, T4 = (T + 3) >> 2;
   uint32_t* s_mask = reinterpret_cast<uint32_t*>(k5_smem);                     // [256]
   double* quot = reinterpret_cast<double*>(k5_smem + 1024);                    // [T + 1]: c / T
-  const size_t q_bytes = ((size_t)(T + 1) * 8 + 15) & ~(size_t)15;
+  double* plogp = quot + (T + 1);                                              // [T + 1]: (c / T) ln(c / T)
+  const size_t q_bytes = ((size_t)(T + 1) * 16 + 15) & ~(size_t)15;
   uint8_t* o1 = k5_smem + 1024 + q_bytes + (size_t)warp * 8 * T4;              // the warp's pair: [2][4 T4]
   uint8_t* o2 = o1 + 4 * T4;
   uint8_t* priv = k5_smem + 1024 + q_bytes + (size_t)(nt >> 5) * 8 * T4;       // [2][T4][nt] words
   const LaneCol s1{priv + 4 * threadIdx.x, 4 * nt}, s2{priv + (size_t)4 * T4 * nt + 4 * threadIdx.x, 4 * nt};
   for (int k = threadIdx.x; k < 256; k += nt) s_mask[k] = cmask[k];
-  for (int k = threadIdx.x; k <= T; k += nt) quot[k] = (double)k / (double)T;
+  for (int k = threadIdx.x; k <= T; k += nt) {
+    const double f = (double)k / (double)T;
+    quot[k] = f;
+    plogp[k] = k ? f * log(f) : 0.;
+  }
   __syncthreads();
   constexpr uint32_t full = A >= 32 ? 0xffffffffu : (1u << A) - 1u;
   constexpr unsigned ALL = 0xffffffffu;
@@ -313,7 +353,9 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k5_permutations(int T, int64_t 
     }
     __syncwarp();
     int count = 0, shuffles = max_perm;
-    double mi = 0.;
+    double mi = 0., f_obs = 0.;
+    unsigned long long w_obs[A <= 4 ? A : 1] = {};
+    bool have_mi = false;
     for (int base = -1; base < max_perm; base += 32) {
       const int q = base + lane;
       if (q < 0) {
@@ -349,11 +391,42 @@ __global__ void __launch_bounds__(128, MIN_CTAS) k5_permutations(int T, int64_t 
           }
         }
       }
-      double m, h;
-      if (amb) pair_stats_generic<A>(s1, s2, T, s_mask, m, h);
-      else indexed_stats<A>(s1, s2, T, quot, m, h);
-      if (base < 0) mi = __shfl_sync(ALL, m, 0);
-      const unsigned hits = __ballot_sync(ALL, q >= 0 && q < max_perm && m >= mi);
+      const bool valid = q >= 0 && q < max_perm;
+      bool hit;
+      bool filtered = false;
+      if constexpr (A <= 4) {
+        if (!amb && use_filter) {
+          // The comparison `rep >= mi` is all a shuffle contributes, and in real arithmetic it is the comparison of the
+          // two tables' sums of p ln p (the marginals do not move).  Those sums come from a table, error < 1e-14; only
+          // when a shuffled sum lies within 1e-12 of the observed one -- a tie, which the reference's formula settles by
+          // its own rounding -- does the warp evaluate that formula, for the observed table (once) and the shuffled ones.
+          filtered = true;
+          unsigned long long w[A];
+          packed_histogram<A>(s1, s2, T, w);
+          const double f = packed_filter<A>(w, plogp);
+          if (base < 0) {
+            f_obs = __shfl_sync(ALL, f, 0);
+#pragma unroll
+            for (int x = 0; x < A; x++) w_obs[x] = __shfl_sync(ALL, w[x], 0);
+            have_mi = false;
+          }
+          const double d = f - f_obs;
+          if (__any_sync(ALL, valid && fabs(d) <= 1e-12)) {
+            double m, h;
+            if (!have_mi) { packed_stats<A>(w_obs, quot, mi, h); have_mi = true; }
+            packed_stats<A>(w, quot, m, h);
+            hit = valid && m >= mi;
+          } else hit = valid && d > 0.;
+        }
+      }
+      if (!filtered) {
+        double m, h;
+        if (amb) pair_stats_generic<A>(s1, s2, T, s_mask, m, h);
+        else indexed_stats<A>(s1, s2, T, quot, m, h);
+        if (base < 0) mi = __shfl_sync(ALL, m, 0);
+        hit = valid && m >= mi;
+      }
+      const unsigned hits = __ballot_sync(ALL, hit);
       const int c = __popc(hits);
       if (count + c >= 5) {                      // the shuffle that brought the count to 5
         unsigned r = hits;
@@ -438,14 +511,15 @@ void launch_mica_permutations(int A, int T, int64_t S, int64_t n_pad, const uint
   if (T > 65535) fail("mica: %d sequences exceed the 16-bit cells of the joint table", T);
   const int64_t n_pairs = S * (S - 1) / 2;
   const size_t T4 = ((size_t)T + 3) / 4;
-  const size_t q_bytes = ((size_t)(T + 1) * 8 + 15) & ~(size_t)15;
-  auto bytes = [&](int nt) { return 1024 + q_bytes + (size_t)(nt / 32) * 8 * T4 + 8 * T4 * nt; };  // masks | c / T | warps' pairs | private copies
+  const size_t q_bytes = ((size_t)(T + 1) * 16 + 15) & ~(size_t)15;
+  auto bytes = [&](int nt) { return 1024 + q_bytes + (size_t)(nt / 32) * 8 * T4 + 8 * T4 * nt; };  // masks | c / T, (c / T) ln(c / T) | warps' pairs | private copies
   int nt = 128;
   while (nt > 32 && bytes(nt) > 64 * 1024) nt >>= 1;
   const size_t smem = bytes(nt);
   if (smem > 200 * 1024) fail("mica permutations: %d sequences exceed the shared memory of a one-warp CTA", T);
-  // registers per thread: 64 (8 CTAs of 128 per SM, a few spilled words), 80 (6) or 96 (5); CMB_K5_CTAS picks one for A/B runs
-  static const int want = [] { const char* e = getenv("CMB_K5_CTAS"); return e ? atoi(e) : 8; }();
+  // register budget: 5 CTAs of 128 per SM (95 registers, nothing spilled; default), 6 (80) or 8 (64, ~300 B spilled);
+  // CMB_K5_CTAS picks one for A/B runs -- before the interval filter the three measured the same
+  static const int want = [] { const char* e = getenv("CMB_K5_CTAS"); return e ? atoi(e) : 5; }();
   auto kernel = A == 4 ? (want <= 5 ? k5_permutations<4, 5> : want <= 6 ? k5_permutations<4, 6> : k5_permutations<4, 8>)
                 : A == 20 ? k5_permutations<20, 5> : nullptr;
   if (!kernel) fail("mica kernels are built for A = 4 and A = 20 (got %d)", A);
@@ -458,7 +532,9 @@ void launch_mica_permutations(int A, int T, int64_t S, int64_t n_pad, const uint
   // persistent warps, one wave; pairs are handed out by a counter: no more warps than pairs
   const int64_t ctas = std::min<int64_t>((int64_t)sms * per_sm, (n_pairs + nt / 32 - 1) / (nt / 32));
   CMB_CUDA(cudaMemsetAsync(next, 0, sizeof(unsigned long long), st));
-  kernel<<<(unsigned)ctas, nt, smem, st>>>(T, S, n_pairs, n_pad, tips, cmask, seed, max_perm, next, pvalue, nperm);
+  // CMB_K5_FILTER=0: every shuffle through the reference's formula (same table; for A/B runs and tests)
+  static const int use_filter = [] { const char* e = getenv("CMB_K5_FILTER"); return e ? atoi(e) : 1; }();
+  kernel<<<(unsigned)ctas, nt, smem, st>>>(T, S, n_pairs, n_pad, tips, cmask, seed, max_perm, use_filter, next, pvalue, nperm);
   CMB_CUDA(cudaGetLastError());
 }
 void launch_mica_average(int64_t S, const double* mi, double* avg, cudaStream_t st) {

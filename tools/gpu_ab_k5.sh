@@ -1,19 +1,17 @@
-# mica's GPU tests, the register-budget A/B of k5_permutations, then one ncu capture of the default
+# mica's GPU tests, then the interval filter of k5_permutations on / off: same tables, kernel time of each
 cd $GRAFT_REPO_ROOT
 O=gpurun_out
-T=${1:-r2v}
+T=${1:-r2w}
 timeout 600 python -m pytest tests/test_gpu_mica.py -x -q -s > $O/${T}_mica_tests.log 2>&1; echo "mica rc=$?"; tail -4 $O/${T}_mica_tests.log
-timeout 600 python -m pytest tests/test_gpu_host.py -x -q -k "mica" > $O/${T}_mica_cli_tests.log 2>&1; echo "mica cli rc=$?"; tail -3 $O/${T}_mica_cli_tests.log
-for c in 5 8; do
-  CMB_K5_CTAS=$c timeout 300 python bench.py --workload mica --no-cpu-baseline --steps 5 > $O/${T}_mica_ctas$c.log 2>&1
-  echo "CTAS=$c $(tail -1 $O/${T}_mica_ctas$c.log | grep -o '"kernel_ms_per_step.*')"
+CMB_K5_FILTER=1 python tools/k5_filter_check.py /tmp/f1.npz > $O/${T}_filter_check.log 2>&1
+CMB_K5_FILTER=0 python tools/k5_filter_check.py /tmp/f0.npz >> $O/${T}_filter_check.log 2>&1
+python -c "
+import numpy as np
+a, b = np.load('/tmp/f1.npz'), np.load('/tmp/f0.npz')
+for k in a.files: print(k, 'identical' if np.array_equal(a[k], b[k]) else 'DIFFERENT: %d rows' % int((a[k] != b[k]).sum()))
+" >> $O/${T}_filter_check.log 2>&1
+cat $O/${T}_filter_check.log
+for f in 1 0; do
+  CMB_K5_FILTER=$f timeout 300 python bench.py --workload mica --no-cpu-baseline --steps 5 > $O/${T}_mica_filter$f.log 2>&1
+  echo "FILTER=$f $(tail -1 $O/${T}_mica_filter$f.log | grep -o '"kernel_ms_per_step.*')"
 done
-SS="python bench.py --workload mica --steps 1 --warmup 3 --no-cpu-baseline"
-k=k5_permutations
-ncu --set full --clock-control none --import-source on -k regex:$k -s 3 -c 1 -f -o $O/${T}_$k $SS > $O/${T}_ncu_$k.log 2>&1
-python tools/ncu_summary.py kernel $O/${T}_$k.ncu-rep $O/${T}_$k.txt
-ncu -i $O/${T}_$k.ncu-rep --page source --csv --print-source sass > /tmp/${T}_src.csv 2>/dev/null
-python tools/ncu_src.py /tmp/${T}_src.csv 14 >> $O/${T}_$k.txt 2>&1
-ncu -i $O/${T}_$k.ncu-rep --page details 2>/dev/null | grep -A3 "Warp Cycles Per Issued\|Executed Ipc\|Branch Efficiency\|Avg. Active Threads" | head -40 >> $O/${T}_$k.txt
-rm -f $O/${T}_$k.ncu-rep
-head -30 $O/${T}_$k.txt | cut -c1-110; grep "stall reasons\|Active Threads\|Ipc Active" $O/${T}_$k.txt

@@ -8,9 +8,11 @@
 // taken from it; sums run rows then columns, as restated in the oracle (orc_site_pair).
 //
 // Layout: the alignment is the tip matrix K1 reads, [T][S_pad] codes with the 256-entry code -> state-mask table.
-// One thread per pair keeps the A x A joint table in local memory (A = 4: 16 doubles, A = 20: 400) -- T byte loads
-// per column (coalesced over the 32 pairs of a warp, which share site i and walk consecutive sites j), A^2 updates
-// and A^2 logarithms per pair.  Not a tiled kernel: the work per pair is a histogram, not a dot product.
+// k5_pairs / k5_listed / k5_entropy: one thread per pair (site); T byte loads per column (coalesced over the 32 pairs of
+// a warp, which share site i and walk consecutive sites j), then the table's A^2 cells.  For A <= 4 and no ambiguous
+// character the joint table sits in packed registers, otherwise in local memory (pair_stats below).  Not a tiled
+// kernel: the work per pair is a histogram, not a dot product.
+// k5_permutations (null.method = permutations, up to 1000 evaluations per pair): one warp per pair, see there.
 #include "kernels.h"
 #include <algorithm>
 #include <cstdlib>
@@ -279,7 +281,8 @@ __global__ void __launch_bounds__(128) k5_listed(int T, int64_t n, const uint8_t
 // One WARP per pair instead: lane l of trip k scores shuffle 32 k + l - 1 (lane 0 of the first trip scores the
 // observed columns), a ballot of `rep >= mi` and a population count find the shuffle at which upstream's loop would
 // have stopped, and at most 31 evaluations per pair are wasted.  Every branch but the ambiguous-character path is
-// warp-uniform.
+// warp-uniform: 16.4 ms; 10.4 with rolled table loops, state indices in the private copies, a quotient table and two
+// draws per generator word; 6.8 with the interval filter in front of the reference's formula (profiles/r2w_k5_history.txt).
 // Shuffle q of pair idx, column c: inside-out Fisher-Yates (s[0] = c[0]; for k = 1 .. T-1: j = floor(w (k + 1) / 2^32),
 // s[k] = s[j], s[j] = c[k]), the words w taken in order from Philox4x32-10 blocks with counter (idx lo, idx hi, q,
 // c << 24 | block) and key = seed.  When T <= 256 a word serves two draws: after the first, w <- w (k + 1) mod 2^32 (the

@@ -75,3 +75,13 @@ def test_cpu_sample_keeps_the_composition_of_the_step():
     assert abs(r["sample_fraction"] - (60 * 59 // 2 + round(1000 * (60 * 59 / 2) / (300 * 299 / 2))) / total) < 1e-12  # 1770 + 39 pairs
     assert r["value"] == r["sample_pairs"] / r["sample_seconds"] and r["full_step_seconds"] == total / r["value"]
     assert 0.2 < r["extrapolated_value"] / r["value"] < 5.0
+
+
+def test_profile_metric_reads_the_committed_k5_summary():
+    """bench.py --workload mica takes the permutation kernel's warp-instruction count and DRAM bytes from the newest
+    committed ncu summary: the parser finds them, and they describe an issue-bound kernel that moves no memory."""
+    inst, src = bench.profile_metric("r2*_k5_permutations.txt", "smsp__inst_executed.sum")
+    assert src and src.startswith("profiles/") and inst > 1e9
+    dr = bench.profile_dram_bytes("r2*_k5_permutations.txt")
+    assert dr and dr["dram_bytes"] < 1e6 and dr["ms"] > 1.0
+    assert bench.profile_metric("no_such_kernel_*.txt", "smsp__inst_executed.sum") == (None, None)

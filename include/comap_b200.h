@@ -320,7 +320,8 @@ int cmb_mica_pair_list(cmb_ctx* ctx, int64_t n, const int32_t* site1, const int3
 /* null.method = permutations (miTest, Mica.cpp:92-118; table columns Perm.p.value / Perm.nb, :666-667): for every pair, in
  * the order of cmb_mica_pairs, both columns are shuffled until 5 shuffled MIs reach the observed one or max_permutations
  * were drawn; pvalue = (count + 1) / (shuffles + 1), nperm = shuffles; 1 and 0 when a column is constant.  Upstream's
- * generator is unseeded: the shuffles here are a function of (seed, pair, shuffle number) only. */
+ * generator is unseeded and its copies are reshuffled in place; here every shuffle is drawn from the original columns
+ * (the same distribution) and is a function of (seed, pair, shuffle number) only -- see DESIGN.md s4 K5. */
 int cmb_mica_permutations(cmb_ctx* ctx, uint64_t seed, int32_t max_permutations, int64_t capacity, double* pvalue, int32_t* nperm,
                           int64_t* n_rows);
 /* null.method = parametric-bootstrap (Mica.cpp:470-545): per outer replicate two simulated alignments of rep_ram sites,
